@@ -1,0 +1,399 @@
+"""baby_shark_b200 -- B200-native implicit-modelling path of baby_shark behind the C ABI in include/bshark.h.
+
+This module is the Python harness over libbshark_cuda.so (ctypes; no torch types cross the boundary). The
+classes mirror the reference's `voxel::prelude` (src/voxel/prelude.rs:1-4) and `remeshing::voxel`
+(src/remeshing/voxel.rs:10-95): same names, builder-style setters, `None` where the reference returns `None`,
+`ReferencePanic` where the reference panics. There is no CPU fallback: without the built library or without a
+B200 the constructors raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbshark_cuda.so")
+
+BS_OK, BS_ERR_EMPTY_MESH, BS_ERR_CUDA, BS_ERR_INVALID, BS_ERR_REFERENCE_PANICS, BS_ERR_RANGE, BS_ERR_NO_DEVICE, \
+    BS_ERR_UNSUPPORTED = range(8)
+_STATUS_NAMES = ["BS_OK", "BS_ERR_EMPTY_MESH", "BS_ERR_CUDA", "BS_ERR_INVALID", "BS_ERR_REFERENCE_PANICS",
+                 "BS_ERR_RANGE", "BS_ERR_NO_DEVICE", "BS_ERR_UNSUPPORTED"]
+
+# every symbol include/bshark.h declares (tests check the built library exports all of them)
+EXPORTS = [
+    "bs_context_create", "bs_context_destroy", "bs_last_error", "bs_context_device", "bs_context_stream",
+    "bs_mesh_to_volume", "bs_mesh_to_volume_device", "bs_mesh_to_volume_sharded",
+    "bs_volume_from_voxels", "bs_volume_empty", "bs_volume_sphere", "bs_volume_cuboid", "bs_volume_iwp",
+    "bs_volume_clone", "bs_volume_free", "bs_volume_voxel_size",
+    "bs_volume_union", "bs_volume_subtract", "bs_volume_intersect", "bs_volume_offset",
+    "bs_mesh_mc", "bs_mesh_dc", "bs_mesh_mc_device", "bs_mesh_dc_device", "bs_buffer_free",
+    "bs_volume_download", "bs_volume_counts", "bs_context_last_stats",
+]
+
+
+class BsharkError(RuntimeError):
+    def __init__(self, status, message=""):
+        self.status = status
+        name = _STATUS_NAMES[status] if 0 <= status < len(_STATUS_NAMES) else str(status)
+        super().__init__("%s%s" % (name, (": " + message) if message else ""))
+
+
+class ReferencePanic(BsharkError):
+    """The reference panics on this input (todo!() / unwrap() / unreachable!())."""
+
+
+_lib = None
+
+
+def load_library(path=None):
+    """Load libbshark_cuda.so (no compute). Raises if the CUDA extension has not been built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise ImportError("%s is missing: build it with `make -C baby_shark_b200/csrc` (there is no CPU fallback)" % path)
+    L = C.CDLL(path)
+    fp, vp = C.POINTER(C.c_float), C.c_void_p
+    pvp = C.POINTER(C.c_void_p)
+    sz = C.c_size_t
+    psz = C.POINTER(sz)
+    sigs = {
+        "bs_context_create": (C.c_int, [C.c_int, pvp]),
+        "bs_context_destroy": (None, [vp]),
+        "bs_last_error": (C.c_char_p, [vp]),
+        "bs_context_device": (C.c_int, [vp]),
+        "bs_context_stream": (vp, [vp]),
+        "bs_mesh_to_volume": (C.c_int, [vp, fp, sz, C.c_float, C.c_int64, pvp]),
+        "bs_mesh_to_volume_device": (C.c_int, [vp, vp, sz, C.c_float, C.c_int64, pvp]),
+        "bs_mesh_to_volume_sharded": (C.c_int, [vp, vp, sz, C.c_float, C.c_int64, C.c_int, C.c_int, pvp]),
+        "bs_volume_from_voxels": (C.c_int, [vp, C.POINTER(C.c_int32), fp, sz, C.c_float, pvp]),
+        "bs_volume_empty": (C.c_int, [vp, C.c_float, pvp]),
+        "bs_volume_sphere": (C.c_int, [vp, C.c_float, C.c_float, fp, pvp]),
+        "bs_volume_cuboid": (C.c_int, [vp, C.c_float, fp, fp, pvp]),
+        "bs_volume_iwp": (C.c_int, [vp, C.c_float, fp, fp, C.c_float, pvp]),
+        "bs_volume_clone": (C.c_int, [vp, pvp]),
+        "bs_volume_free": (None, [vp]),
+        "bs_volume_voxel_size": (C.c_float, [vp]),
+        "bs_volume_union": (C.c_int, [vp, vp, pvp]),
+        "bs_volume_subtract": (C.c_int, [vp, vp, pvp]),
+        "bs_volume_intersect": (C.c_int, [vp, vp, pvp]),
+        "bs_volume_offset": (C.c_int, [vp, C.c_float, pvp]),
+        "bs_mesh_mc": (C.c_int, [vp, C.c_float, C.POINTER(fp), psz]),
+        "bs_mesh_dc": (C.c_int, [vp, C.c_float, C.POINTER(fp), psz]),
+        "bs_mesh_mc_device": (C.c_int, [vp, C.c_float, pvp, psz]),
+        "bs_mesh_dc_device": (C.c_int, [vp, C.c_float, pvp, psz]),
+        "bs_buffer_free": (None, [vp]),
+        "bs_volume_download": (C.c_int, [vp, C.POINTER(C.POINTER(C.c_int32)), C.POINTER(fp), C.POINTER(C.POINTER(C.c_uint64)), psz,
+                                         C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.POINTER(C.c_int32)), C.POINTER(fp), psz]),
+        "bs_volume_counts": (C.c_int, [vp, psz, psz, psz, psz]),
+        "bs_context_last_stats": (sz, [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_double), sz]),
+    }
+    for name, (res, args) in sigs.items():
+        f = getattr(L, name)
+        f.restype, f.argtypes = res, args
+    _lib = L
+    return L
+
+
+class Context:
+    """One CUDA device + stream + memory pool (bs_context). `Context.default()` is the process-wide one."""
+    _default = None
+
+    def __init__(self, device=-1):
+        L = load_library()
+        h = C.c_void_p()
+        st = L.bs_context_create(device, C.byref(h))
+        if st != BS_OK:
+            raise BsharkError(st, "bs_context_create(device=%d): a B200 (sm_100) device is required; there is no CPU fallback" % device)
+        self._h = h
+
+    @classmethod
+    def default(cls):
+        if cls._default is None:
+            cls._default = Context()
+        return cls._default
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().bs_context_destroy(self._h)
+            self._h = None
+
+    def last_error(self):
+        return load_library().bs_last_error(self._h).decode()
+
+    @property
+    def device(self):
+        return load_library().bs_context_device(self._h)
+
+    @property
+    def stream(self):
+        return load_library().bs_context_stream(self._h)
+
+    def last_stats(self):
+        names = (C.c_char_p * 64)()
+        vals = (C.c_double * 64)()
+        n = load_library().bs_context_last_stats(self._h, names, vals, 64)
+        return {names[i].decode(): vals[i] for i in range(n)}
+
+    def check(self, st):
+        if st == BS_OK:
+            return
+        if st == BS_ERR_REFERENCE_PANICS:
+            raise ReferencePanic(st, self.last_error())
+        raise BsharkError(st, self.last_error())
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _as_triangles(mesh):
+    """`Triangles::triangles()` (src/mesh/traits.rs:4-8) flattened: anything array-like of shape [n,9] / [n,3,3] /
+    [3n,3] (a vertex soup, 3 consecutive vertices per triangle like PolygonSoup)."""
+    a = _f32(getattr(mesh, "vertices", mesh))
+    return a.reshape(-1, 9)
+
+
+class Volume:
+    """`voxel::volume::Volume` (src/voxel/volume/mod.rs:10-108) living on the device."""
+
+    def __init__(self, handle, ctx):
+        self._h, self._ctx = handle, ctx
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            load_library().bs_volume_free(self._h)
+            self._h = None
+
+    @staticmethod
+    def with_voxel_size(voxel_size, ctx=None):
+        ctx = ctx or Context.default()
+        h = C.c_void_p()
+        ctx.check(load_library().bs_volume_empty(ctx._h, voxel_size, C.byref(h)))
+        return Volume(h, ctx)
+
+    @staticmethod
+    def from_fn(voxel_size, min, max, narrow_band_width, func, ctx=None):
+        """volume/mod.rs:40-72. `func` maps an [m,3] f32 array of grid points to m f32 values (vectorised closure);
+        it is evaluated on the host exactly as the reference does and only the kept voxels cross the boundary."""
+        ctx = ctx or Context.default()
+        vs = np.float32(voxel_size)
+        nbw = np.float32(narrow_band_width + 1) * vs
+        lo = np.floor(_f32(min) / vs).astype(np.int64)
+        hi = np.ceil(_f32(max) / vs).astype(np.int64)
+        xs, ys, zs = [np.arange(lo[d], hi[d] + 1, dtype=np.int64) for d in range(3)]
+        ijk = np.stack(np.meshgrid(xs, ys, zs, indexing="ij"), -1).reshape(-1, 3)
+        pts = ijk.astype(np.float32) * vs
+        val = _f32(func(pts))
+        keep = ~(np.abs(val) > nbw)
+        ijk32 = np.ascontiguousarray(ijk[keep], np.int32)
+        val = _f32(val[keep])
+        h = C.c_void_p()
+        ctx.check(load_library().bs_volume_from_voxels(ctx._h, ijk32.ctypes.data_as(C.POINTER(C.c_int32)), _fp(val), ijk32.shape[0],
+                                                       voxel_size, C.byref(h)))
+        return Volume(h, ctx)
+
+    def voxel_size(self):
+        return load_library().bs_volume_voxel_size(self._h)
+
+    def clone(self):
+        h = C.c_void_p()
+        self._ctx.check(load_library().bs_volume_clone(self._h, C.byref(h)))
+        return Volume(h, self._ctx)
+
+    def _binary(self, other, name):
+        h = C.c_void_p()
+        a, b = self._h, other._h
+        self._h = other._h = None  # consumed (Rust move semantics)
+        self._ctx.check(getattr(load_library(), "bs_volume_" + name)(a, b, C.byref(h)))
+        return Volume(h, self._ctx)
+
+    def union(self, other):
+        return self._binary(other, "union")
+
+    def subtract(self, other):
+        return self._binary(other, "subtract")
+
+    def intersect(self, other):
+        return self._binary(other, "intersect")
+
+    def offset(self, distance):
+        h = C.c_void_p()
+        a = self._h
+        self._h = None
+        self._ctx.check(load_library().bs_volume_offset(a, distance, C.byref(h)))
+        return Volume(h, self._ctx)
+
+    # parity / debug -------------------------------------------------------------------------------------
+    def counts(self):
+        v = [C.c_size_t() for _ in range(4)]
+        self._ctx.check(load_library().bs_volume_counts(self._h, *[C.byref(x) for x in v]))
+        return dict(leaves=v[0].value, active=v[1].value, negative=v[2].value, tiles=v[3].value)
+
+    def download(self):
+        L = load_library()
+        ijk, tijk, tsz = C.POINTER(C.c_int32)(), C.POINTER(C.c_int32)(), C.POINTER(C.c_int32)()
+        val, tval = C.POINTER(C.c_float)(), C.POINTER(C.c_float)()
+        msk = C.POINTER(C.c_uint64)()
+        n, nt = C.c_size_t(), C.c_size_t()
+        self._ctx.check(L.bs_volume_download(self._h, C.byref(ijk), C.byref(val), C.byref(msk), C.byref(n), C.byref(tijk), C.byref(tsz),
+                                             C.byref(tval), C.byref(nt)))
+        n, nt = n.value, nt.value
+
+        def take(p, count, shape, dtype):
+            out = np.ctypeslib.as_array(p, shape=(max(count, 1),))[:count].astype(dtype, copy=True).reshape(shape)
+            L.bs_buffer_free(C.cast(p, C.c_void_p))
+            return out
+        return dict(origins=take(ijk, n * 3, (-1, 3), np.int32), values=take(val, n * 512, (-1, 512), np.float32),
+                    masks=take(msk, n * 8, (-1, 8), np.uint64), tile_origins=take(tijk, nt * 3, (-1, 3), np.int32),
+                    tile_sizes=take(tsz, nt, (-1,), np.int32), tile_values=take(tval, nt, (-1,), np.float32))
+
+
+class MeshToVolume:
+    """`voxel::mesh_to_volume::MeshToVolume` (src/voxel/mesh_to_volume.rs:17-73, Default :223-236)."""
+
+    def __init__(self, ctx=None):
+        self._ctx = ctx
+        self.voxel_size = 1.0
+        self.band_width = 0
+
+    def with_narrow_band_width(self, width):
+        self.band_width = int(width)
+        return self
+
+    def set_narrow_band_width(self, width):
+        return self.with_narrow_band_width(width)
+
+    def with_voxel_size(self, size):
+        self.voxel_size = float(size)
+        return self
+
+    def set_voxel_size(self, size):
+        return self.with_voxel_size(size)
+
+    def convert(self, mesh):
+        """-> Volume, or None where the reference returns None (empty mesh, :58-60)."""
+        ctx = self._ctx or Context.default()
+        tris = _as_triangles(mesh)
+        h = C.c_void_p()
+        st = load_library().bs_mesh_to_volume(ctx._h, _fp(tris), tris.shape[0], self.voxel_size, self.band_width, C.byref(h))
+        if st == BS_ERR_EMPTY_MESH:
+            return None
+        ctx.check(st)
+        return Volume(h, ctx)
+
+
+class VolumeBuilder:
+    """`voxel::volume::builder::VolumeBuilder` (src/voxel/volume/builder.rs:5-84)."""
+
+    def __init__(self, ctx=None):
+        self._ctx = ctx
+        self.voxel_size = 1.0
+
+    def with_voxel_size(self, voxel_size):
+        self.voxel_size = float(voxel_size)
+        return self
+
+    def set_voxel_size(self, voxel_size):
+        self.voxel_size = float(voxel_size)
+
+    def _make(self, fn, *args):
+        ctx = self._ctx or Context.default()
+        h = C.c_void_p()
+        ctx.check(fn(ctx._h, self.voxel_size, *args, C.byref(h)))
+        return Volume(h, ctx)
+
+    def sphere(self, radius, origin):
+        o = _f32(origin)
+        return self._make(load_library().bs_volume_sphere, radius, _fp(o))
+
+    def cuboid(self, min, max):
+        a, b = _f32(min), _f32(max)
+        return self._make(load_library().bs_volume_cuboid, _fp(a), _fp(b))
+
+    def iwp(self, min, max, cell_size):
+        a, b = _f32(min), _f32(max)
+        return self._make(load_library().bs_volume_iwp, _fp(a), _fp(b), cell_size)
+
+
+def _take_verts(p, n):
+    out = np.ctypeslib.as_array(p, shape=(max(n, 1) * 3,))[: n * 3].copy().reshape(-1, 3)
+    load_library().bs_buffer_free(C.cast(p, C.c_void_p))
+    return out
+
+
+class MarchingCubesMesher:
+    """`voxel::meshing::MarchingCubesMesher` (src/voxel/meshing/marching_cubes.rs:17-63)."""
+
+    def __init__(self):
+        self.voxel_size = 1.0
+
+    def with_voxel_size(self, size):
+        self.voxel_size = float(size)
+        return self
+
+    def set_voxel_size(self, size):
+        return self.with_voxel_size(size)
+
+    def mesh(self, volume):
+        """-> [n_verts,3] f32 vertex soup (3 consecutive vertices per triangle), reference emission order."""
+        p, n = C.POINTER(C.c_float)(), C.c_size_t()
+        volume._ctx.check(load_library().bs_mesh_mc(volume._h, self.voxel_size, C.byref(p), C.byref(n)))
+        return _take_verts(p, n.value)
+
+
+class DualContouringMesher:
+    """`voxel::meshing::DualContouringMesher` (src/voxel/meshing/dual_contouring.rs:13-89)."""
+
+    def __init__(self):
+        self.voxel_size = 1.0
+
+    def with_voxel_size(self, size):
+        self.voxel_size = float(size)
+        return self
+
+    def mesh(self, volume):
+        p, n = C.POINTER(C.c_float)(), C.c_size_t()
+        volume._ctx.check(load_library().bs_mesh_dc(volume._h, self.voxel_size, C.byref(p), C.byref(n)))
+        return _take_verts(p, n.value)
+
+
+class MeshingMethod:
+    """`remeshing::voxel::MeshingMethod` (src/remeshing/voxel.rs:10-15)."""
+    FeaturePreserving = "FeaturePreserving"
+    Manifold = "Manifold"
+
+
+class VoxelRemesher:
+    """`remeshing::voxel::VoxelRemesher` (src/remeshing/voxel.rs:45-95): convert -> MC (Manifold, default) or DC."""
+
+    def __init__(self, ctx=None):
+        self._m2v = MeshToVolume(ctx).with_narrow_band_width(0)
+        self.voxel_size = 1.0
+        self.meshing_method = MeshingMethod.Manifold
+
+    def with_voxel_size(self, size):
+        self._m2v.set_voxel_size(size)
+        self.voxel_size = float(size)
+        return self
+
+    def with_meshing_method(self, method):
+        self.meshing_method = method
+        return self
+
+    def remesh(self, mesh):
+        vol = self._m2v.convert(mesh)
+        if vol is None:
+            return None
+        if self.meshing_method == MeshingMethod.FeaturePreserving:
+            return DualContouringMesher().with_voxel_size(self.voxel_size).mesh(vol)
+        return MarchingCubesMesher().with_voxel_size(self.voxel_size).mesh(vol)
+
+
+__all__ = ["Context", "Volume", "MeshToVolume", "VolumeBuilder", "MarchingCubesMesher", "DualContouringMesher",
+           "VoxelRemesher", "MeshingMethod", "BsharkError", "ReferencePanic", "load_library", "EXPORTS", "LIB_PATH"]

@@ -1,0 +1,136 @@
+// Shared device/host declarations of libbshark_cuda (sm_100a).
+//
+// Data layout in HBM: a volume is a flat, sorted list of 8^3 bricks
+//   keys[n]        u64   brick key, sorted ascending == the reference's leaf visit order
+//   values[n*512]  f32   brick-major, inside a brick the reference's leaf layout x<<6 | y<<3 | z
+//                        (leaf_node/mod.rs:29-36) so a z-line is one 32 B sector and a brick 2 KB
+//   masks[n*8]     u64   512 active bits per brick, bit (o&63) of word (o>>6)
+// plus the (rare, CSG-only) active tiles as two small sorted lists.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <string>
+#include <vector>
+#include "../../include/bshark.h"
+
+// ---- brick keys -------------------------------------------------------------------------------------
+// Brick coordinate b = voxel >> 3 per axis, biased by 2^17 into 18 bits u. The reference's tree is
+// Root(BTreeMap keyed by 4096-voxel origin, lexicographic x,y,z) -> 32^3 node -> 16^3 node -> leaf, visited
+// in ascending slot offset (x-major). Packing [root x,y,z : 9 bits each][node5 slot x,y,z : 5 each]
+// [node4 slot x,y,z : 4 each] makes "ascending key" == that visit order.
+#define BS_COORD_BIAS (1 << 17)
+#define BS_BRICK_MIN (-(1 << 17))
+#define BS_BRICK_MAX ((1 << 17) - 1)
+#define BS_KEY_INVALID 0xFFFFFFFFFFFFFFFFull
+
+__host__ __device__ __forceinline__ uint64_t bs_brick_key(int bx, int by, int bz) {
+    uint32_t ux = (uint32_t)(bx + BS_COORD_BIAS), uy = (uint32_t)(by + BS_COORD_BIAS), uz = (uint32_t)(bz + BS_COORD_BIAS);
+    uint64_t k = 0;
+    k |= (uint64_t)(ux >> 9) << 45; k |= (uint64_t)(uy >> 9) << 36; k |= (uint64_t)(uz >> 9) << 27;
+    k |= (uint64_t)((ux >> 4) & 31) << 22; k |= (uint64_t)((uy >> 4) & 31) << 17; k |= (uint64_t)((uz >> 4) & 31) << 12;
+    k |= (uint64_t)(ux & 15) << 8; k |= (uint64_t)(uy & 15) << 4; k |= (uint64_t)(uz & 15);
+    return k;
+}
+__host__ __device__ __forceinline__ void bs_key_brick(uint64_t k, int& bx, int& by, int& bz) {
+    uint32_t ux = (uint32_t)(((k >> 45) & 511) << 9 | ((k >> 22) & 31) << 4 | ((k >> 8) & 15));
+    uint32_t uy = (uint32_t)(((k >> 36) & 511) << 9 | ((k >> 17) & 31) << 4 | ((k >> 4) & 15));
+    uint32_t uz = (uint32_t)(((k >> 27) & 511) << 9 | ((k >> 12) & 31) << 4 | (k & 15));
+    bx = (int)ux - BS_COORD_BIAS; by = (int)uy - BS_COORD_BIAS; bz = (int)uz - BS_COORD_BIAS;
+}
+// key of the 16^3-brick node (128^3 voxels) and of the 32^3 node (4096^3 voxels) a brick lives in
+__host__ __device__ __forceinline__ uint64_t bs_key_node4(uint64_t k) { return k >> 12; }
+__host__ __device__ __forceinline__ uint64_t bs_key_node5(uint64_t k) { return k >> 27; }
+
+// sentinel for "no distance yet" in the unsigned field: bytes 0x7F -> 3.39e38, below +inf and NaN bit patterns
+#define BS_UDF_SENTINEL_BITS 0x7F7F7F7Fu
+
+// ---- exact (never contracted) f32 arithmetic ----------------------------------------------------------
+// The reference is Rust: no FMA contraction, IEEE round-to-nearest. Everything that decides topology or
+// must be bit-identical (subdivision, boxes, point-triangle distance, MC/DC vertices, fast sweeping) is
+// written with these so -fmad cannot fuse it.
+#ifdef __CUDACC__
+__device__ __forceinline__ float xadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float xsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float xmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float xdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float xsqrt(float a) { return __fsqrt_rn(a); }
+struct f3 { float x, y, z; };
+__device__ __forceinline__ f3 xadd(f3 a, f3 b) { return {xadd(a.x, b.x), xadd(a.y, b.y), xadd(a.z, b.z)}; }
+__device__ __forceinline__ f3 xsub(f3 a, f3 b) { return {xsub(a.x, b.x), xsub(a.y, b.y), xsub(a.z, b.z)}; }
+__device__ __forceinline__ f3 xscale(f3 a, float s) { return {xmul(a.x, s), xmul(a.y, s), xmul(a.z, s)}; }
+// nalgebra 3-vector dot: (x*x' + y*y') + z*z'
+__device__ __forceinline__ float xdot(f3 a, f3 b) { return xadd(xadd(xmul(a.x, b.x), xmul(a.y, b.y)), xmul(a.z, b.z)); }
+__device__ __forceinline__ float xnorm2(f3 a) { return xdot(a, a); }
+__device__ __forceinline__ f3 xcross(f3 a, f3 b) {
+    return {xsub(xmul(a.y, b.z), xmul(a.z, b.y)), xsub(xmul(a.z, b.x), xmul(a.x, b.z)), xsub(xmul(a.x, b.y), xmul(a.y, b.x))};
+}
+#endif
+
+// ---- host-side objects --------------------------------------------------------------------------------
+struct bs_stat { const char* name; double value; };
+
+struct bs_context {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaMemPool_t pool = nullptr;
+    std::string err;
+    std::vector<bs_stat> stats;
+    int8_t* d_mc33 = nullptr;       // MC33 tables blob (mc33_tables.h)
+    float* d_out_verts = nullptr;   // last extraction result left on the device
+    size_t out_verts_cap = 0;
+    // stage timing
+    std::vector<std::pair<const char*, cudaEvent_t>> marks;
+};
+
+struct bs_volume {
+    bs_context* ctx = nullptr;
+    float voxel_size = 1.0f;
+    size_t n_bricks = 0;
+    unsigned long long* keys = nullptr;
+    float* values = nullptr;
+    unsigned long long* masks = nullptr;
+    // active tiles: 8^3 tiles keyed like bricks; 128^3 tiles keyed by bs_key_node4 form. Values are +-FLT_MAX.
+    size_t n_tiles8 = 0, n_tiles128 = 0;
+    unsigned long long* tile8_keys = nullptr; float* tile8_values = nullptr;
+    unsigned long long* tile128_keys = nullptr; float* tile128_values = nullptr;
+    // multi-GPU: bricks [0, n_owned) are this rank's; the rest are read-only halo copies
+    size_t n_owned = 0;
+};
+
+// error plumbing ----------------------------------------------------------------------------------------
+bs_status bs_fail(bs_context* ctx, bs_status st, const char* fmt, ...);
+#define BS_CUDA(ctx, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return bs_fail((ctx), BS_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } while (0)
+#define BS_TRY(call) do { bs_status s_ = (call); if (s_ != BS_OK) return s_; } while (0)
+
+// stream-ordered allocation on the context pool
+template <class T> bs_status bs_alloc(bs_context* ctx, T** p, size_t count) {
+    *p = nullptr;
+    if (count == 0) count = 1;
+    BS_CUDA(ctx, cudaMallocAsync((void**)p, count * sizeof(T), ctx->stream));
+    return BS_OK;
+}
+template <class T> void bs_free(bs_context* ctx, T* p) { if (p) cudaFreeAsync((void*)p, ctx->stream); }
+
+void bs_mark(bs_context* ctx, const char* name);          // record an event named `name` on the stream
+void bs_marks_begin(bs_context* ctx);                     // clear marks + stats, record "begin"
+void bs_marks_end(bs_context* ctx);                       // sync, turn consecutive marks into "<name>_ms" stats
+void bs_stat_add(bs_context* ctx, const char* name, double v);
+
+bs_volume* bs_volume_new(bs_context* ctx, float voxel_size);
+bs_status bs_volume_alloc_bricks(bs_volume* v, size_t n);  // keys / values / masks for n bricks
+
+inline unsigned bs_blocks(size_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
+
+// stage entry points (one .cu each)
+bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, float voxel_size, int64_t band,
+                          int rank, int world, bs_volume** out);
+bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_volume* vol);
+bs_status bs_mc_impl(const bs_volume* v, float voxel_size, const float** d_verts, size_t* n_verts);
+bs_status bs_dc_impl(const bs_volume* v, float voxel_size, const float** d_verts, size_t* n_verts);
+bs_status bs_csg_impl(bs_volume* a, bs_volume* b, int op, bs_volume** out);
+bs_status bs_offset_impl(bs_volume* a, float distance, bs_volume** out);
+bs_status bs_from_voxels_impl(bs_context* ctx, const int32_t* d_ijk, const float* d_values, size_t m, float voxel_size,
+                              bs_volume** out);
+bs_status bs_builder_impl(bs_context* ctx, int kind, float voxel_size, const float* p, bs_volume** out);

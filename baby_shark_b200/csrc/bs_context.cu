@@ -1,0 +1,307 @@
+// Context, volume handles and the extern "C" surface of libbshark_cuda (include/bshark.h).
+#include "bs_common.cuh"
+#include "mc33_tables.h"
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+bs_status bs_fail(bs_context* ctx, bs_status st, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    if (ctx) ctx->err = buf;
+    return st;
+}
+
+void bs_marks_begin(bs_context* ctx) {
+    for (auto& m : ctx->marks) cudaEventDestroy(m.second);
+    ctx->marks.clear(); ctx->stats.clear();
+    bs_mark(ctx, "begin");
+}
+void bs_mark(bs_context* ctx, const char* name) {
+    cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, ctx->stream);
+    ctx->marks.push_back({name, e});
+}
+void bs_marks_end(bs_context* ctx) {
+    cudaStreamSynchronize(ctx->stream);
+    for (size_t i = 1; i < ctx->marks.size(); ++i) {
+        float ms = 0.f; cudaEventElapsedTime(&ms, ctx->marks[i - 1].second, ctx->marks[i].second);
+        ctx->stats.push_back({ctx->marks[i].first, (double)ms});
+    }
+    if (ctx->marks.size() > 1) {
+        float ms = 0.f; cudaEventElapsedTime(&ms, ctx->marks.front().second, ctx->marks.back().second);
+        ctx->stats.push_back({"total_ms", (double)ms});
+    }
+}
+void bs_stat_add(bs_context* ctx, const char* name, double v) { ctx->stats.push_back({name, v}); }
+
+bs_volume* bs_volume_new(bs_context* ctx, float voxel_size) {
+    bs_volume* v = new bs_volume();
+    v->ctx = ctx; v->voxel_size = voxel_size;
+    return v;
+}
+bs_status bs_volume_alloc_bricks(bs_volume* v, size_t n) {
+    v->n_bricks = n; v->n_owned = n;
+    BS_TRY(bs_alloc(v->ctx, &v->keys, n));
+    BS_TRY(bs_alloc(v->ctx, &v->values, n * 512));
+    BS_TRY(bs_alloc(v->ctx, &v->masks, n * 8));
+    return BS_OK;
+}
+
+static const int8_t h_mc33[MC33_BLOB_SIZE] = MC33_BLOB_INIT;
+
+template <class T> static bs_status dup_array(bs_context* c, T** dst, const T* src, size_t n) {
+    BS_TRY(bs_alloc(c, dst, n));
+    if (n) BS_CUDA(c, cudaMemcpyAsync(*dst, src, n * sizeof(T), cudaMemcpyDeviceToDevice, c->stream));
+    return BS_OK;
+}
+template <class T> static bs_status to_host(bs_context* c, T** dst, const T* src, size_t n) {
+    *dst = nullptr;
+    BS_CUDA(c, cudaMallocHost((void**)dst, (n ? n : 1) * sizeof(T)));
+    if (n) BS_CUDA(c, cudaMemcpyAsync(*dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+    return BS_OK;
+}
+
+extern "C" {
+
+bs_status bs_context_create(int device, bs_context** out) {
+    if (!out) return BS_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return BS_ERR_NO_DEVICE;
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) return BS_ERR_NO_DEVICE; }
+    if (device >= count) return BS_ERR_INVALID;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return BS_ERR_NO_DEVICE;
+    if (prop.major != 10) return BS_ERR_NO_DEVICE;  // kernels are built for sm_100a only
+    bs_context* ctx = new bs_context();
+    ctx->device = device; ctx->sm_count = prop.multiProcessorCount;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx; return BS_ERR_CUDA;
+    }
+    cudaDeviceGetDefaultMemPool(&ctx->pool, device);
+    uint64_t thr = UINT64_MAX;  // keep freed blocks in the pool: allocation cost must not show up per call
+    cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    if (cudaMalloc((void**)&ctx->d_mc33, MC33_BLOB_SIZE) != cudaSuccess ||
+        cudaMemcpy(ctx->d_mc33, h_mc33, MC33_BLOB_SIZE, cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaStreamDestroy(ctx->stream); delete ctx; return BS_ERR_CUDA;
+    }
+    *out = ctx;
+    return BS_OK;
+}
+void bs_context_destroy(bs_context* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& m : ctx->marks) cudaEventDestroy(m.second);
+    if (ctx->d_out_verts) cudaFree(ctx->d_out_verts);
+    cudaFree(ctx->d_mc33);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+const char* bs_last_error(const bs_context* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+int bs_context_device(const bs_context* ctx) { return ctx ? ctx->device : -1; }
+void* bs_context_stream(const bs_context* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+size_t bs_context_last_stats(const bs_context* ctx, const char** names, double* values, size_t cap) {
+    if (!ctx) return 0;
+    size_t n = ctx->stats.size() < cap ? ctx->stats.size() : cap;
+    for (size_t i = 0; i < n; ++i) { names[i] = ctx->stats[i].name; values[i] = ctx->stats[i].value; }
+    return n;
+}
+
+void bs_volume_free(bs_volume* v) {
+    if (!v) return;
+    bs_context* c = v->ctx;
+    cudaSetDevice(c->device);
+    bs_free(c, v->keys); bs_free(c, v->values); bs_free(c, v->masks);
+    bs_free(c, v->tile8_keys); bs_free(c, v->tile8_values); bs_free(c, v->tile128_keys); bs_free(c, v->tile128_values);
+    delete v;
+}
+float bs_volume_voxel_size(const bs_volume* v) { return v ? v->voxel_size : 0.0f; }
+
+bs_status bs_volume_empty(bs_context* ctx, float voxel_size, bs_volume** out) {
+    if (!ctx || !out) return BS_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    bs_volume* v = bs_volume_new(ctx, voxel_size);
+    bs_status s = bs_volume_alloc_bricks(v, 0);
+    if (s != BS_OK) { bs_volume_free(v); return s; }
+    *out = v;
+    return BS_OK;
+}
+
+bs_status bs_volume_clone(const bs_volume* v, bs_volume** out) {
+    if (!v || !out) return BS_ERR_INVALID;
+    bs_context* c = v->ctx;
+    cudaSetDevice(c->device);
+    bs_volume* w = bs_volume_new(c, v->voxel_size);
+    w->n_bricks = v->n_bricks; w->n_owned = v->n_owned; w->n_tiles8 = v->n_tiles8; w->n_tiles128 = v->n_tiles128;
+    bs_status s;
+    if ((s = dup_array(c, &w->keys, v->keys, v->n_bricks)) || (s = dup_array(c, &w->values, v->values, v->n_bricks * 512)) ||
+        (s = dup_array(c, &w->masks, v->masks, v->n_bricks * 8)) || (s = dup_array(c, &w->tile8_keys, v->tile8_keys, v->n_tiles8)) ||
+        (s = dup_array(c, &w->tile8_values, v->tile8_values, v->n_tiles8)) || (s = dup_array(c, &w->tile128_keys, v->tile128_keys, v->n_tiles128)) ||
+        (s = dup_array(c, &w->tile128_values, v->tile128_values, v->n_tiles128))) { bs_volume_free(w); return s; }
+    BS_CUDA(c, cudaStreamSynchronize(c->stream));
+    *out = w;
+    return BS_OK;
+}
+
+void bs_buffer_free(void* p) { if (p) cudaFreeHost(p); }
+
+bs_status bs_volume_download(const bs_volume* v, int32_t** brick_ijk, float** values, uint64_t** masks, size_t* n_bricks,
+                             int32_t** tile_ijk, int32_t** tile_size, float** tile_values, size_t* n_tiles) {
+    if (!v || !brick_ijk || !values || !masks || !n_bricks) return BS_ERR_INVALID;
+    bs_context* c = v->ctx;
+    cudaSetDevice(c->device);
+    const size_t n = v->n_bricks;
+    unsigned long long* hkeys = nullptr;
+    BS_TRY(to_host(c, &hkeys, v->keys, n));
+    BS_TRY(to_host(c, values, v->values, n * 512));
+    BS_TRY(to_host(c, (unsigned long long**)masks, v->masks, n * 8));
+    unsigned long long *t8k = nullptr, *t128k = nullptr; float *t8v = nullptr, *t128v = nullptr;
+    BS_TRY(to_host(c, &t8k, v->tile8_keys, v->n_tiles8)); BS_TRY(to_host(c, &t8v, v->tile8_values, v->n_tiles8));
+    BS_TRY(to_host(c, &t128k, v->tile128_keys, v->n_tiles128)); BS_TRY(to_host(c, &t128v, v->tile128_values, v->n_tiles128));
+    BS_CUDA(c, cudaStreamSynchronize(c->stream));
+    BS_CUDA(c, cudaMallocHost((void**)brick_ijk, (n ? n : 1) * 3 * sizeof(int32_t)));
+    for (size_t i = 0; i < n; ++i) {
+        int bx, by, bz; bs_key_brick(hkeys[i], bx, by, bz);
+        (*brick_ijk)[3 * i] = bx * 8; (*brick_ijk)[3 * i + 1] = by * 8; (*brick_ijk)[3 * i + 2] = bz * 8;
+    }
+    *n_bricks = n;
+    if (tile_ijk && tile_size && tile_values && n_tiles) {
+        // merge the two tile lists into the reference's visit order (a 128^3 tile sorts by its node4 key)
+        const size_t nt = v->n_tiles8 + v->n_tiles128;
+        BS_CUDA(c, cudaMallocHost((void**)tile_ijk, (nt ? nt : 1) * 3 * sizeof(int32_t)));
+        BS_CUDA(c, cudaMallocHost((void**)tile_size, (nt ? nt : 1) * sizeof(int32_t)));
+        BS_CUDA(c, cudaMallocHost((void**)tile_values, (nt ? nt : 1) * sizeof(float)));
+        size_t i8 = 0, i128 = 0, o = 0;
+        while (i8 < v->n_tiles8 || i128 < v->n_tiles128) {
+            bool take8 = i128 >= v->n_tiles128 || (i8 < v->n_tiles8 && t8k[i8] < (t128k[i128] << 12));
+            int bx, by, bz;
+            if (take8) { bs_key_brick(t8k[i8], bx, by, bz); (*tile_size)[o] = 8; (*tile_values)[o] = t8v[i8]; ++i8; }
+            else { bs_key_brick(t128k[i128] << 12, bx, by, bz); (*tile_size)[o] = 128; (*tile_values)[o] = t128v[i128]; ++i128; }
+            (*tile_ijk)[3 * o] = bx * 8; (*tile_ijk)[3 * o + 1] = by * 8; (*tile_ijk)[3 * o + 2] = bz * 8;
+            ++o;
+        }
+        *n_tiles = nt;
+    }
+    cudaFreeHost(hkeys); cudaFreeHost(t8k); cudaFreeHost(t8v); cudaFreeHost(t128k); cudaFreeHost(t128v);
+    return BS_OK;
+}
+
+// ---- mesh -> volume ---------------------------------------------------------------------------------------
+bs_status bs_mesh_to_volume_sharded(bs_context* ctx, const float* d_tris, size_t n_tris, float voxel_size, int64_t band,
+                                    int rank, int world, bs_volume** out) {
+    if (!ctx || !out || world < 1 || rank < 0 || rank >= world) return BS_ERR_INVALID;
+    *out = nullptr;
+    if (!(voxel_size > 0.0f) || band < 0 || band > 64) return bs_fail(ctx, BS_ERR_INVALID, "voxel_size must be > 0 and 0 <= band_width <= 64");
+    if (n_tris == 0) return BS_ERR_EMPTY_MESH;
+    cudaSetDevice(ctx->device);
+    return bs_convert_impl(ctx, d_tris, n_tris, voxel_size, band, rank, world, out);
+}
+bs_status bs_mesh_to_volume_device(bs_context* ctx, const float* d_tris, size_t n_tris, float voxel_size, int64_t band, bs_volume** out) {
+    return bs_mesh_to_volume_sharded(ctx, d_tris, n_tris, voxel_size, band, 0, 1, out);
+}
+bs_status bs_mesh_to_volume(bs_context* ctx, const float* tris, size_t n_tris, float voxel_size, int64_t band, bs_volume** out) {
+    if (!ctx || !out) return BS_ERR_INVALID;
+    *out = nullptr;
+    if (n_tris == 0) return BS_ERR_EMPTY_MESH;
+    if (!tris) return BS_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    float* d = nullptr;
+    BS_TRY(bs_alloc(ctx, &d, n_tris * 9));
+    cudaError_t e = cudaMemcpyAsync(d, tris, n_tris * 9 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) { bs_free(ctx, d); return bs_fail(ctx, BS_ERR_CUDA, "H2D triangles: %s", cudaGetErrorString(e)); }
+    bs_status s = bs_mesh_to_volume_device(ctx, d, n_tris, voxel_size, band, out);
+    bs_free(ctx, d);
+    cudaStreamSynchronize(ctx->stream);
+    return s;
+}
+
+// ---- extraction ---------------------------------------------------------------------------------------------
+static bs_status verts_to_host(bs_context* c, const float* d, size_t n, float** verts, size_t* n_verts) {
+    *verts = nullptr; *n_verts = 0;
+    BS_CUDA(c, cudaMallocHost((void**)verts, (n ? n : 1) * 3 * sizeof(float)));
+    if (n) BS_CUDA(c, cudaMemcpyAsync(*verts, d, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    BS_CUDA(c, cudaStreamSynchronize(c->stream));
+    *n_verts = n;
+    return BS_OK;
+}
+bs_status bs_mesh_mc_device(const bs_volume* v, float voxel_size, const float** d_verts, size_t* n_verts) {
+    if (!v || !d_verts || !n_verts) return BS_ERR_INVALID;
+    cudaSetDevice(v->ctx->device);
+    return bs_mc_impl(v, voxel_size, d_verts, n_verts);
+}
+bs_status bs_mesh_mc(const bs_volume* v, float voxel_size, float** verts, size_t* n_verts) {
+    if (!v || !verts || !n_verts) return BS_ERR_INVALID;
+    const float* d = nullptr; size_t n = 0;
+    BS_TRY(bs_mesh_mc_device(v, voxel_size, &d, &n));
+    return verts_to_host(v->ctx, d, n, verts, n_verts);
+}
+bs_status bs_mesh_dc_device(const bs_volume* v, float voxel_size, const float** d_verts, size_t* n_verts) {
+    if (!v || !d_verts || !n_verts) return BS_ERR_INVALID;
+    cudaSetDevice(v->ctx->device);
+    return bs_dc_impl(v, voxel_size, d_verts, n_verts);
+}
+bs_status bs_mesh_dc(const bs_volume* v, float voxel_size, float** verts, size_t* n_verts) {
+    if (!v || !verts || !n_verts) return BS_ERR_INVALID;
+    const float* d = nullptr; size_t n = 0;
+    BS_TRY(bs_mesh_dc_device(v, voxel_size, &d, &n));
+    return verts_to_host(v->ctx, d, n, verts, n_verts);
+}
+
+// ---- CSG / offset -------------------------------------------------------------------------------------------
+static bs_status csg_entry(bs_volume* a, bs_volume* b, int op, bs_volume** out) {
+    if (out) *out = nullptr;
+    if (!a || !b || !out || a == b || a->ctx != b->ctx) { bs_volume_free(a); if (b != a) bs_volume_free(b); return BS_ERR_INVALID; }
+    cudaSetDevice(a->ctx->device);
+    bs_status s = bs_csg_impl(a, b, op, out);
+    bs_volume_free(a); bs_volume_free(b);
+    return s;
+}
+bs_status bs_volume_union(bs_volume* a, bs_volume* b, bs_volume** out) { return csg_entry(a, b, 0, out); }
+bs_status bs_volume_subtract(bs_volume* a, bs_volume* b, bs_volume** out) { return csg_entry(a, b, 1, out); }
+bs_status bs_volume_intersect(bs_volume* a, bs_volume* b, bs_volume** out) { return csg_entry(a, b, 2, out); }
+bs_status bs_volume_offset(bs_volume* a, float distance, bs_volume** out) {
+    if (out) *out = nullptr;
+    if (!a || !out) { bs_volume_free(a); return BS_ERR_INVALID; }
+    cudaSetDevice(a->ctx->device);
+    bs_status s = bs_offset_impl(a, distance, out);
+    bs_volume_free(a);
+    return s;
+}
+
+// ---- builders -----------------------------------------------------------------------------------------------
+bs_status bs_volume_from_voxels(bs_context* ctx, const int32_t* ijk, const float* values, size_t m, float voxel_size, bs_volume** out) {
+    if (!ctx || !out || (m && (!ijk || !values))) return BS_ERR_INVALID;
+    *out = nullptr;
+    cudaSetDevice(ctx->device);
+    if (m == 0) return bs_volume_empty(ctx, voxel_size, out);
+    int32_t* d_ijk = nullptr; float* d_val = nullptr;
+    BS_TRY(bs_alloc(ctx, &d_ijk, m * 3)); BS_TRY(bs_alloc(ctx, &d_val, m));
+    cudaMemcpyAsync(d_ijk, ijk, m * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(d_val, values, m * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+    bs_status s = bs_from_voxels_impl(ctx, d_ijk, d_val, m, voxel_size, out);
+    bs_free(ctx, d_ijk); bs_free(ctx, d_val);
+    cudaStreamSynchronize(ctx->stream);
+    return s;
+}
+bs_status bs_volume_sphere(bs_context* ctx, float voxel_size, float radius, const float origin[3], bs_volume** out) {
+    if (!ctx || !out || !origin) return BS_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    float p[7] = {radius, origin[0], origin[1], origin[2], 0, 0, 0};
+    return bs_builder_impl(ctx, 0, voxel_size, p, out);
+}
+bs_status bs_volume_cuboid(bs_context* ctx, float voxel_size, const float mn[3], const float mx[3], bs_volume** out) {
+    if (!ctx || !out || !mn || !mx) return BS_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    float p[7] = {mn[0], mn[1], mn[2], mx[0], mx[1], mx[2], 0};
+    return bs_builder_impl(ctx, 1, voxel_size, p, out);
+}
+bs_status bs_volume_iwp(bs_context* ctx, float voxel_size, const float mn[3], const float mx[3], float cell_size, bs_volume** out) {
+    if (!ctx || !out || !mn || !mx) return BS_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    float p[7] = {mn[0], mn[1], mn[2], mx[0], mx[1], mx[2], cell_size};
+    return bs_builder_impl(ctx, 2, voxel_size, p, out);
+}
+
+}  // extern "C"

@@ -1,0 +1,394 @@
+// Mesh -> unsigned narrow-band distance field on sorted 8^3 bricks (sm_100a).
+// Replaces MeshToVolume::{subdivide_triangle, compute_unsigned_distance_field}
+// (src/voxel/mesh_to_volume.rs:75-196) and Triangle3::{bbox, closest_point, max_side}
+// (src/geometry/primitives/triangle3.rs:117-124,307-382).
+//
+// value(v) = min over sub-triangles WHOSE INTEGER BOX CONTAINS v of |closest_point(v) - v|   (not the true
+// distance: mesh_to_volume.rs:170-195), topology = union of those boxes. Sub-triangle vertices come from
+// sequential f32 running sums in the reference (:90-115); every thread re-derives its sub-triangle with the
+// same additions in the same order, so boxes and distances are bit-identical and the scatter-min (strict
+// `<`, order independent) can be an atomicMin on the float bits (distances are >= 0).
+//
+// Two passes over the (never materialised) sub-triangle stream:
+//   mark : insert the key of every brick a box touches into an open-addressing hash set
+//   eval : point-triangle distances for every lattice point of every box, atomicMin into the brick
+// with a radix sort of the brick keys in between (sorted key order == the reference's leaf visit order).
+#include "bs_common.cuh"
+#include <cub/cub.cuh>
+#include <cfloat>
+#include <cmath>
+
+namespace {
+
+constexpr int TPB = 256;
+constexpr int MAX_PROBE = 512;
+
+struct ConvertParams {
+    const float* tris; size_t n_tris;
+    const unsigned long long* offsets;  // exclusive prefix sum of per-triangle sub-triangle counts, n_tris + 1
+    unsigned long long total;
+    float vs, inv_vs; int band;
+    unsigned long long* table_keys; unsigned* table_slots; unsigned table_mask;
+    float* values;
+    int* flags;  // [0] hash overflow, [1] index range error
+};
+
+__device__ __forceinline__ unsigned long long hash64(unsigned long long k) {
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33; return k;
+}
+
+__device__ __forceinline__ f3 ld3(const float* p) { return {p[0], p[1], p[2]}; }
+
+// Triangle3::max_side / voxel_size, floored (mesh_to_volume.rs:76)
+__device__ __forceinline__ float num_subs_of(f3 p1, f3 p2, f3 p3, float vs) {
+    float ab = xnorm2(xsub(p2, p1)), ac = xnorm2(xsub(p3, p1)), bc = xnorm2(xsub(p3, p2));
+    float m = fmaxf(fmaxf(ab, ac), bc);
+    return floorf(xdiv(xsqrt(m), vs));
+}
+
+__global__ void k_tri_counts(const float* __restrict__ tris, size_t n_tris, float vs, unsigned long long* counts, double* area_vox) {
+    size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    double a = 0.0;
+    if (t < n_tris) {
+        const float* p = tris + 9 * t;
+        f3 p1 = ld3(p), p2 = ld3(p + 3), p3 = ld3(p + 6);
+        float n = num_subs_of(p1, p2, p3, vs);
+        unsigned long long c;
+        if (n < 2.0f) c = 1; else if (n != n) c = 0; else { double nd = fmin((double)n, 4.0e9); c = (unsigned long long)(nd * nd); }
+        counts[t] = c;
+        f3 cr = xcross(xsub(p2, p1), xsub(p3, p1));
+        float ar = 0.5f * sqrtf(xnorm2(cr));
+        if (ar == ar && ar < 3.0e38f) a = (double)ar / ((double)vs * (double)vs);
+    }
+    // block reduce -> one atomic per block
+    typedef cub::BlockReduce<double, TPB> BR;
+    __shared__ typename BR::TempStorage tmp;
+    double s = BR(tmp).Sum(a);
+    if (threadIdx.x == 0 && s != 0.0) atomicAdd(area_vox, s);
+}
+
+// j-th sub-triangle of triangle (p1,p2,p3) in the reference's construction (mesh_to_volume.rs:75-116):
+// row i = isqrt(j); inside the row, pos = j - i*i: pos == 2i is the row's closing triangle (a,b,c), otherwise
+// step k = pos >> 1 yields (a_prev, b_s, a_s) for even pos and (a_s, b_s, c_s) for odd pos.
+__device__ void make_subtri(f3 p1, f3 p2, f3 p3, float vs, unsigned long long j, f3& A, f3& B, f3& C) {
+    float n = num_subs_of(p1, p2, p3, vs);
+    if (n < 2.0f) { A = p1; B = p2; C = p3; return; }
+    float inv = xdiv(1.0f, n);
+    f3 s1 = xscale(xsub(p2, p1), inv), s2 = xscale(xsub(p3, p2), inv);
+    unsigned long long i = (unsigned long long)sqrt((double)j);
+    while (i * i > j) --i;
+    while ((i + 1) * (i + 1) <= j) ++i;
+    unsigned long long pos = j - i * i;
+    f3 a = p1;
+    for (unsigned long long r = 0; r < i; ++r) a = xadd(a, s1);
+    f3 b = xadd(a, s1);
+    if (pos == 2 * i) { A = a; B = b; C = xadd(b, s2); return; }
+    unsigned long long k = pos >> 1;
+    f3 a_s = xadd(a, s2), b_s = xadd(b, s2), a_prev = a;
+    for (unsigned long long q = 0; q < k; ++q) { a_prev = a_s; a_s = xadd(a_s, s2); b_s = xadd(b_s, s2); }
+    if ((pos & 1) == 0) { A = a_prev; B = b_s; C = a_s; }
+    else { A = a_s; B = b_s; C = xadd(b_s, s2); }  // c_s(k) = b_s(k) + s2 bit for bit (c = b + s2)
+}
+
+// Integer box of a sub-triangle (mesh_to_volume.rs:124-141). Returns false when outside the supported range.
+__device__ __forceinline__ bool subtri_box(f3 A, f3 B, f3 C, float inv_vs, int band, int mn[3], int mx[3]) {
+    float lo[3] = {fminf(C.x, fminf(A.x, B.x)), fminf(C.y, fminf(A.y, B.y)), fminf(C.z, fminf(A.z, B.z))};
+    float hi[3] = {fmaxf(C.x, fmaxf(A.x, B.x)), fmaxf(C.y, fmaxf(A.y, B.y)), fmaxf(C.z, fmaxf(A.z, B.z))};
+    bool ok = true;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        float fl = floorf(xmul(lo[d], inv_vs)), ce = ceilf(xmul(hi[d], inv_vs));
+        if (!(fl > -1.0e6f && ce < 1.0e6f)) { ok = false; fl = 0.f; ce = 0.f; }
+        mn[d] = (int)fl - band; mx[d] = (int)ce + band;
+    }
+    if (mx[0] == mn[0] || mx[1] == mn[1] || mx[2] == mn[2]) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { mn[d] -= 1; mx[d] += 1; }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) if ((mn[d] >> 3) < BS_BRICK_MIN || (mx[d] >> 3) > BS_BRICK_MAX) ok = false;
+    return ok;
+}
+
+// Block-cooperative map from a flat sub-triangle index to (triangle, local index): "last t with
+// offsets[t] <= g" (zero-count triangles repeat an offset and are skipped by taking the LAST such t).
+struct TriCursor { size_t tri; unsigned long long local; bool valid; };
+__device__ __forceinline__ size_t find_tri(const ConvertParams& P, unsigned long long g) {
+    size_t lo = 0, hi = P.n_tris;  // offsets[0] = 0 <= g < total = offsets[n_tris]
+    while (hi - lo > 1) { size_t mid = (lo + hi) >> 1; if (P.offsets[mid] <= g) lo = mid; else hi = mid; }
+    return lo;
+}
+__device__ TriCursor locate(const ConvertParams& P, unsigned long long* s_off /*[TPB+1]*/) {
+    const unsigned long long g0 = (unsigned long long)blockIdx.x * TPB;
+    // uniform search for the triangle containing g0 (every thread walks the same path: broadcast loads), then
+    // a window of TPB+1 offsets in shared memory serves the per-thread searches
+    const size_t base = find_tri(P, g0);
+    for (int i = threadIdx.x; i <= TPB; i += TPB) { size_t idx = base + i; s_off[i] = idx <= P.n_tris ? P.offsets[idx] : ~0ull; }
+    __syncthreads();
+    TriCursor c; c.valid = false; c.tri = 0; c.local = 0;
+    unsigned long long g = g0 + threadIdx.x;
+    if (g < P.total) {
+        int l = 0, h = TPB + 1;
+        while (h - l > 1) { int m = (l + h) >> 1; if (s_off[m] <= g) l = m; else h = m; }
+        size_t t = (l == TPB) ? find_tri(P, g) : base + l;  // window exhausted only if zero-count triangles intervene
+        c.tri = t; c.local = g - P.offsets[t]; c.valid = true;
+    }
+    return c;
+}
+
+__device__ __forceinline__ void hash_insert(const ConvertParams& P, unsigned long long key) {
+    unsigned h = (unsigned)hash64(key) & P.table_mask;
+    for (int probe = 0; probe < MAX_PROBE; ++probe) {
+        unsigned long long cur = P.table_keys[h];
+        if (cur == key) return;
+        if (cur == BS_KEY_INVALID) {
+            unsigned long long prev = atomicCAS(&P.table_keys[h], BS_KEY_INVALID, key);
+            if (prev == BS_KEY_INVALID || prev == key) return;
+        }
+        h = (h + 1) & P.table_mask;
+    }
+    P.flags[0] = 1;
+}
+__device__ __forceinline__ unsigned hash_lookup(const ConvertParams& P, unsigned long long key) {
+    unsigned h = (unsigned)hash64(key) & P.table_mask;
+    for (int probe = 0; probe < MAX_PROBE; ++probe) {
+        unsigned long long cur = P.table_keys[h];
+        if (cur == key) return P.table_slots[h];
+        if (cur == BS_KEY_INVALID) return 0xFFFFFFFFu;
+        h = (h + 1) & P.table_mask;
+    }
+    return 0xFFFFFFFFu;
+}
+
+__global__ void __launch_bounds__(TPB) k_mark(ConvertParams P) {
+    __shared__ unsigned long long s_off[TPB + 1];
+    TriCursor c = locate(P, s_off);
+    if (!c.valid) return;
+    const float* p = P.tris + 9 * c.tri;
+    f3 A, B, C;
+    make_subtri(ld3(p), ld3(p + 3), ld3(p + 6), P.vs, c.local, A, B, C);
+    int mn[3], mx[3];
+    if (!subtri_box(A, B, C, P.inv_vs, P.band, mn, mx)) { P.flags[1] = 1; return; }
+    for (int bx = mn[0] >> 3; bx <= (mx[0] >> 3); ++bx)
+        for (int by = mn[1] >> 3; by <= (mx[1] >> 3); ++by)
+            for (int bz = mn[2] >> 3; bz <= (mx[2] >> 3); ++bz) hash_insert(P, bs_brick_key(bx, by, bz));
+}
+
+// Triangle3::closest_point (triangle3.rs:317-382) then |closest - p| (mesh_to_volume.rs:155)
+__device__ __forceinline__ float point_triangle_distance(f3 a, f3 b, f3 c, f3 ab, f3 ac, f3 p) {
+    f3 cp;
+    f3 ap = xsub(p, a);
+    float d1 = xdot(ab, ap), d2 = xdot(ac, ap);
+    if (d1 <= 0.f && d2 <= 0.f) cp = a;
+    else {
+        f3 bp = xsub(p, b);
+        float d3 = xdot(ab, bp), d4 = xdot(ac, bp);
+        if (d3 >= 0.f && d4 <= d3) cp = b;
+        else {
+            float vc = xsub(xmul(d1, d4), xmul(d3, d2));
+            if (vc <= 0.f && d1 >= 0.f && d3 <= 0.f) cp = xadd(a, xscale(ab, xdiv(d1, xsub(d1, d3))));
+            else {
+                f3 cq = xsub(p, c);
+                float d5 = xdot(ab, cq), d6 = xdot(ac, cq);
+                if (d6 >= 0.f && d5 <= d6) cp = c;
+                else {
+                    float vb = xsub(xmul(d5, d2), xmul(d1, d6));
+                    if (vb <= 0.f && d2 >= 0.f && d6 <= 0.f) cp = xadd(a, xscale(ac, xdiv(d2, xsub(d2, d6))));
+                    else {
+                        float va = xsub(xmul(d3, d6), xmul(d5, d4));
+                        float e43 = xsub(d4, d3), e56 = xsub(d5, d6);
+                        if (va <= 0.f && e43 >= 0.f && e56 >= 0.f) cp = xadd(b, xscale(xsub(c, b), xdiv(e43, xadd(e43, e56))));
+                        else {
+                            float denom = xdiv(1.0f, xadd(xadd(va, vb), vc));
+                            float v = xmul(vb, denom), w = xmul(vc, denom);
+                            cp = xadd(xadd(a, xscale(ab, v)), xscale(ac, w));
+                        }
+                    }
+                }
+            }
+        }
+    }
+    return xsqrt(xnorm2(xsub(cp, p)));
+}
+
+__global__ void __launch_bounds__(TPB) k_eval(ConvertParams P) {
+    __shared__ unsigned long long s_off[TPB + 1];
+    TriCursor cur = locate(P, s_off);
+    if (!cur.valid) return;
+    const float* p = P.tris + 9 * cur.tri;
+    f3 A, B, C;
+    make_subtri(ld3(p), ld3(p + 3), ld3(p + 6), P.vs, cur.local, A, B, C);
+    int mn[3], mx[3];
+    if (!subtri_box(A, B, C, P.inv_vs, P.band, mn, mx)) return;
+    const f3 ab = xsub(B, A), ac = xsub(C, A);
+    unsigned* vals = reinterpret_cast<unsigned*>(P.values);
+    for (int bx = mn[0] >> 3; bx <= (mx[0] >> 3); ++bx)
+        for (int by = mn[1] >> 3; by <= (mx[1] >> 3); ++by)
+            for (int bz = mn[2] >> 3; bz <= (mx[2] >> 3); ++bz) {
+                unsigned slot = hash_lookup(P, bs_brick_key(bx, by, bz));
+                if (slot == 0xFFFFFFFFu) continue;  // brick not kept on this rank
+                unsigned* brick = vals + (size_t)slot * 512;
+                const int x0 = max(mn[0], bx << 3), x1 = min(mx[0], (bx << 3) + 7);
+                const int y0 = max(mn[1], by << 3), y1 = min(mx[1], (by << 3) + 7);
+                const int z0 = max(mn[2], bz << 3), z1 = min(mx[2], (bz << 3) + 7);
+                for (int x = x0; x <= x1; ++x) {
+                    const float xw = xmul((float)x, P.vs);
+                    for (int y = y0; y <= y1; ++y) {
+                        const float yw = xmul((float)y, P.vs);
+                        unsigned* line = brick + ((x & 7) << 6) + ((y & 7) << 3);
+                        for (int z = z0; z <= z1; ++z) {
+                            const float zw = xmul((float)z, P.vs);
+                            float d = point_triangle_distance(A, B, C, ab, ac, f3{xw, yw, zw});
+                            atomicMin(line + (z & 7), __float_as_uint(d));  // d >= 0 or NaN (NaN bits sort above the sentinel)
+                        }
+                    }
+                }
+            }
+}
+
+__global__ void k_fill_slots(const unsigned long long* sorted_keys, size_t n, unsigned long long* table_keys, unsigned* table_slots, unsigned mask) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long key = sorted_keys[i];
+    unsigned h = (unsigned)hash64(key) & mask;
+    while (table_keys[h] != key) h = (h + 1) & mask;
+    table_slots[h] = (unsigned)i;
+}
+
+struct NotEmptyKey { __device__ bool operator()(unsigned long long k) const { return k != BS_KEY_INVALID; } };
+
+__global__ void k_counts(const float* values, const unsigned long long* masks, size_t n_bricks, unsigned long long* out /*[2]*/) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;  // one thread per mask word
+    unsigned long long a = 0, neg = 0;
+    if (i < n_bricks * 8) {
+        unsigned long long m = masks[i];
+        a = __popcll(m);
+        const float* v = values + i * 64;
+        while (m) { int b = __ffsll((long long)m) - 1; m &= m - 1; if (__float_as_uint(v[b]) >> 31) ++neg; }
+    }
+    typedef cub::BlockReduce<unsigned long long, TPB> BR;
+    __shared__ typename BR::TempStorage t1;
+    unsigned long long sa = BR(t1).Sum(a);
+    __syncthreads();
+    unsigned long long sn = BR(t1).Sum(neg);
+    if (threadIdx.x == 0) { if (sa) atomicAdd(out, sa); if (sn) atomicAdd(out + 1, sn); }
+}
+
+}  // namespace
+
+extern "C" bs_status bs_volume_counts(const bs_volume* v, size_t* n_bricks, size_t* n_active, size_t* n_negative, size_t* n_tiles) {
+    if (!v) return BS_ERR_INVALID;
+    bs_context* ctx = v->ctx;
+    cudaSetDevice(ctx->device);
+    unsigned long long* d = nullptr; unsigned long long h[2] = {0, 0};
+    BS_TRY(bs_alloc(ctx, &d, 2));
+    BS_CUDA(ctx, cudaMemsetAsync(d, 0, 16, ctx->stream));
+    if (v->n_bricks) k_counts<<<bs_blocks(v->n_bricks * 8, TPB), TPB, 0, ctx->stream>>>(v->values, v->masks, v->n_bricks, d);
+    BS_CUDA(ctx, cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    BS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    bs_free(ctx, d);
+    if (n_bricks) *n_bricks = v->n_bricks;
+    if (n_active) *n_active = h[0];
+    if (n_negative) *n_negative = h[1];
+    if (n_tiles) *n_tiles = v->n_tiles8 + v->n_tiles128;
+    return BS_OK;
+}
+
+bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, float voxel_size, int64_t band, int rank, int world, bs_volume** out) {
+    cudaStream_t st = ctx->stream;
+    bs_marks_begin(ctx);
+    // 1. per-triangle sub-triangle counts + surface area in voxel^2 (sizing only)
+    unsigned long long *d_counts = nullptr, *d_offsets = nullptr; double* d_area = nullptr; int* d_flags = nullptr;
+    BS_TRY(bs_alloc(ctx, &d_counts, n_tris + 1)); BS_TRY(bs_alloc(ctx, &d_offsets, n_tris + 1));
+    BS_TRY(bs_alloc(ctx, &d_area, 1)); BS_TRY(bs_alloc(ctx, &d_flags, 2));
+    BS_CUDA(ctx, cudaMemsetAsync(d_area, 0, sizeof(double), st));
+    BS_CUDA(ctx, cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), st));
+    BS_CUDA(ctx, cudaMemsetAsync(d_counts + n_tris, 0, sizeof(unsigned long long), st));
+    k_tri_counts<<<bs_blocks(n_tris, TPB), TPB, 0, st>>>(d_tris, n_tris, voxel_size, d_counts, d_area);
+    void* d_tmp = nullptr; size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_counts, d_offsets, n_tris + 1, st);
+    BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp_bytes));
+    cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_counts, d_offsets, n_tris + 1, st);
+    unsigned long long total = 0; double area_vox = 0.0;
+    BS_CUDA(ctx, cudaMemcpyAsync(&total, d_offsets + n_tris, sizeof(total), cudaMemcpyDeviceToHost, st));
+    BS_CUDA(ctx, cudaMemcpyAsync(&area_vox, d_area, sizeof(double), cudaMemcpyDeviceToHost, st));
+    BS_CUDA(ctx, cudaStreamSynchronize(st));
+    bs_free(ctx, d_tmp); bs_free(ctx, d_counts); bs_free(ctx, d_area);
+    bs_mark(ctx, "subdivide_count_ms");
+    if (total == 0) { bs_free(ctx, d_offsets); bs_free(ctx, d_flags); bs_marks_end(ctx); return BS_ERR_EMPTY_MESH; }  // convert -> None (:58-60)
+    if (total > (1ull << 40)) { bs_free(ctx, d_offsets); bs_free(ctx, d_flags); return bs_fail(ctx, BS_ERR_RANGE, "%llu sub-triangles: voxel size too small for this mesh", total); }
+
+    ConvertParams P;
+    P.tris = d_tris; P.n_tris = n_tris; P.offsets = d_offsets; P.total = total;
+    P.vs = voxel_size; P.inv_vs = 1.0f / voxel_size; P.band = (int)band; P.flags = d_flags; P.values = nullptr;
+
+    // 2. mark touched bricks in a hash set; sized from the surface area, doubled on overflow
+    const double bw = (double)(2 * band + 1);
+    double est = 0.15 * area_vox * bw + 8192.0;
+    if (est > 6.0e8) est = 6.0e8;
+    size_t cap = 1; while ((double)cap < 2.0 * est) cap <<= 1;
+    unsigned long long* d_table_keys = nullptr; unsigned* d_table_slots = nullptr;
+    unsigned long long* d_keys = nullptr; size_t n_all = 0;
+    const unsigned grid = (unsigned)((total + TPB - 1) / TPB);
+    for (;;) {
+        BS_TRY(bs_alloc(ctx, &d_table_keys, cap));
+        BS_CUDA(ctx, cudaMemsetAsync(d_table_keys, 0xFF, cap * sizeof(unsigned long long), st));
+        P.table_keys = d_table_keys; P.table_slots = nullptr; P.table_mask = (unsigned)(cap - 1);
+        k_mark<<<grid, TPB, 0, st>>>(P);
+        int flags[2];
+        BS_CUDA(ctx, cudaMemcpyAsync(flags, d_flags, sizeof(flags), cudaMemcpyDeviceToHost, st));
+        BS_CUDA(ctx, cudaStreamSynchronize(st));
+        if (flags[1]) { bs_free(ctx, d_table_keys); bs_free(ctx, d_offsets); bs_free(ctx, d_flags); return bs_fail(ctx, BS_ERR_RANGE, "voxel index outside [-2^20, 2^20)"); }
+        if (!flags[0]) break;
+        bs_free(ctx, d_table_keys);
+        BS_CUDA(ctx, cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), st));
+        cap <<= 1;
+        if (cap > (1ull << 31)) { bs_free(ctx, d_offsets); bs_free(ctx, d_flags); return bs_fail(ctx, BS_ERR_RANGE, "brick hash set overflow"); }
+    }
+    bs_mark(ctx, "mark_bricks_ms");
+    // 3. compact + sort the keys (ascending key == the reference's leaf visit order)
+    {
+        unsigned long long* d_sel = nullptr; size_t* d_nsel = nullptr;
+        BS_TRY(bs_alloc(ctx, &d_sel, cap)); BS_TRY(bs_alloc(ctx, &d_nsel, 1));
+        tmp_bytes = 0;
+        cub::DeviceSelect::If(nullptr, tmp_bytes, d_table_keys, d_sel, d_nsel, cap, NotEmptyKey(), st);
+        BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp_bytes));
+        cub::DeviceSelect::If(d_tmp, tmp_bytes, d_table_keys, d_sel, d_nsel, cap, NotEmptyKey(), st);
+        BS_CUDA(ctx, cudaMemcpyAsync(&n_all, d_nsel, sizeof(size_t), cudaMemcpyDeviceToHost, st));
+        BS_CUDA(ctx, cudaStreamSynchronize(st));
+        bs_free(ctx, d_tmp); bs_free(ctx, d_nsel);
+        BS_TRY(bs_alloc(ctx, &d_keys, n_all));
+        tmp_bytes = 0;
+        cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, d_sel, d_keys, n_all, 0, 54, st);
+        BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp_bytes));
+        cub::DeviceRadixSort::SortKeys(d_tmp, tmp_bytes, d_sel, d_keys, n_all, 0, 54, st);
+        bs_free(ctx, d_tmp); bs_free(ctx, d_sel);
+    }
+    bs_volume* vol = bs_volume_new(ctx, voxel_size);
+    (void)rank; (void)world;  // brick-slab sharding: see bs_shard.cu (all bricks kept when world == 1)
+    bs_status s = bs_volume_alloc_bricks(vol, n_all);
+    if (s != BS_OK) { bs_volume_free(vol); return s; }
+    BS_CUDA(ctx, cudaMemcpyAsync(vol->keys, d_keys, n_all * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+    bs_free(ctx, d_keys);
+    BS_TRY(bs_alloc(ctx, &d_table_slots, cap));
+    BS_CUDA(ctx, cudaMemsetAsync(d_table_slots, 0xFF, cap * sizeof(unsigned), st));
+    k_fill_slots<<<bs_blocks(n_all, TPB), TPB, 0, st>>>((const unsigned long long*)vol->keys, n_all, d_table_keys, d_table_slots, (unsigned)(cap - 1));
+    BS_CUDA(ctx, cudaMemsetAsync(vol->values, 0x7F, n_all * 512 * sizeof(float), st));
+    bs_mark(ctx, "sort_bricks_ms");
+    // 4. distances
+    P.table_slots = d_table_slots; P.values = vol->values;
+    k_eval<<<grid, TPB, 0, st>>>(P);
+    bs_mark(ctx, "udf_ms");
+    bs_free(ctx, d_table_keys); bs_free(ctx, d_table_slots); bs_free(ctx, d_offsets); bs_free(ctx, d_flags);
+    // 5. signs + masks
+    s = bs_sign_impl(ctx, d_tris, n_tris, vol);
+    if (s != BS_OK) { bs_volume_free(vol); return s; }
+    BS_CUDA(ctx, cudaGetLastError());
+    bs_marks_end(ctx);
+    bs_stat_add(ctx, "n_tris", (double)n_tris);
+    bs_stat_add(ctx, "n_sub", (double)total);
+    bs_stat_add(ctx, "n_bricks", (double)n_all);
+    bs_stat_add(ctx, "area_vox", area_vox);
+    *out = vol;
+    return BS_OK;
+}

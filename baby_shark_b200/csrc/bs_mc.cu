@@ -1,0 +1,372 @@
+// Marching Cubes 33 iso-surface extraction on sorted bricks (sm_100a).
+// Replaces MarchingCubesMesher::mesh (src/voxel/meshing/marching_cubes.rs:43-63): ComputeEdgeIntersections
+// (:1013-1121), Cube::from_voxel (:1161-1181), handle_cube (:72-285), add_faces (:287-317), the face /
+// interior tests (:336-916), compute_c_vertex (:918-938); tables from lookup_table.rs via mc33_tables.h.
+//
+// The reference builds three auxiliary sparse grids of edge intersections and then walks every cell with
+// 8 root-to-leaf lookups. Here one CTA owns one brick: it stages the brick plus its +x/+y/+z halo (9^3
+// values, active bits) in shared memory, one thread classifies one cell, and edge intersections are
+// recomputed from the staged values (same f32 expression, so the same bits). Output order is the
+// reference's: bricks in key order (== leaf visit order), cells x-major inside a brick, triangles in table
+// order -- reproduced with a count pass, an exclusive scan over bricks and an emit pass that block-scans
+// the per-cell counts. All arithmetic that feeds a vertex or a branch uses the non-contracting x* helpers.
+#include "bs_common.cuh"
+#include "mc33_tables.h"
+#include <cub/cub.cuh>
+#include <cfloat>
+
+namespace {
+
+constexpr int MC_TPB = 512;
+constexpr float MIN_ABS = 1e-6f;  // MIN_ABS_VERTEX_VALUE (marching_cubes.rs:1123)
+
+__constant__ unsigned char c_iav[96] = MC33_IAV_PERM_INIT;
+__constant__ signed char c_edge_v1[12] = {0, 1, 3, 0, 4, 5, 7, 4, 0, 1, 2, 3};
+__constant__ signed char c_edge_v2[12] = {1, 2, 2, 3, 5, 6, 6, 7, 4, 5, 6, 7};
+__constant__ signed char c_edge_dir[12] = {0, 1, 0, 1, 0, 1, 0, 1, 2, 2, 2, 2};
+__constant__ signed char c_corner[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0}, {0, 0, 1}, {1, 0, 1}, {1, 1, 1}, {0, 1, 1}};
+
+struct VolView {
+    const unsigned long long* keys; const float* values; const unsigned long long* masks; size_t n;
+    const unsigned long long* t8k; const float* t8v; size_t nt8;
+    const unsigned long long* t128k; const float* t128v; size_t nt128;
+};
+
+__device__ __forceinline__ long long find_key(const unsigned long long* keys, size_t n, unsigned long long k) {
+    size_t lo = 0, hi = n;
+    while (lo < hi) { size_t mid = (lo + hi) >> 1; if (keys[mid] < k) lo = mid + 1; else hi = mid; }
+    return (lo < n && keys[lo] == k) ? (long long)lo : -1;
+}
+
+struct Cell {
+    float c[8];       // clamped corner values (Cube::from_voxel)
+    int ox, oy, oz;   // global index of corner 0
+    const signed char* T;
+    int cs, cf;
+    f3 v12;
+};
+
+__device__ __forceinline__ bool test_face(const Cell& q, int face) {  // :378-401
+    float a, b, c, d;
+    switch (face < 0 ? -face : face) {
+        case 1: a = q.c[0]; b = q.c[4]; c = q.c[5]; d = q.c[1]; break;
+        case 2: a = q.c[1]; b = q.c[5]; c = q.c[6]; d = q.c[2]; break;
+        case 3: a = q.c[2]; b = q.c[6]; c = q.c[7]; d = q.c[3]; break;
+        case 4: a = q.c[3]; b = q.c[7]; c = q.c[4]; d = q.c[0]; break;
+        case 5: a = q.c[0]; b = q.c[3]; c = q.c[2]; d = q.c[1]; break;
+        case 6: a = q.c[4]; b = q.c[7]; c = q.c[6]; d = q.c[5]; break;
+        default: return false;
+    }
+    float val = xsub(xmul(a, c), xmul(b, d));
+    if (fabsf(val) < FLT_EPSILON) return face >= 0;
+    return xmul(xmul((float)face, a), val) >= 0.f;
+}
+__device__ __forceinline__ int interior_ambiguity(const Cell& q, int amb_face, int face_i) {  // :474-538
+    const float f = (float)face_i;
+    const bool p17 = xmul(q.c[1], f) > 0.f && xmul(q.c[7], f) > 0.f, p06 = xmul(q.c[0], f) > 0.f && xmul(q.c[6], f) > 0.f;
+    const bool p35 = xmul(q.c[3], f) > 0.f && xmul(q.c[5], f) > 0.f, p24 = xmul(q.c[2], f) > 0.f && xmul(q.c[4], f) > 0.f;
+    int e = 0;
+    switch (amb_face) {
+        case 1: case 3: if (p17) e = 4; if (p06) e = 5; if (p35) e = 6; if (p24) e = 7; break;
+        case 2: case 4: if (p17) e = 0; if (p24) e = 1; if (p35) e = 2; if (p06) e = 3; break;
+        case 5: case 6: case 0: if (p06) e = 8; if (p17) e = 9; if (p24) e = 10; if (p35) e = 11; break;
+        default: break;
+    }
+    return e;
+}
+__device__ __forceinline__ int iav(const Cell& q, int edge) {  // interior_ambiguity_verification :540-916
+    const unsigned char* p = c_iav + 8 * edge;
+    const float A0 = q.c[p[0]], A1 = q.c[p[1]], B0 = q.c[p[2]], B1 = q.c[p[3]], C0 = q.c[p[4]], C1 = q.c[p[5]], D0 = q.c[p[6]], D1 = q.c[p[7]];
+    const float dA = xsub(A1, A0), dB = xsub(B1, B0), dC = xsub(C1, C0), dD = xsub(D1, D0);
+    const float a = xsub(xmul(dA, dC), xmul(dB, dD));
+    const float b = xsub(xsub(xadd(xmul(C0, dA), xmul(A0, dC)), xmul(D0, dB)), xmul(B0, dD));
+    if (a > 0.f) return 1;
+    const float t = xdiv(-b, xmul(2.0f, a));
+    if (t < 0.f || t > 1.f) return 1;
+    const float at = xadd(A0, xmul(dA, t)), bt = xadd(B0, xmul(dB, t)), ct = xadd(C0, xmul(dC, t)), dt = xadd(D0, xmul(dD, t));
+    const float verify = xsub(xmul(at, ct), xmul(bt, dt));
+    if (verify > 0.f) return 0;
+    if (verify < 0.f) return 1;
+    return 0;
+}
+#define TB(name, cfg, i) ((int)q.T[MC33_OFF_##name + (cfg) * MC33_ROW_##name + (i)])
+__device__ bool test_interior(const Cell& q, int face) {  // :403-472
+    switch (q.cs) {
+        case 4: return (iav(q, interior_ambiguity(q, 1, face)) + iav(q, interior_ambiguity(q, 2, face)) + iav(q, interior_ambiguity(q, 5, face))) != 0;
+        case 6: return iav(q, interior_ambiguity(q, abs(TB(TEST_6, q.cf, 0)), face)) != 0;
+        case 7: { const int s = -face; return (iav(q, interior_ambiguity(q, 1, s)) + iav(q, interior_ambiguity(q, 2, s)) + iav(q, interior_ambiguity(q, 5, s))) != 0; }
+        case 10: return iav(q, interior_ambiguity(q, abs(TB(TEST_10, q.cf, 0)), face)) != 0;
+        case 12: return (iav(q, interior_ambiguity(q, abs(TB(TEST_12, q.cf, 0)), face)) + iav(q, interior_ambiguity(q, abs(TB(TEST_12, q.cf, 1)), face))) != 0;
+        default: return false;
+    }
+}
+__device__ bool interior_test_case13(const Cell& q) {  // :336-376
+    const float* c = q.c;
+    const float d01 = xsub(c[0], c[1]), d76 = xsub(c[7], c[6]), d45 = xsub(c[4], c[5]), d32 = xsub(c[3], c[2]);
+    const float a = xsub(xmul(d01, d76), xmul(d45, d32));
+    const float b = xsub(xsub(xadd(xmul(c[6], d01), xmul(c[1], d76)), xmul(c[2], d45)), xmul(c[5], d32));
+    const float cc = xsub(xmul(c[1], c[6]), xmul(c[5], c[2]));
+    const float delta = xsub(xmul(b, b), xmul(xmul(4.0f, a), cc));
+    const float sq = xsqrt(delta), a2 = xadd(a, a);
+    const float t1 = xdiv(xadd(-b, sq), a2), t2 = xdiv(xsub(-b, sq), a2);
+    if (t1 < 1.f && t1 > 0.f && t2 < 1.f && t2 > 0.f) {
+        float xy[4];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const float t = k ? t2 : t1;
+            const float at = xadd(c[1], xmul(d01, t)), bt = xadd(c[5], xmul(d45, t)), ct = xadd(c[6], xmul(d76, t)), dt = xadd(c[2], xmul(d32, t));
+            const float den = xsub(xsub(xadd(at, ct), bt), dt);
+            xy[2 * k] = xdiv(xsub(at, dt), den); xy[2 * k + 1] = xdiv(xsub(at, bt), den);
+        }
+        return !(xy[0] < 1.f && xy[0] > 0.f && xy[2] < 1.f && xy[2] > 0.f && xy[1] < 1.f && xy[1] > 0.f && xy[3] < 1.f && xy[3] > 0.f);
+    }
+    return true;
+}
+
+// handle_cube (:72-285): pick the tiling row for this cell. Returns the blob offset, its length in `len`
+// and whether the interior c-vertex is needed.
+#define ROW1(name, cfg) (len = MC33_ROW_##name, MC33_OFF_##name + (cfg) * MC33_ROW_##name)
+#define ROW2(name, cfg, sub) (len = MC33_ROW_##name, MC33_OFF_##name + ((cfg) * MC33_SUB_##name + (sub)) * MC33_ROW_##name)
+__device__ int select_tiling(const Cell& q, int& len, bool& need_c) {
+    const int cf = q.cf;
+    need_c = false; len = 0;
+    switch (q.cs) {
+        case 1: return ROW1(TILING_1, cf);
+        case 2: return ROW1(TILING_2, cf);
+        case 3: return test_face(q, q.T[MC33_OFF_TEST_3 + cf]) ? ROW1(TILING_3_2, cf) : ROW1(TILING_3_1, cf);
+        case 4: return test_interior(q, q.T[MC33_OFF_TEST_4 + cf]) ? ROW1(TILING_4_1, cf) : ROW1(TILING_4_2, cf);
+        case 5: return ROW1(TILING_5, cf);
+        case 6:
+            if (test_face(q, TB(TEST_6, cf, 0))) return ROW1(TILING_6_2, cf);
+            return test_interior(q, TB(TEST_6, cf, 1)) ? ROW1(TILING_6_1_1, cf) : ROW1(TILING_6_1_2, cf);
+        case 7: {
+            int sub = 0;
+            if (test_face(q, TB(TEST_7, cf, 0))) sub += 1;
+            if (test_face(q, TB(TEST_7, cf, 1))) sub += 2;
+            if (test_face(q, TB(TEST_7, cf, 2))) sub += 4;
+            switch (sub) {
+                case 0: return ROW1(TILING_7_1, cf);
+                case 1: return ROW2(TILING_7_2, cf, 0);
+                case 2: return ROW2(TILING_7_2, cf, 1);
+                case 3: need_c = true; return ROW2(TILING_7_3, cf, 0);
+                case 4: return ROW2(TILING_7_2, cf, 2);
+                case 5: need_c = true; return ROW2(TILING_7_3, cf, 1);
+                case 6: need_c = true; return ROW2(TILING_7_3, cf, 2);
+                default: return test_interior(q, TB(TEST_7, cf, 3)) ? ROW1(TILING_7_4_1, cf) : ROW1(TILING_7_4_2, cf);
+            }
+        }
+        case 8: return ROW1(TILING_8, cf);
+        case 9: return ROW1(TILING_9, cf);
+        case 10:
+            if (test_face(q, TB(TEST_10, cf, 0))) {
+                if (test_face(q, TB(TEST_10, cf, 1))) return test_interior(q, -TB(TEST_10, cf, 2)) ? ROW1(TILING_10_1_1_, cf) : ROW1(TILING_10_1_2, 5 - cf);
+                need_c = true; return ROW1(TILING_10_2, cf);
+            }
+            if (test_face(q, TB(TEST_10, cf, 1))) { need_c = true; return ROW1(TILING_10_2_, cf); }
+            return test_interior(q, TB(TEST_10, cf, 2)) ? ROW1(TILING_10_1_1, cf) : ROW1(TILING_10_1_2, cf);
+        case 11: return ROW1(TILING_11, cf);
+        case 12:
+            if (test_face(q, TB(TEST_12, cf, 0))) {
+                if (test_face(q, TB(TEST_12, cf, 1))) return test_interior(q, -TB(TEST_12, cf, 2)) ? ROW1(TILING_12_1_1_, cf) : ROW1(TILING_12_1_2, 23 - cf);
+                need_c = true; return ROW1(TILING_12_2, cf);
+            }
+            if (test_face(q, TB(TEST_12, cf, 1))) { need_c = true; return ROW1(TILING_12_2_, cf); }
+            return test_interior(q, TB(TEST_12, cf, 2)) ? ROW1(TILING_12_1_1, cf) : ROW1(TILING_12_1_2, cf);
+        case 13: {
+            int sub = 0;
+            for (int i = 0; i < 6; ++i) if (test_face(q, TB(TEST_13, cf, i))) sub += 1 << i;
+            const int sc = q.T[MC33_OFF_SUB_CONFIG_13 + sub];
+            if (sc == 0) return ROW1(TILING_13_1, cf);
+            if (sc >= 1 && sc <= 6) return ROW2(TILING_13_2, cf, sc - 1);
+            if (sc >= 7 && sc <= 18) { need_c = true; return ROW2(TILING_13_3, cf, sc - 7); }
+            if (sc >= 19 && sc <= 22) { need_c = true; return ROW2(TILING_13_4, cf, sc - 19); }
+            if (sc >= 23 && sc <= 26) {
+                const bool in = interior_test_case13(q);
+                if (cf == 0) return in ? ROW2(TILING_13_5_1, 0, sc - 23) : ROW2(TILING_13_5_2, 1, sc - 23);
+                return in ? ROW2(TILING_13_5_1, 1, sc - 23) : ROW2(TILING_13_5_2, 0, sc - 23);
+            }
+            if (sc >= 27 && sc <= 38) { need_c = true; return ROW2(TILING_13_3_, cf, sc - 27); }
+            if (sc >= 39 && sc <= 44) return ROW2(TILING_13_2_, cf, sc - 39);
+            if (sc == 45) return ROW1(TILING_13_1_, cf);
+            return 0;
+        }
+        case 14: return ROW1(TILING_14, cf);
+        default: return 0;
+    }
+}
+
+// MarchingCubesMesher::intersection (:320-334) with the x/y/z_int value recomputed (:1054-1079).
+// Index-space point; false when the reference's aux grid has no entry (no sign change on the edge).
+__device__ __forceinline__ bool edge_point(const Cell& q, int e, f3& out) {
+    if (e == 12) { out = q.v12; return true; }
+    const int v1 = c_edge_v1[e], v2 = c_edge_v2[e];
+    const float a = q.c[v1], b = q.c[v2];
+    if ((__float_as_uint(a) ^ __float_as_uint(b)) >> 31 == 0) return false;
+    const float fa = fabsf(a), fb = fabsf(b);  // already >= MIN_ABS
+    const float t = xdiv(fa, xadd(fa, fb));
+    const int ix = q.ox + c_corner[v1][0], iy = q.oy + c_corner[v1][1], iz = q.oz + c_corner[v1][2];
+    out = f3{(float)ix, (float)iy, (float)iz};
+    const int dir = c_edge_dir[e];
+    if (dir == 0) out.x = xadd(out.x, t); else if (dir == 1) out.y = xadd(out.y, t); else out.z = xadd(out.z, t);
+    return true;
+}
+__device__ void compute_c_vertex(Cell& q) {  // :918-938
+    f3 sum{0.f, 0.f, 0.f}; int count = 0;
+    for (int e = 0; e < 12; ++e) { f3 p; if (edge_point(q, e, p)) { sum = xadd(sum, p); ++count; } }
+    const float n = (float)count;
+    q.v12 = f3{xdiv(sum.x, n), xdiv(sum.y, n), xdiv(sum.z, n)};
+}
+
+// add_faces (:287-317). WRITE = false: count only.
+template <bool WRITE>
+__device__ int emit_cell(Cell& q, float vs, float* out) {
+    int len; bool need_c;
+    const int row = select_tiling(q, len, need_c);
+    if (len == 0) return 0;
+    if (need_c) compute_c_vertex(q);
+    int n = 0;
+    for (int i = 0; i + 2 < len; i += 3) {
+        const int e1 = q.T[row + i], e3 = q.T[row + i + 1], e2 = q.T[row + i + 2];
+        f3 v1, v2, v3;
+        if (!edge_point(q, e1, v1) || !edge_point(q, e2, v2) || !edge_point(q, e3, v3)) continue;
+        v1 = xscale(v1, vs); v2 = xscale(v2, vs); v3 = xscale(v3, vs);
+        if (xnorm2(xcross(xsub(v2, v1), xsub(v3, v1))) == 0.f) continue;  // Triangle3::is_degenerate
+        if (WRITE) {
+            float* o = out + 9 * n;
+            o[0] = v1.x; o[1] = v1.y; o[2] = v1.z; o[3] = v2.x; o[4] = v2.y; o[5] = v2.z; o[6] = v3.x; o[7] = v3.y; o[8] = v3.z;
+        }
+        ++n;
+    }
+    return n;
+}
+
+// Stage brick b and its +x/+y/+z halo: 9^3 values and active flags.
+__device__ void stage_brick(const VolView& V, size_t b, float* s_val /*729*/, unsigned char* s_act /*729*/, long long* s_nb /*8*/, int* s_org /*3*/) {
+    const unsigned tid = threadIdx.x;
+    if (tid < 8) {
+        int bx, by, bz; bs_key_brick(V.keys[b], bx, by, bz);
+        if (tid == 0) { s_nb[0] = (long long)b; s_org[0] = bx << 3; s_org[1] = by << 3; s_org[2] = bz << 3; }
+        else s_nb[tid] = find_key(V.keys, V.n, bs_brick_key(bx + (tid & 1), by + ((tid >> 1) & 1), bz + ((tid >> 2) & 1)));
+    }
+    __syncthreads();
+    for (unsigned i = tid; i < 729; i += blockDim.x) {
+        const unsigned x = i / 81, y = (i / 9) % 9, z = i % 9;
+        const unsigned nb = (x >> 3) | ((y >> 3) << 1) | ((z >> 3) << 2);
+        const long long src = s_nb[nb];
+        const unsigned off = ((x & 7) << 6) | ((y & 7) << 3) | (z & 7);
+        float v = 0.f; unsigned char a = 0;
+        if (src >= 0) {
+            a = (V.masks[src * 8 + (off >> 6)] >> (off & 63)) & 1;
+            v = V.values[src * 512 + off];
+        } else if (V.nt8 | V.nt128) {
+            // active tile fallback (only CSG creates tiles): TreeNode::at returns the tile value
+            int bx = (s_org[0] >> 3) + (int)(x >> 3), by = (s_org[1] >> 3) + (int)(y >> 3), bz = (s_org[2] >> 3) + (int)(z >> 3);
+            const unsigned long long k = bs_brick_key(bx, by, bz);
+            long long t = V.nt8 ? find_key(V.t8k, V.nt8, k) : -1;
+            if (t >= 0) { a = 1; v = V.t8v[t]; }
+            else { t = V.nt128 ? find_key(V.t128k, V.nt128, k >> 12) : -1; if (t >= 0) { a = 1; v = V.t128v[t]; } }
+        }
+        s_val[i] = v; s_act[i] = a;
+    }
+    __syncthreads();
+}
+
+// Cube::from_voxel (:1161-1181) for the cell whose corner 0 is local (x,y,z)
+__device__ __forceinline__ bool load_cell(Cell& q, const float* s_val, const unsigned char* s_act, const int* s_org, unsigned x, unsigned y, unsigned z, int& id) {
+    id = 0;
+    bool all = true;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const unsigned j = (x + c_corner[i][0]) * 81 + (y + c_corner[i][1]) * 9 + (z + c_corner[i][2]);
+        all = all && s_act[j];
+        float v = s_val[j];
+        if (fabsf(v) < MIN_ABS) v = copysignf(MIN_ABS, v);
+        if (v < 0.f) id |= 1 << i;
+        q.c[i] = v;
+    }
+    q.ox = s_org[0] + (int)x; q.oy = s_org[1] + (int)y; q.oz = s_org[2] + (int)z;
+    return all;
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(MC_TPB) k_mc(VolView V, const signed char* __restrict__ tables, float vs,
+                                                unsigned* brick_counts, const unsigned long long* __restrict__ brick_offsets, float* out) {
+    __shared__ float s_val[729];
+    __shared__ unsigned char s_act[732];
+    __shared__ long long s_nb[8];
+    __shared__ int s_org[3];
+    const size_t b = blockIdx.x;
+    if (WRITE) { if (brick_offsets[b + 1] == brick_offsets[b]) return; }  // uniform per block
+    stage_brick(V, b, s_val, s_act, s_nb, s_org);
+    const unsigned tid = threadIdx.x;  // == leaf offset x<<6 | y<<3 | z of the cell's corner 0
+    Cell q; q.T = tables; q.v12 = f3{0.f, 0.f, 0.f};
+    int id;
+    int n = 0;
+    float local[WRITE ? 12 * 9 : 1];
+    if (load_cell(q, s_val, s_act, s_org, tid >> 6, (tid >> 3) & 7, tid & 7, id) && id != 0 && id != 255) {
+        q.cs = tables[MC33_OFF_CASES + 2 * id]; q.cf = tables[MC33_OFF_CASES + 2 * id + 1];
+        n = emit_cell<WRITE>(q, vs, local);
+    }
+    typedef cub::BlockScan<int, MC_TPB> Scan;
+    __shared__ typename Scan::TempStorage tmp;
+    int excl, total;
+    Scan(tmp).ExclusiveSum(n, excl, total);
+    if (!WRITE) { if (tid == 0) brick_counts[b] = (unsigned)total; return; }
+    float* dst = out + (brick_offsets[b] + (unsigned long long)excl) * 9;
+    for (int i = 0; i < n * 9; ++i) dst[i] = local[i];
+}
+
+__global__ void k_widen(const unsigned* in, unsigned long long* out, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
+    if (i == n) out[i] = 0;
+}
+
+}  // namespace
+
+bs_status bs_ensure_out_verts(bs_context* ctx, size_t n_floats) {
+    if (ctx->out_verts_cap < n_floats) {
+        if (ctx->d_out_verts) cudaFree(ctx->d_out_verts);
+        ctx->d_out_verts = nullptr; ctx->out_verts_cap = 0;
+        size_t cap = n_floats + n_floats / 4 + 1024;
+        BS_CUDA(ctx, cudaMalloc((void**)&ctx->d_out_verts, cap * sizeof(float)));
+        ctx->out_verts_cap = cap;
+    }
+    return BS_OK;
+}
+
+bs_status bs_mc_impl(const bs_volume* v, float voxel_size, const float** d_verts, size_t* n_verts) {
+    bs_context* ctx = v->ctx;
+    cudaStream_t st = ctx->stream;
+    *d_verts = nullptr; *n_verts = 0;
+    bs_marks_begin(ctx);
+    if (v->n_tiles8 || v->n_tiles128) return bs_fail(ctx, BS_ERR_UNSUPPORTED, "marching cubes over active tiles is not implemented on the device yet");
+    const size_t n = v->n_bricks;
+    if (n == 0) { bs_marks_end(ctx); return BS_OK; }
+    VolView V{(const unsigned long long*)v->keys, v->values, (const unsigned long long*)v->masks, n,
+              (const unsigned long long*)v->tile8_keys, v->tile8_values, v->n_tiles8,
+              (const unsigned long long*)v->tile128_keys, v->tile128_values, v->n_tiles128};
+    unsigned* d_counts = nullptr; unsigned long long *d_wide = nullptr, *d_off = nullptr;
+    BS_TRY(bs_alloc(ctx, &d_counts, n)); BS_TRY(bs_alloc(ctx, &d_wide, n + 1)); BS_TRY(bs_alloc(ctx, &d_off, n + 1));
+    k_mc<false><<<(unsigned)n, MC_TPB, 0, st>>>(V, (const signed char*)ctx->d_mc33, voxel_size, d_counts, nullptr, nullptr);
+    k_widen<<<bs_blocks(n + 1, 256), 256, 0, st>>>(d_counts, d_wide, n);
+    void* d_tmp = nullptr; size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_wide, d_off, n + 1, st);
+    BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp_bytes));
+    cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_wide, d_off, n + 1, st);
+    unsigned long long n_tris = 0;
+    BS_CUDA(ctx, cudaMemcpyAsync(&n_tris, d_off + n, sizeof(n_tris), cudaMemcpyDeviceToHost, st));
+    BS_CUDA(ctx, cudaStreamSynchronize(st));
+    bs_mark(ctx, "mc_count_ms");
+    bs_status s = bs_ensure_out_verts(ctx, (size_t)n_tris * 9);
+    if (s == BS_OK && n_tris) k_mc<true><<<(unsigned)n, MC_TPB, 0, st>>>(V, (const signed char*)ctx->d_mc33, voxel_size, nullptr, d_off, ctx->d_out_verts);
+    bs_mark(ctx, "mc_emit_ms");
+    bs_free(ctx, d_tmp); bs_free(ctx, d_counts); bs_free(ctx, d_wide); bs_free(ctx, d_off);
+    if (s != BS_OK) return s;
+    BS_CUDA(ctx, cudaGetLastError());
+    bs_marks_end(ctx);
+    bs_stat_add(ctx, "n_bricks", (double)n);
+    bs_stat_add(ctx, "n_out_tris", (double)n_tris);
+    *d_verts = ctx->d_out_verts; *n_verts = (size_t)n_tris * 3;
+    return BS_OK;
+}

@@ -1,0 +1,130 @@
+/* bshark.h -- C ABI of libbshark_cuda.so: the B200 (sm_100a) implementation of baby_shark's
+ * implicit-modelling hot path (mesh -> narrow-band SDF -> CSG / offset -> iso-surface extraction).
+ *
+ * The reference (Rust crate baby_shark 0.3.12) has no FFI for this path; these entry points are what a
+ * drop-in `voxel` module binds instead of its CPU implementation.  Each one cites the reference
+ * interface it replaces (paths under the reference checkout).  INTEGRATION.md shows the Rust shim.
+ *
+ * Conventions
+ *  - Opaque handles own device memory.  `bs_volume` lives on the device between calls; host<->device
+ *    copies happen only for triangles in (bs_mesh_to_volume) and vertices out (bs_mesh_mc / bs_mesh_dc).
+ *  - Consuming operations mirror Rust move semantics: inputs marked "consumed" are freed by the call,
+ *    whether it succeeds or not, and must not be used again.
+ *  - Every call is synchronous at return and never throws or unwinds across the ABI.
+ *  - `bs_status` 0 = ok.  The shim maps BS_ERR_EMPTY_MESH to `None` (reference returns None) and
+ *    BS_ERR_REFERENCE_PANICS to a panic (the reference `todo!()` / `unwrap()` / `unreachable!()`s there).
+ *  - There is NO CPU fallback: without a CUDA device every entry point returns BS_ERR_NO_DEVICE.
+ *  - Voxel indices must lie in [-2^20, 2^20) per axis (BS_ERR_RANGE otherwise); the reference is
+ *    unbounded (isize indices, BTreeMap root).
+ *  - One in-flight call per context; handles may move between host threads.
+ */
+#ifndef BSHARK_H
+#define BSHARK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bs_context bs_context;
+typedef struct bs_volume bs_volume;
+typedef int bs_status;
+
+enum {
+    BS_OK = 0,
+    BS_ERR_EMPTY_MESH = 1,       /* MeshToVolume::convert -> None (mesh_to_volume.rs:58-60) */
+    BS_ERR_CUDA = 2,             /* CUDA runtime error; see bs_last_error */
+    BS_ERR_INVALID = 3,          /* null handle / bad argument / volumes from different contexts */
+    BS_ERR_REFERENCE_PANICS = 4, /* input on which the reference panics (tiles in DC / offset, ...) */
+    BS_ERR_RANGE = 5,            /* voxel index outside [-2^20, 2^20) */
+    BS_ERR_NO_DEVICE = 6,        /* no CUDA device / not an sm_100 device: there is no CPU fallback */
+    BS_ERR_UNSUPPORTED = 7       /* defined in the reference but not implemented on the device yet */
+};
+
+/* ---- context ------------------------------------------------------------------------------------- */
+/* One CUDA device, one stream, one stream-ordered memory pool.  device = -1 uses the current device. */
+bs_status bs_context_create(int device, bs_context** out);
+void bs_context_destroy(bs_context* ctx);
+const char* bs_last_error(const bs_context* ctx);
+int bs_context_device(const bs_context* ctx);
+/* The context's stream as a cudaStream_t (void* to keep CUDA headers out of the ABI). */
+void* bs_context_stream(const bs_context* ctx);
+
+/* ---- mesh -> volume ------------------------------------------------------------------------------- */
+/* Replaces MeshToVolume::convert (src/voxel/mesh_to_volume.rs:52-73) with voxel_size / band_width from
+ * with_voxel_size / with_narrow_band_width (:28-50).  `tris` = n x 9 host floats (p1,p2,p3 per triangle,
+ * the order `Triangles::triangles()` yields, src/mesh/traits.rs:4-8). */
+bs_status bs_mesh_to_volume(bs_context* ctx, const float* tris, size_t n_tris, float voxel_size,
+                            int64_t band_width, bs_volume** out);
+/* Same, triangles already resident on the context's device (n x 9 floats). */
+bs_status bs_mesh_to_volume_device(bs_context* ctx, const float* d_tris, size_t n_tris, float voxel_size,
+                                   int64_t band_width, bs_volume** out);
+/* Brick-sharded variant for multi-GPU runs: the mesh is replicated, rank r of `world` keeps the r-th
+ * contiguous slab of the brick list (in the reference's leaf visit order) plus the +x/+y/+z halo bricks
+ * extraction needs; `owned_bricks` receives how many leading... see DESIGN.md "Multi-GPU". */
+bs_status bs_mesh_to_volume_sharded(bs_context* ctx, const float* d_tris, size_t n_tris, float voxel_size,
+                                    int64_t band_width, int rank, int world, bs_volume** out);
+
+/* ---- volume --------------------------------------------------------------------------------------- */
+/* Volume::from_fn backing (src/voxel/volume/mod.rs:40-72): the shim evaluates the closure on the host
+ * exactly as :53-67 and passes the kept voxels (m x 3 indices, m values). */
+bs_status bs_volume_from_voxels(bs_context* ctx, const int32_t* ijk, const float* values, size_t m,
+                                float voxel_size, bs_volume** out);
+/* Volume::with_voxel_size (volume/mod.rs:18-24): empty volume. */
+bs_status bs_volume_empty(bs_context* ctx, float voxel_size, bs_volume** out);
+/* VolumeBuilder::{sphere,cuboid,iwp} (src/voxel/volume/builder.rs:21-76), evaluated on the device. */
+bs_status bs_volume_sphere(bs_context* ctx, float voxel_size, float radius, const float origin[3], bs_volume** out);
+bs_status bs_volume_cuboid(bs_context* ctx, float voxel_size, const float min[3], const float max[3], bs_volume** out);
+bs_status bs_volume_iwp(bs_context* ctx, float voxel_size, const float min[3], const float max[3], float cell_size,
+                        bs_volume** out);
+/* impl Clone for Volume (volume/mod.rs:116-123) */
+bs_status bs_volume_clone(const bs_volume* v, bs_volume** out);
+void bs_volume_free(bs_volume* v);
+/* Volume::voxel_size (volume/mod.rs:31-34) */
+float bs_volume_voxel_size(const bs_volume* v);
+
+/* Volume::{union,subtract,intersect}(self, other) -> Self (volume/mod.rs:74-93): flood-fill both, then CSG.
+ * Both inputs are consumed. */
+bs_status bs_volume_union(bs_volume* self_consumed, bs_volume* other_consumed, bs_volume** out);
+bs_status bs_volume_subtract(bs_volume* self_consumed, bs_volume* other_consumed, bs_volume** out);
+bs_status bs_volume_intersect(bs_volume* self_consumed, bs_volume* other_consumed, bs_volume** out);
+/* Volume::offset(self, distance) -> Self (volume/mod.rs:95-108). Input consumed. */
+bs_status bs_volume_offset(bs_volume* self_consumed, float distance, bs_volume** out);
+
+/* ---- extraction ----------------------------------------------------------------------------------- */
+/* MarchingCubesMesher::mesh (src/voxel/meshing/marching_cubes.rs:43-63) with with_voxel_size (:32-36):
+ * returns the vertex soup, 3 consecutive xyz per triangle, in the reference's emission order.
+ * *verts is library-owned host memory (bs_buffer_free). */
+bs_status bs_mesh_mc(const bs_volume* v, float voxel_size, float** verts, size_t* n_verts);
+/* DualContouringMesher::mesh (src/voxel/meshing/dual_contouring.rs:23-83). The reference's output order is
+ * nondeterministic (rayon + Mutex); this returns leaves in visit order. BS_ERR_REFERENCE_PANICS where the
+ * reference hits todo!() (active tiles) or unreachable!() (:340). */
+bs_status bs_mesh_dc(const bs_volume* v, float voxel_size, float** verts, size_t* n_verts);
+/* Same, leaving the vertices on the device: *d_verts is a device pointer (n_verts x 3 floats) owned by the
+ * context and valid until the next extraction call on the same context or bs_context_destroy. */
+bs_status bs_mesh_mc_device(const bs_volume* v, float voxel_size, const float** d_verts, size_t* n_verts);
+bs_status bs_mesh_dc_device(const bs_volume* v, float voxel_size, const float** d_verts, size_t* n_verts);
+void bs_buffer_free(void* p);
+
+/* ---- parity / debug -------------------------------------------------------------------------------- */
+/* Leaves in the reference's visit order (root map order, ascending child offsets).  brick_ijk = leaf
+ * origins (n x 3), values = n x 512 in the reference's leaf layout (x<<6 | y<<3 | z, leaf_node/mod.rs:29-36),
+ * masks = n x 8 words, bit (o & 63) of word (o >> 6) = voxel o active.  Active tiles (only CSG creates them)
+ * come back as origin / edge length in voxels / value.  All buffers are library-owned host memory. */
+bs_status bs_volume_download(const bs_volume* v, int32_t** brick_ijk, float** values, uint64_t** masks,
+                             size_t* n_bricks, int32_t** tile_ijk, int32_t** tile_size, float** tile_values,
+                             size_t* n_tiles);
+/* counts only: bricks, active voxels, negative active voxels, active tiles */
+bs_status bs_volume_counts(const bs_volume* v, size_t* n_bricks, size_t* n_active, size_t* n_negative,
+                           size_t* n_tiles);
+
+/* Per-stage device timings (ms, CUDA events on the context stream) and work counters of the most recent
+ * call on the context; names are listed in DESIGN.md.  Returns the number of entries written (<= cap). */
+size_t bs_context_last_stats(const bs_context* ctx, const char** names, double* values, size_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BSHARK_H */

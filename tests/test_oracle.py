@@ -1,0 +1,88 @@
+"""CPU tests (-m "not gpu"): the oracle against the reference's own known answers and golden fixtures."""
+import json
+import os
+
+import numpy as np
+
+from conftest import GOLDEN
+
+KA = json.load(open(os.path.join(GOLDEN, "reference_known_answers.json")))
+
+
+def test_reference_unit_tests_restated(oracle):
+    # leaf CSG known answers, leaf/internal/root flood fill, tree insert/remove/fill (see bs_oracle.cpp:bso_selftest)
+    assert oracle.selftest() == 0
+
+
+def test_volume_offset_known_answer(oracle, box2):
+    # src/voxel/volume/mod.rs:134-152 : box2.stl @0.2 -> offset(0.5) -> MC -> 7944 vertices
+    ka, mid = KA["test_volume_offset"], KA["survey_intermediates"]
+    vol, st = oracle.mesh_to_volume(box2, ka["voxel_size"])
+    assert st["n_sub"] == mid["n_sub"]
+    c = vol.counts()
+    assert (c["active"], c["leaves"], c["negative"]) == (mid["convert_active"], mid["convert_leaves"], mid["convert_negative"])
+    vol.offset(ka["offset"])
+    c = vol.counts()
+    assert (c["active"], c["leaves"]) == (mid["offset_active"], mid["offset_leaves"])
+    verts, stats = oracle.marching_cubes(vol, with_stats=True)
+    assert verts.shape[0] == ka["mc_vertices"]
+    hist = {str(i): int(n) for i, n in enumerate(stats.case_hist) if n}
+    assert hist == mid["mc_case_hist"]
+
+
+def test_voxel_remeshing_cube(oracle):
+    # src/remeshing/voxel.rs:105-112 : unit cube @0.1 -> faces > 0
+    from baby_shark_b200 import synth
+    vol, _ = oracle.mesh_to_volume(synth.cube(), 0.1)
+    assert oracle.marching_cubes(vol).shape[0] > 0
+
+
+def test_empty_mesh_is_none(oracle):
+    vol, _ = oracle.mesh_to_volume(np.zeros((0, 9), np.float32), 0.1)
+    assert vol is None
+
+
+def test_closed_mesh_is_watertight(oracle):
+    # invariant: a closed input gives a closed MC output -- every edge is shared by exactly 2 triangles
+    from baby_shark_b200 import synth
+    tris = synth.uv_sphere(24, 12, 0.4, (0.53, 0.54, 0.55))
+    vol, _ = oracle.mesh_to_volume(tris, 1.0 / 32)
+    v = oracle.marching_cubes(vol)
+    t = v.reshape(-1, 3, 3)
+    uniq, inv = np.unique(v.view(np.uint32).reshape(-1, 3), axis=0, return_inverse=True)
+    f = inv.reshape(-1, 3)
+    e = np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]])
+    e.sort(axis=1)
+    _, counts = np.unique(e, axis=0, return_counts=True)
+    assert t.shape[0] > 100 and (counts == 2).all()
+
+
+def test_union_with_self_is_identity_on_band(oracle):
+    from baby_shark_b200 import synth
+    a, _ = oracle.mesh_to_volume(synth.uv_sphere(24, 12, 0.4, (0.5, 0.5, 0.5)), 1.0 / 32)
+    before = a.clone().download()
+    u = a.clone().union(a.clone()).download()
+    from util import active_mask_bits
+    ba, ua = active_mask_bits(before["masks"]), active_mask_bits(u["masks"])
+    assert np.array_equal(before["origins"], u["origins"]) and np.array_equal(ba, ua)
+    assert np.array_equal(before["values"][ba], u["values"][ua])
+
+
+def test_builders_and_csg_dc(oracle):
+    # examples/dual_contouring.rs:11-18 at a coarser voxel: cuboid.subtract(sphere) -> DC gives a mesh
+    cube = oracle.cuboid(0.5, (0, 0, 0), (10, 10, 10))
+    sph = oracle.sphere(0.5, 3.0, (8, 8, 8))
+    v = oracle.dual_contouring(cube.subtract(sph))
+    assert v is not None and v.shape[0] > 0 and v.shape[0] % 3 == 0
+
+
+def test_offset_roundtrip_in_band(oracle):
+    # offset(+d) then offset(-d) returns the original surface to within a fraction of a voxel (SURVEY 8c invariant)
+    from baby_shark_b200 import synth
+    vs = 1.0 / 32
+    a, _ = oracle.mesh_to_volume(synth.uv_sphere(32, 16, 0.3, (0.5, 0.5, 0.5)), vs)
+    v0 = oracle.marching_cubes(a.clone())
+    v1 = oracle.marching_cubes(a.offset(2 * vs).offset(-2 * vs))
+    r0 = np.linalg.norm(v0 - 0.5, axis=1).mean()
+    r1 = np.linalg.norm(v1 - 0.5, axis=1).mean()
+    assert abs(r0 - r1) < 0.5 * vs
