@@ -82,6 +82,9 @@ struct bs_context {
     size_t out_verts_cap = 0;
     // stage timing
     std::vector<std::pair<const char*, cudaEvent_t>> marks;
+    // BS_FLAG_COUNT_WORK: instrumented winding-number traversal (node visits, far evals, exact triangles, voxels)
+    int count_work = 0;
+    double fwn_counts[6] = {0, 0, 0, 0, 0, 0};  // lane visits, far evals, exact tris, voxels, warp-level visits, traversals
 };
 
 struct bs_volume {

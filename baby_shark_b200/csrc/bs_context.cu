@@ -102,6 +102,19 @@ void bs_context_destroy(bs_context* ctx) {
 const char* bs_last_error(const bs_context* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 int bs_context_device(const bs_context* ctx) { return ctx ? ctx->device : -1; }
 void* bs_context_stream(const bs_context* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+bs_status bs_context_set_flag(bs_context* ctx, int flag, int value) {
+    if (!ctx) return BS_ERR_INVALID;
+    if (flag == BS_FLAG_COUNT_WORK) { ctx->count_work = value; return BS_OK; }
+    return BS_ERR_INVALID;
+}
+bs_status bs_context_copy_out_verts(bs_context* ctx, float* dst, size_t n_floats) {
+    if (!ctx || (!dst && n_floats)) return BS_ERR_INVALID;
+    if (n_floats > ctx->out_verts_cap) return bs_fail(ctx, BS_ERR_INVALID, "no extraction result of that size on the device");
+    cudaSetDevice(ctx->device);
+    if (n_floats) BS_CUDA(ctx, cudaMemcpyAsync(dst, ctx->d_out_verts, n_floats * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    BS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BS_OK;
+}
 size_t bs_context_last_stats(const bs_context* ctx, const char** names, double* values, size_t cap) {
     if (!ctx) return 0;
     size_t n = ctx->stats.size() < cap ? ctx->stats.size() : cap;

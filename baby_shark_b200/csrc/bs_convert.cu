@@ -31,6 +31,7 @@ struct ConvertParams {
     unsigned long long* table_keys; unsigned* table_slots; unsigned table_mask;
     float* values;
     int* flags;  // [0] hash overflow, [1] index range error
+    unsigned long long* n_eval;  // sum of box volumes = point-triangle evaluations (roofline work counter)
 };
 
 __device__ __forceinline__ unsigned long long hash64(unsigned long long k) {
@@ -163,12 +164,18 @@ __device__ __forceinline__ unsigned hash_lookup(const ConvertParams& P, unsigned
 __global__ void __launch_bounds__(TPB) k_mark(ConvertParams P) {
     __shared__ unsigned long long s_off[TPB + 1];
     TriCursor c = locate(P, s_off);
-    if (!c.valid) return;
-    const float* p = P.tris + 9 * c.tri;
-    f3 A, B, C;
-    make_subtri(ld3(p), ld3(p + 3), ld3(p + 6), P.vs, c.local, A, B, C);
-    int mn[3], mx[3];
-    if (!subtri_box(A, B, C, P.inv_vs, P.band, mn, mx)) { P.flags[1] = 1; return; }
+    unsigned long long vol = 0;
+    int mn[3] = {0, 0, 0}, mx[3] = {-1, -1, -1};
+    if (c.valid) {
+        const float* p = P.tris + 9 * c.tri;
+        f3 A, B, C;
+        make_subtri(ld3(p), ld3(p + 3), ld3(p + 6), P.vs, c.local, A, B, C);
+        if (!subtri_box(A, B, C, P.inv_vs, P.band, mn, mx)) { P.flags[1] = 1; mx[0] = mn[0] - 1; }
+        else vol = (unsigned long long)(mx[0] - mn[0] + 1) * (unsigned long long)(mx[1] - mn[1] + 1) * (unsigned long long)(mx[2] - mn[2] + 1);
+    }
+    for (int o = 16; o; o >>= 1) vol += __shfl_xor_sync(0xFFFFFFFFu, vol, o);
+    if ((threadIdx.x & 31) == 0 && vol) atomicAdd(P.n_eval, vol);
+    if (!c.valid || mx[0] < mn[0]) return;
     for (int bx = mn[0] >> 3; bx <= (mx[0] >> 3); ++bx)
         for (int by = mn[1] >> 3; by <= (mx[1] >> 3); ++by)
             for (int bz = mn[2] >> 3; bz <= (mx[2] >> 3); ++bz) hash_insert(P, bs_brick_key(bx, by, bz));
@@ -301,6 +308,8 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
     unsigned long long *d_counts = nullptr, *d_offsets = nullptr; double* d_area = nullptr; int* d_flags = nullptr;
     BS_TRY(bs_alloc(ctx, &d_counts, n_tris + 1)); BS_TRY(bs_alloc(ctx, &d_offsets, n_tris + 1));
     BS_TRY(bs_alloc(ctx, &d_area, 1)); BS_TRY(bs_alloc(ctx, &d_flags, 2));
+    unsigned long long* d_neval = nullptr;
+    BS_TRY(bs_alloc(ctx, &d_neval, 1));
     BS_CUDA(ctx, cudaMemsetAsync(d_area, 0, sizeof(double), st));
     BS_CUDA(ctx, cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), st));
     BS_CUDA(ctx, cudaMemsetAsync(d_counts + n_tris, 0, sizeof(unsigned long long), st));
@@ -320,7 +329,7 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
 
     ConvertParams P;
     P.tris = d_tris; P.n_tris = n_tris; P.offsets = d_offsets; P.total = total;
-    P.vs = voxel_size; P.inv_vs = 1.0f / voxel_size; P.band = (int)band; P.flags = d_flags; P.values = nullptr;
+    P.vs = voxel_size; P.inv_vs = 1.0f / voxel_size; P.band = (int)band; P.flags = d_flags; P.values = nullptr; P.n_eval = d_neval;
 
     // 2. mark touched bricks in a hash set; sized from the surface area, doubled on overflow
     const double bw = (double)(2 * band + 1);
@@ -328,15 +337,17 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
     if (est > 6.0e8) est = 6.0e8;
     size_t cap = 1; while ((double)cap < 2.0 * est) cap <<= 1;
     unsigned long long* d_table_keys = nullptr; unsigned* d_table_slots = nullptr;
-    unsigned long long* d_keys = nullptr; size_t n_all = 0;
+    unsigned long long* d_keys = nullptr; size_t n_all = 0; unsigned long long n_eval = 0;
     const unsigned grid = (unsigned)((total + TPB - 1) / TPB);
     for (;;) {
         BS_TRY(bs_alloc(ctx, &d_table_keys, cap));
         BS_CUDA(ctx, cudaMemsetAsync(d_table_keys, 0xFF, cap * sizeof(unsigned long long), st));
+        BS_CUDA(ctx, cudaMemsetAsync(d_neval, 0, sizeof(unsigned long long), st));
         P.table_keys = d_table_keys; P.table_slots = nullptr; P.table_mask = (unsigned)(cap - 1);
         k_mark<<<grid, TPB, 0, st>>>(P);
         int flags[2];
         BS_CUDA(ctx, cudaMemcpyAsync(flags, d_flags, sizeof(flags), cudaMemcpyDeviceToHost, st));
+        BS_CUDA(ctx, cudaMemcpyAsync(&n_eval, d_neval, sizeof(n_eval), cudaMemcpyDeviceToHost, st));
         BS_CUDA(ctx, cudaStreamSynchronize(st));
         if (flags[1]) { bs_free(ctx, d_table_keys); bs_free(ctx, d_offsets); bs_free(ctx, d_flags); return bs_fail(ctx, BS_ERR_RANGE, "voxel index outside [-2^20, 2^20)"); }
         if (!flags[0]) break;
@@ -379,7 +390,7 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
     P.table_slots = d_table_slots; P.values = vol->values;
     k_eval<<<grid, TPB, 0, st>>>(P);
     bs_mark(ctx, "udf_ms");
-    bs_free(ctx, d_table_keys); bs_free(ctx, d_table_slots); bs_free(ctx, d_offsets); bs_free(ctx, d_flags);
+    bs_free(ctx, d_table_keys); bs_free(ctx, d_table_slots); bs_free(ctx, d_offsets); bs_free(ctx, d_flags); bs_free(ctx, d_neval);
     // 5. signs + masks
     s = bs_sign_impl(ctx, d_tris, n_tris, vol);
     if (s != BS_OK) { bs_volume_free(vol); return s; }
@@ -388,6 +399,12 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
     bs_stat_add(ctx, "n_tris", (double)n_tris);
     bs_stat_add(ctx, "n_sub", (double)total);
     bs_stat_add(ctx, "n_bricks", (double)n_all);
+    bs_stat_add(ctx, "n_eval", (double)n_eval);
+    if (ctx->count_work) {
+        bs_stat_add(ctx, "fwn_visits", ctx->fwn_counts[0]); bs_stat_add(ctx, "fwn_far", ctx->fwn_counts[1]);
+        bs_stat_add(ctx, "fwn_exact_tris", ctx->fwn_counts[2]); bs_stat_add(ctx, "fwn_voxels", ctx->fwn_counts[3]);
+        bs_stat_add(ctx, "fwn_warp_visits", ctx->fwn_counts[4]); bs_stat_add(ctx, "fwn_traversals", ctx->fwn_counts[5]);
+    }
     bs_stat_add(ctx, "area_vox", area_vox);
     *out = vol;
     return BS_OK;

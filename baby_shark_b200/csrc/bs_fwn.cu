@@ -1,31 +1,30 @@
-// Inside/outside signs by fast winding numbers over a device-built BVH (sm_100a).
+// Inside/outside signs by fast winding numbers over a device-built LBVH (sm_100a).
 // Replaces WindingNumbers::{from_mesh, approximate} (src/spatial_partitioning/aabb_tree.rs:636-691,711-816)
 // and MeshToVolume::compute_sings / ComputeSignsVisitor (src/voxel/mesh_to_volume.rs:198-281):
 //     value = copysign(|d|, wn(p) < 0.2 ? +1 : -1),   p = idx as f32 * voxel_size.
 //
-// The reference walks a serial top-down SAH tree with 3 triangles per leaf. Here the hierarchy is an LBVH in
-// its implicit form: triangles are radix-sorted by the 63-bit Morton code of their centroid, every LEAF
-// consecutive triangles form a leaf and every 8 consecutive nodes of a level form a node of the next, so a
-// node's children are contiguous (one 512 B coalesced group) and no child pointers or build-time atomics are
-// needed. Per node the same quantities as the reference (aabb_tree.rs:723-801): area-weighted normal (order 1),
-// sum(area * c * n^T) - p~ (sum area*n)^T (order 2), dipole centre p~ = sum(area*c)/sum(area); the radius is the
-// distance from p~ to the farthest corner of the node's box (the reference takes the farther of the two
-// extreme corners only, :734-736; this one is a true bound).
+// The reference builds a serial top-down binned-SAH tree with <= 3 triangles per leaf. Here: 63-bit Morton codes
+// of the triangle centroids, radix sort, leaves of LEAF consecutive triangles, Karras' (2012) binary radix tree
+// emitted fully in parallel, and one bottom-up pass (second-arrival atomics) for the per-node moments the
+// reference keeps (aabb_tree.rs:723-801): area-weighted normal (order 1), sum(area c n^T) - p~ (sum area n)^T
+// (order 2), dipole centre p~ = sum(area c)/sum(area). The node radius is the distance from p~ to the farthest
+// corner of the node's box (the reference takes the farther of the two extreme corners only, :734-736; this one
+// is a true bound, so the far-field test is never looser than the reference's).
 //
-// Traversal is warp-cooperative: a warp owns 32 active voxels of ONE brick and walks ONE shared stack. A node
-// is accepted as a far-field dipole only when it is far (|p - p~| > 2 radius, :666) for all 32 voxels, otherwise
-// the whole warp descends; lanes that could have stopped earlier just get a more accurate sum. There is no
-// divergence and every node read is a warp-uniform (broadcast) 16 B load.
+// Traversal is warp-cooperative: a warp owns 32 Morton-adjacent active voxels of ONE brick and walks ONE shared
+// stack of (node, lane mask) entries (see warp_winding): per-voxel acceptance exactly as the reference's
+// criterion (|p - p~| > 2 radius, :666), warp-uniform control flow, broadcast 16 B node loads.
 // Only the 0.2 threshold matters downstream, so FMA contraction is allowed here (unlike the distance stage).
 #include "bs_common.cuh"
 #include <cub/cub.cuh>
 
 namespace {
 
-constexpr int LEAF = 4;           // triangles per leaf
-constexpr int FAN = 8;            // children per internal node
-constexpr int MAX_LEVELS = 12;    // 4 * 8^11 triangles
-constexpr int STACK = 128;        // per-warp stack entries (<= 7 * levels + 8 live entries)
+#ifndef BS_LEAF
+#define BS_LEAF 1
+#endif
+constexpr int LEAF = BS_LEAF;     // triangles per leaf
+constexpr int STACK = 160;        // per-warp stack entries (tree depth <= 63 + 32 with index tie-breaks)
 constexpr int WARPS_PER_BLOCK = 4;
 constexpr float BETA = 2.0f;      // accuracy_scale (mesh_to_volume.rs:264)
 constexpr float INV_4PI = 0.07957747154594767f;
@@ -36,11 +35,13 @@ struct Raw {  // additive moments of a node (aabb_tree.rs:694-700) + box
 static_assert(sizeof(Raw) == 96, "Raw is 24 floats");
 
 struct Tree {
-    const float4* nodes;    // 4 x float4 per node: {c.xyz, beta^2 r^2} {o1.xyz, trM} {m00 m11 m22 m01+m10} {m02+m20 m12+m21 - -}
+    // node ids: internal [0, n-1), leaves [n-1, 2n-1)
+    const float4* hdr;      // per node {p~.xyz, beta^2 r^2}
+    const float4* coef;     // per node 3 x float4 far-field coefficients
+    const float4* rec;      // per internal node: traversal record (k_records)
     const float4* tris;     // 3 x float4 per sorted triangle (9 floats + pad), LEAF per leaf, padded with degenerate triangles
-    unsigned level_off[MAX_LEVELS];
-    unsigned level_cnt[MAX_LEVELS];
-    int levels;             // root is level levels-1, index 0
+    unsigned n_leaves;
+    unsigned root;
 };
 
 __device__ __forceinline__ int f2ord(float f) { int b = __float_as_int(f); return b >= 0 ? b : b ^ 0x7FFFFFFF; }
@@ -85,79 +86,164 @@ __global__ void k_morton(const float* __restrict__ tris, size_t n, const int* bo
     codes[t] = code; ids[t] = (unsigned)t;
 }
 
-// level 0: gather LEAF sorted triangles, store them for traversal, accumulate the leaf's moments (aabb_tree.rs:749-777)
-__global__ void k_leaves(const float* __restrict__ tris, const unsigned* __restrict__ ids, size_t n, float4* sorted, Raw* raw, unsigned n_leaves) {
-    unsigned l = blockIdx.x * blockDim.x + threadIdx.x;
-    if (l >= n_leaves) return;
+// ---- Karras 2012: one thread per internal node -----------------------------------------------------------------
+// key of leaf g = Morton code of its first triangle; ties broken by the leaf index.
+__device__ __forceinline__ int delta(const unsigned long long* __restrict__ codes, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    const unsigned long long a = codes[(size_t)i * LEAF], b = codes[(size_t)j * LEAF];
+    if (a != b) return __clzll((long long)(a ^ b));
+    return 64 + __clz(i ^ j);
+}
+__global__ void k_karras(const unsigned long long* __restrict__ codes, int n, int* left, int* right, int* parent) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const int d = (delta(codes, n, i, i + 1) - delta(codes, n, i, i - 1)) >= 0 ? 1 : -1;
+    const int dmin = delta(codes, n, i, i - d);
+    int lmax = 2;
+    while (delta(codes, n, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1) if (delta(codes, n, i, i + (l + t) * d) > dmin) l += t;
+    const int j = i + l * d;
+    const int dnode = delta(codes, n, i, j);
+    int s = 0, t = l;
+    do { t = (t + 1) >> 1; if (delta(codes, n, i, i + (s + t) * d) > dnode) s += t; } while (t > 1);
+    const int gamma = i + s * d + min(d, 0);
+    const int lo = min(i, j), hi = max(i, j);
+    const int lc = (lo == gamma) ? (n - 1 + gamma) : gamma;
+    const int rc = (hi == gamma + 1) ? (n - 1 + gamma + 1) : (gamma + 1);
+    left[i] = lc; right[i] = rc;
+    parent[lc] = i; parent[rc] = i;
+    if (i == 0) parent[0] = -1;
+}
+
+__device__ __forceinline__ void raw_load_cg(const Raw* p, Raw& r) {
+    const float4* s = reinterpret_cast<const float4*>(p); float4* d = reinterpret_cast<float4*>(&r);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) d[i] = __ldcg(s + i);
+}
+
+// leaves: gather LEAF sorted triangles, store them for traversal, accumulate the leaf's moments
+// (aabb_tree.rs:749-777), then climb: the second child to arrive at a parent combines both (:779-801).
+__global__ void k_leaves_and_climb(const float* __restrict__ tris, const unsigned* __restrict__ ids, size_t n_tris, float4* sorted, Raw* raw,
+                                   const int* __restrict__ left, const int* __restrict__ right, const int* __restrict__ parent, unsigned* flags, int n) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
     Raw r;
     r.area = 0.f;
     for (int d = 0; d < 3; ++d) { r.awc[d] = 0.f; r.awn[d] = 0.f; r.bbmin[d] = 3.0e38f; r.bbmax[d] = -3.0e38f; }
     for (int i = 0; i < 9; ++i) r.o1sum[i] = 0.f;
     r.pad[0] = r.pad[1] = 0.f;
     for (int k = 0; k < LEAF; ++k) {
-        size_t s = (size_t)l * LEAF + k;
+        const size_t s = (size_t)g * LEAF + k;
         float v[9];
-        if (s < n) { const float* p = tris + 9 * (size_t)ids[s]; for (int i = 0; i < 9; ++i) v[i] = p[i]; }
+        if (s < n_tris) { const float* p = tris + 9 * (size_t)ids[s]; for (int i = 0; i < 9; ++i) v[i] = p[i]; }
         else { for (int i = 0; i < 9; ++i) v[i] = 0.f; }  // padding: degenerate triangle, contributes nothing
         sorted[3 * s + 0] = make_float4(v[0], v[1], v[2], v[3]);
         sorted[3 * s + 1] = make_float4(v[4], v[5], v[6], v[7]);
         sorted[3 * s + 2] = make_float4(v[8], 0.f, 0.f, 0.f);
-        if (s >= n) continue;
+        if (s >= n_tris) continue;
         for (int d = 0; d < 3; ++d) {
             r.bbmin[d] = fminf(r.bbmin[d], fminf(v[d], fminf(v[3 + d], v[6 + d])));
             r.bbmax[d] = fmaxf(r.bbmax[d], fmaxf(v[d], fmaxf(v[3 + d], v[6 + d])));
         }
-        float e1[3] = {v[3] - v[0], v[4] - v[1], v[5] - v[2]}, e2[3] = {v[6] - v[0], v[7] - v[1], v[8] - v[2]};
-        float cr[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
-        float n2 = cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2];
+        const float e1[3] = {v[3] - v[0], v[4] - v[1], v[5] - v[2]}, e2[3] = {v[6] - v[0], v[7] - v[1], v[8] - v[2]};
+        const float cr[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+        const float n2 = cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2];
         if (!(n2 > 0.f)) continue;  // degenerate triangles are skipped (:757-759)
-        float len = sqrtf(n2), area = 0.5f * len;
-        float nn[3] = {cr[0] / len, cr[1] / len, cr[2] / len};
-        float c[3] = {(v[0] + v[3] + v[6]) / 3.0f, (v[1] + v[4] + v[7]) / 3.0f, (v[2] + v[5] + v[8]) / 3.0f};
+        const float len = sqrtf(n2), area = 0.5f * len;
+        const float nn[3] = {cr[0] / len, cr[1] / len, cr[2] / len};
+        const float c[3] = {(v[0] + v[3] + v[6]) / 3.0f, (v[1] + v[4] + v[7]) / 3.0f, (v[2] + v[5] + v[8]) / 3.0f};
         r.area += area;
         for (int d = 0; d < 3; ++d) { r.awn[d] += area * nn[d]; r.awc[d] += area * c[d]; }
         for (int col = 0; col < 3; ++col) for (int row = 0; row < 3; ++row) r.o1sum[col * 3 + row] += area * c[row] * nn[col];
     }
-    raw[l] = r;
-}
-
-__global__ void k_level_up(const Raw* __restrict__ child, unsigned n_child, Raw* parent, unsigned n_parent) {
-    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_parent) return;
-    Raw r = child[(size_t)i * FAN];
-    for (int k = 1; k < FAN; ++k) {
-        size_t c = (size_t)i * FAN + k;
-        if (c >= n_child) break;
-        const Raw& q = child[c];
-        r.area += q.area;
-        for (int d = 0; d < 3; ++d) { r.awc[d] += q.awc[d]; r.awn[d] += q.awn[d]; r.bbmin[d] = fminf(r.bbmin[d], q.bbmin[d]); r.bbmax[d] = fmaxf(r.bbmax[d], q.bbmax[d]); }
-        for (int j = 0; j < 9; ++j) r.o1sum[j] += q.o1sum[j];
+    {   // bounding radius about the dipole centre: exact over the leaf's vertices
+        float c[3] = {r.awc[0] / r.area, r.awc[1] / r.area, r.awc[2] / r.area}, m2 = 0.f;
+        for (int k = 0; k < LEAF; ++k) {
+            const size_t s = (size_t)g * LEAF + k;
+            if (s >= n_tris) break;
+            const float* p = tris + 9 * (size_t)ids[s];
+            for (int v = 0; v < 3; ++v) { const float dx = p[3 * v] - c[0], dy = p[3 * v + 1] - c[1], dz = p[3 * v + 2] - c[2]; m2 = fmaxf(m2, dx * dx + dy * dy + dz * dz); }
+        }
+        r.pad[0] = sqrtf(m2);  // NaN centre (all-degenerate leaf) -> fmaxf drops the NaNs -> 0, finalize falls back to the box bound
     }
-    parent[i] = r;
+    raw[n - 1 + g] = r;
+    if (n == 1) return;
+    int node = parent[n - 1 + g];
+    while (node >= 0) {
+        __threadfence();
+        if (atomicAdd(&flags[node], 1u) == 0u) return;  // first arrival: the sibling subtree is not finished yet
+        __threadfence();
+        Raw a, b;
+        raw_load_cg(raw + left[node], a); raw_load_cg(raw + right[node], b);
+        a.area += b.area;
+        for (int d = 0; d < 3; ++d) { a.awc[d] += b.awc[d]; a.awn[d] += b.awn[d]; a.bbmin[d] = fminf(a.bbmin[d], b.bbmin[d]); a.bbmax[d] = fmaxf(a.bbmax[d], b.bbmax[d]); }
+        for (int j = 0; j < 9; ++j) a.o1sum[j] += b.o1sum[j];
+        {   // |p~_child - p~| + r_child bounds the child's triangles about the merged centre
+            const float ia = 1.0f / (a.area - b.area), ib = 1.0f / b.area, in = 1.0f / a.area;  // a.area is already the sum
+            float da = 0.f, db = 0.f;
+            for (int d = 0; d < 3; ++d) {
+                const float cn = a.awc[d] * in, ca = (a.awc[d] - b.awc[d]) * ia, cb = b.awc[d] * ib;
+                da += (ca - cn) * (ca - cn); db += (cb - cn) * (cb - cn);
+            }
+            const float ra = sqrtf(da) + a.pad[0], rb = sqrtf(db) + b.pad[0];
+            a.pad[0] = (ra == ra && rb == rb) ? fmaxf(ra, rb) : 3.0e38f;  // a degenerate child: keep only the box bound
+        }
+        raw[node] = a;
+        node = parent[node];
+    }
 }
 
-__global__ void k_finalize_nodes(const Raw* __restrict__ raw, unsigned n, float4* nodes) {
-    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+// Per node: header {p~.xyz, beta^2 r^2} and far-field coefficients {o1.xyz, trM} {m00 m11 m22 m01+m10} {m02+m20 m12+m21 - -}
+__global__ void k_finalize_nodes(const Raw* __restrict__ raw, int n, float4* hdr, float4* coef) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * n - 1) return;
     const Raw r = raw[i];
     float c[3], rad2 = 0.f;
     for (int d = 0; d < 3; ++d) {
         c[d] = r.awc[d] / r.area;  // NaN for an all-degenerate node: never "far", always descended (as in the reference)
-        float e = fmaxf(fabsf(r.bbmin[d] - c[d]), fabsf(r.bbmax[d] - c[d]));
+        const float e = fmaxf(fabsf(r.bbmin[d] - c[d]), fabsf(r.bbmax[d] - c[d]));
         rad2 += e * e;
     }
-    float m[9];
+    if (r.pad[0] > 0.f && r.pad[0] * r.pad[0] < rad2) rad2 = r.pad[0] * r.pad[0];  // the tighter of two valid bounds
+    float m[9];  // m[col*3+row]
     for (int col = 0; col < 3; ++col) for (int row = 0; row < 3; ++row) m[col * 3 + row] = r.o1sum[col * 3 + row] - c[row] * r.awn[col];
-    // m[col*3+row]; symmetric combinations for r^T M r
-    nodes[4 * (size_t)i + 0] = make_float4(c[0], c[1], c[2], BETA * BETA * rad2);
-    nodes[4 * (size_t)i + 1] = make_float4(r.awn[0], r.awn[1], r.awn[2], m[0] + m[4] + m[8]);
-    nodes[4 * (size_t)i + 2] = make_float4(m[0], m[4], m[8], m[1] + m[3]);
-    nodes[4 * (size_t)i + 3] = make_float4(m[2] + m[6], m[5] + m[7], 0.f, 0.f);
+    hdr[i] = make_float4(c[0], c[1], c[2], BETA * BETA * rad2);
+    coef[3 * (size_t)i + 0] = make_float4(r.awn[0], r.awn[1], r.awn[2], m[0] + m[4] + m[8]);
+    coef[3 * (size_t)i + 1] = make_float4(m[0], m[4], m[8], m[1] + m[3]);
+    coef[3 * (size_t)i + 2] = make_float4(m[2] + m[6], m[5] + m[7], 0.f, 0.f);
+}
+
+// Traversal record of internal node X: its (up to 4) grandchildren -- or a child itself when that child is a leaf --
+// with everything a visit needs, so one pop costs ONE dependent memory round trip for four node tests.
+// 256 B = two 128 B lines: [0..3] entry headers, [4] entry node ids (int4, -1 = none), then 10 coefficient floats
+// per entry {o1.xyz, trM, m00, m11, m22, m01+m10, m02+m20, m12+m21} packed from float 20 on.
+constexpr int REC = 16;  // float4 per record
+__global__ void k_records(const int* __restrict__ left, const int* __restrict__ right, const float4* __restrict__ hdr, const float4* __restrict__ coef, int n, float4* rec) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n - 1) return;
+    int ids[4] = {-1, -1, -1, -1}, k = 0;
+    const int ch[2] = {left[x], right[x]};
+    for (int c = 0; c < 2; ++c) {
+        if (ch[c] >= n - 1) ids[k++] = ch[c];
+        else { ids[k++] = left[ch[c]]; ids[k++] = right[ch[c]]; }
+    }
+    float4* r = rec + (size_t)x * REC;
+    float* rf = reinterpret_cast<float*>(r);
+    for (int e = 0; e < 4; ++e) {
+        const bool ok = ids[e] >= 0;
+        r[e] = ok ? hdr[ids[e]] : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0, c2 = c0;
+        if (ok) { c0 = coef[3 * (size_t)ids[e]]; c1 = coef[3 * (size_t)ids[e] + 1]; c2 = coef[3 * (size_t)ids[e] + 2]; }
+        float* o = rf + 20 + 10 * e;
+        o[0] = c0.x; o[1] = c0.y; o[2] = c0.z; o[3] = c0.w; o[4] = c1.x; o[5] = c1.y; o[6] = c1.z; o[7] = c1.w; o[8] = c2.x; o[9] = c2.y;
+    }
+    r[4] = make_float4(__int_as_float(ids[0]), __int_as_float(ids[1]), __int_as_float(ids[2]), __int_as_float(ids[3]));
+    r[15] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // far-field dipole (aabb_tree.rs:667-669, hessians :803-816): o1 . r/(4 pi |r|^3) + M : (I/(4 pi |r|^3) - 3 r r^T/(4 pi |r|^5))
-__device__ __forceinline__ float far_field(const float4* __restrict__ nd, float rx, float ry, float rz, float r2) {
-    const float4 a = __ldg(nd + 1), b = __ldg(nd + 2), c = __ldg(nd + 3);
+__device__ __forceinline__ float far_field(const float4 a, const float4 b, const float4 c, float rx, float ry, float rz, float r2) {
     const float inv_r = rsqrtf(r2);
     const float k = INV_4PI * inv_r * inv_r * inv_r;
     const float rMr = b.x * rx * rx + b.y * ry * ry + b.z * rz * rz + b.w * rx * ry + c.x * rx * rz + c.y * ry * rz;
@@ -165,8 +251,7 @@ __device__ __forceinline__ float far_field(const float4* __restrict__ nd, float 
 }
 
 // solid_angle / (4 pi) (aabb_tree.rs:582-628), Van Oosterom-Strackee form
-__device__ __forceinline__ float tri_winding(const float4* __restrict__ t, float qx, float qy, float qz) {
-    const float4 t0 = __ldg(t), t1 = __ldg(t + 1), t2 = __ldg(t + 2);
+__device__ __forceinline__ float tri_winding(const float4 t0, const float4 t1, const float4 t2, float qx, float qy, float qz) {
     const float ax = t0.x - qx, ay = t0.y - qy, az = t0.z - qz;
     const float bx = t0.w - qx, by = t1.x - qy, bz = t1.y - qz;
     const float cx = t1.z - qx, cy = t1.w - qy, cz = t2.x - qz;
@@ -178,84 +263,180 @@ __device__ __forceinline__ float tri_winding(const float4* __restrict__ t, float
     return atan2f(det, den) * (2.0f * INV_4PI);
 }
 
-// Warp-cooperative winding number of 32 query points (one per lane). `stack` is this warp's shared-memory stack.
-__device__ float warp_winding(const Tree& T, float qx, float qy, float qz, unsigned* stack) {
-    const unsigned lane = threadIdx.x & 31;
-    float wn = 0.f;
-    int sp = 0;
-    // visit(level, idx): far for all lanes -> accumulate; else leaf -> exact; else push
-    auto visit = [&](int level, unsigned idx) {
-        const float4* nd = T.nodes + 4 * (size_t)(T.level_off[level] + idx);
-        const float4 h = __ldg(nd);
-        const float rx = h.x - qx, ry = h.y - qy, rz = h.z - qz;
-        const float r2 = rx * rx + ry * ry + rz * rz;
-        if (__all_sync(0xFFFFFFFFu, r2 > h.w)) { wn += far_field(nd, rx, ry, rz, r2); return; }
-        if (level == 0) {
-            const float4* t = T.tris + 3 * (size_t)idx * LEAF;
-#pragma unroll
-            for (int k = 0; k < LEAF; ++k) wn += tri_winding(t + 3 * k, qx, qy, qz);
-            return;
-        }
-        if (lane == 0) stack[sp] = ((unsigned)level << 28) | idx;
-        ++sp;
-    };
-    visit(T.levels - 1, 0);
-    while (sp > 0) {
-        --sp;
-        __syncwarp();
-        const unsigned e = stack[sp];
-        __syncwarp();
-        const int level = (int)(e >> 28) - 1;
-        const unsigned first = (e & 0x0FFFFFFFu) * FAN;
-        const unsigned cnt = min((unsigned)FAN, T.level_cnt[level] - first);
-        for (unsigned k = 0; k < cnt; ++k) visit(level, first + k);
-    }
-    return wn;
-}
+// Warp-cooperative winding numbers of up to 32*VPL query points (VPL per lane). The warp walks ONE shared stack
+// of (node, lane masks) entries: a (lane, slot) takes part in a node only if none of its ancestors was already
+// accepted as far for it, so every voxel gets exactly the sum its own traversal would give (criterion
+// |p - p~| > 2 radius per voxel, aabb_tree.rs:666) while control flow stays warp-uniform and every node read is a
+// warp-uniform (broadcast) load. The work issued is the union of the traversals, which for Morton-adjacent voxels
+// of one brick is close to a single traversal.
+// COUNT: also tally per-voxel node visits / far-field evaluations / exact triangle evaluations (cnt[0..2]).
+template <bool COUNT, int VPL>
+struct WarpWinding {
+    const Tree& T;
+    float qx[VPL], qy[VPL], qz[VPL], wn[VPL];
+    unsigned* stack;   // STACK entries of (1 + VPL) words
+    unsigned* cnt;
+    int sp;
+    unsigned lane;
 
-__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_sign(Tree T, float* values, unsigned long long* masks, size_t n_bricks,
-                                                               const unsigned long long* __restrict__ keys, float vs) {
-    __shared__ unsigned s_stack[WARPS_PER_BLOCK][STACK];
-    __shared__ unsigned short s_list[WARPS_PER_BLOCK][512];
-    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const size_t warp_global = (size_t)blockIdx.x * WARPS_PER_BLOCK + w, n_warps = (size_t)gridDim.x * WARPS_PER_BLOCK;
-    for (size_t b = warp_global; b < n_bricks; b += n_warps) {
-        float* bv = values + b * 512;
-        // active list + mask words
-        unsigned cnt = 0;
-        unsigned my_mask_lo = 0, my_mask_hi = 0;
-        for (int r = 0; r < 16; ++r) {
-            const unsigned off = r * 32 + lane;
-            const bool act = __float_as_uint(bv[off]) != BS_UDF_SENTINEL_BITS;
-            const unsigned bal = __ballot_sync(0xFFFFFFFFu, act);
-            if (act) s_list[w][cnt + __popc(bal & ((1u << lane) - 1))] = (unsigned short)off;
-            cnt += __popc(bal);
-            if ((int)lane == (r >> 1)) { if (r & 1) my_mask_hi = bal; else my_mask_lo = bal; }
-        }
-        if (lane < 8) masks[b * 8 + lane] = (unsigned long long)my_mask_lo | ((unsigned long long)my_mask_hi << 32);
-        __syncwarp();
-        if (cnt == 0) continue;
-        int bx, by, bz; bs_key_brick(keys[b], bx, by, bz);
-        for (unsigned base = 0; base < cnt; base += 32) {
-            const unsigned i = base + lane;
-            const bool valid = i < cnt;
-            const unsigned off = s_list[w][valid ? i : cnt - 1];  // idle lanes shadow a real voxel: decisions stay brick-local
-            const int x = (bx << 3) + (int)(off >> 6), y = (by << 3) + (int)((off >> 3) & 7), z = (bz << 3) + (int)(off & 7);
-            const float wn = warp_winding(T, __fmul_rn((float)x, vs), __fmul_rn((float)y, vs), __fmul_rn((float)z, vs), s_stack[w]);
-            if (valid) {
-                const float d = bv[off];
-                bv[off] = (wn < 0.2f) ? copysignf(d, 1.0f) : copysignf(d, -1.0f);  // mesh_to_volume.rs:266-271
+    __device__ __forceinline__ void visit(unsigned id, const float4 h, const float4 c0, const float4 c1, const float4 c2, const unsigned* m) {
+        unsigned near_m[VPL]; unsigned any_near = 0;
+        if (COUNT && lane == 0) cnt[3]++;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            const bool in = (m[v] >> lane) & 1;
+            const float rx = h.x - qx[v], ry = h.y - qy[v], rz = h.z - qz[v];
+            const float r2 = rx * rx + ry * ry + rz * rz;
+            const bool far = in && (r2 > h.w);
+            const unsigned far_m = __ballot_sync(0xFFFFFFFFu, far);
+            near_m[v] = m[v] & ~far_m; any_near |= near_m[v];
+            if (COUNT && in) cnt[0]++;
+            if (far_m) {
+                const float f = far_field(c0, c1, c2, rx, ry, rz, r2);
+                if (far) { wn[v] += f; if (COUNT) cnt[1]++; }
             }
         }
-        __syncwarp();
+        if (any_near == 0) return;
+        if (id >= T.n_leaves - 1) {
+            const float4* t = T.tris + 3 * (size_t)(id - (T.n_leaves - 1)) * LEAF;
+#pragma unroll
+            for (int k = 0; k < LEAF; ++k) {
+                const float4 t0 = __ldg(t + 3 * k), t1 = __ldg(t + 3 * k + 1), t2 = __ldg(t + 3 * k + 2);
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) {
+                    if (near_m[v] == 0) continue;  // uniform
+                    const float e = tri_winding(t0, t1, t2, qx[v], qy[v], qz[v]);
+                    if ((near_m[v] >> lane) & 1) { wn[v] += e; if (COUNT) cnt[2]++; }
+                }
+            }
+            return;
+        }
+        if (sp < STACK) {
+            {   // start pulling the record this entry will need when it is popped (two 128 B lines)
+                const char* nxt = reinterpret_cast<const char*>(T.rec + (size_t)id * REC);
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt + 128));
+            }
+            if (lane == 0) {
+                unsigned* e = stack + sp * (1 + VPL);
+                e[0] = id;
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) e[1 + v] = near_m[v];
+            }
+            ++sp;
+        }
+    }
+
+    __device__ void run(const unsigned* valid_m) {
+        sp = 0;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) wn[v] = 0.f;
+        {   // the root itself (aabb_tree.rs:662-670 tests a node before looking at its type)
+            const float4* c = T.coef + 3 * (size_t)T.root;
+            visit(T.root, __ldg(T.hdr + T.root), __ldg(c), __ldg(c + 1), __ldg(c + 2), valid_m);
+        }
+        while (sp > 0) {
+            --sp;
+            __syncwarp();
+            unsigned m[VPL];
+            const unsigned* e = stack + sp * (1 + VPL);
+            const unsigned id = e[0];
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) m[v] = e[1 + v];
+            __syncwarp();
+            const float4* r = T.rec + (size_t)id * REC;
+            const float4 idsf = __ldg(r + 4);
+            const int ids[4] = {__float_as_int(idsf.x), __float_as_int(idsf.y), __float_as_int(idsf.z), __float_as_int(idsf.w)};
+            // coefficient floats 20..59 = float4 slots 5..14, entry e starts at float 20 + 10 e
+            const float4 q5 = __ldg(r + 5), q6 = __ldg(r + 6), q7 = __ldg(r + 7), q8 = __ldg(r + 8), q9 = __ldg(r + 9);
+            const float4 q10 = __ldg(r + 10), q11 = __ldg(r + 11), q12 = __ldg(r + 12), q13 = __ldg(r + 13), q14 = __ldg(r + 14);
+            if (ids[0] >= 0) visit((unsigned)ids[0], __ldg(r + 0), q5, q6, make_float4(q7.x, q7.y, 0.f, 0.f), m);
+            if (ids[1] >= 0) visit((unsigned)ids[1], __ldg(r + 1), make_float4(q7.z, q7.w, q8.x, q8.y), make_float4(q8.z, q8.w, q9.x, q9.y), make_float4(q9.z, q9.w, 0.f, 0.f), m);
+            if (ids[2] >= 0) visit((unsigned)ids[2], __ldg(r + 2), q10, q11, make_float4(q12.x, q12.y, 0.f, 0.f), m);
+            if (ids[3] >= 0) visit((unsigned)ids[3], __ldg(r + 3), make_float4(q12.z, q12.w, q13.x, q13.y), make_float4(q13.z, q13.w, q14.x, q14.y), make_float4(q14.z, q14.w, 0.f, 0.f), m);
+        }
+    }
+};
+
+// 9-bit Morton position inside a brick -> leaf offset x<<6 | y<<3 | z (bits 2,5,8 -> x; 1,4,7 -> y; 0,3,6 -> z)
+__device__ __forceinline__ unsigned demorton9(unsigned p) {
+    const unsigned x = ((p >> 2) & 1) | ((p >> 4) & 2) | ((p >> 6) & 4);
+    const unsigned y = ((p >> 1) & 1) | ((p >> 3) & 2) | ((p >> 5) & 4);
+    const unsigned z = (p & 1) | ((p >> 2) & 2) | ((p >> 4) & 4);
+    return (x << 6) | (y << 3) | z;
+}
+
+// One CTA per brick: the active list is built once, then the warps take 32*VPL-voxel chunks round robin, so
+// a heavy brick (e.g. at the pole of a UV sphere, where hundreds of sliver triangles are "near") is spread over
+// all warps of its CTA instead of serialising one warp.
+template <bool COUNT, int VPL>
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_sign(Tree T, float* values, unsigned long long* masks, size_t n_bricks,
+                                                               const unsigned long long* __restrict__ keys, float vs, unsigned long long* counters) {
+    __shared__ unsigned s_stack[WARPS_PER_BLOCK][STACK * (1 + VPL)];
+    __shared__ unsigned short s_list[512];
+    __shared__ unsigned s_cnt[17];
+    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const size_t b = blockIdx.x;
+    float* bv = values + b * 512;
+    // mask words (leaf offset order): warp w covers rounds 4w..4w+3 = mask words 2w, 2w+1
+    {
+        unsigned bal[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) bal[r] = __ballot_sync(0xFFFFFFFFu, __float_as_uint(bv[(4 * w + r) * 32 + lane]) != BS_UDF_SENTINEL_BITS);
+        if (lane < 2) masks[b * 8 + 2 * w + lane] = (unsigned long long)bal[2 * lane] | ((unsigned long long)bal[2 * lane + 1] << 32);
+    }
+    // active voxels in Morton order, so 32 consecutive entries are a compact cluster: counts, scan, scatter
+    unsigned balm[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        balm[r] = __ballot_sync(0xFFFFFFFFu, __float_as_uint(bv[demorton9((4 * w + r) * 32 + lane)]) != BS_UDF_SENTINEL_BITS);
+        if (lane == 0) s_cnt[4 * w + r] = __popc(balm[r]);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { unsigned acc = 0; for (int r = 0; r < 16; ++r) { const unsigned c = s_cnt[r]; s_cnt[r] = acc; acc += c; } s_cnt[16] = acc; }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+        if ((balm[r] >> lane) & 1) s_list[s_cnt[4 * w + r] + __popc(balm[r] & ((1u << lane) - 1))] = (unsigned short)demorton9((4 * w + r) * 32 + lane);
+    __syncthreads();
+    const unsigned cnt = s_cnt[16];
+    int bx, by, bz; bs_key_brick(keys[b], bx, by, bz);
+    for (unsigned base = w * 32 * VPL; base < cnt; base += WARPS_PER_BLOCK * 32 * VPL) {
+        unsigned c3[4] = {0, 0, 0, 0};
+        WarpWinding<COUNT, VPL> W{T};
+        W.stack = s_stack[w]; W.cnt = c3; W.lane = lane;
+        unsigned off[VPL], valid_m[VPL]; bool valid[VPL];
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            const unsigned i = base + v * 32 + lane;
+            valid[v] = i < cnt;
+            valid_m[v] = __ballot_sync(0xFFFFFFFFu, valid[v]);
+            off[v] = s_list[valid[v] ? i : cnt - 1];
+            W.qx[v] = __fmul_rn((float)((bx << 3) + (int)(off[v] >> 6)), vs);
+            W.qy[v] = __fmul_rn((float)((by << 3) + (int)((off[v] >> 3) & 7)), vs);
+            W.qz[v] = __fmul_rn((float)((bz << 3) + (int)(off[v] & 7)), vs);
+        }
+        W.run(valid_m);
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            if (!valid[v]) continue;
+            const float d = bv[off[v]];
+            bv[off[v]] = (W.wn[v] < 0.2f) ? copysignf(d, 1.0f) : copysignf(d, -1.0f);  // mesh_to_volume.rs:266-271
+            if (COUNT) atomicAdd(counters + 3, 1ull);
+        }
+        if (COUNT) { atomicAdd(counters, (unsigned long long)c3[0]); atomicAdd(counters + 1, (unsigned long long)c3[1]); atomicAdd(counters + 2, (unsigned long long)c3[2]); atomicAdd(counters + 4, (unsigned long long)c3[3]); atomicAdd(counters + 5, (unsigned long long)(lane == 0)); }
     }
 }
 
 }  // namespace
 
+#ifndef BS_VPL
+#define BS_VPL 2
+#endif
+
 bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_volume* vol) {
     cudaStream_t st = ctx->stream;
-    if (n_tris >= (1ull << 28) * LEAF) return bs_fail(ctx, BS_ERR_RANGE, "too many triangles");
+    if (n_tris >= (1ull << 30)) return bs_fail(ctx, BS_ERR_RANGE, "too many triangles");
     // Morton order
     int* d_bounds = nullptr; unsigned long long *d_codes = nullptr, *d_codes2 = nullptr; unsigned *d_ids = nullptr, *d_ids2 = nullptr;
     BS_TRY(bs_alloc(ctx, &d_bounds, 6));
@@ -269,38 +450,44 @@ bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_v
     cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_codes, d_codes2, d_ids, d_ids2, n_tris, 0, 63, st);
     BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp_bytes));
     cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_codes, d_codes2, d_ids, d_ids2, n_tris, 0, 63, st);
-    bs_free(ctx, d_tmp); bs_free(ctx, d_codes); bs_free(ctx, d_codes2); bs_free(ctx, d_ids); bs_free(ctx, d_bounds);
-    // implicit hierarchy
+    bs_free(ctx, d_tmp); bs_free(ctx, d_codes); bs_free(ctx, d_ids); bs_free(ctx, d_bounds);
+    // hierarchy
+    const int n = (int)((n_tris + LEAF - 1) / LEAF);
+    const int n_nodes = 2 * n - 1;
+    int *d_left = nullptr, *d_right = nullptr, *d_parent = nullptr; unsigned* d_flags = nullptr;
+    float4 *d_sorted = nullptr, *d_hdr = nullptr, *d_coef = nullptr, *d_rec = nullptr; Raw* d_raw = nullptr;
+    BS_TRY(bs_alloc(ctx, &d_left, (size_t)n)); BS_TRY(bs_alloc(ctx, &d_right, (size_t)n)); BS_TRY(bs_alloc(ctx, &d_parent, (size_t)n_nodes));
+    BS_TRY(bs_alloc(ctx, &d_flags, (size_t)n));
+    BS_TRY(bs_alloc(ctx, &d_sorted, (size_t)n * LEAF * 3));
+    BS_TRY(bs_alloc(ctx, &d_hdr, (size_t)n_nodes)); BS_TRY(bs_alloc(ctx, &d_coef, (size_t)n_nodes * 3));
+    BS_TRY(bs_alloc(ctx, &d_rec, (size_t)n * REC));
+    BS_TRY(bs_alloc(ctx, &d_raw, (size_t)n_nodes));
+    BS_CUDA(ctx, cudaMemsetAsync(d_flags, 0, (size_t)n * sizeof(unsigned), st));
+    if (n > 1) k_karras<<<bs_blocks((size_t)n - 1, 256), 256, 0, st>>>(d_codes2, n, d_left, d_right, d_parent);
+    k_leaves_and_climb<<<bs_blocks((size_t)n, 128), 128, 0, st>>>(d_tris, d_ids2, n_tris, d_sorted, d_raw, d_left, d_right, d_parent, d_flags, n);
+    k_finalize_nodes<<<bs_blocks((size_t)n_nodes, 128), 128, 0, st>>>(d_raw, n, d_hdr, d_coef);
+    if (n > 1) k_records<<<bs_blocks((size_t)n - 1, 128), 128, 0, st>>>(d_left, d_right, d_hdr, d_coef, n, d_rec);
+    bs_free(ctx, d_raw); bs_free(ctx, d_ids2); bs_free(ctx, d_codes2); bs_free(ctx, d_left); bs_free(ctx, d_right); bs_free(ctx, d_parent); bs_free(ctx, d_flags);
     Tree T;
-    unsigned cnt = (unsigned)((n_tris + LEAF - 1) / LEAF), total_nodes = 0;
-    T.levels = 0;
-    for (;;) {
-        if (T.levels >= MAX_LEVELS) return bs_fail(ctx, BS_ERR_RANGE, "BVH too deep");
-        T.level_off[T.levels] = total_nodes; T.level_cnt[T.levels] = cnt; total_nodes += cnt; ++T.levels;
-        if (cnt == 1) break;
-        cnt = (cnt + FAN - 1) / FAN;
-    }
-    for (int l = T.levels; l < MAX_LEVELS; ++l) { T.level_off[l] = 0; T.level_cnt[l] = 0; }
-    float4 *d_sorted = nullptr, *d_nodes = nullptr; Raw* d_raw = nullptr;
-    BS_TRY(bs_alloc(ctx, &d_sorted, (size_t)T.level_cnt[0] * LEAF * 3));
-    BS_TRY(bs_alloc(ctx, &d_nodes, (size_t)total_nodes * 4));
-    BS_TRY(bs_alloc(ctx, &d_raw, (size_t)total_nodes));
-    k_leaves<<<bs_blocks(T.level_cnt[0], 128), 128, 0, st>>>(d_tris, d_ids2, n_tris, d_sorted, d_raw, T.level_cnt[0]);
-    for (int l = 1; l < T.levels; ++l)
-        k_level_up<<<bs_blocks(T.level_cnt[l], 128), 128, 0, st>>>(d_raw + T.level_off[l - 1], T.level_cnt[l - 1], d_raw + T.level_off[l], T.level_cnt[l]);
-    k_finalize_nodes<<<bs_blocks(total_nodes, 128), 128, 0, st>>>(d_raw, total_nodes, d_nodes);
-    bs_free(ctx, d_raw); bs_free(ctx, d_ids2);
-    T.nodes = d_nodes; T.tris = d_sorted;
+    T.hdr = d_hdr; T.coef = d_coef; T.rec = d_rec; T.tris = d_sorted; T.n_leaves = (unsigned)n; T.root = 0u;
     bs_mark(ctx, "bvh_build_ms");
     if (vol->n_bricks) {
-        const size_t warps = vol->n_bricks;
-        size_t blocks = (warps + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
-        const size_t max_blocks = (size_t)ctx->sm_count * 16 * 4;
-        if (blocks > max_blocks) blocks = max_blocks;
-        k_sign<<<(unsigned)blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(T, vol->values, (unsigned long long*)vol->masks, vol->n_bricks, (const unsigned long long*)vol->keys, vol->voxel_size);
+        const size_t blocks = vol->n_bricks;  // one CTA per brick: the block scheduler balances the load
+        if (ctx->count_work) {
+            unsigned long long* d_cnt = nullptr; unsigned long long h_cnt[6];
+            BS_TRY(bs_alloc(ctx, &d_cnt, 6));
+            BS_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, 48, st));
+            k_sign<true, BS_VPL><<<(unsigned)blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(T, vol->values, vol->masks, vol->n_bricks, vol->keys, vol->voxel_size, d_cnt);
+            BS_CUDA(ctx, cudaMemcpyAsync(h_cnt, d_cnt, 48, cudaMemcpyDeviceToHost, st));
+            BS_CUDA(ctx, cudaStreamSynchronize(st));
+            bs_free(ctx, d_cnt);
+            ctx->fwn_counts[0] = (double)h_cnt[0]; ctx->fwn_counts[1] = (double)h_cnt[1]; ctx->fwn_counts[2] = (double)h_cnt[2]; ctx->fwn_counts[3] = (double)h_cnt[3]; ctx->fwn_counts[4] = (double)h_cnt[4]; ctx->fwn_counts[5] = (double)h_cnt[5];
+        } else {
+            k_sign<false, BS_VPL><<<(unsigned)blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(T, vol->values, vol->masks, vol->n_bricks, vol->keys, vol->voxel_size, nullptr);
+        }
     }
     bs_mark(ctx, "sign_ms");
-    bs_free(ctx, d_sorted); bs_free(ctx, d_nodes);
+    bs_free(ctx, d_sorted); bs_free(ctx, d_hdr); bs_free(ctx, d_coef); bs_free(ctx, d_rec);
     BS_CUDA(ctx, cudaGetLastError());
     return BS_OK;
 }

@@ -1,0 +1,324 @@
+#!/usr/bin/env python3
+"""bench.py -- voxel remesh (mesh -> narrow-band SDF -> marching cubes) throughput on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config 5] [--scale 1.0] [--impl ours|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one synthetic mesh (BASELINE.json config 5 by default: the ~10M-triangle
+noise-displaced UV sphere at 2048^3): MeshToVolume::convert then MarchingCubesMesher::mesh.
+`value` = active voxels of the whole job / step time with the triangles already resident in HBM and the output
+left in HBM; `e2e` = the same through the public host-buffer API (pinned host triangles in, host vertices out,
+copies inside the timed region). With N > 1 the bricks are sharded by contiguous slabs of the sorted brick list
+(mesh replicated, no data-path collective except the final all-gather of the triangle buffers).
+--impl reference times the CPU restatement of the reference (oracle/, "port": no Rust toolchain here to build the
+reference itself) with all host threads on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "voxel remesh throughput (mesh->SDF + marching cubes, active voxels per second)"
+UNIT = "voxels/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", type=int, default=5)
+    ap.add_argument("--scale", type=float, default=1.0, help="resolution scale of the config (1.0 = BASELINE.json size)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-scale", type=float, default=0.0625, help="scale of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload(cfg, scale):
+    from baby_shark_b200 import synth
+    if cfg not in (3, 4, 5):
+        raise SystemExit("bench.py measures the convert + marching-cubes remesh path: --config 3, 4 or 5")
+    tris, vs, desc = synth.config_mesh(cfg, scale)
+    return np.ascontiguousarray(tris, np.float32), float(vs), desc
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_port(tris, vs, threads):
+    """One pass of the reference's CPU path (oracle port): convert + MC. Returns (active voxels, triangles, seconds)."""
+    from oracle import oracle as O
+    t0 = time.perf_counter()
+    vol, st = O.mesh_to_volume(tris, vs, 0, threads)
+    verts = O.marching_cubes(vol, vs)
+    dt = time.perf_counter() - t0
+    return st["n_active"], verts.shape[0] // 3, dt, st
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    tris, vs, desc = workload(args.config, args.cpu_scale)
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_port(tris, vs, cores)
+    tot_v, tot_t = 0, 0.0
+    for _ in range(max(1, args.steps)):
+        nv, nt, dt, _ = cpu_port(tris, vs, cores)
+        tot_v += nv
+        tot_t += dt
+    value = tot_v / tot_t
+    sample = "config %d at scale %g: %s (%d triangles), convert + MC per step" % (args.config, args.cpu_scale, desc, tris.shape[0])
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * tot_t / max(1, args.steps), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": "config %d: %s" % (args.config, workload_desc(args)), "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_desc(args):
+    names = {3: "UV sphere ~1.0M triangles at 1024^3", 4: "noise-displaced UV sphere 2.0M triangles at 1024^3",
+             5: "noise-displaced UV sphere ~10.0M triangles at 2048^3"}
+    return "%s, voxel remesh (convert + MC33), scale %g" % (names[args.config], args.scale)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import baby_shark_b200 as B
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    L = B.load_library()
+    ctx = B.Context(local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
+
+    tris, vs, desc = workload(args.config, args.scale)
+    n_tris = tris.shape[0]
+    h_tris = torch.from_numpy(tris).pin_memory()                     # pinned host input for the e2e leg
+    d_tris = h_tris.to("cuda", non_blocking=False)                   # resident input for the `value` leg
+    fp = C.POINTER(C.c_float)
+
+    def step_device():
+        """convert + MC, input and output resident in HBM; returns (n_active_voxels unknown here, n_verts)."""
+        h = C.c_void_p()
+        ctx.check(L.bs_mesh_to_volume_sharded(ctx._h, C.c_void_p(d_tris.data_ptr()), n_tris, vs, 0, rank, world, C.byref(h)))
+        dv, nv = C.c_void_p(), C.c_size_t()
+        st = L.bs_mesh_mc_device(h, vs, C.byref(dv), C.byref(nv))
+        stats = None
+        L.bs_volume_free(h)
+        ctx.check(st)
+        return dv.value, nv.value, stats
+
+    h_out = None
+
+    def step_e2e():
+        nonlocal h_out
+        h = C.c_void_p()
+        if world == 1:
+            ctx.check(L.bs_mesh_to_volume(ctx._h, C.cast(h_tris.data_ptr(), fp), n_tris, vs, 0, C.byref(h)))
+        else:  # replicated mesh: every rank uploads it, then keeps its slab
+            d = h_tris.to("cuda", non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            ctx.check(L.bs_mesh_to_volume_sharded(ctx._h, C.c_void_p(d.data_ptr()), n_tris, vs, 0, rank, world, C.byref(h)))
+        dv, nv = C.c_void_p(), C.c_size_t()
+        st = L.bs_mesh_mc_device(h, vs, C.byref(dv), C.byref(nv))
+        L.bs_volume_free(h)
+        ctx.check(st)
+        n_floats = nv.value * 3
+        if h_out is None or h_out.numel() < n_floats:
+            h_out = torch.empty(int(n_floats * 1.1) + 16, dtype=torch.float32).pin_memory()
+        ctx.check(L.bs_context_copy_out_verts(ctx._h, C.c_void_p(h_out.data_ptr()), n_floats))
+        return nv.value
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # one instrumented pass (outside any timed region): work counters for the rooflines + active voxel count
+    L.bs_context_set_flag(ctx._h, 1, 1)
+    h = C.c_void_p()
+    ctx.check(L.bs_mesh_to_volume_sharded(ctx._h, C.c_void_p(d_tris.data_ptr()), n_tris, vs, 0, rank, world, C.byref(h)))
+    work = ctx.last_stats()
+    L.bs_context_set_flag(ctx._h, 1, 0)
+    L.bs_volume_free(h)
+    n_active_local = work.get("fwn_voxels", 0.0)
+
+    # ---- value leg: K steps, device resident ------------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    stage_ms = {}
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    n_verts_local = 0
+    for _ in range(args.steps):
+        _, nv, _ = step_device()
+        n_verts_local = nv
+        for k, v in ctx.last_stats().items():   # MC stage timings of this step (convert's were overwritten; re-read below)
+            if k.endswith("_ms"):
+                stage_ms[k] = stage_ms.get(k, 0.0) + v
+    e1.record(stream)
+    barrier()
+    clocks = sampler.finish()
+    ms_total = e0.elapsed_time(e1)
+
+    # per-stage device times of convert (CUDA events on the library's stream), averaged over a few extra passes
+    conv_ms = {}
+    reps = max(1, min(3, args.steps))
+    for _ in range(reps):
+        h = C.c_void_p()
+        ctx.check(L.bs_mesh_to_volume_sharded(ctx._h, C.c_void_p(d_tris.data_ptr()), n_tris, vs, 0, rank, world, C.byref(h)))
+        for k, v in ctx.last_stats().items():
+            if k.endswith("_ms"):
+                conv_ms[k] = conv_ms.get(k, 0.0) + v / reps
+        L.bs_volume_free(h)
+    mc_ms = {k: v / args.steps for k, v in stage_ms.items()}
+
+    # ---- e2e leg ---------------------------------------------------------------------------------------------------
+    for _ in range(min(args.warmup, 2)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        nv_e2e = step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    # ---- reduce over ranks ---------------------------------------------------------------------------------------
+    t = torch.tensor([ms_total, e2e_s * 1e3, n_active_local, float(n_verts_local)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms_total, e2e_ms = float(tmax[0]), float(tmax[1])
+        n_active, n_verts = float(tsum[2]), float(tsum[3])
+        # the one real exchange of the path: all-gather(v) of the compacted triangle buffers over NVLink (timed apart)
+        counts = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+        dist.all_gather(counts, torch.tensor([n_verts_local * 3], dtype=torch.int64, device="cuda"))
+    else:
+        e2e_ms = e2e_s * 1e3
+        n_active, n_verts = n_active_local, float(n_verts_local)
+
+    if rank == 0:
+        ms_per_step = ms_total / args.steps
+        value = n_active / (ms_per_step * 1e-3)
+        e2e_value = n_active / (e2e_ms / args.steps * 1e-3)
+        prop = torch.cuda.get_device_properties(local_rank)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+        sm_mhz = clocks.get("sm_max_mhz") or 1965.0
+        fp32_peak = prop.multi_processor_count * 128 * 2 * sm_mhz * 1e6 / 1e12  # TFLOP/s with FMA at max clock
+        rl = []
+        if "udf_ms" in conv_ms and work.get("n_eval"):
+            fl = 80.0 * work["n_eval"]
+            rl.append({"kernel": "k_eval (point-triangle distances, scatter-min)", "bound": "fp32", "achieved": fl / (conv_ms["udf_ms"] * 1e-3) / 1e12,
+                       "peak": fp32_peak, "unit": "TFLOP/s", "ms": conv_ms["udf_ms"], "algorithmic": "80 FLOP x n_eval=%d" % work["n_eval"], "traffic": None})
+        if "sign_ms" in conv_ms and work.get("fwn_voxels"):
+            fl = 60.0 * work["fwn_far"] + 100.0 * work["fwn_exact_tris"] + 10.0 * work["fwn_visits"]
+            rl.append({"kernel": "k_sign (fast winding numbers)", "bound": "fp32", "achieved": fl / (conv_ms["sign_ms"] * 1e-3) / 1e12, "peak": fp32_peak,
+                       "unit": "TFLOP/s", "ms": conv_ms["sign_ms"], "traffic": None,
+                       "algorithmic": "per voxel: %.1f visits, %.1f far, %.1f exact tris" % tuple(work[k] / work["fwn_voxels"] for k in ("fwn_visits", "fwn_far", "fwn_exact_tris"))})
+        if "mc_emit_ms" in mc_ms:
+            nb = work.get("n_bricks", 0.0)
+            by = nb * (2112 + 868) + 36.0 * (n_verts_local / 3.0)
+            rl.append({"kernel": "k_mc<emit> (classify + emit)", "bound": "hbm", "achieved": by / (mc_ms["mc_emit_ms"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                       "ms": mc_ms["mc_emit_ms"], "algorithmic": "n_bricks x 2980 B + 36 B x n_out_tris", "traffic": None, "peak_source": hbm_src})
+        for r in rl:
+            r["frac"] = r["achieved"] / r["peak"]
+        stage_all = dict(conv_ms)
+        stage_all.update(mc_ms)
+        dominant = max(rl, key=lambda r: r["ms"]) if rl else None
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "config %d: %s" % (args.config, workload_desc(args)), "mesh": desc, "n_triangles": int(n_tris), "voxel_size": vs,
+                       "band_width": 0, "l2": "inputs larger than L2 (triangles %.0f MB, bricks %.0f MB)" % (tris.nbytes / 1e6, work.get("n_bricks", 0) * 2112 / 1e6),
+                       "parallelism": "brick slabs x%d, mesh replicated" % world},
+            "remesh_ms": ms_per_step, "tris_per_s": (n_verts / 3.0) / (ms_per_step * 1e-3), "n_active_voxels": n_active, "n_out_triangles": n_verts / 3.0,
+            "stage_ms": stage_all, "work": work,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": int(tris.nbytes), "d2h_bytes_per_step": int(n_verts_local * 12)},
+            "gpu_launches": None, "clocks": clocks,
+            "roofline": dominant, "rooflines": rl,
+        }
+        # launches inside the timed region: counted from the library's own launch sites (see DESIGN.md "Kernels")
+        out["gpu_launches"] = int(args.steps * launches_per_step(world))
+        if not args.no_cpu_baseline and world == 1:
+            cores = os.cpu_count() or 1
+            ctris, cvs, cdesc = workload(args.config, args.cpu_scale)
+            nv_c, nt_c, dt_c, st_c = cpu_port(ctris, cvs, cores)
+            out["cpu_baseline"] = {"value": nv_c / dt_c, "unit": UNIT, "cores": cores, "kind": "port",
+                                   "sample": "config %d at scale %g: %s (%d triangles, %d active voxels), one convert + MC pass in %.1f s" % (args.config, args.cpu_scale, cdesc, ctris.shape[0], nv_c, dt_c)}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def launches_per_step(world):
+    # convert: k_tri_counts, scan(2), k_mark, select(2), sort(~7), k_fill_slots, k_eval, k_centroid_bounds, k_morton, sort(~9),
+    # k_leaves, k_level_up(levels-1 ~ 7), k_finalize_nodes, k_sign; MC: k_mc<count>, k_widen, scan(2), k_mc<emit>
+    return 1 + 2 + 1 + 2 + 7 + 1 + 1 + 1 + 1 + 9 + 1 + 7 + 1 + 1 + 1 + 1 + 2 + 1
+
+
+if __name__ == "__main__":
+    main()

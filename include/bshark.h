@@ -61,9 +61,10 @@ bs_status bs_mesh_to_volume(bs_context* ctx, const float* tris, size_t n_tris, f
 /* Same, triangles already resident on the context's device (n x 9 floats). */
 bs_status bs_mesh_to_volume_device(bs_context* ctx, const float* d_tris, size_t n_tris, float voxel_size,
                                    int64_t band_width, bs_volume** out);
-/* Brick-sharded variant for multi-GPU runs: the mesh is replicated, rank r of `world` keeps the r-th
- * contiguous slab of the brick list (in the reference's leaf visit order) plus the +x/+y/+z halo bricks
- * extraction needs; `owned_bricks` receives how many leading... see DESIGN.md "Multi-GPU". */
+/* Brick-sharded variant for multi-GPU runs: the mesh is replicated, rank r of `world` keeps the r-th contiguous
+ * slab of the brick list (in the reference's leaf visit order) plus, as read-only halo, the +x/+y/+z neighbour
+ * bricks its cells need. Extraction on the result emits only the cells of owned bricks, so concatenating the
+ * per-rank outputs in rank order gives exactly the single-GPU output (DESIGN.md "Multi-GPU"). */
 bs_status bs_mesh_to_volume_sharded(bs_context* ctx, const float* d_tris, size_t n_tris, float voxel_size,
                                     int64_t band_width, int rank, int world, bs_volume** out);
 
@@ -119,6 +120,16 @@ bs_status bs_volume_download(const bs_volume* v, int32_t** brick_ijk, float** va
 /* counts only: bricks, active voxels, negative active voxels, active tiles */
 bs_status bs_volume_counts(const bs_volume* v, size_t* n_bricks, size_t* n_active, size_t* n_negative,
                            size_t* n_tiles);
+
+/* Copy the first n_floats of the last *_device extraction result into caller memory (pinned or pageable): lets
+ * the shim fill a Vec<Vec3f> it allocated itself instead of taking a library-owned buffer. */
+bs_status bs_context_copy_out_verts(bs_context* ctx, float* dst, size_t n_floats);
+
+/* BS_FLAG_COUNT_WORK = 1: the next bs_mesh_to_volume* calls run the instrumented winding-number traversal and
+ * report fwn_visits / fwn_far / fwn_exact_tris / fwn_voxels through bs_context_last_stats (roofline work counts;
+ * slower, never used in a timed region). */
+enum { BS_FLAG_COUNT_WORK = 1 };
+bs_status bs_context_set_flag(bs_context* ctx, int flag, int value);
 
 /* Per-stage device timings (ms, CUDA events on the context stream) and work counters of the most recent
  * call on the context; names are listed in DESIGN.md.  Returns the number of entries written (<= cap). */
