@@ -14,6 +14,7 @@
 #include "mc33_tables.h"
 #include <cub/cub.cuh>
 #include <cfloat>
+#include <algorithm>
 
 namespace {
 
@@ -288,15 +289,17 @@ __device__ __forceinline__ bool load_cell(Cell& q, const float* s_val, const uns
     return all;
 }
 
+// `pos` maps a brick to its rank in the merged (bricks + active tiles) visit order; nullptr = identity.
 template <bool WRITE>
-__global__ void __launch_bounds__(MC_TPB) k_mc(VolView V, const signed char* __restrict__ tables, float vs,
-                                                unsigned* brick_counts, const unsigned long long* __restrict__ brick_offsets, float* out) {
+__global__ void __launch_bounds__(MC_TPB) k_mc(VolView V, const signed char* __restrict__ tables, float vs, const unsigned* __restrict__ pos,
+                                                unsigned* item_counts, const unsigned long long* __restrict__ item_offsets, float* out) {
     __shared__ float s_val[729];
     __shared__ unsigned char s_act[732];
     __shared__ long long s_nb[8];
     __shared__ int s_org[3];
     const size_t b = blockIdx.x;
-    if (WRITE) { if (brick_offsets[b + 1] == brick_offsets[b]) return; }  // uniform per block
+    const size_t item = pos ? pos[b] : b;
+    if (WRITE) { if (item_offsets[item + 1] == item_offsets[item]) return; }  // uniform per block
     stage_brick(V, b, s_val, s_act, s_nb, s_org);
     const unsigned tid = threadIdx.x;  // == leaf offset x<<6 | y<<3 | z of the cell's corner 0
     Cell q; q.T = tables; q.v12 = f3{0.f, 0.f, 0.f};
@@ -311,9 +314,98 @@ __global__ void __launch_bounds__(MC_TPB) k_mc(VolView V, const signed char* __r
     __shared__ typename Scan::TempStorage tmp;
     int excl, total;
     Scan(tmp).ExclusiveSum(n, excl, total);
-    if (!WRITE) { if (tid == 0) brick_counts[b] = (unsigned)total; return; }
-    float* dst = out + (brick_offsets[b] + (unsigned long long)excl) * 9;
+    if (!WRITE) { if (tid == 0) item_counts[item] = (unsigned)total; return; }
+    float* dst = out + (item_offsets[item] + (unsigned long long)excl) * 9;
     for (int i = 0; i < n * 9; ++i) dst[i] = local[i];
+}
+
+// TreeNode::at on the flat volume: a brick voxel if active, else the value of an active tile covering it
+__device__ bool value_at(const VolView& V, int x, int y, int z, float& v) {
+    const unsigned long long k = bs_brick_key(x >> 3, y >> 3, z >> 3);
+    long long i = find_key(V.keys, V.n, k);
+    if (i >= 0) {
+        const unsigned off = ((x & 7) << 6) | ((y & 7) << 3) | (z & 7);
+        if (!((V.masks[i * 8 + (off >> 6)] >> (off & 63)) & 1)) return false;
+        v = V.values[i * 512 + off];
+        return true;
+    }
+    i = V.nt8 ? find_key(V.t8k, V.nt8, k) : -1;
+    if (i >= 0) { v = V.t8v[i]; return true; }
+    i = V.nt128 ? find_key(V.t128k, V.nt128, k >> 12) : -1;
+    if (i >= 0) { v = V.t128v[i]; return true; }
+    return false;
+}
+
+// Active tiles (CubesVisitor::tile, marching_cubes.rs:970-994): only the boundary voxels of the tile are tested, in
+// the reference's order -- for i, for j: left, right, top, bottom, front, back -- so edge and corner voxels are
+// visited (and their triangles emitted) more than once, exactly like the reference. One CTA per tile.
+template <bool WRITE>
+__global__ void __launch_bounds__(256) k_mc_tiles(VolView V, const signed char* __restrict__ tables, float vs, int level /*0: 8^3, 1: 128^3*/,
+                                                  const unsigned* __restrict__ pos, unsigned* item_counts, const unsigned long long* __restrict__ item_offsets, float* out) {
+    const size_t ti = blockIdx.x;
+    const size_t item = pos[ti];
+    int bx, by, bz;
+    if (level == 0) bs_key_brick(V.t8k[ti], bx, by, bz); else bs_key_brick(V.t128k[ti] << 12, bx, by, bz);
+    const int s = level == 0 ? 8 : 128;
+    const int ox = bx << 3, oy = by << 3, oz = bz << 3;
+    const unsigned n_visits = 6u * s * s;
+    typedef cub::BlockScan<int, 256> Scan;
+    __shared__ typename Scan::TempStorage tmp;
+    unsigned long long running = 0;
+    for (unsigned base = 0; base < n_visits; base += 256) {
+        const unsigned vi = base + threadIdx.x;
+        int n = 0;
+        float local[WRITE ? 12 * 9 : 1];
+        if (vi < n_visits) {
+            const int face = vi % 6, ij = vi / 6, i = ij / s, j = ij % s;
+            int x, y, z;
+            switch (face) {
+                case 0: x = 0; y = i; z = j; break;          // left
+                case 1: x = s - 1; y = i; z = j; break;      // right
+                case 2: x = i; y = j; z = s - 1; break;      // top
+                case 3: x = i; y = j; z = 0; break;          // bottom
+                case 4: x = i; y = s - 1; z = j; break;      // front
+                default: x = i; y = 0; z = j; break;         // back
+            }
+            Cell q; q.T = tables; q.v12 = f3{0.f, 0.f, 0.f};
+            q.ox = ox + x; q.oy = oy + y; q.oz = oz + z;
+            int id = 0; bool all = true;
+            for (int c = 0; c < 8 && all; ++c) {
+                float v;
+                all = value_at(V, q.ox + c_corner[c][0], q.oy + c_corner[c][1], q.oz + c_corner[c][2], v);
+                if (!all) break;
+                if (fabsf(v) < MIN_ABS) v = copysignf(MIN_ABS, v);
+                if (v < 0.f) id |= 1 << c;
+                q.c[c] = v;
+            }
+            if (all && id != 0 && id != 255) {
+                q.cs = tables[MC33_OFF_CASES + 2 * id]; q.cf = tables[MC33_OFF_CASES + 2 * id + 1];
+                n = emit_cell<WRITE>(q, vs, local);
+            }
+        }
+        int excl, total;
+        Scan(tmp).ExclusiveSum(n, excl, total);
+        __syncthreads();
+        if (WRITE) {
+            float* dst = out + (item_offsets[item] + running + (unsigned long long)excl) * 9;
+            for (int k = 0; k < n * 9; ++k) dst[k] = local[k];
+        }
+        running += (unsigned long long)total;
+    }
+    if (!WRITE && threadIdx.x == 0) item_counts[item] = (unsigned)running;
+}
+
+// rank of every brick / tile in the merged key order (a 128^3 tile sorts by its 16^3-node key)
+__global__ void k_merge_pos(VolView V, unsigned* pos_brick, unsigned* pos_t8, unsigned* pos_t128) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    auto lb = [](const unsigned long long* keys, size_t n, unsigned long long k, int shift) {
+        size_t lo = 0, hi = n;
+        while (lo < hi) { size_t mid = (lo + hi) >> 1; if ((keys[mid] << shift) < k) lo = mid + 1; else hi = mid; }
+        return (unsigned)lo;
+    };
+    if (i < V.n) pos_brick[i] = (unsigned)i + lb(V.t8k, V.nt8, V.keys[i], 0) + lb(V.t128k, V.nt128, V.keys[i], 12);
+    if (i < V.nt8) pos_t8[i] = (unsigned)i + lb(V.keys, V.n, V.t8k[i], 0) + lb(V.t128k, V.nt128, V.t8k[i], 12);
+    if (i < V.nt128) pos_t128[i] = (unsigned)i + lb(V.keys, V.n, V.t128k[i] << 12, 0) + lb(V.t8k, V.nt8, V.t128k[i] << 12, 0);
 }
 
 __global__ void k_widen(const unsigned* in, unsigned long long* out, size_t n) {
@@ -340,27 +432,37 @@ bs_status bs_mc_impl(const bs_volume* v, float voxel_size, const float** d_verts
     cudaStream_t st = ctx->stream;
     *d_verts = nullptr; *n_verts = 0;
     bs_marks_begin(ctx);
-    if (v->n_tiles8 || v->n_tiles128) return bs_fail(ctx, BS_ERR_UNSUPPORTED, "marching cubes over active tiles is not implemented on the device yet");
-    const size_t n = v->n_bricks;
-    if (n == 0) { bs_marks_end(ctx); return BS_OK; }
-    VolView V{(const unsigned long long*)v->keys, v->values, (const unsigned long long*)v->masks, n,
-              (const unsigned long long*)v->tile8_keys, v->tile8_values, v->n_tiles8,
-              (const unsigned long long*)v->tile128_keys, v->tile128_values, v->n_tiles128};
-    unsigned* d_counts = nullptr; unsigned long long *d_wide = nullptr, *d_off = nullptr;
-    BS_TRY(bs_alloc(ctx, &d_counts, n)); BS_TRY(bs_alloc(ctx, &d_wide, n + 1)); BS_TRY(bs_alloc(ctx, &d_off, n + 1));
-    k_mc<false><<<(unsigned)n, MC_TPB, 0, st>>>(V, (const signed char*)ctx->d_mc33, voxel_size, d_counts, nullptr, nullptr);
-    k_widen<<<bs_blocks(n + 1, 256), 256, 0, st>>>(d_counts, d_wide, n);
+    const size_t n = v->n_bricks, nt8 = v->n_tiles8, nt128 = v->n_tiles128, n_items = n + nt8 + nt128;
+    if (n_items == 0) { bs_marks_end(ctx); return BS_OK; }
+    VolView V{v->keys, v->values, v->masks, n, v->tile8_keys, v->tile8_values, nt8, v->tile128_keys, v->tile128_values, nt128};
+    const signed char* tables = (const signed char*)ctx->d_mc33;
+    unsigned *d_counts = nullptr, *d_pos = nullptr; unsigned long long *d_wide = nullptr, *d_off = nullptr;
+    BS_TRY(bs_alloc(ctx, &d_counts, n_items)); BS_TRY(bs_alloc(ctx, &d_wide, n_items + 1)); BS_TRY(bs_alloc(ctx, &d_off, n_items + 1));
+    const bool tiles = nt8 || nt128;
+    if (tiles) {
+        BS_TRY(bs_alloc(ctx, &d_pos, n_items));
+        k_merge_pos<<<bs_blocks(std::max(n, std::max(nt8, nt128)), 256), 256, 0, st>>>(V, d_pos, d_pos + n, d_pos + n + nt8);
+    }
+    if (n) k_mc<false><<<(unsigned)n, MC_TPB, 0, st>>>(V, tables, voxel_size, d_pos, d_counts, nullptr, nullptr);
+    if (nt8) k_mc_tiles<false><<<(unsigned)nt8, 256, 0, st>>>(V, tables, voxel_size, 0, d_pos + n, d_counts, nullptr, nullptr);
+    if (nt128) k_mc_tiles<false><<<(unsigned)nt128, 256, 0, st>>>(V, tables, voxel_size, 1, d_pos + n + nt8, d_counts, nullptr, nullptr);
+    k_widen<<<bs_blocks(n_items + 1, 256), 256, 0, st>>>(d_counts, d_wide, n_items);
     void* d_tmp = nullptr; size_t tmp_bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_wide, d_off, n + 1, st);
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_wide, d_off, n_items + 1, st);
     BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp_bytes));
-    cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_wide, d_off, n + 1, st);
+    cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_wide, d_off, n_items + 1, st);
     unsigned long long n_tris = 0;
-    BS_CUDA(ctx, cudaMemcpyAsync(&n_tris, d_off + n, sizeof(n_tris), cudaMemcpyDeviceToHost, st));
+    BS_CUDA(ctx, cudaMemcpyAsync(&n_tris, d_off + n_items, sizeof(n_tris), cudaMemcpyDeviceToHost, st));
     BS_CUDA(ctx, cudaStreamSynchronize(st));
     bs_mark(ctx, "mc_count_ms");
     bs_status s = bs_ensure_out_verts(ctx, (size_t)n_tris * 9);
-    if (s == BS_OK && n_tris) k_mc<true><<<(unsigned)n, MC_TPB, 0, st>>>(V, (const signed char*)ctx->d_mc33, voxel_size, nullptr, d_off, ctx->d_out_verts);
+    if (s == BS_OK && n_tris) {
+        if (n) k_mc<true><<<(unsigned)n, MC_TPB, 0, st>>>(V, tables, voxel_size, d_pos, nullptr, d_off, ctx->d_out_verts);
+        if (nt8) k_mc_tiles<true><<<(unsigned)nt8, 256, 0, st>>>(V, tables, voxel_size, 0, d_pos + n, nullptr, d_off, ctx->d_out_verts);
+        if (nt128) k_mc_tiles<true><<<(unsigned)nt128, 256, 0, st>>>(V, tables, voxel_size, 1, d_pos + n + nt8, nullptr, d_off, ctx->d_out_verts);
+    }
     bs_mark(ctx, "mc_emit_ms");
+    bs_free(ctx, d_pos);
     bs_free(ctx, d_tmp); bs_free(ctx, d_counts); bs_free(ctx, d_wide); bs_free(ctx, d_off);
     if (s != BS_OK) return s;
     BS_CUDA(ctx, cudaGetLastError());

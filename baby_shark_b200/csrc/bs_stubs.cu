@@ -1,7 +1,4 @@
 // Stages not implemented on the device yet report BS_ERR_UNSUPPORTED (never a CPU fallback).
 #include "bs_common.cuh"
 bs_status bs_dc_impl(const bs_volume* v, float, const float**, size_t*) { return bs_fail(v->ctx, BS_ERR_UNSUPPORTED, "dual contouring: not implemented yet"); }
-bs_status bs_csg_impl(bs_volume* a, bs_volume*, int, bs_volume**) { return bs_fail(a->ctx, BS_ERR_UNSUPPORTED, "csg: not implemented yet"); }
 bs_status bs_offset_impl(bs_volume* a, float, bs_volume**) { return bs_fail(a->ctx, BS_ERR_UNSUPPORTED, "offset: not implemented yet"); }
-bs_status bs_from_voxels_impl(bs_context* ctx, const int32_t*, const float*, size_t, float, bs_volume**) { return bs_fail(ctx, BS_ERR_UNSUPPORTED, "from_voxels: not implemented yet"); }
-bs_status bs_builder_impl(bs_context* ctx, int, float, const float*, bs_volume**) { return bs_fail(ctx, BS_ERR_UNSUPPORTED, "builders: not implemented yet"); }
