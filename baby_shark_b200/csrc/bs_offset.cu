@@ -1,0 +1,375 @@
+// Volume::offset on sorted bricks: prune, fast-sweep Eikonal extension, shift (sm_100a).
+// Replaces Volume::offset (src/voxel/volume/mod.rs:95-108) and FastSweeping (src/voxel/fast_sweep.rs:30-287,
+// compute_distance :509-537).
+//
+// The reference runs ONE pass of 8 directional block Gauss-Seidel sweeps. Inside a sweep it pops leaves from a
+// heap ordered lexicographically in the sweep direction, sweeps the 8^3 voxels of a leaf x-outer/z-inner in that
+// direction (every update reads the six face neighbours as they are at that moment), then queues the next leaf
+// along each axis whose exit face holds a value of the sweep's sign below the limit; everything popped in a
+// sweep is queued again for the next one. That order is a topological order of "a leaf after its three upstream
+// face neighbours and before its three downstream ones", and the same holds for voxels inside a leaf, so the
+// result is reproduced exactly by two nested hyperplane wavefronts: leaves with equal +-X+-Y+-Z run concurrently
+// (one CTA each), and inside a CTA the voxels with equal +-x+-y+-z (22 steps). Dynamic queueing becomes a
+// monotone per-brick flag set by the upstream CTA before the next leaf wavefront is launched.
+//
+// Bricks the sweeps may create are pre-allocated empty (dilation of the pruned brick set); a push outside that
+// set raises a flag and the whole operation is retried with a wider dilation.
+#include "bs_common.cuh"
+#include <cub/cub.cuh>
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <vector>
+
+namespace {
+
+typedef unsigned long long u64;
+constexpr int TPB = 256;
+
+__device__ __forceinline__ long long find_key(const u64* keys, size_t n, u64 k) {
+    size_t lo = 0, hi = n;
+    while (lo < hi) { size_t mid = (lo + hi) >> 1; if (keys[mid] < k) lo = mid + 1; else hi = mid; }
+    return (lo < n && keys[lo] == k) ? (long long)lo : -1;
+}
+
+// remove_if(|v| > 2 vs) (volume/mod.rs:96; leaf_node/tree_node.rs remove_if): clears mask bits; flags non-empty bricks
+__global__ void k_prune(const float* __restrict__ values, const u64* __restrict__ masks, size_t n, float thr, u64* out_masks, unsigned char* nonempty) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;  // one thread per mask word
+    if (i >= n * 8) return;
+    u64 m = masks[i], keep = 0;
+    const float* v = values + i * 64;
+    while (m) { const int b = __ffsll((long long)m) - 1; m &= m - 1; if (!(fabsf(v[b]) > thr)) keep |= 1ull << b; }
+    out_masks[i] = keep;
+    if (keep) nonempty[i >> 3] = 1;
+}
+// 27-neighbourhood dilation step of a brick key set
+__global__ void k_dilate(const u64* __restrict__ keys, size_t n, u64* out, int* flags) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n * 27) return;
+    const size_t b = i / 27; const int d = (int)(i % 27);
+    int bx, by, bz; bs_key_brick(keys[b], bx, by, bz);
+    bx += d / 9 - 1; by += (d / 3) % 3 - 1; bz += d % 3 - 1;
+    if (bx < BS_BRICK_MIN || bx > BS_BRICK_MAX || by < BS_BRICK_MIN || by > BS_BRICK_MAX || bz < BS_BRICK_MIN || bz > BS_BRICK_MAX) { flags[0] = 1; out[i] = keys[b]; return; }
+    out[i] = bs_brick_key(bx, by, bz);
+}
+struct IsSet { const unsigned char* f; __device__ bool operator()(const u64&) const { return true; } };
+// scatter the pruned source bricks into the (sorted, dilated) working set and record the six face neighbours
+__global__ void k_place(const u64* __restrict__ src_keys, const float* __restrict__ src_values, const u64* __restrict__ src_masks, const unsigned char* __restrict__ nonempty,
+                        size_t n_src, const u64* __restrict__ keys, size_t n, float* values, u64* masks, u64* frozen, unsigned char* inq) {
+    const size_t b = blockIdx.x;
+    if (!nonempty[b]) return;
+    const long long dst = find_key(keys, n, src_keys[b]);
+    const unsigned t = threadIdx.x;
+    values[dst * 512 + t] = src_values[b * 512 + t];
+    if (t < 8) { masks[dst * 8 + t] = src_masks[b * 8 + t]; frozen[dst * 8 + t] = src_masks[b * 8 + t]; }
+    if (t == 0) inq[dst] = 1;
+}
+__global__ void k_neighbours(const u64* __restrict__ keys, size_t n, int* nbr /*6 per brick: +x -x +y -y +z -z*/) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n * 6) return;
+    const size_t b = i / 6; const int d = (int)(i % 6);
+    int bx, by, bz; bs_key_brick(keys[b], bx, by, bz);
+    const int s = (d & 1) ? -1 : 1;
+    if (d < 2) bx += s; else if (d < 4) by += s; else bz += s;
+    long long j = -1;
+    if (bx >= BS_BRICK_MIN && bx <= BS_BRICK_MAX && by >= BS_BRICK_MIN && by <= BS_BRICK_MAX && bz >= BS_BRICK_MIN && bz <= BS_BRICK_MAX) j = find_key(keys, n, bs_brick_key(bx, by, bz));
+    nbr[i] = (int)j;
+}
+
+// helpers/utils.rs:4-16 + fast_sweep.rs:509-537
+__device__ __forceinline__ float compute_distance(float a1, float a2, float a3, float h) {
+    float t;
+    if (a1 > a3) { t = a1; a1 = a3; a3 = t; }
+    if (a1 > a2) { t = a1; a1 = a2; a2 = t; }
+    if (a2 > a3) { t = a2; a2 = a3; a3 = t; }
+    const float s1 = xadd(a1, h);
+    if (fabsf(s1) <= a2) return s1;
+    const float a12 = xadd(a1, a2), hsq = xmul(h, h), two = xadd(hsq, hsq), d12 = xsub(a1, a2), d12s = xmul(d12, d12);
+    const float s2 = xmul(xadd(a12, xsqrt(xsub(two, d12s))), 0.5f);
+    if (fabsf(s2) <= a3) return s2;
+    const float a123 = xadd(a12, a3), three = xadd(two, hsq), d13 = xsub(a1, a3), d13s = xmul(d13, d13), d23 = xsub(a2, a3), d23s = xmul(d23, d23);
+    return xmul(xadd(a123, xsqrt(xsub(xsub(xsub(three, d12s), d13s), d23s))), xdiv(1.0f, 3.0f));
+}
+
+struct SweepParams {
+    float* values; u64* masks; const u64* frozen; const int* nbr; unsigned char* inq; int* flags;
+    const unsigned* order;   // bricks of this leaf wavefront
+    float h, limit_abs; int sweep_neg;  // sweep sign: 1 = negative
+    int dir;                 // bit0 = -x, bit1 = -y, bit2 = -z (sweep order fast_sweep.rs:39-60)
+};
+
+// One CTA (64 threads = the (y,z) columns in sweep-local coordinates) per queued leaf of the current leaf wavefront.
+__global__ void __launch_bounds__(64) k_sweep(SweepParams P) {
+    __shared__ float s_v[512];          // centre values
+    __shared__ unsigned char s_a[512];  // centre active
+    __shared__ float s_fv[6][64];       // neighbour faces adjacent to the centre: +x -x +y -y +z -z
+    __shared__ unsigned char s_fa[6][64];
+    const unsigned b = P.order[blockIdx.x];
+    if (!P.inq[b]) return;
+    const unsigned t = threadIdx.x;
+    float* gv = P.values + (size_t)b * 512;
+    for (unsigned i = t; i < 512; i += 64) { s_v[i] = gv[i]; s_a[i] = (P.masks[(size_t)b * 8 + (i >> 6)] >> (i & 63)) & 1; }
+    {   // faces: thread t = (u, v) on the face
+        const unsigned u = t >> 3, v = t & 7;
+#pragma unroll
+        for (int d = 0; d < 6; ++d) {
+            const int nb = P.nbr[(size_t)b * 6 + d];
+            float val = 0.f; unsigned char a = 0;
+            if (nb >= 0) {
+                const unsigned c = (d & 1) ? 7u : 0u;  // the +x neighbour contributes its x = 0 face, the -x neighbour its x = 7 face
+                const unsigned off = d < 2 ? ((c << 6) | (u << 3) | v) : (d < 4 ? ((u << 6) | (c << 3) | v) : ((u << 6) | (v << 3) | c));
+                a = (P.masks[(size_t)nb * 8 + (off >> 6)] >> (off & 63)) & 1;
+                val = P.values[(size_t)nb * 512 + off];
+            }
+            s_fv[d][t] = val; s_fa[d][t] = a;
+        }
+    }
+    __syncthreads();
+    const int sx = (P.dir & 1) ? -1 : 1, sy = (P.dir & 2) ? -1 : 1, sz = (P.dir & 4) ? -1 : 1;
+    const int ly = t >> 3, lz = t & 7;  // sweep-local y, z of this thread's column
+    const u64* fz = P.frozen + (size_t)b * 8;
+    for (int step = 0; step < 22; ++step) {
+        const int lx = step - ly - lz;
+        if (lx >= 0 && lx < 8) {
+            const int x = sx > 0 ? lx : 7 - lx, y = sy > 0 ? ly : 7 - ly, z = sz > 0 ? lz : 7 - lz;
+            const unsigned off = (x << 6) | (y << 3) | z;
+            if (!((fz[off >> 6] >> (off & 63)) & 1)) {  // frozen voxels keep their value (:126-128)
+                // stencil.at for the six face neighbours (:130-146, :360-386)
+                float nv[6]; bool na[6];
+                if (x < 7) { na[0] = s_a[off + 64]; nv[0] = s_v[off + 64]; } else { na[0] = s_fa[0][(y << 3) | z]; nv[0] = s_fv[0][(y << 3) | z]; }
+                if (x > 0) { na[1] = s_a[off - 64]; nv[1] = s_v[off - 64]; } else { na[1] = s_fa[1][(y << 3) | z]; nv[1] = s_fv[1][(y << 3) | z]; }
+                if (y < 7) { na[2] = s_a[off + 8]; nv[2] = s_v[off + 8]; } else { na[2] = s_fa[2][(x << 3) | z]; nv[2] = s_fv[2][(x << 3) | z]; }
+                if (y > 0) { na[3] = s_a[off - 8]; nv[3] = s_v[off - 8]; } else { na[3] = s_fa[3][(x << 3) | z]; nv[3] = s_fv[3][(x << 3) | z]; }
+                if (z < 7) { na[4] = s_a[off + 1]; nv[4] = s_v[off + 1]; } else { na[4] = s_fa[4][(x << 3) | y]; nv[4] = s_fv[4][(x << 3) | y]; }
+                if (z > 0) { na[5] = s_a[off - 1]; nv[5] = s_v[off - 1]; } else { na[5] = s_fa[5][(x << 3) | y]; nv[5] = s_fv[5][(x << 3) | y]; }
+                // option_min_by(+, -, cmp_abs): both present -> the smaller |v|, ties -> the + side
+                float d[3]; bool has[3];
+#pragma unroll
+                for (int ax = 0; ax < 3; ++ax) {
+                    const bool ap = na[2 * ax], an = na[2 * ax + 1];
+                    has[ax] = ap || an;
+                    d[ax] = (ap && an) ? ((fabsf(nv[2 * ax]) > fabsf(nv[2 * ax + 1])) ? nv[2 * ax + 1] : nv[2 * ax]) : (ap ? nv[2 * ax] : nv[2 * ax + 1]);
+                }
+                if (has[0] || has[1] || has[2]) {
+                    const float first = has[0] ? d[0] : (has[1] ? d[1] : d[2]);
+                    if ((int)(__float_as_uint(first) >> 31) == P.sweep_neg) {  // outward / inward (:148-156)
+                        const float d1 = has[0] ? fabsf(d[0]) : FLT_MAX, d2 = has[1] ? fabsf(d[1]) : FLT_MAX, d3 = has[2] ? fabsf(d[2]) : FLT_MAX;
+                        const float dn = compute_distance(d1, d2, d3, P.h);
+                        if (!(dn > P.limit_abs)) {
+                            const float old = s_a[off] ? s_v[off] : FLT_MAX;
+                            if (dn < fabsf(old)) { s_v[off] = P.sweep_neg ? -fabsf(dn) : fabsf(dn); s_a[off] = 1; }  // set_sign (value/f32.rs:11-17)
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // write back + queue the downstream leaves (:185-277)
+    for (unsigned i = t; i < 512; i += 64) gv[i] = s_v[i];
+    {
+        // mask words: 8 words x 64 bits; thread t assembles word t for t < 8
+        if (t < 8) { u64 m = 0; for (int k = 0; k < 64; ++k) m |= (u64)s_a[t * 64 + k] << k; P.masks[(size_t)b * 8 + t] = m; }
+    }
+    const unsigned u = t >> 3, v = t & 7;
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) {
+        const int s = ax == 0 ? sx : (ax == 1 ? sy : sz);
+        const unsigned c = s > 0 ? 7u : 0u;  // exit face; the reference's negative-direction index collapses to local 0 via leaf index masking
+        const unsigned off = ax == 0 ? ((c << 6) | (u << 3) | v) : (ax == 1 ? ((u << 6) | (c << 3) | v) : ((u << 6) | (v << 3) | c));
+        const bool q = s_a[off] && ((int)(__float_as_uint(s_v[off]) >> 31) == P.sweep_neg) && (fabsf(s_v[off]) < P.limit_abs);
+        if (__syncthreads_or(q)) {
+            if (t == 0) {
+                const int nb = P.nbr[(size_t)b * 6 + 2 * ax + (s > 0 ? 0 : 1)];
+                if (nb >= 0) P.inq[nb] = 1; else P.flags[0] = 1;  // outside the pre-allocated set: retry wider
+            }
+        }
+    }
+}
+
+__global__ void k_finish(float* values, const u64* __restrict__ masks, size_t n, float distance, unsigned char* nonempty) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;  // one thread per mask word
+    if (i >= n * 8) return;
+    u64 m = masks[i];
+    if (m) nonempty[i >> 3] = 1;
+    float* v = values + i * 64;
+    while (m) { const int b = __ffsll((long long)m) - 1; m &= m - 1; v[b] = __fsub_rn(v[b], distance); }  // *v -= distance (volume/mod.rs:104)
+}
+__global__ void __launch_bounds__(512) k_compact(const u64* __restrict__ keys, const float* __restrict__ values, const u64* __restrict__ masks, const unsigned* __restrict__ rank,
+                                                  const unsigned char* __restrict__ nonempty, u64* okeys, float* ovalues, u64* omasks) {
+    const size_t b = blockIdx.x;
+    if (!nonempty[b]) return;
+    const size_t o = rank[b] - 1;
+    const unsigned t = threadIdx.x;
+    ovalues[o * 512 + t] = values[b * 512 + t];
+    if (t < 8) omasks[o * 8 + t] = masks[b * 8 + t];
+    if (t == 0) okeys[o] = keys[b];
+}
+__global__ void k_widen8(const unsigned char* in, unsigned* out, size_t n) { const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i < n) out[i] = in[i]; }
+
+struct KeyPass { __device__ bool operator()(const u64&) const { return true; } };
+
+bs_status sort_unique(bs_context* ctx, u64* d_in, size_t n_in, u64** d_out, size_t* n_out) {
+    cudaStream_t st = ctx->stream;
+    u64* d_sorted = nullptr; size_t* d_n = nullptr; void* d_tmp = nullptr; size_t tmp = 0;
+    BS_TRY(bs_alloc(ctx, &d_sorted, n_in)); BS_TRY(bs_alloc(ctx, d_out, n_in)); BS_TRY(bs_alloc(ctx, &d_n, 1));
+    cub::DeviceRadixSort::SortKeys(nullptr, tmp, d_in, d_sorted, n_in, 0, 54, st);
+    BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp));
+    cub::DeviceRadixSort::SortKeys(d_tmp, tmp, d_in, d_sorted, n_in, 0, 54, st);
+    bs_free(ctx, d_tmp); tmp = 0;
+    cub::DeviceSelect::Unique(nullptr, tmp, d_sorted, *d_out, d_n, n_in, st);
+    BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp));
+    cub::DeviceSelect::Unique(d_tmp, tmp, d_sorted, *d_out, d_n, n_in, st);
+    BS_CUDA(ctx, cudaMemcpyAsync(n_out, d_n, sizeof(size_t), cudaMemcpyDeviceToHost, st));
+    BS_CUDA(ctx, cudaStreamSynchronize(st));
+    bs_free(ctx, d_tmp); bs_free(ctx, d_sorted); bs_free(ctx, d_n);
+    return BS_OK;
+}
+
+}  // namespace
+
+bs_status bs_offset_impl(bs_volume* A, float distance, bs_volume** out) {
+    bs_context* ctx = A->ctx;
+    cudaStream_t st = ctx->stream;
+    bs_marks_begin(ctx);
+    const float vs = A->voxel_size;
+    const size_t n_src = A->n_bricks;
+    // limit = +-(|d| + vs + vs) (volume/mod.rs:98-99); active tiles (+-MAX) never survive the prune
+    const float limit_abs = (fabsf(distance) + vs) + vs;
+    const int sweep_neg = std::signbit(distance) ? 1 : 0;
+    u64* d_pmasks = nullptr; unsigned char* d_nonempty = nullptr; int* d_flags = nullptr;
+    BS_TRY(bs_alloc(ctx, &d_pmasks, n_src * 8)); BS_TRY(bs_alloc(ctx, &d_nonempty, n_src)); BS_TRY(bs_alloc(ctx, &d_flags, 1));
+    BS_CUDA(ctx, cudaMemsetAsync(d_nonempty, 0, n_src ? n_src : 1, st));
+    if (n_src) k_prune<<<bs_blocks(n_src * 8, TPB), TPB, 0, st>>>(A->values, A->masks, n_src, vs * 2.0f, d_pmasks, d_nonempty);
+    // keys of the non-empty pruned bricks
+    u64* d_seed = nullptr; size_t n_seed = 0;
+    {
+        size_t* d_n = nullptr; void* d_tmp = nullptr; size_t tmp = 0;
+        BS_TRY(bs_alloc(ctx, &d_seed, n_src)); BS_TRY(bs_alloc(ctx, &d_n, 1));
+        cub::DeviceSelect::Flagged(nullptr, tmp, A->keys, d_nonempty, d_seed, d_n, n_src, st);
+        BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp));
+        cub::DeviceSelect::Flagged(d_tmp, tmp, A->keys, d_nonempty, d_seed, d_n, n_src, st);
+        BS_CUDA(ctx, cudaMemcpyAsync(&n_seed, d_n, sizeof(size_t), cudaMemcpyDeviceToHost, st));
+        BS_CUDA(ctx, cudaStreamSynchronize(st));
+        bs_free(ctx, d_tmp); bs_free(ctx, d_n);
+    }
+    bs_mark(ctx, "offset_prune_ms");
+    bs_volume* R = bs_volume_new(ctx, vs);
+    if (n_seed == 0) {  // nothing within 2 voxels of the surface: the sweeps have nothing to extend
+        bs_free(ctx, d_seed); bs_free(ctx, d_pmasks); bs_free(ctx, d_nonempty); bs_free(ctx, d_flags);
+        bs_status s = bs_volume_alloc_bricks(R, 0);
+        if (s != BS_OK) { bs_volume_free(R); return s; }
+        bs_marks_end(ctx);
+        *out = R;
+        return BS_OK;
+    }
+    int K = (int)std::ceil(limit_abs / (8.0f * vs)) + 1;
+    for (int attempt = 0;; ++attempt) {
+        // --- working set: K dilation steps of the seed bricks ---------------------------------------------------
+        u64* d_keys = nullptr; size_t n = n_seed;
+        BS_TRY(bs_alloc(ctx, &d_keys, n));
+        BS_CUDA(ctx, cudaMemcpyAsync(d_keys, d_seed, n * sizeof(u64), cudaMemcpyDeviceToDevice, st));
+        BS_CUDA(ctx, cudaMemsetAsync(d_flags, 0, sizeof(int), st));
+        for (int k = 0; k < K; ++k) {
+            u64 *d_big = nullptr, *d_next = nullptr; size_t n_next = 0;
+            BS_TRY(bs_alloc(ctx, &d_big, n * 27));
+            k_dilate<<<bs_blocks(n * 27, TPB), TPB, 0, st>>>(d_keys, n, d_big, d_flags);
+            BS_TRY(sort_unique(ctx, d_big, n * 27, &d_next, &n_next));
+            bs_free(ctx, d_big); bs_free(ctx, d_keys);
+            d_keys = d_next; n = n_next;
+        }
+        float* d_values = nullptr; u64 *d_masks = nullptr, *d_frozen = nullptr; unsigned char* d_inq = nullptr; int* d_nbr = nullptr;
+        BS_TRY(bs_alloc(ctx, &d_values, n * 512)); BS_TRY(bs_alloc(ctx, &d_masks, n * 8)); BS_TRY(bs_alloc(ctx, &d_frozen, n * 8));
+        BS_TRY(bs_alloc(ctx, &d_inq, n)); BS_TRY(bs_alloc(ctx, &d_nbr, n * 6));
+        BS_CUDA(ctx, cudaMemsetAsync(d_values, 0, n * 512 * sizeof(float), st));
+        BS_CUDA(ctx, cudaMemsetAsync(d_masks, 0, n * 8 * sizeof(u64), st));
+        BS_CUDA(ctx, cudaMemsetAsync(d_frozen, 0, n * 8 * sizeof(u64), st));
+        BS_CUDA(ctx, cudaMemsetAsync(d_inq, 0, n, st));
+        k_place<<<(unsigned)n_src, 512, 0, st>>>(A->keys, A->values, d_pmasks, d_nonempty, n_src, d_keys, n, d_values, d_masks, d_frozen, d_inq);
+        k_neighbours<<<bs_blocks(n * 6, TPB), TPB, 0, st>>>(d_keys, n, d_nbr);
+        // --- leaf wavefronts for the four axis-sign patterns (the other four are their reverses) -------------
+        std::vector<u64> h_keys(n);
+        BS_CUDA(ctx, cudaMemcpyAsync(h_keys.data(), d_keys, n * sizeof(u64), cudaMemcpyDeviceToHost, st));
+        BS_CUDA(ctx, cudaStreamSynchronize(st));
+        std::vector<unsigned> h_order(4 * n);
+        std::vector<std::vector<unsigned>> seg(4);
+        for (int g = 0; g < 4; ++g) {
+            const int sx = (g & 1) ? -1 : 1, sy = (g & 2) ? -1 : 1;
+            int wmin = INT32_MAX, wmax = INT32_MIN;
+            std::vector<int> w(n);
+            for (size_t i = 0; i < n; ++i) { int bx, by, bz; bs_key_brick(h_keys[i], bx, by, bz); w[i] = sx * bx + sy * by + bz; wmin = std::min(wmin, w[i]); wmax = std::max(wmax, w[i]); }
+            seg[g].assign((size_t)(wmax - wmin) + 2, 0);
+            for (size_t i = 0; i < n; ++i) seg[g][(size_t)(w[i] - wmin) + 1]++;
+            for (size_t k = 1; k < seg[g].size(); ++k) seg[g][k] += seg[g][k - 1];
+            std::vector<unsigned> cur(seg[g].begin(), seg[g].end() - 1);
+            for (size_t i = 0; i < n; ++i) h_order[(size_t)g * n + cur[(size_t)(w[i] - wmin)]++] = (unsigned)i;
+        }
+        unsigned* d_order = nullptr;
+        BS_TRY(bs_alloc(ctx, &d_order, 4 * n));
+        BS_CUDA(ctx, cudaMemcpyAsync(d_order, h_order.data(), 4 * n * sizeof(unsigned), cudaMemcpyHostToDevice, st));
+        bs_mark(ctx, "offset_setup_ms");
+        // --- 8 sweeps ---------------------------------------------------------------------------------------------------
+        SweepParams P;
+        P.values = d_values; P.masks = d_masks; P.frozen = d_frozen; P.nbr = d_nbr; P.inq = d_inq; P.flags = d_flags;
+        P.h = vs; P.limit_abs = limit_abs; P.sweep_neg = sweep_neg;
+        size_t n_launch = 0;
+        for (int dir = 0; dir < 8; ++dir) {
+            P.dir = dir;
+            // sz = +1: pattern g = dir & 3 ascending; sz = -1: (sx,sy,-1) is the reverse of pattern (-sx,-sy,+1)
+            const bool rev = dir & 4;
+            const int g = rev ? ((~dir) & 3) : (dir & 3);
+            const size_t nw = seg[g].size() - 1;
+            for (size_t k = 0; k < nw; ++k) {
+                const size_t wi = rev ? nw - 1 - k : k;
+                const unsigned cnt = seg[g][wi + 1] - seg[g][wi];
+                if (!cnt) continue;
+                P.order = d_order + (size_t)g * n + seg[g][wi];
+                k_sweep<<<cnt, 64, 0, st>>>(P);
+                ++n_launch;
+            }
+        }
+        int flag = 0;
+        BS_CUDA(ctx, cudaMemcpyAsync(&flag, d_flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+        BS_CUDA(ctx, cudaStreamSynchronize(st));
+        bs_mark(ctx, "offset_sweep_ms");
+        bs_status s = BS_OK;
+        if (flag && attempt < 3) {  // pushed outside the working set (or index range hit): widen and redo
+            bs_free(ctx, d_keys); bs_free(ctx, d_values); bs_free(ctx, d_masks); bs_free(ctx, d_frozen); bs_free(ctx, d_inq); bs_free(ctx, d_nbr); bs_free(ctx, d_order);
+            K += 2;
+            continue;
+        }
+        if (flag) s = bs_fail(ctx, BS_ERR_RANGE, "offset: sweep left the supported index range");
+        // --- remove_empty_branches + shift ----------------------------------------------------------------------
+        unsigned char* d_ne = nullptr; unsigned *d_ne32 = nullptr, *d_rank = nullptr; void* d_tmp = nullptr; size_t tmp = 0; unsigned n_out = 0;
+        if (s == BS_OK) s = bs_alloc(ctx, &d_ne, n);
+        if (s == BS_OK) s = bs_alloc(ctx, &d_ne32, n);
+        if (s == BS_OK) s = bs_alloc(ctx, &d_rank, n);
+        if (s == BS_OK) {
+            cudaMemsetAsync(d_ne, 0, n, st);
+            k_finish<<<bs_blocks(n * 8, TPB), TPB, 0, st>>>(d_values, d_masks, n, distance, d_ne);
+            k_widen8<<<bs_blocks(n, TPB), TPB, 0, st>>>(d_ne, d_ne32, n);
+            cub::DeviceScan::InclusiveSum(nullptr, tmp, d_ne32, d_rank, n, st);
+            s = bs_alloc(ctx, (char**)&d_tmp, tmp);
+        }
+        if (s == BS_OK) {
+            cub::DeviceScan::InclusiveSum(d_tmp, tmp, d_ne32, d_rank, n, st);
+            cudaMemcpyAsync(&n_out, d_rank + (n - 1), sizeof(unsigned), cudaMemcpyDeviceToHost, st);
+            if (cudaStreamSynchronize(st) != cudaSuccess) s = bs_fail(ctx, BS_ERR_CUDA, "offset kernels failed: %s", cudaGetErrorString(cudaGetLastError()));
+        }
+        if (s == BS_OK) s = bs_volume_alloc_bricks(R, n_out);
+        if (s == BS_OK && n_out) k_compact<<<(unsigned)n, 512, 0, st>>>(d_keys, d_values, d_masks, d_rank, d_ne, R->keys, R->values, R->masks);
+        if (s == BS_OK && (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess)) s = bs_fail(ctx, BS_ERR_CUDA, "offset compaction failed");
+        bs_free(ctx, d_tmp); bs_free(ctx, d_ne); bs_free(ctx, d_ne32); bs_free(ctx, d_rank);
+        bs_free(ctx, d_keys); bs_free(ctx, d_values); bs_free(ctx, d_masks); bs_free(ctx, d_frozen); bs_free(ctx, d_inq); bs_free(ctx, d_nbr); bs_free(ctx, d_order);
+        bs_free(ctx, d_seed); bs_free(ctx, d_pmasks); bs_free(ctx, d_nonempty); bs_free(ctx, d_flags);
+        if (s != BS_OK) { bs_volume_free(R); return s; }
+        bs_mark(ctx, "offset_finish_ms");
+        bs_marks_end(ctx);
+        bs_stat_add(ctx, "n_work_bricks", (double)n);
+        bs_stat_add(ctx, "n_out_bricks", (double)n_out);
+        bs_stat_add(ctx, "n_sweep_launches", (double)n_launch);
+        bs_stat_add(ctx, "dilation", (double)K);
+        *out = R;
+        return BS_OK;
+    }
+}

@@ -1,4 +1,3 @@
 // Stages not implemented on the device yet report BS_ERR_UNSUPPORTED (never a CPU fallback).
 #include "bs_common.cuh"
 bs_status bs_dc_impl(const bs_volume* v, float, const float**, size_t*) { return bs_fail(v->ctx, BS_ERR_UNSUPPORTED, "dual contouring: not implemented yet"); }
-bs_status bs_offset_impl(bs_volume* a, float, bs_volume**) { return bs_fail(a->ctx, BS_ERR_UNSUPPORTED, "offset: not implemented yet"); }
