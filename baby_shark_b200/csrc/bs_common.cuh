@@ -98,7 +98,9 @@ struct bs_volume {
     size_t n_tiles8 = 0, n_tiles128 = 0;
     unsigned long long* tile8_keys = nullptr; float* tile8_values = nullptr;
     unsigned long long* tile128_keys = nullptr; float* tile128_values = nullptr;
-    // multi-GPU: bricks [0, n_owned) are this rank's; the rest are read-only halo copies
+    // multi-GPU (bs_mesh_to_volume_sharded): owned[b] = 1 for this rank's bricks, 0 for read-only halo copies;
+    // nullptr = everything owned. Extraction emits owned bricks only.
+    unsigned char* owned = nullptr;
     size_t n_owned = 0;
 };
 

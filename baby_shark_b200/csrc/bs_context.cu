@@ -107,6 +107,14 @@ bs_status bs_context_set_flag(bs_context* ctx, int flag, int value) {
     if (flag == BS_FLAG_COUNT_WORK) { ctx->count_work = value; return BS_OK; }
     return BS_ERR_INVALID;
 }
+bs_status bs_context_copy_out_verts_device(bs_context* ctx, float* d_dst, size_t n_floats) {
+    if (!ctx || (!d_dst && n_floats)) return BS_ERR_INVALID;
+    if (n_floats > ctx->out_verts_cap) return bs_fail(ctx, BS_ERR_INVALID, "no extraction result of that size on the device");
+    cudaSetDevice(ctx->device);
+    if (n_floats) BS_CUDA(ctx, cudaMemcpyAsync(d_dst, ctx->d_out_verts, n_floats * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    BS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BS_OK;
+}
 bs_status bs_context_copy_out_verts(bs_context* ctx, float* dst, size_t n_floats) {
     if (!ctx || (!dst && n_floats)) return BS_ERR_INVALID;
     if (n_floats > ctx->out_verts_cap) return bs_fail(ctx, BS_ERR_INVALID, "no extraction result of that size on the device");
@@ -126,7 +134,7 @@ void bs_volume_free(bs_volume* v) {
     if (!v) return;
     bs_context* c = v->ctx;
     cudaSetDevice(c->device);
-    bs_free(c, v->keys); bs_free(c, v->values); bs_free(c, v->masks);
+    bs_free(c, v->keys); bs_free(c, v->values); bs_free(c, v->masks); bs_free(c, v->owned);
     bs_free(c, v->tile8_keys); bs_free(c, v->tile8_values); bs_free(c, v->tile128_keys); bs_free(c, v->tile128_values);
     delete v;
 }
@@ -149,7 +157,7 @@ bs_status bs_volume_clone(const bs_volume* v, bs_volume** out) {
     bs_volume* w = bs_volume_new(c, v->voxel_size);
     w->n_bricks = v->n_bricks; w->n_owned = v->n_owned; w->n_tiles8 = v->n_tiles8; w->n_tiles128 = v->n_tiles128;
     bs_status s;
-    if ((s = dup_array(c, &w->keys, v->keys, v->n_bricks)) || (s = dup_array(c, &w->values, v->values, v->n_bricks * 512)) ||
+    if ((v->owned && (s = dup_array(c, &w->owned, v->owned, v->n_bricks))) || (s = dup_array(c, &w->keys, v->keys, v->n_bricks)) || (s = dup_array(c, &w->values, v->values, v->n_bricks * 512)) ||
         (s = dup_array(c, &w->masks, v->masks, v->n_bricks * 8)) || (s = dup_array(c, &w->tile8_keys, v->tile8_keys, v->n_tiles8)) ||
         (s = dup_array(c, &w->tile8_values, v->tile8_values, v->n_tiles8)) || (s = dup_array(c, &w->tile128_keys, v->tile128_keys, v->n_tiles128)) ||
         (s = dup_array(c, &w->tile128_values, v->tile128_values, v->n_tiles128))) { bs_volume_free(w); return s; }
@@ -267,6 +275,7 @@ static bs_status csg_entry(bs_volume* a, bs_volume* b, int op, bs_volume** out) 
     if (out) *out = nullptr;
     if (!a || !b || !out || a == b || a->ctx != b->ctx) { bs_volume_free(a); if (b != a) bs_volume_free(b); return BS_ERR_INVALID; }
     cudaSetDevice(a->ctx->device);
+    if (a->owned || b->owned) { bs_status e = bs_fail(a->ctx, BS_ERR_UNSUPPORTED, "CSG on a brick-sharded volume (DESIGN.md, Multi-GPU)"); bs_volume_free(a); bs_volume_free(b); return e; }
     bs_status s = bs_csg_impl(a, b, op, out);
     bs_volume_free(a); bs_volume_free(b);
     return s;
@@ -278,6 +287,7 @@ bs_status bs_volume_offset(bs_volume* a, float distance, bs_volume** out) {
     if (out) *out = nullptr;
     if (!a || !out) { bs_volume_free(a); return BS_ERR_INVALID; }
     cudaSetDevice(a->ctx->device);
+    if (a->owned) { bs_status e = bs_fail(a->ctx, BS_ERR_UNSUPPORTED, "offset does not shard: the sweep wavefronts cross slabs (DESIGN.md, Multi-GPU)"); bs_volume_free(a); return e; }
     bs_status s = bs_offset_impl(a, distance, out);
     bs_volume_free(a);
     return s;

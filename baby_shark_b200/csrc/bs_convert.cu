@@ -262,6 +262,30 @@ __global__ void k_fill_slots(const unsigned long long* sorted_keys, size_t n, un
     table_slots[h] = (unsigned)i;
 }
 
+__device__ __forceinline__ long long find_sorted(const unsigned long long* keys, size_t n, unsigned long long k) {
+    size_t lo = 0, hi = n;
+    while (lo < hi) { size_t mid = (lo + hi) >> 1; if (keys[mid] < k) lo = mid + 1; else hi = mid; }
+    return (lo < n && keys[lo] == k) ? (long long)lo : -1;
+}
+// keep[] = slab bricks [lo, hi) and their 26 neighbours
+__global__ void k_mark_slab(const unsigned long long* __restrict__ keys, size_t n, size_t lo, size_t hi, unsigned char* keep) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= (hi - lo) * 27) return;
+    const size_t b = lo + i / 27; const int d = (int)(i % 27);
+    if (d == 13) { keep[b] = 1; return; }
+    int bx, by, bz; bs_key_brick(keys[b], bx, by, bz);
+    bx += d / 9 - 1; by += (d / 3) % 3 - 1; bz += d % 3 - 1;
+    if (bx < BS_BRICK_MIN || bx > BS_BRICK_MAX || by < BS_BRICK_MIN || by > BS_BRICK_MAX || bz < BS_BRICK_MIN || bz > BS_BRICK_MAX) return;
+    const long long j = find_sorted(keys, n, bs_brick_key(bx, by, bz));
+    if (j >= 0) keep[j] = 1;
+}
+__global__ void k_owned(const unsigned long long* __restrict__ all_keys, size_t n_all, size_t lo, size_t hi, const unsigned long long* __restrict__ kept, size_t n_kept, unsigned char* owned) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n_kept) return;
+    const long long j = find_sorted(all_keys, n_all, kept[i]);
+    owned[i] = (j >= (long long)lo && j < (long long)hi) ? 1 : 0;
+}
+
 struct NotEmptyKey { __device__ bool operator()(unsigned long long k) const { return k != BS_KEY_INVALID; } };
 
 __global__ void k_counts(const float* values, const unsigned long long* masks, size_t n_bricks, unsigned long long* out /*[2]*/) {
@@ -376,11 +400,37 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
         bs_free(ctx, d_tmp); bs_free(ctx, d_sel);
     }
     bs_volume* vol = bs_volume_new(ctx, voxel_size);
-    (void)rank; (void)world;  // brick-slab sharding: see bs_shard.cu (all bricks kept when world == 1)
-    bs_status s = bs_volume_alloc_bricks(vol, n_all);
-    if (s != BS_OK) { bs_volume_free(vol); return s; }
-    BS_CUDA(ctx, cudaMemcpyAsync(vol->keys, d_keys, n_all * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
-    bs_free(ctx, d_keys);
+    bs_status s = BS_OK;
+    const size_t n_total = n_all;
+    if (world > 1) {
+        // brick-slab sharding: this rank owns the contiguous slab [lo, hi) of the sorted brick list and keeps, as
+        // read-only halo, the 26 neighbours of its bricks (extraction needs +1 for MC, -1..+1 for DC)
+        const size_t lo = n_all * (size_t)rank / (size_t)world, hi = n_all * (size_t)(rank + 1) / (size_t)world;
+        unsigned char* d_keep = nullptr; unsigned long long* d_kept = nullptr; size_t* d_nk = nullptr; size_t n_kept = 0;
+        BS_TRY(bs_alloc(ctx, &d_keep, n_all)); BS_TRY(bs_alloc(ctx, &d_kept, n_all)); BS_TRY(bs_alloc(ctx, &d_nk, 1));
+        BS_CUDA(ctx, cudaMemsetAsync(d_keep, 0, n_all, st));
+        if (hi > lo) k_mark_slab<<<bs_blocks((hi - lo) * 27, TPB), TPB, 0, st>>>(d_keys, n_all, lo, hi, d_keep);
+        tmp_bytes = 0;
+        cub::DeviceSelect::Flagged(nullptr, tmp_bytes, d_keys, d_keep, d_kept, d_nk, n_all, st);
+        BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp_bytes));
+        cub::DeviceSelect::Flagged(d_tmp, tmp_bytes, d_keys, d_keep, d_kept, d_nk, n_all, st);
+        BS_CUDA(ctx, cudaMemcpyAsync(&n_kept, d_nk, sizeof(size_t), cudaMemcpyDeviceToHost, st));
+        BS_CUDA(ctx, cudaStreamSynchronize(st));
+        bs_free(ctx, d_tmp); bs_free(ctx, d_nk); bs_free(ctx, d_keep);
+        s = bs_volume_alloc_bricks(vol, n_kept);
+        if (s == BS_OK) s = bs_alloc(ctx, &vol->owned, n_kept);
+        if (s != BS_OK) { bs_volume_free(vol); return s; }
+        BS_CUDA(ctx, cudaMemcpyAsync(vol->keys, d_kept, n_kept * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+        if (n_kept) k_owned<<<bs_blocks(n_kept, TPB), TPB, 0, st>>>(d_keys, n_all, lo, hi, vol->keys, n_kept, vol->owned);
+        bs_free(ctx, d_kept); bs_free(ctx, d_keys);
+        n_all = n_kept;
+        vol->n_owned = hi - lo;
+    } else {
+        s = bs_volume_alloc_bricks(vol, n_all);
+        if (s != BS_OK) { bs_volume_free(vol); return s; }
+        BS_CUDA(ctx, cudaMemcpyAsync(vol->keys, d_keys, n_all * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+        bs_free(ctx, d_keys);
+    }
     BS_TRY(bs_alloc(ctx, &d_table_slots, cap));
     BS_CUDA(ctx, cudaMemsetAsync(d_table_slots, 0xFF, cap * sizeof(unsigned), st));
     k_fill_slots<<<bs_blocks(n_all, TPB), TPB, 0, st>>>((const unsigned long long*)vol->keys, n_all, d_table_keys, d_table_slots, (unsigned)(cap - 1));
@@ -399,6 +449,8 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
     bs_stat_add(ctx, "n_tris", (double)n_tris);
     bs_stat_add(ctx, "n_sub", (double)total);
     bs_stat_add(ctx, "n_bricks", (double)n_all);
+    bs_stat_add(ctx, "n_bricks_total", (double)n_total);
+    bs_stat_add(ctx, "n_bricks_owned", (double)vol->n_owned);
     bs_stat_add(ctx, "n_eval", (double)n_eval);
     if (ctx->count_work) {
         bs_stat_add(ctx, "fwn_visits", ctx->fwn_counts[0]); bs_stat_add(ctx, "fwn_far", ctx->fwn_counts[1]);

@@ -71,7 +71,7 @@ __device__ bool hermite(const Halo& h, const int* org, int x, int y, int z, int 
 }
 
 __global__ void __launch_bounds__(512) k_dc_cells(const u64* __restrict__ keys, const float* __restrict__ values, const u64* __restrict__ masks, size_t n,
-                                                  float* cell_pts /*n*512*3*/, u64* cell_valid /*n*8*/, int* flags) {
+                                                  const unsigned char* __restrict__ owned, float* cell_pts /*n*512*3*/, u64* cell_valid /*n*8*/, int* flags) {
     __shared__ float s_v[HN];
     __shared__ unsigned char s_a[HN];
     __shared__ long long s_nb[27];
@@ -152,19 +152,20 @@ __global__ void __launch_bounds__(512) k_dc_cells(const u64* __restrict__ keys, 
     o[0] = c.x; o[1] = c.y; o[2] = c.z;
     const unsigned bal = __ballot_sync(0xFFFFFFFFu, valid);
     if ((t & 31) == 0) s_bal[t >> 5] = bal;
-    if (bad) flags[0] = 1;
+    if (bad && (!owned || owned[b])) flags[0] = 1;  // halo bricks of a sharded volume miss part of their own halo
     __syncthreads();
     if (t < 8) cell_valid[b * 8 + t] = (u64)s_bal[2 * t] | ((u64)s_bal[2 * t + 1] << 32);
 }
 
 template <bool WRITE>
 __global__ void __launch_bounds__(512) k_dc_quads(const u64* __restrict__ keys, const float* __restrict__ values, const u64* __restrict__ masks, size_t n,
-                                                  const float* __restrict__ cell_pts, const u64* __restrict__ cell_valid, float vs,
+                                                  const unsigned char* __restrict__ owned, const float* __restrict__ cell_pts, const u64* __restrict__ cell_valid, float vs,
                                                   unsigned* counts, const u64* __restrict__ offsets, float* out) {
     __shared__ long long s_nb[8];   // bit0 = -x, bit1 = -y, bit2 = -z neighbour (cells), index 0 = this brick
     __shared__ long long s_pb[4];   // +x, +y, +z neighbour (values), index 0 = this brick
     const size_t b = blockIdx.x;
     const unsigned t = threadIdx.x;
+    if (owned && !owned[b]) { if (!WRITE && t == 0) counts[b] = 0; return; }
     if (WRITE) { if (offsets[b + 1] == offsets[b]) return; }
     if (t < 8 || (t >= 32 && t < 36)) {
         int bx, by, bz; bs_key_brick(keys[b], bx, by, bz);
@@ -246,9 +247,9 @@ bs_status bs_dc_impl(const bs_volume* v, float voxel_size, const float** d_verts
     BS_TRY(bs_alloc(ctx, &d_cells, n * 512 * 3)); BS_TRY(bs_alloc(ctx, &d_valid, n * 8)); BS_TRY(bs_alloc(ctx, &d_flags, 1));
     BS_TRY(bs_alloc(ctx, &d_counts, n)); BS_TRY(bs_alloc(ctx, &d_wide, n + 1)); BS_TRY(bs_alloc(ctx, &d_off, n + 1));
     BS_CUDA(ctx, cudaMemsetAsync(d_flags, 0, sizeof(int), st));
-    k_dc_cells<<<(unsigned)n, 512, 0, st>>>(v->keys, v->values, v->masks, n, d_cells, d_valid, d_flags);
+    k_dc_cells<<<(unsigned)n, 512, 0, st>>>(v->keys, v->values, v->masks, n, v->owned, d_cells, d_valid, d_flags);
     bs_mark(ctx, "dc_cells_ms");
-    k_dc_quads<false><<<(unsigned)n, 512, 0, st>>>(v->keys, v->values, v->masks, n, d_cells, d_valid, voxel_size, d_counts, nullptr, nullptr);
+    k_dc_quads<false><<<(unsigned)n, 512, 0, st>>>(v->keys, v->values, v->masks, n, v->owned, d_cells, d_valid, voxel_size, d_counts, nullptr, nullptr);
     k_widen<<<bs_blocks(n + 1, 256), 256, 0, st>>>(d_counts, d_wide, n);
     void* d_tmp = nullptr; size_t tmp_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_wide, d_off, n + 1, st);
@@ -262,7 +263,7 @@ bs_status bs_dc_impl(const bs_volume* v, float voxel_size, const float** d_verts
     bs_status s = BS_OK;
     if (flag) s = bs_fail(ctx, BS_ERR_REFERENCE_PANICS, "dual contouring: a sign-change edge end point has no neighbour along some axis; the reference hits unreachable!() (dual_contouring.rs:340)");
     if (s == BS_OK) s = bs_ensure_out_verts(ctx, (size_t)n_tris * 9);
-    if (s == BS_OK && n_tris) k_dc_quads<true><<<(unsigned)n, 512, 0, st>>>(v->keys, v->values, v->masks, n, d_cells, d_valid, voxel_size, nullptr, d_off, ctx->d_out_verts);
+    if (s == BS_OK && n_tris) k_dc_quads<true><<<(unsigned)n, 512, 0, st>>>(v->keys, v->values, v->masks, n, v->owned, d_cells, d_valid, voxel_size, nullptr, d_off, ctx->d_out_verts);
     bs_mark(ctx, "dc_emit_ms");
     bs_free(ctx, d_tmp); bs_free(ctx, d_cells); bs_free(ctx, d_valid); bs_free(ctx, d_counts); bs_free(ctx, d_wide); bs_free(ctx, d_off); bs_free(ctx, d_flags);
     if (s != BS_OK) return s;

@@ -29,6 +29,7 @@ __constant__ signed char c_corner[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 
 
 struct VolView {
     const unsigned long long* keys; const float* values; const unsigned long long* masks; size_t n;
+    const unsigned char* owned;  // nullptr = all
     const unsigned long long* t8k; const float* t8v; size_t nt8;
     const unsigned long long* t128k; const float* t128v; size_t nt128;
 };
@@ -299,6 +300,7 @@ __global__ void __launch_bounds__(MC_TPB) k_mc(VolView V, const signed char* __r
     __shared__ int s_org[3];
     const size_t b = blockIdx.x;
     const size_t item = pos ? pos[b] : b;
+    if (V.owned && !V.owned[b]) { if (!WRITE && threadIdx.x == 0) item_counts[item] = 0; return; }  // halo brick of a sharded volume
     if (WRITE) { if (item_offsets[item + 1] == item_offsets[item]) return; }  // uniform per block
     stage_brick(V, b, s_val, s_act, s_nb, s_org);
     const unsigned tid = threadIdx.x;  // == leaf offset x<<6 | y<<3 | z of the cell's corner 0
@@ -434,7 +436,7 @@ bs_status bs_mc_impl(const bs_volume* v, float voxel_size, const float** d_verts
     bs_marks_begin(ctx);
     const size_t n = v->n_bricks, nt8 = v->n_tiles8, nt128 = v->n_tiles128, n_items = n + nt8 + nt128;
     if (n_items == 0) { bs_marks_end(ctx); return BS_OK; }
-    VolView V{v->keys, v->values, v->masks, n, v->tile8_keys, v->tile8_values, nt8, v->tile128_keys, v->tile128_values, nt128};
+    VolView V{v->keys, v->values, v->masks, n, v->owned, v->tile8_keys, v->tile8_values, nt8, v->tile128_keys, v->tile128_values, nt128};
     const signed char* tables = (const signed char*)ctx->d_mc33;
     unsigned *d_counts = nullptr, *d_pos = nullptr; unsigned long long *d_wide = nullptr, *d_off = nullptr;
     BS_TRY(bs_alloc(ctx, &d_counts, n_items)); BS_TRY(bs_alloc(ctx, &d_wide, n_items + 1)); BS_TRY(bs_alloc(ctx, &d_off, n_items + 1));

@@ -151,16 +151,28 @@ def main():
     d_tris = h_tris.to("cuda", non_blocking=False)                   # resident input for the `value` leg
     fp = C.POINTER(C.c_float)
 
+    from baby_shark_b200.shard import all_gather_varlen
+    gather_buf = {"t": None}
+
+    def gather(n_floats):
+        """the path's one exchange: all-gather(v) of the compacted triangle buffers over NVLink (NCCL)"""
+        if gather_buf["t"] is None or gather_buf["t"].numel() < n_floats:
+            gather_buf["t"] = torch.empty(int(n_floats * 1.2) + 16, dtype=torch.float32, device="cuda")
+        ctx.check(L.bs_context_copy_out_verts_device(ctx._h, C.c_void_p(gather_buf["t"].data_ptr()), n_floats))
+        full, _ = all_gather_varlen(gather_buf["t"][:n_floats])
+        return full
+
     def step_device():
-        """convert + MC, input and output resident in HBM; returns (n_active_voxels unknown here, n_verts)."""
+        """convert + MC (+ all-gather when sharded), input and output resident in HBM; returns local vertex count."""
         h = C.c_void_p()
         ctx.check(L.bs_mesh_to_volume_sharded(ctx._h, C.c_void_p(d_tris.data_ptr()), n_tris, vs, 0, rank, world, C.byref(h)))
         dv, nv = C.c_void_p(), C.c_size_t()
         st = L.bs_mesh_mc_device(h, vs, C.byref(dv), C.byref(nv))
-        stats = None
         L.bs_volume_free(h)
         ctx.check(st)
-        return dv.value, nv.value, stats
+        if world > 1:
+            gather(nv.value * 3)
+        return dv.value, nv.value, None
 
     h_out = None
 
@@ -178,6 +190,13 @@ def main():
         L.bs_volume_free(h)
         ctx.check(st)
         n_floats = nv.value * 3
+        if world > 1:  # gather on the device, then rank 0 reads the whole mesh back
+            full = gather(n_floats)
+            if rank == 0:
+                if h_out is None or h_out.numel() < full.numel():
+                    h_out = torch.empty(int(full.numel() * 1.1) + 16, dtype=torch.float32).pin_memory()
+                h_out[: full.numel()].copy_(full, non_blocking=False)
+            return nv.value
         if h_out is None or h_out.numel() < n_floats:
             h_out = torch.empty(int(n_floats * 1.1) + 16, dtype=torch.float32).pin_memory()
         ctx.check(L.bs_context_copy_out_verts(ctx._h, C.c_void_p(h_out.data_ptr()), n_floats))
@@ -196,6 +215,13 @@ def main():
     L.bs_context_set_flag(ctx._h, 1, 0)
     L.bs_volume_free(h)
     n_active_local = work.get("fwn_voxels", 0.0)
+    if world > 1:  # sharded volumes carry halo bricks: count the job's active voxels once on the unsharded volume
+        h = C.c_void_p()
+        ctx.check(L.bs_mesh_to_volume_device(ctx._h, C.c_void_p(d_tris.data_ptr()), n_tris, vs, 0, C.byref(h)))
+        na = C.c_size_t()
+        ctx.check(L.bs_volume_counts(h, None, C.byref(na), None, None))
+        L.bs_volume_free(h)
+        n_active_local = float(na.value) / world  # summed over ranks below
 
     # ---- value leg: K steps, device resident ------------------------------------------------------------------
     for _ in range(args.warmup):
@@ -211,7 +237,7 @@ def main():
         _, nv, _ = step_device()
         n_verts_local = nv
         for k, v in ctx.last_stats().items():   # MC stage timings of this step (convert's were overwritten; re-read below)
-            if k.endswith("_ms"):
+            if k.endswith("_ms") and k != "total_ms":
                 stage_ms[k] = stage_ms.get(k, 0.0) + v
     e1.record(stream)
     barrier()
@@ -225,7 +251,7 @@ def main():
         h = C.c_void_p()
         ctx.check(L.bs_mesh_to_volume_sharded(ctx._h, C.c_void_p(d_tris.data_ptr()), n_tris, vs, 0, rank, world, C.byref(h)))
         for k, v in ctx.last_stats().items():
-            if k.endswith("_ms"):
+            if k.endswith("_ms") and k != "total_ms":
                 conv_ms[k] = conv_ms.get(k, 0.0) + v / reps
         L.bs_volume_free(h)
     mc_ms = {k: v / args.steps for k, v in stage_ms.items()}
@@ -249,9 +275,6 @@ def main():
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         ms_total, e2e_ms = float(tmax[0]), float(tmax[1])
         n_active, n_verts = float(tsum[2]), float(tsum[3])
-        # the one real exchange of the path: all-gather(v) of the compacted triangle buffers over NVLink (timed apart)
-        counts = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
-        dist.all_gather(counts, torch.tensor([n_verts_local * 3], dtype=torch.int64, device="cuda"))
     else:
         e2e_ms = e2e_s * 1e3
         n_active, n_verts = n_active_local, float(n_verts_local)

@@ -124,6 +124,8 @@ bs_status bs_volume_counts(const bs_volume* v, size_t* n_bricks, size_t* n_activ
 /* Copy the first n_floats of the last *_device extraction result into caller memory (pinned or pageable): lets
  * the shim fill a Vec<Vec3f> it allocated itself instead of taking a library-owned buffer. */
 bs_status bs_context_copy_out_verts(bs_context* ctx, float* dst, size_t n_floats);
+/* Same into device memory of the context's device (e.g. the send buffer of the multi-GPU all-gather). */
+bs_status bs_context_copy_out_verts_device(bs_context* ctx, float* d_dst, size_t n_floats);
 
 /* BS_FLAG_COUNT_WORK = 1: the next bs_mesh_to_volume* calls run the instrumented winding-number traversal and
  * report fwn_visits / fwn_far / fwn_exact_tris / fwn_voxels through bs_context_last_stats (roofline work counts;
