@@ -84,7 +84,7 @@ struct bs_context {
     std::vector<std::pair<const char*, cudaEvent_t>> marks;
     // BS_FLAG_COUNT_WORK: instrumented winding-number traversal (node visits, far evals, exact triangles, voxels)
     int count_work = 0;
-    double fwn_counts[6] = {0, 0, 0, 0, 0, 0};  // lane visits, far evals, exact tris, voxels, warp-level visits, traversals
+    double fwn_counts[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // lane visits, far evals, exact tris, voxels, warp-level visits, traversals, brick-level visits, hoisted nodes
 };
 
 struct bs_volume {

@@ -456,6 +456,7 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
         bs_stat_add(ctx, "fwn_visits", ctx->fwn_counts[0]); bs_stat_add(ctx, "fwn_far", ctx->fwn_counts[1]);
         bs_stat_add(ctx, "fwn_exact_tris", ctx->fwn_counts[2]); bs_stat_add(ctx, "fwn_voxels", ctx->fwn_counts[3]);
         bs_stat_add(ctx, "fwn_warp_visits", ctx->fwn_counts[4]); bs_stat_add(ctx, "fwn_traversals", ctx->fwn_counts[5]);
+        bs_stat_add(ctx, "fwn_brick_visits", ctx->fwn_counts[6]); bs_stat_add(ctx, "fwn_brick_hoisted", ctx->fwn_counts[7]); bs_stat_add(ctx, "fwn_brick_roots", ctx->fwn_counts[8]);
     }
     bs_stat_add(ctx, "area_vox", area_vox);
     *out = vol;

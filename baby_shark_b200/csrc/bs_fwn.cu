@@ -24,7 +24,7 @@ namespace {
 #define BS_LEAF 1
 #endif
 constexpr int LEAF = BS_LEAF;     // triangles per leaf
-constexpr int STACK = 160;        // per-warp stack entries (tree depth <= 63 + 32 with index tie-breaks)
+constexpr int STACK = 208;        // per-warp stack entries: sub-tree roots (<= MAX_ROOTS = 96) + tree depth (<= 63 + 32 with index tie-breaks)
 constexpr int WARPS_PER_BLOCK = 4;
 constexpr float BETA = 2.0f;      // accuracy_scale (mesh_to_volume.rs:264)
 constexpr float INV_4PI = 0.07957747154594767f;
@@ -114,6 +114,21 @@ __global__ void k_karras(const unsigned long long* __restrict__ codes, int n, in
     left[i] = lc; right[i] = rc;
     parent[lc] = i; parent[rc] = i;
     if (i == 0) parent[0] = -1;
+}
+
+// Alternative hierarchy (BS_TREE_BALANCED): midpoint splits of the Morton-sorted sequence. Internal node i is the
+// split position m = i + 1 of exactly one range [a, b) of the recursion [a,b) -> [a,m) + [m,b), m = (a+b)/2.
+__global__ void k_balanced(int n, int* left, int* right, int* parent) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const int m = i + 1;
+    int a = 0, b = n;
+    for (;;) { const int mid = (a + b) >> 1; if (mid == m) break; if (m < mid) b = mid; else a = mid; }
+    const int lc = (m - a == 1) ? (n - 1 + a) : (((a + m) >> 1) - 1);
+    const int rc = (b - m == 1) ? (n - 1 + m) : (((m + b) >> 1) - 1);
+    left[i] = lc; right[i] = rc;
+    parent[lc] = i; parent[rc] = i;
+    if (a == 0 && b == n) parent[i] = -1;
 }
 
 __device__ __forceinline__ void raw_load_cg(const Raw* p, Raw& r) {
@@ -242,14 +257,6 @@ __global__ void k_records(const int* __restrict__ left, const int* __restrict__ 
     r[15] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
-// far-field dipole (aabb_tree.rs:667-669, hessians :803-816): o1 . r/(4 pi |r|^3) + M : (I/(4 pi |r|^3) - 3 r r^T/(4 pi |r|^5))
-__device__ __forceinline__ float far_field(const float4 a, const float4 b, const float4 c, float rx, float ry, float rz, float r2) {
-    const float inv_r = rsqrtf(r2);
-    const float k = INV_4PI * inv_r * inv_r * inv_r;
-    const float rMr = b.x * rx * rx + b.y * ry * ry + b.z * rz * rz + b.w * rx * ry + c.x * rx * rz + c.y * ry * rz;
-    return k * ((a.x * rx + a.y * ry + a.z * rz) + a.w - 3.0f * rMr * (inv_r * inv_r));
-}
-
 // solid_angle / (4 pi) (aabb_tree.rs:582-628), Van Oosterom-Strackee form
 __device__ __forceinline__ float tri_winding(const float4 t0, const float4 t1, const float4 t2, float qx, float qy, float qz) {
     const float ax = t0.x - qx, ay = t0.y - qy, az = t0.z - qz;
@@ -282,37 +289,36 @@ struct WarpWinding {
     __device__ __forceinline__ void visit(unsigned id, const float4 h, const float4 c0, const float4 c1, const float4 c2, const unsigned* m) {
         unsigned near_m[VPL]; unsigned any_near = 0;
         if (COUNT && lane == 0) cnt[3]++;
+        const unsigned lane_bit = 1u << lane;
 #pragma unroll
         for (int v = 0; v < VPL; ++v) {
-            const bool in = (m[v] >> lane) & 1;
+            const bool in = (m[v] & lane_bit) != 0;
             const float rx = h.x - qx[v], ry = h.y - qy[v], rz = h.z - qz[v];
-            const float r2 = rx * rx + ry * ry + rz * rz;
+            const float r2 = fmaf(rz, rz, fmaf(ry, ry, rx * rx));
             const bool far = in && (r2 > h.w);
             const unsigned far_m = __ballot_sync(0xFFFFFFFFu, far);
             near_m[v] = m[v] & ~far_m; any_near |= near_m[v];
             if (COUNT && in) cnt[0]++;
             if (far_m) {
-                const float f = far_field(c0, c1, c2, rx, ry, rz, r2);
+                // far-field dipole (aabb_tree.rs:667-669, hessians :803-816):
+                //   o1 . r/(4 pi |r|^3) + M : (I/(4 pi |r|^3) - 3 r r^T/(4 pi |r|^5)),  r = p~ - q
+                float inv_r;
+                asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv_r) : "f"(r2));
+                const float ir2 = inv_r * inv_r;
+                const float k = (INV_4PI * inv_r) * ir2;
+                const float d = fmaf(c0.x, rx, fmaf(c0.y, ry, fmaf(c0.z, rz, c0.w)));      // o1 . r + tr M
+                const float t1 = fmaf(c1.w, ry, fmaf(c2.x, rz, c1.x * rx));                // m00 rx + (m01+m10) ry + (m02+m20) rz
+                const float t2 = fmaf(c2.y, rz, c1.y * ry);                                // m11 ry + (m12+m21) rz
+                const float rMr = fmaf(rx, t1, fmaf(ry, t2, (c1.z * rz) * rz));
+                const float f = k * fmaf(-3.0f * ir2, rMr, d);
                 if (far) { wn[v] += f; if (COUNT) cnt[1]++; }
             }
         }
         if (any_near == 0) return;
-        if (id >= T.n_leaves - 1) {
-            const float4* t = T.tris + 3 * (size_t)(id - (T.n_leaves - 1)) * LEAF;
-#pragma unroll
-            for (int k = 0; k < LEAF; ++k) {
-                const float4 t0 = __ldg(t + 3 * k), t1 = __ldg(t + 3 * k + 1), t2 = __ldg(t + 3 * k + 2);
-#pragma unroll
-                for (int v = 0; v < VPL; ++v) {
-                    if (near_m[v] == 0) continue;  // uniform
-                    const float e = tri_winding(t0, t1, t2, qx[v], qy[v], qz[v]);
-                    if ((near_m[v] >> lane) & 1) { wn[v] += e; if (COUNT) cnt[2]++; }
-                }
-            }
-            return;
-        }
+        // near for some voxel: internal nodes are expanded, leaves evaluated exactly -- both when popped, so the
+        // (large) exact-evaluation code exists once instead of once per inlined visit
         if (sp < STACK) {
-            {   // start pulling the record this entry will need when it is popped (two 128 B lines)
+            if (id < T.n_leaves - 1) {  // start pulling the record this entry will need (two 128 B lines)
                 const char* nxt = reinterpret_cast<const char*>(T.rec + (size_t)id * REC);
                 asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt));
                 asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt + 128));
@@ -327,13 +333,29 @@ struct WarpWinding {
         }
     }
 
-    __device__ void run(const unsigned* valid_m) {
-        sp = 0;
+    // leaf: sum of solid angles over its triangles (aabb_tree.rs:680-683) for the voxels in m
+    __device__ __forceinline__ void exact_leaf(unsigned id, const unsigned* m) {
+        const float4* t = T.tris + 3 * (size_t)(id - (T.n_leaves - 1)) * LEAF;
 #pragma unroll
-        for (int v = 0; v < VPL; ++v) wn[v] = 0.f;
-        {   // the root itself (aabb_tree.rs:662-670 tests a node before looking at its type)
-            const float4* c = T.coef + 3 * (size_t)T.root;
-            visit(T.root, __ldg(T.hdr + T.root), __ldg(c), __ldg(c + 1), __ldg(c + 2), valid_m);
+        for (int k = 0; k < LEAF; ++k) {
+            const float4 t0 = __ldg(t + 3 * k), t1 = __ldg(t + 3 * k + 1), t2 = __ldg(t + 3 * k + 2);
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                if (m[v] == 0) continue;  // uniform
+                const float e = tri_winding(t0, t1, t2, qx[v], qy[v], qz[v]);
+                if ((m[v] >> lane) & 1) { wn[v] += e; if (COUNT) cnt[2]++; }
+            }
+        }
+    }
+
+    // per-voxel traversal of the sub-trees in roots[0..n_roots); wn[] must hold the hoisted far part on entry.
+    // All near roots are pushed (and their records prefetched) before the single drain loop starts.
+    __device__ void run(const unsigned* valid_m, const unsigned* roots, int n_roots) {
+        sp = 0;
+        for (int ri = 0; ri < n_roots; ++ri) {  // a node is tested before its type is looked at (aabb_tree.rs:662-670)
+            const unsigned rid = roots[ri];
+            const float4* c = T.coef + 3 * (size_t)rid;
+            visit(rid, __ldg(T.hdr + rid), __ldg(c), __ldg(c + 1), __ldg(c + 2), valid_m);
         }
         while (sp > 0) {
             --sp;
@@ -344,6 +366,7 @@ struct WarpWinding {
 #pragma unroll
             for (int v = 0; v < VPL; ++v) m[v] = e[1 + v];
             __syncwarp();
+            if (id >= T.n_leaves - 1) { exact_leaf(id, m); continue; }
             const float4* r = T.rec + (size_t)id * REC;
             const float4 idsf = __ldg(r + 4);
             const int ids[4] = {__float_as_int(idsf.x), __float_as_int(idsf.y), __float_as_int(idsf.z), __float_as_int(idsf.w)};
@@ -358,6 +381,118 @@ struct WarpWinding {
     }
 };
 
+// Brick-level pass (its own kernel, one WARP per brick): walk the top of the tree ONCE per brick, breadth first, one
+// lane per frontier node. A node that is far for every voxel of the brick (|p~ - c_B| - rho > 2 r, rho = half
+// diagonal of the brick) and at least KAPPA * rho away is "hoisted": evaluated at 27 sample points (3 x 3 x 3
+// lattice over the brick, lanes 0..26) and later interpolated tri-quadratically per voxel -- its field varies by
+// O((rho/d)^3) across the brick, far below what the 0.2 threshold can see. Everything closer is handed to the
+// per-voxel traversal as a list of sub-tree roots, so the per-voxel criterion of the reference (aabb_tree.rs:666)
+// still decides there. Lists are built with ballot-ordered compaction: the summation order is deterministic.
+constexpr float KAPPA = 4.0f;
+constexpr int MAX_ROOTS = 96;
+constexpr int MAX_HOIST = 640;
+constexpr int MAX_FRONT = 96;
+constexpr int BP_WARPS = 4;
+struct BrickOut { float far[27]; unsigned n_roots; unsigned roots[MAX_ROOTS]; };  // n_roots = 0xFFFFFFFF: no hoisting, start at the tree root
+
+template <bool COUNT>
+__global__ void __launch_bounds__(32 * BP_WARPS) k_brick_pass(Tree T, const unsigned long long* __restrict__ keys, size_t n_bricks, float vs, BrickOut* out, unsigned long long* counters) {
+    __shared__ unsigned s_front[BP_WARPS][2][MAX_FRONT];
+    __shared__ unsigned s_hoist[BP_WARPS][MAX_HOIST];   // (record id << 2 | entry); the root itself is 0xFFFFFFFF
+    __shared__ unsigned s_roots[BP_WARPS][MAX_ROOTS];
+    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5, lt = (1u << lane) - 1;
+    const size_t b = (size_t)blockIdx.x * BP_WARPS + w;
+    if (b >= n_bricks) return;
+    int bx, by, bz; bs_key_brick(keys[b], bx, by, bz);
+    const float ox = (float)(bx << 3), oy = (float)(by << 3), oz = (float)(bz << 3);
+    const float cx = (ox + 3.5f) * vs, cy = (oy + 3.5f) * vs, cz = (oz + 3.5f) * vs, rho = 6.0621778f * vs, kr = KAPPA * rho;
+    unsigned* front[2] = {s_front[w][0], s_front[w][1]};
+    unsigned* hoist = s_hoist[w]; unsigned* roots = s_roots[w];
+    int nf = 0, nh = 0, nr = 0; bool overflow = false;
+    unsigned n_class = 0;
+    // 0 hoist, 1 root, 2 descend, 3 none
+    auto classify = [&](unsigned id, const float4 h) -> int {
+        const float dx = h.x - cx, dy = h.y - cy, dz = h.z - cz;
+        const float d = sqrtf(dx * dx + dy * dy + dz * dz), br = sqrtf(h.w);  // br = beta * radius
+        const bool brick_far = (d - rho) > br;
+        if (brick_far && d >= kr) return 0;
+        if (brick_far || id >= T.n_leaves - 1 || br <= kr) return 1;  // close: the whole sub-tree goes to the per-voxel traversal
+        return 2;
+    };
+    {
+        const int c = classify(T.root, __ldg(T.hdr + T.root));
+        if (c == 0) { if (lane == 0) hoist[0] = 0xFFFFFFFFu; nh = 1; } else if (c == 1) { if (lane == 0) roots[0] = T.root; nr = 1; } else { if (lane == 0) front[0][0] = T.root; nf = 1; }
+        n_class = 1;
+    }
+    __syncwarp();
+    for (int cur = 0; nf > 0 && !overflow; cur ^= 1) {
+        int nnext = 0;
+        for (int base = 0; base < nf; base += 32) {
+            const bool have = base + (int)lane < nf;
+            const unsigned id = have ? front[cur][base + lane] : 0;
+            int code[4] = {3, 3, 3, 3}; int ids[4] = {-1, -1, -1, -1};
+            if (have) {
+                const float4* r = T.rec + (size_t)id * REC;
+                const float4 idsf = __ldg(r + 4);
+                ids[0] = __float_as_int(idsf.x); ids[1] = __float_as_int(idsf.y); ids[2] = __float_as_int(idsf.z); ids[3] = __float_as_int(idsf.w);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) if (ids[k] >= 0) code[k] = classify((unsigned)ids[k], __ldg(r + k));
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {  // ordered compaction: (round, entry, lane)
+                const unsigned mh = __ballot_sync(0xFFFFFFFFu, code[k] == 0), mr = __ballot_sync(0xFFFFFFFFu, code[k] == 1), md = __ballot_sync(0xFFFFFFFFu, code[k] == 2);
+                if (COUNT) n_class += __popc(mh | mr | md);
+                if (nh + __popc(mh) > MAX_HOIST || nr + __popc(mr) > MAX_ROOTS || nnext + __popc(md) > MAX_FRONT) { overflow = true; break; }
+                if (code[k] == 0) hoist[nh + __popc(mh & lt)] = (id << 2) | k;
+                if (code[k] == 1) roots[nr + __popc(mr & lt)] = (unsigned)ids[k];
+                if (code[k] == 2) front[cur ^ 1][nnext + __popc(md & lt)] = (unsigned)ids[k];
+                nh += __popc(mh); nr += __popc(mr); nnext += __popc(md);
+            }
+            if (overflow) break;
+        }
+        __syncwarp();
+        nf = nnext;
+    }
+    BrickOut* o = out + b;
+    if (overflow) {  // pathological tree: plain per-voxel traversal from the root, nothing hoisted
+        if (lane < 27) o->far[lane] = 0.f;
+        if (lane == 0) o->n_roots = 0xFFFFFFFFu;
+        return;
+    }
+    // hoisted nodes at the 27 sample points
+    const unsigned si = lane < 27 ? lane / 9 : 0, sj = lane < 27 ? (lane / 3) % 3 : 0, sk = lane < 27 ? lane % 3 : 0;
+    const float sx = (ox + 3.5f * si) * vs, sy = (oy + 3.5f * sj) * vs, sz = (oz + 3.5f * sk) * vs;
+    float S = 0.f;
+    for (int i = 0; i < nh; ++i) {
+        const unsigned e = hoist[i];
+        float4 h; float c[10];
+        if (e == 0xFFFFFFFFu) {
+            h = __ldg(T.hdr + T.root);
+            const float4 a0 = __ldg(T.coef + 3 * (size_t)T.root), a1 = __ldg(T.coef + 3 * (size_t)T.root + 1), a2 = __ldg(T.coef + 3 * (size_t)T.root + 2);
+            c[0] = a0.x; c[1] = a0.y; c[2] = a0.z; c[3] = a0.w; c[4] = a1.x; c[5] = a1.y; c[6] = a1.z; c[7] = a1.w; c[8] = a2.x; c[9] = a2.y;
+        } else {
+            const float4* r = T.rec + (size_t)(e >> 2) * REC;
+            h = __ldg(r + (e & 3));
+            const float2* cf = reinterpret_cast<const float2*>(reinterpret_cast<const float*>(r) + 20 + 10 * (e & 3));
+#pragma unroll
+            for (int j = 0; j < 5; ++j) { const float2 t = __ldg(cf + j); c[2 * j] = t.x; c[2 * j + 1] = t.y; }
+        }
+        const float rx = h.x - sx, ry = h.y - sy, rz = h.z - sz;
+        const float r2 = fmaf(rz, rz, fmaf(ry, ry, rx * rx));
+        float inv_r;
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv_r) : "f"(r2));
+        const float ir2 = inv_r * inv_r, k = (INV_4PI * inv_r) * ir2;
+        const float dd = fmaf(c[0], rx, fmaf(c[1], ry, fmaf(c[2], rz, c[3])));
+        const float t1 = fmaf(c[7], ry, fmaf(c[8], rz, c[4] * rx)), t2 = fmaf(c[9], rz, c[5] * ry);
+        const float rMr = fmaf(rx, t1, fmaf(ry, t2, (c[6] * rz) * rz));
+        S += k * fmaf(-3.0f * ir2, rMr, dd);
+    }
+    if (lane < 27) o->far[lane] = S;
+    if (lane == 0) o->n_roots = (unsigned)nr;
+    for (int i = lane; i < nr; i += 32) o->roots[i] = roots[i];
+    if (COUNT && lane == 0) { atomicAdd(counters + 6, (unsigned long long)n_class); atomicAdd(counters + 7, (unsigned long long)nh); atomicAdd(counters + 8, (unsigned long long)nr); }
+}
+
 // 9-bit Morton position inside a brick -> leaf offset x<<6 | y<<3 | z (bits 2,5,8 -> x; 1,4,7 -> y; 0,3,6 -> z)
 __device__ __forceinline__ unsigned demorton9(unsigned p) {
     const unsigned x = ((p >> 2) & 1) | ((p >> 4) & 2) | ((p >> 6) & 4);
@@ -370,14 +505,37 @@ __device__ __forceinline__ unsigned demorton9(unsigned p) {
 // a heavy brick (e.g. at the pole of a UV sphere, where hundreds of sliver triangles are "near") is spread over
 // all warps of its CTA instead of serialising one warp.
 template <bool COUNT, int VPL>
-__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_sign(Tree T, float* values, unsigned long long* masks, size_t n_bricks,
-                                                               const unsigned long long* __restrict__ keys, float vs, unsigned long long* counters) {
+#ifndef BS_SIGN_MINB
+#define BS_SIGN_MINB 8
+#endif
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, BS_SIGN_MINB) k_sign(Tree T, float* values, unsigned long long* masks, size_t n_bricks,
+                                                               const unsigned long long* __restrict__ keys, float vs, const BrickOut* __restrict__ brick_out, unsigned long long* counters) {
     __shared__ unsigned s_stack[WARPS_PER_BLOCK][STACK * (1 + VPL)];
     __shared__ unsigned short s_list[512];
     __shared__ unsigned s_cnt[17];
+    __shared__ float s_far[27];
+    __shared__ unsigned s_roots[MAX_ROOTS];
+    __shared__ int s_nroots;
     const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const size_t b = blockIdx.x;
     float* bv = values + b * 512;
+    int bx, by, bz; bs_key_brick(keys[b], bx, by, bz);
+    {   // result of the brick-level pass: hoisted far field at 27 samples + sub-tree roots
+        const BrickOut* bo = brick_out + b;
+        const unsigned nr = bo->n_roots;
+        if (threadIdx.x < 27) s_far[threadIdx.x] = bo->far[threadIdx.x];
+        if (nr == 0xFFFFFFFFu) { if (threadIdx.x == 0) { s_roots[0] = T.root; s_nroots = 1; } }
+        else {
+            for (unsigned i = threadIdx.x; i < nr; i += blockDim.x) {
+                const unsigned rid = bo->roots[i];
+                s_roots[i] = rid;
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(T.hdr + rid));   // every warp visits every root first
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(T.coef + 3 * (size_t)rid));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(T.coef + 3 * (size_t)rid + 2));
+            }
+            if (threadIdx.x == 0) s_nroots = (int)nr;
+        }
+    }
     // mask words (leaf offset order): warp w covers rounds 4w..4w+3 = mask words 2w, 2w+1
     {
         unsigned bal[4];
@@ -400,7 +558,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_sign(Tree T, float* va
         if ((balm[r] >> lane) & 1) s_list[s_cnt[4 * w + r] + __popc(balm[r] & ((1u << lane) - 1))] = (unsigned short)demorton9((4 * w + r) * 32 + lane);
     __syncthreads();
     const unsigned cnt = s_cnt[16];
-    int bx, by, bz; bs_key_brick(keys[b], bx, by, bz);
+    const int n_roots = s_nroots;
     for (unsigned base = w * 32 * VPL; base < cnt; base += WARPS_PER_BLOCK * 32 * VPL) {
         unsigned c3[4] = {0, 0, 0, 0};
         WarpWinding<COUNT, VPL> W{T};
@@ -415,8 +573,24 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_sign(Tree T, float* va
             W.qx[v] = __fmul_rn((float)((bx << 3) + (int)(off[v] >> 6)), vs);
             W.qy[v] = __fmul_rn((float)((by << 3) + (int)((off[v] >> 3) & 7)), vs);
             W.qz[v] = __fmul_rn((float)((bz << 3) + (int)(off[v] & 7)), vs);
+            // hoisted far part: tri-quadratic Lagrange interpolation on the nodes {0, 3.5, 7} per axis
+            float L[3][3];
+#pragma unroll
+            for (int ax = 0; ax < 3; ++ax) {
+                const float t = (float)(ax == 0 ? (off[v] >> 6) : (ax == 1 ? ((off[v] >> 3) & 7) : (off[v] & 7)));
+                L[ax][0] = (t - 3.5f) * (t - 7.0f) * (1.0f / 24.5f); L[ax][1] = t * (7.0f - t) * (1.0f / 12.25f); L[ax][2] = t * (t - 3.5f) * (1.0f / 24.5f);
+            }
+            float acc = 0.f;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const float wij = L[0][i] * L[1][j];
+                    acc = fmaf(wij, fmaf(L[2][0], s_far[i * 9 + j * 3], fmaf(L[2][1], s_far[i * 9 + j * 3 + 1], L[2][2] * s_far[i * 9 + j * 3 + 2])), acc);
+                }
+            W.wn[v] = acc;
         }
-        W.run(valid_m);
+        W.run(valid_m, s_roots, n_roots);
 #pragma unroll
         for (int v = 0; v < VPL; ++v) {
             if (!valid[v]) continue;
@@ -431,7 +605,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) k_sign(Tree T, float* va
 }  // namespace
 
 #ifndef BS_VPL
-#define BS_VPL 2
+#define BS_VPL 1
 #endif
 
 bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_volume* vol) {
@@ -463,28 +637,40 @@ bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_v
     BS_TRY(bs_alloc(ctx, &d_rec, (size_t)n * REC));
     BS_TRY(bs_alloc(ctx, &d_raw, (size_t)n_nodes));
     BS_CUDA(ctx, cudaMemsetAsync(d_flags, 0, (size_t)n * sizeof(unsigned), st));
+#ifdef BS_TREE_BALANCED
+    if (n > 1) k_balanced<<<bs_blocks((size_t)n - 1, 256), 256, 0, st>>>(n, d_left, d_right, d_parent);
+    const unsigned root_id = n > 1 ? (unsigned)((n >> 1) - 1) : 0u;
+#else
     if (n > 1) k_karras<<<bs_blocks((size_t)n - 1, 256), 256, 0, st>>>(d_codes2, n, d_left, d_right, d_parent);
+    const unsigned root_id = 0u;
+#endif
     k_leaves_and_climb<<<bs_blocks((size_t)n, 128), 128, 0, st>>>(d_tris, d_ids2, n_tris, d_sorted, d_raw, d_left, d_right, d_parent, d_flags, n);
     k_finalize_nodes<<<bs_blocks((size_t)n_nodes, 128), 128, 0, st>>>(d_raw, n, d_hdr, d_coef);
     if (n > 1) k_records<<<bs_blocks((size_t)n - 1, 128), 128, 0, st>>>(d_left, d_right, d_hdr, d_coef, n, d_rec);
     bs_free(ctx, d_raw); bs_free(ctx, d_ids2); bs_free(ctx, d_codes2); bs_free(ctx, d_left); bs_free(ctx, d_right); bs_free(ctx, d_parent); bs_free(ctx, d_flags);
     Tree T;
-    T.hdr = d_hdr; T.coef = d_coef; T.rec = d_rec; T.tris = d_sorted; T.n_leaves = (unsigned)n; T.root = 0u;
+    T.hdr = d_hdr; T.coef = d_coef; T.rec = d_rec; T.tris = d_sorted; T.n_leaves = (unsigned)n; T.root = root_id;
     bs_mark(ctx, "bvh_build_ms");
     if (vol->n_bricks) {
         const size_t blocks = vol->n_bricks;  // one CTA per brick: the block scheduler balances the load
+        BrickOut* d_bo = nullptr;
+        BS_TRY(bs_alloc(ctx, &d_bo, vol->n_bricks));
         if (ctx->count_work) {
-            unsigned long long* d_cnt = nullptr; unsigned long long h_cnt[6];
-            BS_TRY(bs_alloc(ctx, &d_cnt, 6));
-            BS_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, 48, st));
-            k_sign<true, BS_VPL><<<(unsigned)blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(T, vol->values, vol->masks, vol->n_bricks, vol->keys, vol->voxel_size, d_cnt);
-            BS_CUDA(ctx, cudaMemcpyAsync(h_cnt, d_cnt, 48, cudaMemcpyDeviceToHost, st));
+            unsigned long long* d_cnt = nullptr; unsigned long long h_cnt[9];
+            BS_TRY(bs_alloc(ctx, &d_cnt, 9));
+            BS_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, 72, st));
+            k_brick_pass<true><<<bs_blocks(vol->n_bricks, BP_WARPS), 32 * BP_WARPS, 0, st>>>(T, vol->keys, vol->n_bricks, vol->voxel_size, d_bo, d_cnt);
+            k_sign<true, BS_VPL><<<(unsigned)blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(T, vol->values, vol->masks, vol->n_bricks, vol->keys, vol->voxel_size, d_bo, d_cnt);
+            BS_CUDA(ctx, cudaMemcpyAsync(h_cnt, d_cnt, 72, cudaMemcpyDeviceToHost, st));
             BS_CUDA(ctx, cudaStreamSynchronize(st));
             bs_free(ctx, d_cnt);
-            ctx->fwn_counts[0] = (double)h_cnt[0]; ctx->fwn_counts[1] = (double)h_cnt[1]; ctx->fwn_counts[2] = (double)h_cnt[2]; ctx->fwn_counts[3] = (double)h_cnt[3]; ctx->fwn_counts[4] = (double)h_cnt[4]; ctx->fwn_counts[5] = (double)h_cnt[5];
+            ctx->fwn_counts[0] = (double)h_cnt[0]; ctx->fwn_counts[1] = (double)h_cnt[1]; ctx->fwn_counts[2] = (double)h_cnt[2]; ctx->fwn_counts[3] = (double)h_cnt[3]; ctx->fwn_counts[4] = (double)h_cnt[4]; ctx->fwn_counts[5] = (double)h_cnt[5]; ctx->fwn_counts[6] = (double)h_cnt[6]; ctx->fwn_counts[7] = (double)h_cnt[7]; ctx->fwn_counts[8] = (double)h_cnt[8];
         } else {
-            k_sign<false, BS_VPL><<<(unsigned)blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(T, vol->values, vol->masks, vol->n_bricks, vol->keys, vol->voxel_size, nullptr);
+            k_brick_pass<false><<<bs_blocks(vol->n_bricks, BP_WARPS), 32 * BP_WARPS, 0, st>>>(T, vol->keys, vol->n_bricks, vol->voxel_size, d_bo, nullptr);
+            bs_mark(ctx, "sign_brick_pass_ms");
+            k_sign<false, BS_VPL><<<(unsigned)blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(T, vol->values, vol->masks, vol->n_bricks, vol->keys, vol->voxel_size, d_bo, nullptr);
         }
+        bs_free(ctx, d_bo);
     }
     bs_mark(ctx, "sign_ms");
     bs_free(ctx, d_sorted); bs_free(ctx, d_hdr); bs_free(ctx, d_coef); bs_free(ctx, d_rec);
