@@ -218,39 +218,107 @@ __device__ __forceinline__ float point_triangle_distance(f3 a, f3 b, f3 c, f3 ab
     return xsqrt(xnorm2(xsub(cp, p)));
 }
 
+// Distances. Each lane derives one sub-triangle (vertices, box, the <= 2x2x2 brick slots its box touches) and parks
+// it in shared memory; then the warp flattens the (sub-triangle, z-column) pairs of its 32 sub-triangles and deals
+// them out round robin, so lanes stay busy although box sizes differ (a plain thread-per-sub-triangle loop ran at
+// 10 of 32 lanes: r1 ncu). Boxes wider than 9 voxels (large narrow bands) take the per-thread path.
+constexpr int EV_REC = 27;  // words per parked sub-triangle (odd: conflict-free when lanes read different records)
 __global__ void __launch_bounds__(TPB) k_eval(ConvertParams P) {
     __shared__ unsigned long long s_off[TPB + 1];
+    __shared__ unsigned s_rec[TPB / 32][32 * EV_REC];
+    __shared__ unsigned s_pre[TPB / 32][33];
     TriCursor cur = locate(P, s_off);
-    if (!cur.valid) return;
-    const float* p = P.tris + 9 * cur.tri;
-    f3 A, B, C;
-    make_subtri(ld3(p), ld3(p + 3), ld3(p + 6), P.vs, cur.local, A, B, C);
-    int mn[3], mx[3];
-    if (!subtri_box(A, B, C, P.inv_vs, P.band, mn, mx)) return;
-    const f3 ab = xsub(B, A), ac = xsub(C, A);
+    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    unsigned* rec = s_rec[w] + lane * EV_REC;
+    f3 A{0.f, 0.f, 0.f}, B = A, C = A;
+    int mn[3] = {0, 0, 0}, mx[3] = {-1, -1, -1};
+    bool ok = false;
+    if (cur.valid) {
+        const float* p = P.tris + 9 * cur.tri;
+        make_subtri(ld3(p), ld3(p + 3), ld3(p + 6), P.vs, cur.local, A, B, C);
+        ok = subtri_box(A, B, C, P.inv_vs, P.band, mn, mx);
+    }
+    const int dx = ok ? mx[0] - mn[0] + 1 : 0, dy = ok ? mx[1] - mn[1] + 1 : 0, dz = ok ? mx[2] - mn[2] + 1 : 0;
+    const bool wide = dx > 9 || dy > 9 || dz > 9;
     unsigned* vals = reinterpret_cast<unsigned*>(P.values);
-    for (int bx = mn[0] >> 3; bx <= (mx[0] >> 3); ++bx)
-        for (int by = mn[1] >> 3; by <= (mx[1] >> 3); ++by)
-            for (int bz = mn[2] >> 3; bz <= (mx[2] >> 3); ++bz) {
-                unsigned slot = hash_lookup(P, bs_brick_key(bx, by, bz));
-                if (slot == 0xFFFFFFFFu) continue;  // brick not kept on this rank
-                unsigned* brick = vals + (size_t)slot * 512;
-                const int x0 = max(mn[0], bx << 3), x1 = min(mx[0], (bx << 3) + 7);
-                const int y0 = max(mn[1], by << 3), y1 = min(mx[1], (by << 3) + 7);
-                const int z0 = max(mn[2], bz << 3), z1 = min(mx[2], (bz << 3) + 7);
-                for (int x = x0; x <= x1; ++x) {
-                    const float xw = xmul((float)x, P.vs);
-                    for (int y = y0; y <= y1; ++y) {
-                        const float yw = xmul((float)y, P.vs);
-                        unsigned* line = brick + ((x & 7) << 6) + ((y & 7) << 3);
-                        for (int z = z0; z <= z1; ++z) {
-                            const float zw = xmul((float)z, P.vs);
-                            float d = point_triangle_distance(A, B, C, ab, ac, f3{xw, yw, zw});
-                            atomicMin(line + (z & 7), __float_as_uint(d));  // d >= 0 or NaN (NaN bits sort above the sentinel)
+    if (__any_sync(0xFFFFFFFFu, wide)) {  // rare: per-thread loops over the whole box
+        if (!ok) return;
+        const f3 ab = xsub(B, A), ac = xsub(C, A);
+        for (int bx = mn[0] >> 3; bx <= (mx[0] >> 3); ++bx)
+            for (int by = mn[1] >> 3; by <= (mx[1] >> 3); ++by)
+                for (int bz = mn[2] >> 3; bz <= (mx[2] >> 3); ++bz) {
+                    unsigned slot = hash_lookup(P, bs_brick_key(bx, by, bz));
+                    if (slot == 0xFFFFFFFFu) continue;  // brick not kept on this rank
+                    unsigned* brick = vals + (size_t)slot * 512;
+                    const int x0 = max(mn[0], bx << 3), x1 = min(mx[0], (bx << 3) + 7);
+                    const int y0 = max(mn[1], by << 3), y1 = min(mx[1], (by << 3) + 7);
+                    const int z0 = max(mn[2], bz << 3), z1 = min(mx[2], (bz << 3) + 7);
+                    for (int x = x0; x <= x1; ++x) {
+                        const float xw = xmul((float)x, P.vs);
+                        for (int y = y0; y <= y1; ++y) {
+                            const float yw = xmul((float)y, P.vs);
+                            unsigned* line = brick + ((x & 7) << 6) + ((y & 7) << 3);
+                            for (int z = z0; z <= z1; ++z) {
+                                const float zw = xmul((float)z, P.vs);
+                                float d = point_triangle_distance(A, B, C, ab, ac, f3{xw, yw, zw});
+                                atomicMin(line + (z & 7), __float_as_uint(d));  // d >= 0 or NaN (NaN bits sort above the sentinel)
+                            }
                         }
                     }
                 }
-            }
+        return;
+    }
+    // park: vertices, box origin, dims, brick slots
+    rec[0] = __float_as_uint(A.x); rec[1] = __float_as_uint(A.y); rec[2] = __float_as_uint(A.z);
+    rec[3] = __float_as_uint(B.x); rec[4] = __float_as_uint(B.y); rec[5] = __float_as_uint(B.z);
+    rec[6] = __float_as_uint(C.x); rec[7] = __float_as_uint(C.y); rec[8] = __float_as_uint(C.z);
+    rec[9] = (unsigned)mn[0]; rec[10] = (unsigned)mn[1]; rec[11] = (unsigned)mn[2];
+    rec[12] = (unsigned)dy | ((unsigned)dz << 8);
+    if (ok) {
+        const int bx0 = mn[0] >> 3, by0 = mn[1] >> 3, bz0 = mn[2] >> 3;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int bx = bx0 + (k & 1), by = by0 + ((k >> 1) & 1), bz = bz0 + (k >> 2);
+            const bool touched = bx <= (mx[0] >> 3) && by <= (mx[1] >> 3) && bz <= (mx[2] >> 3);
+            rec[13 + k] = touched ? hash_lookup(P, bs_brick_key(bx, by, bz)) : 0xFFFFFFFFu;
+        }
+    }
+    // exclusive prefix of column counts
+    const unsigned ncol = (unsigned)(dx * dy);
+    unsigned inc = ncol;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if ((int)lane >= o) inc += t; }
+    s_pre[w][lane + 1] = inc;
+    if (lane == 0) s_pre[w][0] = 0;
+    __syncwarp();
+    const unsigned total = s_pre[w][32];
+    for (unsigned c = lane; c < total; c += 32) {
+        // owner: last s with pre[s] <= c
+        unsigned lo = 0, hi = 32;
+        while (hi - lo > 1) { const unsigned mid = (lo + hi) >> 1; if (s_pre[w][mid] <= c) lo = mid; else hi = mid; }
+        const unsigned* r = s_rec[w] + lo * EV_REC;
+        const unsigned q = c - s_pre[w][lo];
+        const unsigned ddy = r[12] & 255u, ddz = r[12] >> 8;
+        const unsigned xi = q / ddy;
+        const unsigned yi = q - xi * ddy;
+        const f3 a{__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2])};
+        const f3 bb{__uint_as_float(r[3]), __uint_as_float(r[4]), __uint_as_float(r[5])};
+        const f3 cc{__uint_as_float(r[6]), __uint_as_float(r[7]), __uint_as_float(r[8])};
+        const f3 ab = xsub(bb, a), ac = xsub(cc, a);
+        const int x = (int)r[9] + (int)xi, y = (int)r[10] + (int)yi, z0 = (int)r[11];
+        const int kx = (x >> 3) - ((int)r[9] >> 3), ky = (y >> 3) - ((int)r[10] >> 3);
+        const float xw = xmul((float)x, P.vs), yw = xmul((float)y, P.vs);
+        const unsigned line_off = ((x & 7) << 6) + ((y & 7) << 3);
+        for (unsigned zi = 0; zi < ddz; ++zi) {
+            const int z = z0 + (int)zi;
+            const int kz = (z >> 3) - (z0 >> 3);
+            const unsigned slot = r[13 + kx + 2 * ky + 4 * kz];
+            if (slot == 0xFFFFFFFFu) continue;  // brick not kept on this rank
+            const float zw = xmul((float)z, P.vs);
+            const float d = point_triangle_distance(a, bb, cc, ab, ac, f3{xw, yw, zw});
+            atomicMin(vals + (size_t)slot * 512 + line_off + (z & 7), __float_as_uint(d));
+        }
+    }
 }
 
 __global__ void k_fill_slots(const unsigned long long* sorted_keys, size_t n, unsigned long long* table_keys, unsigned* table_slots, unsigned mask) {

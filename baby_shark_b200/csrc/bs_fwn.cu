@@ -17,6 +17,7 @@
 // Only the 0.2 threshold matters downstream, so FMA contraction is allowed here (unlike the distance stage).
 #include "bs_common.cuh"
 #include <cub/cub.cuh>
+#include <algorithm>
 
 namespace {
 
@@ -48,17 +49,27 @@ __device__ __forceinline__ int f2ord(float f) { int b = __float_as_int(f); retur
 __device__ __forceinline__ float ord2f(int o) { return __int_as_float(o >= 0 ? o : o ^ 0x7FFFFFFF); }
 
 __global__ void k_centroid_bounds(const float* __restrict__ tris, size_t n, int* bounds /*min xyz, max xyz as ordered ints*/) {
-    size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    float c[3] = {0, 0, 0}; bool ok = false;
-    if (t < n) {
+    // grid-stride, then warp shuffle + shared-memory reduction: six atomics per CTA, not per warp
+    __shared__ int s_lo[3][8], s_hi[3][8];
+    int lo[3] = {0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF}, hi[3] = {(int)0x80000000, (int)0x80000000, (int)0x80000000};
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
         const float* p = tris + 9 * t;
+        float c[3];
         for (int d = 0; d < 3; ++d) c[d] = (p[d] + p[3 + d] + p[6 + d]) * (1.0f / 3.0f);
-        ok = (c[0] == c[0]) && (c[1] == c[1]) && (c[2] == c[2]) && fabsf(c[0]) < 1e30f && fabsf(c[1]) < 1e30f && fabsf(c[2]) < 1e30f;
+        const bool ok = (c[0] == c[0]) && (c[1] == c[1]) && (c[2] == c[2]) && fabsf(c[0]) < 1e30f && fabsf(c[1]) < 1e30f && fabsf(c[2]) < 1e30f;
+        if (ok) for (int d = 0; d < 3; ++d) { const int o = f2ord(c[d]); lo[d] = min(lo[d], o); hi[d] = max(hi[d], o); }
     }
+    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (int d = 0; d < 3; ++d) {
-        int lo = ok ? f2ord(c[d]) : 0x7FFFFFFF, hi = ok ? f2ord(c[d]) : (int)0x80000000;
-        for (int o = 16; o; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, o)); hi = max(hi, __shfl_xor_sync(0xFFFFFFFFu, hi, o)); }
-        if ((threadIdx.x & 31) == 0) { atomicMin(bounds + d, lo); atomicMax(bounds + 3 + d, hi); }
+        for (int o = 16; o; o >>= 1) { lo[d] = min(lo[d], __shfl_xor_sync(0xFFFFFFFFu, lo[d], o)); hi[d] = max(hi[d], __shfl_xor_sync(0xFFFFFFFFu, hi[d], o)); }
+        if (lane == 0) { s_lo[d][w] = lo[d]; s_hi[d][w] = hi[d]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        const int d = threadIdx.x;
+        int l = s_lo[d][0], h = s_hi[d][0];
+        for (unsigned k = 1; k < blockDim.x / 32; ++k) { l = min(l, s_lo[d][k]); h = max(h, s_hi[d][k]); }
+        atomicMin(bounds + d, l); atomicMax(bounds + 3 + d, h);
     }
 }
 
@@ -235,7 +246,9 @@ __global__ void k_finalize_nodes(const Raw* __restrict__ raw, int n, float4* hdr
 // per entry {o1.xyz, trM, m00, m11, m22, m01+m10, m02+m20, m12+m21} packed from float 20 on.
 constexpr int REC = 16;  // float4 per record
 __global__ void k_records(const int* __restrict__ left, const int* __restrict__ right, const float4* __restrict__ hdr, const float4* __restrict__ coef, int n, float4* rec) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    // four consecutive lanes build one record (one entry each): 8 records per warp, stores land in 256 B runs
+    const size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const int x = (int)(g >> 2), e = (int)(g & 3);
     if (x >= n - 1) return;
     int ids[4] = {-1, -1, -1, -1}, k = 0;
     const int ch[2] = {left[x], right[x]};
@@ -244,17 +257,14 @@ __global__ void k_records(const int* __restrict__ left, const int* __restrict__ 
         else { ids[k++] = left[ch[c]]; ids[k++] = right[ch[c]]; }
     }
     float4* r = rec + (size_t)x * REC;
-    float* rf = reinterpret_cast<float*>(r);
-    for (int e = 0; e < 4; ++e) {
-        const bool ok = ids[e] >= 0;
-        r[e] = ok ? hdr[ids[e]] : make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0, c2 = c0;
-        if (ok) { c0 = coef[3 * (size_t)ids[e]]; c1 = coef[3 * (size_t)ids[e] + 1]; c2 = coef[3 * (size_t)ids[e] + 2]; }
-        float* o = rf + 20 + 10 * e;
-        o[0] = c0.x; o[1] = c0.y; o[2] = c0.z; o[3] = c0.w; o[4] = c1.x; o[5] = c1.y; o[6] = c1.z; o[7] = c1.w; o[8] = c2.x; o[9] = c2.y;
-    }
-    r[4] = make_float4(__int_as_float(ids[0]), __int_as_float(ids[1]), __int_as_float(ids[2]), __int_as_float(ids[3]));
-    r[15] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int id = ids[e];
+    float4 h = make_float4(0.f, 0.f, 0.f, 0.f), c0 = h, c1 = h, c2 = h;
+    if (id >= 0) { h = hdr[id]; c0 = coef[3 * (size_t)id]; c1 = coef[3 * (size_t)id + 1]; c2 = coef[3 * (size_t)id + 2]; }
+    r[e] = h;
+    float2* o = reinterpret_cast<float2*>(reinterpret_cast<float*>(r) + 20 + 10 * e);  // 8 B aligned
+    o[0] = make_float2(c0.x, c0.y); o[1] = make_float2(c0.z, c0.w); o[2] = make_float2(c1.x, c1.y); o[3] = make_float2(c1.z, c1.w); o[4] = make_float2(c2.x, c2.y);
+    if (e == 0) r[4] = make_float4(__int_as_float(ids[0]), __int_as_float(ids[1]), __int_as_float(ids[2]), __int_as_float(ids[3]));
+    if (e == 1) r[15] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // solid_angle / (4 pi) (aabb_tree.rs:582-628), Van Oosterom-Strackee form
@@ -618,7 +628,7 @@ bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_v
     BS_CUDA(ctx, cudaMemcpyAsync(d_bounds, init, sizeof(init), cudaMemcpyHostToDevice, st));
     BS_TRY(bs_alloc(ctx, &d_codes, n_tris)); BS_TRY(bs_alloc(ctx, &d_codes2, n_tris));
     BS_TRY(bs_alloc(ctx, &d_ids, n_tris)); BS_TRY(bs_alloc(ctx, &d_ids2, n_tris));
-    k_centroid_bounds<<<bs_blocks(n_tris, 256), 256, 0, st>>>(d_tris, n_tris, d_bounds);
+    k_centroid_bounds<<<(unsigned)std::min<size_t>(bs_blocks(n_tris, 256), (size_t)ctx->sm_count * 8), 256, 0, st>>>(d_tris, n_tris, d_bounds);
     k_morton<<<bs_blocks(n_tris, 256), 256, 0, st>>>(d_tris, n_tris, d_bounds, d_codes, d_ids);
     void* d_tmp = nullptr; size_t tmp_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_codes, d_codes2, d_ids, d_ids2, n_tris, 0, 63, st);
@@ -646,7 +656,7 @@ bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_v
 #endif
     k_leaves_and_climb<<<bs_blocks((size_t)n, 128), 128, 0, st>>>(d_tris, d_ids2, n_tris, d_sorted, d_raw, d_left, d_right, d_parent, d_flags, n);
     k_finalize_nodes<<<bs_blocks((size_t)n_nodes, 128), 128, 0, st>>>(d_raw, n, d_hdr, d_coef);
-    if (n > 1) k_records<<<bs_blocks((size_t)n - 1, 128), 128, 0, st>>>(d_left, d_right, d_hdr, d_coef, n, d_rec);
+    if (n > 1) k_records<<<bs_blocks(((size_t)n - 1) * 4, 256), 256, 0, st>>>(d_left, d_right, d_hdr, d_coef, n, d_rec);
     bs_free(ctx, d_raw); bs_free(ctx, d_ids2); bs_free(ctx, d_codes2); bs_free(ctx, d_left); bs_free(ctx, d_right); bs_free(ctx, d_parent); bs_free(ctx, d_flags);
     Tree T;
     T.hdr = d_hdr; T.coef = d_coef; T.rec = d_rec; T.tris = d_sorted; T.n_leaves = (unsigned)n; T.root = root_id;

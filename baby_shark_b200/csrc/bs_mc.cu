@@ -30,6 +30,7 @@ __constant__ signed char c_corner[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 
 struct VolView {
     const unsigned long long* keys; const float* values; const unsigned long long* masks; size_t n;
     const unsigned char* owned;  // nullptr = all
+    const int* nbr;              // 8 per brick: index of the brick at (+dx,+dy,+dz), bit0 = x, bit1 = y, bit2 = z; -1 = absent
     const unsigned long long* t8k; const float* t8v; size_t nt8;
     const unsigned long long* t128k; const float* t128v; size_t nt128;
 };
@@ -246,9 +247,8 @@ __device__ int emit_cell(Cell& q, float vs, float* out) {
 __device__ void stage_brick(const VolView& V, size_t b, float* s_val /*729*/, unsigned char* s_act /*729*/, long long* s_nb /*8*/, int* s_org /*3*/) {
     const unsigned tid = threadIdx.x;
     if (tid < 8) {
-        int bx, by, bz; bs_key_brick(V.keys[b], bx, by, bz);
-        if (tid == 0) { s_nb[0] = (long long)b; s_org[0] = bx << 3; s_org[1] = by << 3; s_org[2] = bz << 3; }
-        else s_nb[tid] = find_key(V.keys, V.n, bs_brick_key(bx + (tid & 1), by + ((tid >> 1) & 1), bz + ((tid >> 2) & 1)));
+        if (tid == 0) { int bx, by, bz; bs_key_brick(V.keys[b], bx, by, bz); s_org[0] = bx << 3; s_org[1] = by << 3; s_org[2] = bz << 3; }
+        s_nb[tid] = V.nbr[b * 8 + tid];  // precomputed: a binary search here would sit on every CTA's critical path
     }
     __syncthreads();
     for (unsigned i = tid; i < 729; i += blockDim.x) {
@@ -319,6 +319,16 @@ __global__ void __launch_bounds__(MC_TPB) k_mc(VolView V, const signed char* __r
     if (!WRITE) { if (tid == 0) item_counts[item] = (unsigned)total; return; }
     float* dst = out + (item_offsets[item] + (unsigned long long)excl) * 9;
     for (int i = 0; i < n * 9; ++i) dst[i] = local[i];
+}
+
+__global__ void k_mc_neighbours(const unsigned long long* __restrict__ keys, size_t n, int* nbr) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n * 8) return;
+    const size_t b = i >> 3; const unsigned d = (unsigned)(i & 7);
+    if (d == 0) { nbr[i] = (int)b; return; }
+    int bx, by, bz; bs_key_brick(keys[b], bx, by, bz);
+    bx += d & 1; by += (d >> 1) & 1; bz += d >> 2;
+    nbr[i] = (bx <= BS_BRICK_MAX && by <= BS_BRICK_MAX && bz <= BS_BRICK_MAX) ? (int)find_key(keys, n, bs_brick_key(bx, by, bz)) : -1;
 }
 
 // TreeNode::at on the flat volume: a brick voxel if active, else the value of an active tile covering it
@@ -436,7 +446,10 @@ bs_status bs_mc_impl(const bs_volume* v, float voxel_size, const float** d_verts
     bs_marks_begin(ctx);
     const size_t n = v->n_bricks, nt8 = v->n_tiles8, nt128 = v->n_tiles128, n_items = n + nt8 + nt128;
     if (n_items == 0) { bs_marks_end(ctx); return BS_OK; }
-    VolView V{v->keys, v->values, v->masks, n, v->owned, v->tile8_keys, v->tile8_values, nt8, v->tile128_keys, v->tile128_values, nt128};
+    int* d_nbr = nullptr;
+    BS_TRY(bs_alloc(ctx, &d_nbr, n * 8));
+    if (n) k_mc_neighbours<<<bs_blocks(n * 8, 256), 256, 0, st>>>(v->keys, n, d_nbr);
+    VolView V{v->keys, v->values, v->masks, n, v->owned, d_nbr, v->tile8_keys, v->tile8_values, nt8, v->tile128_keys, v->tile128_values, nt128};
     const signed char* tables = (const signed char*)ctx->d_mc33;
     unsigned *d_counts = nullptr, *d_pos = nullptr; unsigned long long *d_wide = nullptr, *d_off = nullptr;
     BS_TRY(bs_alloc(ctx, &d_counts, n_items)); BS_TRY(bs_alloc(ctx, &d_wide, n_items + 1)); BS_TRY(bs_alloc(ctx, &d_off, n_items + 1));
@@ -464,7 +477,7 @@ bs_status bs_mc_impl(const bs_volume* v, float voxel_size, const float** d_verts
         if (nt128) k_mc_tiles<true><<<(unsigned)nt128, 256, 0, st>>>(V, tables, voxel_size, 1, d_pos + n + nt8, nullptr, d_off, ctx->d_out_verts);
     }
     bs_mark(ctx, "mc_emit_ms");
-    bs_free(ctx, d_pos);
+    bs_free(ctx, d_pos); bs_free(ctx, d_nbr);
     bs_free(ctx, d_tmp); bs_free(ctx, d_counts); bs_free(ctx, d_wide); bs_free(ctx, d_off);
     if (s != BS_OK) return s;
     BS_CUDA(ctx, cudaGetLastError());
