@@ -130,9 +130,9 @@ __device__ bool interior_test_case13(const Cell& q) {  // :336-376
 // and whether the interior c-vertex is needed.
 #define ROW1(name, cfg) (len = MC33_ROW_##name, MC33_OFF_##name + (cfg) * MC33_ROW_##name)
 #define ROW2(name, cfg, sub) (len = MC33_ROW_##name, MC33_OFF_##name + ((cfg) * MC33_SUB_##name + (sub)) * MC33_ROW_##name)
-__device__ int select_tiling(const Cell& q, int& len, bool& need_c) {
+__device__ int select_tiling(const Cell& q, int& len, bool& need_c, bool& stale) {
     const int cf = q.cf;
-    need_c = false; len = 0;
+    need_c = false; stale = false; len = 0;
     switch (q.cs) {
         case 1: return ROW1(TILING_1, cf);
         case 2: return ROW1(TILING_2, cf);
@@ -141,7 +141,9 @@ __device__ int select_tiling(const Cell& q, int& len, bool& need_c) {
         case 5: return ROW1(TILING_5, cf);
         case 6:
             if (test_face(q, TB(TEST_6, cf, 0))) return ROW1(TILING_6_2, cf);
-            return test_interior(q, TB(TEST_6, cf, 1)) ? ROW1(TILING_6_1_1, cf) : ROW1(TILING_6_1_2, cf);
+            if (test_interior(q, TB(TEST_6, cf, 1))) return ROW1(TILING_6_1_1, cf);
+            stale = true;  // tiling 6.1.2 uses the c-vertex but the reference does not compute it here (marching_cubes.rs:103-111)
+            return ROW1(TILING_6_1_2, cf);
         case 7: {
             int sub = 0;
             if (test_face(q, TB(TEST_7, cf, 0))) sub += 1;
@@ -222,11 +224,7 @@ __device__ void compute_c_vertex(Cell& q) {  // :918-938
 
 // add_faces (:287-317). WRITE = false: count only.
 template <bool WRITE>
-__device__ int emit_cell(Cell& q, float vs, float* out) {
-    int len; bool need_c;
-    const int row = select_tiling(q, len, need_c);
-    if (len == 0) return 0;
-    if (need_c) compute_c_vertex(q);
+__device__ int emit_rows(const Cell& q, float vs, float* out, int row, int len) {
     int n = 0;
     for (int i = 0; i + 2 < len; i += 3) {
         const int e1 = q.T[row + i], e3 = q.T[row + i + 1], e2 = q.T[row + i + 2];
@@ -242,6 +240,19 @@ __device__ int emit_cell(Cell& q, float vs, float* out) {
     }
     return n;
 }
+template <bool WRITE>
+__device__ int emit_cell(Cell& q, float vs, float* out) {  // cells outside the brick pass (tiles): no c-vertex carry
+    int len; bool need_c, stale;
+    const int row = select_tiling(q, len, need_c, stale);
+    if (len == 0) return 0;
+    if (need_c) compute_c_vertex(q);
+    return emit_rows<WRITE>(q, vs, out, row, len);
+}
+
+// The reference keeps ONE c-vertex (`self.v12`) across cells and tiling 6.1.2 reads it without recomputing it, so a
+// 6.1.2 cell emits the c-vertex of the latest earlier cell (in visit order) that computed one, or (0,0,0).
+struct CarryV12 { float x, y, z; int valid; };
+struct CarryOp { __device__ CarryV12 operator()(const CarryV12& a, const CarryV12& b) const { return b.valid ? b : a; } };
 
 // Stage brick b and its +x/+y/+z halo: 9^3 values and active flags.
 __device__ void stage_brick(const VolView& V, size_t b, float* s_val /*729*/, unsigned char* s_act /*729*/, long long* s_nb /*8*/, int* s_org /*3*/) {
@@ -291,27 +302,60 @@ __device__ __forceinline__ bool load_cell(Cell& q, const float* s_val, const uns
 }
 
 // `pos` maps a brick to its rank in the merged (bricks + active tiles) visit order; nullptr = identity.
+// c-vertex carry: `writer[b]` receives the brick's last computed c-vertex (count pass); `incoming[b]` is the carry
+// entering the brick (nullptr = not known yet: readers that need it are counted tentatively and flag the brick in
+// `unresolved`); with `only_flagged` the count pass redoes just those bricks.
 template <bool WRITE>
 __global__ void __launch_bounds__(MC_TPB) k_mc(VolView V, const signed char* __restrict__ tables, float vs, const unsigned* __restrict__ pos,
-                                                unsigned* item_counts, const unsigned long long* __restrict__ item_offsets, float* out) {
+                                                unsigned* item_counts, const unsigned long long* __restrict__ item_offsets, float* out,
+                                                CarryV12* writer, const CarryV12* __restrict__ incoming, unsigned char* unresolved, int only_flagged, int* any_unresolved) {
     __shared__ float s_val[729];
     __shared__ unsigned char s_act[732];
     __shared__ long long s_nb[8];
     __shared__ int s_org[3];
+    __shared__ int s_maxw;
+    __shared__ unsigned s_wmask[16];
+    __shared__ float s_v12[MC_TPB * 3];
     const size_t b = blockIdx.x;
     const size_t item = pos ? pos[b] : b;
-    if (V.owned && !V.owned[b]) { if (!WRITE && threadIdx.x == 0) item_counts[item] = 0; return; }  // halo brick of a sharded volume
+    if (V.owned && !V.owned[b]) { if (!WRITE && !only_flagged && threadIdx.x == 0) { item_counts[item] = 0; writer[b] = CarryV12{0.f, 0.f, 0.f, 0}; unresolved[b] = 0; } return; }  // halo brick of a sharded volume
     if (WRITE) { if (item_offsets[item + 1] == item_offsets[item]) return; }  // uniform per block
-    stage_brick(V, b, s_val, s_act, s_nb, s_org);
+    if (!WRITE && only_flagged && !unresolved[b]) return;
     const unsigned tid = threadIdx.x;  // == leaf offset x<<6 | y<<3 | z of the cell's corner 0
+    if (tid == 0) s_maxw = -1;
+    if (tid < 16) s_wmask[tid] = 0;
+    stage_brick(V, b, s_val, s_act, s_nb, s_org);
     Cell q; q.T = tables; q.v12 = f3{0.f, 0.f, 0.f};
-    int id;
-    int n = 0;
-    float local[WRITE ? 12 * 9 : 1];
+    int id, row = 0, len = 0;
+    bool need_c = false, stale = false;
     if (load_cell(q, s_val, s_act, s_org, tid >> 6, (tid >> 3) & 7, tid & 7, id) && id != 0 && id != 255) {
         q.cs = tables[MC33_OFF_CASES + 2 * id]; q.cf = tables[MC33_OFF_CASES + 2 * id + 1];
-        n = emit_cell<WRITE>(q, vs, local);
+        row = select_tiling(q, len, need_c, stale);
+        if (need_c) { compute_c_vertex(q); atomicMax(&s_maxw, (int)tid); atomicOr(&s_wmask[tid >> 5], 1u << (tid & 31)); s_v12[3 * tid] = q.v12.x; s_v12[3 * tid + 1] = q.v12.y; s_v12[3 * tid + 2] = q.v12.z; }
     }
+    const int any_stale = __syncthreads_or(stale);
+    if (!WRITE && !only_flagged && tid == 0) {
+        const int mw = s_maxw;
+        writer[b] = mw >= 0 ? CarryV12{s_v12[3 * mw], s_v12[3 * mw + 1], s_v12[3 * mw + 2], 1} : CarryV12{0.f, 0.f, 0.f, 0};
+    }
+    bool unres = false;
+    if (any_stale && stale) {  // nearest earlier cell of this brick that computed a c-vertex, else the carry entering the brick
+        int widx = -1;
+        const unsigned wd = tid >> 5, bit = tid & 31;
+        unsigned m = s_wmask[wd] & ((1u << bit) - 1u);
+        if (m) widx = (int)(wd * 32 + (31 - __clz(m)));
+        else for (int k = (int)wd - 1; k >= 0; --k) if (s_wmask[k]) { widx = k * 32 + (31 - __clz(s_wmask[k])); break; }
+        if (widx >= 0) q.v12 = f3{s_v12[3 * widx], s_v12[3 * widx + 1], s_v12[3 * widx + 2]};
+        else if (incoming) { const CarryV12 c = incoming[b]; if (c.valid) q.v12 = f3{c.x, c.y, c.z}; }
+        else unres = true;
+    }
+    if (!WRITE && !only_flagged) {
+        const int u = __syncthreads_or(unres);
+        if (tid == 0) { unresolved[b] = (unsigned char)(u != 0); if (u) *any_unresolved = 1; }
+    }
+    int n = 0;
+    float local[WRITE ? 12 * 9 : 1];
+    if (len) n = emit_rows<WRITE>(q, vs, local, row, len);
     typedef cub::BlockScan<int, MC_TPB> Scan;
     __shared__ typename Scan::TempStorage tmp;
     int excl, total;
@@ -319,6 +363,11 @@ __global__ void __launch_bounds__(MC_TPB) k_mc(VolView V, const signed char* __r
     if (!WRITE) { if (tid == 0) item_counts[item] = (unsigned)total; return; }
     float* dst = out + (item_offsets[item] + (unsigned long long)excl) * 9;
     for (int i = 0; i < n * 9; ++i) dst[i] = local[i];
+}
+
+__global__ void k_shift_carry(const CarryV12* __restrict__ incl, CarryV12* excl, size_t n) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < n) excl[i] = i ? incl[i - 1] : CarryV12{0.f, 0.f, 0.f, 0};
 }
 
 __global__ void k_mc_neighbours(const unsigned long long* __restrict__ keys, size_t n, int* nbr) {
@@ -458,7 +507,22 @@ bs_status bs_mc_impl(const bs_volume* v, float voxel_size, const float** d_verts
         BS_TRY(bs_alloc(ctx, &d_pos, n_items));
         k_merge_pos<<<bs_blocks(std::max(n, std::max(nt8, nt128)), 256), 256, 0, st>>>(V, d_pos, d_pos + n, d_pos + n + nt8);
     }
-    if (n) k_mc<false><<<(unsigned)n, MC_TPB, 0, st>>>(V, tables, voxel_size, d_pos, d_counts, nullptr, nullptr);
+    CarryV12 *d_writer = nullptr, *d_carry_incl = nullptr, *d_incoming = nullptr; unsigned char* d_unres = nullptr; int* d_any = nullptr; int any_unres = 0;
+    BS_TRY(bs_alloc(ctx, &d_writer, n)); BS_TRY(bs_alloc(ctx, &d_unres, n)); BS_TRY(bs_alloc(ctx, &d_any, 1));
+    BS_CUDA(ctx, cudaMemsetAsync(d_any, 0, sizeof(int), st));
+    if (n) k_mc<false><<<(unsigned)n, MC_TPB, 0, st>>>(V, tables, voxel_size, d_pos, d_counts, nullptr, nullptr, d_writer, nullptr, d_unres, 0, d_any);
+    BS_CUDA(ctx, cudaMemcpyAsync(&any_unres, d_any, sizeof(int), cudaMemcpyDeviceToHost, st));
+    BS_CUDA(ctx, cudaStreamSynchronize(st));
+    if (any_unres) {  // rare: some 6.1.2 cell needs the c-vertex left behind by an earlier brick -> carry scan, recount those bricks
+        BS_TRY(bs_alloc(ctx, &d_carry_incl, n)); BS_TRY(bs_alloc(ctx, &d_incoming, n));
+        void* d_t2 = nullptr; size_t t2 = 0;
+        cub::DeviceScan::InclusiveScan(nullptr, t2, d_writer, d_carry_incl, CarryOp(), n, st);
+        BS_TRY(bs_alloc(ctx, (char**)&d_t2, t2));
+        cub::DeviceScan::InclusiveScan(d_t2, t2, d_writer, d_carry_incl, CarryOp(), n, st);
+        k_shift_carry<<<bs_blocks(n, 256), 256, 0, st>>>(d_carry_incl, d_incoming, n);
+        k_mc<false><<<(unsigned)n, MC_TPB, 0, st>>>(V, tables, voxel_size, d_pos, d_counts, nullptr, nullptr, d_writer, d_incoming, d_unres, 1, d_any);
+        bs_free(ctx, d_t2);
+    }
     if (nt8) k_mc_tiles<false><<<(unsigned)nt8, 256, 0, st>>>(V, tables, voxel_size, 0, d_pos + n, d_counts, nullptr, nullptr);
     if (nt128) k_mc_tiles<false><<<(unsigned)nt128, 256, 0, st>>>(V, tables, voxel_size, 1, d_pos + n + nt8, d_counts, nullptr, nullptr);
     k_widen<<<bs_blocks(n_items + 1, 256), 256, 0, st>>>(d_counts, d_wide, n_items);
@@ -472,12 +536,12 @@ bs_status bs_mc_impl(const bs_volume* v, float voxel_size, const float** d_verts
     bs_mark(ctx, "mc_count_ms");
     bs_status s = bs_ensure_out_verts(ctx, (size_t)n_tris * 9);
     if (s == BS_OK && n_tris) {
-        if (n) k_mc<true><<<(unsigned)n, MC_TPB, 0, st>>>(V, tables, voxel_size, d_pos, nullptr, d_off, ctx->d_out_verts);
+        if (n) k_mc<true><<<(unsigned)n, MC_TPB, 0, st>>>(V, tables, voxel_size, d_pos, nullptr, d_off, ctx->d_out_verts, nullptr, d_incoming, nullptr, 0, nullptr);
         if (nt8) k_mc_tiles<true><<<(unsigned)nt8, 256, 0, st>>>(V, tables, voxel_size, 0, d_pos + n, nullptr, d_off, ctx->d_out_verts);
         if (nt128) k_mc_tiles<true><<<(unsigned)nt128, 256, 0, st>>>(V, tables, voxel_size, 1, d_pos + n + nt8, nullptr, d_off, ctx->d_out_verts);
     }
     bs_mark(ctx, "mc_emit_ms");
-    bs_free(ctx, d_pos); bs_free(ctx, d_nbr);
+    bs_free(ctx, d_pos); bs_free(ctx, d_nbr); bs_free(ctx, d_writer); bs_free(ctx, d_carry_incl); bs_free(ctx, d_incoming); bs_free(ctx, d_unres); bs_free(ctx, d_any);
     bs_free(ctx, d_tmp); bs_free(ctx, d_counts); bs_free(ctx, d_wide); bs_free(ctx, d_off);
     if (s != BS_OK) return s;
     BS_CUDA(ctx, cudaGetLastError());

@@ -41,15 +41,102 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-scale", type=float, default=0.0625, help="scale of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ops", action="store_true", help="time the CSG (config 2) / offset (3) / dual contouring (4) rows instead of the remesh")
     return ap.parse_args()
 
 
 def workload(cfg, scale):
     from baby_shark_b200 import synth
     if cfg not in (3, 4, 5):
-        raise SystemExit("bench.py measures the convert + marching-cubes remesh path: --config 3, 4 or 5")
+        raise SystemExit("the remesh bench takes --config 3, 4 or 5")
     tris, vs, desc = synth.config_mesh(cfg, scale)
     return np.ascontiguousarray(tris, np.float32), float(vs), desc
+
+
+def run_ops(args):
+    """--ops: the other rows of the path on their BASELINE.json configs, single GPU, volumes resident in HBM:
+    config 2 = union + subtract of two tori then MC; config 3 = offset(+2 voxels) and offset(-2 voxels) then MC;
+    config 4 = convert + dual contouring. One JSON line with per-stage device times and rooflines."""
+    import torch
+    import baby_shark_b200 as B
+    from baby_shark_b200 import synth
+    L = B.load_library()
+    ctx = B.Context(0)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    cfg = args.config
+    mesh, vs, desc = synth.config_mesh(cfg, args.scale)
+    conv = lambda t: B.MeshToVolume(ctx).with_voxel_size(vs).convert(t)  # noqa: E731
+    stages, work, rl = {}, {}, []
+
+    def timed(fn, reps):
+        """average per-stage device ms over `reps` runs of fn (fn returns the stats dict of the call of interest)"""
+        acc = {}
+        for _ in range(reps):
+            for k, v in fn().items():
+                acc[k] = acc.get(k, 0.0) + v / reps
+        return acc
+
+    mc = B.MarchingCubesMesher().with_voxel_size(vs)
+    if cfg == 2:
+        a, b = conv(mesh[0]), conv(mesh[1])
+        for op in ("union", "subtract"):
+            for _ in range(args.warmup):
+                getattr(a.clone(), op)(b.clone())
+            def one(op=op):
+                r = getattr(a.clone(), op)(b.clone())
+                st = ctx.last_stats()
+                return st
+            st = timed(one, args.steps)
+            stages.update({op + "_" + k: v for k, v in st.items() if k.endswith("_ms")})
+            work.update({op + "_" + k: v for k, v in st.items() if not k.endswith("_ms")})
+            by = 6336.0 * st["n_merged_bricks"] + 4224.0 * (st["n_out_bricks"] - st["n_merged_bricks"])
+            rl.append({"kernel": "k_csg_bricks (%s)" % op, "bound": "hbm", "achieved": by / (st["csg_bricks_ms"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                       "ms": st["csg_bricks_ms"], "algorithmic": "6336 B x merged + 4224 B x copied bricks", "traffic": None})
+        metric, unit = "CSG union+subtract of two tori (flood fill + directory + brick merge)", "ms"
+        value = stages["union_total_ms"] + stages["subtract_total_ms"]
+    elif cfg == 3:
+        a = conv(mesh)
+        for sgn, name in ((2.0, "offset_plus"), (-2.0, "offset_minus")):
+            for _ in range(args.warmup):
+                a.clone().offset(sgn * vs)
+            def one(sgn=sgn):
+                a.clone().offset(sgn * vs)
+                return ctx.last_stats()
+            st = timed(one, args.steps)
+            stages.update({name + "_" + k: v for k, v in st.items() if k.endswith("_ms")})
+            work.update({name + "_" + k: v for k, v in st.items() if not k.endswith("_ms")})
+            by = 8.0 * st["n_out_bricks"] * 4224.0
+            rl.append({"kernel": "k_sweep x %d launches (%s)" % (st["n_sweep_launches"], name), "bound": "hbm", "achieved": by / (st["offset_sweep_ms"] * 1e-3) / 1e9, "peak": hbm_peak,
+                       "unit": "GB/s", "ms": st["offset_sweep_ms"], "algorithmic": "8 sweeps x n_out_bricks x 4224 B (dependency-bound: expected far below the roofline)", "traffic": None})
+        metric, unit = "offset +2 and -2 voxels of a ~1M-triangle sphere at 1024^3 (prune + 8 sweeps + shift)", "ms"
+        value = stages["offset_plus_total_ms"] + stages["offset_minus_total_ms"]
+    else:
+        a = conv(mesh)
+        dc = B.DualContouringMesher().with_voxel_size(vs)
+        for _ in range(args.warmup):
+            dc.mesh(a)
+        def one():
+            dc.mesh(a)
+            return ctx.last_stats()
+        st = timed(one, args.steps)
+        stages.update({k: v for k, v in st.items() if k.endswith("_ms")})
+        work.update({k: v for k, v in st.items() if not k.endswith("_ms")})
+        by = st["n_bricks"] * (11 ** 3 * 4 + 64) + 36.0 * st["n_out_tris"]
+        t = st["dc_cells_ms"] + st["dc_count_ms"] + st["dc_emit_ms"]
+        rl.append({"kernel": "k_dc_cells + k_dc_quads", "bound": "hbm", "achieved": by / (t * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "ms": t,
+                   "algorithmic": "n_bricks x 5388 B + 36 B x n_out_tris", "traffic": None})
+        metric, unit = "dual contouring of a 2M-triangle noise sphere at 1024^3 (triangles per second)", "tris/s"
+        value = st["n_out_tris"] / (t * 1e-3)
+    for r in rl:
+        r["frac"] = r["achieved"] / r["peak"]
+    print(json.dumps({"metric": metric, "value": value, "unit": unit, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "higher_is_better": unit != "ms",
+                      "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": "config %d: %s, scale %g" % (cfg, desc, args.scale), "voxel_size": vs},
+                      "stage_ms": stages, "work": work, "rooflines": rl, "roofline": max(rl, key=lambda r: r["ms"]) if rl else None}))
 
 
 class ClockSampler(threading.Thread):
@@ -133,6 +220,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.ops:
+        if rank == 0:
+            run_ops(args)
         return
 
     import torch

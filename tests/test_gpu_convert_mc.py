@@ -110,16 +110,10 @@ def test_mc_ambiguous_cases_random_field(bs, oracle):
     gv = bs.MarchingCubesMesher().with_voxel_size(0.5).mesh(gvol)
     ov, st = oracle.marching_cubes(ovol, 0.5, with_stats=True)
     assert all(st.case_hist[c] > 0 for c in range(1, 15)), list(st.case_hist)
-    assert gv.shape == ov.shape
-    # Known gap (DESIGN.md "MC33 case 6.1.2"): the reference never calls compute_c_vertex() for tiling 6.1.2
-    # (marching_cubes.rs:103-111) although that tiling uses the c-vertex, so it emits whatever c-vertex the
-    # previous cell left behind. The device path does not reproduce that stale value yet; every other triangle
-    # must be bit-identical and in the same position of the output.
-    same_tri = (gv.view(np.uint32).reshape(-1, 9) == ov.view(np.uint32).reshape(-1, 9)).all(axis=1)
-    assert same_tri.mean() > 0.97, same_tri.mean()
-    bad = ~same_tri
-    per_vertex_same = (gv.view(np.uint32).reshape(-1, 3, 3) == ov.view(np.uint32).reshape(-1, 3, 3)).all(axis=2)
-    assert (per_vertex_same[bad].sum(axis=1) == 2).all(), "a differing triangle may differ in its c-vertex only"
+    # includes tiling 6.1.2, where the reference emits the c-vertex left behind by an earlier cell
+    # (marching_cubes.rs:103-111 never calls compute_c_vertex for it): the device carries that value through the
+    # brick scan, so even those triangles are bit-identical
+    compare_soups(gv, ov, 0.5, ordered=True)
 
 
 def test_voxel_remesher_cube(bs):
@@ -153,3 +147,28 @@ def test_brick_sharded_outputs_concatenate_to_single_gpu_output(bs, world):
     assert owned == full.counts()["leaves"]
     compare_soups(np.concatenate(mc_parts), mc_full, vs, ordered=True)
     compare_soups(np.concatenate(dc_parts), dc_full, vs, ordered=True)
+
+
+def test_bunny_open_mesh_sign_agreement(bs, oracle, bunny):
+    # config 1 mesh (assets/bunny.stl, open at the base) at a coarser voxel so the CPU oracle finishes in seconds.
+    # Topology and |d| must be bit-exact. Signs come from different trees (device LBVH + hoisting vs the reference's
+    # SAH tree): they may differ only where the winding number is close to the 0.2 threshold, i.e. around the holes.
+    vs = 0.5
+    g = bs.MeshToVolume().with_voxel_size(vs).convert(bunny).download()
+    o = oracle.mesh_to_volume(bunny, vs, 0, 8)[0].download()
+    from util import active_mask_bits
+    assert np.array_equal(g["origins"], o["origins"])
+    m = active_mask_bits(o["masks"])
+    assert np.array_equal(active_mask_bits(g["masks"]), m)
+    gv, ov = g["values"][m], o["values"][m]
+    assert np.array_equal(np.abs(gv).view(np.uint32), np.abs(ov).view(np.uint32))
+    diff = np.signbit(gv) != np.signbit(ov)
+    frac = diff.mean()
+    print("bunny: %d active voxels, %d sign disagreements (%.4f%%)" % (gv.size, int(diff.sum()), 100 * frac))
+    assert frac < 2e-3
+    if diff.any():
+        # every disagreement sits where the exact winding number is near the threshold
+        idx = np.argwhere(m)[diff]
+        pts = (o["origins"][idx[:, 0]] + np.stack([idx[:, 1] >> 6, (idx[:, 1] >> 3) & 7, idx[:, 1] & 7], 1)).astype(np.float32) * np.float32(vs)
+        wn_exact, _ = oracle.winding_numbers(bunny, pts[:200], beta=-1.0)
+        assert (np.abs(wn_exact - 0.2) < 0.15).all(), wn_exact
