@@ -18,7 +18,7 @@
 
 namespace {
 
-constexpr int MC_TPB = 512;
+constexpr int MC_TPB = 256;
 constexpr float MIN_ABS = 1e-6f;  // MIN_ABS_VERTEX_VALUE (marching_cubes.rs:1123)
 
 __constant__ unsigned char c_iav[96] = MC33_IAV_PERM_INIT;
@@ -305,6 +305,12 @@ __device__ __forceinline__ bool load_cell(Cell& q, const float* s_val, const uns
 // c-vertex carry: `writer[b]` receives the brick's last computed c-vertex (count pass); `incoming[b]` is the carry
 // entering the brick (nullptr = not known yet: readers that need it are counted tentatively and flag the brick in
 // `unresolved`); with `only_flagged` the count pass redoes just those bricks.
+//
+// Inside the CTA: (1) every thread looks at two cells and keeps those with all 8 corners active and a sign change;
+// (2) the surviving cells (typically 60-120 of 512) are compacted in cell order, so the expensive MC33 logic runs on
+// dense lanes; (3) per-cell triangle counts are scanned; (4) the emit pass writes triangles straight to their final
+// place (no per-thread staging array).
+constexpr int MC_CELLS_PER_THREAD = 512 / MC_TPB;
 template <bool WRITE>
 __global__ void __launch_bounds__(MC_TPB) k_mc(VolView V, const signed char* __restrict__ tables, float vs, const unsigned* __restrict__ pos,
                                                 unsigned* item_counts, const unsigned long long* __restrict__ item_offsets, float* out,
@@ -313,56 +319,93 @@ __global__ void __launch_bounds__(MC_TPB) k_mc(VolView V, const signed char* __r
     __shared__ unsigned char s_act[732];
     __shared__ long long s_nb[8];
     __shared__ int s_org[3];
+    __shared__ unsigned short s_cells[512];      // compacted cell list: (cube id << 9) is kept separately
+    __shared__ unsigned char s_ids[512];
+    __shared__ unsigned s_wcount[MC_TPB / 32 * MC_CELLS_PER_THREAD + 1];
     __shared__ int s_maxw;
     __shared__ unsigned s_wmask[16];
-    __shared__ float s_v12[MC_TPB * 3];
+    __shared__ float s_v12[512 * 3];
     const size_t b = blockIdx.x;
     const size_t item = pos ? pos[b] : b;
     if (V.owned && !V.owned[b]) { if (!WRITE && !only_flagged && threadIdx.x == 0) { item_counts[item] = 0; writer[b] = CarryV12{0.f, 0.f, 0.f, 0}; unresolved[b] = 0; } return; }  // halo brick of a sharded volume
     if (WRITE) { if (item_offsets[item + 1] == item_offsets[item]) return; }  // uniform per block
     if (!WRITE && only_flagged && !unresolved[b]) return;
-    const unsigned tid = threadIdx.x;  // == leaf offset x<<6 | y<<3 | z of the cell's corner 0
+    const unsigned tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     if (tid == 0) s_maxw = -1;
     if (tid < 16) s_wmask[tid] = 0;
     stage_brick(V, b, s_val, s_act, s_nb, s_org);
-    Cell q; q.T = tables; q.v12 = f3{0.f, 0.f, 0.f};
-    int id, row = 0, len = 0;
-    bool need_c = false, stale = false;
-    if (load_cell(q, s_val, s_act, s_org, tid >> 6, (tid >> 3) & 7, tid & 7, id) && id != 0 && id != 255) {
-        q.cs = tables[MC33_OFF_CASES + 2 * id]; q.cf = tables[MC33_OFF_CASES + 2 * id + 1];
-        row = select_tiling(q, len, need_c, stale);
-        if (need_c) { compute_c_vertex(q); atomicMax(&s_maxw, (int)tid); atomicOr(&s_wmask[tid >> 5], 1u << (tid & 31)); s_v12[3 * tid] = q.v12.x; s_v12[3 * tid + 1] = q.v12.y; s_v12[3 * tid + 2] = q.v12.z; }
+    // (1) + (2): candidate cells in cell order (cell c = leaf offset x<<6 | y<<3 | z of corner 0)
+    unsigned bal[MC_CELLS_PER_THREAD]; int cid[MC_CELLS_PER_THREAD];
+#pragma unroll
+    for (int r = 0; r < MC_CELLS_PER_THREAD; ++r) {
+        const unsigned c = r * MC_TPB + tid;
+        const unsigned x = c >> 6, y = (c >> 3) & 7, z = c & 7;
+        int id = 0; bool all = true;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const unsigned j = (x + c_corner[i][0]) * 81 + (y + c_corner[i][1]) * 9 + (z + c_corner[i][2]);
+            all = all && s_act[j];
+            id |= (int)(__float_as_uint(s_val[j]) >> 31) << i;  // clamping to +-1e-6 keeps the sign bit: id bit = sign bit
+        }
+        cid[r] = id;
+        bal[r] = __ballot_sync(0xFFFFFFFFu, all && id != 0 && id != 255);
+        if (lane == 0) s_wcount[r * (MC_TPB / 32) + w] = __popc(bal[r]);
     }
-    const int any_stale = __syncthreads_or(stale);
-    if (!WRITE && !only_flagged && tid == 0) {
-        const int mw = s_maxw;
-        writer[b] = mw >= 0 ? CarryV12{s_v12[3 * mw], s_v12[3 * mw + 1], s_v12[3 * mw + 2], 1} : CarryV12{0.f, 0.f, 0.f, 0};
-    }
-    bool unres = false;
-    if (any_stale && stale) {  // nearest earlier cell of this brick that computed a c-vertex, else the carry entering the brick
-        int widx = -1;
-        const unsigned wd = tid >> 5, bit = tid & 31;
-        unsigned m = s_wmask[wd] & ((1u << bit) - 1u);
-        if (m) widx = (int)(wd * 32 + (31 - __clz(m)));
-        else for (int k = (int)wd - 1; k >= 0; --k) if (s_wmask[k]) { widx = k * 32 + (31 - __clz(s_wmask[k])); break; }
-        if (widx >= 0) q.v12 = f3{s_v12[3 * widx], s_v12[3 * widx + 1], s_v12[3 * widx + 2]};
-        else if (incoming) { const CarryV12 c = incoming[b]; if (c.valid) q.v12 = f3{c.x, c.y, c.z}; }
-        else unres = true;
-    }
-    if (!WRITE && !only_flagged) {
-        const int u = __syncthreads_or(unres);
-        if (tid == 0) { unresolved[b] = (unsigned char)(u != 0); if (u) *any_unresolved = 1; }
-    }
-    int n = 0;
-    float local[WRITE ? 12 * 9 : 1];
-    if (len) n = emit_rows<WRITE>(q, vs, local, row, len);
+    __syncthreads();
+    if (tid == 0) { unsigned acc = 0; for (int i = 0; i < MC_TPB / 32 * MC_CELLS_PER_THREAD; ++i) { const unsigned c = s_wcount[i]; s_wcount[i] = acc; acc += c; } s_wcount[MC_TPB / 32 * MC_CELLS_PER_THREAD] = acc; }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < MC_CELLS_PER_THREAD; ++r)
+        if ((bal[r] >> lane) & 1) { const unsigned p = s_wcount[r * (MC_TPB / 32) + w] + __popc(bal[r] & ((1u << lane) - 1)); s_cells[p] = (unsigned short)(r * MC_TPB + tid); s_ids[p] = (unsigned char)cid[r]; }
+    __syncthreads();
+    const int n_act = (int)s_wcount[MC_TPB / 32 * MC_CELLS_PER_THREAD];
+    // (3): MC33 on the compacted cells; n_act <= 512 -> up to MC_CELLS_PER_THREAD rounds, almost always one
     typedef cub::BlockScan<int, MC_TPB> Scan;
     __shared__ typename Scan::TempStorage tmp;
-    int excl, total;
-    Scan(tmp).ExclusiveSum(n, excl, total);
-    if (!WRITE) { if (tid == 0) item_counts[item] = (unsigned)total; return; }
-    float* dst = out + (item_offsets[item] + (unsigned long long)excl) * 9;
-    for (int i = 0; i < n * 9; ++i) dst[i] = local[i];
+    unsigned long long running = 0;
+    bool brick_unres = false;
+    for (int base = 0; base < n_act || base == 0; base += MC_TPB) {
+        const int j = base + (int)tid;
+        Cell q; q.T = tables; q.v12 = f3{0.f, 0.f, 0.f};
+        int row = 0, len = 0; bool need_c = false, stale = false;
+        if (j < n_act) {
+            const unsigned c = s_cells[j];
+            int id;
+            load_cell(q, s_val, s_act, s_org, c >> 6, (c >> 3) & 7, c & 7, id);
+            q.cs = tables[MC33_OFF_CASES + 2 * id]; q.cf = tables[MC33_OFF_CASES + 2 * id + 1];
+            row = select_tiling(q, len, need_c, stale);
+            if (need_c) { compute_c_vertex(q); atomicMax(&s_maxw, j); atomicOr(&s_wmask[j >> 5], 1u << (j & 31)); s_v12[3 * j] = q.v12.x; s_v12[3 * j + 1] = q.v12.y; s_v12[3 * j + 2] = q.v12.z; }
+        }
+        const int any_stale = __syncthreads_or(stale);
+        bool unres = false;
+        if (any_stale && stale) {  // nearest earlier cell of this brick that computed a c-vertex, else the carry entering the brick
+            int widx = -1;
+            const int wd = j >> 5, bit = j & 31;
+            const unsigned m = s_wmask[wd] & ((1u << bit) - 1u);
+            if (m) widx = wd * 32 + (31 - __clz(m));
+            else for (int k = wd - 1; k >= 0; --k) if (s_wmask[k]) { widx = k * 32 + (31 - __clz(s_wmask[k])); break; }
+            if (widx >= 0) q.v12 = f3{s_v12[3 * widx], s_v12[3 * widx + 1], s_v12[3 * widx + 2]};
+            else if (incoming) { const CarryV12 cv = incoming[b]; if (cv.valid) q.v12 = f3{cv.x, cv.y, cv.z}; }
+            else unres = true;
+        }
+        if (any_stale && !WRITE && !only_flagged) brick_unres = brick_unres || (__syncthreads_or(unres) != 0);
+        int n = 0;
+        if (len) n = emit_rows<false>(q, vs, nullptr, row, len);
+        int excl, total;
+        Scan(tmp).ExclusiveSum(n, excl, total);
+        if (WRITE && n) emit_rows<true>(q, vs, out + (item_offsets[item] + running + (unsigned long long)excl) * 9, row, len);
+        running += (unsigned long long)total;
+        __syncthreads();
+    }
+    if (!WRITE && tid == 0) {
+        item_counts[item] = (unsigned)running;
+        if (!only_flagged) {
+            const int mw = s_maxw;
+            writer[b] = mw >= 0 ? CarryV12{s_v12[3 * mw], s_v12[3 * mw + 1], s_v12[3 * mw + 2], 1} : CarryV12{0.f, 0.f, 0.f, 0};
+            unresolved[b] = (unsigned char)brick_unres;
+            if (brick_unres) *any_unresolved = 1;
+        }
+    }
 }
 
 __global__ void k_shift_carry(const CarryV12* __restrict__ incl, CarryV12* excl, size_t n) {
