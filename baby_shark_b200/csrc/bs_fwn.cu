@@ -18,6 +18,7 @@
 #include "bs_common.cuh"
 #include <cub/cub.cuh>
 #include <algorithm>
+#include <cstdlib>
 
 namespace {
 
@@ -267,17 +268,32 @@ __global__ void k_records(const int* __restrict__ left, const int* __restrict__ 
     if (e == 1) r[15] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+__device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+// atan2 to ~1e-5 rad (odd minimax polynomial on [0,1] + octant folding): the sum of solid angles only has to
+// resolve the 0.2 threshold, libm's 1-ulp atan2f costs three times the instructions
+__device__ __forceinline__ float fast_atan2(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float a = mn * fast_rcp(mx);
+    const float s = a * a;
+    float r = fmaf(fmaf(fmaf(fmaf(0.0208351f, s, -0.0851330f), s, 0.1801410f), s, -0.3302995f), s, 0.9998660f) * a;
+    if (ay > ax) r = 1.57079637f - r;
+    if (x < 0.f) r = 3.14159274f - r;
+    return copysignf(r, y);
+}
+
 // solid_angle / (4 pi) (aabb_tree.rs:582-628), Van Oosterom-Strackee form
 __device__ __forceinline__ float tri_winding(const float4 t0, const float4 t1, const float4 t2, float qx, float qy, float qz) {
     const float ax = t0.x - qx, ay = t0.y - qy, az = t0.z - qz;
     const float bx = t0.w - qx, by = t1.x - qy, bz = t1.y - qz;
     const float cx = t1.z - qx, cy = t1.w - qy, cz = t2.x - qz;
-    const float la = sqrtf(ax * ax + ay * ay + az * az), lb = sqrtf(bx * bx + by * by + bz * bz), lc = sqrtf(cx * cx + cy * cy + cz * cz);
+    const float la = fast_sqrt(fmaf(az, az, fmaf(ay, ay, ax * ax))), lb = fast_sqrt(fmaf(bz, bz, fmaf(by, by, bx * bx))), lc = fast_sqrt(fmaf(cz, cz, fmaf(cy, cy, cx * cx)));
     if (la == 0.f || lb == 0.f || lc == 0.f) return 0.f;
     const float det = ax * (by * cz - bz * cy) + ay * (bz * cx - bx * cz) + az * (bx * cy - by * cx);
     if (det == 0.f) return 0.f;
     const float den = la * lb * lc + (ax * bx + ay * by + az * bz) * lc + (ax * cx + ay * cy + az * cz) * lb + (bx * cx + by * cy + bz * cz) * la;
-    return atan2f(det, den) * (2.0f * INV_4PI);
+    return fast_atan2(det, den) * (2.0f * INV_4PI);
 }
 
 // Warp-cooperative winding numbers of up to 32*VPL query points (VPL per lane). The warp walks ONE shared stack
@@ -398,7 +414,7 @@ struct WarpWinding {
 // O((rho/d)^3) across the brick, far below what the 0.2 threshold can see. Everything closer is handed to the
 // per-voxel traversal as a list of sub-tree roots, so the per-voxel criterion of the reference (aabb_tree.rs:666)
 // still decides there. Lists are built with ballot-ordered compaction: the summation order is deterministic.
-constexpr float KAPPA = 4.0f;
+constexpr float KAPPA_DEFAULT = 4.0f;
 constexpr int MAX_ROOTS = 96;
 constexpr int MAX_HOIST = 640;
 constexpr int MAX_FRONT = 96;
@@ -406,7 +422,7 @@ constexpr int BP_WARPS = 4;
 struct BrickOut { float far[27]; unsigned n_roots; unsigned roots[MAX_ROOTS]; };  // n_roots = 0xFFFFFFFF: no hoisting, start at the tree root
 
 template <bool COUNT>
-__global__ void __launch_bounds__(32 * BP_WARPS) k_brick_pass(Tree T, const unsigned long long* __restrict__ keys, size_t n_bricks, float vs, BrickOut* out, unsigned long long* counters) {
+__global__ void __launch_bounds__(32 * BP_WARPS) k_brick_pass(Tree T, const unsigned long long* __restrict__ keys, size_t n_bricks, float vs, float KAPPA, BrickOut* out, unsigned long long* counters) {
     __shared__ unsigned s_front[BP_WARPS][2][MAX_FRONT];
     __shared__ unsigned s_hoist[BP_WARPS][MAX_HOIST];   // (record id << 2 | entry); the root itself is 0xFFFFFFFF
     __shared__ unsigned s_roots[BP_WARPS][MAX_ROOTS];
@@ -423,7 +439,7 @@ __global__ void __launch_bounds__(32 * BP_WARPS) k_brick_pass(Tree T, const unsi
     // 0 hoist, 1 root, 2 descend, 3 none
     auto classify = [&](unsigned id, const float4 h) -> int {
         const float dx = h.x - cx, dy = h.y - cy, dz = h.z - cz;
-        const float d = sqrtf(dx * dx + dy * dy + dz * dz), br = sqrtf(h.w);  // br = beta * radius
+        const float d = fast_sqrt(dx * dx + dy * dy + dz * dz), br = fast_sqrt(h.w);  // br = beta * radius
         const bool brick_far = (d - rho) > br;
         if (brick_far && d >= kr) return 0;
         if (brick_far || id >= T.n_leaves - 1 || br <= kr) return 1;  // close: the whole sub-tree goes to the per-voxel traversal
@@ -664,19 +680,21 @@ bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_v
     if (vol->n_bricks) {
         const size_t blocks = vol->n_bricks;  // one CTA per brick: the block scheduler balances the load
         BrickOut* d_bo = nullptr;
+        float kappa = KAPPA_DEFAULT;
+        if (const char* e = getenv("BSHARK_KAPPA")) kappa = (float)atof(e);  // tuning knob for experiments only
         BS_TRY(bs_alloc(ctx, &d_bo, vol->n_bricks));
         if (ctx->count_work) {
             unsigned long long* d_cnt = nullptr; unsigned long long h_cnt[9];
             BS_TRY(bs_alloc(ctx, &d_cnt, 9));
             BS_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, 72, st));
-            k_brick_pass<true><<<bs_blocks(vol->n_bricks, BP_WARPS), 32 * BP_WARPS, 0, st>>>(T, vol->keys, vol->n_bricks, vol->voxel_size, d_bo, d_cnt);
+            k_brick_pass<true><<<bs_blocks(vol->n_bricks, BP_WARPS), 32 * BP_WARPS, 0, st>>>(T, vol->keys, vol->n_bricks, vol->voxel_size, kappa, d_bo, d_cnt);
             k_sign<true, BS_VPL><<<(unsigned)blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(T, vol->values, vol->masks, vol->n_bricks, vol->keys, vol->voxel_size, d_bo, d_cnt);
             BS_CUDA(ctx, cudaMemcpyAsync(h_cnt, d_cnt, 72, cudaMemcpyDeviceToHost, st));
             BS_CUDA(ctx, cudaStreamSynchronize(st));
             bs_free(ctx, d_cnt);
             ctx->fwn_counts[0] = (double)h_cnt[0]; ctx->fwn_counts[1] = (double)h_cnt[1]; ctx->fwn_counts[2] = (double)h_cnt[2]; ctx->fwn_counts[3] = (double)h_cnt[3]; ctx->fwn_counts[4] = (double)h_cnt[4]; ctx->fwn_counts[5] = (double)h_cnt[5]; ctx->fwn_counts[6] = (double)h_cnt[6]; ctx->fwn_counts[7] = (double)h_cnt[7]; ctx->fwn_counts[8] = (double)h_cnt[8];
         } else {
-            k_brick_pass<false><<<bs_blocks(vol->n_bricks, BP_WARPS), 32 * BP_WARPS, 0, st>>>(T, vol->keys, vol->n_bricks, vol->voxel_size, d_bo, nullptr);
+            k_brick_pass<false><<<bs_blocks(vol->n_bricks, BP_WARPS), 32 * BP_WARPS, 0, st>>>(T, vol->keys, vol->n_bricks, vol->voxel_size, kappa, d_bo, nullptr);
             bs_mark(ctx, "sign_brick_pass_ms");
             k_sign<false, BS_VPL><<<(unsigned)blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(T, vol->values, vol->masks, vol->n_bricks, vol->keys, vol->voxel_size, d_bo, nullptr);
         }
