@@ -131,7 +131,7 @@ inline unsigned bs_blocks(size_t n, unsigned threads) { return (unsigned)((n + t
 // stage entry points (one .cu each)
 bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, float voxel_size, int64_t band,
                           int rank, int world, bs_volume** out);
-bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_volume* vol);
+bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_volume* vol, const unsigned long long* d_touches /*per brick, may be null*/);
 bs_status bs_mc_impl(const bs_volume* v, float voxel_size, const float** d_verts, size_t* n_verts);
 bs_status bs_dc_impl(const bs_volume* v, float voxel_size, const float** d_verts, size_t* n_verts);
 bs_status bs_csg_impl(bs_volume* a, bs_volume* b, int op, bs_volume** out);

@@ -29,6 +29,7 @@ struct ConvertParams {
     unsigned long long total;
     float vs, inv_vs; int band;
     unsigned long long* table_keys; unsigned* table_slots; unsigned table_mask;
+    unsigned* table_counts;  // per hash slot: how many sub-triangle boxes touch the brick (load-balancing weight for sharding); may be null
     float* values;
     int* flags;  // [0] hash overflow, [1] index range error
     unsigned long long* n_eval;  // sum of box volumes = point-triangle evaluations (roofline work counter)
@@ -141,11 +142,12 @@ __device__ __forceinline__ void hash_insert(const ConvertParams& P, unsigned lon
     unsigned h = (unsigned)hash64(key) & P.table_mask;
     for (int probe = 0; probe < MAX_PROBE; ++probe) {
         unsigned long long cur = P.table_keys[h];
-        if (cur == key) return;
-        if (cur == BS_KEY_INVALID) {
+        bool mine = cur == key;
+        if (!mine && cur == BS_KEY_INVALID) {
             unsigned long long prev = atomicCAS(&P.table_keys[h], BS_KEY_INVALID, key);
-            if (prev == BS_KEY_INVALID || prev == key) return;
+            mine = prev == BS_KEY_INVALID || prev == key;
         }
+        if (mine) { if (P.table_counts) atomicAdd(&P.table_counts[h], 1u); return; }
         h = (h + 1) & P.table_mask;
     }
     P.flags[0] = 1;
@@ -347,6 +349,27 @@ __global__ void k_mark_slab(const unsigned long long* __restrict__ keys, size_t 
     const long long j = find_sorted(keys, n, bs_brick_key(bx, by, bz));
     if (j >= 0) keep[j] = 1;
 }
+// weight of sorted brick i = touches(i) + mean touches; W[i] = inclusive prefix. bounds[r] = first i with W[i] >= r * W_total / world
+__global__ void k_brick_touches(const unsigned long long* __restrict__ keys, size_t n, const unsigned long long* __restrict__ table_keys, const unsigned* __restrict__ table_counts, unsigned mask, unsigned long long* touches) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long key = keys[i];
+    unsigned h = (unsigned)hash64(key) & mask;
+    while (table_keys[h] != key) h = (h + 1) & mask;
+    touches[i] = table_counts[h];
+}
+__global__ void k_slab_bounds(const unsigned long long* __restrict__ C /*inclusive scan of touches*/, size_t n, int world, unsigned long long* bounds /*world + 1*/) {
+    const int r = threadIdx.x;
+    if (r > world) return;
+    if (r == 0) { bounds[0] = 0; return; }
+    if (r == world) { bounds[world] = n; return; }
+    const unsigned long long total = C[n - 1], mean = total / n + 1;
+    const unsigned long long Wtot = total + (unsigned long long)n * mean;
+    const unsigned long long target = Wtot / (unsigned long long)world * (unsigned long long)r;
+    size_t lo = 0, hi = n;  // first i with C[i] + (i+1)*mean >= target
+    while (lo < hi) { const size_t mid = (lo + hi) >> 1; if (C[mid] + (unsigned long long)(mid + 1) * mean < target) lo = mid + 1; else hi = mid; }
+    bounds[r] = lo;
+}
 __global__ void k_owned(const unsigned long long* __restrict__ all_keys, size_t n_all, size_t lo, size_t hi, const unsigned long long* __restrict__ kept, size_t n_kept, unsigned char* owned) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= n_kept) return;
@@ -421,19 +444,21 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
 
     ConvertParams P;
     P.tris = d_tris; P.n_tris = n_tris; P.offsets = d_offsets; P.total = total;
-    P.vs = voxel_size; P.inv_vs = 1.0f / voxel_size; P.band = (int)band; P.flags = d_flags; P.values = nullptr; P.n_eval = d_neval;
+    P.vs = voxel_size; P.inv_vs = 1.0f / voxel_size; P.band = (int)band; P.flags = d_flags; P.values = nullptr; P.n_eval = d_neval; P.table_counts = nullptr;
 
     // 2. mark touched bricks in a hash set; sized from the surface area, doubled on overflow
     const double bw = (double)(2 * band + 1);
     double est = 0.15 * area_vox * bw + 8192.0;
     if (est > 6.0e8) est = 6.0e8;
     size_t cap = 1; while ((double)cap < 2.0 * est) cap <<= 1;
-    unsigned long long* d_table_keys = nullptr; unsigned* d_table_slots = nullptr;
+    unsigned long long* d_table_keys = nullptr; unsigned* d_table_slots = nullptr; unsigned* d_table_counts = nullptr;
     unsigned long long* d_keys = nullptr; size_t n_all = 0; unsigned long long n_eval = 0;
     const unsigned grid = (unsigned)((total + TPB - 1) / TPB);
     for (;;) {
         BS_TRY(bs_alloc(ctx, &d_table_keys, cap));
         BS_CUDA(ctx, cudaMemsetAsync(d_table_keys, 0xFF, cap * sizeof(unsigned long long), st));
+        { BS_TRY(bs_alloc(ctx, &d_table_counts, cap)); BS_CUDA(ctx, cudaMemsetAsync(d_table_counts, 0, cap * sizeof(unsigned), st)); }
+        P.table_counts = d_table_counts;
         BS_CUDA(ctx, cudaMemsetAsync(d_neval, 0, sizeof(unsigned long long), st));
         P.table_keys = d_table_keys; P.table_slots = nullptr; P.table_mask = (unsigned)(cap - 1);
         k_mark<<<grid, TPB, 0, st>>>(P);
@@ -443,7 +468,7 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
         BS_CUDA(ctx, cudaStreamSynchronize(st));
         if (flags[1]) { bs_free(ctx, d_table_keys); bs_free(ctx, d_offsets); bs_free(ctx, d_flags); return bs_fail(ctx, BS_ERR_RANGE, "voxel index outside [-2^20, 2^20)"); }
         if (!flags[0]) break;
-        bs_free(ctx, d_table_keys);
+        bs_free(ctx, d_table_keys); bs_free(ctx, d_table_counts); d_table_counts = nullptr;
         BS_CUDA(ctx, cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), st));
         cap <<= 1;
         if (cap > (1ull << 31)) { bs_free(ctx, d_offsets); bs_free(ctx, d_flags); return bs_fail(ctx, BS_ERR_RANGE, "brick hash set overflow"); }
@@ -473,7 +498,24 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
     if (world > 1) {
         // brick-slab sharding: this rank owns the contiguous slab [lo, hi) of the sorted brick list and keeps, as
         // read-only halo, the 26 neighbours of its bricks (extraction needs +1 for MC, -1..+1 for DC)
-        const size_t lo = n_all * (size_t)rank / (size_t)world, hi = n_all * (size_t)(rank + 1) / (size_t)world;
+        // slab boundaries at equal cumulative weight (weight = sub-triangle boxes touching the brick + their mean): bricks
+        // under dense triangles (e.g. the poles of a UV sphere) cost several times more in the distance and sign stages
+        size_t lo, hi;
+        {
+            unsigned long long *d_touch = nullptr, *d_C = nullptr, *d_bounds = nullptr; unsigned long long h_bounds[2];
+            BS_TRY(bs_alloc(ctx, &d_touch, n_all)); BS_TRY(bs_alloc(ctx, &d_C, n_all)); BS_TRY(bs_alloc(ctx, &d_bounds, (size_t)world + 1));
+            k_brick_touches<<<bs_blocks(n_all, TPB), TPB, 0, st>>>(d_keys, n_all, d_table_keys, d_table_counts, (unsigned)(cap - 1), d_touch);
+            tmp_bytes = 0;
+            cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, d_touch, d_C, n_all, st);
+            BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp_bytes));
+            cub::DeviceScan::InclusiveSum(d_tmp, tmp_bytes, d_touch, d_C, n_all, st);
+            k_slab_bounds<<<1, 64, 0, st>>>(d_C, n_all, world, d_bounds);
+            BS_CUDA(ctx, cudaMemcpyAsync(h_bounds, d_bounds + rank, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            BS_CUDA(ctx, cudaStreamSynchronize(st));
+            bs_free(ctx, d_tmp); bs_free(ctx, d_touch); bs_free(ctx, d_C); bs_free(ctx, d_bounds);
+            lo = (size_t)h_bounds[0]; hi = (size_t)h_bounds[1];
+            if (hi < lo) hi = lo;
+        }
         unsigned char* d_keep = nullptr; unsigned long long* d_kept = nullptr; size_t* d_nk = nullptr; size_t n_kept = 0;
         BS_TRY(bs_alloc(ctx, &d_keep, n_all)); BS_TRY(bs_alloc(ctx, &d_kept, n_all)); BS_TRY(bs_alloc(ctx, &d_nk, 1));
         BS_CUDA(ctx, cudaMemsetAsync(d_keep, 0, n_all, st));
@@ -508,9 +550,14 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
     P.table_slots = d_table_slots; P.values = vol->values;
     k_eval<<<grid, TPB, 0, st>>>(P);
     bs_mark(ctx, "udf_ms");
-    bs_free(ctx, d_table_keys); bs_free(ctx, d_table_slots); bs_free(ctx, d_offsets); bs_free(ctx, d_flags); bs_free(ctx, d_neval);
+    // per-brick "touches" (sub-triangle boxes that hit the brick): the sign stage runs the densest bricks first
+    unsigned long long* d_touch_kept = nullptr;
+    BS_TRY(bs_alloc(ctx, &d_touch_kept, n_all));
+    if (n_all) k_brick_touches<<<bs_blocks(n_all, TPB), TPB, 0, st>>>(vol->keys, n_all, d_table_keys, d_table_counts, (unsigned)(cap - 1), d_touch_kept);
+    bs_free(ctx, d_table_keys); bs_free(ctx, d_table_slots); bs_free(ctx, d_table_counts); bs_free(ctx, d_offsets); bs_free(ctx, d_flags); bs_free(ctx, d_neval);
     // 5. signs + masks
-    s = bs_sign_impl(ctx, d_tris, n_tris, vol);
+    s = bs_sign_impl(ctx, d_tris, n_tris, vol, d_touch_kept);
+    bs_free(ctx, d_touch_kept);
     if (s != BS_OK) { bs_volume_free(vol); return s; }
     BS_CUDA(ctx, cudaGetLastError());
     bs_marks_end(ctx);

@@ -527,75 +527,107 @@ __device__ __forceinline__ unsigned demorton9(unsigned p) {
     return (x << 6) | (y << 3) | z;
 }
 
-// One CTA per brick: the active list is built once, then the warps take 32*VPL-voxel chunks round robin, so
-// a heavy brick (e.g. at the pole of a UV sphere, where hundreds of sliver triangles are "near") is spread over
-// all warps of its CTA instead of serialising one warp.
+// Active masks + the list of work items for the sign kernel: one item = 32*VPL Morton-adjacent active voxels of one brick.
+__global__ void k_masks(const float* __restrict__ values, size_t n_bricks, unsigned long long* masks, unsigned* n_chunks, int per_chunk) {
+    const unsigned lane = threadIdx.x & 31;
+    const size_t b = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
+    if (b >= n_bricks) return;
+    const float* bv = values + b * 512;
+    unsigned lo = 0, hi = 0, cnt = 0;
+    for (int r = 0; r < 16; ++r) {
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, __float_as_uint(bv[r * 32 + lane]) != BS_UDF_SENTINEL_BITS);
+        if ((int)lane == (r >> 1)) { if (r & 1) hi = bal; else lo = bal; }
+        cnt += __popc(bal);
+    }
+    if (lane < 8) masks[b * 8 + lane] = (unsigned long long)lo | ((unsigned long long)hi << 32);
+    if (lane == 0) n_chunks[b] = (cnt + per_chunk - 1) / per_chunk;
+}
+// items are laid out in `order` (bricks under the densest triangles first: their items run longest, so they must not
+// start last); brick_off[b] = first item of brick b
+__global__ void k_order_chunks(const unsigned* __restrict__ order, const unsigned* __restrict__ n_chunks, size_t n_bricks, unsigned* ordered) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < n_bricks) ordered[i] = n_chunks[order ? order[i] : i];
+    if (i == n_bricks) ordered[i] = 0;
+}
+__global__ void k_items(const unsigned* __restrict__ order, const unsigned* __restrict__ off, size_t n_bricks, unsigned* item_brick, unsigned* brick_off) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n_bricks) return;
+    const unsigned b = order ? order[i] : (unsigned)i;
+    brick_off[b] = off[i];
+    for (unsigned k = off[i]; k < off[i + 1]; ++k) item_brick[k] = b;
+}
+__global__ void k_touch_keys(const unsigned long long* __restrict__ touches, size_t n, unsigned* key, unsigned* idx) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long t = touches[i];
+    // only bricks far above the usual few hundred touches move to the front (in buckets); the rest keep their spatial
+    // (visit) order, which is what the caches like
+    const unsigned long long k = t >> 11;
+    key[i] = k > 0xFFFFFFFFull ? 0xFFFFFFFFu : (unsigned)k; idx[i] = (unsigned)i;
+}
+
+// One WARP per work item (32*VPL Morton-adjacent active voxels of one brick): a heavy brick (e.g. at the pole of a UV
+// sphere, where thousands of sliver triangles are "near") is spread over many warps / SMs instead of serialising a CTA.
 template <bool COUNT, int VPL>
 #ifndef BS_SIGN_MINB
 #define BS_SIGN_MINB 8
 #endif
-__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, BS_SIGN_MINB) k_sign(Tree T, float* values, unsigned long long* masks, size_t n_bricks,
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, BS_SIGN_MINB) k_sign(Tree T, float* values, const unsigned long long* __restrict__ masks, unsigned n_items,
+                                                               const unsigned* __restrict__ item_brick, const unsigned* __restrict__ chunk_off,
                                                                const unsigned long long* __restrict__ keys, float vs, const BrickOut* __restrict__ brick_out, unsigned long long* counters) {
     __shared__ unsigned s_stack[WARPS_PER_BLOCK][STACK * (1 + VPL)];
-    __shared__ unsigned short s_list[512];
-    __shared__ unsigned s_cnt[17];
-    __shared__ float s_far[27];
-    __shared__ unsigned s_roots[MAX_ROOTS];
-    __shared__ int s_nroots;
+    __shared__ unsigned short s_list[WARPS_PER_BLOCK][32 * VPL];
+    __shared__ float s_far[WARPS_PER_BLOCK][27];
+    __shared__ unsigned s_roots[WARPS_PER_BLOCK][MAX_ROOTS];
     const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const size_t b = blockIdx.x;
+    const unsigned item = blockIdx.x * WARPS_PER_BLOCK + w;
+    if (item >= n_items) return;
+    const size_t b = item_brick[item];
+    const unsigned chunk = item - chunk_off[b];
     float* bv = values + b * 512;
     int bx, by, bz; bs_key_brick(keys[b], bx, by, bz);
+    int n_roots;
     {   // result of the brick-level pass: hoisted far field at 27 samples + sub-tree roots
         const BrickOut* bo = brick_out + b;
         const unsigned nr = bo->n_roots;
-        if (threadIdx.x < 27) s_far[threadIdx.x] = bo->far[threadIdx.x];
-        if (nr == 0xFFFFFFFFu) { if (threadIdx.x == 0) { s_roots[0] = T.root; s_nroots = 1; } }
+        if (lane < 27) s_far[w][lane] = bo->far[lane];
+        if (nr == 0xFFFFFFFFu) { if (lane == 0) s_roots[w][0] = T.root; n_roots = 1; }
         else {
-            for (unsigned i = threadIdx.x; i < nr; i += blockDim.x) {
+            for (unsigned i = lane; i < nr; i += 32) {
                 const unsigned rid = bo->roots[i];
-                s_roots[i] = rid;
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(T.hdr + rid));   // every warp visits every root first
+                s_roots[w][i] = rid;
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(T.hdr + rid));
                 asm volatile("prefetch.global.L1 [%0];" ::"l"(T.coef + 3 * (size_t)rid));
                 asm volatile("prefetch.global.L1 [%0];" ::"l"(T.coef + 3 * (size_t)rid + 2));
             }
-            if (threadIdx.x == 0) s_nroots = (int)nr;
+            n_roots = (int)nr;
         }
     }
-    // mask words (leaf offset order): warp w covers rounds 4w..4w+3 = mask words 2w, 2w+1
+    // this item's voxels: entries [chunk*32*VPL, +32*VPL) of the brick's active voxels in Morton order
+    unsigned cnt = 0;  // active voxels of the brick seen so far
+    const unsigned first = chunk * 32 * VPL;
+    const unsigned long long* mk = masks + b * 8;
+    for (int r = 0; r < 16; ++r) {
+        const unsigned off = demorton9(r * 32 + lane);
+        const bool act = (mk[off >> 6] >> (off & 63)) & 1;
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, act);
+        const unsigned p = cnt + __popc(bal & ((1u << lane) - 1));
+        if (act && p >= first && p < first + 32 * VPL) s_list[w][p - first] = (unsigned short)off;
+        cnt += __popc(bal);
+    }
+    __syncwarp();
+    const unsigned n_here = min(cnt - first, (unsigned)(32 * VPL));
     {
-        unsigned bal[4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) bal[r] = __ballot_sync(0xFFFFFFFFu, __float_as_uint(bv[(4 * w + r) * 32 + lane]) != BS_UDF_SENTINEL_BITS);
-        if (lane < 2) masks[b * 8 + 2 * w + lane] = (unsigned long long)bal[2 * lane] | ((unsigned long long)bal[2 * lane + 1] << 32);
-    }
-    // active voxels in Morton order, so 32 consecutive entries are a compact cluster: counts, scan, scatter
-    unsigned balm[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        balm[r] = __ballot_sync(0xFFFFFFFFu, __float_as_uint(bv[demorton9((4 * w + r) * 32 + lane)]) != BS_UDF_SENTINEL_BITS);
-        if (lane == 0) s_cnt[4 * w + r] = __popc(balm[r]);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) { unsigned acc = 0; for (int r = 0; r < 16; ++r) { const unsigned c = s_cnt[r]; s_cnt[r] = acc; acc += c; } s_cnt[16] = acc; }
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-        if ((balm[r] >> lane) & 1) s_list[s_cnt[4 * w + r] + __popc(balm[r] & ((1u << lane) - 1))] = (unsigned short)demorton9((4 * w + r) * 32 + lane);
-    __syncthreads();
-    const unsigned cnt = s_cnt[16];
-    const int n_roots = s_nroots;
-    for (unsigned base = w * 32 * VPL; base < cnt; base += WARPS_PER_BLOCK * 32 * VPL) {
         unsigned c3[4] = {0, 0, 0, 0};
         WarpWinding<COUNT, VPL> W{T};
         W.stack = s_stack[w]; W.cnt = c3; W.lane = lane;
         unsigned off[VPL], valid_m[VPL]; bool valid[VPL];
 #pragma unroll
         for (int v = 0; v < VPL; ++v) {
-            const unsigned i = base + v * 32 + lane;
-            valid[v] = i < cnt;
+            const unsigned i = v * 32 + lane;
+            valid[v] = i < n_here;
             valid_m[v] = __ballot_sync(0xFFFFFFFFu, valid[v]);
-            off[v] = s_list[valid[v] ? i : cnt - 1];
+            off[v] = s_list[w][valid[v] ? i : n_here - 1];
             W.qx[v] = __fmul_rn((float)((bx << 3) + (int)(off[v] >> 6)), vs);
             W.qy[v] = __fmul_rn((float)((by << 3) + (int)((off[v] >> 3) & 7)), vs);
             W.qz[v] = __fmul_rn((float)((bz << 3) + (int)(off[v] & 7)), vs);
@@ -608,15 +640,15 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, BS_SIGN_MINB) k_sign(Tre
             }
             float acc = 0.f;
 #pragma unroll
-            for (int i = 0; i < 3; ++i)
+            for (int i2 = 0; i2 < 3; ++i2)
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
-                    const float wij = L[0][i] * L[1][j];
-                    acc = fmaf(wij, fmaf(L[2][0], s_far[i * 9 + j * 3], fmaf(L[2][1], s_far[i * 9 + j * 3 + 1], L[2][2] * s_far[i * 9 + j * 3 + 2])), acc);
+                    const float wij = L[0][i2] * L[1][j];
+                    acc = fmaf(wij, fmaf(L[2][0], s_far[w][i2 * 9 + j * 3], fmaf(L[2][1], s_far[w][i2 * 9 + j * 3 + 1], L[2][2] * s_far[w][i2 * 9 + j * 3 + 2])), acc);
                 }
             W.wn[v] = acc;
         }
-        W.run(valid_m, s_roots, n_roots);
+        W.run(valid_m, s_roots[w], n_roots);
 #pragma unroll
         for (int v = 0; v < VPL; ++v) {
             if (!valid[v]) continue;
@@ -634,7 +666,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, BS_SIGN_MINB) k_sign(Tre
 #define BS_VPL 1
 #endif
 
-bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_volume* vol) {
+bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_volume* vol, const unsigned long long* d_touches) {
     cudaStream_t st = ctx->stream;
     if (n_tris >= (1ull << 30)) return bs_fail(ctx, BS_ERR_RANGE, "too many triangles");
     // Morton order
@@ -678,27 +710,52 @@ bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_v
     T.hdr = d_hdr; T.coef = d_coef; T.rec = d_rec; T.tris = d_sorted; T.n_leaves = (unsigned)n; T.root = root_id;
     bs_mark(ctx, "bvh_build_ms");
     if (vol->n_bricks) {
-        const size_t blocks = vol->n_bricks;  // one CTA per brick: the block scheduler balances the load
+        const size_t nb = vol->n_bricks;
+        unsigned *d_nchunks = nullptr, *d_ordered = nullptr, *d_off = nullptr, *d_chunk_off = nullptr, *d_item_brick = nullptr, *d_order = nullptr; unsigned n_items = 0;
+        BS_TRY(bs_alloc(ctx, &d_nchunks, nb)); BS_TRY(bs_alloc(ctx, &d_ordered, nb + 1)); BS_TRY(bs_alloc(ctx, &d_off, nb + 1)); BS_TRY(bs_alloc(ctx, &d_chunk_off, nb));
+        k_masks<<<bs_blocks(nb * 32, 256), 256, 0, st>>>(vol->values, nb, vol->masks, d_nchunks, 32 * BS_VPL);
+        if (d_touches) {  // heaviest bricks first
+            unsigned *d_k = nullptr, *d_k2 = nullptr, *d_i = nullptr;
+            BS_TRY(bs_alloc(ctx, &d_k, nb)); BS_TRY(bs_alloc(ctx, &d_k2, nb)); BS_TRY(bs_alloc(ctx, &d_i, nb)); BS_TRY(bs_alloc(ctx, &d_order, nb));
+            k_touch_keys<<<bs_blocks(nb, 256), 256, 0, st>>>(d_touches, nb, d_k, d_i);
+            tmp_bytes = 0;
+            cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, d_k, d_k2, d_i, d_order, nb, 0, 32, st);
+            BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp_bytes));
+            cub::DeviceRadixSort::SortPairsDescending(d_tmp, tmp_bytes, d_k, d_k2, d_i, d_order, nb, 0, 32, st);
+            bs_free(ctx, d_tmp); bs_free(ctx, d_k); bs_free(ctx, d_k2); bs_free(ctx, d_i);
+        }
+        k_order_chunks<<<bs_blocks(nb + 1, 256), 256, 0, st>>>(d_order, d_nchunks, nb, d_ordered);
+        tmp_bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_ordered, d_off, nb + 1, st);
+        BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp_bytes));
+        cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_ordered, d_off, nb + 1, st);
+        BS_CUDA(ctx, cudaMemcpyAsync(&n_items, d_off + nb, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        BS_CUDA(ctx, cudaStreamSynchronize(st));
+        bs_free(ctx, d_tmp); bs_free(ctx, d_nchunks); bs_free(ctx, d_ordered);
+        BS_TRY(bs_alloc(ctx, &d_item_brick, n_items));
+        k_items<<<bs_blocks(nb, 256), 256, 0, st>>>(d_order, d_off, nb, d_item_brick, d_chunk_off);
+        bs_free(ctx, d_off); bs_free(ctx, d_order);
+        const size_t blocks = (n_items + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
         BrickOut* d_bo = nullptr;
         float kappa = KAPPA_DEFAULT;
         if (const char* e = getenv("BSHARK_KAPPA")) kappa = (float)atof(e);  // tuning knob for experiments only
-        BS_TRY(bs_alloc(ctx, &d_bo, vol->n_bricks));
+        BS_TRY(bs_alloc(ctx, &d_bo, nb));
         if (ctx->count_work) {
             unsigned long long* d_cnt = nullptr; unsigned long long h_cnt[9];
             BS_TRY(bs_alloc(ctx, &d_cnt, 9));
             BS_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, 72, st));
-            k_brick_pass<true><<<bs_blocks(vol->n_bricks, BP_WARPS), 32 * BP_WARPS, 0, st>>>(T, vol->keys, vol->n_bricks, vol->voxel_size, kappa, d_bo, d_cnt);
-            k_sign<true, BS_VPL><<<(unsigned)blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(T, vol->values, vol->masks, vol->n_bricks, vol->keys, vol->voxel_size, d_bo, d_cnt);
+            k_brick_pass<true><<<bs_blocks(nb, BP_WARPS), 32 * BP_WARPS, 0, st>>>(T, vol->keys, nb, vol->voxel_size, kappa, d_bo, d_cnt);
+            if (n_items) k_sign<true, BS_VPL><<<(unsigned)blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(T, vol->values, vol->masks, n_items, d_item_brick, d_chunk_off, vol->keys, vol->voxel_size, d_bo, d_cnt);
             BS_CUDA(ctx, cudaMemcpyAsync(h_cnt, d_cnt, 72, cudaMemcpyDeviceToHost, st));
             BS_CUDA(ctx, cudaStreamSynchronize(st));
             bs_free(ctx, d_cnt);
-            ctx->fwn_counts[0] = (double)h_cnt[0]; ctx->fwn_counts[1] = (double)h_cnt[1]; ctx->fwn_counts[2] = (double)h_cnt[2]; ctx->fwn_counts[3] = (double)h_cnt[3]; ctx->fwn_counts[4] = (double)h_cnt[4]; ctx->fwn_counts[5] = (double)h_cnt[5]; ctx->fwn_counts[6] = (double)h_cnt[6]; ctx->fwn_counts[7] = (double)h_cnt[7]; ctx->fwn_counts[8] = (double)h_cnt[8];
+            for (int i = 0; i < 9; ++i) ctx->fwn_counts[i] = (double)h_cnt[i];
         } else {
-            k_brick_pass<false><<<bs_blocks(vol->n_bricks, BP_WARPS), 32 * BP_WARPS, 0, st>>>(T, vol->keys, vol->n_bricks, vol->voxel_size, kappa, d_bo, nullptr);
+            k_brick_pass<false><<<bs_blocks(nb, BP_WARPS), 32 * BP_WARPS, 0, st>>>(T, vol->keys, nb, vol->voxel_size, kappa, d_bo, nullptr);
             bs_mark(ctx, "sign_brick_pass_ms");
-            k_sign<false, BS_VPL><<<(unsigned)blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(T, vol->values, vol->masks, vol->n_bricks, vol->keys, vol->voxel_size, d_bo, nullptr);
+            if (n_items) k_sign<false, BS_VPL><<<(unsigned)blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(T, vol->values, vol->masks, n_items, d_item_brick, d_chunk_off, vol->keys, vol->voxel_size, d_bo, nullptr);
         }
-        bs_free(ctx, d_bo);
+        bs_free(ctx, d_bo); bs_free(ctx, d_chunk_off); bs_free(ctx, d_item_brick);
     }
     bs_mark(ctx, "sign_ms");
     bs_free(ctx, d_sorted); bs_free(ctx, d_hdr); bs_free(ctx, d_coef); bs_free(ctx, d_rec);

@@ -250,7 +250,8 @@ def main():
         if gather_buf["t"] is None or gather_buf["t"].numel() < n_floats:
             gather_buf["t"] = torch.empty(int(n_floats * 1.2) + 16, dtype=torch.float32, device="cuda")
         ctx.check(L.bs_context_copy_out_verts_device(ctx._h, C.c_void_p(gather_buf["t"].data_ptr()), n_floats))
-        full, _ = all_gather_varlen(gather_buf["t"][:n_floats])
+        full, _ = all_gather_varlen(gather_buf["t"][:n_floats], out=gather_buf.get("out"))
+        gather_buf["out"] = full
         return full
 
     def step_device():
@@ -370,6 +371,13 @@ def main():
         e2e_ms = e2e_s * 1e3
         n_active, n_verts = n_active_local, float(n_verts_local)
 
+    per_rank = None
+    if world > 1:
+        per_rank = [None] * world
+        mine = dict(conv_ms)
+        mine.update({k: v / args.steps for k, v in stage_ms.items()})
+        mine.update({k: v for k, v in work.items() if k.startswith("fwn_") or k.startswith("n_")})
+        dist.all_gather_object(per_rank, mine)
     if rank == 0:
         ms_per_step = ms_total / args.steps
         value = n_active / (ms_per_step * 1e-3)
@@ -410,7 +418,7 @@ def main():
                        "band_width": 0, "l2": "inputs larger than L2 (triangles %.0f MB, bricks %.0f MB)" % (tris.nbytes / 1e6, work.get("n_bricks", 0) * 2112 / 1e6),
                        "parallelism": "brick slabs x%d, mesh replicated" % world},
             "remesh_ms": ms_per_step, "tris_per_s": (n_verts / 3.0) / (ms_per_step * 1e-3), "n_active_voxels": n_active, "n_out_triangles": n_verts / 3.0,
-            "stage_ms": stage_all, "work": work,
+            "stage_ms": stage_all, "stage_ms_per_rank": per_rank, "work": work,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": int(tris.nbytes), "d2h_bytes_per_step": int(n_verts_local * 12)},
             "gpu_launches": None, "clocks": clocks,
             "roofline": dominant, "rooflines": rl,
