@@ -27,7 +27,7 @@ EXPORTS = [
     "bs_volume_clone", "bs_volume_free", "bs_volume_voxel_size",
     "bs_volume_union", "bs_volume_subtract", "bs_volume_intersect", "bs_volume_offset",
     "bs_mesh_mc", "bs_mesh_dc", "bs_mesh_mc_device", "bs_mesh_dc_device", "bs_buffer_free",
-    "bs_volume_download", "bs_volume_counts", "bs_context_last_stats", "bs_context_copy_out_verts", "bs_context_copy_out_verts_device", "bs_context_set_flag",
+    "bs_volume_download", "bs_volume_counts", "bs_context_last_stats", "bs_context_copy_out_verts", "bs_context_copy_out_verts_device", "bs_context_set_flag", "bs_kernel_launch_count",
 ]
 
 
@@ -91,6 +91,7 @@ def load_library(path=None):
         "bs_context_copy_out_verts": (C.c_int, [vp, vp, sz]),
         "bs_context_copy_out_verts_device": (C.c_int, [vp, vp, sz]),
         "bs_context_set_flag": (C.c_int, [vp, C.c_int, C.c_int]),
+        "bs_kernel_launch_count": (C.c_ulonglong, []),
     }
     for name, (res, args) in sigs.items():
         f = getattr(L, name)

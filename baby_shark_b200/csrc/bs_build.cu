@@ -134,13 +134,13 @@ bs_status bs_from_voxels_impl(bs_context* ctx, const int32_t* d_ijk, const float
     BS_TRY(bs_alloc(ctx, &d_comp, m)); BS_TRY(bs_alloc(ctx, &d_comp2, m)); BS_TRY(bs_alloc(ctx, &d_idx, m)); BS_TRY(bs_alloc(ctx, &d_idx2, m));
     BS_TRY(bs_alloc(ctx, &d_head, m)); BS_TRY(bs_alloc(ctx, &d_rank, m)); BS_TRY(bs_alloc(ctx, &d_flags, 1));
     BS_CUDA(ctx, cudaMemsetAsync(d_flags, 0, sizeof(int), st));
-    k_voxel_keys<<<bs_blocks(m, TPB), TPB, 0, st>>>(d_ijk, m, d_comp, d_idx, d_flags);
+    bs_count_launch(), k_voxel_keys<<<bs_blocks(m, TPB), TPB, 0, st>>>(d_ijk, m, d_comp, d_idx, d_flags);
     void* d_tmp = nullptr; size_t tmp_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_comp, d_comp2, d_idx, d_idx2, m, 0, 63, st);
     BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp_bytes));
     cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_comp, d_comp2, d_idx, d_idx2, m, 0, 63, st);
     bs_free(ctx, d_tmp);
-    k_brick_heads<<<bs_blocks(m, TPB), TPB, 0, st>>>(d_comp2, m, d_head);
+    bs_count_launch(), k_brick_heads<<<bs_blocks(m, TPB), TPB, 0, st>>>(d_comp2, m, d_head);
     tmp_bytes = 0;
     cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, d_head, d_rank, m, st);
     BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp_bytes));
@@ -160,7 +160,7 @@ bs_status bs_from_voxels_impl(bs_context* ctx, const int32_t* d_ijk, const float
     if (s == BS_OK) {
         cudaMemsetAsync(v->values, 0, (size_t)n_bricks * 512 * sizeof(float), st);
         cudaMemsetAsync(v->masks, 0, (size_t)n_bricks * 8 * sizeof(unsigned long long), st);
-        k_scatter_voxels<<<bs_blocks(m, TPB), TPB, 0, st>>>(d_comp2, d_idx2, d_rank, d_values, m, v->keys, v->values, v->masks);
+        bs_count_launch(), k_scatter_voxels<<<bs_blocks(m, TPB), TPB, 0, st>>>(d_comp2, d_idx2, d_rank, d_values, m, v->keys, v->values, v->masks);
         if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) s = bs_fail(ctx, BS_ERR_CUDA, "from_voxels kernels failed");
     }
     bs_free(ctx, d_comp); bs_free(ctx, d_comp2); bs_free(ctx, d_idx); bs_free(ctx, d_idx2); bs_free(ctx, d_head); bs_free(ctx, d_rank); bs_free(ctx, d_flags);
@@ -201,8 +201,8 @@ bs_status bs_builder_impl(bs_context* ctx, int kind, float voxel_size, const flo
     if (n_dense > (1ull << 31) - 1) return bs_fail(ctx, BS_ERR_RANGE, "primitive box too large");
     unsigned char* d_keep = nullptr; unsigned long long *d_keys = nullptr, *d_sel = nullptr; size_t* d_nsel = nullptr;
     BS_TRY(bs_alloc(ctx, &d_keep, n_dense)); BS_TRY(bs_alloc(ctx, &d_keys, n_dense)); BS_TRY(bs_alloc(ctx, &d_sel, n_dense)); BS_TRY(bs_alloc(ctx, &d_nsel, 1));
-    k_prim_flags<<<(unsigned)n_dense, 512, 0, st>>>(P, d_keep);
-    k_prim_keys<<<bs_blocks(n_dense, TPB), TPB, 0, st>>>(P, d_keep, n_dense, d_keys);
+    bs_count_launch(), k_prim_flags<<<(unsigned)n_dense, 512, 0, st>>>(P, d_keep);
+    bs_count_launch(), k_prim_keys<<<bs_blocks(n_dense, TPB), TPB, 0, st>>>(P, d_keep, n_dense, d_keys);
     void* d_tmp = nullptr; size_t tmp_bytes = 0;
     cub::DeviceSelect::If(nullptr, tmp_bytes, d_keys, d_sel, d_nsel, n_dense, NotInvalid(), st);
     BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp_bytes));
@@ -219,7 +219,7 @@ bs_status bs_builder_impl(bs_context* ctx, int kind, float voxel_size, const flo
         s = bs_alloc(ctx, (char**)&d_tmp, tmp_bytes);
         if (s == BS_OK) {
             cub::DeviceRadixSort::SortKeys(d_tmp, tmp_bytes, d_sel, v->keys, n, 0, 54, st);
-            k_prim_fill<<<(unsigned)n, 512, 0, st>>>(P, v->keys, v->values, v->masks);
+            bs_count_launch(), k_prim_fill<<<(unsigned)n, 512, 0, st>>>(P, v->keys, v->values, v->masks);
             bs_free(ctx, d_tmp);
             if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) s = bs_fail(ctx, BS_ERR_CUDA, "builder kernels failed");
         }

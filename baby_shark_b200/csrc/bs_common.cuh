@@ -70,6 +70,11 @@ __device__ __forceinline__ f3 xcross(f3 a, f3 b) {
 // ---- host-side objects --------------------------------------------------------------------------------
 struct bs_stat { const char* name; double value; };
 
+// process-wide count of this library's own kernel launches (CUB plumbing not included); bench.py reports the
+// difference across its timed region as "gpu_launches"
+extern unsigned long long g_bs_launches;
+static inline void bs_count_launch() { ++g_bs_launches; }
+
 struct bs_context {
     int device = 0;
     int sm_count = 0;

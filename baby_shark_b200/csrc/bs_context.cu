@@ -62,6 +62,8 @@ template <class T> static bs_status to_host(bs_context* c, T** dst, const T* src
     return BS_OK;
 }
 
+unsigned long long g_bs_launches = 0;
+
 extern "C" {
 
 bs_status bs_context_create(int device, bs_context** out) {
@@ -99,6 +101,7 @@ void bs_context_destroy(bs_context* ctx) {
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
+unsigned long long bs_kernel_launch_count(void) { return g_bs_launches; }
 const char* bs_last_error(const bs_context* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 int bs_context_device(const bs_context* ctx) { return ctx ? ctx->device : -1; }
 void* bs_context_stream(const bs_context* ctx) { return ctx ? (void*)ctx->stream : nullptr; }

@@ -16,6 +16,7 @@
 #include "bs_common.cuh"
 #include <cub/cub.cuh>
 #include <cfloat>
+#include <climits>
 #include <cmath>
 
 namespace {
@@ -33,6 +34,7 @@ struct ConvertParams {
     float* values;
     int* flags;  // [0] hash overflow, [1] index range error
     unsigned long long* n_eval;  // sum of box volumes = point-triangle evaluations (roofline work counter)
+    int use_clip, clip_mn[3], clip_mx[3];  // sharded runs: voxel bounding box of the bricks this rank keeps
 };
 
 __device__ __forceinline__ unsigned long long hash64(unsigned long long k) {
@@ -237,8 +239,21 @@ __global__ void __launch_bounds__(TPB) k_eval(ConvertParams P) {
     bool ok = false;
     if (cur.valid) {
         const float* p = P.tris + 9 * cur.tri;
-        make_subtri(ld3(p), ld3(p + 3), ld3(p + 6), P.vs, cur.local, A, B, C);
-        ok = subtri_box(A, B, C, P.inv_vs, P.band, mn, mx);
+        const f3 p1 = ld3(p), p2 = ld3(p + 3), p3 = ld3(p + 6);
+        bool hit = true;
+        if (P.use_clip) {  // the whole input triangle (plus band and rounding slack) misses this rank's bricks: skip the subdivision
+            const float lo[3] = {fminf(p1.x, fminf(p2.x, p3.x)), fminf(p1.y, fminf(p2.y, p3.y)), fminf(p1.z, fminf(p2.z, p3.z))};
+            const float hi[3] = {fmaxf(p1.x, fmaxf(p2.x, p3.x)), fmaxf(p1.y, fmaxf(p2.y, p3.y)), fmaxf(p1.z, fmaxf(p2.z, p3.z))};
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const float a = floorf(lo[d] * P.inv_vs) - (float)(P.band + 3), b = ceilf(hi[d] * P.inv_vs) + (float)(P.band + 3);
+                if (b < (float)P.clip_mn[d] || a > (float)P.clip_mx[d]) hit = false;
+            }
+        }
+        if (hit) {
+            make_subtri(p1, p2, p3, P.vs, cur.local, A, B, C);
+            ok = subtri_box(A, B, C, P.inv_vs, P.band, mn, mx);
+        }
     }
     const int dx = ok ? mx[0] - mn[0] + 1 : 0, dy = ok ? mx[1] - mn[1] + 1 : 0, dz = ok ? mx[2] - mn[2] + 1 : 0;
     const bool wide = dx > 9 || dy > 9 || dz > 9;
@@ -370,6 +385,15 @@ __global__ void k_slab_bounds(const unsigned long long* __restrict__ C /*inclusi
     while (lo < hi) { const size_t mid = (lo + hi) >> 1; if (C[mid] + (unsigned long long)(mid + 1) * mean < target) lo = mid + 1; else hi = mid; }
     bounds[r] = lo;
 }
+__global__ void k_key_bounds(const unsigned long long* __restrict__ keys, size_t n, int* bounds /*min xyz, max xyz in voxels*/) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN};
+    if (i < n) { int b[3]; bs_key_brick(keys[i], b[0], b[1], b[2]); for (int d = 0; d < 3; ++d) { lo[d] = b[d] << 3; hi[d] = (b[d] << 3) + 7; } }
+    for (int d = 0; d < 3; ++d) {
+        for (int o = 16; o; o >>= 1) { lo[d] = min(lo[d], __shfl_xor_sync(0xFFFFFFFFu, lo[d], o)); hi[d] = max(hi[d], __shfl_xor_sync(0xFFFFFFFFu, hi[d], o)); }
+        if ((threadIdx.x & 31) == 0) { atomicMin(bounds + d, lo[d]); atomicMax(bounds + 3 + d, hi[d]); }
+    }
+}
 __global__ void k_owned(const unsigned long long* __restrict__ all_keys, size_t n_all, size_t lo, size_t hi, const unsigned long long* __restrict__ kept, size_t n_kept, unsigned char* owned) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= n_kept) return;
@@ -405,7 +429,7 @@ extern "C" bs_status bs_volume_counts(const bs_volume* v, size_t* n_bricks, size
     unsigned long long* d = nullptr; unsigned long long h[2] = {0, 0};
     BS_TRY(bs_alloc(ctx, &d, 2));
     BS_CUDA(ctx, cudaMemsetAsync(d, 0, 16, ctx->stream));
-    if (v->n_bricks) k_counts<<<bs_blocks(v->n_bricks * 8, TPB), TPB, 0, ctx->stream>>>(v->values, v->masks, v->n_bricks, d);
+    if (v->n_bricks) bs_count_launch(), k_counts<<<bs_blocks(v->n_bricks * 8, TPB), TPB, 0, ctx->stream>>>(v->values, v->masks, v->n_bricks, d);
     BS_CUDA(ctx, cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, ctx->stream));
     BS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     bs_free(ctx, d);
@@ -428,7 +452,7 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
     BS_CUDA(ctx, cudaMemsetAsync(d_area, 0, sizeof(double), st));
     BS_CUDA(ctx, cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), st));
     BS_CUDA(ctx, cudaMemsetAsync(d_counts + n_tris, 0, sizeof(unsigned long long), st));
-    k_tri_counts<<<bs_blocks(n_tris, TPB), TPB, 0, st>>>(d_tris, n_tris, voxel_size, d_counts, d_area);
+    bs_count_launch(), k_tri_counts<<<bs_blocks(n_tris, TPB), TPB, 0, st>>>(d_tris, n_tris, voxel_size, d_counts, d_area);
     void* d_tmp = nullptr; size_t tmp_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_counts, d_offsets, n_tris + 1, st);
     BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp_bytes));
@@ -444,7 +468,7 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
 
     ConvertParams P;
     P.tris = d_tris; P.n_tris = n_tris; P.offsets = d_offsets; P.total = total;
-    P.vs = voxel_size; P.inv_vs = 1.0f / voxel_size; P.band = (int)band; P.flags = d_flags; P.values = nullptr; P.n_eval = d_neval; P.table_counts = nullptr;
+    P.vs = voxel_size; P.inv_vs = 1.0f / voxel_size; P.band = (int)band; P.flags = d_flags; P.values = nullptr; P.n_eval = d_neval; P.table_counts = nullptr; P.use_clip = 0;
 
     // 2. mark touched bricks in a hash set; sized from the surface area, doubled on overflow
     const double bw = (double)(2 * band + 1);
@@ -461,7 +485,7 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
         P.table_counts = d_table_counts;
         BS_CUDA(ctx, cudaMemsetAsync(d_neval, 0, sizeof(unsigned long long), st));
         P.table_keys = d_table_keys; P.table_slots = nullptr; P.table_mask = (unsigned)(cap - 1);
-        k_mark<<<grid, TPB, 0, st>>>(P);
+        bs_count_launch(), k_mark<<<grid, TPB, 0, st>>>(P);
         int flags[2];
         BS_CUDA(ctx, cudaMemcpyAsync(flags, d_flags, sizeof(flags), cudaMemcpyDeviceToHost, st));
         BS_CUDA(ctx, cudaMemcpyAsync(&n_eval, d_neval, sizeof(n_eval), cudaMemcpyDeviceToHost, st));
@@ -504,12 +528,12 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
         {
             unsigned long long *d_touch = nullptr, *d_C = nullptr, *d_bounds = nullptr; unsigned long long h_bounds[2];
             BS_TRY(bs_alloc(ctx, &d_touch, n_all)); BS_TRY(bs_alloc(ctx, &d_C, n_all)); BS_TRY(bs_alloc(ctx, &d_bounds, (size_t)world + 1));
-            k_brick_touches<<<bs_blocks(n_all, TPB), TPB, 0, st>>>(d_keys, n_all, d_table_keys, d_table_counts, (unsigned)(cap - 1), d_touch);
+            bs_count_launch(), k_brick_touches<<<bs_blocks(n_all, TPB), TPB, 0, st>>>(d_keys, n_all, d_table_keys, d_table_counts, (unsigned)(cap - 1), d_touch);
             tmp_bytes = 0;
             cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, d_touch, d_C, n_all, st);
             BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp_bytes));
             cub::DeviceScan::InclusiveSum(d_tmp, tmp_bytes, d_touch, d_C, n_all, st);
-            k_slab_bounds<<<1, 64, 0, st>>>(d_C, n_all, world, d_bounds);
+            bs_count_launch(), k_slab_bounds<<<1, 64, 0, st>>>(d_C, n_all, world, d_bounds);
             BS_CUDA(ctx, cudaMemcpyAsync(h_bounds, d_bounds + rank, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
             BS_CUDA(ctx, cudaStreamSynchronize(st));
             bs_free(ctx, d_tmp); bs_free(ctx, d_touch); bs_free(ctx, d_C); bs_free(ctx, d_bounds);
@@ -519,7 +543,7 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
         unsigned char* d_keep = nullptr; unsigned long long* d_kept = nullptr; size_t* d_nk = nullptr; size_t n_kept = 0;
         BS_TRY(bs_alloc(ctx, &d_keep, n_all)); BS_TRY(bs_alloc(ctx, &d_kept, n_all)); BS_TRY(bs_alloc(ctx, &d_nk, 1));
         BS_CUDA(ctx, cudaMemsetAsync(d_keep, 0, n_all, st));
-        if (hi > lo) k_mark_slab<<<bs_blocks((hi - lo) * 27, TPB), TPB, 0, st>>>(d_keys, n_all, lo, hi, d_keep);
+        if (hi > lo) bs_count_launch(), k_mark_slab<<<bs_blocks((hi - lo) * 27, TPB), TPB, 0, st>>>(d_keys, n_all, lo, hi, d_keep);
         tmp_bytes = 0;
         cub::DeviceSelect::Flagged(nullptr, tmp_bytes, d_keys, d_keep, d_kept, d_nk, n_all, st);
         BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp_bytes));
@@ -531,7 +555,7 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
         if (s == BS_OK) s = bs_alloc(ctx, &vol->owned, n_kept);
         if (s != BS_OK) { bs_volume_free(vol); return s; }
         BS_CUDA(ctx, cudaMemcpyAsync(vol->keys, d_kept, n_kept * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
-        if (n_kept) k_owned<<<bs_blocks(n_kept, TPB), TPB, 0, st>>>(d_keys, n_all, lo, hi, vol->keys, n_kept, vol->owned);
+        if (n_kept) bs_count_launch(), k_owned<<<bs_blocks(n_kept, TPB), TPB, 0, st>>>(d_keys, n_all, lo, hi, vol->keys, n_kept, vol->owned);
         bs_free(ctx, d_kept); bs_free(ctx, d_keys);
         n_all = n_kept;
         vol->n_owned = hi - lo;
@@ -543,17 +567,29 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
     }
     BS_TRY(bs_alloc(ctx, &d_table_slots, cap));
     BS_CUDA(ctx, cudaMemsetAsync(d_table_slots, 0xFF, cap * sizeof(unsigned), st));
-    k_fill_slots<<<bs_blocks(n_all, TPB), TPB, 0, st>>>((const unsigned long long*)vol->keys, n_all, d_table_keys, d_table_slots, (unsigned)(cap - 1));
+    bs_count_launch(), k_fill_slots<<<bs_blocks(n_all, TPB), TPB, 0, st>>>((const unsigned long long*)vol->keys, n_all, d_table_keys, d_table_slots, (unsigned)(cap - 1));
     BS_CUDA(ctx, cudaMemsetAsync(vol->values, 0x7F, n_all * 512 * sizeof(float), st));
     bs_mark(ctx, "sort_bricks_ms");
     // 4. distances
     P.table_slots = d_table_slots; P.values = vol->values;
-    k_eval<<<grid, TPB, 0, st>>>(P);
+    P.use_clip = 0;
+    if (world > 1 && n_all) {
+        int* d_kb = nullptr; int h_kb[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
+        BS_TRY(bs_alloc(ctx, &d_kb, 6));
+        BS_CUDA(ctx, cudaMemcpyAsync(d_kb, h_kb, sizeof(h_kb), cudaMemcpyHostToDevice, st));
+        bs_count_launch(), k_key_bounds<<<bs_blocks(n_all, TPB), TPB, 0, st>>>(vol->keys, n_all, d_kb);
+        BS_CUDA(ctx, cudaMemcpyAsync(h_kb, d_kb, sizeof(h_kb), cudaMemcpyDeviceToHost, st));
+        BS_CUDA(ctx, cudaStreamSynchronize(st));
+        bs_free(ctx, d_kb);
+        P.use_clip = 1;
+        for (int d = 0; d < 3; ++d) { P.clip_mn[d] = h_kb[d]; P.clip_mx[d] = h_kb[3 + d]; }
+    }
+    bs_count_launch(), k_eval<<<grid, TPB, 0, st>>>(P);
     bs_mark(ctx, "udf_ms");
     // per-brick "touches" (sub-triangle boxes that hit the brick): the sign stage runs the densest bricks first
     unsigned long long* d_touch_kept = nullptr;
     BS_TRY(bs_alloc(ctx, &d_touch_kept, n_all));
-    if (n_all) k_brick_touches<<<bs_blocks(n_all, TPB), TPB, 0, st>>>(vol->keys, n_all, d_table_keys, d_table_counts, (unsigned)(cap - 1), d_touch_kept);
+    if (n_all) bs_count_launch(), k_brick_touches<<<bs_blocks(n_all, TPB), TPB, 0, st>>>(vol->keys, n_all, d_table_keys, d_table_counts, (unsigned)(cap - 1), d_touch_kept);
     bs_free(ctx, d_table_keys); bs_free(ctx, d_table_slots); bs_free(ctx, d_table_counts); bs_free(ctx, d_offsets); bs_free(ctx, d_flags); bs_free(ctx, d_neval);
     // 5. signs + masks
     s = bs_sign_impl(ctx, d_tris, n_tris, vol, d_touch_kept);

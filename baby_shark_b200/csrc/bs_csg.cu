@@ -158,7 +158,7 @@ bs_status build_dir(bs_context* ctx, const bs_volume* v, Dir& D) {
     u8 *d_first = nullptr, *d_last = nullptr;
     BS_TRY(bs_alloc(ctx, &d_first, n)); BS_TRY(bs_alloc(ctx, &d_last, n));
     if (n) {
-        k_brick_signs<<<(unsigned)n, 512, 0, st>>>(v->values, v->masks, d_first, d_last);
+        bs_count_launch(), k_brick_signs<<<(unsigned)n, 512, 0, st>>>(v->values, v->masks, d_first, d_last);
         BS_CUDA(ctx, cudaMemcpyAsync(D.bkeys.data(), v->keys, n * sizeof(u64), cudaMemcpyDeviceToHost, st));
         BS_CUDA(ctx, cudaMemcpyAsync(D.bfirst.data(), d_first, n, cudaMemcpyDeviceToHost, st));
         BS_CUDA(ctx, cudaMemcpyAsync(D.blast.data(), d_last, n, cudaMemcpyDeviceToHost, st));
@@ -342,7 +342,7 @@ bs_status bs_csg_impl(bs_volume* A, bs_volume* B, int op, bs_volume** out) {
     if (s == BS_OK) s = bs_alloc(ctx, &d_recs, recs.size());
     if (s == BS_OK && !recs.empty()) {
         cudaMemcpyAsync(d_recs, recs.data(), recs.size() * sizeof(OutBrick), cudaMemcpyHostToDevice, st);
-        k_csg_bricks<<<(unsigned)recs.size(), 512, 0, st>>>(d_recs, A->values, A->masks, B->values, B->masks, R->keys, R->values, R->masks);
+        bs_count_launch(), k_csg_bricks<<<(unsigned)recs.size(), 512, 0, st>>>(d_recs, A->values, A->masks, B->values, B->masks, R->keys, R->values, R->masks);
     }
     auto upload_tiles = [&](const std::vector<OutTile>& t, size_t& n, u64*& keys, float*& vals) -> bs_status {
         n = t.size();

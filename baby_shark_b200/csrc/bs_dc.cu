@@ -247,10 +247,10 @@ bs_status bs_dc_impl(const bs_volume* v, float voxel_size, const float** d_verts
     BS_TRY(bs_alloc(ctx, &d_cells, n * 512 * 3)); BS_TRY(bs_alloc(ctx, &d_valid, n * 8)); BS_TRY(bs_alloc(ctx, &d_flags, 1));
     BS_TRY(bs_alloc(ctx, &d_counts, n)); BS_TRY(bs_alloc(ctx, &d_wide, n + 1)); BS_TRY(bs_alloc(ctx, &d_off, n + 1));
     BS_CUDA(ctx, cudaMemsetAsync(d_flags, 0, sizeof(int), st));
-    k_dc_cells<<<(unsigned)n, 512, 0, st>>>(v->keys, v->values, v->masks, n, v->owned, d_cells, d_valid, d_flags);
+    bs_count_launch(), k_dc_cells<<<(unsigned)n, 512, 0, st>>>(v->keys, v->values, v->masks, n, v->owned, d_cells, d_valid, d_flags);
     bs_mark(ctx, "dc_cells_ms");
-    k_dc_quads<false><<<(unsigned)n, 512, 0, st>>>(v->keys, v->values, v->masks, n, v->owned, d_cells, d_valid, voxel_size, d_counts, nullptr, nullptr);
-    k_widen<<<bs_blocks(n + 1, 256), 256, 0, st>>>(d_counts, d_wide, n);
+    bs_count_launch(), k_dc_quads<false><<<(unsigned)n, 512, 0, st>>>(v->keys, v->values, v->masks, n, v->owned, d_cells, d_valid, voxel_size, d_counts, nullptr, nullptr);
+    bs_count_launch(), k_widen<<<bs_blocks(n + 1, 256), 256, 0, st>>>(d_counts, d_wide, n);
     void* d_tmp = nullptr; size_t tmp_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_wide, d_off, n + 1, st);
     BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp_bytes));
@@ -263,7 +263,7 @@ bs_status bs_dc_impl(const bs_volume* v, float voxel_size, const float** d_verts
     bs_status s = BS_OK;
     if (flag) s = bs_fail(ctx, BS_ERR_REFERENCE_PANICS, "dual contouring: a sign-change edge end point has no neighbour along some axis; the reference hits unreachable!() (dual_contouring.rs:340)");
     if (s == BS_OK) s = bs_ensure_out_verts(ctx, (size_t)n_tris * 9);
-    if (s == BS_OK && n_tris) k_dc_quads<true><<<(unsigned)n, 512, 0, st>>>(v->keys, v->values, v->masks, n, v->owned, d_cells, d_valid, voxel_size, nullptr, d_off, ctx->d_out_verts);
+    if (s == BS_OK && n_tris) bs_count_launch(), k_dc_quads<true><<<(unsigned)n, 512, 0, st>>>(v->keys, v->values, v->masks, n, v->owned, d_cells, d_valid, voxel_size, nullptr, d_off, ctx->d_out_verts);
     bs_mark(ctx, "dc_emit_ms");
     bs_free(ctx, d_tmp); bs_free(ctx, d_cells); bs_free(ctx, d_valid); bs_free(ctx, d_counts); bs_free(ctx, d_wide); bs_free(ctx, d_off); bs_free(ctx, d_flags);
     if (s != BS_OK) return s;

@@ -676,8 +676,8 @@ bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_v
     BS_CUDA(ctx, cudaMemcpyAsync(d_bounds, init, sizeof(init), cudaMemcpyHostToDevice, st));
     BS_TRY(bs_alloc(ctx, &d_codes, n_tris)); BS_TRY(bs_alloc(ctx, &d_codes2, n_tris));
     BS_TRY(bs_alloc(ctx, &d_ids, n_tris)); BS_TRY(bs_alloc(ctx, &d_ids2, n_tris));
-    k_centroid_bounds<<<(unsigned)std::min<size_t>(bs_blocks(n_tris, 256), (size_t)ctx->sm_count * 8), 256, 0, st>>>(d_tris, n_tris, d_bounds);
-    k_morton<<<bs_blocks(n_tris, 256), 256, 0, st>>>(d_tris, n_tris, d_bounds, d_codes, d_ids);
+    bs_count_launch(), k_centroid_bounds<<<(unsigned)std::min<size_t>(bs_blocks(n_tris, 256), (size_t)ctx->sm_count * 8), 256, 0, st>>>(d_tris, n_tris, d_bounds);
+    bs_count_launch(), k_morton<<<bs_blocks(n_tris, 256), 256, 0, st>>>(d_tris, n_tris, d_bounds, d_codes, d_ids);
     void* d_tmp = nullptr; size_t tmp_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_codes, d_codes2, d_ids, d_ids2, n_tris, 0, 63, st);
     BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp_bytes));
@@ -696,15 +696,15 @@ bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_v
     BS_TRY(bs_alloc(ctx, &d_raw, (size_t)n_nodes));
     BS_CUDA(ctx, cudaMemsetAsync(d_flags, 0, (size_t)n * sizeof(unsigned), st));
 #ifdef BS_TREE_BALANCED
-    if (n > 1) k_balanced<<<bs_blocks((size_t)n - 1, 256), 256, 0, st>>>(n, d_left, d_right, d_parent);
+    if (n > 1) bs_count_launch(), k_balanced<<<bs_blocks((size_t)n - 1, 256), 256, 0, st>>>(n, d_left, d_right, d_parent);
     const unsigned root_id = n > 1 ? (unsigned)((n >> 1) - 1) : 0u;
 #else
-    if (n > 1) k_karras<<<bs_blocks((size_t)n - 1, 256), 256, 0, st>>>(d_codes2, n, d_left, d_right, d_parent);
+    if (n > 1) bs_count_launch(), k_karras<<<bs_blocks((size_t)n - 1, 256), 256, 0, st>>>(d_codes2, n, d_left, d_right, d_parent);
     const unsigned root_id = 0u;
 #endif
-    k_leaves_and_climb<<<bs_blocks((size_t)n, 128), 128, 0, st>>>(d_tris, d_ids2, n_tris, d_sorted, d_raw, d_left, d_right, d_parent, d_flags, n);
-    k_finalize_nodes<<<bs_blocks((size_t)n_nodes, 128), 128, 0, st>>>(d_raw, n, d_hdr, d_coef);
-    if (n > 1) k_records<<<bs_blocks(((size_t)n - 1) * 4, 256), 256, 0, st>>>(d_left, d_right, d_hdr, d_coef, n, d_rec);
+    bs_count_launch(), k_leaves_and_climb<<<bs_blocks((size_t)n, 128), 128, 0, st>>>(d_tris, d_ids2, n_tris, d_sorted, d_raw, d_left, d_right, d_parent, d_flags, n);
+    bs_count_launch(), k_finalize_nodes<<<bs_blocks((size_t)n_nodes, 128), 128, 0, st>>>(d_raw, n, d_hdr, d_coef);
+    if (n > 1) bs_count_launch(), k_records<<<bs_blocks(((size_t)n - 1) * 4, 256), 256, 0, st>>>(d_left, d_right, d_hdr, d_coef, n, d_rec);
     bs_free(ctx, d_raw); bs_free(ctx, d_ids2); bs_free(ctx, d_codes2); bs_free(ctx, d_left); bs_free(ctx, d_right); bs_free(ctx, d_parent); bs_free(ctx, d_flags);
     Tree T;
     T.hdr = d_hdr; T.coef = d_coef; T.rec = d_rec; T.tris = d_sorted; T.n_leaves = (unsigned)n; T.root = root_id;
@@ -713,18 +713,18 @@ bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_v
         const size_t nb = vol->n_bricks;
         unsigned *d_nchunks = nullptr, *d_ordered = nullptr, *d_off = nullptr, *d_chunk_off = nullptr, *d_item_brick = nullptr, *d_order = nullptr; unsigned n_items = 0;
         BS_TRY(bs_alloc(ctx, &d_nchunks, nb)); BS_TRY(bs_alloc(ctx, &d_ordered, nb + 1)); BS_TRY(bs_alloc(ctx, &d_off, nb + 1)); BS_TRY(bs_alloc(ctx, &d_chunk_off, nb));
-        k_masks<<<bs_blocks(nb * 32, 256), 256, 0, st>>>(vol->values, nb, vol->masks, d_nchunks, 32 * BS_VPL);
+        bs_count_launch(), k_masks<<<bs_blocks(nb * 32, 256), 256, 0, st>>>(vol->values, nb, vol->masks, d_nchunks, 32 * BS_VPL);
         if (d_touches) {  // heaviest bricks first
             unsigned *d_k = nullptr, *d_k2 = nullptr, *d_i = nullptr;
             BS_TRY(bs_alloc(ctx, &d_k, nb)); BS_TRY(bs_alloc(ctx, &d_k2, nb)); BS_TRY(bs_alloc(ctx, &d_i, nb)); BS_TRY(bs_alloc(ctx, &d_order, nb));
-            k_touch_keys<<<bs_blocks(nb, 256), 256, 0, st>>>(d_touches, nb, d_k, d_i);
+            bs_count_launch(), k_touch_keys<<<bs_blocks(nb, 256), 256, 0, st>>>(d_touches, nb, d_k, d_i);
             tmp_bytes = 0;
             cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, d_k, d_k2, d_i, d_order, nb, 0, 32, st);
             BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp_bytes));
             cub::DeviceRadixSort::SortPairsDescending(d_tmp, tmp_bytes, d_k, d_k2, d_i, d_order, nb, 0, 32, st);
             bs_free(ctx, d_tmp); bs_free(ctx, d_k); bs_free(ctx, d_k2); bs_free(ctx, d_i);
         }
-        k_order_chunks<<<bs_blocks(nb + 1, 256), 256, 0, st>>>(d_order, d_nchunks, nb, d_ordered);
+        bs_count_launch(), k_order_chunks<<<bs_blocks(nb + 1, 256), 256, 0, st>>>(d_order, d_nchunks, nb, d_ordered);
         tmp_bytes = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_ordered, d_off, nb + 1, st);
         BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp_bytes));
@@ -733,7 +733,7 @@ bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_v
         BS_CUDA(ctx, cudaStreamSynchronize(st));
         bs_free(ctx, d_tmp); bs_free(ctx, d_nchunks); bs_free(ctx, d_ordered);
         BS_TRY(bs_alloc(ctx, &d_item_brick, n_items));
-        k_items<<<bs_blocks(nb, 256), 256, 0, st>>>(d_order, d_off, nb, d_item_brick, d_chunk_off);
+        bs_count_launch(), k_items<<<bs_blocks(nb, 256), 256, 0, st>>>(d_order, d_off, nb, d_item_brick, d_chunk_off);
         bs_free(ctx, d_off); bs_free(ctx, d_order);
         const size_t blocks = (n_items + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
         BrickOut* d_bo = nullptr;
@@ -744,16 +744,16 @@ bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_v
             unsigned long long* d_cnt = nullptr; unsigned long long h_cnt[9];
             BS_TRY(bs_alloc(ctx, &d_cnt, 9));
             BS_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, 72, st));
-            k_brick_pass<true><<<bs_blocks(nb, BP_WARPS), 32 * BP_WARPS, 0, st>>>(T, vol->keys, nb, vol->voxel_size, kappa, d_bo, d_cnt);
-            if (n_items) k_sign<true, BS_VPL><<<(unsigned)blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(T, vol->values, vol->masks, n_items, d_item_brick, d_chunk_off, vol->keys, vol->voxel_size, d_bo, d_cnt);
+            bs_count_launch(), k_brick_pass<true><<<bs_blocks(nb, BP_WARPS), 32 * BP_WARPS, 0, st>>>(T, vol->keys, nb, vol->voxel_size, kappa, d_bo, d_cnt);
+            if (n_items) bs_count_launch(), k_sign<true, BS_VPL><<<(unsigned)blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(T, vol->values, vol->masks, n_items, d_item_brick, d_chunk_off, vol->keys, vol->voxel_size, d_bo, d_cnt);
             BS_CUDA(ctx, cudaMemcpyAsync(h_cnt, d_cnt, 72, cudaMemcpyDeviceToHost, st));
             BS_CUDA(ctx, cudaStreamSynchronize(st));
             bs_free(ctx, d_cnt);
             for (int i = 0; i < 9; ++i) ctx->fwn_counts[i] = (double)h_cnt[i];
         } else {
-            k_brick_pass<false><<<bs_blocks(nb, BP_WARPS), 32 * BP_WARPS, 0, st>>>(T, vol->keys, nb, vol->voxel_size, kappa, d_bo, nullptr);
+            bs_count_launch(), k_brick_pass<false><<<bs_blocks(nb, BP_WARPS), 32 * BP_WARPS, 0, st>>>(T, vol->keys, nb, vol->voxel_size, kappa, d_bo, nullptr);
             bs_mark(ctx, "sign_brick_pass_ms");
-            if (n_items) k_sign<false, BS_VPL><<<(unsigned)blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(T, vol->values, vol->masks, n_items, d_item_brick, d_chunk_off, vol->keys, vol->voxel_size, d_bo, nullptr);
+            if (n_items) bs_count_launch(), k_sign<false, BS_VPL><<<(unsigned)blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(T, vol->values, vol->masks, n_items, d_item_brick, d_chunk_off, vol->keys, vol->voxel_size, d_bo, nullptr);
         }
         bs_free(ctx, d_bo); bs_free(ctx, d_chunk_off); bs_free(ctx, d_item_brick);
     }

@@ -540,7 +540,7 @@ bs_status bs_mc_impl(const bs_volume* v, float voxel_size, const float** d_verts
     if (n_items == 0) { bs_marks_end(ctx); return BS_OK; }
     int* d_nbr = nullptr;
     BS_TRY(bs_alloc(ctx, &d_nbr, n * 8));
-    if (n) k_mc_neighbours<<<bs_blocks(n * 8, 256), 256, 0, st>>>(v->keys, n, d_nbr);
+    if (n) bs_count_launch(), k_mc_neighbours<<<bs_blocks(n * 8, 256), 256, 0, st>>>(v->keys, n, d_nbr);
     VolView V{v->keys, v->values, v->masks, n, v->owned, d_nbr, v->tile8_keys, v->tile8_values, nt8, v->tile128_keys, v->tile128_values, nt128};
     const signed char* tables = (const signed char*)ctx->d_mc33;
     unsigned *d_counts = nullptr, *d_pos = nullptr; unsigned long long *d_wide = nullptr, *d_off = nullptr;
@@ -548,12 +548,12 @@ bs_status bs_mc_impl(const bs_volume* v, float voxel_size, const float** d_verts
     const bool tiles = nt8 || nt128;
     if (tiles) {
         BS_TRY(bs_alloc(ctx, &d_pos, n_items));
-        k_merge_pos<<<bs_blocks(std::max(n, std::max(nt8, nt128)), 256), 256, 0, st>>>(V, d_pos, d_pos + n, d_pos + n + nt8);
+        bs_count_launch(), k_merge_pos<<<bs_blocks(std::max(n, std::max(nt8, nt128)), 256), 256, 0, st>>>(V, d_pos, d_pos + n, d_pos + n + nt8);
     }
     CarryV12 *d_writer = nullptr, *d_carry_incl = nullptr, *d_incoming = nullptr; unsigned char* d_unres = nullptr; int* d_any = nullptr; int any_unres = 0;
     BS_TRY(bs_alloc(ctx, &d_writer, n)); BS_TRY(bs_alloc(ctx, &d_unres, n)); BS_TRY(bs_alloc(ctx, &d_any, 1));
     BS_CUDA(ctx, cudaMemsetAsync(d_any, 0, sizeof(int), st));
-    if (n) k_mc<false><<<(unsigned)n, MC_TPB, 0, st>>>(V, tables, voxel_size, d_pos, d_counts, nullptr, nullptr, d_writer, nullptr, d_unres, 0, d_any);
+    if (n) bs_count_launch(), k_mc<false><<<(unsigned)n, MC_TPB, 0, st>>>(V, tables, voxel_size, d_pos, d_counts, nullptr, nullptr, d_writer, nullptr, d_unres, 0, d_any);
     BS_CUDA(ctx, cudaMemcpyAsync(&any_unres, d_any, sizeof(int), cudaMemcpyDeviceToHost, st));
     BS_CUDA(ctx, cudaStreamSynchronize(st));
     if (any_unres) {  // rare: some 6.1.2 cell needs the c-vertex left behind by an earlier brick -> carry scan, recount those bricks
@@ -562,13 +562,13 @@ bs_status bs_mc_impl(const bs_volume* v, float voxel_size, const float** d_verts
         cub::DeviceScan::InclusiveScan(nullptr, t2, d_writer, d_carry_incl, CarryOp(), n, st);
         BS_TRY(bs_alloc(ctx, (char**)&d_t2, t2));
         cub::DeviceScan::InclusiveScan(d_t2, t2, d_writer, d_carry_incl, CarryOp(), n, st);
-        k_shift_carry<<<bs_blocks(n, 256), 256, 0, st>>>(d_carry_incl, d_incoming, n);
-        k_mc<false><<<(unsigned)n, MC_TPB, 0, st>>>(V, tables, voxel_size, d_pos, d_counts, nullptr, nullptr, d_writer, d_incoming, d_unres, 1, d_any);
+        bs_count_launch(), k_shift_carry<<<bs_blocks(n, 256), 256, 0, st>>>(d_carry_incl, d_incoming, n);
+        bs_count_launch(), k_mc<false><<<(unsigned)n, MC_TPB, 0, st>>>(V, tables, voxel_size, d_pos, d_counts, nullptr, nullptr, d_writer, d_incoming, d_unres, 1, d_any);
         bs_free(ctx, d_t2);
     }
-    if (nt8) k_mc_tiles<false><<<(unsigned)nt8, 256, 0, st>>>(V, tables, voxel_size, 0, d_pos + n, d_counts, nullptr, nullptr);
-    if (nt128) k_mc_tiles<false><<<(unsigned)nt128, 256, 0, st>>>(V, tables, voxel_size, 1, d_pos + n + nt8, d_counts, nullptr, nullptr);
-    k_widen<<<bs_blocks(n_items + 1, 256), 256, 0, st>>>(d_counts, d_wide, n_items);
+    if (nt8) bs_count_launch(), k_mc_tiles<false><<<(unsigned)nt8, 256, 0, st>>>(V, tables, voxel_size, 0, d_pos + n, d_counts, nullptr, nullptr);
+    if (nt128) bs_count_launch(), k_mc_tiles<false><<<(unsigned)nt128, 256, 0, st>>>(V, tables, voxel_size, 1, d_pos + n + nt8, d_counts, nullptr, nullptr);
+    bs_count_launch(), k_widen<<<bs_blocks(n_items + 1, 256), 256, 0, st>>>(d_counts, d_wide, n_items);
     void* d_tmp = nullptr; size_t tmp_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_wide, d_off, n_items + 1, st);
     BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp_bytes));
@@ -579,9 +579,9 @@ bs_status bs_mc_impl(const bs_volume* v, float voxel_size, const float** d_verts
     bs_mark(ctx, "mc_count_ms");
     bs_status s = bs_ensure_out_verts(ctx, (size_t)n_tris * 9);
     if (s == BS_OK && n_tris) {
-        if (n) k_mc<true><<<(unsigned)n, MC_TPB, 0, st>>>(V, tables, voxel_size, d_pos, nullptr, d_off, ctx->d_out_verts, nullptr, d_incoming, nullptr, 0, nullptr);
-        if (nt8) k_mc_tiles<true><<<(unsigned)nt8, 256, 0, st>>>(V, tables, voxel_size, 0, d_pos + n, nullptr, d_off, ctx->d_out_verts);
-        if (nt128) k_mc_tiles<true><<<(unsigned)nt128, 256, 0, st>>>(V, tables, voxel_size, 1, d_pos + n + nt8, nullptr, d_off, ctx->d_out_verts);
+        if (n) bs_count_launch(), k_mc<true><<<(unsigned)n, MC_TPB, 0, st>>>(V, tables, voxel_size, d_pos, nullptr, d_off, ctx->d_out_verts, nullptr, d_incoming, nullptr, 0, nullptr);
+        if (nt8) bs_count_launch(), k_mc_tiles<true><<<(unsigned)nt8, 256, 0, st>>>(V, tables, voxel_size, 0, d_pos + n, nullptr, d_off, ctx->d_out_verts);
+        if (nt128) bs_count_launch(), k_mc_tiles<true><<<(unsigned)nt128, 256, 0, st>>>(V, tables, voxel_size, 1, d_pos + n + nt8, nullptr, d_off, ctx->d_out_verts);
     }
     bs_mark(ctx, "mc_emit_ms");
     bs_free(ctx, d_pos); bs_free(ctx, d_nbr); bs_free(ctx, d_writer); bs_free(ctx, d_carry_incl); bs_free(ctx, d_incoming); bs_free(ctx, d_unres); bs_free(ctx, d_any);

@@ -240,7 +240,7 @@ bs_status bs_offset_impl(bs_volume* A, float distance, bs_volume** out) {
     u64* d_pmasks = nullptr; unsigned char* d_nonempty = nullptr; int* d_flags = nullptr;
     BS_TRY(bs_alloc(ctx, &d_pmasks, n_src * 8)); BS_TRY(bs_alloc(ctx, &d_nonempty, n_src)); BS_TRY(bs_alloc(ctx, &d_flags, 1));
     BS_CUDA(ctx, cudaMemsetAsync(d_nonempty, 0, n_src ? n_src : 1, st));
-    if (n_src) k_prune<<<bs_blocks(n_src * 8, TPB), TPB, 0, st>>>(A->values, A->masks, n_src, vs * 2.0f, d_pmasks, d_nonempty);
+    if (n_src) bs_count_launch(), k_prune<<<bs_blocks(n_src * 8, TPB), TPB, 0, st>>>(A->values, A->masks, n_src, vs * 2.0f, d_pmasks, d_nonempty);
     // keys of the non-empty pruned bricks
     u64* d_seed = nullptr; size_t n_seed = 0;
     {
@@ -273,7 +273,7 @@ bs_status bs_offset_impl(bs_volume* A, float distance, bs_volume** out) {
         for (int k = 0; k < K; ++k) {
             u64 *d_big = nullptr, *d_next = nullptr; size_t n_next = 0;
             BS_TRY(bs_alloc(ctx, &d_big, n * 27));
-            k_dilate<<<bs_blocks(n * 27, TPB), TPB, 0, st>>>(d_keys, n, d_big, d_flags);
+            bs_count_launch(), k_dilate<<<bs_blocks(n * 27, TPB), TPB, 0, st>>>(d_keys, n, d_big, d_flags);
             BS_TRY(sort_unique(ctx, d_big, n * 27, &d_next, &n_next));
             bs_free(ctx, d_big); bs_free(ctx, d_keys);
             d_keys = d_next; n = n_next;
@@ -285,8 +285,8 @@ bs_status bs_offset_impl(bs_volume* A, float distance, bs_volume** out) {
         BS_CUDA(ctx, cudaMemsetAsync(d_masks, 0, n * 8 * sizeof(u64), st));
         BS_CUDA(ctx, cudaMemsetAsync(d_frozen, 0, n * 8 * sizeof(u64), st));
         BS_CUDA(ctx, cudaMemsetAsync(d_inq, 0, n, st));
-        k_place<<<(unsigned)n_src, 512, 0, st>>>(A->keys, A->values, d_pmasks, d_nonempty, n_src, d_keys, n, d_values, d_masks, d_frozen, d_inq);
-        k_neighbours<<<bs_blocks(n * 6, TPB), TPB, 0, st>>>(d_keys, n, d_nbr);
+        bs_count_launch(), k_place<<<(unsigned)n_src, 512, 0, st>>>(A->keys, A->values, d_pmasks, d_nonempty, n_src, d_keys, n, d_values, d_masks, d_frozen, d_inq);
+        bs_count_launch(), k_neighbours<<<bs_blocks(n * 6, TPB), TPB, 0, st>>>(d_keys, n, d_nbr);
         // --- leaf wavefronts for the four axis-sign patterns (the other four are their reverses) -------------
         std::vector<u64> h_keys(n);
         BS_CUDA(ctx, cudaMemcpyAsync(h_keys.data(), d_keys, n * sizeof(u64), cudaMemcpyDeviceToHost, st));
@@ -324,7 +324,7 @@ bs_status bs_offset_impl(bs_volume* A, float distance, bs_volume** out) {
                 const unsigned cnt = seg[g][wi + 1] - seg[g][wi];
                 if (!cnt) continue;
                 P.order = d_order + (size_t)g * n + seg[g][wi];
-                k_sweep<<<cnt, 64, 0, st>>>(P);
+                bs_count_launch(), k_sweep<<<cnt, 64, 0, st>>>(P);
                 ++n_launch;
             }
         }
@@ -346,8 +346,8 @@ bs_status bs_offset_impl(bs_volume* A, float distance, bs_volume** out) {
         if (s == BS_OK) s = bs_alloc(ctx, &d_rank, n);
         if (s == BS_OK) {
             cudaMemsetAsync(d_ne, 0, n, st);
-            k_finish<<<bs_blocks(n * 8, TPB), TPB, 0, st>>>(d_values, d_masks, n, distance, d_ne);
-            k_widen8<<<bs_blocks(n, TPB), TPB, 0, st>>>(d_ne, d_ne32, n);
+            bs_count_launch(), k_finish<<<bs_blocks(n * 8, TPB), TPB, 0, st>>>(d_values, d_masks, n, distance, d_ne);
+            bs_count_launch(), k_widen8<<<bs_blocks(n, TPB), TPB, 0, st>>>(d_ne, d_ne32, n);
             cub::DeviceScan::InclusiveSum(nullptr, tmp, d_ne32, d_rank, n, st);
             s = bs_alloc(ctx, (char**)&d_tmp, tmp);
         }
@@ -357,7 +357,7 @@ bs_status bs_offset_impl(bs_volume* A, float distance, bs_volume** out) {
             if (cudaStreamSynchronize(st) != cudaSuccess) s = bs_fail(ctx, BS_ERR_CUDA, "offset kernels failed: %s", cudaGetErrorString(cudaGetLastError()));
         }
         if (s == BS_OK) s = bs_volume_alloc_bricks(R, n_out);
-        if (s == BS_OK && n_out) k_compact<<<(unsigned)n, 512, 0, st>>>(d_keys, d_values, d_masks, d_rank, d_ne, R->keys, R->values, R->masks);
+        if (s == BS_OK && n_out) bs_count_launch(), k_compact<<<(unsigned)n, 512, 0, st>>>(d_keys, d_values, d_masks, d_rank, d_ne, R->keys, R->values, R->masks);
         if (s == BS_OK && (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess)) s = bs_fail(ctx, BS_ERR_CUDA, "offset compaction failed");
         bs_free(ctx, d_tmp); bs_free(ctx, d_ne); bs_free(ctx, d_ne32); bs_free(ctx, d_rank);
         bs_free(ctx, d_keys); bs_free(ctx, d_values); bs_free(ctx, d_masks); bs_free(ctx, d_frozen); bs_free(ctx, d_inq); bs_free(ctx, d_nbr); bs_free(ctx, d_order);

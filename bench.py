@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--config", type=int, default=5)
     ap.add_argument("--scale", type=float, default=1.0, help="resolution scale of the config (1.0 = BASELINE.json size)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-scale", type=float, default=0.0625, help="scale of the bounded CPU sample")
+    ap.add_argument("--cpu-scale", type=float, default=0.1875, help="scale of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ops", action="store_true", help="time the CSG (config 2) / offset (3) / dual contouring (4) rows instead of the remesh")
     return ap.parse_args()
@@ -146,7 +146,12 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
+        self.index, self.rows, self.stop_flag, self.proc, self.t_begin = index, [], False, None, None
+
+    def mark_begin(self):
+        """nvidia-smi is started before the warm-up (its start-up takes driver locks that stall launches for 100s of ms);
+        only samples taken after this call -- the timed region -- are kept."""
+        self.t_begin = time.time()
 
     def run(self):
         try:
@@ -155,7 +160,8 @@ class ClockSampler(threading.Thread):
             for line in self.proc.stdout:
                 if self.stop_flag:
                     break
-                self.rows.append([x.strip() for x in line.split(",")])
+                if self.t_begin is not None:  # rows before mark_begin() belong to the warm-up
+                    self.rows.append([x.strip() for x in line.split(",")])
         except Exception:
             pass
 
@@ -316,25 +322,32 @@ def main():
         n_active_local = float(na.value) / world  # summed over ranks below
 
     # ---- value leg: K steps, device resident ------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step_device()
     stage_ms = {}
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     barrier()
+    sampler.mark_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     n_verts_local = 0
+    launches0 = L.bs_kernel_launch_count()
+    marks = []
     for _ in range(args.steps):
         _, nv, _ = step_device()
         n_verts_local = nv
+        marks.append(torch.cuda.Event(enable_timing=True))
+        marks[-1].record(stream)
         for k, v in ctx.last_stats().items():   # MC stage timings of this step (convert's were overwritten; re-read below)
             if k.endswith("_ms") and k != "total_ms":
                 stage_ms[k] = stage_ms.get(k, 0.0) + v
     e1.record(stream)
+    launches = L.bs_kernel_launch_count() - launches0  # this rank's own kernels launched inside the timed region (library sorts / scans excluded)
     barrier()
     clocks = sampler.finish()
     ms_total = e0.elapsed_time(e1)
+    step_ms = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
 
     # per-stage device times of convert (CUDA events on the library's stream), averaged over a few extra passes
     conv_ms = {}
@@ -418,13 +431,12 @@ def main():
                        "band_width": 0, "l2": "inputs larger than L2 (triangles %.0f MB, bricks %.0f MB)" % (tris.nbytes / 1e6, work.get("n_bricks", 0) * 2112 / 1e6),
                        "parallelism": "brick slabs x%d, mesh replicated" % world},
             "remesh_ms": ms_per_step, "tris_per_s": (n_verts / 3.0) / (ms_per_step * 1e-3), "n_active_voxels": n_active, "n_out_triangles": n_verts / 3.0,
-            "stage_ms": stage_all, "stage_ms_per_rank": per_rank, "work": work,
+            "step_ms": step_ms, "stage_ms": stage_all, "stage_ms_per_rank": per_rank, "work": work,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": int(tris.nbytes), "d2h_bytes_per_step": int(n_verts_local * 12)},
             "gpu_launches": None, "clocks": clocks,
             "roofline": dominant, "rooflines": rl,
         }
-        # launches inside the timed region: counted from the library's own launch sites (see DESIGN.md "Kernels")
-        out["gpu_launches"] = int(args.steps * launches_per_step(world))
+        out["gpu_launches"] = int(launches) * world  # counted by the library at its launch sites (bs_kernel_launch_count)
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
             ctris, cvs, cdesc = workload(args.config, args.cpu_scale)
@@ -434,12 +446,6 @@ def main():
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
-
-
-def launches_per_step(world):
-    # convert: k_tri_counts, scan(2), k_mark, select(2), sort(~7), k_fill_slots, k_eval, k_centroid_bounds, k_morton, sort(~9),
-    # k_leaves, k_level_up(levels-1 ~ 7), k_finalize_nodes, k_sign; MC: k_mc<count>, k_widen, scan(2), k_mc<emit>
-    return 1 + 2 + 1 + 2 + 7 + 1 + 1 + 1 + 1 + 9 + 1 + 7 + 1 + 1 + 1 + 1 + 2 + 1
 
 
 if __name__ == "__main__":

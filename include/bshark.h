@@ -133,6 +133,10 @@ bs_status bs_context_copy_out_verts_device(bs_context* ctx, float* d_dst, size_t
 enum { BS_FLAG_COUNT_WORK = 1 };
 bs_status bs_context_set_flag(bs_context* ctx, int flag, int value);
 
+/* Number of kernels of this library launched by the calling process so far (all contexts; library sorts / scans
+ * not included). One in-flight call per context: read it between calls. */
+unsigned long long bs_kernel_launch_count(void);
+
 /* Per-stage device timings (ms, CUDA events on the context stream) and work counters of the most recent
  * call on the context; names are listed in DESIGN.md.  Returns the number of entries written (<= cap). */
 size_t bs_context_last_stats(const bs_context* ctx, const char** names, double* values, size_t cap);
