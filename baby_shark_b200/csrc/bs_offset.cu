@@ -91,6 +91,16 @@ __device__ __forceinline__ float compute_distance(float a1, float a2, float a3, 
     return xmul(xadd(a123, xsqrt(xsub(xsub(xsub(three, d12s), d13s), d23s))), xdiv(1.0f, 3.0f));
 }
 
+// wavefront index of every brick for the four (sx, sy, +z) patterns: w = sx bx + sy by + bz, biased to be >= 0
+__global__ void k_wave_keys(const u64* __restrict__ keys, size_t n, unsigned* wk, unsigned* idx) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= 4 * n) return;
+    const unsigned g = (unsigned)(i / n); const size_t b = i % n;
+    int bx, by, bz; bs_key_brick(keys[b], bx, by, bz);
+    const int w = ((g & 1) ? -bx : bx) + ((g & 2) ? -by : by) + bz;
+    wk[i] = (unsigned)(w + 3 * (1 << 18)); idx[i] = (unsigned)b;
+}
+
 struct SweepParams {
     float* values; u64* masks; const u64* frozen; const int* nbr; unsigned char* inq; int* flags;
     const unsigned* order;   // bricks of this leaf wavefront
@@ -98,50 +108,92 @@ struct SweepParams {
     int dir;                 // bit0 = -x, bit1 = -y, bit2 = -z (sweep order fast_sweep.rs:39-60)
 };
 
-// One CTA (64 threads = the (y,z) columns in sweep-local coordinates) per queued leaf of the current leaf wavefront.
+// One CTA (64 threads = the (y,z) columns) per leaf of the current leaf wavefront; leaves that are not queued exit.
+// The kernel is one link of a ~1700-long dependency chain (8 sweeps x ~210 leaf wavefronts), so it is written for
+// LATENCY: every global load is issued up front in two round trips (brick data + neighbour ids, then the six faces),
+// the brick lives in a 10^3 padded shared array (faces in the halo: no centre/face branches in the stencil), frozen
+// bits sit in a register, the 22 voxel-wavefront steps touch shared memory only.
+constexpr int PAD = 10, PAD2 = 100, PADN = 1000;
 __global__ void __launch_bounds__(64) k_sweep(SweepParams P) {
-    __shared__ float s_v[512];          // centre values
-    __shared__ unsigned char s_a[512];  // centre active
-    __shared__ float s_fv[6][64];       // neighbour faces adjacent to the centre: +x -x +y -y +z -z
-    __shared__ unsigned char s_fa[6][64];
+    __shared__ float s_v[PADN];
+    __shared__ unsigned char s_a[PADN];
     const unsigned b = P.order[blockIdx.x];
-    if (!P.inq[b]) return;
     const unsigned t = threadIdx.x;
-    float* gv = P.values + (size_t)b * 512;
-    for (unsigned i = t; i < 512; i += 64) { s_v[i] = gv[i]; s_a[i] = (P.masks[(size_t)b * 8 + (i >> 6)] >> (i & 63)) & 1; }
-    {   // faces: thread t = (u, v) on the face
-        const unsigned u = t >> 3, v = t & 7;
+    const unsigned ty = t >> 3, tz = t & 7;  // this thread's (y, z) column in brick coordinates (load / store phases)
+    // round trip 1: queue flag, neighbour ids, centre values / masks / frozen masks (all depend on b only)
+    const unsigned char queued = P.inq[b];
+    int nb[6];
+#pragma unroll
+    for (int d = 0; d < 6; ++d) nb[d] = __ldg(P.nbr + (size_t)b * 6 + d);
+    if (!queued) return;
+    const float4* gv4 = reinterpret_cast<const float4*>(P.values + (size_t)b * 512);
+    const float4 c0 = gv4[t], c1 = gv4[t + 64];
+    const unsigned sh = (ty << 3) | tz;
+    unsigned abits = 0, fbits = 0;  // bit x = active / frozen flag of voxel (x, ty, tz)
+    {
+        u64 mw[8], fw[8];
+#pragma unroll
+        for (int x = 0; x < 8; ++x) { mw[x] = P.masks[(size_t)b * 8 + x]; fw[x] = P.frozen[(size_t)b * 8 + x]; }
+#pragma unroll
+        for (int x = 0; x < 8; ++x) { abits |= (unsigned)((mw[x] >> sh) & 1) << x; fbits |= (unsigned)((fw[x] >> sh) & 1) << x; }
+    }
+    // round trip 2: the six faces next to the brick: thread t = (u, v) on each face
+    float fv[6]; unsigned fa = 0;
+    {
+        const unsigned u = ty, v = tz;
 #pragma unroll
         for (int d = 0; d < 6; ++d) {
-            const int nb = P.nbr[(size_t)b * 6 + d];
-            float val = 0.f; unsigned char a = 0;
-            if (nb >= 0) {
+            fv[d] = 0.f;
+            if (nb[d] >= 0) {
                 const unsigned c = (d & 1) ? 7u : 0u;  // the +x neighbour contributes its x = 0 face, the -x neighbour its x = 7 face
                 const unsigned off = d < 2 ? ((c << 6) | (u << 3) | v) : (d < 4 ? ((u << 6) | (c << 3) | v) : ((u << 6) | (v << 3) | c));
-                a = (P.masks[(size_t)nb * 8 + (off >> 6)] >> (off & 63)) & 1;
-                val = P.values[(size_t)nb * 512 + off];
+                fa |= (unsigned)((P.masks[(size_t)nb[d] * 8 + (off >> 6)] >> (off & 63)) & 1) << d;
+                fv[d] = P.values[(size_t)nb[d] * 512 + off];
             }
-            s_fv[d][t] = val; s_fa[d][t] = a;
+        }
+    }
+    // fill the padded array: index (x+1)*100 + (y+1)*10 + (z+1)
+    {
+        // centre: float4 q covers offsets 4q..4q+3 = (x, y, z0..z0+3)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const unsigned q = t + 64 * h, off = q * 4, x = off >> 6, y = (off >> 3) & 7, z = off & 7;
+            const float4 c = h ? c1 : c0;
+            float* d = s_v + (x + 1) * PAD2 + (y + 1) * PAD + (z + 1);
+            d[0] = c.x; d[1] = c.y; d[2] = c.z; d[3] = c.w;
+        }
+#pragma unroll
+        for (int x = 0; x < 8; ++x) s_a[(x + 1) * PAD2 + (ty + 1) * PAD + (tz + 1)] = (abits >> x) & 1;
+        const unsigned u = ty, v = tz;
+#pragma unroll
+        for (int d = 0; d < 6; ++d) {
+            const unsigned c = (d & 1) ? 0u : 9u;  // +x face sits at padded x = 9, -x face at padded x = 0
+            const unsigned p = d < 2 ? (c * PAD2 + (u + 1) * PAD + (v + 1)) : (d < 4 ? ((u + 1) * PAD2 + c * PAD + (v + 1)) : ((u + 1) * PAD2 + (v + 1) * PAD + c));
+            s_v[p] = fv[d]; s_a[p] = (fa >> d) & 1;
         }
     }
     __syncthreads();
     const int sx = (P.dir & 1) ? -1 : 1, sy = (P.dir & 2) ? -1 : 1, sz = (P.dir & 4) ? -1 : 1;
     const int ly = t >> 3, lz = t & 7;  // sweep-local y, z of this thread's column
-    const u64* fz = P.frozen + (size_t)b * 8;
+    const int y = sy > 0 ? ly : 7 - ly, z = sz > 0 ? lz : 7 - lz;
+    unsigned cfz = 0;  // frozen bits of column (y, z): held by the thread whose (ty, tz) == (y, z)
+    {
+        const unsigned src = ((unsigned)y << 3) | (unsigned)z;  // lane (within this warp or the other) that holds them
+        __shared__ unsigned char s_fz[64];
+        s_fz[t] = (unsigned char)fbits;
+        __syncthreads();
+        cfz = s_fz[src];
+    }
+    const int pyz = (y + 1) * PAD + (z + 1);
     for (int step = 0; step < 22; ++step) {
         const int lx = step - ly - lz;
-        if (lx >= 0 && lx < 8) {
-            const int x = sx > 0 ? lx : 7 - lx, y = sy > 0 ? ly : 7 - ly, z = sz > 0 ? lz : 7 - lz;
-            const unsigned off = (x << 6) | (y << 3) | z;
-            if (!((fz[off >> 6] >> (off & 63)) & 1)) {  // frozen voxels keep their value (:126-128)
+        if ((unsigned)lx < 8u) {
+            const int x = sx > 0 ? lx : 7 - lx;
+            if (!((cfz >> x) & 1)) {  // frozen voxels keep their value (:126-128)
+                const int p = (x + 1) * PAD2 + pyz;
                 // stencil.at for the six face neighbours (:130-146, :360-386)
-                float nv[6]; bool na[6];
-                if (x < 7) { na[0] = s_a[off + 64]; nv[0] = s_v[off + 64]; } else { na[0] = s_fa[0][(y << 3) | z]; nv[0] = s_fv[0][(y << 3) | z]; }
-                if (x > 0) { na[1] = s_a[off - 64]; nv[1] = s_v[off - 64]; } else { na[1] = s_fa[1][(y << 3) | z]; nv[1] = s_fv[1][(y << 3) | z]; }
-                if (y < 7) { na[2] = s_a[off + 8]; nv[2] = s_v[off + 8]; } else { na[2] = s_fa[2][(x << 3) | z]; nv[2] = s_fv[2][(x << 3) | z]; }
-                if (y > 0) { na[3] = s_a[off - 8]; nv[3] = s_v[off - 8]; } else { na[3] = s_fa[3][(x << 3) | z]; nv[3] = s_fv[3][(x << 3) | z]; }
-                if (z < 7) { na[4] = s_a[off + 1]; nv[4] = s_v[off + 1]; } else { na[4] = s_fa[4][(x << 3) | y]; nv[4] = s_fv[4][(x << 3) | y]; }
-                if (z > 0) { na[5] = s_a[off - 1]; nv[5] = s_v[off - 1]; } else { na[5] = s_fa[5][(x << 3) | y]; nv[5] = s_fv[5][(x << 3) | y]; }
+                const float nv[6] = {s_v[p + PAD2], s_v[p - PAD2], s_v[p + PAD], s_v[p - PAD], s_v[p + 1], s_v[p - 1]};
+                const bool na[6] = {s_a[p + PAD2] != 0, s_a[p - PAD2] != 0, s_a[p + PAD] != 0, s_a[p - PAD] != 0, s_a[p + 1] != 0, s_a[p - 1] != 0};
                 // option_min_by(+, -, cmp_abs): both present -> the smaller |v|, ties -> the + side
                 float d[3]; bool has[3];
 #pragma unroll
@@ -156,8 +208,8 @@ __global__ void __launch_bounds__(64) k_sweep(SweepParams P) {
                         const float d1 = has[0] ? fabsf(d[0]) : FLT_MAX, d2 = has[1] ? fabsf(d[1]) : FLT_MAX, d3 = has[2] ? fabsf(d[2]) : FLT_MAX;
                         const float dn = compute_distance(d1, d2, d3, P.h);
                         if (!(dn > P.limit_abs)) {
-                            const float old = s_a[off] ? s_v[off] : FLT_MAX;
-                            if (dn < fabsf(old)) { s_v[off] = P.sweep_neg ? -fabsf(dn) : fabsf(dn); s_a[off] = 1; }  // set_sign (value/f32.rs:11-17)
+                            const float old = s_a[p] ? s_v[p] : FLT_MAX;
+                            if (dn < fabsf(old)) { s_v[p] = P.sweep_neg ? -fabsf(dn) : fabsf(dn); s_a[p] = 1; }  // set_sign (value/f32.rs:11-17)
                         }
                     }
                 }
@@ -166,22 +218,33 @@ __global__ void __launch_bounds__(64) k_sweep(SweepParams P) {
         __syncthreads();
     }
     // write back + queue the downstream leaves (:185-277)
-    for (unsigned i = t; i < 512; i += 64) gv[i] = s_v[i];
     {
-        // mask words: 8 words x 64 bits; thread t assembles word t for t < 8
-        if (t < 8) { u64 m = 0; for (int k = 0; k < 64; ++k) m |= (u64)s_a[t * 64 + k] << k; P.masks[(size_t)b * 8 + t] = m; }
+        float4* go4 = reinterpret_cast<float4*>(P.values + (size_t)b * 512);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const unsigned q = t + 64 * h, off = q * 4, x = off >> 6, yy = (off >> 3) & 7, zz = off & 7;
+            const float* d = s_v + (x + 1) * PAD2 + (yy + 1) * PAD + (zz + 1);
+            go4[q] = make_float4(d[0], d[1], d[2], d[3]);
+        }
+        // mask word x, bit (ty << 3 | tz) = t: each warp ballots its half of the word
+        unsigned* gm = reinterpret_cast<unsigned*>(P.masks + (size_t)b * 8);
+#pragma unroll
+        for (int x = 0; x < 8; ++x) {
+            const unsigned bal = __ballot_sync(0xFFFFFFFFu, s_a[(x + 1) * PAD2 + (ty + 1) * PAD + (tz + 1)] != 0);
+            if ((t & 31) == 0) gm[2 * x + (t >> 5)] = bal;
+        }
     }
-    const unsigned u = t >> 3, v = t & 7;
+    const unsigned u = ty, v = tz;
 #pragma unroll
     for (int ax = 0; ax < 3; ++ax) {
         const int s = ax == 0 ? sx : (ax == 1 ? sy : sz);
-        const unsigned c = s > 0 ? 7u : 0u;  // exit face; the reference's negative-direction index collapses to local 0 via leaf index masking
-        const unsigned off = ax == 0 ? ((c << 6) | (u << 3) | v) : (ax == 1 ? ((u << 6) | (c << 3) | v) : ((u << 6) | (v << 3) | c));
-        const bool q = s_a[off] && ((int)(__float_as_uint(s_v[off]) >> 31) == P.sweep_neg) && (fabsf(s_v[off]) < P.limit_abs);
+        const unsigned c = s > 0 ? 8u : 1u;  // exit face (padded coordinate); the reference's negative-direction index collapses to local 0 via leaf index masking
+        const unsigned p = ax == 0 ? (c * PAD2 + (u + 1) * PAD + (v + 1)) : (ax == 1 ? ((u + 1) * PAD2 + c * PAD + (v + 1)) : ((u + 1) * PAD2 + (v + 1) * PAD + c));
+        const bool q = s_a[p] && ((int)(__float_as_uint(s_v[p]) >> 31) == P.sweep_neg) && (fabsf(s_v[p]) < P.limit_abs);
         if (__syncthreads_or(q)) {
             if (t == 0) {
-                const int nb = P.nbr[(size_t)b * 6 + 2 * ax + (s > 0 ? 0 : 1)];
-                if (nb >= 0) P.inq[nb] = 1; else P.flags[0] = 1;  // outside the pre-allocated set: retry wider
+                const int n2 = s > 0 ? nb[2 * ax] : nb[2 * ax + 1];
+                if (n2 >= 0) P.inq[n2] = 1; else P.flags[0] = 1;  // outside the pre-allocated set: retry wider
             }
         }
     }
@@ -287,26 +350,40 @@ bs_status bs_offset_impl(bs_volume* A, float distance, bs_volume** out) {
         BS_CUDA(ctx, cudaMemsetAsync(d_inq, 0, n, st));
         bs_count_launch(), k_place<<<(unsigned)n_src, 512, 0, st>>>(A->keys, A->values, d_pmasks, d_nonempty, n_src, d_keys, n, d_values, d_masks, d_frozen, d_inq);
         bs_count_launch(), k_neighbours<<<bs_blocks(n * 6, TPB), TPB, 0, st>>>(d_keys, n, d_nbr);
-        // --- leaf wavefronts for the four axis-sign patterns (the other four are their reverses) -------------
-        std::vector<u64> h_keys(n);
-        BS_CUDA(ctx, cudaMemcpyAsync(h_keys.data(), d_keys, n * sizeof(u64), cudaMemcpyDeviceToHost, st));
-        BS_CUDA(ctx, cudaStreamSynchronize(st));
-        std::vector<unsigned> h_order(4 * n);
-        std::vector<std::vector<unsigned>> seg(4);
-        for (int g = 0; g < 4; ++g) {
-            const int sx = (g & 1) ? -1 : 1, sy = (g & 2) ? -1 : 1;
-            int wmin = INT32_MAX, wmax = INT32_MIN;
-            std::vector<int> w(n);
-            for (size_t i = 0; i < n; ++i) { int bx, by, bz; bs_key_brick(h_keys[i], bx, by, bz); w[i] = sx * bx + sy * by + bz; wmin = std::min(wmin, w[i]); wmax = std::max(wmax, w[i]); }
-            seg[g].assign((size_t)(wmax - wmin) + 2, 0);
-            for (size_t i = 0; i < n; ++i) seg[g][(size_t)(w[i] - wmin) + 1]++;
-            for (size_t k = 1; k < seg[g].size(); ++k) seg[g][k] += seg[g][k - 1];
-            std::vector<unsigned> cur(seg[g].begin(), seg[g].end() - 1);
-            for (size_t i = 0; i < n; ++i) h_order[(size_t)g * n + cur[(size_t)(w[i] - wmin)]++] = (unsigned)i;
+        // --- leaf wavefronts for the four axis-sign patterns (the other four are their reverses): bricks sorted by
+        // w = +-bx +- by + bz on the device; the host only learns the run lengths (one launch per non-empty w) ---------
+        unsigned *d_wk = nullptr, *d_wks = nullptr, *d_idx = nullptr, *d_order = nullptr, *d_runs = nullptr; int* d_nruns = nullptr;
+        BS_TRY(bs_alloc(ctx, &d_wk, 4 * n)); BS_TRY(bs_alloc(ctx, &d_wks, 4 * n)); BS_TRY(bs_alloc(ctx, &d_idx, 4 * n)); BS_TRY(bs_alloc(ctx, &d_order, 4 * n));
+        const size_t max_runs = std::min<size_t>(n, (size_t)3 << 18);
+        BS_TRY(bs_alloc(ctx, &d_runs, 8 * max_runs)); BS_TRY(bs_alloc(ctx, &d_nruns, 4));
+        bs_count_launch(), k_wave_keys<<<bs_blocks(4 * n, TPB), TPB, 0, st>>>(d_keys, n, d_wk, d_idx);
+        {
+            void* d_tmp = nullptr; size_t tmp = 0, tmp2 = 0;
+            cub::DeviceRadixSort::SortPairs(nullptr, tmp, d_wk, d_wks, d_idx, d_order, (int)n, 0, 21, st);
+            cub::DeviceRunLengthEncode::Encode(nullptr, tmp2, d_wks, d_runs, d_runs + max_runs, d_nruns, (int)n, st);
+            tmp = std::max(tmp, tmp2);
+            BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp));
+            for (int g = 0; g < 4; ++g) {
+                cub::DeviceRadixSort::SortPairs(d_tmp, tmp, d_wk + g * n, d_wks + g * n, d_idx + g * n, d_order + g * n, (int)n, 0, 21, st);
+                cub::DeviceRunLengthEncode::Encode(d_tmp, tmp, d_wks + g * n, d_runs + 2 * g * max_runs, d_runs + (2 * g + 1) * max_runs, d_nruns + g, (int)n, st);
+            }
+            bs_free(ctx, d_tmp);
         }
-        unsigned* d_order = nullptr;
-        BS_TRY(bs_alloc(ctx, &d_order, 4 * n));
-        BS_CUDA(ctx, cudaMemcpyAsync(d_order, h_order.data(), 4 * n * sizeof(unsigned), cudaMemcpyHostToDevice, st));
+        int h_nruns[4];
+        BS_CUDA(ctx, cudaMemcpyAsync(h_nruns, d_nruns, sizeof(h_nruns), cudaMemcpyDeviceToHost, st));
+        BS_CUDA(ctx, cudaStreamSynchronize(st));
+        std::vector<std::vector<unsigned>> seg(4);  // seg[g] = start offsets of the runs of pattern g (+ n)
+        {
+            std::vector<unsigned> cnt;
+            for (int g = 0; g < 4; ++g) {
+                cnt.resize((size_t)h_nruns[g]);
+                BS_CUDA(ctx, cudaMemcpyAsync(cnt.data(), d_runs + (2 * g + 1) * max_runs, cnt.size() * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+                BS_CUDA(ctx, cudaStreamSynchronize(st));
+                seg[g].assign(cnt.size() + 1, 0);
+                for (size_t k = 0; k < cnt.size(); ++k) seg[g][k + 1] = seg[g][k] + cnt[k];
+            }
+        }
+        bs_free(ctx, d_wk); bs_free(ctx, d_wks); bs_free(ctx, d_idx); bs_free(ctx, d_runs); bs_free(ctx, d_nruns);
         bs_mark(ctx, "offset_setup_ms");
         // --- 8 sweeps ---------------------------------------------------------------------------------------------------
         SweepParams P;
