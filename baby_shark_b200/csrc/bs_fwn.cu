@@ -349,12 +349,21 @@ struct WarpWinding {
                 asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt));
                 asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt + 128));
             }
+#ifdef BS_UNIFORM_PUSH
+            {   // every lane stores the same words to the same address: one wavefront, no divergent region
+                unsigned* e = stack + sp * (1 + VPL);
+                e[0] = id;
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) e[1 + v] = near_m[v];
+            }
+#else
             if (lane == 0) {
                 unsigned* e = stack + sp * (1 + VPL);
                 e[0] = id;
 #pragma unroll
                 for (int v = 0; v < VPL; ++v) e[1 + v] = near_m[v];
             }
+#endif
             ++sp;
         }
     }

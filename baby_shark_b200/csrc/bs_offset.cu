@@ -88,7 +88,7 @@ __device__ __forceinline__ float compute_distance(float a1, float a2, float a3, 
     const float s2 = xmul(xadd(a12, xsqrt(xsub(two, d12s))), 0.5f);
     if (fabsf(s2) <= a3) return s2;
     const float a123 = xadd(a12, a3), three = xadd(two, hsq), d13 = xsub(a1, a3), d13s = xmul(d13, d13), d23 = xsub(a2, a3), d23s = xmul(d23, d23);
-    return xmul(xadd(a123, xsqrt(xsub(xsub(xsub(three, d12s), d13s), d23s))), xdiv(1.0f, 3.0f));
+    return xmul(xadd(a123, xsqrt(xsub(xsub(xsub(three, d12s), d13s), d23s))), __uint_as_float(0x3EAAAAABu) /* = 1.0f / 3.0f, correctly rounded */);
 }
 
 // wavefront index of every brick for the four (sx, sy, +z) patterns: w = sx bx + sy by + bz, biased to be >= 0
@@ -120,12 +120,11 @@ __global__ void __launch_bounds__(64) k_sweep(SweepParams P) {
     const unsigned b = P.order[blockIdx.x];
     const unsigned t = threadIdx.x;
     const unsigned ty = t >> 3, tz = t & 7;  // this thread's (y, z) column in brick coordinates (load / store phases)
-    // round trip 1: queue flag, neighbour ids, centre values / masks / frozen masks (all depend on b only)
-    const unsigned char queued = P.inq[b];
+    // round trip 1 (overlaps the previous leaf wavefront under programmatic dependent launch: nothing read here is
+    // written by it): neighbour ids, centre values / masks / frozen masks
     int nb[6];
 #pragma unroll
     for (int d = 0; d < 6; ++d) nb[d] = __ldg(P.nbr + (size_t)b * 6 + d);
-    if (!queued) return;
     const float4* gv4 = reinterpret_cast<const float4*>(P.values + (size_t)b * 512);
     const float4 c0 = gv4[t], c1 = gv4[t + 64];
     const unsigned sh = (ty << 3) | tz;
@@ -137,6 +136,11 @@ __global__ void __launch_bounds__(64) k_sweep(SweepParams P) {
 #pragma unroll
         for (int x = 0; x < 8; ++x) { abits |= (unsigned)((mw[x] >> sh) & 1) << x; fbits |= (unsigned)((fw[x] >> sh) & 1) << x; }
     }
+    // the previous wavefront (which queues this leaf and owns the upstream faces) must be complete from here on;
+    // once this grid is past the wait, the next wavefront may start its own round trip 1
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
+    if (!P.inq[b]) return;
     // round trip 2: the six faces next to the brick: thread t = (u, v) on each face
     float fv[6]; unsigned fa = 0;
     {
@@ -396,12 +400,24 @@ bs_status bs_offset_impl(bs_volume* A, float distance, bs_volume** out) {
             const bool rev = dir & 4;
             const int g = rev ? ((~dir) & 3) : (dir & 3);
             const size_t nw = seg[g].size() - 1;
+            bool first_of_sweep = true;
             for (size_t k = 0; k < nw; ++k) {
                 const size_t wi = rev ? nw - 1 - k : k;
                 const unsigned cnt = seg[g][wi + 1] - seg[g][wi];
                 if (!cnt) continue;
                 P.order = d_order + (size_t)g * n + seg[g][wi];
-                bs_count_launch(), k_sweep<<<cnt, 64, 0, st>>>(P);
+                // programmatic dependent launch: the next wavefront of the same sweep may start its (independent) loads
+                // early; the first launch of a sweep serialises normally, since its bricks can be ones the previous
+                // sweep's last launches still write
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(cnt); cfg.blockDim = dim3(64); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                attr[0].val.programmaticStreamSerializationAllowed = first_of_sweep ? 0 : 1;
+                cfg.attrs = attr; cfg.numAttrs = 1;
+                bs_count_launch();
+                BS_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_sweep, P));
+                first_of_sweep = false;
                 ++n_launch;
             }
         }

@@ -14,7 +14,8 @@ cfg = int(sys.argv[1]) if len(sys.argv) > 1 else 5
 scale = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 tris, vs, desc = synth.config_mesh(cfg, scale)
-L, ctx = bs.load_library(), bs.Context.default()
+L = bs.load_library(os.environ.get("BSHARK_LIB"))  # experiment builds: BSHARK_LIB=path/to/variant.so
+ctx = bs.Context.default()
 d_tris = torch.from_numpy(tris).cuda()
 for _ in range(reps):
     h = C.c_void_p()
