@@ -10,7 +10,9 @@ hdr = rows[hi]
 iS, iE, iSamp = hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("# Samples")
 ops, samp, tot = collections.Counter(), collections.Counter(), 0
 for r in rows[hi + 1:]:
-    if len(r) <= iE or r[0] == "Address" or not r[iE].isdigit():
+    if r and r[0] == "Address":  # the export repeats the listing: count it once
+        break
+    if len(r) <= iE or not r[iE].isdigit():
         continue
     t = r[iS].split()
     op = (t[1] if t[0].startswith("@") else t[0]).split(".")[0]
