@@ -10,7 +10,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <map>
 #include <string>
+#include <unordered_map>
 #include <vector>
 #include "../../include/bshark.h"
 
@@ -79,7 +81,11 @@ struct bs_context {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
-    cudaMemPool_t pool = nullptr;
+    // device memory cache (bs_raw_alloc / bs_raw_free): freed blocks are kept by rounded size and handed out again
+    // without any driver call; everything runs on `stream`, so reuse is ordered by the stream itself
+    std::multimap<size_t, void*> cache_free;
+    std::unordered_map<void*, size_t> cache_live;
+    size_t cache_free_bytes = 0, cache_total_bytes = 0;
     std::string err;
     std::vector<bs_stat> stats;
     int8_t* d_mc33 = nullptr;       // MC33 tables blob (mc33_tables.h)
@@ -114,14 +120,19 @@ bs_status bs_fail(bs_context* ctx, bs_status st, const char* fmt, ...);
 #define BS_CUDA(ctx, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return bs_fail((ctx), BS_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } while (0)
 #define BS_TRY(call) do { bs_status s_ = (call); if (s_ != BS_OK) return s_; } while (0)
 
-// stream-ordered allocation on the context pool
+// device allocations of the library: served from the context's block cache (a steady workload makes no driver calls)
+bs_status bs_raw_alloc(bs_context* ctx, size_t bytes, void** out);
+void bs_raw_free(bs_context* ctx, void* p);
+void bs_cache_release(bs_context* ctx);  // give every cached (free) block back to the driver
 template <class T> bs_status bs_alloc(bs_context* ctx, T** p, size_t count) {
     *p = nullptr;
     if (count == 0) count = 1;
-    BS_CUDA(ctx, cudaMallocAsync((void**)p, count * sizeof(T), ctx->stream));
+    void* q = nullptr;
+    BS_TRY(bs_raw_alloc(ctx, count * sizeof(T), &q));
+    *p = (T*)q;
     return BS_OK;
 }
-template <class T> void bs_free(bs_context* ctx, T* p) { if (p) cudaFreeAsync((void*)p, ctx->stream); }
+template <class T> void bs_free(bs_context* ctx, T* p) { if (p) bs_raw_free(ctx, (void*)p); }
 
 void bs_mark(bs_context* ctx, const char* name);          // record an event named `name` on the stream
 void bs_marks_begin(bs_context* ctx);                     // clear marks + stats, record "begin"

@@ -64,6 +64,46 @@ template <class T> static bs_status to_host(bs_context* c, T** dst, const T* src
 
 unsigned long long g_bs_launches = 0;
 
+// ---- block cache ------------------------------------------------------------------------------------------------------
+// cudaMallocAsync on the default pool showed sporadic 100-500 ms stalls in steady state (pool growth / remapping when
+// the mix of sizes fragments it). The library's allocation pattern is the same every call, so freed blocks are kept
+// by rounded size (granularity 1/8 of the power of two below the request, >= 512 B: <= 12.5 % slack) and reused.
+static size_t bs_round_size(size_t bytes) {
+    if (bytes <= 512) return 512;
+    size_t p = 512;
+    while ((p << 1) <= bytes) p <<= 1;
+    const size_t g = std::max<size_t>(512, p >> 3);
+    return (bytes + g - 1) / g * g;
+}
+void bs_cache_release(bs_context* ctx) {
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& kv : ctx->cache_free) { cudaFree(kv.second); ctx->cache_total_bytes -= kv.first; }
+    ctx->cache_free.clear(); ctx->cache_free_bytes = 0;
+}
+bs_status bs_raw_alloc(bs_context* ctx, size_t bytes, void** out) {
+    const size_t sz = bs_round_size(bytes);
+    auto it = ctx->cache_free.find(sz);
+    void* p = nullptr;
+    if (it != ctx->cache_free.end()) { p = it->second; ctx->cache_free.erase(it); ctx->cache_free_bytes -= sz; }
+    else {
+        cudaError_t e = cudaMalloc(&p, sz);
+        if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); bs_cache_release(ctx); e = cudaMalloc(&p, sz); }
+        if (e != cudaSuccess) { cudaGetLastError(); return bs_fail(ctx, BS_ERR_CUDA, "device allocation of %zu bytes failed: %s", sz, cudaGetErrorString(e)); }
+        ctx->cache_total_bytes += sz;
+    }
+    ctx->cache_live[p] = sz;
+    *out = p;
+    return BS_OK;
+}
+void bs_raw_free(bs_context* ctx, void* p) {
+    auto it = ctx->cache_live.find(p);
+    if (it == ctx->cache_live.end()) return;
+    const size_t sz = it->second;
+    ctx->cache_live.erase(it);
+    ctx->cache_free.emplace(sz, p); ctx->cache_free_bytes += sz;
+    if (ctx->cache_free_bytes > ((size_t)48 << 30)) bs_cache_release(ctx);  // varying workloads: do not hoard HBM
+}
+
 extern "C" {
 
 bs_status bs_context_create(int device, bs_context** out) {
@@ -81,9 +121,6 @@ bs_status bs_context_create(int device, bs_context** out) {
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete ctx; return BS_ERR_CUDA;
     }
-    cudaDeviceGetDefaultMemPool(&ctx->pool, device);
-    uint64_t thr = UINT64_MAX;  // keep freed blocks in the pool: allocation cost must not show up per call
-    cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &thr);
     if (cudaMalloc((void**)&ctx->d_mc33, MC33_BLOB_SIZE) != cudaSuccess ||
         cudaMemcpy(ctx->d_mc33, h_mc33, MC33_BLOB_SIZE, cudaMemcpyHostToDevice) != cudaSuccess) {
         cudaStreamDestroy(ctx->stream); delete ctx; return BS_ERR_CUDA;
@@ -97,6 +134,8 @@ void bs_context_destroy(bs_context* ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (auto& m : ctx->marks) cudaEventDestroy(m.second);
     if (ctx->d_out_verts) cudaFree(ctx->d_out_verts);
+    bs_cache_release(ctx);
+    for (auto& kv : ctx->cache_live) cudaFree(kv.first);  // volumes the caller never freed
     cudaFree(ctx->d_mc33);
     cudaStreamDestroy(ctx->stream);
     delete ctx;

@@ -685,7 +685,7 @@ bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_v
     BS_CUDA(ctx, cudaMemcpyAsync(d_bounds, init, sizeof(init), cudaMemcpyHostToDevice, st));
     BS_TRY(bs_alloc(ctx, &d_codes, n_tris)); BS_TRY(bs_alloc(ctx, &d_codes2, n_tris));
     BS_TRY(bs_alloc(ctx, &d_ids, n_tris)); BS_TRY(bs_alloc(ctx, &d_ids2, n_tris));
-    bs_count_launch(), k_centroid_bounds<<<(unsigned)std::min<size_t>(bs_blocks(n_tris, 256), (size_t)ctx->sm_count * 8), 256, 0, st>>>(d_tris, n_tris, d_bounds);
+    bs_count_launch(), k_centroid_bounds<<<(unsigned)std::min<size_t>(bs_blocks(n_tris, 256), (size_t)ctx->sm_count * 64), 256, 0, st>>>(d_tris, n_tris, d_bounds);
     bs_count_launch(), k_morton<<<bs_blocks(n_tris, 256), 256, 0, st>>>(d_tris, n_tris, d_bounds, d_codes, d_ids);
     void* d_tmp = nullptr; size_t tmp_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_codes, d_codes2, d_ids, d_ids2, n_tris, 0, 63, st);

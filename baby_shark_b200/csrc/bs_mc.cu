@@ -408,6 +408,251 @@ __global__ void __launch_bounds__(MC_TPB) k_mc(VolView V, const signed char* __r
     }
 }
 
+// ---- single-pass extraction (volumes without active tiles) ---------------------------------------------------------------
+// One WARP per brick, persistent warps drawing bricks from a ticket counter (so a brick's predecessors are always
+// running or done). The warp stages the 9^3 values, builds 9-bit active / sign rows per (x, y) from the mask bytes and
+// the staged values, classifies all 512 cells with a handful of bitwise operations per column, runs the MC33 logic on
+// the compacted candidates 32 at a time, and obtains its place in the output from a decoupled look-back over per-brick
+// descriptors (aggregate -> inclusive prefix) instead of a separate count pass + scan. The reference's stale c-vertex
+// (tiling 6.1.2) travels through a second, independent descriptor chain. No block-wide barriers anywhere.
+constexpr int MCF_WARPS = 4;
+constexpr unsigned FULL = 0xFFFFFFFFu;
+struct McDesc {
+    unsigned long long* count;  // [n] state << 62 | triangles: state 1 = this brick only, 2 = all bricks up to and including this one
+    float* carry;               // [n][4] x, y, z, state: 1 = brick computes no c-vertex (look further back), 2 = xyz is the c-vertex leaving the brick
+    unsigned* ticket;
+};
+struct McWarp {
+    float val[732];
+    unsigned short rowA[82], rowS[82];  // per (x, y), x, y in 0..8: bit z = active / negative
+    unsigned short cells[512];          // candidate cells in cell order
+    unsigned info[512];                 // row | len << 14 | need_c << 21 | stale << 22 | triangles << 23
+};
+__device__ __forceinline__ unsigned long long ld_vol(const unsigned long long* p) { return *(const volatile unsigned long long*)p; }
+__device__ __forceinline__ float ld_volf(const float* p) { return *(const volatile float*)p; }
+
+// c-vertex entering brick `tile`: nearest earlier brick that computed one, else the reference's initial (0, 0, 0)
+__device__ f3 mcf_incoming_carry(const McDesc& D, long long tile, unsigned lane) {
+    for (long long base = tile - 1; base >= 0; base -= 32) {
+        const long long idx = base - lane;
+        float st = 1.f;
+        if (idx >= 0) { do { st = ld_volf(D.carry + 4 * idx + 3); } while (st == 0.f); }
+        const unsigned m = __ballot_sync(FULL, st == 2.f);
+        if (m) {
+            const int src = __ffs(m) - 1;  // lane 0 looks at the nearest predecessor
+            f3 v{0.f, 0.f, 0.f};
+            if ((int)lane == src) { __threadfence(); v = f3{ld_volf(D.carry + 4 * idx), ld_volf(D.carry + 4 * idx + 1), ld_volf(D.carry + 4 * idx + 2)}; }
+            return f3{__shfl_sync(FULL, v.x, src), __shfl_sync(FULL, v.y, src), __shfl_sync(FULL, v.z, src)};
+        }
+    }
+    return f3{0.f, 0.f, 0.f};
+}
+
+struct McfCarry { f3 run; bool have_run; f3 incoming; bool incoming_known; };
+// Give a 6.1.2 cell the c-vertex the reference would hold at that point: latest earlier cell of this round / of earlier
+// rounds of the brick / of earlier bricks. Then advance the brick's running c-vertex. Warp-uniform control flow.
+__device__ __forceinline__ void mcf_resolve(Cell& q, bool need_c, bool stale, McfCarry& C, const McDesc& D, long long tile, unsigned lane) {
+    const unsigned wmask = __ballot_sync(FULL, need_c);
+    const unsigned smask = __ballot_sync(FULL, stale);
+    if (smask) {
+        const unsigned m = wmask & ((1u << lane) - 1u);
+        const int src = m ? 31 - __clz(m) : (int)lane;
+        const float sx = __shfl_sync(FULL, q.v12.x, src), sy = __shfl_sync(FULL, q.v12.y, src), sz = __shfl_sync(FULL, q.v12.z, src);
+        const bool outside = stale && !m && !C.have_run;
+        if (__any_sync(FULL, outside) && !C.incoming_known) { C.incoming = mcf_incoming_carry(D, tile, lane); C.incoming_known = true; }
+        if (stale) q.v12 = m ? f3{sx, sy, sz} : (C.have_run ? C.run : C.incoming);
+    }
+    if (wmask) {
+        const int top = 31 - __clz(wmask);
+        const float rx = __shfl_sync(FULL, q.v12.x, top), ry = __shfl_sync(FULL, q.v12.y, top), rz = __shfl_sync(FULL, q.v12.z, top);
+        C.run = f3{rx, ry, rz}; C.have_run = true;
+    }
+}
+__device__ __forceinline__ void mcf_load_cell(Cell& q, const float* val, int ox, int oy, int oz, unsigned c, int& id) {
+    const unsigned x = c >> 6, y = (c >> 3) & 7, z = c & 7;
+    id = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float v = val[(x + c_corner[i][0]) * 81 + (y + c_corner[i][1]) * 9 + (z + c_corner[i][2])];
+        if (fabsf(v) < MIN_ABS) v = copysignf(MIN_ABS, v);
+        if (v < 0.f) id |= 1 << i;
+        q.c[i] = v;
+    }
+    q.ox = ox + (int)x; q.oy = oy + (int)y; q.oz = oz + (int)z;
+}
+
+__global__ void __launch_bounds__(32 * MCF_WARPS, 8) k_mc_fused(VolView V, const signed char* __restrict__ tables, float vs, McDesc D, float* out, unsigned long long cap_tris) {
+    __shared__ McWarp S[MCF_WARPS];
+    const unsigned lane = threadIdx.x & 31;
+    McWarp& s = S[threadIdx.x >> 5];
+    for (;;) {
+        unsigned tk = 0;
+        if (lane == 0) tk = atomicAdd(D.ticket, 1u);
+        tk = __shfl_sync(FULL, tk, 0);
+        if (tk >= V.n) break;
+        const long long tile = tk;
+        const size_t b = tk;
+        const bool halo = V.owned && !V.owned[b];  // halo brick of a sharded volume: emits nothing, passes the c-vertex through
+        if (halo && tk + 1 < V.n) {               // (the last brick always completes its prefix: the host reads the total there)
+            if (lane == 0) {
+                *(volatile float*)(D.carry + 4 * tile + 3) = 1.f;
+                *(volatile unsigned long long*)(D.count + tile) = 1ull << 62;
+            }
+            continue;
+        }
+        int n_act = 0;
+        int ox = 0, oy = 0, oz = 0;
+        if (!halo) {
+        // ---- stage values and flag rows ----------------------------------------------------------------------------
+        int mynb = -1;
+        if (lane < 8) mynb = V.nbr[b * 8 + lane];
+        { int bx, by, bz; bs_key_brick(V.keys[b], bx, by, bz); ox = bx << 3; oy = by << 3; oz = bz << 3; }
+        {
+            const float4* g4 = reinterpret_cast<const float4*>(V.values + b * 512);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const unsigned q4 = lane + 32 * k, off = q4 * 4;
+                const float4 v = g4[q4];
+                float* d = s.val + (off >> 6) * 81 + ((off >> 3) & 7) * 9 + (off & 7);
+                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < 7; ++it) {  // the 217 halo entries: x = 8 plane (81), y = 8 plane without x = 8 (72), z = 8 plane without x, y = 8 (64)
+            const unsigned i = lane + 32 * it;
+            unsigned x = 8, y = 0, z = 0;
+            if (i < 81) { y = i / 9; z = i % 9; }
+            else if (i < 153) { x = (i - 81) / 9; y = 8; z = (i - 81) % 9; }
+            else { x = (i - 153) >> 3; y = (i - 153) & 7; z = 8; }
+            const int src = __shfl_sync(FULL, mynb, (x >> 3) | ((y >> 3) << 1) | ((z >> 3) << 2));
+            if (i < 217) s.val[x * 81 + y * 9 + z] = src >= 0 ? V.values[(size_t)src * 512 + (((x & 7) << 6) | ((y & 7) << 3) | (z & 7))] : 0.f;
+        }
+        const unsigned char* mbytes = reinterpret_cast<const unsigned char*>(V.masks);  // byte y of word x = the z-row (x, y)
+#pragma unroll
+        for (int it = 0; it < 3; ++it) {
+            const unsigned r = lane + 32 * it;
+            const unsigned x = r < 81 ? r / 9 : 0, y = r < 81 ? r % 9 : 0;
+            const unsigned nbi = (x >> 3) | ((y >> 3) << 1);
+            const int s0 = __shfl_sync(FULL, mynb, nbi), s1 = __shfl_sync(FULL, mynb, nbi | 4);
+            if (r < 81) {
+                const unsigned bo = (x & 7) * 8 + (y & 7);
+                unsigned a = s0 >= 0 ? mbytes[(size_t)s0 * 64 + bo] : 0u;
+                if (s1 >= 0) a |= (unsigned)(mbytes[(size_t)s1 * 64 + bo] & 1u) << 8;
+                s.rowA[r] = (unsigned short)a;
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 3; ++it) {
+            const unsigned r = lane + 32 * it;
+            if (r < 81) {
+                const float* p = s.val + (r / 9) * 81 + (r % 9) * 9;
+                unsigned m = 0;
+#pragma unroll
+                for (int z = 0; z < 9; ++z) m |= (__float_as_uint(p[z]) >> 31) << z;
+                s.rowS[r] = (unsigned short)m;
+            }
+        }
+        __syncwarp();
+        // ---- classify: a cell is a candidate if its 8 corners are active and their signs differ ----------------------
+        unsigned cross[2], cnt[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const unsigned c = lane + 32 * h, x = c >> 3, y = c & 7, r = x * 9 + y;
+            const unsigned a = s.rowA[r] & s.rowA[r + 1] & s.rowA[r + 9] & s.rowA[r + 10];
+            const unsigned sa = s.rowS[r] & s.rowS[r + 1] & s.rowS[r + 9] & s.rowS[r + 10];
+            const unsigned so = s.rowS[r] | s.rowS[r + 1] | s.rowS[r + 9] | s.rowS[r + 10];
+            cross[h] = (a & (a >> 1)) & (so | (so >> 1)) & ~(sa & (sa >> 1)) & 0xFFu;
+            cnt[h] = __popc(cross[h]);
+        }
+        unsigned inc0 = cnt[0], inc1 = cnt[1];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t0 = __shfl_up_sync(FULL, inc0, o), t1 = __shfl_up_sync(FULL, inc1, o);
+            if ((int)lane >= o) { inc0 += t0; inc1 += t1; }
+        }
+        const unsigned tot0 = __shfl_sync(FULL, inc0, 31), tot1 = __shfl_sync(FULL, inc1, 31);
+        n_act = (int)(tot0 + tot1);
+        {
+            unsigned o0 = inc0 - cnt[0], o1 = tot0 + inc1 - cnt[1];
+            for (unsigned m = cross[0]; m; m &= m - 1) s.cells[o0++] = (unsigned short)((lane << 3) | (__ffs(m) - 1));
+            for (unsigned m = cross[1]; m; m &= m - 1) s.cells[o1++] = (unsigned short)(((lane + 32) << 3) | (__ffs(m) - 1));
+        }
+        __syncwarp();
+        }
+        // ---- count: tiling per candidate, triangles per candidate ----------------------------------------------------
+        McfCarry C{f3{0.f, 0.f, 0.f}, false, f3{0.f, 0.f, 0.f}, false};
+        unsigned long long total = 0;
+        for (int base = 0; base < n_act; base += 32) {
+            const int j = base + (int)lane;
+            Cell q; q.T = tables; q.v12 = f3{0.f, 0.f, 0.f};
+            int row = 0, len = 0; bool need_c = false, stale = false;
+            if (j < n_act) {
+                int id;
+                mcf_load_cell(q, s.val, ox, oy, oz, s.cells[j], id);
+                q.cs = tables[MC33_OFF_CASES + 2 * id]; q.cf = tables[MC33_OFF_CASES + 2 * id + 1];
+                row = select_tiling(q, len, need_c, stale);
+                if (need_c) compute_c_vertex(q);
+            }
+            mcf_resolve(q, need_c, stale, C, D, tile, lane);
+            int n = 0;
+            if (len) n = emit_rows<false>(q, vs, nullptr, row, len);
+            if (j < n_act) s.info[j] = (unsigned)row | ((unsigned)len << 14) | ((unsigned)need_c << 21) | ((unsigned)stale << 22) | ((unsigned)n << 23);
+            int sum = n;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
+            total += (unsigned long long)sum;
+        }
+        // ---- publish, look back --------------------------------------------------------------------------------------
+        if (lane == 0) {
+            float* cd = D.carry + 4 * tile;
+            const bool val = C.have_run || C.incoming_known;
+            if (val) { const f3 v = C.have_run ? C.run : C.incoming; *(volatile float*)(cd) = v.x; *(volatile float*)(cd + 1) = v.y; *(volatile float*)(cd + 2) = v.z; __threadfence(); }
+            *(volatile float*)(cd + 3) = val ? 2.f : 1.f;
+            *(volatile unsigned long long*)(D.count + tile) = ((tile == 0 ? 2ull : 1ull) << 62) | total;
+        }
+        unsigned long long excl = 0;
+        if (tile > 0) {
+            for (long long basei = tile - 1;; basei -= 32) {
+                const long long idx = basei - lane;
+                unsigned long long d = 2ull << 62;  // before the first brick: inclusive prefix 0
+                if (idx >= 0) { do { d = ld_vol(D.count + idx); } while ((d >> 62) == 0); }
+                const unsigned pm = __ballot_sync(FULL, (d >> 62) == 2);
+                const int first = pm ? __ffs(pm) - 1 : 31;
+                unsigned long long v = ((int)lane <= first) ? (d & ((1ull << 62) - 1)) : 0ull;
+#pragma unroll
+                for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+                excl += v;
+                if (pm) break;
+            }
+            if (lane == 0) *(volatile unsigned long long*)(D.count + tile) = (2ull << 62) | (excl + total);
+        }
+        // ---- emit ----------------------------------------------------------------------------------------------------
+        if (total == 0 || excl + total > cap_tris) { __syncwarp(); continue; }
+        McfCarry C2{f3{0.f, 0.f, 0.f}, false, C.incoming, C.incoming_known};
+        unsigned long long running = excl;
+        for (int base = 0; base < n_act; base += 32) {
+            const int j = base + (int)lane;
+            Cell q; q.T = tables; q.v12 = f3{0.f, 0.f, 0.f};
+            int row = 0, len = 0, n = 0; bool need_c = false, stale = false;
+            if (j < n_act) {
+                const unsigned inf = s.info[j];
+                row = (int)(inf & 0x3FFFu); len = (int)((inf >> 14) & 0x7Fu); need_c = (inf >> 21) & 1u; stale = (inf >> 22) & 1u; n = (int)(inf >> 23);
+                int id;
+                mcf_load_cell(q, s.val, ox, oy, oz, s.cells[j], id);
+                if (need_c) compute_c_vertex(q);
+            }
+            mcf_resolve(q, need_c, stale, C2, D, tile, lane);
+            int inc = n;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, inc, o); if ((int)lane >= o) inc += t; }
+            if (n) emit_rows<true>(q, vs, out + (running + (unsigned long long)(inc - n)) * 9, row, len);
+            running += (unsigned long long)__shfl_sync(FULL, inc, 31);
+        }
+        __syncwarp();
+    }
+}
+
 __global__ void k_shift_carry(const CarryV12* __restrict__ incl, CarryV12* excl, size_t n) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i < n) excl[i] = i ? incl[i - 1] : CarryV12{0.f, 0.f, 0.f, 0};
@@ -543,6 +788,38 @@ bs_status bs_mc_impl(const bs_volume* v, float voxel_size, const float** d_verts
     if (n) bs_count_launch(), k_mc_neighbours<<<bs_blocks(n * 8, 256), 256, 0, st>>>(v->keys, n, d_nbr);
     VolView V{v->keys, v->values, v->masks, n, v->owned, d_nbr, v->tile8_keys, v->tile8_values, nt8, v->tile128_keys, v->tile128_values, nt128};
     const signed char* tables = (const signed char*)ctx->d_mc33;
+    if (!(nt8 || nt128)) {
+        // single pass: per-brick descriptors + ticket; the output buffer is sized from the previous extraction (or a
+        // guess) and the pass is repeated once with the exact size if it turns out too small
+        unsigned long long* d_desc = nullptr;  // [n] count descriptors, [2n] carry records (4 floats each), 1 ticket word
+        BS_TRY(bs_alloc(ctx, &d_desc, 3 * n + 1));
+        McDesc D{d_desc, reinterpret_cast<float*>(d_desc + n), reinterpret_cast<unsigned*>(d_desc + 3 * n)};
+        static bool carve = false;
+        if (!carve) { cudaFuncSetAttribute(k_mc_fused, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); carve = true; }
+        const unsigned grid = (unsigned)std::min<size_t>((n + MCF_WARPS - 1) / MCF_WARPS, (size_t)ctx->sm_count * 8);
+        unsigned long long n_tris = 0;
+        bs_status s = BS_OK;
+        if (ctx->out_verts_cap == 0) s = bs_ensure_out_verts(ctx, n * 160 * 9);
+        for (int attempt = 0; s == BS_OK && attempt < 2; ++attempt) {
+            BS_CUDA(ctx, cudaMemsetAsync(d_desc, 0, (3 * n + 1) * sizeof(unsigned long long), st));
+            bs_count_launch(), k_mc_fused<<<grid, 32 * MCF_WARPS, 0, st>>>(V, tables, voxel_size, D, ctx->d_out_verts, (unsigned long long)(ctx->out_verts_cap / 9));
+            BS_CUDA(ctx, cudaMemcpyAsync(&n_tris, d_desc + (n - 1), sizeof(n_tris), cudaMemcpyDeviceToHost, st));
+            BS_CUDA(ctx, cudaStreamSynchronize(st));
+            n_tris &= (1ull << 62) - 1;
+            if ((size_t)n_tris * 9 <= ctx->out_verts_cap) break;
+            s = bs_ensure_out_verts(ctx, (size_t)n_tris * 9);  // too small: grow to the exact size and run again
+        }
+        bs_mark(ctx, "mc_emit_ms");
+        bs_free(ctx, d_desc); bs_free(ctx, d_nbr);
+        if (s != BS_OK) return s;
+        BS_CUDA(ctx, cudaGetLastError());
+        bs_marks_end(ctx);
+        bs_stat_add(ctx, "n_bricks", (double)n);
+        bs_stat_add(ctx, "n_out_tris", (double)n_tris);
+        *d_verts = ctx->d_out_verts; *n_verts = (size_t)n_tris * 3;
+        return BS_OK;
+    }
+    // volumes with active tiles (CSG unions): count pass, scan over bricks and tiles in merged order, emit pass
     unsigned *d_counts = nullptr, *d_pos = nullptr; unsigned long long *d_wide = nullptr, *d_off = nullptr;
     BS_TRY(bs_alloc(ctx, &d_counts, n_items)); BS_TRY(bs_alloc(ctx, &d_wide, n_items + 1)); BS_TRY(bs_alloc(ctx, &d_off, n_items + 1));
     const bool tiles = nt8 || nt128;

@@ -417,7 +417,7 @@ def main():
         if "mc_emit_ms" in mc_ms:
             nb = work.get("n_bricks", 0.0)
             by = nb * (2112 + 868) + 36.0 * (n_verts_local / 3.0)
-            rl.append({"kernel": "k_mc<emit> (classify + emit)", "bound": "hbm", "achieved": by / (mc_ms["mc_emit_ms"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+            rl.append({"kernel": "k_mc_fused (stage + classify + MC33 + look-back + emit, one pass)", "bound": "hbm", "achieved": by / (mc_ms["mc_emit_ms"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                        "ms": mc_ms["mc_emit_ms"], "algorithmic": "n_bricks x 2980 B + 36 B x n_out_tris", "traffic": None, "peak_source": hbm_src})
         for r in rl:
             r["frac"] = r["achieved"] / r["peak"]
