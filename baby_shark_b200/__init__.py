@@ -28,6 +28,8 @@ EXPORTS = [
     "bs_volume_union", "bs_volume_subtract", "bs_volume_intersect", "bs_volume_offset",
     "bs_mesh_mc", "bs_mesh_dc", "bs_mesh_mc_device", "bs_mesh_dc_device", "bs_buffer_free",
     "bs_volume_download", "bs_volume_counts", "bs_context_last_stats", "bs_context_copy_out_verts", "bs_context_copy_out_verts_device", "bs_context_set_flag", "bs_kernel_launch_count",
+    "bs_stl_decode", "bs_stl_decode_device", "bs_stl_encode", "bs_stl_encode_device", "bs_mesh_active_voxels", "bs_mesh_active_voxels_device",
+    "bs_merge_points", "bs_merge_points_device", "bs_device_free",
 ]
 
 
@@ -92,6 +94,15 @@ def load_library(path=None):
         "bs_context_copy_out_verts_device": (C.c_int, [vp, vp, sz]),
         "bs_context_set_flag": (C.c_int, [vp, C.c_int, C.c_int]),
         "bs_kernel_launch_count": (C.c_ulonglong, []),
+        "bs_stl_decode": (C.c_int, [vp, vp, sz, pvp, psz]),
+        "bs_stl_decode_device": (C.c_int, [vp, vp, sz, pvp, psz]),
+        "bs_stl_encode": (C.c_int, [vp, vp, sz, pvp, psz]),
+        "bs_stl_encode_device": (C.c_int, [vp, vp, sz, pvp, psz]),
+        "bs_mesh_active_voxels": (C.c_int, [vp, pvp, psz]),
+        "bs_mesh_active_voxels_device": (C.c_int, [vp, pvp, psz]),
+        "bs_merge_points": (C.c_int, [vp, vp, sz, pvp, psz, pvp]),
+        "bs_merge_points_device": (C.c_int, [vp, vp, sz, pvp, psz, pvp]),
+        "bs_device_free": (None, [vp, vp]),
     }
     for name, (res, args) in sigs.items():
         f = getattr(L, name)
@@ -283,9 +294,13 @@ class MeshToVolume:
     def convert(self, mesh):
         """-> Volume, or None where the reference returns None (empty mesh, :58-60)."""
         ctx = self._ctx or Context.default()
-        tris = _as_triangles(mesh)
         h = C.c_void_p()
-        st = load_library().bs_mesh_to_volume(ctx._h, _fp(tris), tris.shape[0], self.voxel_size, self.band_width, C.byref(h))
+        if isinstance(mesh, DeviceTriangles):  # decoded STL: already on the device, no host round trip
+            st = load_library().bs_mesh_to_volume_device(mesh._ctx._h, mesh.ptr, mesh.n_tris, self.voxel_size, self.band_width, C.byref(h))
+            ctx = mesh._ctx
+        else:
+            tris = _as_triangles(mesh)
+            st = load_library().bs_mesh_to_volume(ctx._h, _fp(tris), tris.shape[0], self.voxel_size, self.band_width, C.byref(h))
         if st == BS_ERR_EMPTY_MESH:
             return None
         ctx.check(st)
@@ -399,5 +414,109 @@ class VoxelRemesher:
         return MarchingCubesMesher().with_voxel_size(self.voxel_size).mesh(vol)
 
 
+class DeviceTriangles:
+    """n x 9 f32 triangles resident on the context's device (library-owned): the output of `StlReader`, accepted by
+    `MeshToVolume.convert`."""
+
+    def __init__(self, ptr, n_tris, ctx):
+        self.ptr, self.n_tris, self._ctx = ptr, n_tris, ctx
+
+    def __del__(self):
+        if getattr(self, "ptr", None):
+            load_library().bs_device_free(self._ctx._h, self.ptr)
+            self.ptr = None
+
+    def numpy(self):
+        import ctypes.util  # noqa: F401
+        rt = _cudart()
+        out = np.empty((self.n_tris, 9), np.float32)
+        if self.n_tris:
+            rt.cudaMemcpy(out.ctypes.data_as(C.c_void_p), self.ptr, out.nbytes, 2)
+        return out
+
+
+def _cudart():
+    """libcudart as loaded by libbshark_cuda.so (only used to read DeviceTriangles back in tests)."""
+    global _rt
+    if _rt is None:
+        import glob
+        cands = glob.glob("/usr/local/cuda/lib64/libcudart.so*")
+        _rt = C.CDLL(sorted(cands)[-1])
+        _rt.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    return _rt
+
+
+_rt = None
+
+
+class StlReader:
+    """`io::stl::StlReader` (src/io/stl.rs:14-95): binary STL -> triangles, decoded on the device."""
+
+    def __init__(self, ctx=None):
+        self._ctx = ctx
+
+    def read_from_buffer(self, data):
+        """bytes -> DeviceTriangles; raises BsharkError where the reference returns ReadError (short buffer)."""
+        ctx = self._ctx or Context.default()
+        buf = np.frombuffer(bytes(data), dtype=np.uint8)
+        p, n = C.c_void_p(), C.c_size_t()
+        ctx.check(load_library().bs_stl_decode(ctx._h, buf.ctypes.data_as(C.c_void_p), buf.size, C.byref(p), C.byref(n)))
+        return DeviceTriangles(p, n.value, ctx)
+
+    def read_stl_from_file(self, path):
+        with open(path, "rb") as f:
+            return self.read_from_buffer(f.read())
+
+
+class StlWriter:
+    """`io::stl::StlWriter` (src/io/stl.rs:110-191) for a vertex soup: normals recomputed on the device."""
+
+    def __init__(self, ctx=None):
+        self._ctx = ctx
+
+    def write_to_buffer(self, verts):
+        """(3 n, 3) float32 vertex soup (host) -> bytes"""
+        import torch
+        ctx = self._ctx or Context.default()
+        v = torch.from_numpy(_f32(verts).reshape(-1, 3)).cuda(ctx.device)
+        p, n = C.c_void_p(), C.c_size_t()
+        ctx.check(load_library().bs_stl_encode(ctx._h, C.c_void_p(v.data_ptr()), v.shape[0], C.byref(p), C.byref(n)))
+        out = C.string_at(p, n.value)
+        load_library().bs_buffer_free(p)
+        return out
+
+
+class ActiveVoxelsMesher:
+    """`voxel::meshing::ActiveVoxelsMesher` (src/voxel/meshing/active_voxels.rs:4-22)."""
+
+    def mesh(self, volume):
+        """-> (m, 3) int32 vertices, three consecutive rows per triangle"""
+        p, n = C.c_void_p(), C.c_size_t()
+        volume._ctx.check(load_library().bs_mesh_active_voxels(volume._h, C.byref(p), C.byref(n)))
+        out = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int32)), shape=(max(n.value, 1) * 3,))[: n.value * 3].copy().reshape(-1, 3)
+        load_library().bs_buffer_free(p)
+        return out
+
+
+class IndexedVertices:
+    """`algo::merge_points::IndexedVertices` (src/algo/merge_points.rs:4-9)."""
+
+    def __init__(self, points, indices):
+        self.points, self.indices = points, indices
+
+
+def merge_points(points, ctx=None):
+    """`algo::merge_points::merge_points` (src/algo/merge_points.rs:12-41) on the device."""
+    ctx = ctx or Context.default()
+    pts = _f32(points).reshape(-1, 3)
+    pu, pi, nu = C.c_void_p(), C.c_void_p(), C.c_size_t()
+    ctx.check(load_library().bs_merge_points(ctx._h, pts.ctypes.data_as(C.c_void_p), pts.shape[0], C.byref(pu), C.byref(nu), C.byref(pi)))
+    uniq = np.ctypeslib.as_array(C.cast(pu, C.POINTER(C.c_float)), shape=(max(nu.value, 1) * 3,))[: nu.value * 3].copy().reshape(-1, 3)
+    idx = np.ctypeslib.as_array(C.cast(pi, C.POINTER(C.c_uint32)), shape=(max(pts.shape[0], 1),))[: pts.shape[0]].copy()
+    load_library().bs_buffer_free(pu)
+    load_library().bs_buffer_free(pi)
+    return IndexedVertices(uniq, idx)
+
+
 __all__ = ["Context", "Volume", "MeshToVolume", "VolumeBuilder", "MarchingCubesMesher", "DualContouringMesher",
-           "VoxelRemesher", "MeshingMethod", "BsharkError", "ReferencePanic", "load_library", "EXPORTS", "LIB_PATH"]
+           "VoxelRemesher", "MeshingMethod", "StlReader", "StlWriter", "DeviceTriangles", "ActiveVoxelsMesher", "IndexedVertices", "merge_points", "BsharkError", "ReferencePanic", "load_library", "EXPORTS", "LIB_PATH"]

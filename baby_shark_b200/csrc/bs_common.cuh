@@ -154,4 +154,8 @@ bs_status bs_csg_impl(bs_volume* a, bs_volume* b, int op, bs_volume** out);
 bs_status bs_offset_impl(bs_volume* a, float distance, bs_volume** out);
 bs_status bs_from_voxels_impl(bs_context* ctx, const int32_t* d_ijk, const float* d_values, size_t m, float voxel_size,
                               bs_volume** out);
+bs_status bs_stl_decode_impl(bs_context* ctx, const unsigned char* d_stl, size_t n_bytes, float** d_tris, size_t* n_tris);
+bs_status bs_stl_encode_impl(bs_context* ctx, const float* d_verts, size_t n_verts, unsigned char** d_stl, size_t* n_bytes);
+bs_status bs_active_voxels_impl(const bs_volume* v, int** d_verts, size_t* n_verts);
+bs_status bs_merge_points_impl(bs_context* ctx, const float* d_pts, size_t n, float** d_unique, size_t* n_unique, unsigned** d_indices);
 bs_status bs_builder_impl(bs_context* ctx, int kind, float voxel_size, const float* p, bs_volume** out);

@@ -104,6 +104,16 @@ void bs_raw_free(bs_context* ctx, void* p) {
     if (ctx->cache_free_bytes > ((size_t)48 << 30)) bs_cache_release(ctx);  // varying workloads: do not hoard HBM
 }
 
+template <class T> static bs_status to_pinned(bs_context* c, const T* d_src, size_t n, T** out) {
+    *out = nullptr;
+    T* h = nullptr;
+    BS_CUDA(c, cudaMallocHost((void**)&h, (n ? n : 1) * sizeof(T)));
+    if (n && cudaMemcpyAsync(h, d_src, n * sizeof(T), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) { cudaFreeHost(h); return bs_fail(c, BS_ERR_CUDA, "device to host copy failed"); }
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) { cudaFreeHost(h); return bs_fail(c, BS_ERR_CUDA, "device to host copy failed"); }
+    *out = h;
+    return BS_OK;
+}
+
 extern "C" {
 
 bs_status bs_context_create(int device, bs_context** out) {
@@ -209,6 +219,72 @@ bs_status bs_volume_clone(const bs_volume* v, bs_volume** out) {
 }
 
 void bs_buffer_free(void* p) { if (p) cudaFreeHost(p); }
+
+// ---- data formats either side of the path (bs_io.cu) ---------------------------------------------------------------------------
+void bs_device_free(bs_context* ctx, void* d_ptr) { if (ctx && d_ptr) { cudaSetDevice(ctx->device); bs_raw_free(ctx, d_ptr); } }
+bs_status bs_stl_decode_device(bs_context* ctx, const unsigned char* d_stl, size_t n_bytes, float** d_tris, size_t* n_tris) {
+    if (!ctx || !d_tris || !n_tris || (!d_stl && n_bytes)) return BS_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    return bs_stl_decode_impl(ctx, d_stl, n_bytes, d_tris, n_tris);
+}
+bs_status bs_stl_decode(bs_context* ctx, const unsigned char* stl, size_t n_bytes, float** d_tris, size_t* n_tris) {
+    if (!ctx || !d_tris || !n_tris || (!stl && n_bytes)) return BS_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    unsigned char* d = nullptr;
+    BS_TRY(bs_alloc(ctx, &d, n_bytes + 4));
+    if (n_bytes && cudaMemcpyAsync(d, stl, n_bytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { bs_free(ctx, d); return bs_fail(ctx, BS_ERR_CUDA, "host to device copy failed"); }
+    const bs_status s = bs_stl_decode_impl(ctx, d, n_bytes, d_tris, n_tris);
+    bs_free(ctx, d);
+    return s;
+}
+bs_status bs_stl_encode_device(bs_context* ctx, const float* d_verts, size_t n_verts, unsigned char** d_stl, size_t* n_bytes) {
+    if (!ctx || !d_stl || !n_bytes || (!d_verts && n_verts)) return BS_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    return bs_stl_encode_impl(ctx, d_verts, n_verts, d_stl, n_bytes);
+}
+bs_status bs_stl_encode(bs_context* ctx, const float* d_verts, size_t n_verts, unsigned char** stl, size_t* n_bytes) {
+    if (!ctx || !stl || !n_bytes || (!d_verts && n_verts)) return BS_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    unsigned char* d = nullptr;
+    BS_TRY(bs_stl_encode_impl(ctx, d_verts, n_verts, &d, n_bytes));
+    const bs_status s = to_pinned(ctx, d, *n_bytes, stl);
+    bs_free(ctx, d);
+    return s;
+}
+bs_status bs_mesh_active_voxels_device(const bs_volume* v, int32_t** d_verts, size_t* n_verts) {
+    if (!v || !d_verts || !n_verts) return BS_ERR_INVALID;
+    cudaSetDevice(v->ctx->device);
+    return bs_active_voxels_impl(v, d_verts, n_verts);
+}
+bs_status bs_mesh_active_voxels(const bs_volume* v, int32_t** verts, size_t* n_verts) {
+    if (!v || !verts || !n_verts) return BS_ERR_INVALID;
+    cudaSetDevice(v->ctx->device);
+    int* d = nullptr;
+    BS_TRY(bs_active_voxels_impl(v, &d, n_verts));
+    const bs_status s = to_pinned(v->ctx, d, *n_verts * 3, verts);
+    bs_free(v->ctx, d);
+    return s;
+}
+bs_status bs_merge_points_device(bs_context* ctx, const float* d_points, size_t n, float** d_unique, size_t* n_unique, uint32_t** d_indices) {
+    if (!ctx || !d_unique || !n_unique || !d_indices || (!d_points && n)) return BS_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    return bs_merge_points_impl(ctx, d_points, n, d_unique, n_unique, d_indices);
+}
+bs_status bs_merge_points(bs_context* ctx, const float* points, size_t n, float** unique, size_t* n_unique, uint32_t** indices) {
+    if (!ctx || !unique || !n_unique || !indices || (!points && n)) return BS_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    float* d_p = nullptr; float* d_u = nullptr; unsigned* d_i = nullptr;
+    BS_TRY(bs_alloc(ctx, &d_p, n * 3));
+    if (n && cudaMemcpyAsync(d_p, points, n * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { bs_free(ctx, d_p); return bs_fail(ctx, BS_ERR_CUDA, "host to device copy failed"); }
+    bs_status s = bs_merge_points_impl(ctx, d_p, n, &d_u, n_unique, &d_i);
+    bs_free(ctx, d_p);
+    if (s != BS_OK) return s;
+    s = to_pinned(ctx, d_u, *n_unique * 3, unique);
+    if (s == BS_OK) { s = to_pinned(ctx, d_i, n, indices); if (s != BS_OK) { cudaFreeHost(*unique); *unique = nullptr; } }
+    bs_free(ctx, d_u); bs_free(ctx, d_i);
+    return s;
+}
+
 
 bs_status bs_volume_download(const bs_volume* v, int32_t** brick_ijk, float** values, uint64_t** masks, size_t* n_bricks,
                              int32_t** tile_ijk, int32_t** tile_size, float** tile_values, size_t* n_tiles) {

@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-scale", type=float, default=0.1875, help="scale of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--io", action="store_true", help="time the rows either side of the path on the --config mesh: STL decode / encode, merge_points, ActiveVoxelsMesher")
     ap.add_argument("--ops", action="store_true", help="time the CSG (config 2) / offset (3) / dual contouring (4) rows instead of the remesh")
     return ap.parse_args()
 
@@ -139,6 +140,88 @@ def run_ops(args):
                       "stage_ms": stages, "work": work, "rooflines": rl, "roofline": max(rl, key=lambda r: r["ms"]) if rl else None}))
 
 
+def run_io(args):
+    """--io: STL bytes -> device triangles -> volume -> MC soup -> {STL bytes, merged vertices}, plus ActiveVoxelsMesher;
+    everything resident in HBM, per-kernel device times and HBM rooflines in one JSON line."""
+    import torch
+    import baby_shark_b200 as B
+    L = B.load_library()
+    ctx = B.Context(0)
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        hbm_peak = 6650.0
+    tris, vs, desc = workload(args.config, args.scale)
+    n = tris.shape[0]
+    rec = np.zeros((n, 50), np.uint8)
+    rec[:, 12:48] = tris.view(np.uint8).reshape(n, 36)
+    stl = torch.from_numpy(np.concatenate([np.zeros(80, np.uint8), np.frombuffer(np.uint32(n).tobytes(), np.uint8), rec.reshape(-1)])).cuda()
+    del rec
+    stages, rl = {}, []
+
+    def avg(fn, key):
+        for _ in range(args.warmup):
+            fn()
+        acc = 0.0
+        for _ in range(args.steps):
+            fn()
+            acc += ctx.last_stats()[key] / args.steps
+        return acc
+
+    keep = {}
+
+    def decode():
+        if keep.get("tris"):
+            L.bs_device_free(ctx._h, keep["tris"])
+        p, m = C.c_void_p(), C.c_size_t()
+        ctx.check(L.bs_stl_decode_device(ctx._h, C.c_void_p(stl.data_ptr()), stl.numel(), C.byref(p), C.byref(m)))
+        keep["tris"], keep["n"] = p, m.value
+    stages["stl_decode_ms"] = avg(decode, "stl_decode_ms")
+    rl.append({"kernel": "k_stl_decode", "ms": stages["stl_decode_ms"], "algorithmic": "86 B x %d triangles" % n, "bytes": 86.0 * n})
+    h = C.c_void_p()
+    ctx.check(L.bs_mesh_to_volume_device(ctx._h, keep["tris"], n, vs, 0, C.byref(h)))
+    dv, nv = C.c_void_p(), C.c_size_t()
+    ctx.check(L.bs_mesh_mc_device(h, vs, C.byref(dv), C.byref(nv)))
+    n_out = nv.value // 3
+
+    def encode():
+        p, m = C.c_void_p(), C.c_size_t()
+        ctx.check(L.bs_stl_encode_device(ctx._h, dv, nv.value, C.byref(p), C.byref(m)))
+        L.bs_device_free(ctx._h, p)
+    stages["stl_encode_ms"] = avg(encode, "stl_encode_ms")
+    rl.append({"kernel": "k_stl_encode", "ms": stages["stl_encode_ms"], "algorithmic": "86 B x %d triangles" % n_out, "bytes": 86.0 * n_out})
+    uniq = {}
+
+    def merge():
+        pu, pi, nu = C.c_void_p(), C.c_void_p(), C.c_size_t()
+        ctx.check(L.bs_merge_points_device(ctx._h, dv, nv.value, C.byref(pu), C.byref(nu), C.byref(pi)))
+        uniq["n"] = nu.value
+        L.bs_device_free(ctx._h, pu)
+        L.bs_device_free(ctx._h, pi)
+    stages["merge_points_ms"] = avg(merge, "merge_points_ms")
+    rl.append({"kernel": "k_mp_insert + k_mp_first + scan + k_mp_emit", "ms": stages["merge_points_ms"],
+               "algorithmic": "16 B x %d points + 12 B x %d unique" % (nv.value, uniq["n"]), "bytes": 16.0 * nv.value + 12.0 * uniq["n"]})
+    faces = {}
+
+    def boxes():
+        p, m = C.c_void_p(), C.c_size_t()
+        ctx.check(L.bs_mesh_active_voxels_device(h, C.byref(p), C.byref(m)))
+        faces["n"] = m.value // 6
+        L.bs_device_free(ctx._h, p)
+    stages["active_voxels_ms"] = avg(boxes, "active_voxels_ms")
+    nb = ctx.last_stats().get("n_bricks", 0.0)
+    rl.append({"kernel": "k_active_voxels<count> + scan + k_active_voxels<emit>", "ms": stages["active_voxels_ms"],
+               "algorithmic": "72 B x %d exposed faces (+ 7 x 64 B of masks per brick, twice)" % faces["n"], "bytes": 72.0 * faces["n"]})
+    L.bs_volume_free(h)
+    for r in rl:
+        r.update({"bound": "hbm", "achieved": r.pop("bytes") / (r["ms"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "traffic": None})
+        r["frac"] = r["achieved"] / r["peak"]
+    print(json.dumps({"metric": "STL decode + encode + merge_points + ActiveVoxelsMesher on the --config mesh", "value": sum(stages.values()), "unit": "ms", "n_gpus": 1,
+                      "steps": args.steps, "warmup": args.warmup, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "u8/f32/u32", "data": "synthetic",
+                      "config": {"workload": "config %d: %s, scale %g" % (args.config, desc, args.scale), "n_triangles": int(n), "n_out_triangles": int(n_out), "n_unique_vertices": uniq["n"]},
+                      "stage_ms": stages, "rooflines": rl, "roofline": max(rl, key=lambda r: r["ms"])}))
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -230,6 +313,10 @@ def main():
     if args.ops:
         if rank == 0:
             run_ops(args)
+        return
+    if args.io:
+        if rank == 0:
+            run_io(args)
         return
 
     import torch

@@ -7,6 +7,7 @@
 #pragma once
 #include <array>
 #include <cstddef>
+#include <cstdint>
 #include <optional>
 #include <stdexcept>
 #include <string>
@@ -158,6 +159,86 @@ private:
 };
 
 }  // namespace voxel
+
+// io::stl (src/io/stl.rs): binary STL decoded / encoded on the device
+namespace io {
+// n x 9 f32 triangles resident on the device (library-owned); feeds MeshToVolume::convert without a host round trip
+class DeviceTriangles {
+public:
+    DeviceTriangles(float* d, std::size_t n, Context* c) : d_(d), n_(n), ctx_(c) {}
+    DeviceTriangles(DeviceTriangles&& o) noexcept : d_(std::exchange(o.d_, nullptr)), n_(o.n_), ctx_(o.ctx_) {}
+    DeviceTriangles(const DeviceTriangles&) = delete;
+    ~DeviceTriangles() { if (d_) bs_device_free(ctx_->get(), d_); }
+    const float* data() const { return d_; }
+    std::size_t size() const { return n_; }
+    Context& context() const { return *ctx_; }
+private:
+    float* d_; std::size_t n_; Context* ctx_;
+};
+class StlReader {  // src/io/stl.rs:14-95
+public:
+    explicit StlReader(Context& c = Context::global()) : ctx_(&c) {}
+    // throws Error where the reference returns Err(ReadError) (buffer shorter than the header announces)
+    DeviceTriangles read_from_buffer(const unsigned char* bytes, std::size_t n_bytes) {
+        float* d = nullptr; std::size_t n = 0;
+        ctx_->check(bs_stl_decode(ctx_->get(), bytes, n_bytes, &d, &n));
+        return DeviceTriangles(d, n, ctx_);
+    }
+private:
+    Context* ctx_;
+};
+class StlWriter {  // src/io/stl.rs:110-191, for the vertex soup of the last *_device extraction or any device soup
+public:
+    explicit StlWriter(Context& c = Context::global()) : ctx_(&c) {}
+    std::vector<unsigned char> write_to_buffer(const float* d_verts, std::size_t n_verts) {
+        unsigned char* h = nullptr; std::size_t n = 0;
+        ctx_->check(bs_stl_encode(ctx_->get(), d_verts, n_verts, &h, &n));
+        std::vector<unsigned char> out(h, h + n);
+        bs_buffer_free(h);
+        return out;
+    }
+private:
+    Context* ctx_;
+};
+}  // namespace io
+
+namespace voxel {
+inline std::optional<Volume> convert(MeshToVolume& m2v, const io::DeviceTriangles& t, float voxel_size, long band = 0) {
+    (void)m2v;
+    bs_volume* h = nullptr;
+    const bs_status s = bs_mesh_to_volume_device(t.context().get(), t.data(), t.size(), voxel_size, band, &h);
+    if (s == BS_ERR_EMPTY_MESH) return std::nullopt;
+    t.context().check(s);
+    return Volume(h, &t.context());
+}
+// voxel::meshing::ActiveVoxelsMesher (src/voxel/meshing/active_voxels.rs:4-22); the reference returns Vector3<isize>
+class ActiveVoxelsMesher {
+public:
+    std::vector<std::array<long, 3>> mesh(const Volume& volume) {
+        int32_t* h = nullptr; std::size_t n = 0;
+        volume.context().check(bs_mesh_active_voxels(volume.raw(), &h, &n));
+        std::vector<std::array<long, 3>> out(n);
+        for (std::size_t i = 0; i < n; ++i) out[i] = {h[3 * i], h[3 * i + 1], h[3 * i + 2]};
+        bs_buffer_free(h);
+        return out;
+    }
+};
+}  // namespace voxel
+
+namespace algo {
+// algo::merge_points (src/algo/merge_points.rs:4-41)
+struct IndexedVertices { std::vector<Vec3f> points; std::vector<std::size_t> indices; };
+inline IndexedVertices merge_points(const std::vector<Vec3f>& points, Context& c = Context::global()) {
+    float* u = nullptr; uint32_t* idx = nullptr; std::size_t nu = 0;
+    c.check(bs_merge_points(c.get(), points.empty() ? nullptr : points[0].data(), points.size(), &u, &nu, &idx));
+    IndexedVertices out;
+    out.points.resize(nu);
+    for (std::size_t i = 0; i < nu; ++i) out.points[i] = {u[3 * i], u[3 * i + 1], u[3 * i + 2]};
+    out.indices.assign(idx, idx + points.size());
+    bs_buffer_free(u); bs_buffer_free(idx);
+    return out;
+}
+}  // namespace algo
 
 namespace remeshing {
 enum class MeshingMethod { FeaturePreserving, Manifold };  // remeshing/voxel.rs:10-15

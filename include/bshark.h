@@ -109,6 +109,33 @@ bs_status bs_mesh_mc_device(const bs_volume* v, float voxel_size, const float** 
 bs_status bs_mesh_dc_device(const bs_volume* v, float voxel_size, const float** d_verts, size_t* n_verts);
 void bs_buffer_free(void* p);
 
+/* ---- data formats either side of the path ---------------------------------------------------------------- */
+/* StlReader::read_from_buffer (src/io/stl.rs:65-95): binary STL bytes (80-byte header, u32 count, 50-byte records)
+ * -> count x 9 floats in device memory, ready for bs_mesh_to_volume_device. *d_tris is library-owned device memory
+ * (bs_device_free). A buffer shorter than its header announces is BS_ERR_INVALID (the reference: ReadError). */
+bs_status bs_stl_decode(bs_context* ctx, const unsigned char* stl, size_t n_bytes, float** d_tris, size_t* n_tris);
+bs_status bs_stl_decode_device(bs_context* ctx, const unsigned char* d_stl, size_t n_bytes, float** d_tris,
+                               size_t* n_tris);
+/* StlWriter::write_to_buffer (src/io/stl.rs:143-191) for a vertex soup on the device (e.g. the result of
+ * bs_mesh_mc_device): zero header, count, per face the recomputed normal (zeros if degenerate), the three vertices
+ * and a zero attribute. *stl is library-owned host memory (bs_buffer_free), *d_stl device memory (bs_device_free). */
+bs_status bs_stl_encode(bs_context* ctx, const float* d_verts, size_t n_verts, unsigned char** stl, size_t* n_bytes);
+bs_status bs_stl_encode_device(bs_context* ctx, const float* d_verts, size_t n_verts, unsigned char** d_stl,
+                               size_t* n_bytes);
+/* ActiveVoxelsMesher::mesh (src/voxel/meshing/active_voxels.rs:12-22): two triangles per exposed voxel face, integer
+ * vertices (the reference returns Vector3<isize>), 3 consecutive xyz per triangle, in the reference's order.
+ * BS_ERR_UNSUPPORTED for volumes with active tiles. Host result: bs_buffer_free; device result: bs_device_free. */
+bs_status bs_mesh_active_voxels(const bs_volume* v, int32_t** verts, size_t* n_verts);
+bs_status bs_mesh_active_voxels_device(const bs_volume* v, int32_t** d_verts, size_t* n_verts);
+/* merge_points (src/algo/merge_points.rs:12-41): exactly coincident points share an index; unique points keep
+ * first-occurrence order. unique = n_unique x 3 floats, indices = n entries. */
+bs_status bs_merge_points(bs_context* ctx, const float* points, size_t n, float** unique, size_t* n_unique,
+                          uint32_t** indices);
+bs_status bs_merge_points_device(bs_context* ctx, const float* d_points, size_t n, float** d_unique,
+                                 size_t* n_unique, uint32_t** d_indices);
+/* Frees device memory returned by the *_device entry points above. */
+void bs_device_free(bs_context* ctx, void* d_ptr);
+
 /* ---- parity / debug -------------------------------------------------------------------------------- */
 /* Leaves in the reference's visit order (root map order, ascending child offsets).  brick_ijk = leaf
  * origins (n x 3), values = n x 512 in the reference's leaf layout (x<<6 | y<<3 | z, leaf_node/mod.rs:29-36),

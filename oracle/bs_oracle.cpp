@@ -9,7 +9,7 @@
 // everything else (winding numbers, tree build, MC33 ambiguous branches, DC, internal/root CSG,
 // builders) is "parity unpinned by the reference": the reference has no tests for it and cannot be
 // built here (no Rust toolchain), so this restatement is the only pin.
-#include "bso_meshing.h"
+#include "bso_io.h"
 #include <chrono>
 #include <stdexcept>
 #include <cstdio>
@@ -121,6 +121,34 @@ void bso_winding_numbers(const float* tris, size_t n, const float* pts, size_t m
     }
     if (counters) { counters[0] = wn.n_visit; counters[1] = wn.n_far; counters[2] = wn.n_exact; counters[3] = wn.nodes.size(); }
 }
+// data formats either side of the path
+int bso_stl_decode(const uint8_t* bytes, size_t n_bytes, float** tris, size_t* n_tris) {
+    std::vector<float> t;
+    if (!stl_decode(bytes, n_bytes, t)) { *tris = nullptr; *n_tris = 0; return 1; }
+    *n_tris = t.size() / 9;
+    *tris = (float*)std::malloc(std::max<size_t>(1, t.size()) * sizeof(float));
+    std::memcpy(*tris, t.data(), t.size() * sizeof(float));
+    return 0;
+}
+void bso_stl_encode(const float* verts, size_t n_tris, uint8_t* out /* 84 + 50 n_tris bytes */) {
+    std::vector<uint8_t> o; stl_encode(verts, n_tris, o);
+    std::memcpy(out, o.data(), o.size());
+}
+size_t bso_active_voxels(void* v, int32_t** out) {
+    ActiveVoxels av{((Volume*)v)->grid, {}};
+    ((Volume*)v)->grid->visit_leafs(av);
+    *out = (int32_t*)std::malloc(std::max<size_t>(1, av.out.size()) * 3 * sizeof(int32_t));
+    for (size_t i = 0; i < av.out.size(); ++i) { (*out)[3 * i] = (int32_t)av.out[i].x; (*out)[3 * i + 1] = (int32_t)av.out[i].y; (*out)[3 * i + 2] = (int32_t)av.out[i].z; }
+    return av.out.size();
+}
+size_t bso_merge_points(const float* pts, size_t n, float* unique /* up to 3 n */, uint32_t* indices /* n */) {
+    std::vector<float> u; std::vector<uint32_t> idx;
+    merge_points(pts, n, u, idx);
+    std::memcpy(unique, u.data(), u.size() * sizeof(float));
+    std::memcpy(indices, idx.data(), idx.size() * sizeof(uint32_t));
+    return u.size() / 3;
+}
+void bso_free(void* p) { std::free(p); }
 float bso_compute_distance(float a1, float a2, float a3, float h) { return compute_distance(a1, a2, a3, h); }
 
 // ------------------------------------------------------------------------------------------------

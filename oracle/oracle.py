@@ -80,6 +80,15 @@ def lib():
         L.bso_compute_distance.restype = C.c_float
         L.bso_compute_distance.argtypes = [C.c_float] * 4
         L.bso_selftest.restype = C.c_int
+        u8p = C.POINTER(C.c_uint8)
+        L.bso_stl_decode.argtypes = [u8p, C.c_size_t, C.POINTER(fp), C.POINTER(C.c_size_t)]
+        L.bso_stl_encode.argtypes = [fp, C.c_size_t, u8p]
+        L.bso_stl_encode.restype = None
+        L.bso_active_voxels.restype = C.c_size_t
+        L.bso_active_voxels.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_int32))]
+        L.bso_merge_points.restype = C.c_size_t
+        L.bso_merge_points.argtypes = [fp, C.c_size_t, fp, C.POINTER(C.c_uint32)]
+        L.bso_free.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -239,6 +248,43 @@ def winding_numbers(tris, pts, beta=2.0):
     cnt = (C.c_uint64 * 4)()
     lib().bso_winding_numbers(_fp(tris), tris.shape[0], _fp(pts), pts.shape[0], beta, _fp(out), cnt)
     return out, dict(visit=cnt[0], far=cnt[1], exact=cnt[2], nodes=cnt[3])
+
+
+def stl_decode(data):
+    """io/stl.rs StlReader: bytes -> (n, 9) float32 triangles, or None on a short buffer (the reference returns ReadError)."""
+    buf = np.frombuffer(bytes(data), dtype=np.uint8)
+    out, n = C.POINTER(C.c_float)(), C.c_size_t()
+    if lib().bso_stl_decode(buf.ctypes.data_as(C.POINTER(C.c_uint8)), buf.size, C.byref(out), C.byref(n)):
+        return None
+    a = np.ctypeslib.as_array(out, shape=(max(1, n.value * 9),))[: n.value * 9].copy().reshape(-1, 9)
+    lib().bso_free(out)
+    return a
+
+
+def stl_encode(verts):
+    """io/stl.rs StlWriter on a triangle soup ((3 n, 3) float32 vertices) -> bytes."""
+    v = _f32(verts).reshape(-1, 9)
+    out = np.zeros(84 + 50 * v.shape[0], np.uint8)
+    lib().bso_stl_encode(_fp(v), v.shape[0], out.ctypes.data_as(C.POINTER(C.c_uint8)))
+    return out.tobytes()
+
+
+def active_voxels(vol):
+    """ActiveVoxelsMesher::mesh -> (m, 3) int32 vertices, three consecutive rows per triangle."""
+    out = C.POINTER(C.c_int32)()
+    n = lib().bso_active_voxels(vol._h, C.byref(out))
+    a = np.ctypeslib.as_array(out, shape=(max(1, n * 3),))[: n * 3].copy().reshape(-1, 3)
+    lib().bso_free(out)
+    return a
+
+
+def merge_points(points):
+    """algo::merge_points -> (unique (k, 3) float32 in first-occurrence order, indices (n,) uint32)."""
+    p = _f32(points).reshape(-1, 3)
+    uniq = np.zeros((max(1, p.shape[0]), 3), np.float32)
+    idx = np.zeros(max(1, p.shape[0]), np.uint32)
+    k = lib().bso_merge_points(_fp(p), p.shape[0], _fp(uniq), idx.ctypes.data_as(C.POINTER(C.c_uint32)))
+    return uniq[:k].copy(), idx[: p.shape[0]].copy()
 
 
 def selftest():

@@ -3,6 +3,7 @@
 //   src/remeshing/voxel.rs:105-112   unit cube @0.1 -> faces > 0
 //   examples/dual_contouring.rs      cuboid.subtract(sphere) -> DC gives a mesh
 #include <cstdio>
+#include <cstring>
 #include "baby_shark.hpp"
 using namespace baby_shark;
 
@@ -37,6 +38,25 @@ int main() {
         try { auto u = builder.sphere(0.6f, {1.5f, 0.3f, 0.2f}).union_(builder.sphere(4.0f, {0.1f, 0.2f, 0.3f})); voxel::DualContouringMesher().with_voxel_size(0.2f).mesh(u); }
         catch (const Panic&) { panicked = true; }
         CHECK(panicked);
+    }
+    {   // io::stl + ActiveVoxelsMesher + merge_points on the unit-cube remesh
+        std::vector<unsigned char> stl(84 + 12 * 50, 0);
+        stl[80] = 12;
+        for (int t = 0; t < 12; ++t) std::memcpy(&stl[84 + 50 * t + 12], BOX2 + 9 * t, 36);
+        auto tris = io::StlReader().read_from_buffer(stl.data(), stl.size());
+        CHECK(tris.size() == 12);
+        voxel::MeshToVolume m2v;
+        auto vol = voxel::convert(m2v, tris, 0.2f);
+        CHECK(vol.has_value());
+        auto soup = voxel::MarchingCubesMesher().with_voxel_size(0.2f).mesh(*vol);
+        auto merged = algo::merge_points(soup);
+        CHECK(merged.indices.size() == soup.size() && merged.points.size() * 3 < soup.size());
+        CHECK((long)merged.points.size() - (long)soup.size() / 2 + (long)soup.size() / 3 == 2);  // closed genus-0 surface
+        auto boxes = voxel::ActiveVoxelsMesher().mesh(*vol);
+        CHECK(boxes.size() > 0 && boxes.size() % 6 == 0);
+        bool failed = false;
+        try { io::StlReader().read_from_buffer(stl.data(), stl.size() - 1); } catch (const Error&) { failed = true; }
+        CHECK(failed);
     }
     std::printf("mirror ok\n");
     return 0;

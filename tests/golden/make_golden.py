@@ -4,6 +4,7 @@ only: /root/reference does not exist on the GPU box).
 
   box2_tris.npy, box_tris.npy   the 12 triangles of assets/box2.stl / assets/box.stl as [n,9] f32 in file order
                                 (vertex order matters: it fixes the subdivision direction, mesh_to_volume.rs:90-91)
+  box.stl                       assets/box.stl byte for byte (684 bytes): the STL reader's known input (io/stl.rs)
   bunny_tris.npz                assets/bunny.stl (13 000 triangles), compressed
   reference_known_answers.json  the known answers the reference's own tests hold for this path plus the
                                 survey-derived intermediates, with their source lines
@@ -24,6 +25,7 @@ def read_binary_stl(path):  # io/stl.rs:32-95: 80 B header, u32 count, 50 B reco
 
 np.save(os.path.join(OUT, "box2_tris.npy"), read_binary_stl(os.path.join(REF, "assets/box2.stl")))
 np.save(os.path.join(OUT, "box_tris.npy"), read_binary_stl(os.path.join(REF, "assets/box.stl")))
+open(os.path.join(OUT, "box.stl"), "wb").write(open(os.path.join(REF, "assets/box.stl"), "rb").read())
 np.savez_compressed(os.path.join(OUT, "bunny_tris.npz"), tris=read_binary_stl(os.path.join(REF, "assets/bunny.stl")))
 json.dump({
     "test_volume_offset": {"source": "src/voxel/volume/mod.rs:134-152", "mesh": "box2_tris.npy", "voxel_size": 0.2,

@@ -86,3 +86,32 @@ def test_offset_roundtrip_in_band(oracle):
     r0 = np.linalg.norm(v0 - 0.5, axis=1).mean()
     r1 = np.linalg.norm(v1 - 0.5, axis=1).mean()
     assert abs(r0 - r1) < 0.5 * vs
+
+
+def test_stl_codec_and_reference_asset(oracle, box):
+    # io/stl.rs: the reader ignores header / normals / attributes; assets/box.stl decodes to the golden triangles
+    import os
+    data = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "box.stl"), "rb").read()
+    t = oracle.stl_decode(data)
+    assert np.array_equal(t, box.reshape(-1, 9))
+    assert oracle.stl_decode(data[:-1]) is None
+    out = oracle.stl_encode(t.reshape(-1, 3))
+    assert len(out) == len(data) and out[:80] == b"\0" * 80 and out[80:84] == data[80:84]
+    assert np.array_equal(oracle.stl_decode(out), t)
+    # the writer recomputes unit normals (box.stl stores the same ones)
+    n_out = np.frombuffer(out, np.uint8)[84:].reshape(-1, 50)[:, :12].copy().view(np.float32)
+    n_in = np.frombuffer(data, np.uint8)[84:].reshape(-1, 50)[:, :12].copy().view(np.float32)
+    assert np.allclose(np.linalg.norm(n_out, axis=1), 1.0, atol=1e-6) and np.allclose(n_out, n_in, atol=1e-6)
+
+
+def test_active_voxels_and_merge_points_invariants(oracle):
+    # one voxel: 6 exposed faces x 2 triangles; a 2-voxel bar hides the shared face
+    v1 = oracle.from_voxels(np.int32([[3, 4, 5]]), np.float32([0.1]), 1.0)
+    a = oracle.active_voxels(v1)
+    assert a.shape == (36, 3) and a.min(0).tolist() == [3, 4, 5] and a.max(0).tolist() == [4, 5, 6]
+    assert a[:6].tolist() == [[3, 4, 6], [4, 5, 6], [3, 5, 6], [3, 4, 6], [4, 4, 6], [4, 5, 6]]  # the top face comes first (active_voxels.rs:45-56)
+    v2 = oracle.from_voxels(np.int32([[7, 0, 0], [8, 0, 0]]), np.float32([0.1, 0.2]), 1.0)  # across a leaf boundary
+    assert oracle.active_voxels(v2).shape == (60, 3)
+    uq, idx = oracle.merge_points(a.astype(np.float32))
+    assert uq.shape == (8, 3) and idx.max() == 7 and np.array_equal(uq[idx], a.astype(np.float32))
+    assert idx[:3].tolist() == [0, 1, 2]  # first-occurrence order
