@@ -7,6 +7,7 @@ use std::os::raw::{c_char, c_float, c_int, c_void};
 pub type bs_status = c_int;
 pub const BS_OK: bs_status = 0;
 pub const BS_ERR_EMPTY_MESH: bs_status = 1;
+pub const BS_ERR_INVALID: bs_status = 3;
 pub const BS_ERR_REFERENCE_PANICS: bs_status = 4;
 
 extern "C" {
@@ -30,4 +31,10 @@ extern "C" {
     pub fn bs_mesh_dc_device(v: *const bs_volume, voxel_size: c_float, d_verts: *mut *const c_float, n_verts: *mut usize) -> bs_status;
     pub fn bs_context_copy_out_verts(ctx: *mut bs_context, dst: *mut c_float, n_floats: usize) -> bs_status;
     pub fn bs_buffer_free(p: *mut c_void);
+    pub fn bs_device_free(ctx: *mut bs_context, d_ptr: *mut c_void);
+    pub fn bs_mesh_to_volume_device(ctx: *mut bs_context, d_tris: *const c_float, n_tris: usize, voxel_size: c_float, band_width: i64, out: *mut *mut bs_volume) -> bs_status;
+    pub fn bs_stl_decode(ctx: *mut bs_context, stl: *const u8, n_bytes: usize, d_tris: *mut *mut c_float, n_tris: *mut usize) -> bs_status;
+    pub fn bs_stl_encode(ctx: *mut bs_context, d_verts: *const c_float, n_verts: usize, stl: *mut *mut u8, n_bytes: *mut usize) -> bs_status;
+    pub fn bs_mesh_active_voxels(v: *const bs_volume, verts: *mut *mut i32, n_verts: *mut usize) -> bs_status;
+    pub fn bs_merge_points(ctx: *mut bs_context, points: *const c_float, n: usize, unique: *mut *mut c_float, n_unique: *mut usize, indices: *mut *mut u32) -> bs_status;
 }

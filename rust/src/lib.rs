@@ -136,6 +136,52 @@ impl DualContouringMesher {
     }
 }
 
+/// voxel::meshing::ActiveVoxelsMesher (src/voxel/meshing/active_voxels.rs:4-22)
+#[derive(Default)]
+pub struct ActiveVoxelsMesher;
+impl ActiveVoxelsMesher {
+    pub fn mesh(&mut self, volume: &Volume) -> Vec<Vector3<isize>> {
+        let (mut p, mut n) = (ptr::null_mut(), 0usize);
+        check(unsafe { ffi::bs_mesh_active_voxels(volume.h, &mut p, &mut n) });
+        let s = unsafe { std::slice::from_raw_parts(p, n * 3) };
+        let out = s.chunks_exact(3).map(|c| Vector3::new(c[0] as isize, c[1] as isize, c[2] as isize)).collect();
+        unsafe { ffi::bs_buffer_free(p as *mut _) };
+        out
+    }
+}
+
+/// algo::merge_points (src/algo/merge_points.rs:4-41) for 3-D f32 points
+pub struct IndexedVertices { pub points: Vec<Vec3f>, pub indices: Vec<usize> }
+pub fn merge_points(points: impl Iterator<Item = Vec3f>) -> IndexedVertices {
+    let flat: Vec<f32> = points.flat_map(|p| [p.x, p.y, p.z]).collect();
+    let (mut u, mut nu, mut idx) = (ptr::null_mut(), 0usize, ptr::null_mut());
+    check(unsafe { ffi::bs_merge_points(ctx(), flat.as_ptr(), flat.len() / 3, &mut u, &mut nu, &mut idx) });
+    let points = unsafe { std::slice::from_raw_parts(u, nu * 3) }.chunks_exact(3).map(|c| Vec3f::new(c[0], c[1], c[2])).collect();
+    let indices = unsafe { std::slice::from_raw_parts(idx, flat.len() / 3) }.iter().map(|&i| i as usize).collect();
+    unsafe { ffi::bs_buffer_free(u as *mut _); ffi::bs_buffer_free(idx as *mut _) };
+    IndexedVertices { points, indices }
+}
+
+/// io::stl (src/io/stl.rs): the reader leaves the triangles on the device, where `MeshToVolume::convert_device` takes them
+pub struct DeviceTriangles { d: *mut f32, n: usize }
+impl Drop for DeviceTriangles { fn drop(&mut self) { unsafe { ffi::bs_device_free(ctx(), self.d as *mut _) } } }
+pub fn read_stl_to_device(bytes: &[u8]) -> std::io::Result<DeviceTriangles> {
+    let (mut d, mut n) = (ptr::null_mut(), 0usize);
+    let st = unsafe { ffi::bs_stl_decode(ctx(), bytes.as_ptr(), bytes.len(), &mut d, &mut n) };
+    if st == ffi::BS_ERR_INVALID { return Err(std::io::Error::new(std::io::ErrorKind::UnexpectedEof, "short STL buffer")); }  // read_exact in io/stl.rs:47-59
+    check(st);
+    Ok(DeviceTriangles { d, n })
+}
+impl MeshToVolume {
+    pub fn convert_device(&mut self, tris: &DeviceTriangles) -> Option<Volume> {
+        let mut h = ptr::null_mut();
+        let st = unsafe { ffi::bs_mesh_to_volume_device(ctx(), tris.d, tris.n, self.voxel_size, self.band_width as i64, &mut h) };
+        if st == ffi::BS_ERR_EMPTY_MESH { return None; }
+        check(st);
+        Some(Volume { h })
+    }
+}
+
 pub mod prelude {
     pub use super::{DualContouringMesher, MarchingCubesMesher, MeshToVolume, Volume, VolumeBuilder};
 }
