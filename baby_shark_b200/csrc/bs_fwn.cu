@@ -25,6 +25,14 @@ namespace {
 #ifndef BS_LEAF
 #define BS_LEAF 1
 #endif
+#ifndef BS_VPL
+#define BS_VPL 1
+#endif
+// Traversal records keep their entries interleaved in pairs and k_sign evaluates a pair with packed f32x2 instructions
+// (FFMA2 / FMUL2 / FADD2, new on sm_100): 36.4 -> 33.3 ms on config 5. -DBS_NO_PAIRS restores the scalar path.
+#if BS_VPL == 1 && !defined(BS_NO_PAIRS) && !defined(BS_PAIRS)
+#define BS_PAIRS
+#endif
 constexpr int LEAF = BS_LEAF;     // triangles per leaf
 constexpr int STACK = 208;        // per-warp stack entries: sub-tree roots (<= MAX_ROOTS = 96) + tree depth (<= 63 + 32 with index tie-breaks)
 constexpr int WARPS_PER_BLOCK = 4;
@@ -250,7 +258,7 @@ __global__ void k_records(const int* __restrict__ left, const int* __restrict__ 
     // four consecutive lanes build one record (one entry each): 8 records per warp, stores land in 256 B runs
     const size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     const int x = (int)(g >> 2), e = (int)(g & 3);
-    if (x >= n - 1) return;
+    if (x >= n - 1) return;  // whole groups of four lanes leave together (the pair shuffles below stay inside a group)
     int ids[4] = {-1, -1, -1, -1}, k = 0;
     const int ch[2] = {left[x], right[x]};
     for (int c = 0; c < 2; ++c) {
@@ -261,9 +269,28 @@ __global__ void k_records(const int* __restrict__ left, const int* __restrict__ 
     const int id = ids[e];
     float4 h = make_float4(0.f, 0.f, 0.f, 0.f), c0 = h, c1 = h, c2 = h;
     if (id >= 0) { h = hdr[id]; c0 = coef[3 * (size_t)id]; c1 = coef[3 * (size_t)id + 1]; c2 = coef[3 * (size_t)id + 2]; }
+#ifdef BS_PAIRS
+    // entries are interleaved pairwise -- (e0, e1) and (e2, e3) -- so that every 64-bit word holds the same quantity of
+    // two entries: the traversal evaluates a pair with packed f32x2 instructions (FFMA2 / FMUL2 / FADD2)
+    {
+        float* f = reinterpret_cast<float*>(r);
+        const int p = e >> 1, half = e & 1;
+        const float q[14] = {h.x, h.y, h.z, h.w, c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y};
+        // the two lanes of a pair swap their values so that each writes whole 64-bit words (7 of the 14 quantities each)
+#pragma unroll
+        for (int j = 0; j < 14; ++j) {
+            const float other = __shfl_xor_sync(0xFFFFFFFFu, q[j], 1);
+            if ((j < 7) == (half == 0)) {
+                const int off = j < 4 ? p * 8 + j * 2 : 20 + p * 20 + (j - 4) * 2;
+                *reinterpret_cast<float2*>(f + off) = half ? make_float2(other, q[j]) : make_float2(q[j], other);
+            }
+        }
+    }
+#else
     r[e] = h;
     float2* o = reinterpret_cast<float2*>(reinterpret_cast<float*>(r) + 20 + 10 * e);  // 8 B aligned
     o[0] = make_float2(c0.x, c0.y); o[1] = make_float2(c0.z, c0.w); o[2] = make_float2(c1.x, c1.y); o[3] = make_float2(c1.z, c1.w); o[4] = make_float2(c2.x, c2.y);
+#endif
     if (e == 0) r[4] = make_float4(__int_as_float(ids[0]), __int_as_float(ids[1]), __int_as_float(ids[2]), __int_as_float(ids[3]));
     if (e == 1) r[15] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
@@ -383,6 +410,45 @@ struct WarpWinding {
         }
     }
 
+#ifdef BS_PAIRS
+    __device__ __forceinline__ void push(unsigned id, unsigned near_m) {
+        if (near_m == 0 || sp >= STACK) return;
+        if (id < T.n_leaves - 1) {
+            const char* nxt = reinterpret_cast<const char*>(T.rec + (size_t)id * REC);
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt + 128));
+        }
+        if (lane == 0) { unsigned* e = stack + sp * 2; e[0] = id; e[1] = near_m; }
+        ++sp;
+    }
+    // two entries of a record at once; every float2 holds (entry a, entry b). VPL == 1 only.
+    __device__ __forceinline__ void visit2(int ida, int idb, const float2 hx, const float2 hy, const float2 hz, const float2 hw, const float2* c, unsigned m) {
+        const bool in = (m >> lane) & 1u;
+        const float2 rx = __fadd2_rn(hx, make_float2(-qx[0], -qx[0])), ry = __fadd2_rn(hy, make_float2(-qy[0], -qy[0])), rz = __fadd2_rn(hz, make_float2(-qz[0], -qz[0]));
+        const float2 r2 = __ffma2_rn(rz, rz, __ffma2_rn(ry, ry, __fmul2_rn(rx, rx)));
+        const bool fa = in && ida >= 0 && r2.x > hw.x, fb = in && idb >= 0 && r2.y > hw.y;
+        const unsigned fma_ = __ballot_sync(0xFFFFFFFFu, fa), fmb = __ballot_sync(0xFFFFFFFFu, fb);
+        if (COUNT) { if (lane == 0) cnt[3] += (ida >= 0) + (idb >= 0); if (in) cnt[0] += (ida >= 0) + (idb >= 0); }
+        if (fma_ | fmb) {
+            float2 inv;
+            asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv.x) : "f"(r2.x));
+            asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv.y) : "f"(r2.y));
+            const float2 ir2 = __fmul2_rn(inv, inv);
+            const float2 k = __fmul2_rn(__fmul2_rn(inv, make_float2(INV_4PI, INV_4PI)), ir2);
+            // c[0..9] = o1.x o1.y o1.z trM m00 m11 m22 (m01+m10) (m02+m20) (m12+m21)
+            const float2 d = __ffma2_rn(c[0], rx, __ffma2_rn(c[1], ry, __ffma2_rn(c[2], rz, c[3])));
+            const float2 t1 = __ffma2_rn(c[7], ry, __ffma2_rn(c[8], rz, __fmul2_rn(c[4], rx)));
+            const float2 t2 = __ffma2_rn(c[9], rz, __fmul2_rn(c[5], ry));
+            const float2 rMr = __ffma2_rn(rx, t1, __ffma2_rn(ry, t2, __fmul2_rn(__fmul2_rn(c[6], rz), rz)));
+            const float2 f = __fmul2_rn(k, __ffma2_rn(__fmul2_rn(ir2, make_float2(-3.0f, -3.0f)), rMr, d));
+            if (fa) { wn[0] += f.x; if (COUNT) cnt[1]++; }
+            if (fb) { wn[0] += f.y; if (COUNT) cnt[1]++; }
+        }
+        if (ida >= 0) push((unsigned)ida, m & ~fma_);
+        if (idb >= 0) push((unsigned)idb, m & ~fmb);
+    }
+#endif
+
     // per-voxel traversal of the sub-trees in roots[0..n_roots); wn[] must hold the hoisted far part on entry.
     // All near roots are pushed (and their records prefetched) before the single drain loop starts.
     __device__ void run(const unsigned* valid_m, const unsigned* roots, int n_roots) {
@@ -402,6 +468,22 @@ struct WarpWinding {
             for (int v = 0; v < VPL; ++v) m[v] = e[1 + v];
             __syncwarp();
             if (id >= T.n_leaves - 1) { exact_leaf(id, m); continue; }
+#ifdef BS_PAIRS
+            {
+                const float4* r = T.rec + (size_t)id * REC;
+                const float4 idsf = __ldg(r + 4);
+                const int ids[4] = {__float_as_int(idsf.x), __float_as_int(idsf.y), __float_as_int(idsf.z), __float_as_int(idsf.w)};
+#pragma unroll
+                for (int p = 0; p < 2; ++p) {
+                    if (ids[2 * p] < 0 && ids[2 * p + 1] < 0) continue;
+                    const float4 h0 = __ldg(r + 2 * p), h1 = __ldg(r + 2 * p + 1);
+                    float2 c[10];
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) { const float4 q = __ldg(r + 5 + 5 * p + k); c[2 * k] = make_float2(q.x, q.y); c[2 * k + 1] = make_float2(q.z, q.w); }
+                    visit2(ids[2 * p], ids[2 * p + 1], make_float2(h0.x, h0.y), make_float2(h0.z, h0.w), make_float2(h1.x, h1.y), make_float2(h1.z, h1.w), c, m[0]);
+                }
+            }
+#else
             const float4* r = T.rec + (size_t)id * REC;
             const float4 idsf = __ldg(r + 4);
             const int ids[4] = {__float_as_int(idsf.x), __float_as_int(idsf.y), __float_as_int(idsf.z), __float_as_int(idsf.w)};
@@ -412,6 +494,7 @@ struct WarpWinding {
             if (ids[1] >= 0) visit((unsigned)ids[1], __ldg(r + 1), make_float4(q7.z, q7.w, q8.x, q8.y), make_float4(q8.z, q8.w, q9.x, q9.y), make_float4(q9.z, q9.w, 0.f, 0.f), m);
             if (ids[2] >= 0) visit((unsigned)ids[2], __ldg(r + 2), q10, q11, make_float4(q12.x, q12.y, 0.f, 0.f), m);
             if (ids[3] >= 0) visit((unsigned)ids[3], __ldg(r + 3), make_float4(q12.z, q12.w, q13.x, q13.y), make_float4(q13.z, q13.w, q14.x, q14.y), make_float4(q14.z, q14.w, 0.f, 0.f), m);
+#endif
         }
     }
 };
@@ -471,14 +554,14 @@ __global__ void __launch_bounds__(32 * BP_WARPS) k_brick_pass(Tree T, const unsi
                 const float4 idsf = __ldg(r + 4);
                 ids[0] = __float_as_int(idsf.x); ids[1] = __float_as_int(idsf.y); ids[2] = __float_as_int(idsf.z); ids[3] = __float_as_int(idsf.w);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) if (ids[k] >= 0) code[k] = classify((unsigned)ids[k], __ldg(r + k));
+                for (int k = 0; k < 4; ++k) if (ids[k] >= 0) code[k] = classify((unsigned)ids[k], __ldg(T.hdr + ids[k]));
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {  // ordered compaction: (round, entry, lane)
                 const unsigned mh = __ballot_sync(0xFFFFFFFFu, code[k] == 0), mr = __ballot_sync(0xFFFFFFFFu, code[k] == 1), md = __ballot_sync(0xFFFFFFFFu, code[k] == 2);
                 if (COUNT) n_class += __popc(mh | mr | md);
                 if (nh + __popc(mh) > MAX_HOIST || nr + __popc(mr) > MAX_ROOTS || nnext + __popc(md) > MAX_FRONT) { overflow = true; break; }
-                if (code[k] == 0) hoist[nh + __popc(mh & lt)] = (id << 2) | k;
+                if (code[k] == 0) hoist[nh + __popc(mh & lt)] = (unsigned)ids[k];
                 if (code[k] == 1) roots[nr + __popc(mr & lt)] = (unsigned)ids[k];
                 if (code[k] == 2) front[cur ^ 1][nnext + __popc(md & lt)] = (unsigned)ids[k];
                 nh += __popc(mh); nr += __popc(mr); nnext += __popc(md);
@@ -500,18 +583,10 @@ __global__ void __launch_bounds__(32 * BP_WARPS) k_brick_pass(Tree T, const unsi
     float S = 0.f;
     for (int i = 0; i < nh; ++i) {
         const unsigned e = hoist[i];
-        float4 h; float c[10];
-        if (e == 0xFFFFFFFFu) {
-            h = __ldg(T.hdr + T.root);
-            const float4 a0 = __ldg(T.coef + 3 * (size_t)T.root), a1 = __ldg(T.coef + 3 * (size_t)T.root + 1), a2 = __ldg(T.coef + 3 * (size_t)T.root + 2);
-            c[0] = a0.x; c[1] = a0.y; c[2] = a0.z; c[3] = a0.w; c[4] = a1.x; c[5] = a1.y; c[6] = a1.z; c[7] = a1.w; c[8] = a2.x; c[9] = a2.y;
-        } else {
-            const float4* r = T.rec + (size_t)(e >> 2) * REC;
-            h = __ldg(r + (e & 3));
-            const float2* cf = reinterpret_cast<const float2*>(reinterpret_cast<const float*>(r) + 20 + 10 * (e & 3));
-#pragma unroll
-            for (int j = 0; j < 5; ++j) { const float2 t = __ldg(cf + j); c[2 * j] = t.x; c[2 * j + 1] = t.y; }
-        }
+        const unsigned nid = e == 0xFFFFFFFFu ? T.root : e;  // warp-uniform: broadcast loads
+        const float4 h = __ldg(T.hdr + nid);
+        const float4 a0 = __ldg(T.coef + 3 * (size_t)nid), a1 = __ldg(T.coef + 3 * (size_t)nid + 1), a2 = __ldg(T.coef + 3 * (size_t)nid + 2);
+        const float c[10] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y};
         const float rx = h.x - sx, ry = h.y - sy, rz = h.z - sz;
         const float r2 = fmaf(rz, rz, fmaf(ry, ry, rx * rx));
         float inv_r;
