@@ -506,8 +506,16 @@ def main():
             by = nb * (2112 + 868) + 36.0 * (n_verts_local / 3.0)
             rl.append({"kernel": "k_mc_fused (stage + classify + MC33 + look-back + emit, one pass)", "bound": "hbm", "achieved": by / (mc_ms["mc_emit_ms"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                        "ms": mc_ms["mc_emit_ms"], "algorithmic": "n_bricks x 2980 B + 36 B x n_out_tris", "traffic": None, "peak_source": hbm_src})
+        # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` captures of
+        # this exact workload (profiles/r1_final_sign_kernels_ncu_summary.txt, r1_mc_ncu_summary.txt, r1_k_mc_fused_ncu_summary.txt)
+        if args.config == 5 and args.scale == 1.0 and world == 1:
+            ncu_traffic = {"k_eval": 1.191240e9 + 529.150720e6, "k_sign": 2.388182e9 + 285.550336e6, "k_mc_fused": 625.867776e6 + 1.209232e9}
+            for r in rl:
+                r["traffic"] = ncu_traffic.get(r["kernel"].split(" ")[0])
         for r in rl:
             r["frac"] = r["achieved"] / r["peak"]
+            if r["bound"] == "fp32":
+                r["note"] = "FP32 CUDA-core kernel (no stage of this path is a dense contraction or a stream): peak = SMs x 128 lanes x 2 x max SM clock; achieved counts algorithmic FLOPs only"
         stage_all = dict(conv_ms)
         stage_all.update(mc_ms)
         dominant = max(rl, key=lambda r: r["ms"]) if rl else None
