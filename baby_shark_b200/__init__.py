@@ -29,7 +29,7 @@ EXPORTS = [
     "bs_mesh_mc", "bs_mesh_dc", "bs_mesh_mc_device", "bs_mesh_dc_device", "bs_buffer_free",
     "bs_volume_download", "bs_volume_counts", "bs_context_last_stats", "bs_context_copy_out_verts", "bs_context_copy_out_verts_device", "bs_context_set_flag", "bs_kernel_launch_count",
     "bs_stl_decode", "bs_stl_decode_device", "bs_stl_encode", "bs_stl_encode_device", "bs_mesh_active_voxels", "bs_mesh_active_voxels_device",
-    "bs_merge_points", "bs_merge_points_device", "bs_device_free",
+    "bs_merge_points", "bs_merge_points_device", "bs_device_free", "bs_mesh_mc_indexed", "bs_mesh_mc_indexed_device", "bs_copy_to_host",
 ]
 
 
@@ -103,6 +103,9 @@ def load_library(path=None):
         "bs_merge_points": (C.c_int, [vp, vp, sz, pvp, psz, pvp]),
         "bs_merge_points_device": (C.c_int, [vp, vp, sz, pvp, psz, pvp]),
         "bs_device_free": (None, [vp, vp]),
+        "bs_mesh_mc_indexed": (C.c_int, [vp, C.c_float, pvp, psz, pvp, psz]),
+        "bs_mesh_mc_indexed_device": (C.c_int, [vp, C.c_float, pvp, psz, pvp, psz]),
+        "bs_copy_to_host": (C.c_int, [vp, vp, vp, sz]),
     }
     for name, (res, args) in sigs.items():
         f = getattr(L, name)
@@ -366,6 +369,18 @@ class MarchingCubesMesher:
         return _take_verts(p, n.value)
 
 
+def mesh_indexed(volume, voxel_size):
+    """Marching cubes + merge_points on the device -> IndexedVertices: the input an indexed mesh type builds from
+    (src/remeshing/voxel.rs:73-83 with T = CornerTable, mesh/corner_table/builder.rs:294)."""
+    pp, pi, npnt, nidx = C.c_void_p(), C.c_void_p(), C.c_size_t(), C.c_size_t()
+    volume._ctx.check(load_library().bs_mesh_mc_indexed(volume._h, voxel_size, C.byref(pp), C.byref(npnt), C.byref(pi), C.byref(nidx)))
+    pts = np.ctypeslib.as_array(C.cast(pp, C.POINTER(C.c_float)), shape=(max(npnt.value, 1) * 3,))[: npnt.value * 3].copy().reshape(-1, 3)
+    idx = np.ctypeslib.as_array(C.cast(pi, C.POINTER(C.c_uint32)), shape=(max(nidx.value, 1),))[: nidx.value].copy()
+    load_library().bs_buffer_free(pp)
+    load_library().bs_buffer_free(pi)
+    return IndexedVertices(pts, idx)
+
+
 class DualContouringMesher:
     """`voxel::meshing::DualContouringMesher` (src/voxel/meshing/dual_contouring.rs:13-89)."""
 
@@ -519,4 +534,4 @@ def merge_points(points, ctx=None):
 
 
 __all__ = ["Context", "Volume", "MeshToVolume", "VolumeBuilder", "MarchingCubesMesher", "DualContouringMesher",
-           "VoxelRemesher", "MeshingMethod", "StlReader", "StlWriter", "DeviceTriangles", "ActiveVoxelsMesher", "IndexedVertices", "merge_points", "BsharkError", "ReferencePanic", "load_library", "EXPORTS", "LIB_PATH"]
+           "VoxelRemesher", "MeshingMethod", "StlReader", "StlWriter", "DeviceTriangles", "ActiveVoxelsMesher", "IndexedVertices", "merge_points", "mesh_indexed", "BsharkError", "ReferencePanic", "load_library", "EXPORTS", "LIB_PATH"]

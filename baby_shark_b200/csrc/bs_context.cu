@@ -270,6 +270,36 @@ bs_status bs_merge_points_device(bs_context* ctx, const float* d_points, size_t 
     cudaSetDevice(ctx->device);
     return bs_merge_points_impl(ctx, d_points, n, d_unique, n_unique, d_indices);
 }
+bs_status bs_copy_to_host(bs_context* ctx, const void* d_src, void* dst, size_t bytes) {
+    if (!ctx || ((!d_src || !dst) && bytes)) return BS_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    if (bytes) BS_CUDA(ctx, cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    BS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BS_OK;
+}
+bs_status bs_mesh_mc_indexed_device(const bs_volume* v, float voxel_size, float** d_points, size_t* n_points, uint32_t** d_indices, size_t* n_indices) {
+    if (!v || !d_points || !n_points || !d_indices || !n_indices) return BS_ERR_INVALID;
+    bs_context* ctx = v->ctx;
+    cudaSetDevice(ctx->device);
+    const float* d_soup = nullptr; size_t n = 0;
+    BS_TRY(bs_mc_impl(v, voxel_size, &d_soup, &n));
+    *n_indices = n;
+    return bs_merge_points_impl(ctx, d_soup, n, d_points, n_points, d_indices);
+}
+bs_status bs_mesh_mc_indexed(const bs_volume* v, float voxel_size, float** points, size_t* n_points, uint32_t** indices, size_t* n_indices) {
+    if (!v || !points || !n_points || !indices || !n_indices) return BS_ERR_INVALID;
+    bs_context* ctx = v->ctx;
+    cudaSetDevice(ctx->device);
+    const float* d_soup = nullptr; size_t n = 0;
+    BS_TRY(bs_mc_impl(v, voxel_size, &d_soup, &n));
+    float* d_u = nullptr; unsigned* d_i = nullptr;
+    BS_TRY(bs_merge_points_impl(ctx, d_soup, n, &d_u, n_points, &d_i));
+    bs_status s = to_pinned(ctx, d_u, *n_points * 3, points);
+    if (s == BS_OK) { s = to_pinned(ctx, d_i, n, indices); if (s != BS_OK) { cudaFreeHost(*points); *points = nullptr; } }
+    bs_free(ctx, d_u); bs_free(ctx, d_i);
+    *n_indices = n;
+    return s;
+}
 bs_status bs_merge_points(bs_context* ctx, const float* points, size_t n, float** unique, size_t* n_unique, uint32_t** indices) {
     if (!ctx || !unique || !n_unique || !indices || (!points && n)) return BS_ERR_INVALID;
     cudaSetDevice(ctx->device);

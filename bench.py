@@ -458,6 +458,40 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
 
+    # ---- e2e, indexed output (single GPU): the same remesh handed to an indexed mesh type -- MC + merge_points on the
+    # device, unique points + indices read back (half the bytes of the soup, no host hash pass) -------------------------
+    e2e_indexed = None
+    if world == 1:
+        h_pts = h_idx = None
+
+        def step_e2e_indexed():
+            nonlocal h_pts, h_idx
+            h = C.c_void_p()
+            ctx.check(L.bs_mesh_to_volume(ctx._h, C.cast(h_tris.data_ptr(), fp), n_tris, vs, 0, C.byref(h)))
+            dp, di, npnt, nidx = C.c_void_p(), C.c_void_p(), C.c_size_t(), C.c_size_t()
+            st = L.bs_mesh_mc_indexed_device(h, vs, C.byref(dp), C.byref(npnt), C.byref(di), C.byref(nidx))
+            L.bs_volume_free(h)
+            ctx.check(st)
+            if h_pts is None or h_pts.numel() < npnt.value * 3:
+                h_pts = torch.empty(int(npnt.value * 3.3) + 16, dtype=torch.float32).pin_memory()
+            if h_idx is None or h_idx.numel() < nidx.value:
+                h_idx = torch.empty(int(nidx.value * 1.1) + 16, dtype=torch.int32).pin_memory()
+            ctx.check(L.bs_copy_to_host(ctx._h, dp, C.c_void_p(h_pts.data_ptr()), npnt.value * 12))
+            ctx.check(L.bs_copy_to_host(ctx._h, di, C.c_void_p(h_idx.data_ptr()), nidx.value * 4))
+            L.bs_device_free(ctx._h, dp)
+            L.bs_device_free(ctx._h, di)
+            return npnt.value, nidx.value
+        for _ in range(2):
+            step_e2e_indexed()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            n_pts, n_idx = step_e2e_indexed()
+        torch.cuda.synchronize()
+        ms_i = (time.perf_counter() - t0) * 1e3 / args.steps
+        e2e_indexed = {"ms_per_step": ms_i, "h2d_bytes_per_step": int(tris.nbytes), "d2h_bytes_per_step": int(n_pts * 12 + n_idx * 4),
+                       "n_unique_vertices": int(n_pts), "what": "bs_mesh_to_volume + bs_mesh_mc_indexed_device + read-back of unique points and indices"}
+
     # ---- reduce over ranks ---------------------------------------------------------------------------------------
     t = torch.tensor([ms_total, e2e_s * 1e3, n_active_local, float(n_verts_local)], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -528,9 +562,13 @@ def main():
             "remesh_ms": ms_per_step, "tris_per_s": (n_verts / 3.0) / (ms_per_step * 1e-3), "n_active_voxels": n_active, "n_out_triangles": n_verts / 3.0,
             "step_ms": step_ms, "stage_ms": stage_all, "stage_ms_per_rank": per_rank, "work": work,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": int(tris.nbytes), "d2h_bytes_per_step": int(n_verts_local * 12)},
-            "gpu_launches": None, "clocks": clocks,
+            "e2e_indexed": None, "gpu_launches": None, "clocks": clocks,
             "roofline": dominant, "rooflines": rl,
         }
+        if e2e_indexed:
+            e2e_indexed["value"] = n_active / (e2e_indexed["ms_per_step"] * 1e-3)
+            e2e_indexed["unit"] = UNIT
+            out["e2e_indexed"] = e2e_indexed
         out["gpu_launches"] = int(launches) * world  # counted by the library at its launch sites (bs_kernel_launch_count)
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1

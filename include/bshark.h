@@ -133,6 +133,18 @@ bs_status bs_merge_points(bs_context* ctx, const float* points, size_t n, float*
                           uint32_t** indices);
 bs_status bs_merge_points_device(bs_context* ctx, const float* d_points, size_t n, float** d_unique,
                                  size_t* n_unique, uint32_t** d_indices);
+/* MarchingCubesMesher::mesh followed by merge_points, without leaving the device: what `T::from_triangles_soup` does
+ * for an indexed mesh type (src/remeshing/voxel.rs:73-83 -> mesh/corner_table/builder.rs:294), minus the host hash
+ * pass and with half the bytes to read back. points = n_points x 3 floats (first-occurrence order), indices = one per
+ * soup vertex (3 per triangle). Host results: bs_buffer_free. */
+bs_status bs_mesh_mc_indexed(const bs_volume* v, float voxel_size, float** points, size_t* n_points, uint32_t** indices,
+                             size_t* n_indices);
+/* Same, results left on the device (bs_device_free). */
+bs_status bs_mesh_mc_indexed_device(const bs_volume* v, float voxel_size, float** d_points, size_t* n_points,
+                                    uint32_t** d_indices, size_t* n_indices);
+/* Copies `bytes` from device memory of the context's device into caller memory (pinned or pageable) on the context's
+ * stream and waits: lets the shim fill buffers it owns from any *_device result. */
+bs_status bs_copy_to_host(bs_context* ctx, const void* d_src, void* dst, size_t bytes);
 /* Frees device memory returned by the *_device entry points above. */
 void bs_device_free(bs_context* ctx, void* d_ptr);
 

@@ -119,3 +119,14 @@ def test_merge_points_edge_cases(bs, oracle):
     many = rng.integers(0, 50, size=(200000, 3)).astype(np.float32)   # heavy duplication: long probe chains, atomicMin races
     got, (uq, idx) = bs.merge_points(many), oracle.merge_points(many)
     assert np.array_equal(got.indices, idx) and np.array_equal(got.points, uq)
+
+
+def test_mesh_indexed_equals_mc_then_merge_points(bs, oracle):
+    from baby_shark_b200 import synth
+    tris, vs, _ = synth.config_mesh(4, 0.06)
+    g = bs.MeshToVolume().with_voxel_size(vs).convert(tris)
+    soup = bs.MarchingCubesMesher().with_voxel_size(vs).mesh(g)
+    got = bs.mesh_indexed(g, vs)
+    uq, idx = oracle.merge_points(soup)
+    assert np.array_equal(got.indices, idx) and np.array_equal(got.points.view(np.uint32), uq.view(np.uint32))
+    assert np.array_equal(got.points[got.indices].view(np.uint32), soup.view(np.uint32))
