@@ -216,6 +216,16 @@ class Volume:
                                                        voxel_size, C.byref(h)))
         return Volume(h, ctx)
 
+    @staticmethod
+    def from_voxels(ijk, values, voxel_size, ctx=None):
+        """the kept voxels of a `from_fn` run, given directly: ijk [m,3] int32, values [m] f32 (later entries win)"""
+        ctx = ctx or Context.default()
+        ijk32, val = np.ascontiguousarray(ijk, np.int32).reshape(-1, 3), _f32(values)
+        h = C.c_void_p()
+        ctx.check(load_library().bs_volume_from_voxels(ctx._h, ijk32.ctypes.data_as(C.POINTER(C.c_int32)), _fp(val), ijk32.shape[0],
+                                                       voxel_size, C.byref(h)))
+        return Volume(h, ctx)
+
     def voxel_size(self):
         return load_library().bs_volume_voxel_size(self._h)
 

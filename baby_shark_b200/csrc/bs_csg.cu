@@ -13,8 +13,7 @@
 // scan-line sign of leaf_node/flood_fill.rs) and applies min / max(a,-b) / max over all 512 slots, mask |= mask.
 // Per merged brick: read 2 x 2112 B, write 2112 B.
 //
-// Not reproduced (documented in DESIGN.md): (1) root flood fill inserting all-negative 4096^3 nodes between two
-// inside nodes on a z-line (needs volumes > 8192 voxels across) -> BS_ERR_UNSUPPORTED; (2) a 16^3 node that a
+// Not reproduced (documented in DESIGN.md): a 16^3 node that a
 // subtract/intersect emptied stays in the reference's tree with stale background signs read by later flood
 // fills (dangling union bytes, undefined in the reference) -> here it disappears.
 #include "bs_common.cuh"
@@ -207,11 +206,30 @@ bs_status build_dir(bs_context* ctx, const bs_volume* v, Dir& D) {
         D.n5first[j] = kind_of(s[0]) == K_CHILD ? D.n4first[slot_n4[0]] : (u8)neg_of(s[0]);
         D.n5last[j] = kind_of(s[32767]) == K_CHILD ? D.n4first[slot_n4[32767]] : (u8)neg_of(s[32767]);
     }
-    // root flood fill (root_node/flood_fill.rs:17-41) would insert all-negative nodes into z-line gaps
+    // root flood fill (root_node/flood_fill.rs:17-41): two consecutive 4096^3 nodes on the same z-line that are not
+    // adjacent and face each other with negative signs get every key between them filled with an empty node whose
+    // background is negative: all of its slots then read as inside tiles in the CSG rules below
+    std::vector<u64> ins;
     for (size_t j = 0; j + 1 < n5; ++j) {
         const u64 a = D.n5k[j], b = D.n5k[j + 1];
         if ((a >> 9) != (b >> 9) || (b & 511) == (a & 511) + 1) continue;
-        if (D.n5last[j] && D.n5first[j + 1]) return bs_fail(ctx, BS_ERR_UNSUPPORTED, "root-level flood fill across a gap of 4096^3 nodes is not implemented");
+        if (!(D.n5last[j] && D.n5first[j + 1])) continue;
+        for (u64 z = (a & 511) + 1; z < (b & 511); ++z) ins.push_back((a & ~511ull) | z);
+    }
+    if (!ins.empty()) {
+        if (ins.size() > 4096) return bs_fail(ctx, BS_ERR_UNSUPPORTED, "root-level flood fill would insert %zu empty 4096^3 nodes", ins.size());
+        std::vector<u64> k2; std::vector<u8> st2, f2, l2;
+        k2.reserve(n5 + ins.size()); st2.reserve((n5 + ins.size()) * 32768);
+        size_t ia = 0, ib = 0;
+        while (ia < n5 || ib < ins.size()) {
+            if (ib >= ins.size() || (ia < n5 && D.n5k[ia] < ins[ib])) {
+                k2.push_back(D.n5k[ia]); st2.insert(st2.end(), D.n5state.begin() + ia * 32768, D.n5state.begin() + (ia + 1) * 32768);
+                f2.push_back(D.n5first[ia]); l2.push_back(D.n5last[ia]); ++ia;
+            } else {
+                k2.push_back(ins[ib]); st2.insert(st2.end(), 32768, mk(K_INACTIVE, true)); f2.push_back(1); l2.push_back(1); ++ib;
+            }
+        }
+        D.n5k.swap(k2); D.n5state.swap(st2); D.n5first.swap(f2); D.n5last.swap(l2);
     }
     return BS_OK;
 }

@@ -85,3 +85,25 @@ def test_union_with_self_and_empty(bs, oracle):
     e = a.clone().union(bs.Volume.with_voxel_size(vs)).download()
     assert np.array_equal(before["origins"], e["origins"]) and np.array_equal(before["values"][m], e["values"][m])
     assert a.clone().intersect(bs.Volume.with_voxel_size(vs)).counts()["leaves"] == 0
+
+
+@pytest.mark.parametrize("op", OPS)
+@pytest.mark.parametrize("swap", [False, True])
+def test_root_level_flood_fill_fills_the_gap_between_inside_nodes(bs, oracle, op, swap):
+    # root_node/flood_fill.rs:17-41: two 4096^3 root nodes on one z-line, both "inside" at their facing ends and not
+    # adjacent, get the keys between them filled with empty all-negative nodes; a sphere sitting in that gap is then
+    # (partly) swallowed by a union, turned into 32768 active tiles when it is the left operand, etc.
+    ijk = np.int32([(x, y, z) for z0 in (4000, 8300) for x in range(10, 13) for y in range(10, 13) for z in range(z0, z0 + 3)])
+    val = np.full(ijk.shape[0], -0.5, np.float32)
+    def blobs(B):
+        return oracle.from_voxels(ijk, val, 1.0) if B is oracle else bs.Volume.from_voxels(ijk, val, 1.0)
+    def ball(B):
+        return oracle.sphere(1.0, 20.0, (11.0, 11.0, 6000.0)) if B is oracle else bs.VolumeBuilder().with_voxel_size(1.0).sphere(20.0, (11.0, 11.0, 6000.0))
+    ga, gb_ = (ball(bs), blobs(bs)) if swap else (blobs(bs), ball(bs))
+    oa, ob = (ball(oracle), blobs(oracle)) if swap else (blobs(oracle), ball(oracle))
+    g, o = getattr(ga, op)(gb_), getattr(oa, op)(ob)
+    gd, od = g.download(), o.download()
+    compare_volumes(gd, od, 1.0)
+    if op == "union":
+        assert od["origins"].shape[0] == 68                      # part of the ball is gone: the gap node is "inside"
+        assert (od["tile_sizes"].size == 32768) == swap            # make_child_inside on every slot of the gap node
