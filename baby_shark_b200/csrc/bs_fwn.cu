@@ -100,7 +100,7 @@ __global__ void k_morton(const float* __restrict__ tris, size_t n, const int* bo
         float u = ext > 0.f ? (c - lo) / ext : 0.f;
         if (!(u >= 0.f)) u = 0.f;
         if (u > 1.f) u = 1.f;
-        unsigned long long q = (unsigned long long)(u * 2097151.0f);
+        unsigned long long q = (unsigned long long)(u * 65535.0f);  // 16 bits per axis: 32 cells per voxel at 2048^3, two radix passes fewer than 21
         code |= spread21(q) << (2 - d);
     }
     codes[t] = code; ids[t] = (unsigned)t;
@@ -157,10 +157,28 @@ __device__ __forceinline__ void raw_load_cg(const Raw* p, Raw& r) {
     for (int i = 0; i < 6; ++i) d[i] = __ldcg(s + i);
 }
 
+// Per node: header {p~.xyz, beta^2 r^2} and far-field coefficients {o1.xyz, trM} {m00 m11 m22 m01+m10} {m02+m20 m12+m21 - -}
+__device__ __forceinline__ void finalize_node(const Raw& r, size_t i, float4* hdr, float4* coef) {
+    float c[3], rad2 = 0.f;
+    for (int d = 0; d < 3; ++d) {
+        c[d] = r.awc[d] / r.area;  // NaN for an all-degenerate node: never "far", always descended (as in the reference)
+        const float e = fmaxf(fabsf(r.bbmin[d] - c[d]), fabsf(r.bbmax[d] - c[d]));
+        rad2 += e * e;
+    }
+    if (r.pad[0] > 0.f && r.pad[0] * r.pad[0] < rad2) rad2 = r.pad[0] * r.pad[0];  // the tighter of two valid bounds
+    float m[9];  // m[col*3+row]
+    for (int col = 0; col < 3; ++col) for (int row = 0; row < 3; ++row) m[col * 3 + row] = r.o1sum[col * 3 + row] - c[row] * r.awn[col];
+    hdr[i] = make_float4(c[0], c[1], c[2], BETA * BETA * rad2);
+    coef[3 * (size_t)i + 0] = make_float4(r.awn[0], r.awn[1], r.awn[2], m[0] + m[4] + m[8]);
+    coef[3 * (size_t)i + 1] = make_float4(m[0], m[4], m[8], m[1] + m[3]);
+    coef[3 * (size_t)i + 2] = make_float4(m[2] + m[6], m[5] + m[7], 0.f, 0.f);
+}
+
 // leaves: gather LEAF sorted triangles, store them for traversal, accumulate the leaf's moments
 // (aabb_tree.rs:749-777), then climb: the second child to arrive at a parent combines both (:779-801).
 __global__ void k_leaves_and_climb(const float* __restrict__ tris, const unsigned* __restrict__ ids, size_t n_tris, float4* sorted, Raw* raw,
-                                   const int* __restrict__ left, const int* __restrict__ right, const int* __restrict__ parent, unsigned* flags, int n) {
+                                   const int* __restrict__ left, const int* __restrict__ right, const int* __restrict__ parent, unsigned* flags, int n,
+                                   float4* hdr, float4* coef) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n) return;
     Raw r;
@@ -203,6 +221,7 @@ __global__ void k_leaves_and_climb(const float* __restrict__ tris, const unsigne
         r.pad[0] = sqrtf(m2);  // NaN centre (all-degenerate leaf) -> fmaxf drops the NaNs -> 0, finalize falls back to the box bound
     }
     raw[n - 1 + g] = r;
+    finalize_node(r, (size_t)(n - 1 + g), hdr, coef);  // header + far-field coefficients as soon as the moments are complete
     if (n == 1) return;
     int node = parent[n - 1 + g];
     while (node >= 0) {
@@ -225,28 +244,9 @@ __global__ void k_leaves_and_climb(const float* __restrict__ tris, const unsigne
             a.pad[0] = (ra == ra && rb == rb) ? fmaxf(ra, rb) : 3.0e38f;  // a degenerate child: keep only the box bound
         }
         raw[node] = a;
+        finalize_node(a, (size_t)node, hdr, coef);
         node = parent[node];
     }
-}
-
-// Per node: header {p~.xyz, beta^2 r^2} and far-field coefficients {o1.xyz, trM} {m00 m11 m22 m01+m10} {m02+m20 m12+m21 - -}
-__global__ void k_finalize_nodes(const Raw* __restrict__ raw, int n, float4* hdr, float4* coef) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 2 * n - 1) return;
-    const Raw r = raw[i];
-    float c[3], rad2 = 0.f;
-    for (int d = 0; d < 3; ++d) {
-        c[d] = r.awc[d] / r.area;  // NaN for an all-degenerate node: never "far", always descended (as in the reference)
-        const float e = fmaxf(fabsf(r.bbmin[d] - c[d]), fabsf(r.bbmax[d] - c[d]));
-        rad2 += e * e;
-    }
-    if (r.pad[0] > 0.f && r.pad[0] * r.pad[0] < rad2) rad2 = r.pad[0] * r.pad[0];  // the tighter of two valid bounds
-    float m[9];  // m[col*3+row]
-    for (int col = 0; col < 3; ++col) for (int row = 0; row < 3; ++row) m[col * 3 + row] = r.o1sum[col * 3 + row] - c[row] * r.awn[col];
-    hdr[i] = make_float4(c[0], c[1], c[2], BETA * BETA * rad2);
-    coef[3 * (size_t)i + 0] = make_float4(r.awn[0], r.awn[1], r.awn[2], m[0] + m[4] + m[8]);
-    coef[3 * (size_t)i + 1] = make_float4(m[0], m[4], m[8], m[1] + m[3]);
-    coef[3 * (size_t)i + 2] = make_float4(m[2] + m[6], m[5] + m[7], 0.f, 0.f);
 }
 
 // Traversal record of internal node X: its (up to 4) grandchildren -- or a child itself when that child is a leaf --
@@ -254,18 +254,22 @@ __global__ void k_finalize_nodes(const Raw* __restrict__ raw, int n, float4* hdr
 // 256 B = two 128 B lines: [0..3] entry headers, [4] entry node ids (int4, -1 = none), then 10 coefficient floats
 // per entry {o1.xyz, trM, m00, m11, m22, m01+m10, m02+m20, m12+m21} packed from float 20 on.
 constexpr int REC = 16;  // float4 per record
-__global__ void k_records(const int* __restrict__ left, const int* __restrict__ right, const float4* __restrict__ hdr, const float4* __restrict__ coef, int n, float4* rec) {
-    // four consecutive lanes build one record (one entry each): 8 records per warp, stores land in 256 B runs
+__global__ void __launch_bounds__(256) k_records(const int* __restrict__ left, const int* __restrict__ right, const float4* __restrict__ hdr, const float4* __restrict__ coef, int n, float4* rec) {
+    // four consecutive lanes build one record (one entry each) in shared memory; the CTA's 64 records (16 KB, contiguous
+    // in global memory) then leave with coalesced 128-bit stores
+    __shared__ float4 s_rec[64 * REC];
     const size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     const int x = (int)(g >> 2), e = (int)(g & 3);
-    if (x >= n - 1) return;  // whole groups of four lanes leave together (the pair shuffles below stay inside a group)
+    const bool valid = x < n - 1;
     int ids[4] = {-1, -1, -1, -1}, k = 0;
-    const int ch[2] = {left[x], right[x]};
-    for (int c = 0; c < 2; ++c) {
-        if (ch[c] >= n - 1) ids[k++] = ch[c];
-        else { ids[k++] = left[ch[c]]; ids[k++] = right[ch[c]]; }
+    if (valid) {
+        const int ch[2] = {left[x], right[x]};
+        for (int c = 0; c < 2; ++c) {
+            if (ch[c] >= n - 1) ids[k++] = ch[c];
+            else { ids[k++] = left[ch[c]]; ids[k++] = right[ch[c]]; }
+        }
     }
-    float4* r = rec + (size_t)x * REC;
+    float4* r = s_rec + (threadIdx.x >> 2) * REC;
     const int id = ids[e];
     float4 h = make_float4(0.f, 0.f, 0.f, 0.f), c0 = h, c1 = h, c2 = h;
     if (id >= 0) { h = hdr[id]; c0 = coef[3 * (size_t)id]; c1 = coef[3 * (size_t)id + 1]; c2 = coef[3 * (size_t)id + 2]; }
@@ -276,15 +280,8 @@ __global__ void k_records(const int* __restrict__ left, const int* __restrict__ 
         float* f = reinterpret_cast<float*>(r);
         const int p = e >> 1, half = e & 1;
         const float q[14] = {h.x, h.y, h.z, h.w, c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x, c2.y};
-        // the two lanes of a pair swap their values so that each writes whole 64-bit words (7 of the 14 quantities each)
 #pragma unroll
-        for (int j = 0; j < 14; ++j) {
-            const float other = __shfl_xor_sync(0xFFFFFFFFu, q[j], 1);
-            if ((j < 7) == (half == 0)) {
-                const int off = j < 4 ? p * 8 + j * 2 : 20 + p * 20 + (j - 4) * 2;
-                *reinterpret_cast<float2*>(f + off) = half ? make_float2(other, q[j]) : make_float2(q[j], other);
-            }
-        }
+        for (int j = 0; j < 14; ++j) f[(j < 4 ? p * 8 + j * 2 : 20 + p * 20 + (j - 4) * 2) + half] = q[j];
     }
 #else
     r[e] = h;
@@ -293,6 +290,11 @@ __global__ void k_records(const int* __restrict__ left, const int* __restrict__ 
 #endif
     if (e == 0) r[4] = make_float4(__int_as_float(ids[0]), __int_as_float(ids[1]), __int_as_float(ids[2]), __int_as_float(ids[3]));
     if (e == 1) r[15] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    const size_t first = (size_t)blockIdx.x * 64;                       // first record of this CTA
+    const size_t n_here = first < (size_t)(n - 1) ? min((size_t)64, (size_t)(n - 1) - first) : 0;
+    float4* dst = rec + first * REC;
+    for (unsigned i = threadIdx.x; i < n_here * REC; i += 256) dst[i] = s_rec[i];
 }
 
 __device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
@@ -763,10 +765,11 @@ bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_v
     bs_count_launch(), k_centroid_bounds<<<(unsigned)std::min<size_t>(bs_blocks(n_tris, 256), (size_t)ctx->sm_count * 64), 256, 0, st>>>(d_tris, n_tris, d_bounds);
     bs_count_launch(), k_morton<<<bs_blocks(n_tris, 256), 256, 0, st>>>(d_tris, n_tris, d_bounds, d_codes, d_ids);
     void* d_tmp = nullptr; size_t tmp_bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_codes, d_codes2, d_ids, d_ids2, n_tris, 0, 63, st);
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_codes, d_codes2, d_ids, d_ids2, n_tris, 0, 48, st);
     BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp_bytes));
-    cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_codes, d_codes2, d_ids, d_ids2, n_tris, 0, 63, st);
+    cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_codes, d_codes2, d_ids, d_ids2, n_tris, 0, 48, st);
     bs_free(ctx, d_tmp); bs_free(ctx, d_codes); bs_free(ctx, d_ids); bs_free(ctx, d_bounds);
+    bs_mark(ctx, "bvh_sort_ms");
     // hierarchy
     const int n = (int)((n_tris + LEAF - 1) / LEAF);
     const int n_nodes = 2 * n - 1;
@@ -786,13 +789,14 @@ bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_v
     if (n > 1) bs_count_launch(), k_karras<<<bs_blocks((size_t)n - 1, 256), 256, 0, st>>>(d_codes2, n, d_left, d_right, d_parent);
     const unsigned root_id = 0u;
 #endif
-    bs_count_launch(), k_leaves_and_climb<<<bs_blocks((size_t)n, 128), 128, 0, st>>>(d_tris, d_ids2, n_tris, d_sorted, d_raw, d_left, d_right, d_parent, d_flags, n);
-    bs_count_launch(), k_finalize_nodes<<<bs_blocks((size_t)n_nodes, 128), 128, 0, st>>>(d_raw, n, d_hdr, d_coef);
+    bs_mark(ctx, "bvh_tree_ms");
+    bs_count_launch(), k_leaves_and_climb<<<bs_blocks((size_t)n, 128), 128, 0, st>>>(d_tris, d_ids2, n_tris, d_sorted, d_raw, d_left, d_right, d_parent, d_flags, n, d_hdr, d_coef);
+    bs_mark(ctx, "bvh_moments_ms");
     if (n > 1) bs_count_launch(), k_records<<<bs_blocks(((size_t)n - 1) * 4, 256), 256, 0, st>>>(d_left, d_right, d_hdr, d_coef, n, d_rec);
     bs_free(ctx, d_raw); bs_free(ctx, d_ids2); bs_free(ctx, d_codes2); bs_free(ctx, d_left); bs_free(ctx, d_right); bs_free(ctx, d_parent); bs_free(ctx, d_flags);
     Tree T;
     T.hdr = d_hdr; T.coef = d_coef; T.rec = d_rec; T.tris = d_sorted; T.n_leaves = (unsigned)n; T.root = root_id;
-    bs_mark(ctx, "bvh_build_ms");
+    bs_mark(ctx, "bvh_records_ms");
     if (vol->n_bricks) {
         const size_t nb = vol->n_bricks;
         unsigned *d_nchunks = nullptr, *d_ordered = nullptr, *d_off = nullptr, *d_chunk_off = nullptr, *d_item_brick = nullptr, *d_order = nullptr; unsigned n_items = 0;
