@@ -373,16 +373,23 @@ __global__ void k_brick_touches(const unsigned long long* __restrict__ keys, siz
     while (table_keys[h] != key) h = (h + 1) & mask;
     touches[i] = table_counts[h];
 }
-__global__ void k_slab_bounds(const unsigned long long* __restrict__ C /*inclusive scan of touches*/, size_t n, int world, unsigned long long* bounds /*world + 1*/) {
+// cost model of a brick for the sign stage (which dominates): t = sub-triangle boxes touching it, m = mean t.
+// w = m + t + t^2 / m: linear for ordinary bricks, quadratic for bricks under dense slivers, where every voxel is "near"
+// every triangle (measured on the UV-sphere poles of config 5: t = 33 m costs ~650 ordinary bricks; t + m gave 17)
+__global__ void k_brick_weights(const unsigned long long* __restrict__ touches, const unsigned long long* __restrict__ C_touch, size_t n, unsigned long long* w) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long m = C_touch[n - 1] / n + 1, t = touches[i];
+    w[i] = m + t + t * t / m;
+}
+__global__ void k_slab_bounds(const unsigned long long* __restrict__ C /*inclusive scan of the weights*/, size_t n, int world, unsigned long long* bounds /*world + 1*/) {
     const int r = threadIdx.x;
     if (r > world) return;
     if (r == 0) { bounds[0] = 0; return; }
     if (r == world) { bounds[world] = n; return; }
-    const unsigned long long total = C[n - 1], mean = total / n + 1;
-    const unsigned long long Wtot = total + (unsigned long long)n * mean;
-    const unsigned long long target = Wtot / (unsigned long long)world * (unsigned long long)r;
-    size_t lo = 0, hi = n;  // first i with C[i] + (i+1)*mean >= target
-    while (lo < hi) { const size_t mid = (lo + hi) >> 1; if (C[mid] + (unsigned long long)(mid + 1) * mean < target) lo = mid + 1; else hi = mid; }
+    const unsigned long long target = C[n - 1] / (unsigned long long)world * (unsigned long long)r;
+    size_t lo = 0, hi = n;  // first i with C[i] >= target
+    while (lo < hi) { const size_t mid = (lo + hi) >> 1; if (C[mid] < target) lo = mid + 1; else hi = mid; }
     bounds[r] = lo;
 }
 __global__ void k_key_bounds(const unsigned long long* __restrict__ keys, size_t n, int* bounds /*min xyz, max xyz in voxels*/) {
@@ -522,8 +529,8 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
     if (world > 1) {
         // brick-slab sharding: this rank owns the contiguous slab [lo, hi) of the sorted brick list and keeps, as
         // read-only halo, the 26 neighbours of its bricks (extraction needs +1 for MC, -1..+1 for DC)
-        // slab boundaries at equal cumulative weight (weight = sub-triangle boxes touching the brick + their mean): bricks
-        // under dense triangles (e.g. the poles of a UV sphere) cost several times more in the distance and sign stages
+        // slab boundaries at equal cumulative weight (k_brick_weights): bricks under dense triangles (e.g. the poles of a
+        // UV sphere) cost hundreds of times more in the sign stage
         size_t lo, hi;
         {
             unsigned long long *d_touch = nullptr, *d_C = nullptr, *d_bounds = nullptr; unsigned long long h_bounds[2];
@@ -533,6 +540,11 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
             cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, d_touch, d_C, n_all, st);
             BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp_bytes));
             cub::DeviceScan::InclusiveSum(d_tmp, tmp_bytes, d_touch, d_C, n_all, st);
+            unsigned long long* d_w = nullptr;
+            BS_TRY(bs_alloc(ctx, &d_w, n_all));
+            bs_count_launch(), k_brick_weights<<<bs_blocks(n_all, TPB), TPB, 0, st>>>(d_touch, d_C, n_all, d_w);
+            cub::DeviceScan::InclusiveSum(d_tmp, tmp_bytes, d_w, d_C, n_all, st);
+            bs_free(ctx, d_w);
             bs_count_launch(), k_slab_bounds<<<1, 64, 0, st>>>(d_C, n_all, world, d_bounds);
             BS_CUDA(ctx, cudaMemcpyAsync(h_bounds, d_bounds + rank, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
             BS_CUDA(ctx, cudaStreamSynchronize(st));

@@ -659,14 +659,107 @@ __global__ void k_items(const unsigned* __restrict__ order, const unsigned* __re
     brick_off[b] = off[i];
     for (unsigned k = off[i]; k < off[i + 1]; ++k) item_brick[k] = b;
 }
-__global__ void k_touch_keys(const unsigned long long* __restrict__ touches, size_t n, unsigned* key, unsigned* idx) {
+__global__ void k_touch_keys(const unsigned long long* __restrict__ touches, const unsigned long long* __restrict__ total, size_t n, int shift, int buckets, unsigned* key, unsigned* idx) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const unsigned long long t = touches[i];
-    // only bricks far above the usual few hundred touches move to the front (in buckets); the rest keep their spatial
-    // (visit) order, which is what the caches like
-    const unsigned long long k = t >> 11;
-    key[i] = k > 0xFFFFFFFFull ? 0xFFFFFFFFu : (unsigned)k; idx[i] = (unsigned)i;
+    const unsigned long long t = touches[i], m = *total / n + 1;
+    // Bricks keep their spatial (visit) order, which is what the caches like, unless they sit under unusually dense
+    // triangles: those move to the front in buckets of doubling density (their items run long and must not start last;
+    // on a brick slab whose dense region comes last in key order that tail was 3 ms of an 11 ms stage).
+    // Bits 8..: heavy bricks (>= 2^shift touches), densest first; bits 0..7: log2 bucket of t / mean.
+    unsigned k = 0;
+    if (buckets && t >= 2 * m) k = 1u + (unsigned)(63 - __clzll((long long)(t / m)));  // (single GPU: the tail hides behind 30 ms of other items, plain order is 0.3 ms faster)
+    const unsigned long long hv = t >> shift;
+    key[i] = (hv ? ((hv > 0xFFFFFFull ? 0xFFFFFFu : (unsigned)hv) << 8) : 0u) | k;
+    idx[i] = (unsigned)i;
+}
+// ---- heavy bricks --------------------------------------------------------------------------------------------------------
+// A brick under thousands of sliver triangles (the pole of a UV sphere) makes every one of its items walk ~10^4 leaves:
+// milliseconds for a single warp, which is the floor of the whole stage once the bricks are spread over 4-8 GPUs.
+// Those items are split by TRIANGLES: the brick's root list is expanded breadth first into up to HEAVY_CAP small
+// sub-trees, HEAVY_REPL warps per item each walk every HEAVY_REPL-th of them, and k_sign_finish adds the partial sums in
+// a fixed order (deterministic) and sets the sign. A node that would have been accepted as far may be replaced by its
+// descendants here, each still tested with the per-voxel criterion: never less accurate than the unsplit walk.
+constexpr int HEAVY_CAP = 1024, HEAVY_REPL = 16;  // <= HEAVY_CAP / HEAVY_REPL = 64 roots per replica (MAX_ROOTS = 96)
+struct HeavyRoots { unsigned n; unsigned ids[HEAVY_CAP]; };
+struct HeavySplit { unsigned repl, n_hitems; const HeavyRoots* roots; const unsigned* slot_of_brick; float* partial; unsigned short* offs; };
+
+// one warp per heavy brick. Entries are expanded by SIZE (leaves under a Karras node i: |i - other[i]| + 1): every round
+// replaces the internal entries holding more than 1/256 of the list's leaves by the entries of their records, so the
+// fan of slivers ends up in a few hundred pieces of similar size that the replicas share round-robin.
+__global__ void __launch_bounds__(128) k_expand_roots(Tree T, const int* __restrict__ other, const unsigned* __restrict__ heavy_bricks, unsigned n_heavy, const BrickOut* __restrict__ brick_out, HeavyRoots* out) {
+    __shared__ unsigned s_l[4][2][HEAVY_CAP];
+    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5, h = blockIdx.x * 4 + w;
+    if (h >= n_heavy) return;
+    const BrickOut* bo = brick_out + heavy_bricks[h];
+    unsigned n = bo->n_roots;
+    if (n == 0xFFFFFFFFu) { if (lane == 0) s_l[w][0][0] = T.root; n = 1; }
+    else for (unsigned i = lane; i < n; i += 32) s_l[w][0][i] = bo->roots[i];
+    __syncwarp();
+    auto size_of = [&](unsigned id) -> unsigned { return id >= T.n_leaves - 1 ? 1u : (unsigned)abs((int)id - other[id]) + 1u; };
+    int cur = 0;
+    for (int round = 0; round < 24; ++round) {
+        unsigned leaves = 0;
+        for (unsigned i = lane; i < n; i += 32) leaves += size_of(s_l[w][cur][i]);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) leaves += __shfl_xor_sync(0xFFFFFFFFu, leaves, o);
+        const unsigned thr = max(16u, leaves / 256u);
+        unsigned total = 0, big = 0;
+        for (unsigned base = 0; base < n; base += 32) {
+            const unsigned i = base + lane;
+            unsigned c = 0;
+            if (i < n) {
+                const unsigned id = s_l[w][cur][i];
+                if (size_of(id) <= thr) c = 1;
+                else { const float4 idsf = __ldg(T.rec + (size_t)id * REC + 4); c = 2 + (__float_as_int(idsf.z) >= 0) + (__float_as_int(idsf.w) >= 0); big = 1; }
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+            total += c;
+        }
+        if (!__any_sync(0xFFFFFFFFu, big) || total > (unsigned)HEAVY_CAP) break;
+        unsigned wr = 0;
+        for (unsigned base = 0; base < n; base += 32) {
+            const unsigned i = base + lane;
+            int ids[4] = {-1, -1, -1, -1}; unsigned c = 0;
+            if (i < n) {
+                const unsigned id = s_l[w][cur][i];
+                if (size_of(id) <= thr) { ids[0] = (int)id; c = 1; }
+                else { const float4 idsf = __ldg(T.rec + (size_t)id * REC + 4); ids[0] = __float_as_int(idsf.x); ids[1] = __float_as_int(idsf.y); ids[2] = __float_as_int(idsf.z); ids[3] = __float_as_int(idsf.w); c = 2 + (ids[2] >= 0) + (ids[3] >= 0); }
+            }
+            unsigned inc = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if ((int)lane >= o) inc += t; }
+            unsigned p = wr + inc - c;
+            for (int k = 0; k < 4; ++k) if (ids[k] >= 0) s_l[w][cur ^ 1][p++] = (unsigned)ids[k];
+            wr += __shfl_sync(0xFFFFFFFFu, inc, 31);
+        }
+        __syncwarp();
+        cur ^= 1; n = wr;
+    }
+    HeavyRoots* o = out + h;
+    if (lane == 0) o->n = n;
+    for (unsigned i = lane; i < n; i += 32) o->ids[i] = s_l[w][cur][i];
+}
+
+// one warp per heavy item: partial sums in replica order, then the sign (mesh_to_volume.rs:266-271)
+template <int VPL>
+__global__ void k_sign_finish(float* values, const unsigned* __restrict__ item_brick, unsigned first_item, unsigned n_items, unsigned repl, const float* __restrict__ partial, const unsigned short* __restrict__ offs) {
+    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (t >= (size_t)n_items * 32 * VPL) return;
+    const size_t it = t / (32 * VPL); const unsigned slot = (unsigned)(t % (32 * VPL));
+    const unsigned off = offs[t];
+    if (off == 0xFFFFu) return;
+    float wn = 0.f;
+    for (unsigned r = 0; r < repl; ++r) wn += partial[(it * repl + r) * (32 * VPL) + slot];
+    float* bv = values + (size_t)item_brick[first_item + it] * 512;
+    const float d = bv[off];
+    bv[off] = (wn < 0.2f) ? copysignf(d, 1.0f) : copysignf(d, -1.0f);
+}
+__global__ void k_heavy_list(const unsigned* __restrict__ order, const unsigned* __restrict__ keys_sorted_desc, size_t n, unsigned* heavy_bricks, unsigned* slot_of_brick, unsigned* n_heavy) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if ((keys_sorted_desc[i] >> 8) > 0) { heavy_bricks[i] = order[i]; slot_of_brick[order[i]] = (unsigned)i; atomicMax(n_heavy, (unsigned)i + 1); }  // heavy bricks are the first entries of `order`
 }
 
 // One WARP per work item (32*VPL Morton-adjacent active voxels of one brick): a heavy brick (e.g. at the pole of a UV
@@ -677,13 +770,20 @@ template <bool COUNT, int VPL>
 #endif
 __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, BS_SIGN_MINB) k_sign(Tree T, float* values, const unsigned long long* __restrict__ masks, unsigned n_items,
                                                                const unsigned* __restrict__ item_brick, const unsigned* __restrict__ chunk_off,
-                                                               const unsigned long long* __restrict__ keys, float vs, const BrickOut* __restrict__ brick_out, unsigned long long* counters) {
+                                                               const unsigned long long* __restrict__ keys, float vs, const BrickOut* __restrict__ brick_out, unsigned long long* counters,
+                                                               HeavySplit H) {
     __shared__ unsigned s_stack[WARPS_PER_BLOCK][STACK * (1 + VPL)];
     __shared__ unsigned short s_list[WARPS_PER_BLOCK][32 * VPL];
     __shared__ float s_far[WARPS_PER_BLOCK][27];
     __shared__ unsigned s_roots[WARPS_PER_BLOCK][MAX_ROOTS];
     const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const unsigned item = blockIdx.x * WARPS_PER_BLOCK + w;
+    // The first H.n_hitems items belong to heavy bricks: H.repl warps each, replica r walks every H.repl-th entry of the
+    // brick's expanded root list and leaves a partial sum for k_sign_finish. All other items: one warp. One launch, so
+    // the ordinary items fill the SMs while the long replicas run.
+    const unsigned wi = blockIdx.x * WARPS_PER_BLOCK + w;
+    const unsigned nhw = H.n_hitems * H.repl;
+    const bool heavy = wi < nhw;
+    const unsigned item = heavy ? wi / H.repl : H.n_hitems + (wi - nhw), rep = heavy ? wi % H.repl : 0;
     if (item >= n_items) return;
     const size_t b = item_brick[item];
     const unsigned chunk = item - chunk_off[b];
@@ -694,7 +794,14 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, BS_SIGN_MINB) k_sign(Tre
         const BrickOut* bo = brick_out + b;
         const unsigned nr = bo->n_roots;
         if (lane < 27) s_far[w][lane] = bo->far[lane];
-        if (nr == 0xFFFFFFFFu) { if (lane == 0) s_roots[w][0] = T.root; n_roots = 1; }
+        if (heavy) {
+            const HeavyRoots* hr = H.roots + H.slot_of_brick[b];
+            const unsigned n_all = hr->n;
+            n_roots = 0;
+            for (unsigned i = rep + lane * H.repl; i < n_all; i += 32 * H.repl) s_roots[w][(i - rep) / H.repl] = hr->ids[i];
+            n_roots = (int)((n_all > rep) ? (n_all - rep + H.repl - 1) / H.repl : 0);
+        }
+        else if (nr == 0xFFFFFFFFu) { if (lane == 0) s_roots[w][0] = T.root; n_roots = 1; }
         else {
             for (unsigned i = lane; i < nr; i += 32) {
                 const unsigned rid = bo->roots[i];
@@ -749,9 +856,19 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, BS_SIGN_MINB) k_sign(Tre
                     const float wij = L[0][i2] * L[1][j];
                     acc = fmaf(wij, fmaf(L[2][0], s_far[w][i2 * 9 + j * 3], fmaf(L[2][1], s_far[w][i2 * 9 + j * 3 + 1], L[2][2] * s_far[w][i2 * 9 + j * 3 + 2])), acc);
                 }
-            W.wn[v] = acc;
+            W.wn[v] = (heavy && rep) ? 0.f : acc;  // the hoisted part is counted once
         }
+        __syncwarp();
         W.run(valid_m, s_roots[w], n_roots);
+        if (heavy) {  // partial sums and (once) the voxel offsets, for the finish kernel
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                H.partial[((size_t)item * H.repl + rep) * (32 * VPL) + v * 32 + lane] = W.wn[v];
+                if (rep == 0) H.offs[(size_t)item * (32 * VPL) + v * 32 + lane] = valid[v] ? (unsigned short)off[v] : (unsigned short)0xFFFFu;
+            }
+            if (COUNT) { if (rep == 0) { for (int v = 0; v < VPL; ++v) if (valid[v]) atomicAdd(counters + 3, 1ull); } atomicAdd(counters, (unsigned long long)c3[0]); atomicAdd(counters + 1, (unsigned long long)c3[1]); atomicAdd(counters + 2, (unsigned long long)c3[2]); atomicAdd(counters + 4, (unsigned long long)c3[3]); atomicAdd(counters + 5, (unsigned long long)(lane == 0)); }
+            return;
+        }
 #pragma unroll
         for (int v = 0; v < VPL; ++v) {
             if (!valid[v]) continue;
@@ -805,7 +922,7 @@ bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_v
     bs_count_launch(), k_leaves_and_climb<<<bs_blocks((size_t)n, CLIMB_TPB), CLIMB_TPB, 0, st>>>(d_tris, d_ids2, n_tris, d_sorted, d_raw, d_left, d_right, d_parent, d_other, d_flags, n, d_hdr, d_coef);
     bs_mark(ctx, "bvh_moments_ms");
     if (n > 1) bs_count_launch(), k_records<<<bs_blocks(((size_t)n - 1) * 4, 256), 256, 0, st>>>(d_left, d_right, d_hdr, d_coef, n, d_rec);
-    bs_free(ctx, d_raw); bs_free(ctx, d_ids2); bs_free(ctx, d_codes2); bs_free(ctx, d_left); bs_free(ctx, d_right); bs_free(ctx, d_parent); bs_free(ctx, d_flags); bs_free(ctx, d_other);
+    bs_free(ctx, d_raw); bs_free(ctx, d_ids2); bs_free(ctx, d_codes2); bs_free(ctx, d_left); bs_free(ctx, d_right); bs_free(ctx, d_parent); bs_free(ctx, d_flags);
     Tree T;
     T.hdr = d_hdr; T.coef = d_coef; T.rec = d_rec; T.tris = d_sorted; T.n_leaves = (unsigned)n; T.root = root_id;
     bs_mark(ctx, "bvh_records_ms");
@@ -814,15 +931,33 @@ bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_v
         unsigned *d_nchunks = nullptr, *d_ordered = nullptr, *d_off = nullptr, *d_chunk_off = nullptr, *d_item_brick = nullptr, *d_order = nullptr; unsigned n_items = 0;
         BS_TRY(bs_alloc(ctx, &d_nchunks, nb)); BS_TRY(bs_alloc(ctx, &d_ordered, nb + 1)); BS_TRY(bs_alloc(ctx, &d_off, nb + 1)); BS_TRY(bs_alloc(ctx, &d_chunk_off, nb));
         bs_count_launch(), k_masks<<<bs_blocks(nb * 32, 256), 256, 0, st>>>(vol->values, nb, vol->masks, d_nchunks, 32 * BS_VPL);
-        if (d_touches) {  // heaviest bricks first
+        unsigned *d_heavy = nullptr, *d_slot = nullptr, *d_nheavy = nullptr; unsigned n_heavy = 0, n_hitems = 0;
+        if (d_touches) {  // heaviest bricks first; bricks with >= 2^shift touching sub-triangle boxes are "heavy" (split by triangles)
+            int shift = 11;
+            // On one GPU the long items simply start first and hide behind the rest (splitting them costs 1.6 ms of extra
+            // launches and refinement on config 5); on a brick slab they ARE the stage time, so sharded runs split.
+            bool split = vol->owned != nullptr;
+            if (const char* e = getenv("BSHARK_HEAVY_SHIFT")) { shift = atoi(e); split = true; }  // tests: force the heavy path on small meshes
             unsigned *d_k = nullptr, *d_k2 = nullptr, *d_i = nullptr;
             BS_TRY(bs_alloc(ctx, &d_k, nb)); BS_TRY(bs_alloc(ctx, &d_k2, nb)); BS_TRY(bs_alloc(ctx, &d_i, nb)); BS_TRY(bs_alloc(ctx, &d_order, nb));
-            bs_count_launch(), k_touch_keys<<<bs_blocks(nb, 256), 256, 0, st>>>(d_touches, nb, d_k, d_i);
+            BS_TRY(bs_alloc(ctx, &d_heavy, nb)); BS_TRY(bs_alloc(ctx, &d_slot, nb)); BS_TRY(bs_alloc(ctx, &d_nheavy, 1));
+            BS_CUDA(ctx, cudaMemsetAsync(d_nheavy, 0, sizeof(unsigned), st));
+            unsigned long long* d_tot = nullptr;
+            BS_TRY(bs_alloc(ctx, &d_tot, 1));
+            tmp_bytes = 0;
+            cub::DeviceReduce::Sum(nullptr, tmp_bytes, d_touches, d_tot, (int)nb, st);
+            BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp_bytes));
+            cub::DeviceReduce::Sum(d_tmp, tmp_bytes, d_touches, d_tot, (int)nb, st);
+            bs_free(ctx, d_tmp);
+            bs_count_launch(), k_touch_keys<<<bs_blocks(nb, 256), 256, 0, st>>>(d_touches, d_tot, nb, shift, split ? 1 : 0, d_k, d_i);
+            bs_free(ctx, d_tot);
             tmp_bytes = 0;
             cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, d_k, d_k2, d_i, d_order, nb, 0, 32, st);
             BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp_bytes));
             cub::DeviceRadixSort::SortPairsDescending(d_tmp, tmp_bytes, d_k, d_k2, d_i, d_order, nb, 0, 32, st);
-            bs_free(ctx, d_tmp); bs_free(ctx, d_k); bs_free(ctx, d_k2); bs_free(ctx, d_i);
+            if (split) bs_count_launch(), k_heavy_list<<<bs_blocks(nb, 256), 256, 0, st>>>(d_order, d_k2, nb, d_heavy, d_slot, d_nheavy);
+            BS_CUDA(ctx, cudaMemcpyAsync(&n_heavy, d_nheavy, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+            bs_free(ctx, d_tmp); bs_free(ctx, d_k); bs_free(ctx, d_k2); bs_free(ctx, d_i); bs_free(ctx, d_nheavy);
         }
         bs_count_launch(), k_order_chunks<<<bs_blocks(nb + 1, 256), 256, 0, st>>>(d_order, d_nchunks, nb, d_ordered);
         tmp_bytes = 0;
@@ -830,35 +965,51 @@ bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_v
         BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp_bytes));
         cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_ordered, d_off, nb + 1, st);
         BS_CUDA(ctx, cudaMemcpyAsync(&n_items, d_off + nb, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-        BS_CUDA(ctx, cudaStreamSynchronize(st));
+        BS_CUDA(ctx, cudaStreamSynchronize(st));  // n_heavy has arrived too
+        if (n_heavy) {  // the heavy bricks head `order`: their items are items [0, n_hitems)
+            BS_CUDA(ctx, cudaMemcpyAsync(&n_hitems, d_off + n_heavy, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+            BS_CUDA(ctx, cudaStreamSynchronize(st));
+        }
         bs_free(ctx, d_tmp); bs_free(ctx, d_nchunks); bs_free(ctx, d_ordered);
         BS_TRY(bs_alloc(ctx, &d_item_brick, n_items));
         bs_count_launch(), k_items<<<bs_blocks(nb, 256), 256, 0, st>>>(d_order, d_off, nb, d_item_brick, d_chunk_off);
         bs_free(ctx, d_off); bs_free(ctx, d_order);
-        const size_t blocks = (n_items + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
         BrickOut* d_bo = nullptr;
         float kappa = KAPPA_DEFAULT;
         if (const char* e = getenv("BSHARK_KAPPA")) kappa = (float)atof(e);  // tuning knob for experiments only
         BS_TRY(bs_alloc(ctx, &d_bo, nb));
+        HeavyRoots* d_hr = nullptr; float* d_partial = nullptr; unsigned short* d_offs = nullptr;
+        if (n_hitems) {
+            BS_TRY(bs_alloc(ctx, &d_hr, n_heavy)); BS_TRY(bs_alloc(ctx, &d_partial, (size_t)n_hitems * HEAVY_REPL * 32 * BS_VPL)); BS_TRY(bs_alloc(ctx, &d_offs, (size_t)n_hitems * 32 * BS_VPL));
+        }
+        const HeavySplit H{(unsigned)HEAVY_REPL, n_hitems, d_hr, d_slot, d_partial, d_offs};
+        const size_t n_warps = (size_t)n_hitems * HEAVY_REPL + (n_items - n_hitems);
+        const unsigned blocks = (unsigned)((n_warps + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+        unsigned long long* d_cnt = nullptr;
+        if (ctx->count_work) { BS_TRY(bs_alloc(ctx, &d_cnt, 9)); BS_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, 72, st)); }
+        if (ctx->count_work) bs_count_launch(), k_brick_pass<true><<<bs_blocks(nb, BP_WARPS), 32 * BP_WARPS, 0, st>>>(T, vol->keys, nb, vol->voxel_size, kappa, d_bo, d_cnt);
+        else bs_count_launch(), k_brick_pass<false><<<bs_blocks(nb, BP_WARPS), 32 * BP_WARPS, 0, st>>>(T, vol->keys, nb, vol->voxel_size, kappa, d_bo, nullptr);
+        if (!ctx->count_work) bs_mark(ctx, "sign_brick_pass_ms");
+        if (n_hitems) bs_count_launch(), k_expand_roots<<<bs_blocks(n_heavy, 4), 128, 0, st>>>(T, d_other, d_heavy, n_heavy, d_bo, d_hr);
+        if (n_items) {
+            if (ctx->count_work) bs_count_launch(), k_sign<true, BS_VPL><<<blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(T, vol->values, vol->masks, n_items, d_item_brick, d_chunk_off, vol->keys, vol->voxel_size, d_bo, d_cnt, H);
+            else bs_count_launch(), k_sign<false, BS_VPL><<<blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(T, vol->values, vol->masks, n_items, d_item_brick, d_chunk_off, vol->keys, vol->voxel_size, d_bo, nullptr, H);
+        }
+        if (n_hitems) bs_count_launch(), k_sign_finish<BS_VPL><<<bs_blocks((size_t)n_hitems * 32 * BS_VPL, 256), 256, 0, st>>>(vol->values, d_item_brick, 0u, n_hitems, (unsigned)HEAVY_REPL, d_partial, d_offs);
         if (ctx->count_work) {
-            unsigned long long* d_cnt = nullptr; unsigned long long h_cnt[9];
-            BS_TRY(bs_alloc(ctx, &d_cnt, 9));
-            BS_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, 72, st));
-            bs_count_launch(), k_brick_pass<true><<<bs_blocks(nb, BP_WARPS), 32 * BP_WARPS, 0, st>>>(T, vol->keys, nb, vol->voxel_size, kappa, d_bo, d_cnt);
-            if (n_items) bs_count_launch(), k_sign<true, BS_VPL><<<(unsigned)blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(T, vol->values, vol->masks, n_items, d_item_brick, d_chunk_off, vol->keys, vol->voxel_size, d_bo, d_cnt);
+            unsigned long long h_cnt[9];
             BS_CUDA(ctx, cudaMemcpyAsync(h_cnt, d_cnt, 72, cudaMemcpyDeviceToHost, st));
             BS_CUDA(ctx, cudaStreamSynchronize(st));
             bs_free(ctx, d_cnt);
             for (int i = 0; i < 9; ++i) ctx->fwn_counts[i] = (double)h_cnt[i];
-        } else {
-            bs_count_launch(), k_brick_pass<false><<<bs_blocks(nb, BP_WARPS), 32 * BP_WARPS, 0, st>>>(T, vol->keys, nb, vol->voxel_size, kappa, d_bo, nullptr);
-            bs_mark(ctx, "sign_brick_pass_ms");
-            if (n_items) bs_count_launch(), k_sign<false, BS_VPL><<<(unsigned)blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(T, vol->values, vol->masks, n_items, d_item_brick, d_chunk_off, vol->keys, vol->voxel_size, d_bo, nullptr);
         }
+        bs_stat_add(ctx, "n_heavy_bricks", (double)n_heavy);
+        bs_stat_add(ctx, "n_heavy_items", (double)n_hitems);
+        bs_free(ctx, d_hr); bs_free(ctx, d_partial); bs_free(ctx, d_offs); bs_free(ctx, d_heavy); bs_free(ctx, d_slot);
         bs_free(ctx, d_bo); bs_free(ctx, d_chunk_off); bs_free(ctx, d_item_brick);
     }
     bs_mark(ctx, "sign_ms");
-    bs_free(ctx, d_sorted); bs_free(ctx, d_hdr); bs_free(ctx, d_coef); bs_free(ctx, d_rec);
+    bs_free(ctx, d_sorted); bs_free(ctx, d_hdr); bs_free(ctx, d_coef); bs_free(ctx, d_rec); bs_free(ctx, d_other);
     BS_CUDA(ctx, cudaGetLastError());
     return BS_OK;
 }

@@ -172,3 +172,31 @@ def test_bunny_open_mesh_sign_agreement(bs, oracle, bunny):
         pts = (o["origins"][idx[:, 0]] + np.stack([idx[:, 1] >> 6, (idx[:, 1] >> 3) & 7, idx[:, 1] & 7], 1)).astype(np.float32) * np.float32(vs)
         wn_exact, _ = oracle.winding_numbers(bunny, pts[:200], beta=-1.0)
         assert (np.abs(wn_exact - 0.2) < 0.15).all(), wn_exact
+
+
+@pytest.mark.parametrize("shift", [4, 7])
+def test_heavy_brick_split_gives_the_same_volume(bs, oracle, shift, monkeypatch):
+    # bricks under many triangles are signed by 16 warps per work item, each walking a share of an expanded root list
+    # (bs_fwn.cu "heavy bricks"); BSHARK_HEAVY_SHIFT lowers the threshold so that small test meshes take that path
+    from baby_shark_b200 import synth
+    monkeypatch.setenv("BSHARK_HEAVY_SHIFT", str(shift))
+    for cfg, scale in ((5, 0.05), (3, 0.06)):
+        tris, vs, _ = synth.config_mesh(cfg, scale)
+        g = bs.MeshToVolume().with_voxel_size(vs).convert(tris)
+        assert bs.Context.default().last_stats()["n_heavy_bricks"] > 0
+        o, _ = oracle.mesh_to_volume(tris, vs, 0, 8)
+        compare_volumes(g.download(), o.download(), vs)
+    monkeypatch.delenv("BSHARK_HEAVY_SHIFT")
+    g2 = bs.MeshToVolume().with_voxel_size(vs).convert(tris)
+    assert np.array_equal(g.download()["values"].view(np.uint32), g2.download()["values"].view(np.uint32))
+
+
+def test_heavy_split_on_open_mesh_matches_unsplit_signs(bs, bunny, monkeypatch):
+    a = bs.MeshToVolume().with_voxel_size(0.5).convert(bunny).download()
+    monkeypatch.setenv("BSHARK_HEAVY_SHIFT", "5")
+    b = bs.MeshToVolume().with_voxel_size(0.5).convert(bunny).download()
+    assert bs.Context.default().last_stats()["n_heavy_bricks"] > 0
+    from util import active_mask_bits
+    m = active_mask_bits(a["masks"])
+    diff = np.signbit(a["values"][m]) != np.signbit(b["values"][m])
+    assert diff.mean() < 2e-3  # the split walk refines some far nodes: only voxels at the 0.2 threshold may move
