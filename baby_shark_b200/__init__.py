@@ -184,8 +184,8 @@ class Volume:
         self._h, self._ctx = handle, ctx
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            load_library().bs_volume_free(self._h)
+        if getattr(self, "_h", None) and _lib is not None:  # at interpreter shutdown the module globals may be gone already
+            _lib.bs_volume_free(self._h)
             self._h = None
 
     @staticmethod
@@ -447,8 +447,8 @@ class DeviceTriangles:
         self.ptr, self.n_tris, self._ctx = ptr, n_tris, ctx
 
     def __del__(self):
-        if getattr(self, "ptr", None):
-            load_library().bs_device_free(self._ctx._h, self.ptr)
+        if getattr(self, "ptr", None) and _lib is not None:
+            _lib.bs_device_free(self._ctx._h, self.ptr)
             self.ptr = None
 
     def numpy(self):
