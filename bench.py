@@ -48,8 +48,8 @@ def parse():
 
 def workload(cfg, scale):
     from baby_shark_b200 import synth
-    if cfg not in (3, 4, 5):
-        raise SystemExit("the remesh bench takes --config 3, 4 or 5")
+    if cfg not in (1, 3, 4, 5):
+        raise SystemExit("the remesh bench takes --config 1, 3, 4 or 5")
     tris, vs, desc = synth.config_mesh(cfg, scale)
     return np.ascontiguousarray(tris, np.float32), float(vs), desc
 
@@ -297,7 +297,7 @@ def run_reference(args, rank, world):
 
 
 def workload_desc(args):
-    names = {3: "UV sphere ~1.0M triangles at 1024^3", 4: "noise-displaced UV sphere 2.0M triangles at 1024^3",
+    names = {1: "voxel_remeshing example, assets/bunny.stl at voxel_size 0.01 (open mesh)", 3: "UV sphere ~1.0M triangles at 1024^3", 4: "noise-displaced UV sphere 2.0M triangles at 1024^3",
              5: "noise-displaced UV sphere ~10.0M triangles at 2048^3"}
     return "%s, voxel remesh (convert + MC33), scale %g" % (names[args.config], args.scale)
 
