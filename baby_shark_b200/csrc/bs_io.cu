@@ -82,8 +82,15 @@ __device__ __forceinline__ long long av_find_key(const u64* keys, size_t n, u64 
 }
 // One warp per brick. s_m[0] = the brick's mask words, s_m[1 + d] = those of the face neighbour d (+z -z -x +x +y -y,
 // the reference's probe order top bottom left right front back), zeros when absent.
+struct AvTiles { const u64* t8k; size_t nt8; const u64* t128k; size_t nt128; };
+// active tile (8^3 keyed like a brick, 128^3 keyed by key >> 12) covering brick (bx, by, bz)?
+__device__ __forceinline__ bool av_tile_covers(const AvTiles& Tl, int bx, int by, int bz) {
+    if (bx < BS_BRICK_MIN || bx > BS_BRICK_MAX || by < BS_BRICK_MIN || by > BS_BRICK_MAX || bz < BS_BRICK_MIN || bz > BS_BRICK_MAX) return false;
+    const u64 k = bs_brick_key(bx, by, bz);
+    return (Tl.nt8 && av_find_key(Tl.t8k, Tl.nt8, k) >= 0) || (Tl.nt128 && av_find_key(Tl.t128k, Tl.nt128, k >> 12) >= 0);
+}
 template <bool WRITE>
-__global__ void __launch_bounds__(128) k_active_voxels(const u64* __restrict__ keys, const u64* __restrict__ masks, size_t n, unsigned* counts, const u64* __restrict__ offsets, int* out) {
+__global__ void __launch_bounds__(128) k_active_voxels(const u64* __restrict__ keys, const u64* __restrict__ masks, size_t n, AvTiles Tl, const unsigned* __restrict__ pos, unsigned* counts, const u64* __restrict__ offsets, int* out) {
     __shared__ u64 s_m[4][7][8];
     const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const size_t b = (size_t)blockIdx.x * 4 + w;
@@ -96,9 +103,13 @@ __global__ void __launch_bounds__(128) k_active_voxels(const u64* __restrict__ k
         if (x >= BS_BRICK_MIN && x <= BS_BRICK_MAX && y >= BS_BRICK_MIN && y <= BS_BRICK_MAX && z >= BS_BRICK_MIN && z <= BS_BRICK_MAX) nb = av_find_key(keys, n, bs_brick_key(x, y, z));
     }
     if (lane == 0) nb = (long long)b;
+    if (lane >= 1 && lane < 7 && nb < 0 && (Tl.nt8 | Tl.nt128)) {  // no brick there: an active tile reads as all active (grid.at is Some)
+        const int d = lane - 1;
+        if (av_tile_covers(Tl, bx + N[d][0], by + N[d][1], bz + N[d][2])) nb = -2;
+    }
     for (int k = 0; k < 7; ++k) {
         const long long src = __shfl_sync(0xFFFFFFFFu, nb, k);
-        if (lane < 8) s_m[w][k][lane] = src >= 0 ? masks[(size_t)src * 8 + lane] : 0ull;
+        if (lane < 8) s_m[w][k][lane] = src >= 0 ? masks[(size_t)src * 8 + lane] : (src == -2 ? ~0ull : 0ull);
     }
     __syncwarp();
     auto active = [&](int x, int y, int z) -> bool {  // (x, y, z) in -1..8, at most one coordinate outside 0..7
@@ -108,7 +119,8 @@ __global__ void __launch_bounds__(128) k_active_voxels(const u64* __restrict__ k
     };
     const int B[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0}, {0, 0, 1}, {1, 0, 1}, {1, 1, 1}, {0, 1, 1}};  // CUBE_OFFSETS (voxel/utils.rs:86-95)
     const int F[6][6] = {{4, 6, 7, 4, 5, 6}, {1, 0, 3, 1, 3, 2}, {0, 4, 3, 4, 7, 3}, {1, 6, 5, 1, 2, 6}, {2, 3, 6, 6, 3, 7}, {1, 5, 0, 5, 4, 0}};
-    unsigned long long run = WRITE ? offsets[b] : 0ull;
+    const size_t item = pos ? pos[b] : b;  // rank among bricks and tiles in visit order
+    unsigned long long run = WRITE ? offsets[item] : 0ull;
     unsigned total = 0;
     for (int r = 0; r < 16; ++r) {  // voxels in leaf order x<<6 | y<<3 | z
         const unsigned o = r * 32 + lane;
@@ -133,7 +145,75 @@ __global__ void __launch_bounds__(128) k_active_voxels(const u64* __restrict__ k
         const unsigned rt = __shfl_sync(0xFFFFFFFFu, inc, 31);
         run += rt; total += rt;
     }
-    if (!WRITE && lane == 0) counts[b] = total;  // open faces of the brick
+    if (!WRITE && lane == 0) counts[item] = total;  // open faces of the brick
+}
+
+// is voxel (x, y, z) active (in a brick with its bit set, or inside an active tile)?  TreeNode::at(...).is_some()
+__device__ bool av_voxel_active(const u64* __restrict__ keys, const u64* __restrict__ masks, size_t n, const AvTiles& Tl, int x, int y, int z) {
+    const int bx = x >> 3, by = y >> 3, bz = z >> 3;
+    if (bx < BS_BRICK_MIN || bx > BS_BRICK_MAX || by < BS_BRICK_MIN || by > BS_BRICK_MAX || bz < BS_BRICK_MIN || bz > BS_BRICK_MAX) return false;
+    const long long b = av_find_key(keys, n, bs_brick_key(bx, by, bz));
+    if (b >= 0) return (masks[(size_t)b * 8 + (x & 7)] >> (((y & 7) << 3) | (z & 7))) & 1ull;
+    return av_tile_covers(Tl, bx, by, bz);
+}
+// Active tiles (active_voxels.rs:128-151): only boundary voxels are tested, for every (i, j) in the order left, right,
+// top, bottom, front, back -- edge and corner voxels several times, duplicates are emitted as the reference does.
+// One CTA per tile; candidates (6 per (i, j)) are taken 256 at a time and block-scanned to keep that order.
+template <bool WRITE>
+__global__ void __launch_bounds__(256) k_active_voxels_tiles(const u64* __restrict__ keys, const u64* __restrict__ masks, size_t n, AvTiles Tl, int level /*0: 8^3, 1: 128^3*/,
+                                                             const unsigned* __restrict__ pos, unsigned* counts, const u64* __restrict__ offsets, int* out) {
+    typedef cub::BlockScan<unsigned, 256> Scan;
+    __shared__ typename Scan::TempStorage tmp;
+    const size_t t = blockIdx.x;
+    const int size = level ? 128 : 8;
+    int ox, oy, oz;
+    {
+        int bx, by, bz;
+        if (level) bs_key_brick(Tl.t128k[t] << 12, bx, by, bz); else bs_key_brick(Tl.t8k[t], bx, by, bz);
+        ox = bx << 3; oy = by << 3; oz = bz << 3;
+    }
+    const int N[6][3] = {{0, 0, 1}, {0, 0, -1}, {-1, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, -1, 0}};
+    const int B[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0}, {0, 0, 1}, {1, 0, 1}, {1, 1, 1}, {0, 1, 1}};
+    const int F[6][6] = {{4, 6, 7, 4, 5, 6}, {1, 0, 3, 1, 3, 2}, {0, 4, 3, 4, 7, 3}, {1, 6, 5, 1, 2, 6}, {2, 3, 6, 6, 3, 7}, {1, 5, 0, 5, 4, 0}};
+    const size_t item = pos[t];
+    unsigned long long run = WRITE ? offsets[item] : 0ull;
+    unsigned long long total = 0;
+    const unsigned n_cand = 6u * (unsigned)size * (unsigned)size;
+    for (unsigned base = 0; base < n_cand; base += 256) {
+        const unsigned c = base + threadIdx.x;
+        unsigned open = 0; int vx = 0, vy = 0, vz = 0;
+        if (c < n_cand) {
+            const int pair = (int)(c / 6), which = (int)(c % 6), i = pair / size, j = pair % size, s1 = size - 1;
+            const int lx = which == 0 ? 0 : (which == 1 ? s1 : i), ly = which < 2 ? i : (which < 4 ? j : (which == 4 ? s1 : 0)), lz = which < 2 ? j : (which == 2 ? s1 : (which == 3 ? 0 : j));
+            vx = ox + lx; vy = oy + ly; vz = oz + lz;
+            for (int d = 0; d < 6; ++d) {
+                const int qx = lx + N[d][0], qy = ly + N[d][1], qz = lz + N[d][2];
+                const bool inside = qx >= 0 && qx < size && qy >= 0 && qy < size && qz >= 0 && qz < size;
+                if (!inside && !av_voxel_active(keys, masks, n, Tl, ox + qx, oy + qy, oz + qz)) open |= 1u << d;
+            }
+        }
+        const unsigned cnt = __popc(open);
+        unsigned excl, sum;
+        Scan(tmp).ExclusiveSum(cnt, excl, sum);
+        if (WRITE && open) {
+            int* dst = out + (run + excl) * 18;
+            for (int d = 0; d < 6; ++d) {
+                if (!((open >> d) & 1)) continue;
+                for (int k = 0; k < 6; ++k) { const int* cc = B[F[d][k]]; dst[0] = vx + cc[0]; dst[1] = vy + cc[1]; dst[2] = vz + cc[2]; dst += 3; }
+            }
+        }
+        run += sum; total += sum;
+        __syncthreads();
+    }
+    if (!WRITE && threadIdx.x == 0) counts[item] = (unsigned)total;
+}
+// rank of every brick / tile in the merged key order (a 128^3 tile sorts by its 16^3-node key), as in bs_mc.cu
+__global__ void k_av_merge_pos(const u64* __restrict__ keys, size_t n, AvTiles Tl, unsigned* pos_brick, unsigned* pos_t8, unsigned* pos_t128) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    auto lb = [](const u64* k, size_t m, u64 key, int shift) { size_t lo = 0, hi = m; while (lo < hi) { const size_t mid = (lo + hi) >> 1; if ((k[mid] << shift) < key) lo = mid + 1; else hi = mid; } return (unsigned)lo; };
+    if (i < n) pos_brick[i] = (unsigned)i + lb(Tl.t8k, Tl.nt8, keys[i], 0) + lb(Tl.t128k, Tl.nt128, keys[i], 12);
+    if (i < Tl.nt8) pos_t8[i] = (unsigned)i + lb(keys, n, Tl.t8k[i], 0) + lb(Tl.t128k, Tl.nt128, Tl.t8k[i], 12);
+    if (i < Tl.nt128) pos_t128[i] = (unsigned)i + lb(keys, n, Tl.t128k[i] << 12, 0) + lb(Tl.t8k, Tl.nt8, Tl.t128k[i] << 12, 0);
 }
 __global__ void k_widen_u32(const unsigned* in, u64* out, size_t n) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -225,25 +305,36 @@ bs_status bs_active_voxels_impl(const bs_volume* v, int** d_verts, size_t* n_ver
     bs_context* ctx = v->ctx;
     cudaStream_t st = ctx->stream;
     *d_verts = nullptr; *n_verts = 0;
-    if (v->n_tiles8 || v->n_tiles128) return bs_fail(ctx, BS_ERR_UNSUPPORTED, "ActiveVoxelsMesher on a volume with active tiles is not implemented on the device");
-    const size_t n = v->n_bricks;
-    if (n == 0) return BS_OK;
+    const size_t n = v->n_bricks, nt8 = v->n_tiles8, nt128 = v->n_tiles128, n_items = n + nt8 + nt128;
+    if (n_items == 0) return BS_OK;
+    if (nt128 > 64) return bs_fail(ctx, BS_ERR_UNSUPPORTED, "ActiveVoxelsMesher: %zu active 128^3 tiles (98 304 boundary probes each)", nt128);
     bs_marks_begin(ctx);
-    unsigned* d_cnt = nullptr; u64 *d_wide = nullptr, *d_off = nullptr; void* d_tmp = nullptr; size_t tmp = 0;
-    BS_TRY(bs_alloc(ctx, &d_cnt, n)); BS_TRY(bs_alloc(ctx, &d_wide, n + 1)); BS_TRY(bs_alloc(ctx, &d_off, n + 1));
-    bs_count_launch(), k_active_voxels<false><<<bs_blocks(n, 4), 128, 0, st>>>(v->keys, v->masks, n, d_cnt, nullptr, nullptr);
-    bs_count_launch(), k_widen_u32<<<bs_blocks(n + 1, 256), 256, 0, st>>>(d_cnt, d_wide, n);
-    cub::DeviceScan::ExclusiveSum(nullptr, tmp, d_wide, d_off, n + 1, st);
+    const AvTiles Tl{v->tile8_keys, nt8, v->tile128_keys, nt128};
+    unsigned *d_cnt = nullptr, *d_pos = nullptr; u64 *d_wide = nullptr, *d_off = nullptr; void* d_tmp = nullptr; size_t tmp = 0;
+    BS_TRY(bs_alloc(ctx, &d_cnt, n_items)); BS_TRY(bs_alloc(ctx, &d_wide, n_items + 1)); BS_TRY(bs_alloc(ctx, &d_off, n_items + 1));
+    if (nt8 || nt128) {
+        BS_TRY(bs_alloc(ctx, &d_pos, n_items));
+        bs_count_launch(), k_av_merge_pos<<<bs_blocks(std::max(n, std::max(nt8, nt128)), 256), 256, 0, st>>>(v->keys, n, Tl, d_pos, d_pos + n, d_pos + n + nt8);
+    }
+    if (n) bs_count_launch(), k_active_voxels<false><<<bs_blocks(n, 4), 128, 0, st>>>(v->keys, v->masks, n, Tl, d_pos, d_cnt, nullptr, nullptr);
+    if (nt8) bs_count_launch(), k_active_voxels_tiles<false><<<(unsigned)nt8, 256, 0, st>>>(v->keys, v->masks, n, Tl, 0, d_pos + n, d_cnt, nullptr, nullptr);
+    if (nt128) bs_count_launch(), k_active_voxels_tiles<false><<<(unsigned)nt128, 256, 0, st>>>(v->keys, v->masks, n, Tl, 1, d_pos + n + nt8, d_cnt, nullptr, nullptr);
+    bs_count_launch(), k_widen_u32<<<bs_blocks(n_items + 1, 256), 256, 0, st>>>(d_cnt, d_wide, n_items);
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, d_wide, d_off, n_items + 1, st);
     BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp));
-    cub::DeviceScan::ExclusiveSum(d_tmp, tmp, d_wide, d_off, n + 1, st);
+    cub::DeviceScan::ExclusiveSum(d_tmp, tmp, d_wide, d_off, n_items + 1, st);
     u64 faces = 0;
-    BS_CUDA(ctx, cudaMemcpyAsync(&faces, d_off + n, sizeof(faces), cudaMemcpyDeviceToHost, st));
+    BS_CUDA(ctx, cudaMemcpyAsync(&faces, d_off + n_items, sizeof(faces), cudaMemcpyDeviceToHost, st));
     BS_CUDA(ctx, cudaStreamSynchronize(st));
     int* o = nullptr;
     bs_status s = bs_alloc(ctx, &o, (size_t)faces * 18);
-    if (s == BS_OK && faces) bs_count_launch(), k_active_voxels<true><<<bs_blocks(n, 4), 128, 0, st>>>(v->keys, v->masks, n, nullptr, d_off, o);
+    if (s == BS_OK && faces) {
+        if (n) bs_count_launch(), k_active_voxels<true><<<bs_blocks(n, 4), 128, 0, st>>>(v->keys, v->masks, n, Tl, d_pos, nullptr, d_off, o);
+        if (nt8) bs_count_launch(), k_active_voxels_tiles<true><<<(unsigned)nt8, 256, 0, st>>>(v->keys, v->masks, n, Tl, 0, d_pos + n, nullptr, d_off, o);
+        if (nt128) bs_count_launch(), k_active_voxels_tiles<true><<<(unsigned)nt128, 256, 0, st>>>(v->keys, v->masks, n, Tl, 1, d_pos + n + nt8, nullptr, d_off, o);
+    }
     bs_mark(ctx, "active_voxels_ms");
-    bs_free(ctx, d_tmp); bs_free(ctx, d_cnt); bs_free(ctx, d_wide); bs_free(ctx, d_off);
+    bs_free(ctx, d_tmp); bs_free(ctx, d_cnt); bs_free(ctx, d_wide); bs_free(ctx, d_off); bs_free(ctx, d_pos);
     if (s != BS_OK) return s;
     BS_CUDA(ctx, cudaGetLastError());
     bs_marks_end(ctx);

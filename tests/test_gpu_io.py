@@ -130,3 +130,15 @@ def test_mesh_indexed_equals_mc_then_merge_points(bs, oracle):
     uq, idx = oracle.merge_points(soup)
     assert np.array_equal(got.indices, idx) and np.array_equal(got.points.view(np.uint32), uq.view(np.uint32))
     assert np.array_equal(got.points[got.indices].view(np.uint32), soup.view(np.uint32))
+
+
+def test_active_voxels_mesher_on_active_tiles(bs, oracle):
+    # a union that leaves active 8^3 tiles (the big sphere's interior slots): tiles contribute their boundary voxels --
+    # edge and corner voxels several times, as in the reference -- and count as active neighbours of brick voxels
+    vs = 0.05
+    g = bs.VolumeBuilder().with_voxel_size(vs).sphere(0.6, (1.5, 0.3, 0.2)).union(bs.VolumeBuilder().with_voxel_size(vs).sphere(2.0, (0.1, 0.2, 0.3)))
+    o = oracle.sphere(vs, 0.6, (1.5, 0.3, 0.2)).union(oracle.sphere(vs, 2.0, (0.1, 0.2, 0.3)))
+    assert o.download()["tile_sizes"].size > 0
+    gv, ov = bs.ActiveVoxelsMesher().mesh(g), oracle.active_voxels(o)
+    assert gv.shape == ov.shape and gv.shape[0] > 0
+    assert np.array_equal(gv, ov)
