@@ -84,7 +84,12 @@ struct bs_context {
     // device memory cache (bs_raw_alloc / bs_raw_free): freed blocks are kept by rounded size and handed out again
     // without any driver call; everything runs on `stream`, so reuse is ordered by the stream itself
     std::multimap<size_t, void*> cache_free;
-    std::unordered_map<void*, size_t> cache_live;
+    struct LiveBlock { size_t size; unsigned long long epoch; };
+    std::unordered_map<void*, LiveBlock> cache_live;
+    // every entry point of the ABI starts a new epoch (bs_op_begin); an epoch in which bs_fail was called has its
+    // still-live blocks handed back to the cache when the next one starts: error paths return early and do not free
+    unsigned long long epoch = 0, failed_epoch = 0;
+    bool fail_pending = false;
     size_t cache_free_bytes = 0, cache_total_bytes = 0;
     std::string err;
     std::vector<bs_stat> stats;
@@ -124,6 +129,7 @@ bs_status bs_fail(bs_context* ctx, bs_status st, const char* fmt, ...);
 bs_status bs_raw_alloc(bs_context* ctx, size_t bytes, void** out);
 void bs_raw_free(bs_context* ctx, void* p);
 void bs_cache_release(bs_context* ctx);  // give every cached (free) block back to the driver
+void bs_op_begin(bs_context* ctx);       // first thing an ABI entry point does once its handles are validated
 template <class T> bs_status bs_alloc(bs_context* ctx, T** p, size_t count) {
     *p = nullptr;
     if (count == 0) count = 1;

@@ -57,3 +57,27 @@ def test_from_voxels_duplicates_last_wins(bs, oracle):
     ctx.check(bs.load_library().bs_volume_from_voxels(ctx._h, ijk.ctypes.data_as(C.POINTER(C.c_int32)), val.ctypes.data_as(C.POINTER(C.c_float)), 6, 1.0, C.byref(h)))
     g = bs.Volume(h, ctx)
     compare_volumes(g.download(), oracle.from_voxels(ijk, val, 1.0).download(), 1.0)
+
+
+def test_failed_calls_do_not_disturb_live_volumes(bs, oracle):
+    # error paths return early; what they still hold goes back to the block cache when the next call starts -- and
+    # nothing else: a volume created before the failing calls must stay intact
+    import ctypes as C
+    from baby_shark_b200 import synth
+    tris, vs, _ = synth.config_mesh(3, 0.04)
+    keep = bs.MeshToVolume().with_voxel_size(vs).convert(tris)
+    before = keep.download()
+    L, ctx = bs.load_library(), bs.Context.default()
+    for _ in range(3):
+        with pytest.raises(bs.BsharkError):
+            bs.StlReader().read_from_buffer(b"\0" * 80 + (1000).to_bytes(4, "little") + b"\0" * 50)   # short buffer
+        with pytest.raises(bs.BsharkError):
+            bs.MeshToVolume().with_voxel_size(-1.0).convert(tris)                                        # invalid argument
+        u = bs.VolumeBuilder().with_voxel_size(0.2).sphere(0.6, (1.5, 0.3, 0.2)).union(bs.VolumeBuilder().with_voxel_size(0.2).sphere(4.0, (0.1, 0.2, 0.3)))
+        with pytest.raises(bs.ReferencePanic):
+            bs.DualContouringMesher().with_voxel_size(0.2).mesh(u)                                      # todo!() on active tiles
+        assert ctx.check(L.bs_context_copy_out_verts(ctx._h, None, 0)) is None
+        other = bs.MeshToVolume().with_voxel_size(vs).convert(tris)                                     # reuses reclaimed blocks
+        after = keep.download()
+        assert np.array_equal(before["values"].view(np.uint32), after["values"].view(np.uint32)) and np.array_equal(before["masks"], after["masks"])
+        assert np.array_equal(other.download()["values"].view(np.uint32), before["values"].view(np.uint32))
