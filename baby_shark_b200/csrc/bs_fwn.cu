@@ -3,17 +3,20 @@
 // and MeshToVolume::compute_sings / ComputeSignsVisitor (src/voxel/mesh_to_volume.rs:198-281):
 //     value = copysign(|d|, wn(p) < 0.2 ? +1 : -1),   p = idx as f32 * voxel_size.
 //
-// The reference builds a serial top-down binned-SAH tree with <= 3 triangles per leaf. Here: 63-bit Morton codes
-// of the triangle centroids, radix sort, leaves of LEAF consecutive triangles, Karras' (2012) binary radix tree
-// emitted fully in parallel, and one bottom-up pass (second-arrival atomics) for the per-node moments the
-// reference keeps (aabb_tree.rs:723-801): area-weighted normal (order 1), sum(area c n^T) - p~ (sum area n)^T
+// The reference builds a serial top-down binned-SAH tree with <= 3 triangles per leaf. Here: 48-bit Morton codes
+// of the triangle centroids, radix sort, leaves of LEAF (= 1) consecutive triangles, Karras' (2012) binary radix tree
+// emitted fully in parallel, and one bottom-up pass (second-arrival atomics, in shared memory for the 94 % of the
+// parents whose leaves belong to one CTA) for the per-node moments the reference keeps (aabb_tree.rs:723-801): area-weighted normal (order 1), sum(area c n^T) - p~ (sum area n)^T
 // (order 2), dipole centre p~ = sum(area c)/sum(area). The node radius is the distance from p~ to the farthest
 // corner of the node's box (the reference takes the farther of the two extreme corners only, :734-736; this one
 // is a true bound, so the far-field test is never looser than the reference's).
 //
 // Traversal is warp-cooperative: a warp owns 32 Morton-adjacent active voxels of ONE brick and walks ONE shared
-// stack of (node, lane mask) entries (see warp_winding): per-voxel acceptance exactly as the reference's
-// criterion (|p - p~| > 2 radius, :666), warp-uniform control flow, broadcast 16 B node loads.
+// stack of (node, lane mask) entries (see WarpWinding): per-voxel acceptance exactly as the reference's
+// criterion (|p - p~| > 2 radius, :666), warp-uniform control flow, broadcast loads of 256-byte traversal records
+// (a node's four grandchildren, interleaved in pairs for packed f32x2 evaluation). The top of the tree is walked once
+// per brick (k_brick_pass): nodes far from the whole brick are sampled at 27 points and interpolated per voxel.
+// Sharded runs split the work items of bricks under dense slivers by triangles (k_expand_roots, k_sign_finish).
 // Only the 0.2 threshold matters downstream, so FMA contraction is allowed here (unlike the distance stage).
 #include "bs_common.cuh"
 #include <cub/cub.cuh>
