@@ -39,7 +39,9 @@ def parse():
     ap.add_argument("--config", type=int, default=5)
     ap.add_argument("--scale", type=float, default=1.0, help="resolution scale of the config (1.0 = BASELINE.json size)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-scale", type=float, default=0.1875, help="scale of the bounded CPU sample")
+    ap.add_argument("--cpu-scale", type=float, default=None,
+                    help="scale of the bounded CPU sample (default: 0.1875 for the cpu_baseline of our arm; the reference arm picks the largest of "
+                         "0.1875 / 0.125 / 0.09375 / 0.0625 whose steps + warm-up fit in ~150 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--io", action="store_true", help="time the rows either side of the path on the --config mesh: STL decode / encode, merge_points, ActiveVoxelsMesher")
     ap.add_argument("--ops", action="store_true", help="time the CSG (config 2) / offset (3) / dual contouring (4) rows instead of the remesh")
@@ -277,6 +279,11 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
+    if args.cpu_scale is None:
+        # seconds per pass measured on the 16-core GPU host for config 5 (time grows ~ scale^2.6); keep the whole run bounded
+        n_pass = max(1, args.steps) + max(0, min(args.warmup, 1))
+        est = {0.1875: 15.0, 0.125: 5.5, 0.09375: 2.7, 0.0625: 1.2}
+        args.cpu_scale = next((sc for sc in sorted(est, reverse=True) if est[sc] * 16.0 / cores * n_pass <= 150.0), 0.0625)
     tris, vs, desc = workload(args.config, args.cpu_scale)
     for _ in range(max(0, min(args.warmup, 1))):
         cpu_port(tris, vs, cores)
@@ -572,10 +579,11 @@ def main():
         out["gpu_launches"] = int(launches) * world  # counted by the library at its launch sites (bs_kernel_launch_count)
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
-            ctris, cvs, cdesc = workload(args.config, args.cpu_scale)
+            cpu_scale = args.cpu_scale if args.cpu_scale is not None else 0.1875
+            ctris, cvs, cdesc = workload(args.config, cpu_scale)
             nv_c, nt_c, dt_c, st_c = cpu_port(ctris, cvs, cores)
             out["cpu_baseline"] = {"value": nv_c / dt_c, "unit": UNIT, "cores": cores, "kind": "port",
-                                   "sample": "config %d at scale %g: %s (%d triangles, %d active voxels), one convert + MC pass in %.1f s" % (args.config, args.cpu_scale, cdesc, ctris.shape[0], nv_c, dt_c)}
+                                   "sample": "config %d at scale %g: %s (%d triangles, %d active voxels), one convert + MC pass in %.1f s" % (args.config, cpu_scale, cdesc, ctris.shape[0], nv_c, dt_c)}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
