@@ -164,4 +164,9 @@ bs_status bs_stl_decode_impl(bs_context* ctx, const unsigned char* d_stl, size_t
 bs_status bs_stl_encode_impl(bs_context* ctx, const float* d_verts, size_t n_verts, unsigned char** d_stl, size_t* n_bytes);
 bs_status bs_active_voxels_impl(const bs_volume* v, int** d_verts, size_t* n_verts);
 bs_status bs_merge_points_impl(bs_context* ctx, const float* d_pts, size_t n, float** d_unique, size_t* n_unique, unsigned** d_indices);
+// experimental sign propagation on closed meshes (bs_signprop.cu), enabled by BSHARK_SIGN_PROPAGATION only
+bs_status bs_mesh_closed_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bool* closed);
+bs_status bs_sign_components_impl(bs_context* ctx, const bs_volume* vol, unsigned** d_par, unsigned long long** d_seed);
+void bs_sign_chunks_from_masks(bs_context* ctx, const unsigned long long* d_masks, size_t n_bricks, unsigned* d_nchunks, int per_chunk);
+bs_status bs_sign_broadcast_impl(bs_context* ctx, bs_volume* vol, const unsigned* d_par);
 bs_status bs_builder_impl(bs_context* ctx, int kind, float voxel_size, const float* p, bs_volume** out);

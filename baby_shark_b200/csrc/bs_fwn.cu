@@ -892,6 +892,10 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, BS_SIGN_MINB) k_sign(Tre
 bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_volume* vol, const unsigned long long* d_touches) {
     cudaStream_t st = ctx->stream;
     if (n_tris >= (1ull << 30)) return bs_fail(ctx, BS_ERR_RANGE, "too many triangles");
+    // EXPERIMENTAL, off unless BSHARK_SIGN_PROPAGATION is set (bs_signprop.cu; not yet run on a GPU): on a closed mesh only one
+    // voxel per connected band component is traversed, the others copy its sign
+    bool prop = getenv("BSHARK_SIGN_PROPAGATION") != nullptr;
+    if (prop) { bool closed = false; BS_TRY(bs_mesh_closed_impl(ctx, d_tris, n_tris, &closed)); prop = closed; }
     // Morton order
     int* d_bounds = nullptr; unsigned long long *d_codes = nullptr, *d_codes2 = nullptr; unsigned *d_ids = nullptr, *d_ids2 = nullptr;
     BS_TRY(bs_alloc(ctx, &d_bounds, 6));
@@ -934,6 +938,12 @@ bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_v
         unsigned *d_nchunks = nullptr, *d_ordered = nullptr, *d_off = nullptr, *d_chunk_off = nullptr, *d_item_brick = nullptr, *d_order = nullptr; unsigned n_items = 0;
         BS_TRY(bs_alloc(ctx, &d_nchunks, nb)); BS_TRY(bs_alloc(ctx, &d_ordered, nb + 1)); BS_TRY(bs_alloc(ctx, &d_off, nb + 1)); BS_TRY(bs_alloc(ctx, &d_chunk_off, nb));
         bs_count_launch(), k_masks<<<bs_blocks(nb * 32, 256), 256, 0, st>>>(vol->values, nb, vol->masks, d_nchunks, 32 * BS_VPL);
+        unsigned* d_par = nullptr; unsigned long long* d_seed = nullptr;
+        if (prop) {  // work items are formed from the component representatives instead of all active voxels
+            BS_TRY(bs_sign_components_impl(ctx, vol, &d_par, &d_seed));
+            bs_sign_chunks_from_masks(ctx, d_seed, nb, d_nchunks, 32 * BS_VPL);
+        }
+        const unsigned long long* item_masks = prop ? d_seed : vol->masks;
         unsigned *d_heavy = nullptr, *d_slot = nullptr, *d_nheavy = nullptr; unsigned n_heavy = 0, n_hitems = 0;
         if (d_touches) {  // heaviest bricks first; bricks with >= 2^shift touching sub-triangle boxes are "heavy" (split by triangles)
             int shift = 11;
@@ -995,8 +1005,8 @@ bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_v
         if (!ctx->count_work) bs_mark(ctx, "sign_brick_pass_ms");
         if (n_hitems) bs_count_launch(), k_expand_roots<<<bs_blocks(n_heavy, 4), 128, 0, st>>>(T, d_other, d_heavy, n_heavy, d_bo, d_hr);
         if (n_items) {
-            if (ctx->count_work) bs_count_launch(), k_sign<true, BS_VPL><<<blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(T, vol->values, vol->masks, n_items, d_item_brick, d_chunk_off, vol->keys, vol->voxel_size, d_bo, d_cnt, H);
-            else bs_count_launch(), k_sign<false, BS_VPL><<<blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(T, vol->values, vol->masks, n_items, d_item_brick, d_chunk_off, vol->keys, vol->voxel_size, d_bo, nullptr, H);
+            if (ctx->count_work) bs_count_launch(), k_sign<true, BS_VPL><<<blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(T, vol->values, item_masks, n_items, d_item_brick, d_chunk_off, vol->keys, vol->voxel_size, d_bo, d_cnt, H);
+            else bs_count_launch(), k_sign<false, BS_VPL><<<blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(T, vol->values, item_masks, n_items, d_item_brick, d_chunk_off, vol->keys, vol->voxel_size, d_bo, nullptr, H);
         }
         if (n_hitems) bs_count_launch(), k_sign_finish<BS_VPL><<<bs_blocks((size_t)n_hitems * 32 * BS_VPL, 256), 256, 0, st>>>(vol->values, d_item_brick, 0u, n_hitems, (unsigned)HEAVY_REPL, d_partial, d_offs);
         if (ctx->count_work) {
@@ -1006,6 +1016,8 @@ bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_v
             bs_free(ctx, d_cnt);
             for (int i = 0; i < 9; ++i) ctx->fwn_counts[i] = (double)h_cnt[i];
         }
+        if (prop) { BS_TRY(bs_sign_broadcast_impl(ctx, vol, d_par)); bs_free(ctx, d_par); bs_free(ctx, d_seed); }
+        bs_stat_add(ctx, "sign_propagation", prop ? 1.0 : 0.0);
         bs_stat_add(ctx, "n_heavy_bricks", (double)n_heavy);
         bs_stat_add(ctx, "n_heavy_items", (double)n_hitems);
         bs_free(ctx, d_hr); bs_free(ctx, d_partial); bs_free(ctx, d_offs); bs_free(ctx, d_heavy); bs_free(ctx, d_slot);

@@ -89,7 +89,7 @@ OFF_GRID = np.array([0.3, 0.4, 0.5])  # avoids grid alignment
 def config_mesh(cfg, scale=1.0):
     """Benchmark config -> (tris, voxel_size, description). `scale` < 1 shrinks the resolution (and triangle
     count quadratically) for parity tests; scale = 1 is the BASELINE.json size."""
-    if cfg == 1:  # examples/voxel_remeshing.rs on assets/bunny.stl (13 000 triangles, open at the base), voxel_size 0.01
+    if cfg == 1:  # examples/voxel_remeshing.rs on assets/bunny.stl (13 000 triangles, closed), voxel_size 0.01
         import os
         path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "bunny_tris.npz")
         vs = 0.01 / scale

@@ -304,7 +304,7 @@ def run_reference(args, rank, world):
 
 
 def workload_desc(args):
-    names = {1: "voxel_remeshing example, assets/bunny.stl at voxel_size 0.01 (open mesh)", 3: "UV sphere ~1.0M triangles at 1024^3", 4: "noise-displaced UV sphere 2.0M triangles at 1024^3",
+    names = {1: "voxel_remeshing example, assets/bunny.stl at voxel_size 0.01", 3: "UV sphere ~1.0M triangles at 1024^3", 4: "noise-displaced UV sphere 2.0M triangles at 1024^3",
              5: "noise-displaced UV sphere ~10.0M triangles at 2048^3"}
     return "%s, voxel remesh (convert + MC33), scale %g" % (names[args.config], args.scale)
 

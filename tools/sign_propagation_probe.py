@@ -14,6 +14,24 @@ from oracle import oracle as O  # noqa: E402
 from baby_shark_b200 import synth  # noqa: E402
 
 
+def mesh_is_closed(tris):
+    """numpy restatement of bs_mesh_closed_impl (bs_signprop.cu): vertices identified by exact coordinates (-0 == +0),
+    no triangle with a repeated vertex, every directed edge exactly once and its reverse exactly once."""
+    v = np.ascontiguousarray(np.asarray(tris, np.float32).reshape(-1, 3)) + np.float32(0.0)
+    u, idx = np.unique(v.view(np.uint32).reshape(-1, 3), axis=0, return_inverse=True)
+    t = idx.reshape(-1, 3).astype(np.int64)
+    if ((t[:, 0] == t[:, 1]) | (t[:, 1] == t[:, 2]) | (t[:, 2] == t[:, 0])).any():
+        return False
+    e = np.concatenate([t[:, [0, 1]], t[:, [1, 2]], t[:, [2, 0]]])
+    k, kr = e[:, 0] * (len(u) + 1) + e[:, 1], e[:, 1] * (len(u) + 1) + e[:, 0]
+    ks = np.sort(k)
+    if (ks[1:] == ks[:-1]).any():
+        return False
+    pos = np.searchsorted(ks, kr)
+    pos[pos >= ks.size] = 0
+    return bool((ks[pos] == kr).all())
+
+
 def probe(name, tris, vs, neighbours=6):
     d = O.mesh_to_volume(tris, vs, 0, os.cpu_count() or 1)[0].download()
     m = np.unpackbits(np.ascontiguousarray(d["masks"]).view(np.uint8).reshape(-1, 8, 8), axis=-1, bitorder="little").reshape(-1, 512).astype(bool)
@@ -47,8 +65,8 @@ def probe(name, tris, vs, neighbours=6):
     g = coo_matrix((np.ones(src.size, np.int8), (src, dst)), shape=(val.size, val.size))
     ncomp, lab = connected_components(g, directed=False)
     sizes = np.bincount(lab)
-    print("%-28s voxels %8d  links %9d certified %9d  sign conflicts on certified links %d  components %7d (largest %d, singletons %d = %.2f%% of voxels)"
-          % (name, val.size, n_links, src.size, bad, ncomp, sizes.max(), int((sizes == 1).sum()), 100.0 * (sizes == 1).sum() / val.size))
+    print("%-28s closed %-5s voxels %8d  links %9d certified %9d  sign conflicts on certified links %d  components %7d (largest %d, singletons %d = %.2f%% of voxels)"
+          % (name, mesh_is_closed(tris), val.size, n_links, src.size, bad, ncomp, sizes.max(), int((sizes == 1).sum()), 100.0 * (sizes == 1).sum() / val.size))
 
 
 if __name__ == "__main__":
