@@ -115,3 +115,22 @@ def test_active_voxels_and_merge_points_invariants(oracle):
     uq, idx = oracle.merge_points(a.astype(np.float32))
     assert uq.shape == (8, 3) and idx.max() == 7 and np.array_equal(uq[idx], a.astype(np.float32))
     assert idx[:3].tolist() == [0, 1, 2]  # first-occurrence order
+
+
+def test_half_edge_closedness_rule():
+    # the rule bs_signprop.cu applies before propagating signs (numpy restatement in tools/sign_propagation_probe.py):
+    # closed and consistently oriented <=> every directed edge once, its reverse once, no repeated vertex in a triangle
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tools"))
+    from sign_propagation_probe import mesh_is_closed
+    from baby_shark_b200 import synth
+    sphere = synth.uv_sphere(24, 12, 1.0, (0.1, 0.2, 0.3))
+    assert mesh_is_closed(sphere) and mesh_is_closed(synth.cube()) and mesh_is_closed(synth.torus(16, 8, 1.0, 0.3, (0, 0, 0)))
+    assert not mesh_is_closed(sphere[:-1])                                   # a hole: boundary edges
+    flipped = sphere.copy(); flipped[5] = flipped[5].reshape(3, 3)[[0, 2, 1]].reshape(9)
+    assert not mesh_is_closed(flipped)                                       # one triangle with the other orientation
+    assert not mesh_is_closed(np.concatenate([sphere, sphere[:1]]))          # a duplicated triangle: the same directed edges twice
+    degenerate = sphere.copy(); degenerate[3, 3:6] = degenerate[3, 0:3]
+    assert not mesh_is_closed(degenerate)                                    # repeated vertex inside a triangle
+    assert mesh_is_closed(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bunny_tris.npz"))["tris"])
