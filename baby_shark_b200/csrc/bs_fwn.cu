@@ -892,7 +892,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, BS_SIGN_MINB) k_sign(Tre
 bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_volume* vol, const unsigned long long* d_touches) {
     cudaStream_t st = ctx->stream;
     if (n_tris >= (1ull << 30)) return bs_fail(ctx, BS_ERR_RANGE, "too many triangles");
-    // EXPERIMENTAL, off unless BSHARK_SIGN_PROPAGATION is set (bs_signprop.cu; not yet run on a GPU): on a closed mesh only one
+    // EXPERIMENTAL, off unless BSHARK_SIGN_PROPAGATION is set (bs_signprop.cu; parity-tested once on small meshes, not yet timed): on a closed mesh only one
     // voxel per connected band component is traversed, the others copy its sign
     bool prop = getenv("BSHARK_SIGN_PROPAGATION") != nullptr;
     if (prop) { bool closed = false; BS_TRY(bs_mesh_closed_impl(ctx, d_tris, n_tris, &closed)); prop = closed; }

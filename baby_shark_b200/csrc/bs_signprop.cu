@@ -1,6 +1,8 @@
 // EXPERIMENTAL, OFF BY DEFAULT (enabled by the environment variable BSHARK_SIGN_PROPAGATION; written at the end of
-// round 1 with the GPU budget spent: it compiles, its algorithm is checked on the CPU by tools/sign_propagation_probe.py,
-// but it has NOT run on a B200 yet -- no test depends on it and the default path never calls it).
+// round 1: its algorithm is checked on the CPU by tools/sign_propagation_probe.py and tools/signprop_emulation.py, and
+// with the last GPU seconds of the round test_experimental_sign_propagation_matches_per_voxel_signs passed on a B200
+// (bit-identical volumes on three closed test meshes, fallback on an open one). It has NOT been timed or run at the
+// benchmark size yet, so the default path never calls it).
 //
 // Sign propagation for closed meshes. MeshToVolume::compute_sings (mesh_to_volume.rs:198-281)
 // evaluates the winding number of every active voxel. On a closed, consistently oriented mesh the winding number is an

@@ -202,7 +202,7 @@ def test_heavy_split_on_bunny_matches_unsplit_signs(bs, bunny, monkeypatch):
     assert diff.mean() < 2e-3  # the split walk refines some far nodes: only voxels at the 0.2 threshold may move
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("BSHARK_TEST_EXPERIMENTAL"), reason="experimental path (bs_signprop.cu), not yet validated on a GPU: set BSHARK_TEST_EXPERIMENTAL=1")
+@pytest.mark.skipif(not __import__("os").environ.get("BSHARK_TEST_EXPERIMENTAL"), reason="experimental path (bs_signprop.cu), off by default and not yet run at benchmark size: set BSHARK_TEST_EXPERIMENTAL=1")
 def test_experimental_sign_propagation_matches_per_voxel_signs(bs, oracle, monkeypatch):
     # closed meshes: one traversal per connected band component, the rest copy the sign -> identical volumes;
     # an open mesh must fall back to the per-voxel path
