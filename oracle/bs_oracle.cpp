@@ -22,8 +22,8 @@ using namespace bso;
 
 extern "C" {
 
-void* bso_mesh_to_volume(const float* tris, size_t n, float voxel_size, int64_t band, int threads, ConvertStats* st) {
-    VolumeGrid* g = mesh_to_volume(tris, n, voxel_size, band, threads, st);
+void* bso_mesh_to_volume(const float* tris, size_t n, float voxel_size, int64_t band, int threads, ConvertStats* st, int count_work) {
+    VolumeGrid* g = mesh_to_volume(tris, n, voxel_size, band, threads, st, count_work != 0);
     if (!g) return nullptr;
     return new Volume{g, voxel_size};
 }
@@ -114,12 +114,13 @@ void bso_point_triangle_distance(const float* tri9, const float* pts, size_t m, 
 // approximate (beta > 0) or exact (beta <= 0) winding numbers on the reference's SAH tree
 void bso_winding_numbers(const float* tris, size_t n, const float* pts, size_t m, float beta, float* out, uint64_t* counters) {
     WindingNumbers wn; wn.build(tris, n);
+    WindingNumbers::Counters cnt;
     for (size_t i = 0; i < m; ++i) {
         Vec3f p{pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
-        if (beta > 0.0f) out[i] = wn.approximate(p, beta);
+        if (beta > 0.0f) out[i] = wn.approximate(p, beta, counters ? &cnt : nullptr);
         else { float w = 0.0f; for (auto& o : wn.objects) w += WindingNumbers::solid_angle(o.first, p); out[i] = w / (4.0f * 3.14159265358979323846f); }
     }
-    if (counters) { counters[0] = wn.n_visit; counters[1] = wn.n_far; counters[2] = wn.n_exact; counters[3] = wn.nodes.size(); }
+    if (counters) { counters[0] = cnt.n_visit; counters[1] = cnt.n_far; counters[2] = cnt.n_exact; counters[3] = wn.nodes.size(); }
 }
 // data formats either side of the path
 int bso_stl_decode(const uint8_t* bytes, size_t n_bytes, float** tris, size_t* n_tris) {

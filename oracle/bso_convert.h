@@ -94,8 +94,9 @@ struct WindingNumbers {
     std::vector<std::pair<Tri, Box3f>> objects;
     std::vector<NodeData> data;
     size_t min_objects_per_leaf = 3, max_depth = 40;
-    // traversal counters
-    mutable std::atomic<uint64_t> n_visit{0}, n_far{0}, n_exact{0};
+    // traversal counters: only the COUNT instantiation of fast_wn touches them, and then through a
+    // caller-owned (thread-local) block -- the timed path has no shared writes
+    struct Counters { uint64_t n_visit = 0, n_far = 0, n_exact = 0; };
 
     void build(const float* tris, size_t n) {
         objects.clear(); nodes.clear(); data.clear();
@@ -222,13 +223,16 @@ struct WindingNumbers {
         float den = 1.0f + dot(qa, qb) + dot(qa, qc) + dot(qb, qc);
         return std::atan2(num, den) * 2.0f;
     }
-    float approximate(const Vec3f& p, float beta) const { return nodes.empty() ? 0.0f : fast_wn(nodes.size() - 1, p, beta); }
-    float fast_wn(size_t idx, const Vec3f& p, float beta) const {
+    float approximate(const Vec3f& p, float beta, Counters* c = nullptr) const {
+        if (nodes.empty()) return 0.0f;
+        return c ? fast_wn<true>(nodes.size() - 1, p, beta, c) : fast_wn<false>(nodes.size() - 1, p, beta, nullptr);
+    }
+    template <bool COUNT> float fast_wn(size_t idx, const Vec3f& p, float beta, Counters* c) const {
         const NodeData& nd = data[idx];
-        n_visit.fetch_add(1, std::memory_order_relaxed);
+        if (COUNT) c->n_visit++;
         float dist = norm(p - nd.center);
         if (dist > nd.radius * beta) {
-            n_far.fetch_add(1, std::memory_order_relaxed);
+            if (COUNT) c->n_far++;
             const float PI = 3.14159265358979323846f;
             Vec3f r = nd.center - p;
             float r2 = norm_squared(r), r1 = std::sqrt(r2), r3 = r2 * r1;
@@ -248,10 +252,10 @@ struct WindingNumbers {
         if (node.leaf) {
             float wn = 0.0f;
             for (size_t t = node.left; t < node.right; ++t) wn += solid_angle(objects[t].first, p);
-            n_exact.fetch_add(node.right - node.left, std::memory_order_relaxed);
+            if (COUNT) c->n_exact += node.right - node.left;
             return wn / (4.0f * 3.14159265358979323846f);
         }
-        return fast_wn(node.left, p, beta) + fast_wn(node.right, p, beta);
+        return fast_wn<COUNT>(node.left, p, beta, c) + fast_wn<COUNT>(node.right, p, beta, c);
     }
 };
 
@@ -300,7 +304,8 @@ inline void subdivide_triangle(const Tri& tri, float voxel_size, std::vector<Tri
 double now_s();
 
 // MeshToVolume::convert (mesh_to_volume.rs:52-73). Returns nullptr where the reference returns None.
-inline VolumeGrid* mesh_to_volume(const float* tris, size_t n_tris, float voxel_size, idx_t band, int threads, ConvertStats* st) {
+// count_work: also tally the winding-number traversal (per-leaf counter blocks, summed afterwards); off in every timed run
+inline VolumeGrid* mesh_to_volume(const float* tris, size_t n_tris, float voxel_size, idx_t band, int threads, ConvertStats* st, bool count_work = false) {
     const float inverse_voxel_size = 1.0f / voxel_size;
     ConvertStats s; std::memset(&s, 0, sizeof(s));
     s.n_tris = n_tris;
@@ -365,15 +370,17 @@ inline VolumeGrid* mesh_to_volume(const float* tris, size_t n_tris, float voxel_
     // signs (:198-281): same topology, value = copysign(|d|, wn < 0.2 ? + : -)
     struct Collect { std::vector<Leaf3<float>*> leaves; void dense(const Leaf3<float>& l) { leaves.push_back(const_cast<Leaf3<float>*>(&l)); } void tile(const Tile<float>&) {} } col;
     grid->visit_leafs(col);
+    std::vector<WindingNumbers::Counters> wc(count_work ? col.leaves.size() : 0);
     parallel_for(col.leaves.size(), threads, [&](size_t li) {
         Leaf3<float>* leaf = col.leaves[li];
+        WindingNumbers::Counters* cnt = count_work ? &wc[li] : nullptr;
         Vec3i o = leaf->origin();
         for (idx_t x = o.x; x < o.x + 8; ++x) for (idx_t y = o.y; y < o.y + 8; ++y) for (idx_t z = o.z; z < o.z + 8; ++z) {
             Vec3i idx{x, y, z};
             size_t off = Leaf3<float>::offset(idx);
             if (!leaf->value_mask.at(off)) continue;
             Vec3f gp{float(x) * voxel_size, float(y) * voxel_size, float(z) * voxel_size};
-            float w = wn.approximate(gp, 2.0f);
+            float w = wn.approximate(gp, 2.0f, cnt);
             float d = leaf->values[off];
             leaf->values[off] = (w < 0.2f) ? std::copysign(d, 1.0f) : std::copysign(d, -1.0f);
         }
@@ -381,7 +388,7 @@ inline VolumeGrid* mesh_to_volume(const float* tris, size_t n_tris, float voxel_
     double t4 = now_s(); s.t_sign = t4 - t3;
     s.n_leaves = col.leaves.size();
     for (auto* l : col.leaves) for (int i = 0; i < 512; ++i) if (l->value_mask.at(i)) { s.n_active++; if (std::signbit(l->values[i])) s.n_negative++; }
-    s.wn_visit = wn.n_visit; s.wn_far = wn.n_far; s.wn_exact = wn.n_exact;
+    for (const auto& c : wc) { s.wn_visit += c.n_visit; s.wn_far += c.n_far; s.wn_exact += c.n_exact; }
     if (st) *st = s;
     return grid;
 }

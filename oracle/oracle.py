@@ -45,7 +45,7 @@ def lib():
         L = C.CDLL(_LIB_PATH)
         fp = C.POINTER(C.c_float)
         L.bso_mesh_to_volume.restype = C.c_void_p
-        L.bso_mesh_to_volume.argtypes = [fp, C.c_size_t, C.c_float, C.c_int64, C.c_int, C.POINTER(ConvertStats)]
+        L.bso_mesh_to_volume.argtypes = [fp, C.c_size_t, C.c_float, C.c_int64, C.c_int, C.POINTER(ConvertStats), C.c_int]
         L.bso_volume_sphere.restype = C.c_void_p
         L.bso_volume_sphere.argtypes = [C.c_float] * 5
         L.bso_volume_cuboid.restype = C.c_void_p
@@ -168,11 +168,12 @@ class Volume:
         return lib().bso_volume_sign_at(self._h, x, y, z)
 
 
-def mesh_to_volume(tris, voxel_size, band=0, threads=1):
-    """reference `MeshToVolume::convert` (mesh_to_volume.rs:52-73); returns (Volume | None, stats dict)."""
+def mesh_to_volume(tris, voxel_size, band=0, threads=1, count_work=False):
+    """reference `MeshToVolume::convert` (mesh_to_volume.rs:52-73); returns (Volume | None, stats dict).
+    count_work: also fill the wn_* traversal counters (never set in a timed run)."""
     tris = _f32(tris).reshape(-1, 9)
     st = ConvertStats()
-    h = lib().bso_mesh_to_volume(_fp(tris), tris.shape[0], voxel_size, band, threads, C.byref(st))
+    h = lib().bso_mesh_to_volume(_fp(tris), tris.shape[0], voxel_size, band, threads, C.byref(st), int(bool(count_work)))
     return (Volume(h) if h else None), st.as_dict()
 
 
