@@ -19,6 +19,8 @@ BS_OK, BS_ERR_EMPTY_MESH, BS_ERR_CUDA, BS_ERR_INVALID, BS_ERR_REFERENCE_PANICS, 
 _STATUS_NAMES = ["BS_OK", "BS_ERR_EMPTY_MESH", "BS_ERR_CUDA", "BS_ERR_INVALID", "BS_ERR_REFERENCE_PANICS",
                  "BS_ERR_RANGE", "BS_ERR_NO_DEVICE", "BS_ERR_UNSUPPORTED"]
 
+BS_FLAG_COUNT_WORK, BS_FLAG_SIGN_PROPAGATION = 1, 2
+
 # every symbol include/bshark.h declares (tests check the built library exports all of them)
 EXPORTS = [
     "bs_context_create", "bs_context_destroy", "bs_last_error", "bs_context_device", "bs_context_stream",
@@ -139,6 +141,10 @@ class Context:
 
     def last_error(self):
         return load_library().bs_last_error(self._h).decode()
+
+    def set_flag(self, flag, value):
+        """bs_context_set_flag: BS_FLAG_COUNT_WORK = 1, BS_FLAG_SIGN_PROPAGATION = 2 (include/bshark.h)."""
+        self.check(load_library().bs_context_set_flag(self._h, int(flag), int(value)))
 
     @property
     def device(self):

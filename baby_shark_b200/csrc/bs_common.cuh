@@ -94,12 +94,20 @@ struct bs_context {
     std::string err;
     std::vector<bs_stat> stats;
     int8_t* d_mc33 = nullptr;       // MC33 tables blob (mc33_tables.h)
+    // device-side error word of the running call (BS_DERR_*): kernels OR bits into it instead of dropping work silently;
+    // bs_convert_impl clears it at the start and turns a non-zero word into BS_ERR_RANGE at its final synchronisation
+    unsigned* d_err = nullptr;
     float* d_out_verts = nullptr;   // last extraction result left on the device
     size_t out_verts_cap = 0;
     // stage timing
     std::vector<std::pair<const char*, cudaEvent_t>> marks;
     // BS_FLAG_COUNT_WORK: instrumented winding-number traversal (node visits, far evals, exact triangles, voxels)
     int count_work = 0;
+    // BS_FLAG_SIGN_PROPAGATION (default 1): closed meshes take one winding-number traversal per connected band component
+    int sign_propagation = 1;
+    // per-convert: is the mesh a closed 2-cycle, and the f32 rounding tolerance of the link certificate (world units)
+    bool mesh_closed = false;
+    float sp_tol = 0.f;
     double fwn_counts[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // lane visits, far evals, exact tris, voxels, warp-level visits, traversals, brick-level visits, hoisted nodes
 };
 
@@ -119,6 +127,10 @@ struct bs_volume {
     unsigned char* owned = nullptr;
     size_t n_owned = 0;
 };
+
+#define BS_DERR_STACK 1u      /* winding-number traversal stack full (bs_fwn.cu STACK) */
+#define BS_DERR_PROBE 2u      /* brick hash: key not found within the probe limit */
+#define BS_DERR_BRICKPASS 4u  /* reserved */
 
 // error plumbing ----------------------------------------------------------------------------------------
 bs_status bs_fail(bs_context* ctx, bs_status st, const char* fmt, ...);
@@ -164,9 +176,10 @@ bs_status bs_stl_decode_impl(bs_context* ctx, const unsigned char* d_stl, size_t
 bs_status bs_stl_encode_impl(bs_context* ctx, const float* d_verts, size_t n_verts, unsigned char** d_stl, size_t* n_bytes);
 bs_status bs_active_voxels_impl(const bs_volume* v, int** d_verts, size_t* n_verts);
 bs_status bs_merge_points_impl(bs_context* ctx, const float* d_pts, size_t n, float** d_unique, size_t* n_unique, unsigned** d_indices);
-// experimental sign propagation on closed meshes (bs_signprop.cu), enabled by BSHARK_SIGN_PROPAGATION only
-bs_status bs_mesh_closed_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bool* closed);
-bs_status bs_sign_components_impl(bs_context* ctx, const bs_volume* vol, unsigned** d_par, unsigned long long** d_seed);
-void bs_sign_chunks_from_masks(bs_context* ctx, const unsigned long long* d_masks, size_t n_bricks, unsigned* d_nchunks, int per_chunk);
+// sign propagation on closed meshes (bs_signprop.cu)
+struct bs_closed_check { bool exact, closed, pending; unsigned long long* d_sums; int* d_bad; unsigned long long h_sums[4]; int h_bad; };
+bs_status bs_mesh_closed_begin(bs_context* ctx, const float* d_tris, size_t n_tris, bs_closed_check* chk);  // enqueue; verdict after the next stream sync
+bool bs_mesh_closed_finish(bs_context* ctx, bs_closed_check* chk);
+bs_status bs_sign_components_impl(bs_context* ctx, const bs_volume* vol, float tol, unsigned** d_par, unsigned long long** d_seed, unsigned* d_nchunks, int per_chunk, unsigned long long* d_nseeds, bool* applicable);
 bs_status bs_sign_broadcast_impl(bs_context* ctx, bs_volume* vol, const unsigned* d_par);
 bs_status bs_builder_impl(bs_context* ctx, int kind, float voxel_size, const float* p, bs_volume** out);

@@ -137,10 +137,12 @@ bs_status bs_context_create(int device, bs_context** out) {
     if (prop.major != 10) return BS_ERR_NO_DEVICE;  // kernels are built for sm_100a only
     bs_context* ctx = new bs_context();
     ctx->device = device; ctx->sm_count = prop.multiProcessorCount;
+    if (const char* e = getenv("BSHARK_SIGN_PROPAGATION")) ctx->sign_propagation = atoi(e);  // A/B runs: 0 = per-voxel signs everywhere
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete ctx; return BS_ERR_CUDA;
     }
-    if (cudaMalloc((void**)&ctx->d_mc33, MC33_BLOB_SIZE) != cudaSuccess ||
+    if (cudaMalloc((void**)&ctx->d_err, sizeof(unsigned)) != cudaSuccess || cudaMemset(ctx->d_err, 0, sizeof(unsigned)) != cudaSuccess ||
+        cudaMalloc((void**)&ctx->d_mc33, MC33_BLOB_SIZE) != cudaSuccess ||
         cudaMemcpy(ctx->d_mc33, h_mc33, MC33_BLOB_SIZE, cudaMemcpyHostToDevice) != cudaSuccess) {
         cudaStreamDestroy(ctx->stream); delete ctx; return BS_ERR_CUDA;
     }
@@ -155,7 +157,7 @@ void bs_context_destroy(bs_context* ctx) {
     if (ctx->d_out_verts) cudaFree(ctx->d_out_verts);
     bs_cache_release(ctx);
     for (auto& kv : ctx->cache_live) cudaFree(kv.first);  // volumes the caller never freed
-    cudaFree(ctx->d_mc33);
+    cudaFree(ctx->d_mc33); cudaFree(ctx->d_err);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -166,6 +168,7 @@ void* bs_context_stream(const bs_context* ctx) { return ctx ? (void*)ctx->stream
 bs_status bs_context_set_flag(bs_context* ctx, int flag, int value) {
     if (!ctx) return BS_ERR_INVALID;
     if (flag == BS_FLAG_COUNT_WORK) { ctx->count_work = value; return BS_OK; }
+    if (flag == BS_FLAG_SIGN_PROPAGATION) { ctx->sign_propagation = value; return BS_OK; }
     return BS_ERR_INVALID;
 }
 bs_status bs_context_copy_out_verts_device(bs_context* ctx, float* d_dst, size_t n_floats) {

@@ -18,6 +18,7 @@
 #include <cfloat>
 #include <climits>
 #include <cmath>
+#include <cstring>
 
 namespace {
 
@@ -33,6 +34,7 @@ struct ConvertParams {
     unsigned* table_counts;  // per hash slot: how many sub-triangle boxes touch the brick (load-balancing weight for sharding); may be null
     float* values;
     int* flags;  // [0] hash overflow, [1] index range error
+    unsigned* derr;  // bs_context::d_err
     unsigned long long* n_eval;  // sum of box volumes = point-triangle evaluations (roofline work counter)
     int use_clip, clip_mn[3], clip_mx[3];  // sharded runs: voxel bounding box of the bricks this rank keeps
 };
@@ -50,9 +52,14 @@ __device__ __forceinline__ float num_subs_of(f3 p1, f3 p2, f3 p3, float vs) {
     return floorf(xdiv(xsqrt(m), vs));
 }
 
-__global__ void k_tri_counts(const float* __restrict__ tris, size_t n_tris, float vs, unsigned long long* counts, double* area_vox) {
+// also: sp_tol = max over triangles of the f32 rounding tolerance of the sign-propagation link certificate
+// (bs_signprop.cu): 2 x the drift of a sub-triangle vertex built from <= n + 1 running-sum additions
+// (1.74 (n + 13) 2^-24 max|coord|, only when the triangle is subdivided) + 32 x 2^-24 max|coord| for the lattice
+// positions, box roundings and the distance evaluation itself
+__global__ void k_tri_counts(const float* __restrict__ tris, size_t n_tris, float vs, unsigned long long* counts, double* area_vox, unsigned* sp_tol_bits) {
     size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     double a = 0.0;
+    float tol = 0.f;
     if (t < n_tris) {
         const float* p = tris + 9 * t;
         f3 p1 = ld3(p), p2 = ld3(p + 3), p3 = ld3(p + 6);
@@ -60,6 +67,12 @@ __global__ void k_tri_counts(const float* __restrict__ tris, size_t n_tris, floa
         unsigned long long c;
         if (n < 2.0f) c = 1; else if (n != n) c = 0; else { double nd = fmin((double)n, 4.0e9); c = (unsigned long long)(nd * nd); }
         counts[t] = c;
+        float ma = 0.f;
+        for (int i = 0; i < 9; ++i) ma = fmaxf(ma, fabsf(p[i]));
+        const float u = 5.9604645e-8f * ma;  // 2^-24 max|coord|
+        tol = 32.0f * u + (n >= 2.0f ? 2.0f * 1.74f * (n + 13.0f) * u : 0.f);
+        tol *= 1.01f;
+        if (!(tol >= 0.f) || !(tol < 3.0e38f)) tol = 3.0e38f;  // NaN / inf coordinates: no certificate
         f3 cr = xcross(xsub(p2, p1), xsub(p3, p1));
         float ar = 0.5f * sqrtf(xnorm2(cr));
         if (ar == ar && ar < 3.0e38f) a = (double)ar / ((double)vs * (double)vs);
@@ -69,6 +82,8 @@ __global__ void k_tri_counts(const float* __restrict__ tris, size_t n_tris, floa
     __shared__ typename BR::TempStorage tmp;
     double s = BR(tmp).Sum(a);
     if (threadIdx.x == 0 && s != 0.0) atomicAdd(area_vox, s);
+    for (int o = 16; o; o >>= 1) tol = fmaxf(tol, __shfl_xor_sync(0xFFFFFFFFu, tol, o));
+    if ((threadIdx.x & 31) == 0 && tol > 0.f) atomicMax(sp_tol_bits, __float_as_uint(tol));  // non-negative floats order like their bits
 }
 
 // j-th sub-triangle of triangle (p1,p2,p3) in the reference's construction (mesh_to_volume.rs:75-116):
@@ -162,6 +177,7 @@ __device__ __forceinline__ unsigned hash_lookup(const ConvertParams& P, unsigned
         if (cur == BS_KEY_INVALID) return 0xFFFFFFFFu;
         h = (h + 1) & P.table_mask;
     }
+    atomicOr(P.derr, BS_DERR_PROBE);  // cannot happen after a mark pass without overflow (every insert ended within MAX_PROBE); never a silent miss
     return 0xFFFFFFFFu;
 }
 
@@ -338,12 +354,13 @@ __global__ void __launch_bounds__(TPB) k_eval(ConvertParams P) {
     }
 }
 
-__global__ void k_fill_slots(const unsigned long long* sorted_keys, size_t n, unsigned long long* table_keys, unsigned* table_slots, unsigned mask) {
+__global__ void k_fill_slots(const unsigned long long* sorted_keys, size_t n, unsigned long long* table_keys, unsigned* table_slots, unsigned mask, unsigned* derr) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     unsigned long long key = sorted_keys[i];
     unsigned h = (unsigned)hash64(key) & mask;
-    while (table_keys[h] != key) h = (h + 1) & mask;
+    int probe = 0;
+    while (table_keys[h] != key) { h = (h + 1) & mask; if (++probe > MAX_PROBE) { atomicOr(derr, BS_DERR_PROBE); return; } }
     table_slots[h] = (unsigned)i;
 }
 
@@ -365,12 +382,13 @@ __global__ void k_mark_slab(const unsigned long long* __restrict__ keys, size_t 
     if (j >= 0) keep[j] = 1;
 }
 // weight of sorted brick i = touches(i) + mean touches; W[i] = inclusive prefix. bounds[r] = first i with W[i] >= r * W_total / world
-__global__ void k_brick_touches(const unsigned long long* __restrict__ keys, size_t n, const unsigned long long* __restrict__ table_keys, const unsigned* __restrict__ table_counts, unsigned mask, unsigned long long* touches) {
+__global__ void k_brick_touches(const unsigned long long* __restrict__ keys, size_t n, const unsigned long long* __restrict__ table_keys, const unsigned* __restrict__ table_counts, unsigned mask, unsigned long long* touches, unsigned* derr) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned long long key = keys[i];
     unsigned h = (unsigned)hash64(key) & mask;
-    while (table_keys[h] != key) h = (h + 1) & mask;
+    int probe = 0;
+    while (table_keys[h] != key) { h = (h + 1) & mask; if (++probe > MAX_PROBE) { atomicOr(derr, BS_DERR_PROBE); touches[i] = 0; return; } }
     touches[i] = table_counts[h];
 }
 // cost model of a brick for the sign stage (which dominates): t = sub-triangle boxes touching it, m = mean t.
@@ -450,16 +468,22 @@ extern "C" bs_status bs_volume_counts(const bs_volume* v, size_t* n_bricks, size
 bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, float voxel_size, int64_t band, int rank, int world, bs_volume** out) {
     cudaStream_t st = ctx->stream;
     bs_marks_begin(ctx);
+    BS_CUDA(ctx, cudaMemsetAsync(ctx->d_err, 0, sizeof(unsigned), st));
     // 1. per-triangle sub-triangle counts + surface area in voxel^2 (sizing only)
     unsigned long long *d_counts = nullptr, *d_offsets = nullptr; double* d_area = nullptr; int* d_flags = nullptr;
     BS_TRY(bs_alloc(ctx, &d_counts, n_tris + 1)); BS_TRY(bs_alloc(ctx, &d_offsets, n_tris + 1));
     BS_TRY(bs_alloc(ctx, &d_area, 1)); BS_TRY(bs_alloc(ctx, &d_flags, 2));
-    unsigned long long* d_neval = nullptr;
-    BS_TRY(bs_alloc(ctx, &d_neval, 1));
+    unsigned long long* d_neval = nullptr; unsigned* d_tol = nullptr;
+    BS_TRY(bs_alloc(ctx, &d_neval, 1)); BS_TRY(bs_alloc(ctx, &d_tol, 1));
     BS_CUDA(ctx, cudaMemsetAsync(d_area, 0, sizeof(double), st));
     BS_CUDA(ctx, cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), st));
+    BS_CUDA(ctx, cudaMemsetAsync(d_tol, 0, sizeof(unsigned), st));
     BS_CUDA(ctx, cudaMemsetAsync(d_counts + n_tris, 0, sizeof(unsigned long long), st));
-    bs_count_launch(), k_tri_counts<<<bs_blocks(n_tris, TPB), TPB, 0, st>>>(d_tris, n_tris, voxel_size, d_counts, d_area);
+    // closed mesh? (bs_signprop.cu) -- enqueued here, read at the synchronisation below
+    bs_closed_check chk; chk.pending = false; chk.closed = false; chk.exact = false; chk.d_sums = nullptr; chk.d_bad = nullptr;
+    ctx->mesh_closed = false; ctx->sp_tol = 0.f;
+    if (ctx->sign_propagation) BS_TRY(bs_mesh_closed_begin(ctx, d_tris, n_tris, &chk));
+    bs_count_launch(), k_tri_counts<<<bs_blocks(n_tris, TPB), TPB, 0, st>>>(d_tris, n_tris, voxel_size, d_counts, d_area, d_tol);
     void* d_tmp = nullptr; size_t tmp_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_counts, d_offsets, n_tris + 1, st);
     BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp_bytes));
@@ -467,15 +491,19 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
     unsigned long long total = 0; double area_vox = 0.0;
     BS_CUDA(ctx, cudaMemcpyAsync(&total, d_offsets + n_tris, sizeof(total), cudaMemcpyDeviceToHost, st));
     BS_CUDA(ctx, cudaMemcpyAsync(&area_vox, d_area, sizeof(double), cudaMemcpyDeviceToHost, st));
+    unsigned tol_bits = 0;
+    BS_CUDA(ctx, cudaMemcpyAsync(&tol_bits, d_tol, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     BS_CUDA(ctx, cudaStreamSynchronize(st));
-    bs_free(ctx, d_tmp); bs_free(ctx, d_counts); bs_free(ctx, d_area);
+    ctx->mesh_closed = ctx->sign_propagation && bs_mesh_closed_finish(ctx, &chk);
+    memcpy(&ctx->sp_tol, &tol_bits, sizeof(float));
+    bs_free(ctx, d_tmp); bs_free(ctx, d_counts); bs_free(ctx, d_area); bs_free(ctx, d_tol);
     bs_mark(ctx, "subdivide_count_ms");
-    if (total == 0) { bs_free(ctx, d_offsets); bs_free(ctx, d_flags); bs_marks_end(ctx); return BS_ERR_EMPTY_MESH; }  // convert -> None (:58-60)
-    if (total > (1ull << 40)) { bs_free(ctx, d_offsets); bs_free(ctx, d_flags); return bs_fail(ctx, BS_ERR_RANGE, "%llu sub-triangles: voxel size too small for this mesh", total); }
+    if (total == 0) { bs_free(ctx, d_offsets); bs_free(ctx, d_flags); bs_free(ctx, d_neval); bs_marks_end(ctx); return BS_ERR_EMPTY_MESH; }  // convert -> None (:58-60)
+    if (total > (1ull << 40)) { bs_free(ctx, d_offsets); bs_free(ctx, d_flags); bs_free(ctx, d_neval); return bs_fail(ctx, BS_ERR_RANGE, "%llu sub-triangles: voxel size too small for this mesh", total); }
 
     ConvertParams P;
     P.tris = d_tris; P.n_tris = n_tris; P.offsets = d_offsets; P.total = total;
-    P.vs = voxel_size; P.inv_vs = 1.0f / voxel_size; P.band = (int)band; P.flags = d_flags; P.values = nullptr; P.n_eval = d_neval; P.table_counts = nullptr; P.use_clip = 0;
+    P.vs = voxel_size; P.inv_vs = 1.0f / voxel_size; P.band = (int)band; P.flags = d_flags; P.values = nullptr; P.n_eval = d_neval; P.table_counts = nullptr; P.use_clip = 0; P.derr = ctx->d_err;
 
     // 2. mark touched bricks in a hash set; sized from the surface area, doubled on overflow
     const double bw = (double)(2 * band + 1);
@@ -535,7 +563,7 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
         {
             unsigned long long *d_touch = nullptr, *d_C = nullptr, *d_bounds = nullptr; unsigned long long h_bounds[2];
             BS_TRY(bs_alloc(ctx, &d_touch, n_all)); BS_TRY(bs_alloc(ctx, &d_C, n_all)); BS_TRY(bs_alloc(ctx, &d_bounds, (size_t)world + 1));
-            bs_count_launch(), k_brick_touches<<<bs_blocks(n_all, TPB), TPB, 0, st>>>(d_keys, n_all, d_table_keys, d_table_counts, (unsigned)(cap - 1), d_touch);
+            bs_count_launch(), k_brick_touches<<<bs_blocks(n_all, TPB), TPB, 0, st>>>(d_keys, n_all, d_table_keys, d_table_counts, (unsigned)(cap - 1), d_touch, ctx->d_err);
             tmp_bytes = 0;
             cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, d_touch, d_C, n_all, st);
             BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp_bytes));
@@ -579,7 +607,7 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
     }
     BS_TRY(bs_alloc(ctx, &d_table_slots, cap));
     BS_CUDA(ctx, cudaMemsetAsync(d_table_slots, 0xFF, cap * sizeof(unsigned), st));
-    bs_count_launch(), k_fill_slots<<<bs_blocks(n_all, TPB), TPB, 0, st>>>((const unsigned long long*)vol->keys, n_all, d_table_keys, d_table_slots, (unsigned)(cap - 1));
+    bs_count_launch(), k_fill_slots<<<bs_blocks(n_all, TPB), TPB, 0, st>>>((const unsigned long long*)vol->keys, n_all, d_table_keys, d_table_slots, (unsigned)(cap - 1), ctx->d_err);
     BS_CUDA(ctx, cudaMemsetAsync(vol->values, 0x7F, n_all * 512 * sizeof(float), st));
     bs_mark(ctx, "sort_bricks_ms");
     // 4. distances
@@ -601,14 +629,20 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
     // per-brick "touches" (sub-triangle boxes that hit the brick): the sign stage runs the densest bricks first
     unsigned long long* d_touch_kept = nullptr;
     BS_TRY(bs_alloc(ctx, &d_touch_kept, n_all));
-    if (n_all) bs_count_launch(), k_brick_touches<<<bs_blocks(n_all, TPB), TPB, 0, st>>>(vol->keys, n_all, d_table_keys, d_table_counts, (unsigned)(cap - 1), d_touch_kept);
+    if (n_all) bs_count_launch(), k_brick_touches<<<bs_blocks(n_all, TPB), TPB, 0, st>>>(vol->keys, n_all, d_table_keys, d_table_counts, (unsigned)(cap - 1), d_touch_kept, ctx->d_err);
     bs_free(ctx, d_table_keys); bs_free(ctx, d_table_slots); bs_free(ctx, d_table_counts); bs_free(ctx, d_offsets); bs_free(ctx, d_flags); bs_free(ctx, d_neval);
     // 5. signs + masks
     s = bs_sign_impl(ctx, d_tris, n_tris, vol, d_touch_kept);
     bs_free(ctx, d_touch_kept);
     if (s != BS_OK) { bs_volume_free(vol); return s; }
     BS_CUDA(ctx, cudaGetLastError());
-    bs_marks_end(ctx);
+    unsigned derr = 0;
+    BS_CUDA(ctx, cudaMemcpyAsync(&derr, ctx->d_err, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    bs_marks_end(ctx);  // synchronises
+    if (derr) {  // a kernel ran out of a fixed-size resource: an error, never a silently wrong volume
+        bs_volume_free(vol);
+        return bs_fail(ctx, BS_ERR_RANGE, "device limit exceeded:%s%s", (derr & BS_DERR_STACK) ? " winding-number traversal stack" : "", (derr & BS_DERR_PROBE) ? " brick hash probe length" : "");
+    }
     bs_stat_add(ctx, "n_tris", (double)n_tris);
     bs_stat_add(ctx, "n_sub", (double)total);
     bs_stat_add(ctx, "n_bricks", (double)n_all);

@@ -55,6 +55,7 @@ struct Tree {
     const float4* tris;     // 3 x float4 per sorted triangle (9 floats + pad), LEAF per leaf, padded with degenerate triangles
     unsigned n_leaves;
     unsigned root;
+    unsigned* derr;         // bs_context::d_err
 };
 
 __device__ __forceinline__ int f2ord(float f) { int b = __float_as_int(f); return b >= 0 ? b : b ^ 0x7FFFFFFF; }
@@ -392,7 +393,8 @@ struct WarpWinding {
         if (any_near == 0) return;
         // near for some voxel: internal nodes are expanded, leaves evaluated exactly -- both when popped, so the
         // (large) exact-evaluation code exists once instead of once per inlined visit
-        if (sp < STACK) {
+        if (sp >= STACK) { if (lane == 0) atomicOr(T.derr, BS_DERR_STACK); return; }  // reported as BS_ERR_RANGE by bs_convert_impl
+        {
             if (id < T.n_leaves - 1) {  // start pulling the record this entry will need (two 128 B lines)
                 const char* nxt = reinterpret_cast<const char*>(T.rec + (size_t)id * REC);
                 asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt));
@@ -434,7 +436,8 @@ struct WarpWinding {
 
 #ifdef BS_PAIRS
     __device__ __forceinline__ void push(unsigned id, unsigned near_m) {
-        if (near_m == 0 || sp >= STACK) return;
+        if (near_m == 0) return;
+        if (sp >= STACK) { if (lane == 0) atomicOr(T.derr, BS_DERR_STACK); return; }  // reported as BS_ERR_RANGE by bs_convert_impl
         if (id < T.n_leaves - 1) {
             const char* nxt = reinterpret_cast<const char*>(T.rec + (size_t)id * REC);
             asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt));
@@ -634,7 +637,7 @@ __device__ __forceinline__ unsigned demorton9(unsigned p) {
 }
 
 // Active masks + the list of work items for the sign kernel: one item = 32*VPL Morton-adjacent active voxels of one brick.
-__global__ void k_masks(const float* __restrict__ values, size_t n_bricks, unsigned long long* masks, unsigned* n_chunks, int per_chunk) {
+__global__ void k_masks(const float* __restrict__ values, size_t n_bricks, unsigned long long* masks, unsigned* n_chunks, int per_chunk, unsigned long long* n_active) {
     const unsigned lane = threadIdx.x & 31;
     const size_t b = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
     if (b >= n_bricks) return;
@@ -646,7 +649,7 @@ __global__ void k_masks(const float* __restrict__ values, size_t n_bricks, unsig
         cnt += __popc(bal);
     }
     if (lane < 8) masks[b * 8 + lane] = (unsigned long long)lo | ((unsigned long long)hi << 32);
-    if (lane == 0) n_chunks[b] = (cnt + per_chunk - 1) / per_chunk;
+    if (lane == 0) { n_chunks[b] = (cnt + per_chunk - 1) / per_chunk; if (cnt) atomicAdd(n_active, (unsigned long long)cnt); }
 }
 // items are laid out in `order` (bricks under the densest triangles first: their items run longest, so they must not
 // start last); brick_off[b] = first item of brick b
@@ -892,10 +895,9 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, BS_SIGN_MINB) k_sign(Tre
 bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_volume* vol, const unsigned long long* d_touches) {
     cudaStream_t st = ctx->stream;
     if (n_tris >= (1ull << 30)) return bs_fail(ctx, BS_ERR_RANGE, "too many triangles");
-    // EXPERIMENTAL, off unless BSHARK_SIGN_PROPAGATION is set (bs_signprop.cu; parity-tested once on small meshes, not yet timed): on a closed mesh only one
-    // voxel per connected band component is traversed, the others copy its sign
-    bool prop = getenv("BSHARK_SIGN_PROPAGATION") != nullptr;
-    if (prop) { bool closed = false; BS_TRY(bs_mesh_closed_impl(ctx, d_tris, n_tris, &closed)); prop = closed; }
+    // closed mesh (tested by bs_convert_impl, bs_signprop.cu): only one voxel per connected band component is traversed,
+    // the others copy its sign
+    bool prop = ctx->sign_propagation && ctx->mesh_closed;
     // Morton order
     int* d_bounds = nullptr; unsigned long long *d_codes = nullptr, *d_codes2 = nullptr; unsigned *d_ids = nullptr, *d_ids2 = nullptr;
     BS_TRY(bs_alloc(ctx, &d_bounds, 6));
@@ -931,17 +933,20 @@ bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_v
     if (n > 1) bs_count_launch(), k_records<<<bs_blocks(((size_t)n - 1) * 4, 256), 256, 0, st>>>(d_left, d_right, d_hdr, d_coef, n, d_rec);
     bs_free(ctx, d_raw); bs_free(ctx, d_ids2); bs_free(ctx, d_codes2); bs_free(ctx, d_left); bs_free(ctx, d_right); bs_free(ctx, d_parent); bs_free(ctx, d_flags);
     Tree T;
-    T.hdr = d_hdr; T.coef = d_coef; T.rec = d_rec; T.tris = d_sorted; T.n_leaves = (unsigned)n; T.root = root_id;
+    T.hdr = d_hdr; T.coef = d_coef; T.rec = d_rec; T.tris = d_sorted; T.n_leaves = (unsigned)n; T.root = root_id; T.derr = ctx->d_err;
     bs_mark(ctx, "bvh_records_ms");
     if (vol->n_bricks) {
         const size_t nb = vol->n_bricks;
         unsigned *d_nchunks = nullptr, *d_ordered = nullptr, *d_off = nullptr, *d_chunk_off = nullptr, *d_item_brick = nullptr, *d_order = nullptr; unsigned n_items = 0;
         BS_TRY(bs_alloc(ctx, &d_nchunks, nb)); BS_TRY(bs_alloc(ctx, &d_ordered, nb + 1)); BS_TRY(bs_alloc(ctx, &d_off, nb + 1)); BS_TRY(bs_alloc(ctx, &d_chunk_off, nb));
-        bs_count_launch(), k_masks<<<bs_blocks(nb * 32, 256), 256, 0, st>>>(vol->values, nb, vol->masks, d_nchunks, 32 * BS_VPL);
+        unsigned long long* d_sc = nullptr; unsigned long long h_sc[2] = {0, 0};  // active voxels, traversed representatives
+        BS_TRY(bs_alloc(ctx, &d_sc, 2));
+        BS_CUDA(ctx, cudaMemsetAsync(d_sc, 0, 2 * sizeof(unsigned long long), st));
+        bs_count_launch(), k_masks<<<bs_blocks(nb * 32, 256), 256, 0, st>>>(vol->values, nb, vol->masks, d_nchunks, 32 * BS_VPL, d_sc);
         unsigned* d_par = nullptr; unsigned long long* d_seed = nullptr;
         if (prop) {  // work items are formed from the component representatives instead of all active voxels
-            BS_TRY(bs_sign_components_impl(ctx, vol, &d_par, &d_seed));
-            bs_sign_chunks_from_masks(ctx, d_seed, nb, d_nchunks, 32 * BS_VPL);
+            BS_TRY(bs_sign_components_impl(ctx, vol, ctx->sp_tol, &d_par, &d_seed, d_nchunks, 32 * BS_VPL, d_sc + 1, &prop));
+            if (!ctx->count_work) bs_mark(ctx, "sign_components_ms");
         }
         const unsigned long long* item_masks = prop ? d_seed : vol->masks;
         unsigned *d_heavy = nullptr, *d_slot = nullptr, *d_nheavy = nullptr; unsigned n_heavy = 0, n_hitems = 0;
@@ -978,7 +983,9 @@ bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_v
         BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp_bytes));
         cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_ordered, d_off, nb + 1, st);
         BS_CUDA(ctx, cudaMemcpyAsync(&n_items, d_off + nb, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        BS_CUDA(ctx, cudaMemcpyAsync(h_sc, d_sc, sizeof(h_sc), cudaMemcpyDeviceToHost, st));
         BS_CUDA(ctx, cudaStreamSynchronize(st));  // n_heavy has arrived too
+        bs_free(ctx, d_sc);
         if (n_heavy) {  // the heavy bricks head `order`: their items are items [0, n_hitems)
             BS_CUDA(ctx, cudaMemcpyAsync(&n_hitems, d_off + n_heavy, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
             BS_CUDA(ctx, cudaStreamSynchronize(st));
@@ -1018,6 +1025,10 @@ bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_v
         }
         if (prop) { BS_TRY(bs_sign_broadcast_impl(ctx, vol, d_par)); bs_free(ctx, d_par); bs_free(ctx, d_seed); }
         bs_stat_add(ctx, "sign_propagation", prop ? 1.0 : 0.0);
+        bs_stat_add(ctx, "n_active", (double)h_sc[0]);
+        bs_stat_add(ctx, "n_sign_seeds", (double)(prop ? h_sc[1] : h_sc[0]));
+        bs_stat_add(ctx, "n_sign_items", (double)n_items);
+        bs_stat_add(ctx, "sign_tol_voxels", (double)(ctx->sp_tol / vol->voxel_size));
         bs_stat_add(ctx, "n_heavy_bricks", (double)n_heavy);
         bs_stat_add(ctx, "n_heavy_items", (double)n_hitems);
         bs_free(ctx, d_hr); bs_free(ctx, d_partial); bs_free(ctx, d_offs); bs_free(ctx, d_heavy); bs_free(ctx, d_slot);

@@ -43,8 +43,8 @@ def parse():
                     help="scale of the bounded CPU sample (default: 0.1875 for the cpu_baseline of our arm; the reference arm picks the largest of "
                          "0.1875 / 0.125 / 0.09375 / 0.0625 whose steps + warm-up fit in ~150 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sign-propagation", action="store_true",
-                    help="EXPERIMENTAL (off by default, not part of any reported number): set BSHARK_SIGN_PROPAGATION for the library, see DESIGN.md section 7")
+    ap.add_argument("--no-sign-propagation", action="store_true",
+                    help="A/B switch: per-voxel winding numbers even on closed meshes (BS_FLAG_SIGN_PROPAGATION = 0); recorded in config")
     ap.add_argument("--io", action="store_true", help="time the rows either side of the path on the --config mesh: STL decode / encode, merge_points, ActiveVoxelsMesher")
     ap.add_argument("--ops", action="store_true", help="time the CSG (config 2) / offset (3) / dual contouring (4) rows instead of the remesh")
     return ap.parse_args()
@@ -313,8 +313,8 @@ def workload_desc(args):
 
 def main():
     args = parse()
-    if args.sign_propagation:
-        os.environ["BSHARK_SIGN_PROPAGATION"] = "1"
+    if args.no_sign_propagation:
+        os.environ["BSHARK_SIGN_PROPAGATION"] = "0"
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -410,7 +410,7 @@ def main():
     work = ctx.last_stats()
     L.bs_context_set_flag(ctx._h, 1, 0)
     L.bs_volume_free(h)
-    n_active_local = work.get("fwn_voxels", 0.0)
+    n_active_local = work.get("n_active", 0.0)
     if world > 1:  # sharded volumes carry halo bricks: count the job's active voxels once on the unsharded volume
         h = C.c_void_p()
         ctx.check(L.bs_mesh_to_volume_device(ctx._h, C.c_void_p(d_tris.data_ptr()), n_tris, vs, 0, C.byref(h)))
@@ -569,7 +569,7 @@ def main():
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "config %d: %s" % (args.config, workload_desc(args)), "mesh": desc, "n_triangles": int(n_tris), "voxel_size": vs,
                        "band_width": 0, "l2": "inputs larger than L2 (triangles %.0f MB, bricks %.0f MB)" % (tris.nbytes / 1e6, work.get("n_bricks", 0) * 2112 / 1e6),
-                       "parallelism": "brick slabs x%d, mesh replicated" % world, "experimental_sign_propagation": bool(args.sign_propagation)},
+                       "parallelism": "brick slabs x%d, mesh replicated" % world, "sign_propagation": bool(work.get("sign_propagation", 0.0))},
             "remesh_ms": ms_per_step, "tris_per_s": (n_verts / 3.0) / (ms_per_step * 1e-3), "n_active_voxels": n_active, "n_out_triangles": n_verts / 3.0,
             "step_ms": step_ms, "stage_ms": stage_all, "stage_ms_per_rank": per_rank, "work": work,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": int(tris.nbytes), "d2h_bytes_per_step": int(n_verts_local * 12)},

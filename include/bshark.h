@@ -169,8 +169,12 @@ bs_status bs_context_copy_out_verts_device(bs_context* ctx, float* d_dst, size_t
 
 /* BS_FLAG_COUNT_WORK = 1: the next bs_mesh_to_volume* calls run the instrumented winding-number traversal and
  * report fwn_visits / fwn_far / fwn_exact_tris / fwn_voxels through bs_context_last_stats (roofline work counts;
- * slower, never used in a timed region). */
-enum { BS_FLAG_COUNT_WORK = 1 };
+ * slower, never used in a timed region).
+ * BS_FLAG_SIGN_PROPAGATION = 2 (default 1): on a closed input mesh (every directed edge matched by its reverse) the
+ * winding number is traversed once per connected component of the band -- certified from the unsigned distances --
+ * instead of once per voxel (mesh_to_volume.rs:198-281 evaluates every voxel; same signs). 0 = always
+ * per voxel. Open meshes always take the per-voxel path. */
+enum { BS_FLAG_COUNT_WORK = 1, BS_FLAG_SIGN_PROPAGATION = 2 };
 bs_status bs_context_set_flag(bs_context* ctx, int flag, int value);
 
 /* Number of kernels of this library launched by the calling process so far (all contexts; library sorts / scans
