@@ -206,7 +206,9 @@ __global__ void __launch_bounds__(512) k_sp_flatten(unsigned* par, u64* seed_mas
     __syncthreads();
     const unsigned g = (unsigned)(b * 512 + t);
     bool seed = false;
-    if (par[g] != SP_EMPTY) { const unsigned r = sp_find_g(par, g); par[g] = r; seed = r == g; }  // roots are final: compressing while others read is safe
+    // read-only find: a path-halving write by another thread could land AFTER this thread's `par[g] = r` and leave g
+    // pointing at an intermediate ancestor (seen at 2048^3: 31 voxels of 36 M took the sign of a non-representative)
+    if (par[g] != SP_EMPTY) { unsigned r = g, p; volatile unsigned* vp = par; while ((p = vp[r]) != r) r = p; par[g] = r; seed = r == g; }
     const unsigned bal = __ballot_sync(0xFFFFFFFFu, seed);
     if ((t & 31) == 0) { reinterpret_cast<unsigned*>(seed_masks + b * 8)[t >> 5] = bal; if (bal) atomicAdd(&s_cnt, (unsigned)__popc(bal)); }  // bit t of the brick's 512-bit mask
     __syncthreads();

@@ -469,6 +469,25 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
 
+    # ---- self-check: the vertices the e2e leg just delivered to the host (and, on one GPU, the volume itself) must be the
+    # CPU oracle's, bit for bit and in order (fingerprints written by tests/golden/make_config_hashes.py at this size) ------
+    verify_out = None
+    if rank == 0:
+        from baby_shark_b200 import verify
+        try:
+            golden = json.load(open(os.path.join(ROOT, "tests", "golden", "config_hashes.json"))).get("cfg%d@%g" % (args.config, args.scale))
+        except Exception:
+            golden = None
+        if golden is not None:
+            n_fl = int(gather_buf["out"].numel()) if world > 1 else int(nv_e2e) * 3
+            got = verify.fingerprint_soup(h_out[:n_fl].numpy())
+            if world == 1:
+                hv = C.c_void_p()
+                ctx.check(L.bs_mesh_to_volume_device(ctx._h, C.c_void_p(d_tris.data_ptr()), n_tris, vs, 0, C.byref(hv)))
+                got.update(verify.fingerprint_volume(B.Volume(hv, ctx).download()))
+            bad = sorted(k for k, v in got.items() if golden.get(k) != v)
+            verify_out = {"verified": not bad, "checked": sorted(got), "mismatch": bad, "golden": "tests/golden/config_hashes.json cfg%d@%g (CPU oracle, %s)" % (args.config, args.scale, golden.get("desc", ""))}
+
     # ---- e2e, indexed output (single GPU): the same remesh handed to an indexed mesh type -- MC + merge_points on the
     # device, unique points + indices read back (half the bytes of the soup, no host hash pass) -------------------------
     e2e_indexed = None
@@ -575,6 +594,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": int(tris.nbytes), "d2h_bytes_per_step": int(n_verts_local * 12)},
             "e2e_indexed": None, "gpu_launches": None, "clocks": clocks,
             "roofline": dominant, "rooflines": rl,
+            "verified": verify_out["verified"] if verify_out else None, "verify": verify_out,
         }
         if e2e_indexed:
             e2e_indexed["value"] = n_active / (e2e_indexed["ms_per_step"] * 1e-3)
