@@ -105,9 +105,8 @@ struct bs_context {
     int count_work = 0;
     // BS_FLAG_SIGN_PROPAGATION (default 1): closed meshes take one winding-number traversal per connected band component
     int sign_propagation = 1;
-    // per-convert: is the mesh a closed 2-cycle, and the f32 rounding tolerance of the link certificate (world units)
+    // per-convert: is the mesh a closed 2-cycle (bs_signprop.cu)
     bool mesh_closed = false;
-    float sp_tol = 0.f;
     double fwn_counts[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // lane visits, far evals, exact tris, voxels, warp-level visits, traversals, brick-level visits, hoisted nodes
 };
 
@@ -130,7 +129,6 @@ struct bs_volume {
 
 #define BS_DERR_STACK 1u      /* winding-number traversal stack full (bs_fwn.cu STACK) */
 #define BS_DERR_PROBE 2u      /* brick hash: key not found within the probe limit */
-#define BS_DERR_BRICKPASS 4u  /* reserved */
 
 // error plumbing ----------------------------------------------------------------------------------------
 bs_status bs_fail(bs_context* ctx, bs_status st, const char* fmt, ...);
@@ -165,7 +163,8 @@ inline unsigned bs_blocks(size_t n, unsigned threads) { return (unsigned)((n + t
 // stage entry points (one .cu each)
 bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, float voxel_size, int64_t band,
                           int rank, int world, bs_volume** out);
-bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_volume* vol, const unsigned long long* d_touches /*per brick, may be null*/);
+bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_volume* vol, const unsigned long long* d_touches /*per brick, may be null*/,
+                       const unsigned long long* d_blk /*blocked lattice edges, 24 words per brick; null = per-voxel signs*/);
 bs_status bs_mc_impl(const bs_volume* v, float voxel_size, const float** d_verts, size_t* n_verts);
 bs_status bs_dc_impl(const bs_volume* v, float voxel_size, const float** d_verts, size_t* n_verts);
 bs_status bs_csg_impl(bs_volume* a, bs_volume* b, int op, bs_volume** out);
@@ -180,6 +179,14 @@ bs_status bs_merge_points_impl(bs_context* ctx, const float* d_pts, size_t n, fl
 struct bs_closed_check { bool exact, closed, pending; unsigned long long* d_sums; int* d_bad; unsigned long long h_sums[4]; int h_bad; };
 bs_status bs_mesh_closed_begin(bs_context* ctx, const float* d_tris, size_t n_tris, bs_closed_check* chk);  // enqueue; verdict after the next stream sync
 bool bs_mesh_closed_finish(bs_context* ctx, bs_closed_check* chk);
-bs_status bs_sign_components_impl(bs_context* ctx, const bs_volume* vol, float tol, unsigned** d_par, unsigned long long** d_seed, unsigned* d_nchunks, int per_chunk, unsigned long long* d_nseeds, bool* applicable);
-bs_status bs_sign_broadcast_impl(bs_context* ctx, bs_volume* vol, const unsigned* d_par);
+struct bs_sign_components {  // per-brick component tables (8 components per brick)
+    bool ok;
+    unsigned long long *comp /*[n][8][8] masks*/, *planes /*[n][8][6] face planes*/, *face /*[n][9]*/, *rest /*[n][8]*/, *seed /*[n][8] voxels to evaluate*/;
+    unsigned char* ncomp; unsigned short* first /*[n][8] first voxel of a component*/; unsigned* par /*[n][8] union-find over (brick, component)*/;
+};
+bs_status bs_sign_components_impl(bs_context* ctx, const bs_volume* vol, const unsigned long long* d_blk, bs_sign_components* C, unsigned* d_nchunks, int per_chunk, unsigned long long* d_nseeds);
+void bs_sign_components_free(bs_context* ctx, bs_sign_components* C);
+int bs_sign_brute_max();
+bs_status bs_sign_brute_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_volume* vol, const bs_sign_components* C, unsigned n_seeds);
+bs_status bs_sign_broadcast_impl(bs_context* ctx, bs_volume* vol, const bs_sign_components* C);
 bs_status bs_builder_impl(bs_context* ctx, int kind, float voxel_size, const float* p, bs_volume** out);

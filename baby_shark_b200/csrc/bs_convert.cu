@@ -354,6 +354,130 @@ __global__ void __launch_bounds__(TPB) k_eval(ConvertParams P) {
     }
 }
 
+// ---- blocked lattice edges (sign propagation on closed meshes, bs_signprop.cu) ----------------------------------------------
+// For every lattice edge (p, p + e_a) that an ORIGINAL triangle meets -- or comes within a rounding margin of -- set the
+// edge's bit in blk[brick(p)][a]: bit ((y&7)<<3 | (z&7)) of word a*8 + (x&7). Two active lattice neighbours whose edge
+// is not blocked see the same winding number, exactly. The test is a conservative rasterisation in fp64: for each axis a
+// the triangle is projected along a, every lattice column (u, v) inside the projection inflated by eps is intersected
+// with the triangle's plane, and the lattice edges overlapping [z - dz, z + dz] are blocked (dz grows with the slope; a
+// projection thinner than eps -- an edge-on triangle -- blocks its whole extent along a). Lattice positions are the f32
+// products idx * vs every other stage uses, widened exactly to double; vertices are the f32 inputs: the only rounding is
+// fp64 (2^-53), and eps = 64 * 2^-24 * max|coord| + 1e-6 * vs is there for the reference's own f32 winding-number
+// arithmetic, which cannot tell a voxel within a few ulps of the surface from one on it: such voxels lose all six edges
+// and are evaluated on their own.
+constexpr unsigned long long RASTER_SMALL = 256;  // columns a single thread walks; larger projections go to k_block_edges_big
+__device__ __forceinline__ double lat(int i, float vs) { return (double)__fmul_rn((float)i, vs); }
+struct RasterSetup {
+    double V[3][3];  // vertex k, coordinates (u, v, z) = (axis a+1, a+2, a)
+    double eps, umin, umax, vmin, vmax, zmin, zmax, du[3], dv[3], len[3], s, gu, gv, slope;
+    int iu0, iv0, a, kbig; unsigned long long nu, nv; bool thin, ok;
+};
+__device__ __forceinline__ void raster_setup(const ConvertParams& P, size_t t, int a, RasterSetup& R) {
+    const float* p = P.tris + 9 * t;
+    const int ua = (a + 1) % 3, va = (a + 2) % 3;
+    double ma = 0.0; bool finite = true;
+    for (int k = 0; k < 3; ++k) {
+        R.V[k][0] = (double)p[3 * k + ua]; R.V[k][1] = (double)p[3 * k + va]; R.V[k][2] = (double)p[3 * k + a];
+        for (int c = 0; c < 3; ++c) { const double f = fabs((double)p[3 * k + c]); ma = fmax(ma, f); if (!(f < 1.0e30)) finite = false; }
+    }
+    R.a = a; R.ok = finite;
+    if (!finite) { R.nu = R.nv = 0; return; }
+    R.eps = 64.0 * 5.9604644775390625e-8 * ma + 1.0e-6 * (double)P.vs;
+    R.umin = fmin(R.V[0][0], fmin(R.V[1][0], R.V[2][0])); R.umax = fmax(R.V[0][0], fmax(R.V[1][0], R.V[2][0]));
+    R.vmin = fmin(R.V[0][1], fmin(R.V[1][1], R.V[2][1])); R.vmax = fmax(R.V[0][1], fmax(R.V[1][1], R.V[2][1]));
+    R.zmin = fmin(R.V[0][2], fmin(R.V[1][2], R.V[2][2])); R.zmax = fmax(R.V[0][2], fmax(R.V[1][2], R.V[2][2]));
+    const double ivs = 1.0 / (double)P.vs, lim = 1048576.0;
+    const double fu0 = floor((R.umin - R.eps) * ivs) - 1.0, fu1 = ceil((R.umax + R.eps) * ivs) + 1.0;
+    const double fv0 = floor((R.vmin - R.eps) * ivs) - 1.0, fv1 = ceil((R.vmax + R.eps) * ivs) + 1.0;
+    if (!(fu0 > -lim && fu1 < lim && fv0 > -lim && fv1 < lim)) { R.ok = false; R.nu = R.nv = 0; return; }  // outside the supported index range: k_mark reports it
+    R.iu0 = (int)fu0; R.iv0 = (int)fv0; R.nu = (unsigned long long)(fu1 - fu0) + 1; R.nv = (unsigned long long)(fv1 - fv0) + 1;
+    double lmax = -1.0; R.kbig = 0;
+    for (int k = 0; k < 3; ++k) {
+        const int b = (k + 1) % 3;
+        R.du[k] = R.V[b][0] - R.V[k][0]; R.dv[k] = R.V[b][1] - R.V[k][1];
+        R.len[k] = sqrt(R.du[k] * R.du[k] + R.dv[k] * R.dv[k]);
+        if (R.len[k] > lmax) { lmax = R.len[k]; R.kbig = k; }
+    }
+    // (u, v, z) components of e1 x e2
+    const double e1u = R.V[1][0] - R.V[0][0], e1v = R.V[1][1] - R.V[0][1], e1z = R.V[1][2] - R.V[0][2];
+    const double e2u = R.V[2][0] - R.V[0][0], e2v = R.V[2][1] - R.V[0][1], e2z = R.V[2][2] - R.V[0][2];
+    const double nu_ = e1v * e2z - e1z * e2v, nv_ = e1z * e2u - e1u * e2z, nz_ = e1u * e2v - e1v * e2u;
+    R.thin = !(fabs(nz_) > R.eps * (R.len[0] + R.len[1] + R.len[2]));  // projected height below ~eps (or NaN): edge-on
+    R.s = nz_ >= 0.0 ? 1.0 : -1.0;
+    if (!R.thin) { R.gu = -nu_ / nz_; R.gv = -nv_ / nz_; R.slope = fabs(R.gu) + fabs(R.gv); } else { R.gu = R.gv = R.slope = 0.0; }
+}
+__device__ __forceinline__ void raster_block(const ConvertParams& P, unsigned long long* blk, int a, int iu, int iv, int k, unsigned long long& last_key, unsigned& last_slot) {
+    int x, y, z;
+    if (a == 0) { x = k; y = iu; z = iv; } else if (a == 1) { y = k; z = iu; x = iv; } else { z = k; x = iu; y = iv; }
+    const int bx = x >> 3, by = y >> 3, bz = z >> 3;
+    if (bx < BS_BRICK_MIN || bx > BS_BRICK_MAX || by < BS_BRICK_MIN || by > BS_BRICK_MAX || bz < BS_BRICK_MIN || bz > BS_BRICK_MAX) return;
+    const unsigned long long key = bs_brick_key(bx, by, bz);
+    if (key != last_key) { last_key = key; last_slot = hash_lookup(P, key); }
+    if (last_slot == 0xFFFFFFFFu) return;  // no such brick (or not kept on this rank): the edge has no active lower end
+    atomicOr(blk + (size_t)last_slot * 24 + a * 8 + (x & 7), 1ull << (((y & 7) << 3) | (z & 7)));
+}
+__device__ __forceinline__ void raster_column(const ConvertParams& P, unsigned long long* blk, const RasterSetup& R, unsigned long long c, unsigned long long& last_key, unsigned& last_slot) {
+    const int iu = R.iu0 + (int)(c / R.nv), iv = R.iv0 + (int)(c % R.nv);
+    const double pu = lat(iu, P.vs), pv = lat(iv, P.vs);
+    if (pu < R.umin - R.eps || pu > R.umax + R.eps || pv < R.vmin - R.eps || pv > R.vmax + R.eps) return;
+    double lo = R.zmin - R.eps, hi = R.zmax + R.eps;
+    if (!R.thin) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double E = R.du[k] * (pv - R.V[k][1]) - R.dv[k] * (pu - R.V[k][0]);
+            if (R.s * E < -R.eps * R.len[k]) return;  // outside the projection inflated by eps
+        }
+        const double zc = R.V[0][2] + R.gu * (pu - R.V[0][0]) + R.gv * (pv - R.V[0][1]);
+        const double dz = R.eps * (2.0 + R.slope);
+        if (zc - dz > lo) lo = zc - dz;
+        if (zc + dz < hi) hi = zc + dz;
+        if (!(lo <= hi)) { lo = R.zmin - R.eps; hi = R.zmax + R.eps; }  // numerically impossible; stay conservative
+    } else {
+        const int k = R.kbig;  // the projection is (within eps) the segment of its longest edge
+        const double E = R.du[k] * (pv - R.V[k][1]) - R.dv[k] * (pu - R.V[k][0]);
+        if (fabs(E) > 3.0 * R.eps * R.len[k] && R.len[k] > 0.0) return;
+    }
+    const double ivs = 1.0 / (double)P.vs;
+    const int k0 = (int)floor(lo * ivs) - 1, k1 = (int)floor(hi * ivs) + 1;
+    for (int k = k0; k <= k1; ++k)
+        if (lat(k + 1, P.vs) >= lo && lat(k, P.vs) <= hi) raster_block(P, blk, R.a, iu, iv, k, last_key, last_slot);
+}
+__global__ void __launch_bounds__(256) k_block_edges(ConvertParams P, unsigned long long* blk, unsigned long long* big_list, unsigned* n_big, unsigned big_cap) {
+    const size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (g >= P.n_tris * 3) return;
+    const size_t t = g / 3; const int a = (int)(g % 3);
+    if (P.use_clip) {  // sharded: the triangle's box (plus slack) misses every brick this rank keeps
+        const float* p = P.tris + 9 * t;
+        for (int d = 0; d < 3; ++d) {
+            const float lo = fminf(p[d], fminf(p[3 + d], p[6 + d])), hi = fmaxf(p[d], fmaxf(p[3 + d], p[6 + d]));
+            if (ceilf(hi * P.inv_vs) + 3.0f < (float)P.clip_mn[d] || floorf(lo * P.inv_vs) - 3.0f > (float)P.clip_mx[d]) return;
+        }
+    }
+    RasterSetup R;
+    raster_setup(P, t, a, R);
+    if (!R.ok) return;  // non-finite input never passes the closedness test; out-of-range indices were reported by k_mark
+    const unsigned long long ncols = R.nu * R.nv;
+    if (ncols > RASTER_SMALL) {
+        const unsigned i = atomicAdd(n_big, 1u);
+        if (i < big_cap) { big_list[i] = (unsigned long long)g; return; }  // (a full list: this thread walks the columns itself)
+    }
+    unsigned long long last_key = BS_KEY_INVALID; unsigned last_slot = 0xFFFFFFFFu;
+    for (unsigned long long c = 0; c < ncols; ++c) raster_column(P, blk, R, c, last_key, last_slot);
+}
+// projections of more than RASTER_SMALL columns: one CTA per (triangle, axis), threads stride over the columns
+__global__ void __launch_bounds__(256) k_block_edges_big(ConvertParams P, unsigned long long* blk, const unsigned long long* big_list, const unsigned* n_big, unsigned big_cap) {
+    const unsigned n = min(*n_big, big_cap);
+    for (unsigned i = blockIdx.x; i < n; i += gridDim.x) {
+        const unsigned long long g = big_list[i];
+        RasterSetup R;
+        raster_setup(P, (size_t)(g / 3), (int)(g % 3), R);
+        if (!R.ok) continue;
+        const unsigned long long ncols = R.nu * R.nv;
+        unsigned long long last_key = BS_KEY_INVALID; unsigned last_slot = 0xFFFFFFFFu;
+        for (unsigned long long c = threadIdx.x; c < ncols; c += blockDim.x) raster_column(P, blk, R, c, last_key, last_slot);
+    }
+}
+
 __global__ void k_fill_slots(const unsigned long long* sorted_keys, size_t n, unsigned long long* table_keys, unsigned* table_slots, unsigned mask, unsigned* derr) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -481,7 +605,7 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
     BS_CUDA(ctx, cudaMemsetAsync(d_counts + n_tris, 0, sizeof(unsigned long long), st));
     // closed mesh? (bs_signprop.cu) -- enqueued here, read at the synchronisation below
     bs_closed_check chk; chk.pending = false; chk.closed = false; chk.exact = false; chk.d_sums = nullptr; chk.d_bad = nullptr;
-    ctx->mesh_closed = false; ctx->sp_tol = 0.f;
+    ctx->mesh_closed = false;
     if (ctx->sign_propagation) BS_TRY(bs_mesh_closed_begin(ctx, d_tris, n_tris, &chk));
     bs_count_launch(), k_tri_counts<<<bs_blocks(n_tris, TPB), TPB, 0, st>>>(d_tris, n_tris, voxel_size, d_counts, d_area, d_tol);
     void* d_tmp = nullptr; size_t tmp_bytes = 0;
@@ -495,7 +619,7 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
     BS_CUDA(ctx, cudaMemcpyAsync(&tol_bits, d_tol, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     BS_CUDA(ctx, cudaStreamSynchronize(st));
     ctx->mesh_closed = ctx->sign_propagation && bs_mesh_closed_finish(ctx, &chk);
-    memcpy(&ctx->sp_tol, &tol_bits, sizeof(float));
+    (void)tol_bits;
     bs_free(ctx, d_tmp); bs_free(ctx, d_counts); bs_free(ctx, d_area); bs_free(ctx, d_tol);
     bs_mark(ctx, "subdivide_count_ms");
     if (total == 0) { bs_free(ctx, d_offsets); bs_free(ctx, d_flags); bs_free(ctx, d_neval); bs_marks_end(ctx); return BS_ERR_EMPTY_MESH; }  // convert -> None (:58-60)
@@ -626,14 +750,27 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
     }
     bs_count_launch(), k_eval<<<grid, TPB, 0, st>>>(P);
     bs_mark(ctx, "udf_ms");
+    // closed mesh: lattice edges met by a triangle (sign propagation, bs_signprop.cu); needs the brick hash, so it runs here
+    unsigned long long* d_blk = nullptr;
+    if (ctx->mesh_closed && n_all) {
+        const unsigned big_cap = 1u << 22;
+        unsigned long long* d_big = nullptr; unsigned* d_nbig = nullptr;
+        BS_TRY(bs_alloc(ctx, &d_blk, n_all * 24)); BS_TRY(bs_alloc(ctx, &d_big, (size_t)big_cap)); BS_TRY(bs_alloc(ctx, &d_nbig, 1));
+        BS_CUDA(ctx, cudaMemsetAsync(d_blk, 0, n_all * 24 * sizeof(unsigned long long), st));
+        BS_CUDA(ctx, cudaMemsetAsync(d_nbig, 0, sizeof(unsigned), st));
+        bs_count_launch(), k_block_edges<<<bs_blocks(n_tris * 3, TPB), TPB, 0, st>>>(P, d_blk, d_big, d_nbig, big_cap);
+        bs_count_launch(), k_block_edges_big<<<(unsigned)ctx->sm_count * 8, TPB, 0, st>>>(P, d_blk, d_big, d_nbig, big_cap);
+        bs_free(ctx, d_big); bs_free(ctx, d_nbig);
+        bs_mark(ctx, "sign_block_edges_ms");
+    }
     // per-brick "touches" (sub-triangle boxes that hit the brick): the sign stage runs the densest bricks first
     unsigned long long* d_touch_kept = nullptr;
     BS_TRY(bs_alloc(ctx, &d_touch_kept, n_all));
     if (n_all) bs_count_launch(), k_brick_touches<<<bs_blocks(n_all, TPB), TPB, 0, st>>>(vol->keys, n_all, d_table_keys, d_table_counts, (unsigned)(cap - 1), d_touch_kept, ctx->d_err);
     bs_free(ctx, d_table_keys); bs_free(ctx, d_table_slots); bs_free(ctx, d_table_counts); bs_free(ctx, d_offsets); bs_free(ctx, d_flags); bs_free(ctx, d_neval);
     // 5. signs + masks
-    s = bs_sign_impl(ctx, d_tris, n_tris, vol, d_touch_kept);
-    bs_free(ctx, d_touch_kept);
+    s = bs_sign_impl(ctx, d_tris, n_tris, vol, d_touch_kept, d_blk);
+    bs_free(ctx, d_touch_kept); bs_free(ctx, d_blk);
     if (s != BS_OK) { bs_volume_free(vol); return s; }
     BS_CUDA(ctx, cudaGetLastError());
     unsigned derr = 0;

@@ -22,6 +22,7 @@
 #include <cub/cub.cuh>
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 namespace {
 
@@ -892,13 +893,12 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, BS_SIGN_MINB) k_sign(Tre
 #define BS_VPL 1
 #endif
 
-bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_volume* vol, const unsigned long long* d_touches) {
+namespace {
+struct TreeBuffers { float4 *sorted = nullptr, *hdr = nullptr, *coef = nullptr, *rec = nullptr; int* other = nullptr; };
+void free_tree(bs_context* ctx, TreeBuffers& B) { bs_free(ctx, B.sorted); bs_free(ctx, B.hdr); bs_free(ctx, B.coef); bs_free(ctx, B.rec); bs_free(ctx, B.other); B = TreeBuffers(); }
+// LBVH over the triangles: Morton order, Karras hierarchy, moments, traversal records
+bs_status build_tree(bs_context* ctx, const float* d_tris, size_t n_tris, Tree& T, TreeBuffers& B) {
     cudaStream_t st = ctx->stream;
-    if (n_tris >= (1ull << 30)) return bs_fail(ctx, BS_ERR_RANGE, "too many triangles");
-    // closed mesh (tested by bs_convert_impl, bs_signprop.cu): only one voxel per connected band component is traversed,
-    // the others copy its sign
-    bool prop = ctx->sign_propagation && ctx->mesh_closed;
-    // Morton order
     int* d_bounds = nullptr; unsigned long long *d_codes = nullptr, *d_codes2 = nullptr; unsigned *d_ids = nullptr, *d_ids2 = nullptr;
     BS_TRY(bs_alloc(ctx, &d_bounds, 6));
     const int init[6] = {0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF, (int)0x80000000, (int)0x80000000, (int)0x80000000};
@@ -913,48 +913,70 @@ bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_v
     cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_codes, d_codes2, d_ids, d_ids2, n_tris, 0, 48, st);
     bs_free(ctx, d_tmp); bs_free(ctx, d_codes); bs_free(ctx, d_ids); bs_free(ctx, d_bounds);
     bs_mark(ctx, "bvh_sort_ms");
-    // hierarchy
     const int n = (int)((n_tris + LEAF - 1) / LEAF);
     const int n_nodes = 2 * n - 1;
-    int *d_left = nullptr, *d_right = nullptr, *d_parent = nullptr, *d_other = nullptr; unsigned* d_flags = nullptr;
-    float4 *d_sorted = nullptr, *d_hdr = nullptr, *d_coef = nullptr, *d_rec = nullptr; Raw* d_raw = nullptr;
+    int *d_left = nullptr, *d_right = nullptr, *d_parent = nullptr; unsigned* d_flags = nullptr; Raw* d_raw = nullptr;
     BS_TRY(bs_alloc(ctx, &d_left, (size_t)n)); BS_TRY(bs_alloc(ctx, &d_right, (size_t)n)); BS_TRY(bs_alloc(ctx, &d_parent, (size_t)n_nodes));
-    BS_TRY(bs_alloc(ctx, &d_flags, (size_t)n)); BS_TRY(bs_alloc(ctx, &d_other, (size_t)n));
-    BS_TRY(bs_alloc(ctx, &d_sorted, (size_t)n * LEAF * 3));
-    BS_TRY(bs_alloc(ctx, &d_hdr, (size_t)n_nodes)); BS_TRY(bs_alloc(ctx, &d_coef, (size_t)n_nodes * 3));
-    BS_TRY(bs_alloc(ctx, &d_rec, (size_t)n * REC));
+    BS_TRY(bs_alloc(ctx, &d_flags, (size_t)n)); BS_TRY(bs_alloc(ctx, &B.other, (size_t)n));
+    BS_TRY(bs_alloc(ctx, &B.sorted, (size_t)n * LEAF * 3));
+    BS_TRY(bs_alloc(ctx, &B.hdr, (size_t)n_nodes)); BS_TRY(bs_alloc(ctx, &B.coef, (size_t)n_nodes * 3));
+    BS_TRY(bs_alloc(ctx, &B.rec, (size_t)n * REC));
     BS_TRY(bs_alloc(ctx, &d_raw, (size_t)n_nodes));
     BS_CUDA(ctx, cudaMemsetAsync(d_flags, 0, (size_t)n * sizeof(unsigned), st));
-    if (n > 1) bs_count_launch(), k_karras<<<bs_blocks((size_t)n - 1, 256), 256, 0, st>>>(d_codes2, n, d_left, d_right, d_parent, d_other);
-    const unsigned root_id = 0u;
+    if (n > 1) bs_count_launch(), k_karras<<<bs_blocks((size_t)n - 1, 256), 256, 0, st>>>(d_codes2, n, d_left, d_right, d_parent, B.other);
     bs_mark(ctx, "bvh_tree_ms");
-    bs_count_launch(), k_leaves_and_climb<<<bs_blocks((size_t)n, CLIMB_TPB), CLIMB_TPB, 0, st>>>(d_tris, d_ids2, n_tris, d_sorted, d_raw, d_left, d_right, d_parent, d_other, d_flags, n, d_hdr, d_coef);
+    bs_count_launch(), k_leaves_and_climb<<<bs_blocks((size_t)n, CLIMB_TPB), CLIMB_TPB, 0, st>>>(d_tris, d_ids2, n_tris, B.sorted, d_raw, d_left, d_right, d_parent, B.other, d_flags, n, B.hdr, B.coef);
     bs_mark(ctx, "bvh_moments_ms");
-    if (n > 1) bs_count_launch(), k_records<<<bs_blocks(((size_t)n - 1) * 4, 256), 256, 0, st>>>(d_left, d_right, d_hdr, d_coef, n, d_rec);
+    if (n > 1) bs_count_launch(), k_records<<<bs_blocks(((size_t)n - 1) * 4, 256), 256, 0, st>>>(d_left, d_right, B.hdr, B.coef, n, B.rec);
     bs_free(ctx, d_raw); bs_free(ctx, d_ids2); bs_free(ctx, d_codes2); bs_free(ctx, d_left); bs_free(ctx, d_right); bs_free(ctx, d_parent); bs_free(ctx, d_flags);
-    Tree T;
-    T.hdr = d_hdr; T.coef = d_coef; T.rec = d_rec; T.tris = d_sorted; T.n_leaves = (unsigned)n; T.root = root_id; T.derr = ctx->d_err;
+    T.hdr = B.hdr; T.coef = B.coef; T.rec = B.rec; T.tris = B.sorted; T.n_leaves = (unsigned)n; T.root = 0u; T.derr = ctx->d_err;
     bs_mark(ctx, "bvh_records_ms");
-    if (vol->n_bricks) {
-        const size_t nb = vol->n_bricks;
-        unsigned *d_nchunks = nullptr, *d_ordered = nullptr, *d_off = nullptr, *d_chunk_off = nullptr, *d_item_brick = nullptr, *d_order = nullptr; unsigned n_items = 0;
-        BS_TRY(bs_alloc(ctx, &d_nchunks, nb)); BS_TRY(bs_alloc(ctx, &d_ordered, nb + 1)); BS_TRY(bs_alloc(ctx, &d_off, nb + 1)); BS_TRY(bs_alloc(ctx, &d_chunk_off, nb));
-        unsigned long long* d_sc = nullptr; unsigned long long h_sc[2] = {0, 0};  // active voxels, traversed representatives
-        BS_TRY(bs_alloc(ctx, &d_sc, 2));
-        BS_CUDA(ctx, cudaMemsetAsync(d_sc, 0, 2 * sizeof(unsigned long long), st));
-        bs_count_launch(), k_masks<<<bs_blocks(nb * 32, 256), 256, 0, st>>>(vol->values, nb, vol->masks, d_nchunks, 32 * BS_VPL, d_sc);
-        unsigned* d_par = nullptr; unsigned long long* d_seed = nullptr;
-        if (prop) {  // work items are formed from the component representatives instead of all active voxels
-            BS_TRY(bs_sign_components_impl(ctx, vol, ctx->sp_tol, &d_par, &d_seed, d_nchunks, 32 * BS_VPL, d_sc + 1, &prop));
-            if (!ctx->count_work) bs_mark(ctx, "sign_components_ms");
+    return BS_OK;
+}
+}  // namespace
+
+bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_volume* vol, const unsigned long long* d_touches, const unsigned long long* d_blk) {
+    cudaStream_t st = ctx->stream;
+    if (n_tris >= (1ull << 30)) return bs_fail(ctx, BS_ERR_RANGE, "too many triangles");
+    const size_t nb = vol->n_bricks;
+    if (nb == 0) return BS_OK;
+    // closed mesh (tested by bs_convert_impl, bs_signprop.cu): only one voxel per connected band component is evaluated,
+    // the others copy its sign
+    bool prop = ctx->sign_propagation && ctx->mesh_closed && d_blk != nullptr;
+    void* d_tmp = nullptr; size_t tmp_bytes = 0;
+    unsigned *d_nchunks = nullptr, *d_ordered = nullptr, *d_off = nullptr, *d_chunk_off = nullptr, *d_item_brick = nullptr, *d_order = nullptr; unsigned n_items = 0;
+    BS_TRY(bs_alloc(ctx, &d_nchunks, nb)); BS_TRY(bs_alloc(ctx, &d_ordered, nb + 1)); BS_TRY(bs_alloc(ctx, &d_off, nb + 1)); BS_TRY(bs_alloc(ctx, &d_chunk_off, nb));
+    unsigned long long* d_sc = nullptr; unsigned long long h_sc[2] = {0, 0};  // active voxels, evaluated representatives
+    BS_TRY(bs_alloc(ctx, &d_sc, 2));
+    BS_CUDA(ctx, cudaMemsetAsync(d_sc, 0, 2 * sizeof(unsigned long long), st));
+    bs_count_launch(), k_masks<<<bs_blocks(nb * 32, 256), 256, 0, st>>>(vol->values, nb, vol->masks, d_nchunks, 32 * BS_VPL, d_sc);
+    bs_sign_components C; memset(&C, 0, sizeof(C));
+    bool brute = false;
+    if (prop) {  // work items are formed from the component representatives instead of all active voxels
+        BS_TRY(bs_sign_components_impl(ctx, vol, d_blk, &C, d_nchunks, 32 * BS_VPL, d_sc + 1));
+        prop = C.ok;
+        if (prop) {
+            BS_CUDA(ctx, cudaMemcpyAsync(h_sc, d_sc, sizeof(h_sc), cudaMemcpyDeviceToHost, st));
+            BS_CUDA(ctx, cudaStreamSynchronize(st));
+            brute = h_sc[1] <= (unsigned long long)bs_sign_brute_max() && !ctx->count_work && !getenv("BSHARK_NO_BRUTE");
         }
-        const unsigned long long* item_masks = prop ? d_seed : vol->masks;
-        unsigned *d_heavy = nullptr, *d_slot = nullptr, *d_nheavy = nullptr; unsigned n_heavy = 0, n_hitems = 0;
+        bs_mark(ctx, "sign_components_ms");
+    }
+    unsigned n_heavy = 0, n_hitems = 0;
+    if (brute) {
+        BS_TRY(bs_sign_brute_impl(ctx, d_tris, n_tris, vol, &C, (unsigned)h_sc[1]));
+        bs_mark(ctx, "sign_brute_ms");
+    } else {
+        Tree T; TreeBuffers TB;
+        BS_TRY(build_tree(ctx, d_tris, n_tris, T, TB));
+        const unsigned long long* item_masks = prop ? C.seed : vol->masks;
+        unsigned *d_heavy = nullptr, *d_slot = nullptr, *d_nheavy = nullptr;
         if (d_touches) {  // heaviest bricks first; bricks with >= 2^shift touching sub-triangle boxes are "heavy" (split by triangles)
             int shift = 11;
-            // On one GPU the long items simply start first and hide behind the rest (splitting them costs 1.6 ms of extra
-            // launches and refinement on config 5); on a brick slab they ARE the stage time, so sharded runs split.
-            bool split = vol->owned != nullptr;
+            // On one GPU with every voxel traversed the long items simply start first and hide behind the rest (splitting them
+            // costs 1.6 ms of extra launches and refinement on config 5); on a brick slab, or when only the representatives
+            // are traversed, they ARE the stage time, so those runs split.
+            bool split = vol->owned != nullptr || prop;
             if (const char* e = getenv("BSHARK_HEAVY_SHIFT")) { shift = atoi(e); split = true; }  // tests: force the heavy path on small meshes
             unsigned *d_k = nullptr, *d_k2 = nullptr, *d_i = nullptr;
             BS_TRY(bs_alloc(ctx, &d_k, nb)); BS_TRY(bs_alloc(ctx, &d_k2, nb)); BS_TRY(bs_alloc(ctx, &d_i, nb)); BS_TRY(bs_alloc(ctx, &d_order, nb));
@@ -985,15 +1007,13 @@ bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_v
         BS_CUDA(ctx, cudaMemcpyAsync(&n_items, d_off + nb, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
         BS_CUDA(ctx, cudaMemcpyAsync(h_sc, d_sc, sizeof(h_sc), cudaMemcpyDeviceToHost, st));
         BS_CUDA(ctx, cudaStreamSynchronize(st));  // n_heavy has arrived too
-        bs_free(ctx, d_sc);
         if (n_heavy) {  // the heavy bricks head `order`: their items are items [0, n_hitems)
             BS_CUDA(ctx, cudaMemcpyAsync(&n_hitems, d_off + n_heavy, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
             BS_CUDA(ctx, cudaStreamSynchronize(st));
         }
-        bs_free(ctx, d_tmp); bs_free(ctx, d_nchunks); bs_free(ctx, d_ordered);
+        bs_free(ctx, d_tmp);
         BS_TRY(bs_alloc(ctx, &d_item_brick, n_items));
         bs_count_launch(), k_items<<<bs_blocks(nb, 256), 256, 0, st>>>(d_order, d_off, nb, d_item_brick, d_chunk_off);
-        bs_free(ctx, d_off); bs_free(ctx, d_order);
         BrickOut* d_bo = nullptr;
         float kappa = KAPPA_DEFAULT;
         if (const char* e = getenv("BSHARK_KAPPA")) kappa = (float)atof(e);  // tuning knob for experiments only
@@ -1010,7 +1030,7 @@ bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_v
         if (ctx->count_work) bs_count_launch(), k_brick_pass<true><<<bs_blocks(nb, BP_WARPS), 32 * BP_WARPS, 0, st>>>(T, vol->keys, nb, vol->voxel_size, kappa, d_bo, d_cnt);
         else bs_count_launch(), k_brick_pass<false><<<bs_blocks(nb, BP_WARPS), 32 * BP_WARPS, 0, st>>>(T, vol->keys, nb, vol->voxel_size, kappa, d_bo, nullptr);
         if (!ctx->count_work) bs_mark(ctx, "sign_brick_pass_ms");
-        if (n_hitems) bs_count_launch(), k_expand_roots<<<bs_blocks(n_heavy, 4), 128, 0, st>>>(T, d_other, d_heavy, n_heavy, d_bo, d_hr);
+        if (n_hitems) bs_count_launch(), k_expand_roots<<<bs_blocks(n_heavy, 4), 128, 0, st>>>(T, TB.other, d_heavy, n_heavy, d_bo, d_hr);
         if (n_items) {
             if (ctx->count_work) bs_count_launch(), k_sign<true, BS_VPL><<<blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(T, vol->values, item_masks, n_items, d_item_brick, d_chunk_off, vol->keys, vol->voxel_size, d_bo, d_cnt, H);
             else bs_count_launch(), k_sign<false, BS_VPL><<<blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(T, vol->values, item_masks, n_items, d_item_brick, d_chunk_off, vol->keys, vol->voxel_size, d_bo, nullptr, H);
@@ -1023,19 +1043,21 @@ bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_v
             bs_free(ctx, d_cnt);
             for (int i = 0; i < 9; ++i) ctx->fwn_counts[i] = (double)h_cnt[i];
         }
-        if (prop) { BS_TRY(bs_sign_broadcast_impl(ctx, vol, d_par)); bs_free(ctx, d_par); bs_free(ctx, d_seed); }
-        bs_stat_add(ctx, "sign_propagation", prop ? 1.0 : 0.0);
-        bs_stat_add(ctx, "n_active", (double)h_sc[0]);
-        bs_stat_add(ctx, "n_sign_seeds", (double)(prop ? h_sc[1] : h_sc[0]));
-        bs_stat_add(ctx, "n_sign_items", (double)n_items);
-        bs_stat_add(ctx, "sign_tol_voxels", (double)(ctx->sp_tol / vol->voxel_size));
-        bs_stat_add(ctx, "n_heavy_bricks", (double)n_heavy);
-        bs_stat_add(ctx, "n_heavy_items", (double)n_hitems);
         bs_free(ctx, d_hr); bs_free(ctx, d_partial); bs_free(ctx, d_offs); bs_free(ctx, d_heavy); bs_free(ctx, d_slot);
-        bs_free(ctx, d_bo); bs_free(ctx, d_chunk_off); bs_free(ctx, d_item_brick);
+        bs_free(ctx, d_bo); bs_free(ctx, d_item_brick);
+        free_tree(ctx, TB);
+        bs_mark(ctx, "sign_ms");
     }
-    bs_mark(ctx, "sign_ms");
-    bs_free(ctx, d_sorted); bs_free(ctx, d_hdr); bs_free(ctx, d_coef); bs_free(ctx, d_rec); bs_free(ctx, d_other);
+    if (prop) { BS_TRY(bs_sign_broadcast_impl(ctx, vol, &C)); bs_mark(ctx, "sign_broadcast_ms"); }
+    bs_sign_components_free(ctx, &C);
+    bs_free(ctx, d_sc); bs_free(ctx, d_nchunks); bs_free(ctx, d_ordered); bs_free(ctx, d_off); bs_free(ctx, d_order); bs_free(ctx, d_chunk_off);
+    bs_stat_add(ctx, "sign_propagation", prop ? 1.0 : 0.0);
+    bs_stat_add(ctx, "sign_brute_force", brute ? 1.0 : 0.0);
+    bs_stat_add(ctx, "n_active", (double)h_sc[0]);
+    bs_stat_add(ctx, "n_sign_seeds", (double)(prop ? h_sc[1] : h_sc[0]));
+    bs_stat_add(ctx, "n_sign_items", (double)n_items);
+    bs_stat_add(ctx, "n_heavy_bricks", (double)n_heavy);
+    bs_stat_add(ctx, "n_heavy_items", (double)n_hitems);
     BS_CUDA(ctx, cudaGetLastError());
     return BS_OK;
 }

@@ -4,26 +4,24 @@
 //
 // The reference evaluates the (approximate) winding number of EVERY active voxel and thresholds it at 0.2. On a closed
 // mesh -- every directed edge a->b is matched by an edge b->a, i.e. the boundary of the triangle chain is zero -- the
-// exact winding number is an integer that only changes across the surface, so it is the same for two lattice neighbours
-// p, q whenever the segment pq cannot meet the surface. That is certified from the unsigned distances already computed:
-//     min(d_p, vs) + min(d_q, vs) > |pq| + tol
-// (the scatter-min distance of bs_convert.cu is exact below one voxel: a sub-triangle whose integer box misses a lattice
-// point is at least one voxel away from it). `tol` (bs_context::sp_tol, computed per mesh by k_tri_counts) bounds what
-// f32 rounding can move: the sub-triangles the distances were measured to come from running sums of up to n+1 f32
-// additions (mesh_to_volume.rs:90-115) and drift from the true triangle -- which is what the winding number sees -- by at
-// most 1.74 (n + 13) 2^-24 max|coord|, and the lattice positions / box roundings add a few ulps of the coordinates.
+// exact winding number is an integer that changes only across the surface: two lattice neighbours p, q have the same
+// winding number unless a triangle meets the segment pq. k_block_edges (bs_convert.cu) marks exactly those lattice edges
+// (conservatively, in fp64, from the original triangles); every other edge between two active voxels is a certified link.
 //
-// Steps: (1) closed? (2) union-find over the certified face links of the band voxels -- inside a brick in shared memory,
-// across brick faces in global memory with path halving; (3) the per-voxel traversal of bs_fwn.cu runs on ONE voxel per
-// component (two shell components plus the 5-10 % of voxels that hug the surface and certify no link); (4) every other
+// Steps: (1) closed? (2) connected components of the band under certified links: inside a brick a bit-parallel flood fill
+// over the brick's 512-bit masks (8 lanes per brick, one 64-bit x-slab each; <= 8 components per brick, anything beyond
+// becomes individually evaluated voxels), across brick faces a lock-free union-find over (brick, component) ids -- 8 ids
+// per brick, not one per voxel; (3) ONE voxel per component is evaluated -- by a brute-force sum of solid angles over all
+// triangles when there are only a few (typically the inside shell, the outside shell and the handful of voxels that lie
+// on the surface within rounding), else by the LBVH traversal of bs_fwn.cu on the representatives only; (4) every other
 // voxel copies the sign of its component's representative.
 //
 // (1) has two implementations. Default: a 128-bit multiset fingerprint -- sum over directed edges of H(a, b) must equal
 // the sum of H(b, a), H a 2 x 64-bit mix of the six coordinate words (-0 folded into +0; any non-finite coordinate means
-// "not closed"): one streaming pass over the triangles (0.1 ms for 10 M) instead of a hash table + 64-bit sort of 30 M
-// edge keys (3.6 ms); a false "closed" needs a 128-bit collision. BSHARK_CLOSED_CHECK=exact selects the sort-based test
-// (vertices identified by exact coordinates like merge_points, every directed edge exactly once and its reverse exactly
-// once); tests/test_gpu_signprop.py runs both on every test mesh.
+// "not closed"): one streaming pass over the triangles instead of a hash table + 64-bit sort of 3 n edge keys; a false
+// "closed" needs a 128-bit collision. BSHARK_CLOSED_CHECK=exact selects the sort-based test (vertices identified by exact
+// coordinates like merge_points, every directed edge exactly once and its reverse exactly once);
+// tests/test_gpu_signprop.py runs both on every test mesh.
 #include "bs_common.cuh"
 #include <cub/cub.cuh>
 #include <cstdlib>
@@ -109,23 +107,77 @@ __global__ void k_sp_edges_check(const u64* __restrict__ keys /*sorted*/, size_t
     if (!(lo < m && keys[lo] == rev)) *bad = 1;               // boundary edge
 }
 
-// ---- (2) union-find over certified links ------------------------------------------------------------------------------------
-// shared-memory phase (one brick): plain find, the trees are shallow
-__device__ __forceinline__ unsigned sp_find_s(volatile unsigned* par, unsigned x) {
-    unsigned p;
-    while ((p = par[x]) != x) x = p;
-    return x;
+// ---- (2) components -------------------------------------------------------------------------------------------------------
+// Brick bit layout (bs_common.cuh): voxel (x, y, z) = bit (y << 3 | z) of word x. Face planes are 64-bit words:
+// x faces: bit (y << 3 | z); y faces: bit (x << 3 | z); z faces: bit (x << 3 | y).
+constexpr int SP_K = 8;  // components per brick
+__device__ __forceinline__ u64 sp_gather8(u64 v) { return ((v & 0x0101010101010101ULL) * 0x0102040810204080ULL) >> 56; }  // bits 0, 8, .., 56 -> bits 0..7
+__device__ __forceinline__ u64 sp_group_or(u64 v, unsigned gmask) {
+    v |= __shfl_xor_sync(gmask, v, 1); v |= __shfl_xor_sync(gmask, v, 2); v |= __shfl_xor_sync(gmask, v, 4);
+    return v;
 }
-__device__ __forceinline__ void sp_union_s(unsigned* par, unsigned a, unsigned b) {
+// the six face planes (-x, +x, -y, +y, -z, +z) of a 512-bit set held one word per lane of an 8-lane group
+__device__ __forceinline__ void sp_planes(u64 S, unsigned w, unsigned gmask, u64 out[6]) {
+    out[0] = sp_group_or(w == 0 ? S : 0, gmask); out[1] = sp_group_or(w == 7 ? S : 0, gmask);
+    out[2] = sp_group_or((S & 0xFF) << (8 * w), gmask); out[3] = sp_group_or((S >> 56) << (8 * w), gmask);
+    out[4] = sp_group_or(sp_gather8(S) << (8 * w), gmask); out[5] = sp_group_or(sp_gather8(S >> 7) << (8 * w), gmask);
+}
+// 8 lanes per brick, lane w holds the x = w slab of every mask
+__global__ void __launch_bounds__(256) k_sp_bricks(const u64* __restrict__ masks, const u64* __restrict__ blk, size_t n,
+                                                   u64* comp /*[n][K][8]*/, u64* planes /*[n][K][6]*/, u64* face /*[n][9]: active -x +x -y +y -z +z, blocked +x +y +z*/,
+                                                   u64* rest /*[n][8]*/, unsigned char* ncomp, unsigned short* first /*[n][K]*/, unsigned* par /*[n][K]*/) {
+    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t b = t >> 3;
+    const unsigned w = (unsigned)(t & 7), gl = (threadIdx.x & 31) & ~7u, gmask = 0xFFu << gl;
+    if (b >= n) return;  // whole groups leave together
+    const u64 A = masks[b * 8 + w], BX = blk[b * 24 + w], BY = blk[b * 24 + 8 + w], BZ = blk[b * 24 + 16 + w];
+    const u64 A_up = __shfl_down_sync(gmask, A, 1, 8);
+    const u64 LZ = A & (A >> 1) & ~BZ & 0x7F7F7F7F7F7F7F7FULL;   // voxel linked to its +z neighbour
+    const u64 LY = A & (A >> 8) & ~BY & 0x00FFFFFFFFFFFFFFULL;   // ... +y
+    const u64 LX = w < 7 ? (A & A_up & ~BX) : 0;                 // ... +x (same bit of the next word)
+    u64 LXdn = __shfl_up_sync(gmask, LX, 1, 8); if (w == 0) LXdn = 0;
+    const u64 linked = LZ | (LZ << 1) | LY | (LY << 8) | LX | LXdn;
+    // voxels without any link inside the brick and not on a face can have no link at all: evaluated on their own
+    const u64 R = A & ~linked & ((w == 0 || w == 7) ? 0 : 0x007E7E7E7E7E7E00ULL);
+    u64 U = A & ~R;
+    unsigned k = 0;
     for (;;) {
-        a = sp_find_s(par, a); b = sp_find_s(par, b);
-        if (a == b) return;
-        if (a > b) { const unsigned t = a; a = b; b = t; }
-        if (atomicCAS(par + b, b, a) == b) return;
+        const unsigned nz = (__ballot_sync(gmask, U != 0) >> gl) & 0xFFu;
+        if (nz == 0 || k == SP_K) break;
+        const unsigned wl = __ffs(nz) - 1;
+        u64 S = (w == wl) ? (U & (0 - U)) : 0;  // lowest voxel not yet in a component
+        const unsigned f0 = (wl << 6) | (unsigned)(__ffsll((long long)__shfl_sync(gmask, U, gl + wl)) - 1);
+        for (;;) {
+            const u64 S0 = S;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) S |= ((S & LZ) << 1) | ((S >> 1) & LZ) | ((S & LY) << 8) | ((S >> 8) & LY);
+            u64 up = __shfl_up_sync(gmask, S & LX, 1, 8); if (w == 0) up = 0;
+            const u64 dn = __shfl_down_sync(gmask, S, 1, 8) & LX;  // LX is 0 on lane 7
+            S |= up | dn;
+            if (!__any_sync(gmask, S != S0)) break;
+        }
+        comp[(b * SP_K + k) * 8 + w] = S;
+        U &= ~S;
+        u64 pl[6];
+        sp_planes(S, w, gmask, pl);
+        if (w < 6) planes[(b * SP_K + k) * 6 + w] = pl[w];
+        if (w == 0) first[b * SP_K + k] = (unsigned short)f0;
+        ++k;
     }
+    rest[b * 8 + w] = R | U;  // (U != 0 only when the brick holds more than SP_K components)
+    par[b * SP_K + w] = (unsigned)(b * SP_K + w);
+    if (w == 0) ncomp[b] = (unsigned char)k;
+    u64 pa[6], pb[6];
+    sp_planes(A, w, gmask, pa);
+    if (w < 6) face[b * 9 + w] = pa[w];
+    // blocked bits of the edges leaving through +x (word 7 of BX), +y (y = 7 rows of BY), +z (z = 7 bits of BZ)
+    sp_planes(BX, w, gmask, pb); const u64 bx = pb[1];
+    sp_planes(BY, w, gmask, pb); const u64 by = pb[3];
+    sp_planes(BZ, w, gmask, pb); const u64 bz = pb[5];
+    if (w == 0) { face[b * 9 + 6] = bx; face[b * 9 + 7] = by; face[b * 9 + 8] = bz; }
 }
-// global phase: the two shell components span every brick, so finds halve the path as they go (a stale or concurrent
-// write only ever replaces a parent by one of its ancestors; roots change by atomicCAS alone). Loads bypass L1.
+// union-find over (brick, component) ids: the larger root is hooked under the smaller one by atomicCAS; finds halve the
+// path as they go (a halving write only ever replaces a parent by one of its ancestors). Loads bypass L1.
 __device__ __forceinline__ unsigned sp_find_g(unsigned* par, unsigned x) {
     volatile unsigned* vp = par;
     unsigned p = vp[x];
@@ -144,83 +196,152 @@ __device__ __forceinline__ void sp_union_g(unsigned* par, unsigned a, unsigned b
         if (atomicCAS(par + b, b, a) == b) return;
     }
 }
-// one CTA (512 threads, one per voxel) per brick: components of the brick's own certified links, written as global ids
-__global__ void __launch_bounds__(512) k_sp_bricks(const float* __restrict__ values, const u64* __restrict__ masks, float vs, float thr, unsigned* par) {
-    __shared__ unsigned s_par[512];
-    __shared__ float s_cap[512];
-    const size_t b = blockIdx.x;
-    const unsigned t = threadIdx.x;
-    const bool act = (masks[b * 8 + (t >> 6)] >> (t & 63)) & 1ull;
-    const float cap = act ? fminf(fabsf(values[b * 512 + t]), vs) : -1.0f;
-    s_par[t] = t; s_cap[t] = cap;
-    __syncthreads();
-    if (act) {
-        const unsigned x = t >> 6, y = (t >> 3) & 7, z = t & 7;
-        if (x < 7 && s_cap[t + 64] >= 0.f && cap + s_cap[t + 64] > thr) sp_union_s(s_par, t, t + 64);
-        if (y < 7 && s_cap[t + 8] >= 0.f && cap + s_cap[t + 8] > thr) sp_union_s(s_par, t, t + 8);
-        if (z < 7 && s_cap[t + 1] >= 0.f && cap + s_cap[t + 1] > thr) sp_union_s(s_par, t, t + 1);
-    }
-    __syncthreads();
-    par[b * 512 + t] = act ? (unsigned)(b * 512) + sp_find_s(s_par, t) : SP_EMPTY;
-}
 __device__ __forceinline__ long long sp_find_key(const u64* keys, size_t n, u64 k) {
     size_t lo = 0, hi = n;
     while (lo < hi) { const size_t mid = (lo + hi) >> 1; if (keys[mid] < k) lo = mid + 1; else hi = mid; }
     return (lo < n && keys[lo] == k) ? (long long)lo : -1;
 }
-// one CTA (192 threads) per brick: certified links across its +x, +y, +z faces. Most of a face's links join the same
-// two brick-level roots: a lane skips its union when the previous lane of its warp holds the same pair.
-__global__ void __launch_bounds__(192) k_sp_faces(const u64* __restrict__ keys, size_t n, const float* __restrict__ values, const u64* __restrict__ masks, float vs, float thr, unsigned* par) {
-    __shared__ long long s_nb[3];
-    const size_t b = blockIdx.x;
-    if (threadIdx.x < 3) {
-        int bx, by, bz; bs_key_brick(keys[b], bx, by, bz);
-        const int ax = threadIdx.x;
-        bx += ax == 0; by += ax == 1; bz += ax == 2;
-        s_nb[ax] = (bx <= BS_BRICK_MAX && by <= BS_BRICK_MAX && bz <= BS_BRICK_MAX) ? sp_find_key(keys, n, bs_brick_key(bx, by, bz)) : -1;
-    }
-    __syncthreads();
-    const unsigned ax = threadIdx.x >> 6, u = (threadIdx.x >> 3) & 7, v = threadIdx.x & 7;
-    const long long nb = s_nb[ax];  // uniform per warp (64 threads per axis)
+// one thread per (brick, axis): certified links across the brick's +axis face join components of the two bricks
+__global__ void __launch_bounds__(256) k_sp_faces(const u64* __restrict__ keys, size_t n, const u64* __restrict__ planes, const u64* __restrict__ face,
+                                                  const unsigned char* __restrict__ ncomp, unsigned* par) {
+    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (t >= n * 3) return;
+    const size_t b = t / 3; const int a = (int)(t % 3);
+    const unsigned nc = ncomp[b];
+    if (nc == 0) return;
+    int bx, by, bz; bs_key_brick(keys[b], bx, by, bz);
+    bx += a == 0; by += a == 1; bz += a == 2;
+    if (bx > BS_BRICK_MAX || by > BS_BRICK_MAX || bz > BS_BRICK_MAX) return;
+    const long long nb = sp_find_key(keys, n, bs_brick_key(bx, by, bz));
     if (nb < 0) return;
-    const unsigned op = ax == 0 ? ((7u << 6) | (u << 3) | v) : (ax == 1 ? ((u << 6) | (7u << 3) | v) : ((u << 6) | (v << 3) | 7u));
-    const unsigned oq = ax == 0 ? ((u << 3) | v) : (ax == 1 ? ((u << 6) | v) : ((u << 6) | (v << 3)));
-    const bool ap = (masks[b * 8 + (op >> 6)] >> (op & 63)) & 1ull, aq = (masks[(size_t)nb * 8 + (oq >> 6)] >> (oq & 63)) & 1ull;
-    bool link = false; unsigned gp = 0, gq = 0, rp = SP_EMPTY, rq = SP_EMPTY;
-    if (ap && aq) {
-        const float cp = fminf(fabsf(values[b * 512 + op]), vs), cq = fminf(fabsf(values[(size_t)nb * 512 + oq]), vs);
-        link = cp + cq > thr;
-        gp = (unsigned)(b * 512 + op); gq = (unsigned)((size_t)nb * 512 + oq);
-        if (link) { rp = __ldcg(par + gp); rq = __ldcg(par + gq); }  // brick-level roots (or already something above them)
+    const u64 L = face[b * 9 + 2 * a + 1] & face[(size_t)nb * 9 + 2 * a] & ~face[b * 9 + 6 + a];
+    if (L == 0) return;
+    const unsigned nn = ncomp[nb];
+    for (unsigned k = 0; k < nc; ++k) {
+        const u64 pk = planes[(b * SP_K + k) * 6 + 2 * a + 1] & L;
+        if (pk == 0) continue;
+        for (unsigned j = 0; j < nn; ++j)
+            if (pk & planes[((size_t)nb * SP_K + j) * 6 + 2 * a]) sp_union_g(par, (unsigned)(b * SP_K + k), (unsigned)((size_t)nb * SP_K + j));
     }
+}
+// 8 lanes per brick, lane k = component k: flatten (read-only finds: a halving write by another thread could land after
+// this thread's own store and leave a non-root behind) and build the mask of the voxels to evaluate: the leftover voxels
+// plus the first voxel of every component that is its class's root.
+__global__ void __launch_bounds__(256) k_sp_flatten(size_t n, unsigned* par, const unsigned char* __restrict__ ncomp, const unsigned short* __restrict__ first,
+                                                    const u64* __restrict__ rest, u64* seed_masks, unsigned* n_chunks, int per_chunk, u64* n_seeds) {
+    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t b = t >> 3;
+    const unsigned k = (unsigned)(t & 7), gl = (threadIdx.x & 31) & ~7u, gmask = 0xFFu << gl;
+    if (b >= n) return;
+    const unsigned id = (unsigned)(b * SP_K + k);
+    bool root = false; unsigned off = 0;
+    if (k < ncomp[b]) {
+        unsigned r = id, p; volatile unsigned* vp = par;
+        while ((p = vp[r]) != r) r = p;
+        par[id] = r;
+        root = r == id; off = first[id];
+    }
+    u64 word = rest[b * 8 + k];  // lane k doubles as the owner of word k
+#pragma unroll
+    for (int j = 0; j < SP_K; ++j) {
+        const unsigned oj = __shfl_sync(gmask, root ? off : 0xFFFFu, gl + j);
+        if (oj != 0xFFFFu && (oj >> 6) == k) word |= 1ull << (oj & 63);
+    }
+    seed_masks[b * 8 + k] = word;
+    unsigned c = (unsigned)__popcll(word);
+    c += __shfl_xor_sync(gmask, c, 1); c += __shfl_xor_sync(gmask, c, 2); c += __shfl_xor_sync(gmask, c, 4);
+    if (k == 0) { n_chunks[b] = (c + per_chunk - 1) / per_chunk; if (c) atomicAdd(n_seeds, (u64)c); }
+}
+
+// ---- (3) few representatives: brute force ---------------------------------------------------------------------------------
+constexpr int SP_BRUTE_MAX = 64;
+__global__ void k_sp_collect(const u64* __restrict__ seed_masks, size_t n_words, unsigned* list /*voxel ids brick*512+off*/, unsigned* count, unsigned cap) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n_words) return;
+    u64 m = seed_masks[i];
+    while (m) {
+        const int bit = __ffsll((long long)m) - 1; m &= m - 1;
+        const unsigned slot = atomicAdd(count, 1u);
+        if (slot < cap) list[slot] = (unsigned)(i * 64 + bit);
+    }
+}
+// solid_angle (aabb_tree.rs:582-615) of every triangle seen from each listed voxel, summed in double
+__global__ void __launch_bounds__(256) k_sp_brute(const float* __restrict__ tris, size_t n_tris, const unsigned* __restrict__ list, unsigned n_list,
+                                                  const u64* __restrict__ keys, float vs, double* wn /*[n_list]*/) {
+    __shared__ float s_q[SP_BRUTE_MAX][3];
+    __shared__ double s_acc[SP_BRUTE_MAX];
+    for (unsigned i = threadIdx.x; i < n_list; i += blockDim.x) {
+        const unsigned g = list[i], off = g & 511;
+        int bx, by, bz; bs_key_brick(keys[g >> 9], bx, by, bz);
+        s_q[i][0] = __fmul_rn((float)((bx << 3) + (int)(off >> 6)), vs);
+        s_q[i][1] = __fmul_rn((float)((by << 3) + (int)((off >> 3) & 7)), vs);
+        s_q[i][2] = __fmul_rn((float)((bz << 3) + (int)(off & 7)), vs);
+        s_acc[i] = 0.0;
+    }
+    __syncthreads();
+    for (unsigned base = 0; base < n_list; base += 8) {
+        double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const unsigned m = min(8u, n_list - base);
+        for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n_tris; t += (size_t)gridDim.x * blockDim.x) {
+            const float* p = tris + 9 * t;
+            const float v[9] = {p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[8]};
+#pragma unroll
+            for (unsigned i = 0; i < 8; ++i) {
+                if (i >= m) break;
+                const float qx = s_q[base + i][0], qy = s_q[base + i][1], qz = s_q[base + i][2];
+                const float ax = v[0] - qx, ay = v[1] - qy, az = v[2] - qz, bx = v[3] - qx, by = v[4] - qy, bz = v[5] - qz, cx = v[6] - qx, cy = v[7] - qy, cz = v[8] - qz;
+                const float la = sqrtf(ax * ax + ay * ay + az * az), lb = sqrtf(bx * bx + by * by + bz * bz), lc = sqrtf(cx * cx + cy * cy + cz * cz);
+                if (la == 0.f || lb == 0.f || lc == 0.f) continue;
+                const float det = ax * (by * cz - bz * cy) + ay * (bz * cx - bx * cz) + az * (bx * cy - by * cx);
+                if (det == 0.f) continue;
+                const float den = la * lb * lc + (ax * bx + ay * by + az * bz) * lc + (ax * cx + ay * cy + az * cz) * lb + (bx * cx + by * cy + bz * cz) * la;
+                acc[i] += (double)atan2f(det, den);
+            }
+        }
+        for (unsigned i = 0; i < m; ++i) {
+            double a = acc[i];
+            for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xFFFFFFFFu, a, o);
+            if ((threadIdx.x & 31) == 0) atomicAdd(&s_acc[base + i], a);
+        }
+    }
+    __syncthreads();
+    for (unsigned i = threadIdx.x; i < n_list; i += blockDim.x) atomicAdd(wn + i, s_acc[i] * (2.0 / 12.566370614359172));
+}
+__global__ void k_sp_brute_apply(float* values, const unsigned* __restrict__ list, unsigned n_list, const double* __restrict__ wn) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_list) return;
+    const float d = values[list[i]];
+    values[list[i]] = ((float)wn[i] < 0.2f) ? copysignf(d, 1.0f) : copysignf(d, -1.0f);  // mesh_to_volume.rs:266-271
+}
+
+// ---- (4) every voxel of a component takes the sign its class's representative got -----------------------------------------
+// one warp per brick
+__global__ void __launch_bounds__(256) k_sp_broadcast(float* values, size_t n, const u64* __restrict__ comp, const unsigned char* __restrict__ ncomp,
+                                                      const unsigned short* __restrict__ first, const unsigned* __restrict__ par) {
+    const size_t b = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
     const unsigned lane = threadIdx.x & 31;
-    const unsigned prp = __shfl_up_sync(0xFFFFFFFFu, rp, 1), prq = __shfl_up_sync(0xFFFFFFFFu, rq, 1);
-    if (link && !(lane > 0 && prp == rp && prq == rq)) sp_union_g(par, gp, gq);
-}
-// flatten + seed masks: a voxel is its component's representative iff it is its own root
-__global__ void __launch_bounds__(512) k_sp_flatten(unsigned* par, u64* seed_masks, unsigned* n_chunks, int per_chunk, u64* n_seeds) {
-    __shared__ unsigned s_cnt;
-    const size_t b = blockIdx.x;
-    const unsigned t = threadIdx.x;
-    if (t == 0) s_cnt = 0;
-    __syncthreads();
-    const unsigned g = (unsigned)(b * 512 + t);
-    bool seed = false;
-    // read-only find: a path-halving write by another thread could land AFTER this thread's `par[g] = r` and leave g
-    // pointing at an intermediate ancestor (seen at 2048^3: 31 voxels of 36 M took the sign of a non-representative)
-    if (par[g] != SP_EMPTY) { unsigned r = g, p; volatile unsigned* vp = par; while ((p = vp[r]) != r) r = p; par[g] = r; seed = r == g; }
-    const unsigned bal = __ballot_sync(0xFFFFFFFFu, seed);
-    if ((t & 31) == 0) { reinterpret_cast<unsigned*>(seed_masks + b * 8)[t >> 5] = bal; if (bal) atomicAdd(&s_cnt, (unsigned)__popc(bal)); }  // bit t of the brick's 512-bit mask
-    __syncthreads();
-    if (t == 0) { n_chunks[b] = (s_cnt + per_chunk - 1) / per_chunk; if (s_cnt) atomicAdd(n_seeds, (u64)s_cnt); }
-}
-// (4) every non-representative voxel takes the sign its representative got from the traversal
-__global__ void k_sp_broadcast(float* values, const unsigned* __restrict__ par, size_t n_vox) {
-    const size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (g >= n_vox) return;
-    const unsigned r = par[g];
-    if (r == SP_EMPTY || r == (unsigned)g) return;
-    values[g] = copysignf(values[g], __ldcg(values + r));
+    if (b >= n) return;
+    const unsigned nc = ncomp[b];
+    if (nc == 0) return;
+    bool neg = false;
+    if (lane < nc) {
+        const unsigned r = par[b * SP_K + lane];  // flattened: the class's root component
+        neg = (__float_as_uint(__ldcg(values + (size_t)(r / SP_K) * 512 + first[r])) >> 31) != 0;
+    }
+    const unsigned negm = __ballot_sync(0xFFFFFFFFu, neg);
+    u64 ALL = 0, NEG = 0;
+    if (lane < 8)
+        for (unsigned k = 0; k < nc; ++k) { const u64 m = comp[(b * SP_K + k) * 8 + lane]; ALL |= m; if ((negm >> k) & 1u) NEG |= m; }
+    float* bv = values + b * 512;
+#pragma unroll 4
+    for (int r = 0; r < 16; ++r) {
+        const u64 all = __shfl_sync(0xFFFFFFFFu, ALL, r >> 1), ng = __shfl_sync(0xFFFFFFFFu, NEG, r >> 1);
+        const unsigned sh = (r & 1) * 32 + lane;
+        if ((all >> sh) & 1ull) {
+            const float v = bv[r * 32 + lane];
+            bv[r * 32 + lane] = ((ng >> sh) & 1ull) ? -fabsf(v) : fabsf(v);
+        }
+    }
 }
 
 }  // namespace
@@ -275,30 +396,49 @@ bool bs_mesh_closed_finish(bs_context* ctx, bs_closed_check* chk) {
     return chk->closed;
 }
 
-// components of the band voxels of `vol` (values = unsigned distances, masks = active bits): *d_par[g] = representative
-// voxel of g = brick * 512 + offset (0xFFFFFFFF for inactive voxels), *d_seed = masks of the representatives,
-// d_nchunks[b] = work items (of per_chunk representatives) of brick b. *applicable = false (nothing allocated) when the
-// volume is too large for 32-bit voxel ids or the rounding tolerance leaves no certifiable link: the caller keeps the
-// per-voxel path.
-bs_status bs_sign_components_impl(bs_context* ctx, const bs_volume* vol, float tol, unsigned** d_par, unsigned long long** d_seed, unsigned* d_nchunks, int per_chunk, unsigned long long* d_nseeds, bool* applicable) {
+// Components of the band voxels of `vol` (masks = active bits, d_blk = blocked lattice edges from k_block_edges).
+// On return C holds the per-brick component tables, C->seed the masks of the voxels to evaluate, d_nchunks[b] the work
+// items (of per_chunk representatives) of brick b and *d_nseeds their total. C->ok = false (nothing allocated): the
+// volume has too many bricks for 32-bit component ids and the caller keeps the per-voxel path.
+bs_status bs_sign_components_impl(bs_context* ctx, const bs_volume* vol, const unsigned long long* d_blk, bs_sign_components* C, unsigned* d_nchunks, int per_chunk, unsigned long long* d_nseeds) {
     cudaStream_t st = ctx->stream;
     const size_t n = vol->n_bricks;
-    *d_par = nullptr; *d_seed = nullptr; *applicable = false;
-    const float vs = vol->voxel_size;
-    if (n == 0 || n * 512 >= 0xFFFFFFFFull || !(tol >= 0.f) || !(tol < 0.5f * vs)) return BS_OK;
-    const float thr = vs + tol;
-    unsigned* par = nullptr; u64* seed = nullptr;
-    BS_TRY(bs_alloc(ctx, &par, n * 512)); BS_TRY(bs_alloc(ctx, &seed, n * 8));
-    bs_count_launch(), k_sp_bricks<<<(unsigned)n, 512, 0, st>>>(vol->values, vol->masks, vs, thr, par);
-    bs_count_launch(), k_sp_faces<<<(unsigned)n, 192, 0, st>>>(vol->keys, n, vol->values, vol->masks, vs, thr, par);
-    bs_count_launch(), k_sp_flatten<<<(unsigned)n, 512, 0, st>>>(par, seed, d_nchunks, per_chunk, d_nseeds);
+    memset(C, 0, sizeof(*C));
+    if (n == 0 || n * SP_K >= 0xFFFFFFFFull || !d_blk) return BS_OK;
+    BS_TRY(bs_alloc(ctx, &C->comp, n * SP_K * 8)); BS_TRY(bs_alloc(ctx, &C->planes, n * SP_K * 6)); BS_TRY(bs_alloc(ctx, &C->face, n * 9));
+    BS_TRY(bs_alloc(ctx, &C->rest, n * 8)); BS_TRY(bs_alloc(ctx, &C->ncomp, n)); BS_TRY(bs_alloc(ctx, &C->first, n * SP_K));
+    BS_TRY(bs_alloc(ctx, &C->par, n * SP_K)); BS_TRY(bs_alloc(ctx, &C->seed, n * 8));
+    bs_count_launch(), k_sp_bricks<<<bs_blocks(n * 8, 256), 256, 0, st>>>(vol->masks, d_blk, n, C->comp, C->planes, C->face, C->rest, C->ncomp, C->first, C->par);
+    bs_count_launch(), k_sp_faces<<<bs_blocks(n * 3, 256), 256, 0, st>>>(vol->keys, n, C->planes, C->face, C->ncomp, C->par);
+    bs_count_launch(), k_sp_flatten<<<bs_blocks(n * 8, 256), 256, 0, st>>>(n, C->par, C->ncomp, C->first, C->rest, C->seed, d_nchunks, per_chunk, d_nseeds);
     BS_CUDA(ctx, cudaGetLastError());
-    *d_par = par; *d_seed = seed; *applicable = true;
+    C->ok = true;
     return BS_OK;
 }
-bs_status bs_sign_broadcast_impl(bs_context* ctx, bs_volume* vol, const unsigned* d_par) {
-    const size_t nv = vol->n_bricks * 512;
-    if (nv) bs_count_launch(), k_sp_broadcast<<<bs_blocks(nv, 256), 256, 0, ctx->stream>>>(vol->values, d_par, nv);
+void bs_sign_components_free(bs_context* ctx, bs_sign_components* C) {
+    bs_free(ctx, C->comp); bs_free(ctx, C->planes); bs_free(ctx, C->face); bs_free(ctx, C->rest); bs_free(ctx, C->ncomp); bs_free(ctx, C->first); bs_free(ctx, C->par); bs_free(ctx, C->seed);
+    memset(C, 0, sizeof(*C));
+}
+int bs_sign_brute_max() { return SP_BRUTE_MAX; }
+// evaluates the (<= SP_BRUTE_MAX) representatives by brute force over all triangles and sets their signs
+bs_status bs_sign_brute_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_volume* vol, const bs_sign_components* C, unsigned n_seeds) {
+    cudaStream_t st = ctx->stream;
+    if (n_seeds == 0) return BS_OK;
+    unsigned *d_list = nullptr, *d_count = nullptr; double* d_wn = nullptr;
+    BS_TRY(bs_alloc(ctx, &d_list, (size_t)SP_BRUTE_MAX)); BS_TRY(bs_alloc(ctx, &d_count, 1)); BS_TRY(bs_alloc(ctx, &d_wn, (size_t)SP_BRUTE_MAX));
+    BS_CUDA(ctx, cudaMemsetAsync(d_count, 0, sizeof(unsigned), st));
+    BS_CUDA(ctx, cudaMemsetAsync(d_wn, 0, SP_BRUTE_MAX * sizeof(double), st));
+    bs_count_launch(), k_sp_collect<<<bs_blocks(vol->n_bricks * 8, 256), 256, 0, st>>>(C->seed, vol->n_bricks * 8, d_list, d_count, (unsigned)SP_BRUTE_MAX);
+    const unsigned grid = (unsigned)std::min<size_t>(bs_blocks(n_tris, 256), (size_t)ctx->sm_count * 8);
+    bs_count_launch(), k_sp_brute<<<grid, 256, 0, st>>>(d_tris, n_tris, d_list, n_seeds, vol->keys, vol->voxel_size, d_wn);
+    bs_count_launch(), k_sp_brute_apply<<<1, SP_BRUTE_MAX, 0, st>>>(vol->values, d_list, n_seeds, d_wn);
+    bs_free(ctx, d_list); bs_free(ctx, d_count); bs_free(ctx, d_wn);
+    BS_CUDA(ctx, cudaGetLastError());
+    return BS_OK;
+}
+bs_status bs_sign_broadcast_impl(bs_context* ctx, bs_volume* vol, const bs_sign_components* C) {
+    const size_t n = vol->n_bricks;
+    if (n) bs_count_launch(), k_sp_broadcast<<<bs_blocks(n * 32, 256), 256, 0, ctx->stream>>>(vol->values, n, C->comp, C->ncomp, C->first, C->par);
     BS_CUDA(ctx, cudaGetLastError());
     return BS_OK;
 }

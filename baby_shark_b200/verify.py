@@ -1,7 +1,7 @@
 """Order-sensitive fingerprints of a downloaded volume and of a vertex soup (numpy + hashlib only).
 
 `bench.py` asserts the fingerprints of its own output against `tests/golden/config_hashes.json`, which
-`tests/golden/make_config_hashes.py` wrote from the CPU oracle at the same size: a benchmark whose result is not the
+`tests/golden/make_config_hashes.py` wrote from the CPU checker at the same size: a benchmark whose result is not the
 reference's result is not a result."""
 import hashlib
 

@@ -23,7 +23,7 @@ def active_values(d):
 
 
 @pytest.mark.parametrize("cfg,scale", [(5, 0.05), (3, 0.06), (4, 0.08), (5, 0.125)])
-def test_propagated_signs_equal_per_voxel_signs_and_the_oracle(bs, oracle, cfg, scale):
+def test_propagated_signs_equal_per_voxel_signs_and_the_oracle(bs, oracle, cfg, scale, monkeypatch):
     from baby_shark_b200 import synth
     tris, vs, _ = synth.config_mesh(cfg, scale)
     a, st_a = convert(bs, tris, vs, prop=False)
@@ -32,10 +32,16 @@ def test_propagated_signs_equal_per_voxel_signs_and_the_oracle(bs, oracle, cfg, 
     da, db = a.download(), b.download()
     assert np.array_equal(da["masks"], db["masks"])
     assert np.array_equal(active_values(da).view(np.uint32), active_values(db).view(np.uint32))
-    # only a fraction of the band is traversed
-    assert st_b["n_sign_seeds"] < 0.25 * st_b["n_active"], st_b
+    # only a handful of voxels is evaluated: the shells' representatives and voxels on the surface within rounding
+    assert st_b["n_sign_seeds"] < 1e-3 * st_b["n_active"] + 8, st_b
+    assert st_b["sign_brute_force"] == 1.0
     o, _ = oracle.mesh_to_volume(tris, vs, 0, threads=8)
     compare_volumes(db, o.download(), vs)
+    # the same representatives through the LBVH traversal instead of the brute-force sum
+    monkeypatch.setenv("BSHARK_NO_BRUTE", "1")
+    c, st_c = convert(bs, tris, vs, prop=True)
+    assert st_c["sign_propagation"] == 1.0 and st_c["sign_brute_force"] == 0.0
+    assert np.array_equal(active_values(c.download()).view(np.uint32), active_values(db).view(np.uint32))
 
 
 def test_tori_and_bands(bs, oracle):
