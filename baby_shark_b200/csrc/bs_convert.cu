@@ -52,14 +52,9 @@ __device__ __forceinline__ float num_subs_of(f3 p1, f3 p2, f3 p3, float vs) {
     return floorf(xdiv(xsqrt(m), vs));
 }
 
-// also: sp_tol = max over triangles of the f32 rounding tolerance of the sign-propagation link certificate
-// (bs_signprop.cu): 2 x the drift of a sub-triangle vertex built from <= n + 1 running-sum additions
-// (1.74 (n + 13) 2^-24 max|coord|, only when the triangle is subdivided) + 32 x 2^-24 max|coord| for the lattice
-// positions, box roundings and the distance evaluation itself
-__global__ void k_tri_counts(const float* __restrict__ tris, size_t n_tris, float vs, unsigned long long* counts, double* area_vox, unsigned* sp_tol_bits) {
+__global__ void k_tri_counts(const float* __restrict__ tris, size_t n_tris, float vs, unsigned long long* counts, double* area_vox) {
     size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     double a = 0.0;
-    float tol = 0.f;
     if (t < n_tris) {
         const float* p = tris + 9 * t;
         f3 p1 = ld3(p), p2 = ld3(p + 3), p3 = ld3(p + 6);
@@ -67,12 +62,6 @@ __global__ void k_tri_counts(const float* __restrict__ tris, size_t n_tris, floa
         unsigned long long c;
         if (n < 2.0f) c = 1; else if (n != n) c = 0; else { double nd = fmin((double)n, 4.0e9); c = (unsigned long long)(nd * nd); }
         counts[t] = c;
-        float ma = 0.f;
-        for (int i = 0; i < 9; ++i) ma = fmaxf(ma, fabsf(p[i]));
-        const float u = 5.9604645e-8f * ma;  // 2^-24 max|coord|
-        tol = 32.0f * u + (n >= 2.0f ? 2.0f * 1.74f * (n + 13.0f) * u : 0.f);
-        tol *= 1.01f;
-        if (!(tol >= 0.f) || !(tol < 3.0e38f)) tol = 3.0e38f;  // NaN / inf coordinates: no certificate
         f3 cr = xcross(xsub(p2, p1), xsub(p3, p1));
         float ar = 0.5f * sqrtf(xnorm2(cr));
         if (ar == ar && ar < 3.0e38f) a = (double)ar / ((double)vs * (double)vs);
@@ -82,8 +71,6 @@ __global__ void k_tri_counts(const float* __restrict__ tris, size_t n_tris, floa
     __shared__ typename BR::TempStorage tmp;
     double s = BR(tmp).Sum(a);
     if (threadIdx.x == 0 && s != 0.0) atomicAdd(area_vox, s);
-    for (int o = 16; o; o >>= 1) tol = fmaxf(tol, __shfl_xor_sync(0xFFFFFFFFu, tol, o));
-    if ((threadIdx.x & 31) == 0 && tol > 0.f) atomicMax(sp_tol_bits, __float_as_uint(tol));  // non-negative floats order like their bits
 }
 
 // j-th sub-triangle of triangle (p1,p2,p3) in the reference's construction (mesh_to_volume.rs:75-116):
@@ -361,88 +348,114 @@ __global__ void __launch_bounds__(TPB) k_eval(ConvertParams P) {
 // the triangle is projected along a, every lattice column (u, v) inside the projection inflated by eps is intersected
 // with the triangle's plane, and the lattice edges overlapping [z - dz, z + dz] are blocked (dz grows with the slope; a
 // projection thinner than eps -- an edge-on triangle -- blocks its whole extent along a). Lattice positions are the f32
-// products idx * vs every other stage uses, widened exactly to double; vertices are the f32 inputs: the only rounding is
-// fp64 (2^-53), and eps = 64 * 2^-24 * max|coord| + 1e-6 * vs is there for the reference's own f32 winding-number
-// arithmetic, which cannot tell a voxel within a few ulps of the surface from one on it: such voxels lose all six edges
-// and are evaluated on their own.
-constexpr unsigned long long RASTER_SMALL = 256;  // columns a single thread walks; larger projections go to k_block_edges_big
+// products idx * vs every other stage uses, widened exactly to double; vertices are the f32 inputs: the predicate itself
+// only rounds at 2^-53. eps = 16 * 2^-24 * (longest edge) + 2e-6 * vs is there for the REFERENCE's arithmetic: its f32
+// solid angles (aabb_tree.rs:582-615) resolve the side of a triangle only down to a few 2^-24 of the triangle's size, so
+// a voxel that close to the surface loses all six edges and is evaluated on its own, like the reference does.
+constexpr unsigned RASTER_SMALL = 256;  // columns a single thread walks; larger projections go to k_block_edges_big
 __device__ __forceinline__ double lat(int i, float vs) { return (double)__fmul_rn((float)i, vs); }
-struct RasterSetup {
-    double V[3][3];  // vertex k, coordinates (u, v, z) = (axis a+1, a+2, a)
-    double eps, umin, umax, vmin, vmax, zmin, zmax, du[3], dv[3], len[3], s, gu, gv, slope;
-    int iu0, iv0, a, kbig; unsigned long long nu, nv; bool thin, ok;
+struct RasterTri {  // one triangle projected along axis A: coordinates (u, v, z) = (axis A+1, A+2, A)
+    double U0, V0, Z0, U1, V1, Z1, U2, V2, Z2;
+    double eps, umin, umax, vmin, vmax, zlo, zhi;       // zlo / zhi: extent along the axis, already widened by eps
+    double du0, dv0, du1, dv1, du2, dv2, m0, m1, m2;   // edge vectors of the projection, m_k = eps * |edge k|
+    double s, gu, gv, dz, ivs;                          // orientation, plane gradient, half-width of the z interval, 1 / vs
+    double lu, lv, lm, lU, lV;                          // thin projections: direction, margin and start of the longest edge
+    int iu0, iv0, nu, nv; bool thin, ok;
 };
-__device__ __forceinline__ void raster_setup(const ConvertParams& P, size_t t, int a, RasterSetup& R) {
+template <int A> __device__ __forceinline__ void raster_setup(const ConvertParams& P, size_t t, RasterTri& R) {
     const float* p = P.tris + 9 * t;
-    const int ua = (a + 1) % 3, va = (a + 2) % 3;
-    double ma = 0.0; bool finite = true;
-    for (int k = 0; k < 3; ++k) {
-        R.V[k][0] = (double)p[3 * k + ua]; R.V[k][1] = (double)p[3 * k + va]; R.V[k][2] = (double)p[3 * k + a];
-        for (int c = 0; c < 3; ++c) { const double f = fabs((double)p[3 * k + c]); ma = fmax(ma, f); if (!(f < 1.0e30)) finite = false; }
-    }
-    R.a = a; R.ok = finite;
-    if (!finite) { R.nu = R.nv = 0; return; }
-    R.eps = 64.0 * 5.9604644775390625e-8 * ma + 1.0e-6 * (double)P.vs;
-    R.umin = fmin(R.V[0][0], fmin(R.V[1][0], R.V[2][0])); R.umax = fmax(R.V[0][0], fmax(R.V[1][0], R.V[2][0]));
-    R.vmin = fmin(R.V[0][1], fmin(R.V[1][1], R.V[2][1])); R.vmax = fmax(R.V[0][1], fmax(R.V[1][1], R.V[2][1]));
-    R.zmin = fmin(R.V[0][2], fmin(R.V[1][2], R.V[2][2])); R.zmax = fmax(R.V[0][2], fmax(R.V[1][2], R.V[2][2]));
-    const double ivs = 1.0 / (double)P.vs, lim = 1048576.0;
-    const double fu0 = floor((R.umin - R.eps) * ivs) - 1.0, fu1 = ceil((R.umax + R.eps) * ivs) + 1.0;
-    const double fv0 = floor((R.vmin - R.eps) * ivs) - 1.0, fv1 = ceil((R.vmax + R.eps) * ivs) + 1.0;
-    if (!(fu0 > -lim && fu1 < lim && fv0 > -lim && fv1 < lim)) { R.ok = false; R.nu = R.nv = 0; return; }  // outside the supported index range: k_mark reports it
-    R.iu0 = (int)fu0; R.iv0 = (int)fv0; R.nu = (unsigned long long)(fu1 - fu0) + 1; R.nv = (unsigned long long)(fv1 - fv0) + 1;
-    double lmax = -1.0; R.kbig = 0;
-    for (int k = 0; k < 3; ++k) {
-        const int b = (k + 1) % 3;
-        R.du[k] = R.V[b][0] - R.V[k][0]; R.dv[k] = R.V[b][1] - R.V[k][1];
-        R.len[k] = sqrt(R.du[k] * R.du[k] + R.dv[k] * R.dv[k]);
-        if (R.len[k] > lmax) { lmax = R.len[k]; R.kbig = k; }
-    }
-    // (u, v, z) components of e1 x e2
-    const double e1u = R.V[1][0] - R.V[0][0], e1v = R.V[1][1] - R.V[0][1], e1z = R.V[1][2] - R.V[0][2];
-    const double e2u = R.V[2][0] - R.V[0][0], e2v = R.V[2][1] - R.V[0][1], e2z = R.V[2][2] - R.V[0][2];
-    const double nu_ = e1v * e2z - e1z * e2v, nv_ = e1z * e2u - e1u * e2z, nz_ = e1u * e2v - e1v * e2u;
-    R.thin = !(fabs(nz_) > R.eps * (R.len[0] + R.len[1] + R.len[2]));  // projected height below ~eps (or NaN): edge-on
+    constexpr int UA = (A + 1) % 3, VA = (A + 2) % 3;
+    R.U0 = (double)p[UA]; R.V0 = (double)p[VA]; R.Z0 = (double)p[A];
+    R.U1 = (double)p[3 + UA]; R.V1 = (double)p[3 + VA]; R.Z1 = (double)p[3 + A];
+    R.U2 = (double)p[6 + UA]; R.V2 = (double)p[6 + VA]; R.Z2 = (double)p[6 + A];
+    const double e1u = R.U1 - R.U0, e1v = R.V1 - R.V0, e1z = R.Z1 - R.Z0, e2u = R.U2 - R.U0, e2v = R.V2 - R.V0, e2z = R.Z2 - R.Z0;
+    const double e3u = R.U2 - R.U1, e3v = R.V2 - R.V1, e3z = R.Z2 - R.Z1;
+    const double l2 = fmax(e1u * e1u + e1v * e1v + e1z * e1z, fmax(e2u * e2u + e2v * e2v + e2z * e2z, e3u * e3u + e3v * e3v + e3z * e3z));
+    R.ok = l2 < 1.0e60;  // finite
+    R.nu = R.nv = 0;
+    if (!R.ok) return;
+    R.ivs = 1.0 / (double)P.vs;
+    R.eps = 16.0 * 5.9604644775390625e-8 * ((double)sqrtf((float)l2) * 1.0001 + 1.0e-300) + 2.0e-6 * (double)P.vs;
+    R.umin = fmin(R.U0, fmin(R.U1, R.U2)); R.umax = fmax(R.U0, fmax(R.U1, R.U2));
+    R.vmin = fmin(R.V0, fmin(R.V1, R.V2)); R.vmax = fmax(R.V0, fmax(R.V1, R.V2));
+    R.zlo = fmin(R.Z0, fmin(R.Z1, R.Z2)) - R.eps; R.zhi = fmax(R.Z0, fmax(R.Z1, R.Z2)) + R.eps;
+    const double lim = 1048576.0;
+    const double fu0 = floor((R.umin - R.eps) * R.ivs) - 1.0, fu1 = ceil((R.umax + R.eps) * R.ivs) + 1.0;
+    const double fv0 = floor((R.vmin - R.eps) * R.ivs) - 1.0, fv1 = ceil((R.vmax + R.eps) * R.ivs) + 1.0;
+    if (!(fu0 > -lim && fu1 < lim && fv0 > -lim && fv1 < lim)) { R.ok = false; return; }  // outside the index range: k_mark reports it
+    R.iu0 = (int)fu0; R.iv0 = (int)fv0; R.nu = (int)(fu1 - fu0) + 1; R.nv = (int)(fv1 - fv0) + 1;
+    R.du0 = e1u; R.dv0 = e1v; R.du1 = e3u; R.dv1 = e3v; R.du2 = -e2u; R.dv2 = -e2v;
+    const double len0 = (double)sqrtf((float)(e1u * e1u + e1v * e1v)) * 1.0001, len1 = (double)sqrtf((float)(e3u * e3u + e3v * e3v)) * 1.0001, len2 = (double)sqrtf((float)(e2u * e2u + e2v * e2v)) * 1.0001;
+    R.m0 = R.eps * len0; R.m1 = R.eps * len1; R.m2 = R.eps * len2;
+    const double nu_ = e1v * e2z - e1z * e2v, nv_ = e1z * e2u - e1u * e2z, nz_ = e1u * e2v - e1v * e2u;  // (u, v, z) components of e1 x e2
+    R.thin = !(fabs(nz_) > R.eps * (len0 + len1 + len2));  // projected height below ~eps (or NaN): edge-on
     R.s = nz_ >= 0.0 ? 1.0 : -1.0;
-    if (!R.thin) { R.gu = -nu_ / nz_; R.gv = -nv_ / nz_; R.slope = fabs(R.gu) + fabs(R.gv); } else { R.gu = R.gv = R.slope = 0.0; }
+    if (!R.thin) {
+        const double inz = 1.0 / nz_;
+        R.gu = -nu_ * inz; R.gv = -nv_ * inz; R.dz = R.eps * (2.0 + fabs(R.gu) + fabs(R.gv));
+    } else {  // the projection is (within eps) the segment of its longest edge
+        R.gu = R.gv = R.dz = 0.0;
+        if (len0 >= len1 && len0 >= len2) { R.lu = R.du0; R.lv = R.dv0; R.lm = 3.0 * R.m0; R.lU = R.U0; R.lV = R.V0; }
+        else if (len1 >= len2) { R.lu = R.du1; R.lv = R.dv1; R.lm = 3.0 * R.m1; R.lU = R.U1; R.lV = R.V1; }
+        else { R.lu = R.du2; R.lv = R.dv2; R.lm = 3.0 * R.m2; R.lU = R.U2; R.lV = R.V2; }
+    }
 }
-__device__ __forceinline__ void raster_block(const ConvertParams& P, unsigned long long* blk, int a, int iu, int iv, int k, unsigned long long& last_key, unsigned& last_slot) {
+template <int A> __device__ __forceinline__ void raster_block(const ConvertParams& P, unsigned long long* blk, int iu, int iv, int k, unsigned long long& last_key, unsigned& last_slot) {
     int x, y, z;
-    if (a == 0) { x = k; y = iu; z = iv; } else if (a == 1) { y = k; z = iu; x = iv; } else { z = k; x = iu; y = iv; }
+    if (A == 0) { x = k; y = iu; z = iv; } else if (A == 1) { y = k; z = iu; x = iv; } else { z = k; x = iu; y = iv; }
     const int bx = x >> 3, by = y >> 3, bz = z >> 3;
     if (bx < BS_BRICK_MIN || bx > BS_BRICK_MAX || by < BS_BRICK_MIN || by > BS_BRICK_MAX || bz < BS_BRICK_MIN || bz > BS_BRICK_MAX) return;
     const unsigned long long key = bs_brick_key(bx, by, bz);
     if (key != last_key) { last_key = key; last_slot = hash_lookup(P, key); }
     if (last_slot == 0xFFFFFFFFu) return;  // no such brick (or not kept on this rank): the edge has no active lower end
-    atomicOr(blk + (size_t)last_slot * 24 + a * 8 + (x & 7), 1ull << (((y & 7) << 3) | (z & 7)));
+    atomicOr(blk + (size_t)last_slot * 24 + A * 8 + (x & 7), 1ull << (((y & 7) << 3) | (z & 7)));
 }
-__device__ __forceinline__ void raster_column(const ConvertParams& P, unsigned long long* blk, const RasterSetup& R, unsigned long long c, unsigned long long& last_key, unsigned& last_slot) {
-    const int iu = R.iu0 + (int)(c / R.nv), iv = R.iv0 + (int)(c % R.nv);
-    const double pu = lat(iu, P.vs), pv = lat(iv, P.vs);
-    if (pu < R.umin - R.eps || pu > R.umax + R.eps || pv < R.vmin - R.eps || pv > R.vmax + R.eps) return;
-    double lo = R.zmin - R.eps, hi = R.zmax + R.eps;
+template <int A> __device__ __forceinline__ void raster_column(const ConvertParams& P, unsigned long long* blk, const RasterTri& R, int iu, int iv, double pu, unsigned long long& last_key, unsigned& last_slot) {
+    const double pv = lat(iv, P.vs);
+    if (pv < R.vmin - R.eps || pv > R.vmax + R.eps) return;
+    double lo = R.zlo, hi = R.zhi;
     if (!R.thin) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const double E = R.du[k] * (pv - R.V[k][1]) - R.dv[k] * (pu - R.V[k][0]);
-            if (R.s * E < -R.eps * R.len[k]) return;  // outside the projection inflated by eps
-        }
-        const double zc = R.V[0][2] + R.gu * (pu - R.V[0][0]) + R.gv * (pv - R.V[0][1]);
-        const double dz = R.eps * (2.0 + R.slope);
-        if (zc - dz > lo) lo = zc - dz;
-        if (zc + dz < hi) hi = zc + dz;
-        if (!(lo <= hi)) { lo = R.zmin - R.eps; hi = R.zmax + R.eps; }  // numerically impossible; stay conservative
-    } else {
-        const int k = R.kbig;  // the projection is (within eps) the segment of its longest edge
-        const double E = R.du[k] * (pv - R.V[k][1]) - R.dv[k] * (pu - R.V[k][0]);
-        if (fabs(E) > 3.0 * R.eps * R.len[k] && R.len[k] > 0.0) return;
-    }
-    const double ivs = 1.0 / (double)P.vs;
-    const int k0 = (int)floor(lo * ivs) - 1, k1 = (int)floor(hi * ivs) + 1;
+        if (R.s * (R.du0 * (pv - R.V0) - R.dv0 * (pu - R.U0)) < -R.m0) return;  // outside the projection inflated by eps
+        if (R.s * (R.du1 * (pv - R.V1) - R.dv1 * (pu - R.U1)) < -R.m1) return;
+        if (R.s * (R.du2 * (pv - R.V2) - R.dv2 * (pu - R.U2)) < -R.m2) return;
+        const double zc = R.Z0 + R.gu * (pu - R.U0) + R.gv * (pv - R.V0);
+        const double a = fmax(lo, zc - R.dz), b = fmin(hi, zc + R.dz);
+        if (a <= b) { lo = a; hi = b; }  // (else: numerically impossible; stay with the full extent)
+    } else if (fabs(R.lu * (pv - R.lV) - R.lv * (pu - R.lU)) > R.lm) return;
+    const int k0 = (int)floor(lo * R.ivs) - 1, k1 = (int)floor(hi * R.ivs) + 1;
     for (int k = k0; k <= k1; ++k)
-        if (lat(k + 1, P.vs) >= lo && lat(k, P.vs) <= hi) raster_block(P, blk, R.a, iu, iv, k, last_key, last_slot);
+        if (lat(k + 1, P.vs) >= lo && lat(k, P.vs) <= hi) raster_block<A>(P, blk, iu, iv, k, last_key, last_slot);
 }
-__global__ void __launch_bounds__(256) k_block_edges(ConvertParams P, unsigned long long* blk, unsigned long long* big_list, unsigned* n_big, unsigned big_cap) {
+template <int A> __device__ __forceinline__ void raster_small(const ConvertParams& P, unsigned long long* blk, size_t t, unsigned long long g, unsigned long long* big_list, unsigned* n_big, unsigned big_cap) {
+    RasterTri R;
+    raster_setup<A>(P, t, R);
+    if (!R.ok) return;  // non-finite input never passes the closedness test; out-of-range indices were reported by k_mark
+    if ((unsigned long long)R.nu * (unsigned long long)R.nv > RASTER_SMALL) {
+        const unsigned i = atomicAdd(n_big, 1u);
+        if (i < big_cap) { big_list[i] = g; return; }  // (a full list: this thread walks the columns itself)
+    }
+    unsigned long long last_key = BS_KEY_INVALID; unsigned last_slot = 0xFFFFFFFFu;
+    for (int i = 0; i < R.nu; ++i) {
+        const int iu = R.iu0 + i;
+        const double pu = lat(iu, P.vs);
+        if (pu < R.umin - R.eps || pu > R.umax + R.eps) continue;
+        for (int j = 0; j < R.nv; ++j) raster_column<A>(P, blk, R, iu, R.iv0 + j, pu, last_key, last_slot);
+    }
+}
+template <int A> __device__ __forceinline__ void raster_big(const ConvertParams& P, unsigned long long* blk, size_t t) {
+    RasterTri R;
+    raster_setup<A>(P, t, R);
+    if (!R.ok) return;
+    const unsigned long long ncols = (unsigned long long)R.nu * (unsigned long long)R.nv;
+    unsigned long long last_key = BS_KEY_INVALID; unsigned last_slot = 0xFFFFFFFFu;
+    for (unsigned long long c = threadIdx.x; c < ncols; c += blockDim.x) {
+        const int iu = R.iu0 + (int)(c / (unsigned)R.nv), iv = R.iv0 + (int)(c % (unsigned)R.nv);
+        const double pu = lat(iu, P.vs);
+        if (pu < R.umin - R.eps || pu > R.umax + R.eps) continue;
+        raster_column<A>(P, blk, R, iu, iv, pu, last_key, last_slot);
+    }
+}
+__global__ void __launch_bounds__(128, 3) k_block_edges(ConvertParams P, unsigned long long* blk, unsigned long long* big_list, unsigned* n_big, unsigned big_cap) {
     const size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (g >= P.n_tris * 3) return;
     const size_t t = g / 3; const int a = (int)(g % 3);
@@ -453,28 +466,17 @@ __global__ void __launch_bounds__(256) k_block_edges(ConvertParams P, unsigned l
             if (ceilf(hi * P.inv_vs) + 3.0f < (float)P.clip_mn[d] || floorf(lo * P.inv_vs) - 3.0f > (float)P.clip_mx[d]) return;
         }
     }
-    RasterSetup R;
-    raster_setup(P, t, a, R);
-    if (!R.ok) return;  // non-finite input never passes the closedness test; out-of-range indices were reported by k_mark
-    const unsigned long long ncols = R.nu * R.nv;
-    if (ncols > RASTER_SMALL) {
-        const unsigned i = atomicAdd(n_big, 1u);
-        if (i < big_cap) { big_list[i] = (unsigned long long)g; return; }  // (a full list: this thread walks the columns itself)
-    }
-    unsigned long long last_key = BS_KEY_INVALID; unsigned last_slot = 0xFFFFFFFFu;
-    for (unsigned long long c = 0; c < ncols; ++c) raster_column(P, blk, R, c, last_key, last_slot);
+    if (a == 0) raster_small<0>(P, blk, t, g, big_list, n_big, big_cap);
+    else if (a == 1) raster_small<1>(P, blk, t, g, big_list, n_big, big_cap);
+    else raster_small<2>(P, blk, t, g, big_list, n_big, big_cap);
 }
 // projections of more than RASTER_SMALL columns: one CTA per (triangle, axis), threads stride over the columns
 __global__ void __launch_bounds__(256) k_block_edges_big(ConvertParams P, unsigned long long* blk, const unsigned long long* big_list, const unsigned* n_big, unsigned big_cap) {
     const unsigned n = min(*n_big, big_cap);
     for (unsigned i = blockIdx.x; i < n; i += gridDim.x) {
         const unsigned long long g = big_list[i];
-        RasterSetup R;
-        raster_setup(P, (size_t)(g / 3), (int)(g % 3), R);
-        if (!R.ok) continue;
-        const unsigned long long ncols = R.nu * R.nv;
-        unsigned long long last_key = BS_KEY_INVALID; unsigned last_slot = 0xFFFFFFFFu;
-        for (unsigned long long c = threadIdx.x; c < ncols; c += blockDim.x) raster_column(P, blk, R, c, last_key, last_slot);
+        const size_t t = (size_t)(g / 3); const int a = (int)(g % 3);
+        if (a == 0) raster_big<0>(P, blk, t); else if (a == 1) raster_big<1>(P, blk, t); else raster_big<2>(P, blk, t);
     }
 }
 
@@ -597,17 +599,16 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
     unsigned long long *d_counts = nullptr, *d_offsets = nullptr; double* d_area = nullptr; int* d_flags = nullptr;
     BS_TRY(bs_alloc(ctx, &d_counts, n_tris + 1)); BS_TRY(bs_alloc(ctx, &d_offsets, n_tris + 1));
     BS_TRY(bs_alloc(ctx, &d_area, 1)); BS_TRY(bs_alloc(ctx, &d_flags, 2));
-    unsigned long long* d_neval = nullptr; unsigned* d_tol = nullptr;
-    BS_TRY(bs_alloc(ctx, &d_neval, 1)); BS_TRY(bs_alloc(ctx, &d_tol, 1));
+    unsigned long long* d_neval = nullptr;
+    BS_TRY(bs_alloc(ctx, &d_neval, 1));
     BS_CUDA(ctx, cudaMemsetAsync(d_area, 0, sizeof(double), st));
     BS_CUDA(ctx, cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), st));
-    BS_CUDA(ctx, cudaMemsetAsync(d_tol, 0, sizeof(unsigned), st));
     BS_CUDA(ctx, cudaMemsetAsync(d_counts + n_tris, 0, sizeof(unsigned long long), st));
     // closed mesh? (bs_signprop.cu) -- enqueued here, read at the synchronisation below
     bs_closed_check chk; chk.pending = false; chk.closed = false; chk.exact = false; chk.d_sums = nullptr; chk.d_bad = nullptr;
     ctx->mesh_closed = false;
     if (ctx->sign_propagation) BS_TRY(bs_mesh_closed_begin(ctx, d_tris, n_tris, &chk));
-    bs_count_launch(), k_tri_counts<<<bs_blocks(n_tris, TPB), TPB, 0, st>>>(d_tris, n_tris, voxel_size, d_counts, d_area, d_tol);
+    bs_count_launch(), k_tri_counts<<<bs_blocks(n_tris, TPB), TPB, 0, st>>>(d_tris, n_tris, voxel_size, d_counts, d_area);
     void* d_tmp = nullptr; size_t tmp_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_counts, d_offsets, n_tris + 1, st);
     BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp_bytes));
@@ -615,12 +616,9 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
     unsigned long long total = 0; double area_vox = 0.0;
     BS_CUDA(ctx, cudaMemcpyAsync(&total, d_offsets + n_tris, sizeof(total), cudaMemcpyDeviceToHost, st));
     BS_CUDA(ctx, cudaMemcpyAsync(&area_vox, d_area, sizeof(double), cudaMemcpyDeviceToHost, st));
-    unsigned tol_bits = 0;
-    BS_CUDA(ctx, cudaMemcpyAsync(&tol_bits, d_tol, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     BS_CUDA(ctx, cudaStreamSynchronize(st));
     ctx->mesh_closed = ctx->sign_propagation && bs_mesh_closed_finish(ctx, &chk);
-    (void)tol_bits;
-    bs_free(ctx, d_tmp); bs_free(ctx, d_counts); bs_free(ctx, d_area); bs_free(ctx, d_tol);
+    bs_free(ctx, d_tmp); bs_free(ctx, d_counts); bs_free(ctx, d_area);
     bs_mark(ctx, "subdivide_count_ms");
     if (total == 0) { bs_free(ctx, d_offsets); bs_free(ctx, d_flags); bs_free(ctx, d_neval); bs_marks_end(ctx); return BS_ERR_EMPTY_MESH; }  // convert -> None (:58-60)
     if (total > (1ull << 40)) { bs_free(ctx, d_offsets); bs_free(ctx, d_flags); bs_free(ctx, d_neval); return bs_fail(ctx, BS_ERR_RANGE, "%llu sub-triangles: voxel size too small for this mesh", total); }
@@ -758,7 +756,7 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
         BS_TRY(bs_alloc(ctx, &d_blk, n_all * 24)); BS_TRY(bs_alloc(ctx, &d_big, (size_t)big_cap)); BS_TRY(bs_alloc(ctx, &d_nbig, 1));
         BS_CUDA(ctx, cudaMemsetAsync(d_blk, 0, n_all * 24 * sizeof(unsigned long long), st));
         BS_CUDA(ctx, cudaMemsetAsync(d_nbig, 0, sizeof(unsigned), st));
-        bs_count_launch(), k_block_edges<<<bs_blocks(n_tris * 3, TPB), TPB, 0, st>>>(P, d_blk, d_big, d_nbig, big_cap);
+        bs_count_launch(), k_block_edges<<<bs_blocks(n_tris * 3, 128), 128, 0, st>>>(P, d_blk, d_big, d_nbig, big_cap);
         bs_count_launch(), k_block_edges_big<<<(unsigned)ctx->sm_count * 8, TPB, 0, st>>>(P, d_blk, d_big, d_nbig, big_cap);
         bs_free(ctx, d_big); bs_free(ctx, d_nbig);
         bs_mark(ctx, "sign_block_edges_ms");

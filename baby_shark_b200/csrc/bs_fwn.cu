@@ -540,13 +540,14 @@ constexpr int BP_WARPS = 4;
 struct BrickOut { float far[27]; unsigned n_roots; unsigned roots[MAX_ROOTS]; };  // n_roots = 0xFFFFFFFF: no hoisting, start at the tree root
 
 template <bool COUNT>
-__global__ void __launch_bounds__(32 * BP_WARPS) k_brick_pass(Tree T, const unsigned long long* __restrict__ keys, size_t n_bricks, float vs, float KAPPA, BrickOut* out, unsigned long long* counters) {
+__global__ void __launch_bounds__(32 * BP_WARPS) k_brick_pass(Tree T, const unsigned long long* __restrict__ keys, size_t n_bricks, const unsigned* __restrict__ brick_list /*bricks that hold work items*/, float vs, float KAPPA, BrickOut* out, unsigned long long* counters) {
     __shared__ unsigned s_front[BP_WARPS][2][MAX_FRONT];
     __shared__ unsigned s_hoist[BP_WARPS][MAX_HOIST];   // (record id << 2 | entry); the root itself is 0xFFFFFFFF
     __shared__ unsigned s_roots[BP_WARPS][MAX_ROOTS];
     const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5, lt = (1u << lane) - 1;
-    const size_t b = (size_t)blockIdx.x * BP_WARPS + w;
-    if (b >= n_bricks) return;
+    const size_t bi = (size_t)blockIdx.x * BP_WARPS + w;
+    if (bi >= n_bricks) return;
+    const size_t b = brick_list[bi];
     int bx, by, bz; bs_key_brick(keys[b], bx, by, bz);
     const float ox = (float)(bx << 3), oy = (float)(by << 3), oz = (float)(bz << 3);
     const float cx = (ox + 3.5f) * vs, cy = (oy + 3.5f) * vs, cz = (oz + 3.5f) * vs, rho = 6.0621778f * vs, kr = KAPPA * rho;
@@ -665,6 +666,16 @@ __global__ void k_items(const unsigned* __restrict__ order, const unsigned* __re
     const unsigned b = order ? order[i] : (unsigned)i;
     brick_off[b] = off[i];
     for (unsigned k = off[i]; k < off[i + 1]; ++k) item_brick[k] = b;
+}
+// bricks with at least one work item (with sign propagation most bricks have none)
+__global__ void k_item_bricks(const unsigned* __restrict__ n_chunks, size_t n_bricks, unsigned* list, unsigned* count) {
+    const size_t b = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const bool has = b < n_bricks && n_chunks[b] != 0;
+    const unsigned bal = __ballot_sync(0xFFFFFFFFu, has), lane = threadIdx.x & 31;
+    unsigned base = 0;
+    if (lane == 0 && bal) base = atomicAdd(count, (unsigned)__popc(bal));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (has) list[base + __popc(bal & ((1u << lane) - 1))] = (unsigned)b;
 }
 __global__ void k_touch_keys(const unsigned long long* __restrict__ touches, const unsigned long long* __restrict__ total, size_t n, int shift, int buckets, unsigned* key, unsigned* idx) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -999,6 +1010,11 @@ bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_v
             BS_CUDA(ctx, cudaMemcpyAsync(&n_heavy, d_nheavy, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
             bs_free(ctx, d_tmp); bs_free(ctx, d_k); bs_free(ctx, d_k2); bs_free(ctx, d_i); bs_free(ctx, d_nheavy);
         }
+        unsigned *d_blist = nullptr, *d_nblist = nullptr; unsigned n_blist = 0;
+        BS_TRY(bs_alloc(ctx, &d_blist, nb)); BS_TRY(bs_alloc(ctx, &d_nblist, 1));
+        BS_CUDA(ctx, cudaMemsetAsync(d_nblist, 0, sizeof(unsigned), st));
+        bs_count_launch(), k_item_bricks<<<bs_blocks(nb, 256), 256, 0, st>>>(d_nchunks, nb, d_blist, d_nblist);
+        BS_CUDA(ctx, cudaMemcpyAsync(&n_blist, d_nblist, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
         bs_count_launch(), k_order_chunks<<<bs_blocks(nb + 1, 256), 256, 0, st>>>(d_order, d_nchunks, nb, d_ordered);
         tmp_bytes = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_ordered, d_off, nb + 1, st);
@@ -1027,8 +1043,10 @@ bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_v
         const unsigned blocks = (unsigned)((n_warps + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
         unsigned long long* d_cnt = nullptr;
         if (ctx->count_work) { BS_TRY(bs_alloc(ctx, &d_cnt, 9)); BS_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, 72, st)); }
-        if (ctx->count_work) bs_count_launch(), k_brick_pass<true><<<bs_blocks(nb, BP_WARPS), 32 * BP_WARPS, 0, st>>>(T, vol->keys, nb, vol->voxel_size, kappa, d_bo, d_cnt);
-        else bs_count_launch(), k_brick_pass<false><<<bs_blocks(nb, BP_WARPS), 32 * BP_WARPS, 0, st>>>(T, vol->keys, nb, vol->voxel_size, kappa, d_bo, nullptr);
+        if (n_blist) {
+            if (ctx->count_work) bs_count_launch(), k_brick_pass<true><<<bs_blocks(n_blist, BP_WARPS), 32 * BP_WARPS, 0, st>>>(T, vol->keys, n_blist, d_blist, vol->voxel_size, kappa, d_bo, d_cnt);
+            else bs_count_launch(), k_brick_pass<false><<<bs_blocks(n_blist, BP_WARPS), 32 * BP_WARPS, 0, st>>>(T, vol->keys, n_blist, d_blist, vol->voxel_size, kappa, d_bo, nullptr);
+        }
         if (!ctx->count_work) bs_mark(ctx, "sign_brick_pass_ms");
         if (n_hitems) bs_count_launch(), k_expand_roots<<<bs_blocks(n_heavy, 4), 128, 0, st>>>(T, TB.other, d_heavy, n_heavy, d_bo, d_hr);
         if (n_items) {
@@ -1044,7 +1062,7 @@ bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_v
             for (int i = 0; i < 9; ++i) ctx->fwn_counts[i] = (double)h_cnt[i];
         }
         bs_free(ctx, d_hr); bs_free(ctx, d_partial); bs_free(ctx, d_offs); bs_free(ctx, d_heavy); bs_free(ctx, d_slot);
-        bs_free(ctx, d_bo); bs_free(ctx, d_item_brick);
+        bs_free(ctx, d_bo); bs_free(ctx, d_item_brick); bs_free(ctx, d_blist); bs_free(ctx, d_nblist);
         free_tree(ctx, TB);
         bs_mark(ctx, "sign_ms");
     }

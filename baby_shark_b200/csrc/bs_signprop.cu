@@ -11,9 +11,9 @@
 // Steps: (1) closed? (2) connected components of the band under certified links: inside a brick a bit-parallel flood fill
 // over the brick's 512-bit masks (8 lanes per brick, one 64-bit x-slab each; <= 8 components per brick, anything beyond
 // becomes individually evaluated voxels), across brick faces a lock-free union-find over (brick, component) ids -- 8 ids
-// per brick, not one per voxel; (3) ONE voxel per component is evaluated -- by a brute-force sum of solid angles over all
-// triangles when there are only a few (typically the inside shell, the outside shell and the handful of voxels that lie
-// on the surface within rounding), else by the LBVH traversal of bs_fwn.cu on the representatives only; (4) every other
+// per brick, not one per voxel; (3) ONE voxel per component is evaluated -- when there are only a few hundred (typically the
+// inside shell, the outside shell and the voxels that lie on the surface within rounding) by one streaming pass over the
+// triangles (k_sp_stream: groups of 32 consecutive triangles, far groups by their dipole expansion), else by the LBVH traversal of bs_fwn.cu on the representatives only; (4) every other
 // voxel copies the sign of its component's representative.
 //
 // (1) has two implementations. Default: a 128-bit multiset fingerprint -- sum over directed edges of H(a, b) must equal
@@ -253,8 +253,14 @@ __global__ void __launch_bounds__(256) k_sp_flatten(size_t n, unsigned* par, con
     if (k == 0) { n_chunks[b] = (c + per_chunk - 1) / per_chunk; if (c) atomicAdd(n_seeds, (u64)c); }
 }
 
-// ---- (3) few representatives: brute force ---------------------------------------------------------------------------------
-constexpr int SP_BRUTE_MAX = 64;
+// ---- (3) up to SP_BRUTE_MAX representatives: one streaming pass over the triangles, no tree ------------------------------------
+// A warp takes 32 consecutive triangles of the input (in most meshes a spatially compact strip), reduces them to the
+// reference's node moments (aabb_tree.rs:723-801: area, area-weighted centre and normal, order-2 tensor, bounding radius about
+// the centre) and then serves the representatives 32 at a time, one per lane: far ones (|p - p~| > 2.5 r, the reference
+// accepts at 2 r) get the order-1 + order-2 expansion (:667-669, 803-816), near ones the exact solid angles of the 32
+// triangles, one triangle per lane (:582-615). Input order only affects speed: a scattered group has a large radius and
+// is evaluated exactly.
+constexpr int SP_BRUTE_MAX = 512, SP_NC = SP_BRUTE_MAX / 32;
 __global__ void k_sp_collect(const u64* __restrict__ seed_masks, size_t n_words, unsigned* list /*voxel ids brick*512+off*/, unsigned* count, unsigned cap) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= n_words) return;
@@ -265,47 +271,90 @@ __global__ void k_sp_collect(const u64* __restrict__ seed_masks, size_t n_words,
         if (slot < cap) list[slot] = (unsigned)(i * 64 + bit);
     }
 }
-// solid_angle (aabb_tree.rs:582-615) of every triangle seen from each listed voxel, summed in double
-__global__ void __launch_bounds__(256) k_sp_brute(const float* __restrict__ tris, size_t n_tris, const unsigned* __restrict__ list, unsigned n_list,
-                                                  const u64* __restrict__ keys, float vs, double* wn /*[n_list]*/) {
+__device__ __forceinline__ float sp_warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+__global__ void __launch_bounds__(256) k_sp_stream(const float* __restrict__ tris, size_t n_tris, const unsigned* __restrict__ list, unsigned n_list,
+                                                   const u64* __restrict__ keys, float vs, double* wn /*[n_list]*/) {
     __shared__ float s_q[SP_BRUTE_MAX][3];
     __shared__ double s_acc[SP_BRUTE_MAX];
-    for (unsigned i = threadIdx.x; i < n_list; i += blockDim.x) {
-        const unsigned g = list[i], off = g & 511;
-        int bx, by, bz; bs_key_brick(keys[g >> 9], bx, by, bz);
-        s_q[i][0] = __fmul_rn((float)((bx << 3) + (int)(off >> 6)), vs);
-        s_q[i][1] = __fmul_rn((float)((by << 3) + (int)((off >> 3) & 7)), vs);
-        s_q[i][2] = __fmul_rn((float)((bz << 3) + (int)(off & 7)), vs);
+    for (unsigned i = threadIdx.x; i < SP_BRUTE_MAX; i += blockDim.x) {
         s_acc[i] = 0.0;
+        if (i < n_list) {
+            const unsigned g = list[i], off = g & 511;
+            int bx, by, bz; bs_key_brick(keys[g >> 9], bx, by, bz);
+            s_q[i][0] = __fmul_rn((float)((bx << 3) + (int)(off >> 6)), vs);
+            s_q[i][1] = __fmul_rn((float)((by << 3) + (int)((off >> 3) & 7)), vs);
+            s_q[i][2] = __fmul_rn((float)((bz << 3) + (int)(off & 7)), vs);
+        } else { s_q[i][0] = s_q[i][1] = s_q[i][2] = 0.f; }
     }
     __syncthreads();
-    for (unsigned base = 0; base < n_list; base += 8) {
-        double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        const unsigned m = min(8u, n_list - base);
-        for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n_tris; t += (size_t)gridDim.x * blockDim.x) {
-            const float* p = tris + 9 * t;
-            const float v[9] = {p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[8]};
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned nc = (n_list + 31) / 32;
+    float acc[SP_NC];
 #pragma unroll
-            for (unsigned i = 0; i < 8; ++i) {
-                if (i >= m) break;
-                const float qx = s_q[base + i][0], qy = s_q[base + i][1], qz = s_q[base + i][2];
-                const float ax = v[0] - qx, ay = v[1] - qy, az = v[2] - qz, bx = v[3] - qx, by = v[4] - qy, bz = v[5] - qz, cx = v[6] - qx, cy = v[7] - qy, cz = v[8] - qz;
-                const float la = sqrtf(ax * ax + ay * ay + az * az), lb = sqrtf(bx * bx + by * by + bz * bz), lc = sqrtf(cx * cx + cy * cy + cz * cz);
-                if (la == 0.f || lb == 0.f || lc == 0.f) continue;
-                const float det = ax * (by * cz - bz * cy) + ay * (bz * cx - bx * cz) + az * (bx * cy - by * cx);
-                if (det == 0.f) continue;
-                const float den = la * lb * lc + (ax * bx + ay * by + az * bz) * lc + (ax * cx + ay * cy + az * cz) * lb + (bx * cx + by * cy + bz * cz) * la;
-                acc[i] += (double)atan2f(det, den);
+    for (int c = 0; c < SP_NC; ++c) acc[c] = 0.f;
+    const size_t n_groups = (n_tris + 31) / 32, warp0 = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5, n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t g = warp0; g < n_groups; g += n_warps) {
+        const size_t t = g * 32 + lane;
+        float v[9];
+        if (t < n_tris) { const float* p = tris + 9 * t; for (int i = 0; i < 9; ++i) v[i] = p[i]; } else { for (int i = 0; i < 9; ++i) v[i] = 0.f; }
+        const float e1x = v[3] - v[0], e1y = v[4] - v[1], e1z = v[5] - v[2], e2x = v[6] - v[0], e2y = v[7] - v[1], e2z = v[8] - v[2];
+        float hx = 0.5f * (e1y * e2z - e1z * e2y), hy = 0.5f * (e1z * e2x - e1x * e2z), hz = 0.5f * (e1x * e2y - e1y * e2x);  // area * normal
+        float area = sqrtf(hx * hx + hy * hy + hz * hz);
+        if (!(area > 0.f) || !(area < 3.0e38f)) { area = 0.f; hx = hy = hz = 0.f; }  // degenerate triangles are skipped (:757-759)
+        const float cx = (v[0] + v[3] + v[6]) * (1.0f / 3.0f), cy = (v[1] + v[4] + v[7]) * (1.0f / 3.0f), cz = (v[2] + v[5] + v[8]) * (1.0f / 3.0f);
+        const float A = sp_warp_sum(area);
+        if (!(A > 0.f)) continue;  // warp-uniform
+        const float iA = 1.0f / A;
+        const float px = sp_warp_sum(area * cx) * iA, py = sp_warp_sum(area * cy) * iA, pz = sp_warp_sum(area * cz) * iA;  // p~
+        const float ox = sp_warp_sum(hx), oy = sp_warp_sum(hy), oz = sp_warp_sum(hz);                                       // order 1
+        // order 2 about p~: M[col][row] = sum (c[row] - p~[row]) * h[col]; only tr M and the symmetric parts enter r^T M r
+        const float dx = cx - px, dy = cy - py, dz = cz - pz;
+        const float m00 = sp_warp_sum(dx * hx), m11 = sp_warp_sum(dy * hy), m22 = sp_warp_sum(dz * hz);
+        const float m01 = sp_warp_sum(dy * hx + dx * hy), m02 = sp_warp_sum(dz * hx + dx * hz), m12 = sp_warp_sum(dz * hy + dy * hz);
+        float r2max = 0.f;
+        if (t < n_tris) for (int k = 0; k < 3; ++k) { const float ax = v[3 * k] - px, ay = v[3 * k + 1] - py, az = v[3 * k + 2] - pz; r2max = fmaxf(r2max, ax * ax + ay * ay + az * az); }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) r2max = fmaxf(r2max, __shfl_xor_sync(0xFFFFFFFFu, r2max, o));
+        const float far2 = 6.25f * r2max;  // (2.5 r)^2
+#pragma unroll
+        for (int c = 0; c < SP_NC; ++c) {
+            if ((unsigned)c >= nc) break;  // uniform
+            const unsigned si = c * 32 + lane;
+            const float qx = s_q[si][0], qy = s_q[si][1], qz = s_q[si][2];
+            const float rx = px - qx, ry = py - qy, rz = pz - qz;
+            const float r2 = rx * rx + ry * ry + rz * rz;
+            const bool valid = si < n_list, far = valid && r2 > far2;
+            if (far) {
+                const float inv_r = rsqrtf(r2), ir2 = inv_r * inv_r, k = 0.07957747154594767f * inv_r * ir2;
+                const float d = ox * rx + oy * ry + oz * rz + (m00 + m11 + m22);
+                const float rMr = rx * (m00 * rx + m01 * ry + m02 * rz) + ry * (m11 * ry + m12 * rz) + m22 * rz * rz;
+                acc[c] += k * (d - 3.0f * ir2 * rMr);
+            }
+            unsigned near = __ballot_sync(0xFFFFFFFFu, valid && !far);
+            while (near) {  // exact: lane = triangle, one representative at a time
+                const int j = __ffs(near) - 1; near &= near - 1;
+                const float sx = s_q[c * 32 + j][0], sy = s_q[c * 32 + j][1], sz = s_q[c * 32 + j][2];
+                const float ax = v[0] - sx, ay = v[1] - sy, az = v[2] - sz, bx = v[3] - sx, by = v[4] - sy, bz = v[5] - sz, ccx = v[6] - sx, ccy = v[7] - sy, ccz = v[8] - sz;
+                const float la = sqrtf(ax * ax + ay * ay + az * az), lb = sqrtf(bx * bx + by * by + bz * bz), lc = sqrtf(ccx * ccx + ccy * ccy + ccz * ccz);
+                float w = 0.f;
+                if (la != 0.f && lb != 0.f && lc != 0.f) {
+                    const float det = ax * (by * ccz - bz * ccy) + ay * (bz * ccx - bx * ccz) + az * (bx * ccy - by * ccx);
+                    const float den = la * lb * lc + (ax * bx + ay * by + az * bz) * lc + (ax * ccx + ay * ccy + az * ccz) * lb + (bx * ccx + by * ccy + bz * ccz) * la;
+                    if (det != 0.f) w = atan2f(det, den) * (2.0f * 0.07957747154594767f);
+                }
+                w = sp_warp_sum(w);
+                if ((int)lane == j) acc[c] += w;
             }
         }
-        for (unsigned i = 0; i < m; ++i) {
-            double a = acc[i];
-            for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xFFFFFFFFu, a, o);
-            if ((threadIdx.x & 31) == 0) atomicAdd(&s_acc[base + i], a);
-        }
     }
+#pragma unroll
+    for (int c = 0; c < SP_NC; ++c) if ((unsigned)c < nc && acc[c] != 0.f) atomicAdd(&s_acc[c * 32 + lane], (double)acc[c]);
     __syncthreads();
-    for (unsigned i = threadIdx.x; i < n_list; i += blockDim.x) atomicAdd(wn + i, s_acc[i] * (2.0 / 12.566370614359172));
+    for (unsigned i = threadIdx.x; i < n_list; i += blockDim.x) if (s_acc[i] != 0.0) atomicAdd(wn + i, s_acc[i]);
 }
 __global__ void k_sp_brute_apply(float* values, const unsigned* __restrict__ list, unsigned n_list, const double* __restrict__ wn) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -420,7 +469,7 @@ void bs_sign_components_free(bs_context* ctx, bs_sign_components* C) {
     memset(C, 0, sizeof(*C));
 }
 int bs_sign_brute_max() { return SP_BRUTE_MAX; }
-// evaluates the (<= SP_BRUTE_MAX) representatives by brute force over all triangles and sets their signs
+// evaluates the (<= SP_BRUTE_MAX) representatives in one streaming pass over all triangles and sets their signs
 bs_status bs_sign_brute_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_volume* vol, const bs_sign_components* C, unsigned n_seeds) {
     cudaStream_t st = ctx->stream;
     if (n_seeds == 0) return BS_OK;
@@ -429,9 +478,9 @@ bs_status bs_sign_brute_impl(bs_context* ctx, const float* d_tris, size_t n_tris
     BS_CUDA(ctx, cudaMemsetAsync(d_count, 0, sizeof(unsigned), st));
     BS_CUDA(ctx, cudaMemsetAsync(d_wn, 0, SP_BRUTE_MAX * sizeof(double), st));
     bs_count_launch(), k_sp_collect<<<bs_blocks(vol->n_bricks * 8, 256), 256, 0, st>>>(C->seed, vol->n_bricks * 8, d_list, d_count, (unsigned)SP_BRUTE_MAX);
-    const unsigned grid = (unsigned)std::min<size_t>(bs_blocks(n_tris, 256), (size_t)ctx->sm_count * 8);
-    bs_count_launch(), k_sp_brute<<<grid, 256, 0, st>>>(d_tris, n_tris, d_list, n_seeds, vol->keys, vol->voxel_size, d_wn);
-    bs_count_launch(), k_sp_brute_apply<<<1, SP_BRUTE_MAX, 0, st>>>(vol->values, d_list, n_seeds, d_wn);
+    const unsigned grid = (unsigned)std::min<size_t>(bs_blocks((n_tris + 31) / 32 * 32, 256), (size_t)ctx->sm_count * 6);
+    bs_count_launch(), k_sp_stream<<<grid, 256, 0, st>>>(d_tris, n_tris, d_list, n_seeds, vol->keys, vol->voxel_size, d_wn);
+    bs_count_launch(), k_sp_brute_apply<<<bs_blocks(SP_BRUTE_MAX, 256), 256, 0, st>>>(vol->values, d_list, n_seeds, d_wn);
     bs_free(ctx, d_list); bs_free(ctx, d_count); bs_free(ctx, d_wn);
     BS_CUDA(ctx, cudaGetLastError());
     return BS_OK;

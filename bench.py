@@ -40,8 +40,8 @@ def parse():
     ap.add_argument("--scale", type=float, default=1.0, help="resolution scale of the config (1.0 = BASELINE.json size)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-scale", type=float, default=None,
-                    help="scale of the bounded CPU sample (default: 0.1875 for the cpu_baseline of our arm; the reference arm picks the largest of "
-                         "0.1875 / 0.125 / 0.09375 / 0.0625 whose steps + warm-up fit in ~150 s)")
+                    help="scale of the bounded CPU sample (default: the largest scale of CPU_LADDER that fits the time budget on this host, "
+                         "extrapolated from two measured calibration passes: ~25 s for the cpu_baseline pass of our arm, ~150 s for the reference arm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sign-propagation", action="store_true",
                     help="A/B switch: per-voxel winding numbers even on closed meshes (BS_FLAG_SIGN_PROPAGATION = 0); recorded in config")
@@ -268,39 +268,65 @@ class ClockSampler(threading.Thread):
 
 
 def cpu_port(tris, vs, threads):
-    """One pass of the reference's CPU path (oracle port): convert + MC. Returns (active voxels, triangles, seconds)."""
+    """One pass of the reference's CPU path (oracle port): convert + MC. Returns (active voxels, triangles, seconds, stats)."""
     from oracle import oracle as O
     t0 = time.perf_counter()
     vol, st = O.mesh_to_volume(tris, vs, 0, threads)
+    t1 = time.perf_counter()
     verts = O.marching_cubes(vol, vs)
     dt = time.perf_counter() - t0
+    st = dict(st)
+    st["t_mc"] = time.perf_counter() - t1
     return st["n_active"], verts.shape[0] // 3, dt, st
+
+
+CPU_LADDER = (1.0, 0.75, 0.5, 0.375, 0.25, 0.1875, 0.125, 0.09375, 0.0625)
+
+
+def cpu_pick_scale(cfg, threads, n_pass, budget_s):
+    """Largest scale of CPU_LADDER whose n_pass passes fit in budget_s, from two MEASURED calibration passes (scales 0.0625 and
+    0.125): seconds(scale) = t_0.125 * (scale / 0.125) ** p with the measured exponent p. Returns (scale, p, calibration dict)."""
+    import math
+    t = {}
+    for sc in (0.0625, 0.125):
+        tris, vs, _ = workload(cfg, sc)
+        t[sc] = cpu_port(tris, vs, threads)[2]
+    p = max(2.0, min(3.5, math.log(t[0.125] / t[0.0625]) / math.log(2.0)))
+    budget = budget_s - t[0.0625] - t[0.125]
+    scale = next((sc for sc in CPU_LADDER if t[0.125] * (sc / 0.125) ** p * n_pass <= budget), 0.0625)
+    return scale, p, {"seconds_at_0.0625": round(t[0.0625], 2), "seconds_at_0.125": round(t[0.125], 2)}
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    if args.cpu_scale is None:
-        # seconds per pass measured on the 16-core GPU host for config 5 (time grows ~ scale^2.6); keep the whole run bounded
-        n_pass = max(1, args.steps) + max(0, min(args.warmup, 1))
-        est = {0.1875: 15.0, 0.125: 5.5, 0.09375: 2.7, 0.0625: 1.2}
-        args.cpu_scale = next((sc for sc in sorted(est, reverse=True) if est[sc] * 16.0 / cores * n_pass <= 150.0), 0.0625)
+    n_warm = max(0, min(args.warmup, 1))
+    n_pass = max(1, args.steps) + n_warm
+    calib, expo = None, None
+    if args.cpu_scale is None:  # the largest sample whose steps + warm-up fit in ~150 s on THIS host, measured not tabulated
+        args.cpu_scale, expo, calib = cpu_pick_scale(args.config, cores, n_pass, 150.0)
     tris, vs, desc = workload(args.config, args.cpu_scale)
-    for _ in range(max(0, min(args.warmup, 1))):
+    for _ in range(n_warm):
         cpu_port(tris, vs, cores)
-    tot_v, tot_t = 0, 0.0
+    tot_v, tot_t, stage = 0, 0.0, {}
     for _ in range(max(1, args.steps)):
-        nv, nt, dt, _ = cpu_port(tris, vs, cores)
+        nv, nt, dt, st = cpu_port(tris, vs, cores)
         tot_v += nv
         tot_t += dt
+        for k in ("t_subdivide", "t_tree", "t_udf", "t_sign", "t_mc"):
+            stage[k] = stage.get(k, 0.0) + st[k] / max(1, args.steps)
     value = tot_v / tot_t
-    sample = "config %d at scale %g: %s (%d triangles), convert + MC per step" % (args.config, args.cpu_scale, desc, tris.shape[0])
+    sample = "config %d at scale %g: %s (%d triangles, %d active voxels), convert + MC per step" % (args.config, args.cpu_scale, desc, tris.shape[0], nv)
+    cb = {"value": value, "unit": UNIT, "cores": cores, "threads": cores, "kind": "port", "sample": sample,
+          "stage_seconds": {k: round(v, 3) for k, v in stage.items()},
+          "note": "C++ restatement of the reference (no Rust toolchain): distance evaluations and the sign pass run on all host threads, tree build / min-merge / MC are serial as in the reference"}
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * tot_t / max(1, args.steps), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": "config %d: %s" % (args.config, workload_desc(args)), "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "data": "synthetic", "config": {"workload": "config %d: %s" % (args.config, workload_desc(args)), "sample": sample, "sample_scale": args.cpu_scale},
+        "same_config": bool(args.cpu_scale == args.scale), "time_exponent_vs_scale": expo, "calibration": calib,
+        "cpu_baseline": cb,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -591,7 +617,8 @@ def main():
                        "parallelism": "brick slabs x%d, mesh replicated" % world, "sign_propagation": bool(work.get("sign_propagation", 0.0))},
             "remesh_ms": ms_per_step, "tris_per_s": (n_verts / 3.0) / (ms_per_step * 1e-3), "n_active_voxels": n_active, "n_out_triangles": n_verts / 3.0,
             "step_ms": step_ms, "stage_ms": stage_all, "stage_ms_per_rank": per_rank, "work": work,
-            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": int(tris.nbytes), "d2h_bytes_per_step": int(n_verts_local * 12)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": int(tris.nbytes) * world, "d2h_bytes_per_step": int(n_verts * 12),
+                    "what": "pinned host triangles in (every rank uploads the mesh), all output vertices back on the host of rank 0"},
             "e2e_indexed": None, "gpu_launches": None, "clocks": clocks,
             "roofline": dominant, "rooflines": rl,
             "verified": verify_out["verified"] if verify_out else None, "verify": verify_out,
@@ -603,10 +630,13 @@ def main():
         out["gpu_launches"] = int(launches) * world  # counted by the library at its launch sites (bs_kernel_launch_count)
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
-            cpu_scale = args.cpu_scale if args.cpu_scale is not None else 0.1875
+            cpu_scale = args.cpu_scale
+            if cpu_scale is None:  # one pass of ~20 s on this host, sized from two measured calibration passes
+                cpu_scale, _, _ = cpu_pick_scale(args.config, cores, 1, 25.0)
             ctris, cvs, cdesc = workload(args.config, cpu_scale)
             nv_c, nt_c, dt_c, st_c = cpu_port(ctris, cvs, cores)
-            out["cpu_baseline"] = {"value": nv_c / dt_c, "unit": UNIT, "cores": cores, "kind": "port",
+            out["cpu_baseline"] = {"value": nv_c / dt_c, "unit": UNIT, "cores": cores, "threads": cores, "kind": "port",
+                                   "stage_seconds": {k: round(st_c[k], 3) for k in ("t_subdivide", "t_tree", "t_udf", "t_sign", "t_mc")},
                                    "sample": "config %d at scale %g: %s (%d triangles, %d active voxels), one convert + MC pass in %.1f s" % (args.config, cpu_scale, cdesc, ctris.shape[0], nv_c, dt_c)}
         print(json.dumps(out))
     if world > 1:
