@@ -11,6 +11,8 @@
 #include <stdint.h>
 #include <stddef.h>
 #include <map>
+#include <mutex>
+#include <unordered_set>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -77,7 +79,14 @@ struct bs_stat { const char* name; double value; };
 extern unsigned long long g_bs_launches;
 static inline void bs_count_launch() { ++g_bs_launches; }
 
+struct bs_volume;
 struct bs_context {
+    // One in-flight call per context: every entry point of the ABI holds this lock for its whole duration (BS_ENTER),
+    // so handles may be used from several host threads. The result of a *_device extraction stays valid until the next
+    // extraction on the context: callers that pair bs_mesh_mc_device with bs_context_copy_out_verts from several threads
+    // must serialise the pair themselves (bs_mesh_mc / bs_mesh_dc do both under one lock).
+    std::recursive_mutex mtx;
+    std::unordered_set<bs_volume*> live_volumes;  // handles that still point at this context (bs_context_destroy orphans them)
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
@@ -140,6 +149,8 @@ bs_status bs_raw_alloc(bs_context* ctx, size_t bytes, void** out);
 void bs_raw_free(bs_context* ctx, void* p);
 void bs_cache_release(bs_context* ctx);  // give every cached (free) block back to the driver
 void bs_op_begin(bs_context* ctx);       // first thing an ABI entry point does once its handles are validated
+// lock the context for the rest of the enclosing scope, select its device, start a new allocation epoch
+#define BS_ENTER(c) std::lock_guard<std::recursive_mutex> bs_lock_((c)->mtx); cudaSetDevice((c)->device); bs_op_begin(c)
 template <class T> bs_status bs_alloc(bs_context* ctx, T** p, size_t count) {
     *p = nullptr;
     if (count == 0) count = 1;

@@ -38,6 +38,7 @@ void bs_stat_add(bs_context* ctx, const char* name, double v) { ctx->stats.push_
 bs_volume* bs_volume_new(bs_context* ctx, float voxel_size) {
     bs_volume* v = new bs_volume();
     v->ctx = ctx; v->voxel_size = voxel_size;
+    ctx->live_volumes.insert(v);
     return v;
 }
 bs_status bs_volume_alloc_bricks(bs_volume* v, size_t n) {
@@ -151,14 +152,20 @@ bs_status bs_context_create(int device, bs_context** out) {
 }
 void bs_context_destroy(bs_context* ctx) {
     if (!ctx) return;
-    cudaSetDevice(ctx->device); bs_op_begin(ctx);
+    {
+    BS_ENTER(ctx);
     cudaStreamSynchronize(ctx->stream);
+    // volumes the caller still holds lose their context (their device memory goes with it): bs_volume_free on such a handle
+    // only deletes the host object, every other call on it is BS_ERR_INVALID
+    for (bs_volume* v : ctx->live_volumes) { v->ctx = nullptr; v->keys = nullptr; v->values = nullptr; v->masks = nullptr; v->owned = nullptr; v->tile8_keys = nullptr; v->tile8_values = nullptr; v->tile128_keys = nullptr; v->tile128_values = nullptr; v->n_bricks = 0; }
+    ctx->live_volumes.clear();
     for (auto& m : ctx->marks) cudaEventDestroy(m.second);
     if (ctx->d_out_verts) cudaFree(ctx->d_out_verts);
     bs_cache_release(ctx);
     for (auto& kv : ctx->cache_live) cudaFree(kv.first);  // volumes the caller never freed
     cudaFree(ctx->d_mc33); cudaFree(ctx->d_err);
     cudaStreamDestroy(ctx->stream);
+    }
     delete ctx;
 }
 unsigned long long bs_kernel_launch_count(void) { return g_bs_launches; }
@@ -173,7 +180,7 @@ bs_status bs_context_set_flag(bs_context* ctx, int flag, int value) {
 }
 bs_status bs_context_copy_out_verts_device(bs_context* ctx, float* d_dst, size_t n_floats) {
     if (!ctx || (!d_dst && n_floats)) return BS_ERR_INVALID;
-    cudaSetDevice(ctx->device); bs_op_begin(ctx);  // before any bs_fail: a failure belongs to THIS call's epoch
+    BS_ENTER(ctx);  // before any bs_fail: a failure belongs to THIS call's epoch
     if (n_floats > ctx->out_verts_cap) return bs_fail(ctx, BS_ERR_INVALID, "no extraction result of that size on the device");
     if (n_floats) BS_CUDA(ctx, cudaMemcpyAsync(d_dst, ctx->d_out_verts, n_floats * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
     BS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -181,7 +188,7 @@ bs_status bs_context_copy_out_verts_device(bs_context* ctx, float* d_dst, size_t
 }
 bs_status bs_context_copy_out_verts(bs_context* ctx, float* dst, size_t n_floats) {
     if (!ctx || (!dst && n_floats)) return BS_ERR_INVALID;
-    cudaSetDevice(ctx->device); bs_op_begin(ctx);  // before any bs_fail: a failure belongs to THIS call's epoch
+    BS_ENTER(ctx);  // before any bs_fail: a failure belongs to THIS call's epoch
     if (n_floats > ctx->out_verts_cap) return bs_fail(ctx, BS_ERR_INVALID, "no extraction result of that size on the device");
     if (n_floats) BS_CUDA(ctx, cudaMemcpyAsync(dst, ctx->d_out_verts, n_floats * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     BS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -197,7 +204,9 @@ size_t bs_context_last_stats(const bs_context* ctx, const char** names, double* 
 void bs_volume_free(bs_volume* v) {
     if (!v) return;
     bs_context* c = v->ctx;
-    cudaSetDevice(c->device); bs_op_begin(c);
+    if (!c) { delete v; return; }  // orphaned by bs_context_destroy
+    BS_ENTER(c);
+    c->live_volumes.erase(v);
     bs_free(c, v->keys); bs_free(c, v->values); bs_free(c, v->masks); bs_free(c, v->owned);
     bs_free(c, v->tile8_keys); bs_free(c, v->tile8_values); bs_free(c, v->tile128_keys); bs_free(c, v->tile128_values);
     delete v;
@@ -206,7 +215,7 @@ float bs_volume_voxel_size(const bs_volume* v) { return v ? v->voxel_size : 0.0f
 
 bs_status bs_volume_empty(bs_context* ctx, float voxel_size, bs_volume** out) {
     if (!ctx || !out) return BS_ERR_INVALID;
-    cudaSetDevice(ctx->device); bs_op_begin(ctx);
+    BS_ENTER(ctx);
     bs_volume* v = bs_volume_new(ctx, voxel_size);
     bs_status s = bs_volume_alloc_bricks(v, 0);
     if (s != BS_OK) { bs_volume_free(v); return s; }
@@ -215,9 +224,9 @@ bs_status bs_volume_empty(bs_context* ctx, float voxel_size, bs_volume** out) {
 }
 
 bs_status bs_volume_clone(const bs_volume* v, bs_volume** out) {
-    if (!v || !out) return BS_ERR_INVALID;
+    if (!v || !v->ctx || !out) return BS_ERR_INVALID;
     bs_context* c = v->ctx;
-    cudaSetDevice(c->device); bs_op_begin(c);
+    BS_ENTER(c);
     bs_volume* w = bs_volume_new(c, v->voxel_size);
     w->n_bricks = v->n_bricks; w->n_owned = v->n_owned; w->n_tiles8 = v->n_tiles8; w->n_tiles128 = v->n_tiles128;
     bs_status s;
@@ -233,15 +242,15 @@ bs_status bs_volume_clone(const bs_volume* v, bs_volume** out) {
 void bs_buffer_free(void* p) { if (p) cudaFreeHost(p); }
 
 // ---- data formats either side of the path (bs_io.cu) ---------------------------------------------------------------------------
-void bs_device_free(bs_context* ctx, void* d_ptr) { if (ctx && d_ptr) { cudaSetDevice(ctx->device); bs_op_begin(ctx); bs_raw_free(ctx, d_ptr); } }
+void bs_device_free(bs_context* ctx, void* d_ptr) { if (ctx && d_ptr) { BS_ENTER(ctx); bs_raw_free(ctx, d_ptr); } }
 bs_status bs_stl_decode_device(bs_context* ctx, const unsigned char* d_stl, size_t n_bytes, float** d_tris, size_t* n_tris) {
     if (!ctx || !d_tris || !n_tris || (!d_stl && n_bytes)) return BS_ERR_INVALID;
-    cudaSetDevice(ctx->device); bs_op_begin(ctx);
+    BS_ENTER(ctx);
     return bs_stl_decode_impl(ctx, d_stl, n_bytes, d_tris, n_tris);
 }
 bs_status bs_stl_decode(bs_context* ctx, const unsigned char* stl, size_t n_bytes, float** d_tris, size_t* n_tris) {
     if (!ctx || !d_tris || !n_tris || (!stl && n_bytes)) return BS_ERR_INVALID;
-    cudaSetDevice(ctx->device); bs_op_begin(ctx);
+    BS_ENTER(ctx);
     unsigned char* d = nullptr;
     BS_TRY(bs_alloc(ctx, &d, n_bytes + 4));
     if (n_bytes && cudaMemcpyAsync(d, stl, n_bytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { bs_free(ctx, d); return bs_fail(ctx, BS_ERR_CUDA, "host to device copy failed"); }
@@ -251,12 +260,12 @@ bs_status bs_stl_decode(bs_context* ctx, const unsigned char* stl, size_t n_byte
 }
 bs_status bs_stl_encode_device(bs_context* ctx, const float* d_verts, size_t n_verts, unsigned char** d_stl, size_t* n_bytes) {
     if (!ctx || !d_stl || !n_bytes || (!d_verts && n_verts)) return BS_ERR_INVALID;
-    cudaSetDevice(ctx->device); bs_op_begin(ctx);
+    BS_ENTER(ctx);
     return bs_stl_encode_impl(ctx, d_verts, n_verts, d_stl, n_bytes);
 }
 bs_status bs_stl_encode(bs_context* ctx, const float* d_verts, size_t n_verts, unsigned char** stl, size_t* n_bytes) {
     if (!ctx || !stl || !n_bytes || (!d_verts && n_verts)) return BS_ERR_INVALID;
-    cudaSetDevice(ctx->device); bs_op_begin(ctx);
+    BS_ENTER(ctx);
     unsigned char* d = nullptr;
     BS_TRY(bs_stl_encode_impl(ctx, d_verts, n_verts, &d, n_bytes));
     const bs_status s = to_pinned(ctx, d, *n_bytes, stl);
@@ -264,13 +273,13 @@ bs_status bs_stl_encode(bs_context* ctx, const float* d_verts, size_t n_verts, u
     return s;
 }
 bs_status bs_mesh_active_voxels_device(const bs_volume* v, int32_t** d_verts, size_t* n_verts) {
-    if (!v || !d_verts || !n_verts) return BS_ERR_INVALID;
-    cudaSetDevice(v->ctx->device); bs_op_begin(v->ctx);
+    if (!v || !v->ctx || !d_verts || !n_verts) return BS_ERR_INVALID;
+    BS_ENTER(v->ctx);
     return bs_active_voxels_impl(v, d_verts, n_verts);
 }
 bs_status bs_mesh_active_voxels(const bs_volume* v, int32_t** verts, size_t* n_verts) {
-    if (!v || !verts || !n_verts) return BS_ERR_INVALID;
-    cudaSetDevice(v->ctx->device); bs_op_begin(v->ctx);
+    if (!v || !v->ctx || !verts || !n_verts) return BS_ERR_INVALID;
+    BS_ENTER(v->ctx);
     int* d = nullptr;
     BS_TRY(bs_active_voxels_impl(v, &d, n_verts));
     const bs_status s = to_pinned(v->ctx, d, *n_verts * 3, verts);
@@ -279,29 +288,29 @@ bs_status bs_mesh_active_voxels(const bs_volume* v, int32_t** verts, size_t* n_v
 }
 bs_status bs_merge_points_device(bs_context* ctx, const float* d_points, size_t n, float** d_unique, size_t* n_unique, uint32_t** d_indices) {
     if (!ctx || !d_unique || !n_unique || !d_indices || (!d_points && n)) return BS_ERR_INVALID;
-    cudaSetDevice(ctx->device); bs_op_begin(ctx);
+    BS_ENTER(ctx);
     return bs_merge_points_impl(ctx, d_points, n, d_unique, n_unique, d_indices);
 }
 bs_status bs_copy_to_host(bs_context* ctx, const void* d_src, void* dst, size_t bytes) {
     if (!ctx || ((!d_src || !dst) && bytes)) return BS_ERR_INVALID;
-    cudaSetDevice(ctx->device); bs_op_begin(ctx);
+    BS_ENTER(ctx);
     if (bytes) BS_CUDA(ctx, cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     BS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return BS_OK;
 }
 bs_status bs_mesh_mc_indexed_device(const bs_volume* v, float voxel_size, float** d_points, size_t* n_points, uint32_t** d_indices, size_t* n_indices) {
-    if (!v || !d_points || !n_points || !d_indices || !n_indices) return BS_ERR_INVALID;
+    if (!v || !v->ctx || !d_points || !n_points || !d_indices || !n_indices) return BS_ERR_INVALID;
     bs_context* ctx = v->ctx;
-    cudaSetDevice(ctx->device); bs_op_begin(ctx);
+    BS_ENTER(ctx);
     const float* d_soup = nullptr; size_t n = 0;
     BS_TRY(bs_mc_impl(v, voxel_size, &d_soup, &n));
     *n_indices = n;
     return bs_merge_points_impl(ctx, d_soup, n, d_points, n_points, d_indices);
 }
 bs_status bs_mesh_mc_indexed(const bs_volume* v, float voxel_size, float** points, size_t* n_points, uint32_t** indices, size_t* n_indices) {
-    if (!v || !points || !n_points || !indices || !n_indices) return BS_ERR_INVALID;
+    if (!v || !v->ctx || !points || !n_points || !indices || !n_indices) return BS_ERR_INVALID;
     bs_context* ctx = v->ctx;
-    cudaSetDevice(ctx->device); bs_op_begin(ctx);
+    BS_ENTER(ctx);
     const float* d_soup = nullptr; size_t n = 0;
     BS_TRY(bs_mc_impl(v, voxel_size, &d_soup, &n));
     float* d_u = nullptr; unsigned* d_i = nullptr;
@@ -314,7 +323,7 @@ bs_status bs_mesh_mc_indexed(const bs_volume* v, float voxel_size, float** point
 }
 bs_status bs_merge_points(bs_context* ctx, const float* points, size_t n, float** unique, size_t* n_unique, uint32_t** indices) {
     if (!ctx || !unique || !n_unique || !indices || (!points && n)) return BS_ERR_INVALID;
-    cudaSetDevice(ctx->device); bs_op_begin(ctx);
+    BS_ENTER(ctx);
     float* d_p = nullptr; float* d_u = nullptr; unsigned* d_i = nullptr;
     BS_TRY(bs_alloc(ctx, &d_p, n * 3));
     if (n && cudaMemcpyAsync(d_p, points, n * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { bs_free(ctx, d_p); return bs_fail(ctx, BS_ERR_CUDA, "host to device copy failed"); }
@@ -330,9 +339,9 @@ bs_status bs_merge_points(bs_context* ctx, const float* points, size_t n, float*
 
 bs_status bs_volume_download(const bs_volume* v, int32_t** brick_ijk, float** values, uint64_t** masks, size_t* n_bricks,
                              int32_t** tile_ijk, int32_t** tile_size, float** tile_values, size_t* n_tiles) {
-    if (!v || !brick_ijk || !values || !masks || !n_bricks) return BS_ERR_INVALID;
+    if (!v || !v->ctx || !brick_ijk || !values || !masks || !n_bricks) return BS_ERR_INVALID;
     bs_context* c = v->ctx;
-    cudaSetDevice(c->device); bs_op_begin(c);
+    BS_ENTER(c);
     const size_t n = v->n_bricks;
     unsigned long long* hkeys = nullptr;
     BS_TRY(to_host(c, &hkeys, v->keys, n));
@@ -374,7 +383,7 @@ bs_status bs_mesh_to_volume_sharded(bs_context* ctx, const float* d_tris, size_t
                                     int rank, int world, bs_volume** out) {
     if (!ctx || !out || world < 1 || rank < 0 || rank >= world) return BS_ERR_INVALID;
     *out = nullptr;
-    cudaSetDevice(ctx->device); bs_op_begin(ctx);  // before any bs_fail: a failure belongs to THIS call's epoch
+    BS_ENTER(ctx);  // before any bs_fail: a failure belongs to THIS call's epoch
     if (!(voxel_size > 0.0f) || band < 0 || band > 64) return bs_fail(ctx, BS_ERR_INVALID, "voxel_size must be > 0 and 0 <= band_width <= 64");
     if (n_tris == 0) return BS_ERR_EMPTY_MESH;
     return bs_convert_impl(ctx, d_tris, n_tris, voxel_size, band, rank, world, out);
@@ -387,7 +396,7 @@ bs_status bs_mesh_to_volume(bs_context* ctx, const float* tris, size_t n_tris, f
     *out = nullptr;
     if (n_tris == 0) return BS_ERR_EMPTY_MESH;
     if (!tris) return BS_ERR_INVALID;
-    cudaSetDevice(ctx->device); bs_op_begin(ctx);
+    BS_ENTER(ctx);
     float* d = nullptr;
     BS_TRY(bs_alloc(ctx, &d, n_tris * 9));
     cudaError_t e = cudaMemcpyAsync(d, tris, n_tris * 9 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
@@ -408,23 +417,25 @@ static bs_status verts_to_host(bs_context* c, const float* d, size_t n, float** 
     return BS_OK;
 }
 bs_status bs_mesh_mc_device(const bs_volume* v, float voxel_size, const float** d_verts, size_t* n_verts) {
-    if (!v || !d_verts || !n_verts) return BS_ERR_INVALID;
-    cudaSetDevice(v->ctx->device); bs_op_begin(v->ctx);
+    if (!v || !v->ctx || !d_verts || !n_verts) return BS_ERR_INVALID;
+    BS_ENTER(v->ctx);
     return bs_mc_impl(v, voxel_size, d_verts, n_verts);
 }
 bs_status bs_mesh_mc(const bs_volume* v, float voxel_size, float** verts, size_t* n_verts) {
-    if (!v || !verts || !n_verts) return BS_ERR_INVALID;
+    if (!v || !v->ctx || !verts || !n_verts) return BS_ERR_INVALID;
+    BS_ENTER(v->ctx);  // extraction + read-back under one lock
     const float* d = nullptr; size_t n = 0;
     BS_TRY(bs_mesh_mc_device(v, voxel_size, &d, &n));
     return verts_to_host(v->ctx, d, n, verts, n_verts);
 }
 bs_status bs_mesh_dc_device(const bs_volume* v, float voxel_size, const float** d_verts, size_t* n_verts) {
-    if (!v || !d_verts || !n_verts) return BS_ERR_INVALID;
-    cudaSetDevice(v->ctx->device); bs_op_begin(v->ctx);
+    if (!v || !v->ctx || !d_verts || !n_verts) return BS_ERR_INVALID;
+    BS_ENTER(v->ctx);
     return bs_dc_impl(v, voxel_size, d_verts, n_verts);
 }
 bs_status bs_mesh_dc(const bs_volume* v, float voxel_size, float** verts, size_t* n_verts) {
-    if (!v || !verts || !n_verts) return BS_ERR_INVALID;
+    if (!v || !v->ctx || !verts || !n_verts) return BS_ERR_INVALID;
+    BS_ENTER(v->ctx);  // extraction + read-back under one lock
     const float* d = nullptr; size_t n = 0;
     BS_TRY(bs_mesh_dc_device(v, voxel_size, &d, &n));
     return verts_to_host(v->ctx, d, n, verts, n_verts);
@@ -433,8 +444,8 @@ bs_status bs_mesh_dc(const bs_volume* v, float voxel_size, float** verts, size_t
 // ---- CSG / offset -------------------------------------------------------------------------------------------
 static bs_status csg_entry(bs_volume* a, bs_volume* b, int op, bs_volume** out) {
     if (out) *out = nullptr;
-    if (!a || !b || !out || a == b || a->ctx != b->ctx) { bs_volume_free(a); if (b != a) bs_volume_free(b); return BS_ERR_INVALID; }
-    cudaSetDevice(a->ctx->device); bs_op_begin(a->ctx);
+    if (!a || !b || !out || a == b || !a->ctx || a->ctx != b->ctx) { bs_volume_free(a); if (b != a) bs_volume_free(b); return BS_ERR_INVALID; }
+    BS_ENTER(a->ctx);
     if (a->owned || b->owned) { bs_status e = bs_fail(a->ctx, BS_ERR_UNSUPPORTED, "CSG on a brick-sharded volume (DESIGN.md, Multi-GPU)"); bs_volume_free(a); bs_volume_free(b); return e; }
     bs_status s = bs_csg_impl(a, b, op, out);
     bs_volume_free(a); bs_volume_free(b);
@@ -445,8 +456,8 @@ bs_status bs_volume_subtract(bs_volume* a, bs_volume* b, bs_volume** out) { retu
 bs_status bs_volume_intersect(bs_volume* a, bs_volume* b, bs_volume** out) { return csg_entry(a, b, 2, out); }
 bs_status bs_volume_offset(bs_volume* a, float distance, bs_volume** out) {
     if (out) *out = nullptr;
-    if (!a || !out) { bs_volume_free(a); return BS_ERR_INVALID; }
-    cudaSetDevice(a->ctx->device); bs_op_begin(a->ctx);
+    if (!a || !out || !a->ctx) { bs_volume_free(a); return BS_ERR_INVALID; }
+    BS_ENTER(a->ctx);
     if (a->owned) { bs_status e = bs_fail(a->ctx, BS_ERR_UNSUPPORTED, "offset does not shard: the sweep wavefronts cross slabs (DESIGN.md, Multi-GPU)"); bs_volume_free(a); return e; }
     bs_status s = bs_offset_impl(a, distance, out);
     bs_volume_free(a);
@@ -457,7 +468,7 @@ bs_status bs_volume_offset(bs_volume* a, float distance, bs_volume** out) {
 bs_status bs_volume_from_voxels(bs_context* ctx, const int32_t* ijk, const float* values, size_t m, float voxel_size, bs_volume** out) {
     if (!ctx || !out || (m && (!ijk || !values))) return BS_ERR_INVALID;
     *out = nullptr;
-    cudaSetDevice(ctx->device); bs_op_begin(ctx);
+    BS_ENTER(ctx);
     if (m == 0) return bs_volume_empty(ctx, voxel_size, out);
     int32_t* d_ijk = nullptr; float* d_val = nullptr;
     BS_TRY(bs_alloc(ctx, &d_ijk, m * 3)); BS_TRY(bs_alloc(ctx, &d_val, m));
@@ -470,19 +481,19 @@ bs_status bs_volume_from_voxels(bs_context* ctx, const int32_t* ijk, const float
 }
 bs_status bs_volume_sphere(bs_context* ctx, float voxel_size, float radius, const float origin[3], bs_volume** out) {
     if (!ctx || !out || !origin) return BS_ERR_INVALID;
-    cudaSetDevice(ctx->device); bs_op_begin(ctx);
+    BS_ENTER(ctx);
     float p[7] = {radius, origin[0], origin[1], origin[2], 0, 0, 0};
     return bs_builder_impl(ctx, 0, voxel_size, p, out);
 }
 bs_status bs_volume_cuboid(bs_context* ctx, float voxel_size, const float mn[3], const float mx[3], bs_volume** out) {
     if (!ctx || !out || !mn || !mx) return BS_ERR_INVALID;
-    cudaSetDevice(ctx->device); bs_op_begin(ctx);
+    BS_ENTER(ctx);
     float p[7] = {mn[0], mn[1], mn[2], mx[0], mx[1], mx[2], 0};
     return bs_builder_impl(ctx, 1, voxel_size, p, out);
 }
 bs_status bs_volume_iwp(bs_context* ctx, float voxel_size, const float mn[3], const float mx[3], float cell_size, bs_volume** out) {
     if (!ctx || !out || !mn || !mx) return BS_ERR_INVALID;
-    cudaSetDevice(ctx->device); bs_op_begin(ctx);
+    BS_ENTER(ctx);
     float p[7] = {mn[0], mn[1], mn[2], mx[0], mx[1], mx[2], cell_size};
     return bs_builder_impl(ctx, 2, voxel_size, p, out);
 }

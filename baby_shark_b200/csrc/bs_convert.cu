@@ -574,9 +574,9 @@ __global__ void k_counts(const float* values, const unsigned long long* masks, s
 }  // namespace
 
 extern "C" bs_status bs_volume_counts(const bs_volume* v, size_t* n_bricks, size_t* n_active, size_t* n_negative, size_t* n_tiles) {
-    if (!v) return BS_ERR_INVALID;
+    if (!v || !v->ctx) return BS_ERR_INVALID;
     bs_context* ctx = v->ctx;
-    cudaSetDevice(ctx->device);
+    BS_ENTER(ctx);
     unsigned long long* d = nullptr; unsigned long long h[2] = {0, 0};
     BS_TRY(bs_alloc(ctx, &d, 2));
     BS_CUDA(ctx, cudaMemsetAsync(d, 0, 16, ctx->stream));

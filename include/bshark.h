@@ -16,7 +16,12 @@
  *  - There is NO CPU fallback: without a CUDA device every entry point returns BS_ERR_NO_DEVICE.
  *  - Voxel indices must lie in [-2^20, 2^20) per axis (BS_ERR_RANGE otherwise); the reference is
  *    unbounded (isize indices, BTreeMap root).
- *  - One in-flight call per context; handles may move between host threads.
+ *  - Every entry point locks its context for the duration of the call: handles may be shared between host threads.
+ *    The result of a *_device extraction lives in a per-context buffer until the next extraction; a caller that pairs
+ *    bs_mesh_mc_device with bs_context_copy_out_verts from several threads serialises the pair itself (bs_mesh_mc /
+ *    bs_mesh_dc do both under one lock).
+ *  - bs_context_destroy with volumes still alive orphans them: bs_volume_free on such a handle is safe, everything else
+ *    is BS_ERR_INVALID.
  */
 #ifndef BSHARK_H
 #define BSHARK_H

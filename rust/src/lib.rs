@@ -10,8 +10,12 @@ use std::sync::OnceLock;
 pub type Vec3f = Vector3<f32>;
 
 struct Ctx(*mut ffi::bs_context);
+// The library serialises every call on a context with its own lock (bs_common.cuh BS_ENTER), so the handle may be shared.
+// A `*_device` extraction leaves its result in a per-context buffer until the next extraction: EXTRACT keeps
+// "extract, then copy out" one critical section across threads.
 unsafe impl Send for Ctx {}
 unsafe impl Sync for Ctx {}
+static EXTRACT: std::sync::Mutex<()> = std::sync::Mutex::new(());
 fn ctx() -> *mut ffi::bs_context {
     static CTX: OnceLock<Ctx> = OnceLock::new();
     CTX.get_or_init(|| {
@@ -118,6 +122,7 @@ impl MarchingCubesMesher {
     pub fn with_voxel_size(mut self, size: f32) -> Self { self.voxel_size = size; self }
     pub fn set_voxel_size(&mut self, size: f32) -> &mut Self { self.voxel_size = size; self }
     pub fn mesh(&mut self, sdf: &Volume) -> Vec<Vec3f> {
+        let _pair = EXTRACT.lock().unwrap_or_else(|e| e.into_inner());
         let (mut d, mut n) = (ptr::null(), 0usize);
         check(unsafe { ffi::bs_mesh_mc_device(sdf.h, self.voxel_size, &mut d, &mut n) });
         take_vertices(n)
@@ -130,6 +135,7 @@ impl Default for DualContouringMesher { fn default() -> Self { Self { voxel_size
 impl DualContouringMesher {
     pub fn with_voxel_size(mut self, voxel_size: f32) -> Self { self.voxel_size = voxel_size; self }
     pub fn mesh(&mut self, volume: &Volume) -> Option<Vec<Vec3f>> {
+        let _pair = EXTRACT.lock().unwrap_or_else(|e| e.into_inner());
         let (mut d, mut n) = (ptr::null(), 0usize);
         check(unsafe { ffi::bs_mesh_dc_device(volume.h, self.voxel_size, &mut d, &mut n) });  // panics where the reference panics
         Some(take_vertices(n))

@@ -45,3 +45,18 @@ def test_product_does_not_touch_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", "Makefile")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in text.lower() or f == "bs_stubs.cu" and False, "%s mentions the oracle" % f
+
+
+def test_rust_ffi_declarations_match_the_header():
+    # no Rust toolchain here: rust/src/ffi.rs is generated from include/bshark.h (tools/gen_ffi_rs.py) and must be current --
+    # every export declared, same order, same arity and pointer constness; lib.rs may only call what ffi.rs declares
+    import re
+    import subprocess
+    import sys
+    assert subprocess.call([sys.executable, os.path.join(ROOT, "tools", "gen_ffi_rs.py"), "--check"]) == 0, "run tools/gen_ffi_rs.py"
+    ffi = open(os.path.join(ROOT, "rust", "src", "ffi.rs")).read()
+    declared = {m.group(1): m.group(2).count(":") for m in re.finditer(r"pub fn (bs_\w+)\((.*?)\)", ffi)}
+    assert set(declared) == set(B.EXPORTS)
+    lib = open(os.path.join(ROOT, "rust", "src", "lib.rs")).read()
+    for name, args in re.findall(r"ffi::(bs_[a-z_0-9]+)\((.*?)\) \}", lib):
+        assert name in declared, name
