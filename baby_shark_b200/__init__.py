@@ -54,7 +54,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    path = path or LIB_PATH
+    path = path or os.environ.get("BSHARK_LIB") or LIB_PATH  # BSHARK_LIB: experiment builds (tools/, bench A/B runs)
     if not os.path.exists(path):
         raise ImportError("%s is missing: build it with `make -C baby_shark_b200/csrc` (there is no CPU fallback)" % path)
     L = C.CDLL(path)

@@ -230,7 +230,10 @@ __device__ __forceinline__ float point_triangle_distance(f3 a, f3 b, f3 c, f3 ab
 // them out round robin, so lanes stay busy although box sizes differ (a plain thread-per-sub-triangle loop ran at
 // 10 of 32 lanes: r1 ncu). Boxes wider than 9 voxels (large narrow bands) take the per-thread path.
 constexpr int EV_REC = 27;  // words per parked sub-triangle (odd: conflict-free when lanes read different records)
-__global__ void __launch_bounds__(TPB) k_eval(ConvertParams P) {
+#ifndef BS_EVAL_MINB
+#define BS_EVAL_MINB 4
+#endif
+__global__ void __launch_bounds__(TPB, BS_EVAL_MINB) k_eval(ConvertParams P) {
     __shared__ unsigned long long s_off[TPB + 1];
     __shared__ unsigned s_rec[TPB / 32][32 * EV_REC];
     __shared__ unsigned s_pre[TPB / 32][33];
@@ -354,6 +357,19 @@ __global__ void __launch_bounds__(TPB) k_eval(ConvertParams P) {
 // a voxel that close to the surface loses all six edges and is evaluated on its own, like the reference does.
 constexpr unsigned RASTER_SMALL = 256;  // columns a single thread walks; larger projections go to k_block_edges_big
 __device__ __forceinline__ double lat(int i, float vs) { return (double)__fmul_rn((float)i, vs); }
+// smallest index whose lattice position is >= x / largest index whose lattice position is <= x (positions are monotone in the index)
+__device__ __forceinline__ int lat_first(double x, double ivs, float vs) {
+    int i = (int)ceil(x * ivs);
+    while (lat(i - 1, vs) >= x) --i;
+    while (lat(i, vs) < x) ++i;
+    return i;
+}
+__device__ __forceinline__ int lat_last(double x, double ivs, float vs) {
+    int i = (int)floor(x * ivs);
+    while (lat(i + 1, vs) <= x) ++i;
+    while (lat(i, vs) > x) --i;
+    return i;
+}
 struct RasterTri {  // one triangle projected along axis A: coordinates (u, v, z) = (axis A+1, A+2, A)
     double U0, V0, Z0, U1, V1, Z1, U2, V2, Z2;
     double eps, umin, umax, vmin, vmax, zlo, zhi;       // zlo / zhi: extent along the axis, already widened by eps
@@ -379,11 +395,12 @@ template <int A> __device__ __forceinline__ void raster_setup(const ConvertParam
     R.umin = fmin(R.U0, fmin(R.U1, R.U2)); R.umax = fmax(R.U0, fmax(R.U1, R.U2));
     R.vmin = fmin(R.V0, fmin(R.V1, R.V2)); R.vmax = fmax(R.V0, fmax(R.V1, R.V2));
     R.zlo = fmin(R.Z0, fmin(R.Z1, R.Z2)) - R.eps; R.zhi = fmax(R.Z0, fmax(R.Z1, R.Z2)) + R.eps;
-    const double lim = 1048576.0;
-    const double fu0 = floor((R.umin - R.eps) * R.ivs) - 1.0, fu1 = ceil((R.umax + R.eps) * R.ivs) + 1.0;
-    const double fv0 = floor((R.vmin - R.eps) * R.ivs) - 1.0, fv1 = ceil((R.vmax + R.eps) * R.ivs) + 1.0;
-    if (!(fu0 > -lim && fu1 < lim && fv0 > -lim && fv1 < lim)) { R.ok = false; return; }  // outside the index range: k_mark reports it
-    R.iu0 = (int)fu0; R.iv0 = (int)fv0; R.nu = (int)(fu1 - fu0) + 1; R.nv = (int)(fv1 - fv0) + 1;
+    const double lim = 1048000.0;
+    if (!(R.umin * R.ivs > -lim && R.umax * R.ivs < lim && R.vmin * R.ivs > -lim && R.vmax * R.ivs < lim && R.zlo * R.ivs > -lim && R.zhi * R.ivs < lim)) { R.ok = false; return; }  // outside the index range: k_mark reports it
+    // exactly the lattice lines whose f32 position lies in [min - eps, max + eps]
+    const int u0 = lat_first(R.umin - R.eps, R.ivs, P.vs), u1 = lat_last(R.umax + R.eps, R.ivs, P.vs);
+    const int v0 = lat_first(R.vmin - R.eps, R.ivs, P.vs), v1 = lat_last(R.vmax + R.eps, R.ivs, P.vs);
+    R.iu0 = u0; R.iv0 = v0; R.nu = max(0, u1 - u0 + 1); R.nv = max(0, v1 - v0 + 1);
     R.du0 = e1u; R.dv0 = e1v; R.du1 = e3u; R.dv1 = e3v; R.du2 = -e2u; R.dv2 = -e2v;
     const double len0 = (double)sqrtf((float)(e1u * e1u + e1v * e1v)) * 1.0001, len1 = (double)sqrtf((float)(e3u * e3u + e3v * e3v)) * 1.0001, len2 = (double)sqrtf((float)(e2u * e2u + e2v * e2v)) * 1.0001;
     R.m0 = R.eps * len0; R.m1 = R.eps * len1; R.m2 = R.eps * len2;
@@ -412,7 +429,6 @@ template <int A> __device__ __forceinline__ void raster_block(const ConvertParam
 }
 template <int A> __device__ __forceinline__ void raster_column(const ConvertParams& P, unsigned long long* blk, const RasterTri& R, int iu, int iv, double pu, unsigned long long& last_key, unsigned& last_slot) {
     const double pv = lat(iv, P.vs);
-    if (pv < R.vmin - R.eps || pv > R.vmax + R.eps) return;
     double lo = R.zlo, hi = R.zhi;
     if (!R.thin) {
         if (R.s * (R.du0 * (pv - R.V0) - R.dv0 * (pu - R.U0)) < -R.m0) return;  // outside the projection inflated by eps
@@ -422,9 +438,10 @@ template <int A> __device__ __forceinline__ void raster_column(const ConvertPara
         const double a = fmax(lo, zc - R.dz), b = fmin(hi, zc + R.dz);
         if (a <= b) { lo = a; hi = b; }  // (else: numerically impossible; stay with the full extent)
     } else if (fabs(R.lu * (pv - R.lV) - R.lv * (pu - R.lU)) > R.lm) return;
-    const int k0 = (int)floor(lo * R.ivs) - 1, k1 = (int)floor(hi * R.ivs) + 1;
-    for (int k = k0; k <= k1; ++k)
-        if (lat(k + 1, P.vs) >= lo && lat(k, P.vs) <= hi) raster_block<A>(P, blk, iu, iv, k, last_key, last_slot);
+    // lattice edges [k, k + 1] that overlap [lo, hi]: from the last index at or below lo (minus one when lo is a lattice
+    // position itself) to the last index at or below hi
+    const int k0 = lat_first(lo, R.ivs, P.vs) - 1, k1 = lat_last(hi, R.ivs, P.vs);
+    for (int k = k0; k <= k1; ++k) raster_block<A>(P, blk, iu, iv, k, last_key, last_slot);
 }
 template <int A> __device__ __forceinline__ void raster_small(const ConvertParams& P, unsigned long long* blk, size_t t, unsigned long long g, unsigned long long* big_list, unsigned* n_big, unsigned big_cap) {
     RasterTri R;
@@ -438,7 +455,6 @@ template <int A> __device__ __forceinline__ void raster_small(const ConvertParam
     for (int i = 0; i < R.nu; ++i) {
         const int iu = R.iu0 + i;
         const double pu = lat(iu, P.vs);
-        if (pu < R.umin - R.eps || pu > R.umax + R.eps) continue;
         for (int j = 0; j < R.nv; ++j) raster_column<A>(P, blk, R, iu, R.iv0 + j, pu, last_key, last_slot);
     }
 }
@@ -450,15 +466,14 @@ template <int A> __device__ __forceinline__ void raster_big(const ConvertParams&
     unsigned long long last_key = BS_KEY_INVALID; unsigned last_slot = 0xFFFFFFFFu;
     for (unsigned long long c = threadIdx.x; c < ncols; c += blockDim.x) {
         const int iu = R.iu0 + (int)(c / (unsigned)R.nv), iv = R.iv0 + (int)(c % (unsigned)R.nv);
-        const double pu = lat(iu, P.vs);
-        if (pu < R.umin - R.eps || pu > R.umax + R.eps) continue;
-        raster_column<A>(P, blk, R, iu, iv, pu, last_key, last_slot);
+        raster_column<A>(P, blk, R, iu, iv, lat(iu, P.vs), last_key, last_slot);
     }
 }
 __global__ void __launch_bounds__(128, 3) k_block_edges(ConvertParams P, unsigned long long* blk, unsigned long long* big_list, unsigned* n_big, unsigned big_cap) {
+    // one thread per (axis, triangle); the axis is the SLOW index, so a warp runs one instantiation of the rasteriser
     const size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (g >= P.n_tris * 3) return;
-    const size_t t = g / 3; const int a = (int)(g % 3);
+    const size_t t = g % P.n_tris; const int a = (int)(g / P.n_tris);
     if (P.use_clip) {  // sharded: the triangle's box (plus slack) misses every brick this rank keeps
         const float* p = P.tris + 9 * t;
         for (int d = 0; d < 3; ++d) {
@@ -475,7 +490,7 @@ __global__ void __launch_bounds__(256) k_block_edges_big(ConvertParams P, unsign
     const unsigned n = min(*n_big, big_cap);
     for (unsigned i = blockIdx.x; i < n; i += gridDim.x) {
         const unsigned long long g = big_list[i];
-        const size_t t = (size_t)(g / 3); const int a = (int)(g % 3);
+        const size_t t = (size_t)(g % P.n_tris); const int a = (int)(g / P.n_tris);
         if (a == 0) raster_big<0>(P, blk, t); else if (a == 1) raster_big<1>(P, blk, t); else raster_big<2>(P, blk, t);
     }
 }

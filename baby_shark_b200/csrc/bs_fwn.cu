@@ -705,10 +705,11 @@ struct HeavySplit { unsigned repl, n_hitems; const HeavyRoots* roots; const unsi
 // one warp per heavy brick. Entries are expanded by SIZE (leaves under a Karras node i: |i - other[i]| + 1): every round
 // replaces the internal entries holding more than 1/256 of the list's leaves by the entries of their records, so the
 // fan of slivers ends up in a few hundred pieces of similar size that the replicas share round-robin.
-__global__ void __launch_bounds__(128) k_expand_roots(Tree T, const int* __restrict__ other, const unsigned* __restrict__ heavy_bricks, unsigned n_heavy, const BrickOut* __restrict__ brick_out, HeavyRoots* out) {
+__global__ void __launch_bounds__(128) k_expand_roots(Tree T, const int* __restrict__ other, const unsigned* __restrict__ heavy_bricks, unsigned n_heavy, const BrickOut* __restrict__ brick_out, const unsigned* __restrict__ n_chunks, HeavyRoots* out) {
     __shared__ unsigned s_l[4][2][HEAVY_CAP];
     const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5, h = blockIdx.x * 4 + w;
     if (h >= n_heavy) return;
+    if (n_chunks[heavy_bricks[h]] == 0) { if (lane == 0) out[h].n = 0; return; }  // no work items: the brick pass skipped this brick
     const BrickOut* bo = brick_out + heavy_bricks[h];
     unsigned n = bo->n_roots;
     if (n == 0xFFFFFFFFu) { if (lane == 0) s_l[w][0][0] = T.root; n = 1; }
@@ -1048,7 +1049,7 @@ bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_v
             else bs_count_launch(), k_brick_pass<false><<<bs_blocks(n_blist, BP_WARPS), 32 * BP_WARPS, 0, st>>>(T, vol->keys, n_blist, d_blist, vol->voxel_size, kappa, d_bo, nullptr);
         }
         if (!ctx->count_work) bs_mark(ctx, "sign_brick_pass_ms");
-        if (n_hitems) bs_count_launch(), k_expand_roots<<<bs_blocks(n_heavy, 4), 128, 0, st>>>(T, TB.other, d_heavy, n_heavy, d_bo, d_hr);
+        if (n_hitems) bs_count_launch(), k_expand_roots<<<bs_blocks(n_heavy, 4), 128, 0, st>>>(T, TB.other, d_heavy, n_heavy, d_bo, d_nchunks, d_hr);
         if (n_items) {
             if (ctx->count_work) bs_count_launch(), k_sign<true, BS_VPL><<<blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(T, vol->values, item_masks, n_items, d_item_brick, d_chunk_off, vol->keys, vol->voxel_size, d_bo, d_cnt, H);
             else bs_count_launch(), k_sign<false, BS_VPL><<<blocks, 32 * WARPS_PER_BLOCK, 0, st>>>(T, vol->values, item_masks, n_items, d_item_brick, d_chunk_off, vol->keys, vol->voxel_size, d_bo, nullptr, H);

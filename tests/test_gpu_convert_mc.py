@@ -180,6 +180,7 @@ def test_heavy_brick_split_gives_the_same_volume(bs, oracle, shift, monkeypatch)
     # (bs_fwn.cu "heavy bricks"); BSHARK_HEAVY_SHIFT lowers the threshold so that small test meshes take that path
     from baby_shark_b200 import synth
     monkeypatch.setenv("BSHARK_HEAVY_SHIFT", str(shift))
+    monkeypatch.setenv("BSHARK_NO_BRUTE", "1")  # the split belongs to the LBVH traversal: keep closed meshes on it
     for cfg, scale in ((5, 0.05), (3, 0.06)):
         tris, vs, _ = synth.config_mesh(cfg, scale)
         g = bs.MeshToVolume().with_voxel_size(vs).convert(tris)
@@ -192,6 +193,7 @@ def test_heavy_brick_split_gives_the_same_volume(bs, oracle, shift, monkeypatch)
 
 
 def test_heavy_split_on_bunny_matches_unsplit_signs(bs, bunny, monkeypatch):
+    monkeypatch.setenv("BSHARK_NO_BRUTE", "1")
     a = bs.MeshToVolume().with_voxel_size(0.5).convert(bunny).download()
     monkeypatch.setenv("BSHARK_HEAVY_SHIFT", "5")
     b = bs.MeshToVolume().with_voxel_size(0.5).convert(bunny).download()
