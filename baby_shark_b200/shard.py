@@ -17,28 +17,36 @@ def slab_bounds(n_bricks, rank, world):
     return n_bricks * rank // world, n_bricks * (rank + 1) // world
 
 
-def all_gather_varlen(local, group=None, out=None):
+def all_gather_varlen(local, group=None, out=None, counts=None):
     """local: 1-D tensor (any length, same dtype/device on all ranks) -> (concatenation in rank order, counts list).
-    One tiny all-gather of the counts, then every rank's slice is broadcast straight into its final place of `out`
-    (reused if large enough): no padding, no staging copies, no concatenation pass."""
+    `counts` (per-rank lengths) may be passed when the caller already knows them (a steady workload: the sizes of the
+    previous step) -- then there is no count exchange and no host synchronisation at all. Every rank's slice travels
+    straight into its final place of `out` (reused if large enough): NCCL takes the uneven all-gather as ONE grouped launch
+    of broadcasts; gloo (CPU tests) gets one broadcast per rank. No padding, no staging copies, no concatenation pass."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    n = torch.tensor([local.numel()], dtype=torch.int64, device=local.device)
-    counts = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(counts, n, group=group)
-    counts = [int(c.item()) for c in counts]
+    if counts is None:
+        n = torch.tensor([local.numel()], dtype=torch.int64, device=local.device)
+        got = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(got, n, group=group)
+        counts = [int(c.item()) for c in got]
+    assert counts[rank] == local.numel(), "stale counts: %d expected, %d local" % (counts[rank], local.numel())
     total = sum(counts)
     if out is None or out.numel() < total or out.dtype != local.dtype or out.device != local.device:
         out = torch.empty(max(total, 1), dtype=local.dtype, device=local.device)
     offs = [0]
     for c in counts:
         offs.append(offs[-1] + c)
-    out[offs[rank]:offs[rank + 1]].copy_(local)
-    works = []
-    for r in range(world):
-        if counts[r]:
-            src = dist.get_global_rank(group, r) if group is not None else r
-            works.append(dist.broadcast(out[offs[r]:offs[r + 1]], src=src, group=group, async_op=True))
-    for w in works:
-        w.wait()
+    views = [out[offs[r]:offs[r + 1]] for r in range(world)]
+    if dist.get_backend(group) == "nccl" and all(counts):
+        dist.all_gather(views, local, group=group)
+    else:
+        views[rank].copy_(local)
+        works = []
+        for r in range(world):
+            if counts[r]:
+                src = dist.get_global_rank(group, r) if group is not None else r
+                works.append(dist.broadcast(views[r], src=src, group=group, async_op=True))
+        for w in works:
+            w.wait()
     return out[:total], counts

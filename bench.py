@@ -373,15 +373,26 @@ def main():
     fp = C.POINTER(C.c_float)
 
     from baby_shark_b200.shard import all_gather_varlen
-    gather_buf = {"t": None}
+    gather_buf = {"out": None, "counts": None}
 
-    def gather(n_floats):
-        """the path's one exchange: all-gather(v) of the compacted triangle buffers over NVLink (NCCL)"""
-        if gather_buf["t"] is None or gather_buf["t"].numel() < n_floats:
-            gather_buf["t"] = torch.empty(int(n_floats * 1.2) + 16, dtype=torch.float32, device="cuda")
-        ctx.check(L.bs_context_copy_out_verts_device(ctx._h, C.c_void_p(gather_buf["t"].data_ptr()), n_floats))
-        full, _ = all_gather_varlen(gather_buf["t"][:n_floats], out=gather_buf.get("out"))
-        gather_buf["out"] = full
+    class _DeviceF32:
+        """zero-copy torch view of a device buffer the library owns (CUDA array interface)"""
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+    def gather(dv_ptr, n_floats):
+        """the path's one exchange: all-gather(v) of the compacted triangle buffers over NVLink (NCCL), straight out of the
+        library's result buffer into the final one, on the library's stream (so the stream's events time it). The per-rank
+        sizes of a steady workload are those of the previous step: no count exchange, no host synchronisation."""
+        local = torch.as_tensor(_DeviceF32(dv_ptr, n_floats), device="cuda")
+        counts = gather_buf["counts"]
+        if counts is not None and counts[rank] != n_floats:
+            counts = None
+        with torch.cuda.stream(stream):
+            full, counts = all_gather_varlen(local, out=gather_buf["out"], counts=counts)
+        if gather_buf["out"] is None or gather_buf["out"].data_ptr() != full.data_ptr():
+            gather_buf["out"] = torch.empty(int(full.numel() * 1.1) + 16, dtype=torch.float32, device="cuda")
+        gather_buf["counts"] = counts
         return full
 
     def step_device():
@@ -393,31 +404,60 @@ def main():
         L.bs_volume_free(h)
         ctx.check(st)
         if world > 1:
-            gather(nv.value * 3)
+            gather(dv.value, nv.value * 3)
         return dv.value, nv.value, None
 
     h_out = None
+    shm = {"t": None, "offs": None, "path": None}
+    d_in = torch.empty_like(d_tris) if world > 1 else None
+
+    def shared_host_buffer(n_floats_total):
+        """N > 1: one page-locked host buffer shared by all ranks (a /dev/shm file mapped and cudaHostRegister-ed by every
+        process): each rank copies ITS slice of the result to the host over its own PCIe link, rank 0 reads the whole mesh."""
+        import mmap
+        path = "/dev/shm/bshark_bench_%s_%d" % (os.environ.get("MASTER_PORT", "0"), n_floats_total)
+        nbytes = max(4, n_floats_total * 4)
+        if rank == 0:
+            with open(path, "wb") as f:
+                f.truncate(nbytes)
+        dist.barrier()
+        f = open(path, "r+b")
+        mm = mmap.mmap(f.fileno(), nbytes)
+        arr = np.frombuffer(mm, dtype=np.float32)
+        t = torch.from_numpy(arr)
+        rc = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), nbytes, 0)
+        assert int(rc) == 0, "cudaHostRegister failed: %s" % rc
+        dist.barrier()
+        if rank == 0:
+            os.unlink(path)
+        return t
 
     def step_e2e():
         nonlocal h_out
         h = C.c_void_p()
         if world == 1:
             ctx.check(L.bs_mesh_to_volume(ctx._h, C.cast(h_tris.data_ptr(), fp), n_tris, vs, 0, C.byref(h)))
-        else:  # replicated mesh: every rank uploads it, then keeps its slab
-            d = h_tris.to("cuda", non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            ctx.check(L.bs_mesh_to_volume_sharded(ctx._h, C.c_void_p(d.data_ptr()), n_tris, vs, 0, rank, world, C.byref(h)))
+        else:  # replicated mesh: uploaded once (rank 0), broadcast over NVLink, every rank keeps its slab
+            with torch.cuda.stream(stream):
+                if rank == 0:
+                    d_in.copy_(h_tris, non_blocking=True)
+                dist.broadcast(d_in, src=0)
+            ctx.check(L.bs_mesh_to_volume_sharded(ctx._h, C.c_void_p(d_in.data_ptr()), n_tris, vs, 0, rank, world, C.byref(h)))
         dv, nv = C.c_void_p(), C.c_size_t()
         st = L.bs_mesh_mc_device(h, vs, C.byref(dv), C.byref(nv))
         L.bs_volume_free(h)
         ctx.check(st)
         n_floats = nv.value * 3
-        if world > 1:  # gather on the device, then rank 0 reads the whole mesh back
-            full = gather(n_floats)
-            if rank == 0:
-                if h_out is None or h_out.numel() < full.numel():
-                    h_out = torch.empty(int(full.numel() * 1.1) + 16, dtype=torch.float32).pin_memory()
-                h_out[: full.numel()].copy_(full, non_blocking=False)
+        if world > 1:  # every rank writes its slice of the soup into the shared pinned host buffer
+            if shm["t"] is None or shm["counts"][rank] != n_floats:
+                cnt = torch.tensor([n_floats], dtype=torch.int64, device="cuda")
+                got = [torch.zeros_like(cnt) for _ in range(world)]
+                dist.all_gather(got, cnt)
+                shm["counts"] = [int(c.item()) for c in got]
+                shm["offs"] = [sum(shm["counts"][:r]) for r in range(world + 1)]
+                shm["t"] = shared_host_buffer(shm["offs"][world])
+            ctx.check(L.bs_context_copy_out_verts(ctx._h, C.c_void_p(shm["t"].data_ptr() + 4 * shm["offs"][rank]), n_floats))
+            dist.barrier()  # the step is done when every slice has landed
             return nv.value
         if h_out is None or h_out.numel() < n_floats:
             h_out = torch.empty(int(n_floats * 1.1) + 16, dtype=torch.float32).pin_memory()
@@ -505,8 +545,8 @@ def main():
         except Exception:
             golden = None
         if golden is not None:
-            n_fl = int(gather_buf["out"].numel()) if world > 1 else int(nv_e2e) * 3
-            got = verify.fingerprint_soup(h_out[:n_fl].numpy())
+            host = shm["t"][: shm["offs"][world]] if world > 1 else h_out[: int(nv_e2e) * 3]
+            got = verify.fingerprint_soup(host.numpy())
             if world == 1:
                 hv = C.c_void_p()
                 ctx.check(L.bs_mesh_to_volume_device(ctx._h, C.c_void_p(d_tris.data_ptr()), n_tris, vs, 0, C.byref(hv)))
@@ -586,22 +626,37 @@ def main():
             fl = 80.0 * work["n_eval"]
             rl.append({"kernel": "k_eval (point-triangle distances, scatter-min)", "bound": "fp32", "achieved": fl / (conv_ms["udf_ms"] * 1e-3) / 1e12,
                        "peak": fp32_peak, "unit": "TFLOP/s", "ms": conv_ms["udf_ms"], "algorithmic": "80 FLOP x n_eval=%d" % work["n_eval"], "traffic": None})
-        if "sign_ms" in conv_ms and work.get("fwn_voxels"):
+        if "sign_ms" in conv_ms and work.get("fwn_voxels") and not work.get("sign_propagation"):
             fl = 60.0 * work["fwn_far"] + 100.0 * work["fwn_exact_tris"] + 10.0 * work["fwn_visits"]
             rl.append({"kernel": "k_sign (fast winding numbers)", "bound": "fp32", "achieved": fl / (conv_ms["sign_ms"] * 1e-3) / 1e12, "peak": fp32_peak,
                        "unit": "TFLOP/s", "ms": conv_ms["sign_ms"], "traffic": None,
                        "algorithmic": "per voxel: %.1f visits, %.1f far, %.1f exact tris" % tuple(work[k] / work["fwn_voxels"] for k in ("fwn_visits", "fwn_far", "fwn_exact_tris"))})
+        if work.get("sign_propagation") and "sign_block_edges_ms" in conv_ms:
+            # closed mesh: signs by propagation. The stage is bounded by instruction issue (fp64 predicates per projected lattice
+            # column, bit-parallel flood fill); reported against HBM with the bytes it has to move as an honest lower bound.
+            sp_ms = sum(conv_ms.get(k, 0.0) for k in ("sign_block_edges_ms", "sign_components_ms", "sign_brute_ms", "sign_broadcast_ms"))
+            nb = work.get("n_bricks", 0.0)
+            by = 36.0 * n_tris * 2 + nb * (192 * 2 + 64 + 800) + 8.0 * work.get("n_active", 0.0)
+            rl.append({"kernel": "k_block_edges + k_sp_bricks + k_sp_faces + k_sp_flatten + k_sp_stream + k_sp_broadcast (sign propagation)", "bound": "hbm", "achieved": by / (sp_ms * 1e-3) / 1e9,
+                       "peak": hbm_peak, "unit": "GB/s", "ms": sp_ms, "traffic": None, "peak_source": hbm_src,
+                       "algorithmic": "72 B x n_tris (two passes over the triangles) + 1248 B x n_bricks (edge masks, component tables) + 8 B x n_active (sign write-back); %d representatives evaluated" % int(work.get("n_sign_seeds", 0))})
         if "mc_emit_ms" in mc_ms:
             nb = work.get("n_bricks", 0.0)
             by = nb * (2112 + 868) + 36.0 * (n_verts_local / 3.0)
             rl.append({"kernel": "k_mc_fused (stage + classify + MC33 + look-back + emit, one pass)", "bound": "hbm", "achieved": by / (mc_ms["mc_emit_ms"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                        "ms": mc_ms["mc_emit_ms"], "algorithmic": "n_bricks x 2980 B + 36 B x n_out_tris", "traffic": None, "peak_source": hbm_src})
-        # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` captures of
-        # this exact workload (profiles/r1_final_sign_kernels_ncu_summary.txt, r1_mc_ncu_summary.txt, r1_k_mc_fused_ncu_summary.txt)
+        # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum): read from the committed ncu capture of this exact
+        # workload (profiles/r2_ncu_traffic_cfg5.json, written by tools/ncu_traffic.py from an `ncu --set full` report)
         if args.config == 5 and args.scale == 1.0 and world == 1:
-            ncu_traffic = {"k_eval": 1.191240e9 + 529.150720e6, "k_sign": 2.388182e9 + 285.550336e6, "k_mc_fused": 625.867776e6 + 1.209232e9}
-            for r in rl:
-                r["traffic"] = ncu_traffic.get(r["kernel"].split(" ")[0])
+            try:
+                tr = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_traffic_cfg5.json")))["kernels"]
+                for r in rl:
+                    k = tr.get(r["kernel"].split(" ")[0])
+                    r["traffic"] = k["dram_bytes_per_launch"] if k else None
+                    if k:
+                        r["traffic_source"] = "profiles/r2_ncu_traffic_cfg5.json"
+            except Exception:
+                pass
         for r in rl:
             r["frac"] = r["achieved"] / r["peak"]
             if r["bound"] == "fp32":
@@ -617,8 +672,8 @@ def main():
                        "parallelism": "brick slabs x%d, mesh replicated" % world, "sign_propagation": bool(work.get("sign_propagation", 0.0))},
             "remesh_ms": ms_per_step, "tris_per_s": (n_verts / 3.0) / (ms_per_step * 1e-3), "n_active_voxels": n_active, "n_out_triangles": n_verts / 3.0,
             "step_ms": step_ms, "stage_ms": stage_all, "stage_ms_per_rank": per_rank, "work": work,
-            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": int(tris.nbytes) * world, "d2h_bytes_per_step": int(n_verts * 12),
-                    "what": "pinned host triangles in (every rank uploads the mesh), all output vertices back on the host of rank 0"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": int(tris.nbytes), "d2h_bytes_per_step": int(n_verts * 12),
+                    "what": "pinned host triangles in (N > 1: uploaded by rank 0, broadcast over NVLink), all output vertices back in host memory (N > 1: every rank copies its slice into one shared page-locked buffer)"},
             "e2e_indexed": None, "gpu_launches": None, "clocks": clocks,
             "roofline": dominant, "rooflines": rl,
             "verified": verify_out["verified"] if verify_out else None, "verify": verify_out,
