@@ -4,10 +4,11 @@
 // find_feature_point :429-458), quads (TriangulateVisitor :93-172), offsets tables :389-423.
 //
 // The reference keeps Hermite data and cell points in three + one auxiliary sparse trees behind mutexes. Here:
-//   pass A  one CTA per brick stages the brick with an 11^3 halo ([-1, +9] per axis) in shared memory; one
-//           thread per cell re-derives the Hermite samples of its 12 edges (gradients by central / one-sided
-//           differences from the staged values) and runs the 50-iteration particle solve in registers; the
-//           feature point goes to a per-brick array (512 x float3) with a validity mask. The same pass checks,
+//   pass A  one CTA per brick stages the brick with an 11^3 halo ([-1, +9] per axis) in shared memory; the cells are
+//           classified, the surface cells (all 8 corners active, mixed signs) compacted, and dense lanes re-derive the
+//           Hermite samples of a cell's 12 edges (gradients by central / one-sided differences from the staged values)
+//           and run the 50-iteration particle solve in registers; the feature point goes to a per-brick array
+//           (512 x float3) with a validity mask. The same pass checks,
 //           for every sign-change edge the brick owns, that both end points have a neighbour on every axis
 //           (the reference hits unreachable!() otherwise, :340).
 //   pass B  one CTA per brick, one thread per voxel: for +x/+y/+z sign-change edges fetch the four surrounding
@@ -53,7 +54,7 @@ __device__ __forceinline__ float grad(const Halo& h, int x, int y, int z, int ax
     return 0.f;
 }
 // intersection + normal of the edge (lower voxel local (x,y,z), dir); false if no sign change (:266-307)
-__device__ bool hermite(const Halo& h, const int* org, int x, int y, int z, int dir, f3& point, f3& normal, bool* bad) {
+__device__ __noinline__ bool hermite(const Halo& h, const int* org, int x, int y, int z, int dir, f3& point, f3& normal, bool* bad) {
     const int x2 = x + (dir == 0), y2 = y + (dir == 1), z2 = z + (dir == 2);
     const float v1 = h.v[hidx(x, y, z)], v2 = h.v[hidx(x2, y2, z2)];
     if (((__float_as_uint(v1) ^ __float_as_uint(v2)) >> 31) == 0) return false;
@@ -70,96 +71,143 @@ __device__ bool hermite(const Halo& h, const int* org, int x, int y, int z, int 
     return true;
 }
 
-__global__ void __launch_bounds__(512) k_dc_cells(const u64* __restrict__ keys, const float* __restrict__ values, const u64* __restrict__ masks, size_t n,
-                                                  const unsigned char* __restrict__ owned, float* cell_pts /*n*512*3*/, u64* cell_valid /*n*8*/, int* flags) {
+// 27-neighbourhood of every brick (index into the sorted brick list, -1 = absent), one thread per (brick, neighbour): the
+// binary searches run at throughput here instead of as a dependent chain at the head of every k_dc_cells CTA
+__global__ void k_dc_neighbours(const u64* __restrict__ keys, size_t n, int* nbr /*[n][27]*/) {
+    const size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (g >= n * 27) return;
+    const size_t b = g / 27; const unsigned t = (unsigned)(g % 27);
+    if (t == 13) { nbr[g] = (int)b; return; }
+    int bx, by, bz; bs_key_brick(keys[b], bx, by, bz);
+    const int nx = bx + (int)(t / 9) - 1, ny = by + (int)((t / 3) % 3) - 1, nz = bz + (int)(t % 3) - 1;
+    const bool ok = nx >= BS_BRICK_MIN && nx <= BS_BRICK_MAX && ny >= BS_BRICK_MIN && ny <= BS_BRICK_MAX && nz >= BS_BRICK_MIN && nz <= BS_BRICK_MAX;
+    nbr[g] = ok ? (int)find_key(keys, n, bs_brick_key(nx, ny, nz)) : -1;
+}
+
+// One CTA of 128 threads per brick. Only ~10 % of a band brick's cells hold a sign change: the cells are classified first
+// (4 per thread), the surface cells are compacted in shared memory, and the Hermite samples + 50-iteration solve run on
+// dense lanes; other cells cost a classification and nothing else (their slot of cell_pts is never read: k_dc_quads
+// tests cell_valid first).
+constexpr int DC_TPB = 128;
+__global__ void __launch_bounds__(DC_TPB, 6) k_dc_cells(const u64* __restrict__ keys, const float* __restrict__ values, const u64* __restrict__ masks, size_t n, const int* __restrict__ nbr,
+                                                        const unsigned char* __restrict__ owned, float* cell_pts /*n*512*3*/, u64* cell_valid /*n*8*/, int* flags) {
     __shared__ float s_v[HN];
     __shared__ unsigned char s_a[HN];
-    __shared__ long long s_nb[27];
+    __shared__ int s_nb[27];
     __shared__ int s_org[3];
     __shared__ unsigned s_bal[16];
+    __shared__ unsigned short s_list[512];
+    __shared__ float s_damp[50];  // 1 - it / 50 (:447), the same for every cell
     const size_t b = blockIdx.x;
     const unsigned t = threadIdx.x;
-    if (t < 27) {
-        int bx, by, bz; bs_key_brick(keys[b], bx, by, bz);
-        if (t == 13) { s_org[0] = bx << 3; s_org[1] = by << 3; s_org[2] = bz << 3; }
-        const int dx = (int)(t / 9) - 1, dy = (int)((t / 3) % 3) - 1, dz = (int)(t % 3) - 1;
-        const int nx = bx + dx, ny = by + dy, nz = bz + dz;
-        const bool ok = nx >= BS_BRICK_MIN && nx <= BS_BRICK_MAX && ny >= BS_BRICK_MIN && ny <= BS_BRICK_MAX && nz >= BS_BRICK_MIN && nz <= BS_BRICK_MAX;
-        s_nb[t] = (t == 13) ? (long long)b : (ok ? find_key(keys, n, bs_brick_key(nx, ny, nz)) : -1);
-    }
+    if (t >= 64 && t < 114) s_damp[t - 64] = xsub(1.0f, xdiv((float)(t - 64), 50.0f));
+    if (t < 27) s_nb[t] = nbr[b * 27 + t];
+    if (t == 32) { int bx, by, bz; bs_key_brick(keys[b], bx, by, bz); s_org[0] = bx << 3; s_org[1] = by << 3; s_org[2] = bz << 3; }
     __syncthreads();
-    for (unsigned i = t; i < HN; i += 512) {
-        const int lx = i / (H * H), ly = (i / H) % H, lz = i % H;        // local; voxel offset = l - 1
-        const int ox = lx - 1, oy = ly - 1, oz = lz - 1;
-        const int nbx = ox < 0 ? 0 : (ox > 7 ? 2 : 1), nby = oy < 0 ? 0 : (oy > 7 ? 2 : 1), nbz = oz < 0 ? 0 : (oz > 7 ? 2 : 1);
-        const long long src = s_nb[(nbx * 3 + nby) * 3 + nbz];
-        float v = 0.f; unsigned char a = 0;
-        if (src >= 0) {
-            const unsigned off = ((ox & 7) << 6) | ((oy & 7) << 3) | (oz & 7);
-            a = (masks[src * 8 + (off >> 6)] >> (off & 63)) & 1;
-            v = values[src * 512 + off];
+    {   // stage the 11^3 halo: all loads of a thread are issued before the first store
+        constexpr int NQ = (HN + DC_TPB - 1) / DC_TPB;
+        float v[NQ]; u64 m[NQ]; unsigned sh[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const unsigned i = t + DC_TPB * q;
+            v[q] = 0.f; m[q] = 0; sh[q] = 0;
+            if (i < HN) {
+                const int lx = i / (H * H), ly = (i / H) % H, lz = i % H;        // local; voxel offset = l - 1
+                const int ox = lx - 1, oy = ly - 1, oz = lz - 1;
+                const int nbx = ox < 0 ? 0 : (ox > 7 ? 2 : 1), nby = oy < 0 ? 0 : (oy > 7 ? 2 : 1), nbz = oz < 0 ? 0 : (oz > 7 ? 2 : 1);
+                const int src = s_nb[(nbx * 3 + nby) * 3 + nbz];
+                if (src >= 0) {
+                    const unsigned off = ((ox & 7) << 6) | ((oy & 7) << 3) | (oz & 7);
+                    m[q] = masks[(size_t)src * 8 + (off >> 6)]; sh[q] = off & 63;
+                    v[q] = values[(size_t)src * 512 + off];
+                }
+            }
         }
-        s_v[i] = v; s_a[i] = a;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const unsigned i = t + DC_TPB * q;
+            if (i < HN) { s_v[i] = v[q]; s_a[i] = (unsigned char)((m[q] >> sh[q]) & 1ull); }
+        }
     }
     __syncthreads();
     const Halo h{s_v, s_a};
-    const int x = (t >> 6) + 1, y = ((t >> 3) & 7) + 1, z = (t & 7) + 1;  // local coords of this thread's voxel / cell origin
     bool bad = false;
-    // (b) every sign-change edge owned by this brick must have computable normals (else the reference panics)
-    if (s_a[hidx(x, y, z)]) {
-#pragma unroll
-        for (int dir = 0; dir < 3; ++dir) {
-            const int x2 = x + (dir == 0), y2 = y + (dir == 1), z2 = z + (dir == 2);
-            if (!s_a[hidx(x2, y2, z2)]) continue;
-            f3 p, nrm;
-            hermite(h, s_org, x, y, z, dir, p, nrm, &bad);
-        }
-    }
-    // (c) the cell whose corner 0 is this voxel (:187-240)
-    bool valid = true; unsigned neg = 0;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const int i = hidx(x + c_corner[c][0], y + c_corner[c][1], z + c_corner[c][2]);
-        valid = valid && s_a[i];
-        neg |= (__float_as_uint(s_v[i]) >> 31) << c;
-    }
-    valid = valid && neg != 0 && neg != 255;
-    f3 c{0.f, 0.f, 0.f};
-    if (valid) {
-        f3 pts[12], nrm[12]; int m = 0;
-        bool bad2 = false;  // edges owned by other bricks are checked by their owners
-        for (int e = 0; e < 12; ++e) {
-            f3 p, nn;
-            if (hermite(h, s_org, x + c_edge[e][0], y + c_edge[e][1], z + c_edge[e][2], c_edge[e][3], p, nn, &bad2)) { pts[m] = p; nrm[m] = nn; ++m; }
-        }
-        // find_feature_point (:429-458)
-        const float fm = (float)m;
-        for (int i = 0; i < m; ++i) c = xadd(c, pts[i]);
-        c = f3{xdiv(c.x, fm), xdiv(c.y, fm), xdiv(c.z, fm)};
-        for (int it = 0; it < 50; ++it) {
-            f3 force{0.f, 0.f, 0.f};
-            for (int i = 0; i < m; ++i) {
-                const f3 nneg = xscale(nrm[i], -1.0f);
-                force = xadd(force, xscale(nneg, xdot(nrm[i], xsub(c, pts[i]))));
+#pragma unroll 1  // (code size: the instruction cache, not the math, bounds this kernel when everything is unrolled)
+    for (int q = 0; q < 512 / DC_TPB; ++q) {
+        const unsigned c = t + DC_TPB * q;
+        const int x = (c >> 6) + 1, y = ((c >> 3) & 7) + 1, z = (c & 7) + 1;  // local coords of this voxel / cell origin
+        // (b) every sign-change edge owned by this brick must have computable normals (else the reference panics)
+        if (s_a[hidx(x, y, z)]) {
+#pragma unroll 1
+            for (int dir = 0; dir < 3; ++dir) {
+                const int x2 = x + (dir == 0), y2 = y + (dir == 1), z2 = z + (dir == 2);
+                if (!s_a[hidx(x2, y2, z2)]) continue;
+                if (((__float_as_uint(s_v[hidx(x, y, z)]) ^ __float_as_uint(s_v[hidx(x2, y2, z2)])) >> 31) == 0) continue;
+                f3 p, nrm;
+                hermite(h, s_org, x, y, z, dir, p, nrm, &bad);
             }
-            const float damping = xsub(1.0f, xdiv((float)it, 50.0f));
-            const f3 fd = xscale(force, damping);
-            c = xadd(c, f3{xdiv(fd.x, fm), xdiv(fd.y, fm), xdiv(fd.z, fm)});
-            if (xnorm2(force) < 1e-6f) break;
         }
+        // (c) is the cell whose corner 0 is this voxel a surface cell? (:187-199)
+        bool valid = true; unsigned neg = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int i = hidx(x + c_corner[k][0], y + c_corner[k][1], z + c_corner[k][2]);
+            valid = valid && s_a[i];
+            neg |= (__float_as_uint(s_v[i]) >> 31) << k;
+        }
+        valid = valid && neg != 0 && neg != 255;
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, valid);
+        if ((t & 31) == 0) s_bal[c >> 5] = bal;
     }
-    float* o = cell_pts + (b * 512 + t) * 3;
-    o[0] = c.x; o[1] = c.y; o[2] = c.z;
-    const unsigned bal = __ballot_sync(0xFFFFFFFFu, valid);
-    if ((t & 31) == 0) s_bal[t >> 5] = bal;
     if (bad && (!owned || owned[b])) flags[0] = 1;  // halo bricks of a sharded volume miss part of their own halo
     __syncthreads();
     if (t < 8) cell_valid[b * 8 + t] = (u64)s_bal[2 * t] | ((u64)s_bal[2 * t + 1] << 32);
+    unsigned n_valid = 0;
+#pragma unroll
+    for (int w = 0; w < 16; ++w) {
+        const unsigned m = s_bal[w];
+        if (t < 32 && ((m >> t) & 1u)) s_list[n_valid + __popc(m & ((1u << t) - 1u))] = (unsigned short)(w * 32 + t);
+        n_valid += __popc(m);
+    }
+    __syncthreads();
+    for (unsigned i = t; i < n_valid; i += DC_TPB) {
+        const unsigned c = s_list[i];
+        const int x = (c >> 6) + 1, y = ((c >> 3) & 7) + 1, z = (c & 7) + 1;
+        // the cell's Hermite samples, compacted in EDGE_OFFSETS order (thread-local arrays; the solve walks only the m samples
+        // that exist -- typically 3 to 6 of the 12 edges)
+        f3 pts[12], nng[12]; int m = 0;
+        bool bad2 = false;  // edges owned by other bricks are checked by their owners
+#pragma unroll 1
+        for (int e = 0; e < 12; ++e) {
+            f3 p, nn;
+            if (hermite(h, s_org, x + c_edge[e][0], y + c_edge[e][1], z + c_edge[e][2], c_edge[e][3], p, nn, &bad2)) { pts[m] = p; nng[m] = nn; ++m; }
+        }
+        // find_feature_point (:429-458)
+        const float fm = (float)m;
+        f3 cc{0.f, 0.f, 0.f};
+        for (int i = 0; i < m; ++i) cc = xadd(cc, pts[i]);
+        cc = f3{xdiv(cc.x, fm), xdiv(cc.y, fm), xdiv(cc.z, fm)};
+#pragma unroll 1
+        for (int it = 0; it < 50; ++it) {
+            f3 force{0.f, 0.f, 0.f};
+#pragma unroll 1
+            for (int i = 0; i < m; ++i) {
+                const f3 nn = nng[i];
+                const f3 nneg = xscale(nn, -1.0f);
+                force = xadd(force, xscale(nneg, xdot(nn, xsub(cc, pts[i]))));
+            }
+            const f3 fd = xscale(force, s_damp[it]);
+            cc = xadd(cc, f3{xdiv(fd.x, fm), xdiv(fd.y, fm), xdiv(fd.z, fm)});
+            if (xnorm2(force) < 1e-6f) break;
+        }
+        float* o = cell_pts + (b * 512 + c) * 3;
+        o[0] = cc.x; o[1] = cc.y; o[2] = cc.z;
+    }
 }
 
 template <bool WRITE>
 __global__ void __launch_bounds__(512) k_dc_quads(const u64* __restrict__ keys, const float* __restrict__ values, const u64* __restrict__ masks, size_t n,
-                                                  const unsigned char* __restrict__ owned, const float* __restrict__ cell_pts, const u64* __restrict__ cell_valid, float vs,
+                                                  const int* __restrict__ nbr, const unsigned char* __restrict__ owned, const float* __restrict__ cell_pts, const u64* __restrict__ cell_valid, float vs,
                                                   unsigned* counts, const u64* __restrict__ offsets, float* out) {
     __shared__ long long s_nb[8];   // bit0 = -x, bit1 = -y, bit2 = -z neighbour (cells), index 0 = this brick
     __shared__ long long s_pb[4];   // +x, +y, +z neighbour (values), index 0 = this brick
@@ -167,19 +215,8 @@ __global__ void __launch_bounds__(512) k_dc_quads(const u64* __restrict__ keys, 
     const unsigned t = threadIdx.x;
     if (owned && !owned[b]) { if (!WRITE && t == 0) counts[b] = 0; return; }
     if (WRITE) { if (offsets[b + 1] == offsets[b]) return; }
-    if (t < 8 || (t >= 32 && t < 36)) {
-        int bx, by, bz; bs_key_brick(keys[b], bx, by, bz);
-        if (t < 8) {
-            const int nx = bx - (t & 1), ny = by - ((t >> 1) & 1), nz = bz - ((t >> 2) & 1);
-            const bool ok = nx >= BS_BRICK_MIN && ny >= BS_BRICK_MIN && nz >= BS_BRICK_MIN;
-            s_nb[t] = t == 0 ? (long long)b : (ok ? find_key(keys, n, bs_brick_key(nx, ny, nz)) : -1);
-        } else {
-            const unsigned d = t - 32;
-            const int nx = bx + (d == 1), ny = by + (d == 2), nz = bz + (d == 3);
-            const bool ok = nx <= BS_BRICK_MAX && ny <= BS_BRICK_MAX && nz <= BS_BRICK_MAX;
-            s_pb[d] = d == 0 ? (long long)b : (ok ? find_key(keys, n, bs_brick_key(nx, ny, nz)) : -1);
-        }
-    }
+    if (t < 8) s_nb[t] = nbr[b * 27 + (1 - (t & 1)) * 9 + (1 - ((t >> 1) & 1)) * 3 + (1 - ((t >> 2) & 1))];
+    else if (t >= 32 && t < 36) { const unsigned d = t - 32; s_pb[d] = nbr[b * 27 + (d == 0 ? 13 : (d == 1 ? 22 : (d == 2 ? 16 : 14)))]; }
     __syncthreads();
     const int x = t >> 6, y = (t >> 3) & 7, z = t & 7;
     int ntri = 0;
@@ -243,13 +280,15 @@ bs_status bs_dc_impl(const bs_volume* v, float voxel_size, const float** d_verts
     if (v->n_tiles8 || v->n_tiles128) return bs_fail(ctx, BS_ERR_REFERENCE_PANICS, "dual contouring over active tiles: the reference hits todo!() (dual_contouring.rs:139,186,347)");
     const size_t n = v->n_bricks;
     if (n == 0) { bs_marks_end(ctx); return BS_OK; }
-    float* d_cells = nullptr; u64 *d_valid = nullptr, *d_wide = nullptr, *d_off = nullptr; unsigned* d_counts = nullptr; int* d_flags = nullptr;
+    float* d_cells = nullptr; u64 *d_valid = nullptr, *d_wide = nullptr, *d_off = nullptr; unsigned* d_counts = nullptr; int *d_flags = nullptr, *d_nbr = nullptr;
+    BS_TRY(bs_alloc(ctx, &d_nbr, n * 27));
+    bs_count_launch(), k_dc_neighbours<<<bs_blocks(n * 27, 256), 256, 0, st>>>(v->keys, n, d_nbr);
     BS_TRY(bs_alloc(ctx, &d_cells, n * 512 * 3)); BS_TRY(bs_alloc(ctx, &d_valid, n * 8)); BS_TRY(bs_alloc(ctx, &d_flags, 1));
     BS_TRY(bs_alloc(ctx, &d_counts, n)); BS_TRY(bs_alloc(ctx, &d_wide, n + 1)); BS_TRY(bs_alloc(ctx, &d_off, n + 1));
     BS_CUDA(ctx, cudaMemsetAsync(d_flags, 0, sizeof(int), st));
-    bs_count_launch(), k_dc_cells<<<(unsigned)n, 512, 0, st>>>(v->keys, v->values, v->masks, n, v->owned, d_cells, d_valid, d_flags);
+    bs_count_launch(), k_dc_cells<<<(unsigned)n, DC_TPB, 0, st>>>(v->keys, v->values, v->masks, n, d_nbr, v->owned, d_cells, d_valid, d_flags);
     bs_mark(ctx, "dc_cells_ms");
-    bs_count_launch(), k_dc_quads<false><<<(unsigned)n, 512, 0, st>>>(v->keys, v->values, v->masks, n, v->owned, d_cells, d_valid, voxel_size, d_counts, nullptr, nullptr);
+    bs_count_launch(), k_dc_quads<false><<<(unsigned)n, 512, 0, st>>>(v->keys, v->values, v->masks, n, d_nbr, v->owned, d_cells, d_valid, voxel_size, d_counts, nullptr, nullptr);
     bs_count_launch(), k_widen<<<bs_blocks(n + 1, 256), 256, 0, st>>>(d_counts, d_wide, n);
     void* d_tmp = nullptr; size_t tmp_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_wide, d_off, n + 1, st);
@@ -263,9 +302,9 @@ bs_status bs_dc_impl(const bs_volume* v, float voxel_size, const float** d_verts
     bs_status s = BS_OK;
     if (flag) s = bs_fail(ctx, BS_ERR_REFERENCE_PANICS, "dual contouring: a sign-change edge end point has no neighbour along some axis; the reference hits unreachable!() (dual_contouring.rs:340)");
     if (s == BS_OK) s = bs_ensure_out_verts(ctx, (size_t)n_tris * 9);
-    if (s == BS_OK && n_tris) bs_count_launch(), k_dc_quads<true><<<(unsigned)n, 512, 0, st>>>(v->keys, v->values, v->masks, n, v->owned, d_cells, d_valid, voxel_size, nullptr, d_off, ctx->d_out_verts);
+    if (s == BS_OK && n_tris) bs_count_launch(), k_dc_quads<true><<<(unsigned)n, 512, 0, st>>>(v->keys, v->values, v->masks, n, d_nbr, v->owned, d_cells, d_valid, voxel_size, nullptr, d_off, ctx->d_out_verts);
     bs_mark(ctx, "dc_emit_ms");
-    bs_free(ctx, d_tmp); bs_free(ctx, d_cells); bs_free(ctx, d_valid); bs_free(ctx, d_counts); bs_free(ctx, d_wide); bs_free(ctx, d_off); bs_free(ctx, d_flags);
+    bs_free(ctx, d_tmp); bs_free(ctx, d_cells); bs_free(ctx, d_valid); bs_free(ctx, d_counts); bs_free(ctx, d_wide); bs_free(ctx, d_off); bs_free(ctx, d_flags); bs_free(ctx, d_nbr);
     if (s != BS_OK) return s;
     BS_CUDA(ctx, cudaStreamSynchronize(st));
     BS_CUDA(ctx, cudaGetLastError());
