@@ -8,9 +8,10 @@
 // along each axis whose exit face holds a value of the sweep's sign below the limit; everything popped in a
 // sweep is queued again for the next one. That order is a topological order of "a leaf after its three upstream
 // face neighbours and before its three downstream ones", and the same holds for voxels inside a leaf, so the
-// result is reproduced exactly by two nested hyperplane wavefronts: leaves with equal +-X+-Y+-Z run concurrently
-// (one CTA each), and inside a CTA the voxels with equal +-x+-y+-z (22 steps). Dynamic queueing becomes a
-// monotone per-brick flag set by the upstream CTA before the next leaf wavefront is launched.
+// result is reproduced exactly by a dataflow over the leaves (a leaf runs as soon as its upstream face neighbours have
+// finished the sweep; all 8 sweeps in one persistent kernel, see k_sweep_all) and, inside a leaf, by a hyperplane
+// wavefront over the voxels with equal +-x+-y+-z (22 steps). Dynamic queueing becomes a monotone per-brick flag set by
+// the upstream leaf before it publishes its completion.
 //
 // Bricks the sweeps may create are pre-allocated empty (dilation of the pruned brick set); a push outside that
 // set raises a flag and the whole operation is retried with a wider dilation.
@@ -103,154 +104,190 @@ __global__ void k_wave_keys(const u64* __restrict__ keys, size_t n, unsigned* wk
 
 struct SweepParams {
     float* values; u64* masks; const u64* frozen; const int* nbr; unsigned char* inq; int* flags;
-    const unsigned* order;   // bricks of this leaf wavefront
+    const unsigned* order;   // [4][n]: bricks sorted by leaf wavefront for the four (sx, sy, +z) patterns
+    unsigned n;              // bricks of the working set
+    unsigned* done;          // [n] sweeps a brick has completed (task (sweep s, brick b) done  <=>  done[b] >= s + 1)
     float h, limit_abs; int sweep_neg;  // sweep sign: 1 = negative
-    int dir;                 // bit0 = -x, bit1 = -y, bit2 = -z (sweep order fast_sweep.rs:39-60)
 };
+__device__ __forceinline__ unsigned ld_done(const unsigned* p) { return *(const volatile unsigned*)p; }
 
-// One CTA (64 threads = the (y,z) columns) per leaf of the current leaf wavefront; leaves that are not queued exit.
-// The kernel is one link of a ~1700-long dependency chain (8 sweeps x ~210 leaf wavefronts), so it is written for
-// LATENCY: every global load is issued up front in two round trips (brick data + neighbour ids, then the six faces),
-// the brick lives in a 10^3 padded shared array (faces in the halo: no centre/face branches in the stencil), frozen
-// bits sit in a register, the 22 voxel-wavefront steps touch shared memory only.
+// All 8 sweeps in ONE persistent kernel, as a dataflow over the tasks (sweep, leaf): task T = sweep * n + i takes the i-th
+// leaf in the sweep's wavefront order (fast_sweep.rs:39-60: +++, -++, +-+, --+, ++-, -+-, +--, ---). The reference's order is
+// a topological order of "a leaf after its three upstream face neighbours and before its three downstream ones"; a task may
+// therefore start as soon as
+//   * its three upstream neighbours have finished THIS sweep (their exit faces are what the stencil reads, and they are the
+//     ones that queue this leaf), and
+//   * the leaf itself and its three downstream neighbours have finished the PREVIOUS sweep (the stencil reads their faces as
+//     that sweep left them; and nobody still reads this leaf's old values, because every neighbour is past that sweep),
+// which is tracked by one counter per leaf (done[]). CTA c owns tasks c, c + G, c + 2G, ... of the global order: every wait is
+// on a task with a smaller index, each CTA walks its tasks in increasing order and all G CTAs are resident, so the smallest
+// unfinished task can always run -- no grid-wide barrier, no launch per wavefront (round 1: 1682 dependent launches), and
+// consecutive sweeps overlap wherever the geometry allows. Data written by other CTAs is read with ld.global.cg (L2).
+// One CTA = 64 threads = the (y, z) columns of a leaf; the brick lives in a 10^3 padded shared array (faces in the halo: no
+// centre/face branches in the stencil), frozen bits sit in a register, the 22 voxel-wavefront steps touch shared memory only.
 constexpr int PAD = 10, PAD2 = 100, PADN = 1000;
-__global__ void __launch_bounds__(64) k_sweep(SweepParams P) {
+__global__ void __launch_bounds__(64) k_sweep_all(SweepParams P) {
     __shared__ float s_v[PADN];
     __shared__ unsigned char s_a[PADN];
-    const unsigned b = P.order[blockIdx.x];
+    __shared__ unsigned char s_fz[64];
     const unsigned t = threadIdx.x;
     const unsigned ty = t >> 3, tz = t & 7;  // this thread's (y, z) column in brick coordinates (load / store phases)
-    // round trip 1 (overlaps the previous leaf wavefront under programmatic dependent launch: nothing read here is
-    // written by it): neighbour ids, centre values / masks / frozen masks
-    int nb[6];
+    const unsigned long long n_tasks = 8ull * P.n;
+    for (unsigned long long T = blockIdx.x; T < n_tasks; T += gridDim.x) {
+        const int dir = (int)(T / P.n);          // bit0 = -x, bit1 = -y, bit2 = -z
+        const unsigned i = (unsigned)(T % P.n);
+        // sz = +1: pattern g = dir & 3 ascending; sz = -1: (sx, sy, -1) is the reverse of pattern (-sx, -sy, +1)
+        const bool rev = dir & 4;
+        const int g = rev ? ((~dir) & 3) : (dir & 3);
+        const unsigned b = __ldg(P.order + (size_t)g * P.n + (rev ? P.n - 1 - i : i));
+        const int sx = (dir & 1) ? -1 : 1, sy = (dir & 2) ? -1 : 1, sz = (dir & 4) ? -1 : 1;
+        int nb[6];  // +x -x +y -y +z -z
 #pragma unroll
-    for (int d = 0; d < 6; ++d) nb[d] = __ldg(P.nbr + (size_t)b * 6 + d);
-    const float4* gv4 = reinterpret_cast<const float4*>(P.values + (size_t)b * 512);
-    const float4 c0 = gv4[t], c1 = gv4[t + 64];
-    const unsigned sh = (ty << 3) | tz;
-    unsigned abits = 0, fbits = 0;  // bit x = active / frozen flag of voxel (x, ty, tz)
-    {
-        u64 mw[8], fw[8];
+        for (int d = 0; d < 6; ++d) nb[d] = __ldg(P.nbr + (size_t)b * 6 + d);
+        // ---- dependencies, in two phases so that the loads of everything that is already final overlap the wait for the
+        // upstream leaves (the chain of upstream waits is the critical path of the whole operation) ---------------------
+        bool up[6];
 #pragma unroll
-        for (int x = 0; x < 8; ++x) { mw[x] = P.masks[(size_t)b * 8 + x]; fw[x] = P.frozen[(size_t)b * 8 + x]; }
-#pragma unroll
-        for (int x = 0; x < 8; ++x) { abits |= (unsigned)((mw[x] >> sh) & 1) << x; fbits |= (unsigned)((fw[x] >> sh) & 1) << x; }
-    }
-    // the previous wavefront (which queues this leaf and owns the upstream faces) must be complete from here on;
-    // once this grid is past the wait, the next wavefront may start its own round trip 1
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;");
-    if (!P.inq[b]) return;
-    // round trip 2: the six faces next to the brick: thread t = (u, v) on each face
-    float fv[6]; unsigned fa = 0;
-    {
+        for (int d = 0; d < 6; ++d) { const int s = d < 2 ? sx : (d < 4 ? sy : sz); up[d] = (s > 0) == ((d & 1) != 0); }  // sweeping towards +: the - neighbour is upstream
+        // phase 1: the leaf itself and its downstream neighbours are past the previous sweep (almost always true already)
+        if (t < 7) {
+            const int which = t < 6 ? nb[t] : (int)b;
+            if (which >= 0 && !(t < 6 && up[t])) while (ld_done(P.done + which) < (unsigned)dir) __nanosleep(32);
+        }
+        __syncthreads();
+        // a leaf queued in an earlier sweep stays queued: start its loads now (centre, masks, downstream faces)
+        const bool early = __ldcg(P.inq + b) != 0;
+        const float4* gv4 = reinterpret_cast<const float4*>(P.values + (size_t)b * 512);
+        const unsigned sh = (ty << 3) | tz;
         const unsigned u = ty, v = tz;
+        float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
+        u64 mw[8], fw[8];
+        float fv[6]; unsigned fa = 0;
+        auto load_centre = [&]() {
+            c0 = __ldcg(gv4 + t); c1 = __ldcg(gv4 + t + 64);
 #pragma unroll
-        for (int d = 0; d < 6; ++d) {
+            for (int x = 0; x < 8; ++x) { mw[x] = __ldcg(P.masks + (size_t)b * 8 + x); fw[x] = __ldg(P.frozen + (size_t)b * 8 + x); }
+        };
+        auto load_face = [&](int d) {
             fv[d] = 0.f;
             if (nb[d] >= 0) {
                 const unsigned c = (d & 1) ? 7u : 0u;  // the +x neighbour contributes its x = 0 face, the -x neighbour its x = 7 face
                 const unsigned off = d < 2 ? ((c << 6) | (u << 3) | v) : (d < 4 ? ((u << 6) | (c << 3) | v) : ((u << 6) | (v << 3) | c));
-                fa |= (unsigned)((P.masks[(size_t)nb[d] * 8 + (off >> 6)] >> (off & 63)) & 1) << d;
-                fv[d] = P.values[(size_t)nb[d] * 512 + off];
+                fa |= (unsigned)((__ldcg(P.masks + (size_t)nb[d] * 8 + (off >> 6)) >> (off & 63)) & 1) << d;
+                fv[d] = __ldcg(P.values + (size_t)nb[d] * 512 + off);
             }
-        }
-    }
-    // fill the padded array: index (x+1)*100 + (y+1)*10 + (z+1)
-    {
-        // centre: float4 q covers offsets 4q..4q+3 = (x, y, z0..z0+3)
+        };
+        if (early) {
+            load_centre();
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const unsigned q = t + 64 * h, off = q * 4, x = off >> 6, y = (off >> 3) & 7, z = off & 7;
-            const float4 c = h ? c1 : c0;
-            float* d = s_v + (x + 1) * PAD2 + (y + 1) * PAD + (z + 1);
-            d[0] = c.x; d[1] = c.y; d[2] = c.z; d[3] = c.w;
+            for (int d = 0; d < 6; ++d) if (!up[d]) load_face(d);
         }
-#pragma unroll
-        for (int x = 0; x < 8; ++x) s_a[(x + 1) * PAD2 + (ty + 1) * PAD + (tz + 1)] = (abits >> x) & 1;
-        const unsigned u = ty, v = tz;
-#pragma unroll
-        for (int d = 0; d < 6; ++d) {
-            const unsigned c = (d & 1) ? 0u : 9u;  // +x face sits at padded x = 9, -x face at padded x = 0
-            const unsigned p = d < 2 ? (c * PAD2 + (u + 1) * PAD + (v + 1)) : (d < 4 ? ((u + 1) * PAD2 + c * PAD + (v + 1)) : ((u + 1) * PAD2 + (v + 1) * PAD + c));
-            s_v[p] = fv[d]; s_a[p] = (fa >> d) & 1;
-        }
-    }
-    __syncthreads();
-    const int sx = (P.dir & 1) ? -1 : 1, sy = (P.dir & 2) ? -1 : 1, sz = (P.dir & 4) ? -1 : 1;
-    const int ly = t >> 3, lz = t & 7;  // sweep-local y, z of this thread's column
-    const int y = sy > 0 ? ly : 7 - ly, z = sz > 0 ? lz : 7 - lz;
-    unsigned cfz = 0;  // frozen bits of column (y, z): held by the thread whose (ty, tz) == (y, z)
-    {
-        const unsigned src = ((unsigned)y << 3) | (unsigned)z;  // lane (within this warp or the other) that holds them
-        __shared__ unsigned char s_fz[64];
-        s_fz[t] = (unsigned char)fbits;
+        // phase 2: the upstream neighbours have finished THIS sweep
+        if (t < 6 && up[t] && nb[t] >= 0) while (ld_done(P.done + nb[t]) < (unsigned)dir + 1u) __nanosleep(32);
         __syncthreads();
-        cfz = s_fz[src];
-    }
-    const int pyz = (y + 1) * PAD + (z + 1);
-    for (int step = 0; step < 22; ++step) {
-        const int lx = step - ly - lz;
-        if ((unsigned)lx < 8u) {
-            const int x = sx > 0 ? lx : 7 - lx;
-            if (!((cfz >> x) & 1)) {  // frozen voxels keep their value (:126-128)
-                const int p = (x + 1) * PAD2 + pyz;
-                // stencil.at for the six face neighbours (:130-146, :360-386)
-                const float nv[6] = {s_v[p + PAD2], s_v[p - PAD2], s_v[p + PAD], s_v[p - PAD], s_v[p + 1], s_v[p - 1]};
-                const bool na[6] = {s_a[p + PAD2] != 0, s_a[p - PAD2] != 0, s_a[p + PAD] != 0, s_a[p - PAD] != 0, s_a[p + 1] != 0, s_a[p - 1] != 0};
-                // option_min_by(+, -, cmp_abs): both present -> the smaller |v|, ties -> the + side
-                float d[3]; bool has[3];
+        const bool queued = early || __ldcg(P.inq + b) != 0;
+        if (queued) {
+            if (!early) {
+                load_centre();
 #pragma unroll
-                for (int ax = 0; ax < 3; ++ax) {
-                    const bool ap = na[2 * ax], an = na[2 * ax + 1];
-                    has[ax] = ap || an;
-                    d[ax] = (ap && an) ? ((fabsf(nv[2 * ax]) > fabsf(nv[2 * ax + 1])) ? nv[2 * ax + 1] : nv[2 * ax]) : (ap ? nv[2 * ax] : nv[2 * ax + 1]);
+                for (int d = 0; d < 6; ++d) if (!up[d]) load_face(d);
+            }
+#pragma unroll
+            for (int d = 0; d < 6; ++d) if (up[d]) load_face(d);
+            unsigned abits = 0, fbits = 0;  // bit x = active / frozen flag of voxel (x, ty, tz)
+#pragma unroll
+            for (int x = 0; x < 8; ++x) { abits |= (unsigned)((mw[x] >> sh) & 1) << x; fbits |= (unsigned)((fw[x] >> sh) & 1) << x; }
+            // fill the padded array: index (x+1)*100 + (y+1)*10 + (z+1)
+            {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {  // centre: float4 q covers offsets 4q..4q+3 = (x, y, z0..z0+3)
+                    const unsigned q = t + 64 * h, off = q * 4, x = off >> 6, y = (off >> 3) & 7, z = off & 7;
+                    const float4 c = h ? c1 : c0;
+                    float* d = s_v + (x + 1) * PAD2 + (y + 1) * PAD + (z + 1);
+                    d[0] = c.x; d[1] = c.y; d[2] = c.z; d[3] = c.w;
                 }
-                if (has[0] || has[1] || has[2]) {
-                    const float first = has[0] ? d[0] : (has[1] ? d[1] : d[2]);
-                    if ((int)(__float_as_uint(first) >> 31) == P.sweep_neg) {  // outward / inward (:148-156)
-                        const float d1 = has[0] ? fabsf(d[0]) : FLT_MAX, d2 = has[1] ? fabsf(d[1]) : FLT_MAX, d3 = has[2] ? fabsf(d[2]) : FLT_MAX;
-                        const float dn = compute_distance(d1, d2, d3, P.h);
-                        if (!(dn > P.limit_abs)) {
-                            const float old = s_a[p] ? s_v[p] : FLT_MAX;
-                            if (dn < fabsf(old)) { s_v[p] = P.sweep_neg ? -fabsf(dn) : fabsf(dn); s_a[p] = 1; }  // set_sign (value/f32.rs:11-17)
+#pragma unroll
+                for (int x = 0; x < 8; ++x) s_a[(x + 1) * PAD2 + (ty + 1) * PAD + (tz + 1)] = (abits >> x) & 1;
+#pragma unroll
+                for (int d = 0; d < 6; ++d) {
+                    const unsigned c = (d & 1) ? 0u : 9u;  // +x face sits at padded x = 9, -x face at padded x = 0
+                    const unsigned p = d < 2 ? (c * PAD2 + (u + 1) * PAD + (v + 1)) : (d < 4 ? ((u + 1) * PAD2 + c * PAD + (v + 1)) : ((u + 1) * PAD2 + (v + 1) * PAD + c));
+                    s_v[p] = fv[d]; s_a[p] = (fa >> d) & 1;
+                }
+                s_fz[t] = (unsigned char)fbits;
+            }
+            __syncthreads();
+            const int ly = t >> 3, lz = t & 7;  // sweep-local y, z of this thread's column
+            const int y = sy > 0 ? ly : 7 - ly, z = sz > 0 ? lz : 7 - lz;
+            const unsigned cfz = s_fz[((unsigned)y << 3) | (unsigned)z];  // frozen bits of column (y, z)
+            const int pyz = (y + 1) * PAD + (z + 1);
+            for (int step = 0; step < 22; ++step) {
+                const int lx = step - ly - lz;
+                if ((unsigned)lx < 8u) {
+                    const int x = sx > 0 ? lx : 7 - lx;
+                    if (!((cfz >> x) & 1)) {  // frozen voxels keep their value (:126-128)
+                        const int p = (x + 1) * PAD2 + pyz;
+                        // stencil.at for the six face neighbours (:130-146, :360-386)
+                        const float nv[6] = {s_v[p + PAD2], s_v[p - PAD2], s_v[p + PAD], s_v[p - PAD], s_v[p + 1], s_v[p - 1]};
+                        const bool na[6] = {s_a[p + PAD2] != 0, s_a[p - PAD2] != 0, s_a[p + PAD] != 0, s_a[p - PAD] != 0, s_a[p + 1] != 0, s_a[p - 1] != 0};
+                        // option_min_by(+, -, cmp_abs): both present -> the smaller |v|, ties -> the + side
+                        float d[3]; bool has[3];
+#pragma unroll
+                        for (int ax = 0; ax < 3; ++ax) {
+                            const bool ap = na[2 * ax], an = na[2 * ax + 1];
+                            has[ax] = ap || an;
+                            d[ax] = (ap && an) ? ((fabsf(nv[2 * ax]) > fabsf(nv[2 * ax + 1])) ? nv[2 * ax + 1] : nv[2 * ax]) : (ap ? nv[2 * ax] : nv[2 * ax + 1]);
                         }
+                        if (has[0] || has[1] || has[2]) {
+                            const float first = has[0] ? d[0] : (has[1] ? d[1] : d[2]);
+                            if ((int)(__float_as_uint(first) >> 31) == P.sweep_neg) {  // outward / inward (:148-156)
+                                const float d1 = has[0] ? fabsf(d[0]) : FLT_MAX, d2 = has[1] ? fabsf(d[1]) : FLT_MAX, d3 = has[2] ? fabsf(d[2]) : FLT_MAX;
+                                const float dn = compute_distance(d1, d2, d3, P.h);
+                                if (!(dn > P.limit_abs)) {
+                                    const float old = s_a[p] ? s_v[p] : FLT_MAX;
+                                    if (dn < fabsf(old)) { s_v[p] = P.sweep_neg ? -fabsf(dn) : fabsf(dn); s_a[p] = 1; }  // set_sign (value/f32.rs:11-17)
+                                }
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+            // write back + queue the downstream leaves (:185-277)
+            {
+                float4* go4 = reinterpret_cast<float4*>(P.values + (size_t)b * 512);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const unsigned q = t + 64 * h, off = q * 4, x = off >> 6, yy = (off >> 3) & 7, zz = off & 7;
+                    const float* d = s_v + (x + 1) * PAD2 + (yy + 1) * PAD + (zz + 1);
+                    go4[q] = make_float4(d[0], d[1], d[2], d[3]);
+                }
+                // mask word x, bit (ty << 3 | tz) = t: each warp ballots its half of the word
+                unsigned* gm = reinterpret_cast<unsigned*>(P.masks + (size_t)b * 8);
+#pragma unroll
+                for (int x = 0; x < 8; ++x) {
+                    const unsigned bal = __ballot_sync(0xFFFFFFFFu, s_a[(x + 1) * PAD2 + (ty + 1) * PAD + (tz + 1)] != 0);
+                    if ((t & 31) == 0) gm[2 * x + (t >> 5)] = bal;
+                }
+            }
+#pragma unroll
+            for (int ax = 0; ax < 3; ++ax) {
+                const int s = ax == 0 ? sx : (ax == 1 ? sy : sz);
+                const unsigned c = s > 0 ? 8u : 1u;  // exit face (padded coordinate); the reference's negative-direction index collapses to local 0 via leaf index masking
+                const unsigned p = ax == 0 ? (c * PAD2 + (u + 1) * PAD + (v + 1)) : (ax == 1 ? ((u + 1) * PAD2 + c * PAD + (v + 1)) : ((u + 1) * PAD2 + (v + 1) * PAD + c));
+                const bool q = s_a[p] && ((int)(__float_as_uint(s_v[p]) >> 31) == P.sweep_neg) && (fabsf(s_v[p]) < P.limit_abs);
+                if (__syncthreads_or(q)) {
+                    if (t == 0) {
+                        const int n2 = s > 0 ? nb[2 * ax] : nb[2 * ax + 1];
+                        if (n2 >= 0) P.inq[n2] = 1; else P.flags[0] = 1;  // outside the pre-allocated set: retry wider
                     }
                 }
             }
         }
+        // publish: everything this CTA wrote is visible before the counter moves (a leaf that was not queued wrote nothing)
+        if (queued) __threadfence();
         __syncthreads();
-    }
-    // write back + queue the downstream leaves (:185-277)
-    {
-        float4* go4 = reinterpret_cast<float4*>(P.values + (size_t)b * 512);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const unsigned q = t + 64 * h, off = q * 4, x = off >> 6, yy = (off >> 3) & 7, zz = off & 7;
-            const float* d = s_v + (x + 1) * PAD2 + (yy + 1) * PAD + (zz + 1);
-            go4[q] = make_float4(d[0], d[1], d[2], d[3]);
-        }
-        // mask word x, bit (ty << 3 | tz) = t: each warp ballots its half of the word
-        unsigned* gm = reinterpret_cast<unsigned*>(P.masks + (size_t)b * 8);
-#pragma unroll
-        for (int x = 0; x < 8; ++x) {
-            const unsigned bal = __ballot_sync(0xFFFFFFFFu, s_a[(x + 1) * PAD2 + (ty + 1) * PAD + (tz + 1)] != 0);
-            if ((t & 31) == 0) gm[2 * x + (t >> 5)] = bal;
-        }
-    }
-    const unsigned u = ty, v = tz;
-#pragma unroll
-    for (int ax = 0; ax < 3; ++ax) {
-        const int s = ax == 0 ? sx : (ax == 1 ? sy : sz);
-        const unsigned c = s > 0 ? 8u : 1u;  // exit face (padded coordinate); the reference's negative-direction index collapses to local 0 via leaf index masking
-        const unsigned p = ax == 0 ? (c * PAD2 + (u + 1) * PAD + (v + 1)) : (ax == 1 ? ((u + 1) * PAD2 + c * PAD + (v + 1)) : ((u + 1) * PAD2 + (v + 1) * PAD + c));
-        const bool q = s_a[p] && ((int)(__float_as_uint(s_v[p]) >> 31) == P.sweep_neg) && (fabsf(s_v[p]) < P.limit_abs);
-        if (__syncthreads_or(q)) {
-            if (t == 0) {
-                const int n2 = s > 0 ? nb[2 * ax] : nb[2 * ax + 1];
-                if (n2 >= 0) P.inq[n2] = 1; else P.flags[0] = 1;  // outside the pre-allocated set: retry wider
-            }
-        }
+        if (t == 0) *(volatile unsigned*)(P.done + b) = (unsigned)dir + 1u;
     }
 }
 
@@ -354,80 +391,40 @@ bs_status bs_offset_impl(bs_volume* A, float distance, bs_volume** out) {
         BS_CUDA(ctx, cudaMemsetAsync(d_inq, 0, n, st));
         bs_count_launch(), k_place<<<(unsigned)n_src, 512, 0, st>>>(A->keys, A->values, d_pmasks, d_nonempty, n_src, d_keys, n, d_values, d_masks, d_frozen, d_inq);
         bs_count_launch(), k_neighbours<<<bs_blocks(n * 6, TPB), TPB, 0, st>>>(d_keys, n, d_nbr);
-        // --- leaf wavefronts for the four axis-sign patterns (the other four are their reverses): bricks sorted by
-        // w = +-bx +- by + bz on the device; the host only learns the run lengths (one launch per non-empty w) ---------
-        unsigned *d_wk = nullptr, *d_wks = nullptr, *d_idx = nullptr, *d_order = nullptr, *d_runs = nullptr; int* d_nruns = nullptr;
+        // --- leaf wavefront order for the four axis-sign patterns (the other four are their reverses): bricks sorted by
+        // w = +-bx +- by + bz on the device -----------------------------------------------------------------------
+        unsigned *d_wk = nullptr, *d_wks = nullptr, *d_idx = nullptr, *d_order = nullptr;
         BS_TRY(bs_alloc(ctx, &d_wk, 4 * n)); BS_TRY(bs_alloc(ctx, &d_wks, 4 * n)); BS_TRY(bs_alloc(ctx, &d_idx, 4 * n)); BS_TRY(bs_alloc(ctx, &d_order, 4 * n));
-        const size_t max_runs = std::min<size_t>(n, (size_t)3 << 18);
-        BS_TRY(bs_alloc(ctx, &d_runs, 8 * max_runs)); BS_TRY(bs_alloc(ctx, &d_nruns, 4));
         bs_count_launch(), k_wave_keys<<<bs_blocks(4 * n, TPB), TPB, 0, st>>>(d_keys, n, d_wk, d_idx);
         {
-            void* d_tmp = nullptr; size_t tmp = 0, tmp2 = 0;
+            void* d_tmp = nullptr; size_t tmp = 0;
             cub::DeviceRadixSort::SortPairs(nullptr, tmp, d_wk, d_wks, d_idx, d_order, (int)n, 0, 21, st);
-            cub::DeviceRunLengthEncode::Encode(nullptr, tmp2, d_wks, d_runs, d_runs + max_runs, d_nruns, (int)n, st);
-            tmp = std::max(tmp, tmp2);
             BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp));
-            for (int g = 0; g < 4; ++g) {
-                cub::DeviceRadixSort::SortPairs(d_tmp, tmp, d_wk + g * n, d_wks + g * n, d_idx + g * n, d_order + g * n, (int)n, 0, 21, st);
-                cub::DeviceRunLengthEncode::Encode(d_tmp, tmp, d_wks + g * n, d_runs + 2 * g * max_runs, d_runs + (2 * g + 1) * max_runs, d_nruns + g, (int)n, st);
-            }
+            for (int g = 0; g < 4; ++g) cub::DeviceRadixSort::SortPairs(d_tmp, tmp, d_wk + g * n, d_wks + g * n, d_idx + g * n, d_order + g * n, (int)n, 0, 21, st);
             bs_free(ctx, d_tmp);
         }
-        int h_nruns[4];
-        BS_CUDA(ctx, cudaMemcpyAsync(h_nruns, d_nruns, sizeof(h_nruns), cudaMemcpyDeviceToHost, st));
-        BS_CUDA(ctx, cudaStreamSynchronize(st));
-        std::vector<std::vector<unsigned>> seg(4);  // seg[g] = start offsets of the runs of pattern g (+ n)
-        {
-            std::vector<unsigned> cnt;
-            for (int g = 0; g < 4; ++g) {
-                cnt.resize((size_t)h_nruns[g]);
-                BS_CUDA(ctx, cudaMemcpyAsync(cnt.data(), d_runs + (2 * g + 1) * max_runs, cnt.size() * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-                BS_CUDA(ctx, cudaStreamSynchronize(st));
-                seg[g].assign(cnt.size() + 1, 0);
-                for (size_t k = 0; k < cnt.size(); ++k) seg[g][k + 1] = seg[g][k] + cnt[k];
-            }
-        }
-        bs_free(ctx, d_wk); bs_free(ctx, d_wks); bs_free(ctx, d_idx); bs_free(ctx, d_runs); bs_free(ctx, d_nruns);
+        bs_free(ctx, d_wk); bs_free(ctx, d_wks); bs_free(ctx, d_idx);
         bs_mark(ctx, "offset_setup_ms");
-        // --- 8 sweeps ---------------------------------------------------------------------------------------------------
+        // --- 8 sweeps: one persistent kernel, every CTA resident -----------------------------------------------------------
+        unsigned* d_done = nullptr;
+        BS_TRY(bs_alloc(ctx, &d_done, n));
+        BS_CUDA(ctx, cudaMemsetAsync(d_done, 0, n * sizeof(unsigned), st));
         SweepParams P;
         P.values = d_values; P.masks = d_masks; P.frozen = d_frozen; P.nbr = d_nbr; P.inq = d_inq; P.flags = d_flags;
+        P.order = d_order; P.n = (unsigned)n; P.done = d_done;
         P.h = vs; P.limit_abs = limit_abs; P.sweep_neg = sweep_neg;
-        size_t n_launch = 0;
-        for (int dir = 0; dir < 8; ++dir) {
-            P.dir = dir;
-            // sz = +1: pattern g = dir & 3 ascending; sz = -1: (sx,sy,-1) is the reverse of pattern (-sx,-sy,+1)
-            const bool rev = dir & 4;
-            const int g = rev ? ((~dir) & 3) : (dir & 3);
-            const size_t nw = seg[g].size() - 1;
-            bool first_of_sweep = true;
-            for (size_t k = 0; k < nw; ++k) {
-                const size_t wi = rev ? nw - 1 - k : k;
-                const unsigned cnt = seg[g][wi + 1] - seg[g][wi];
-                if (!cnt) continue;
-                P.order = d_order + (size_t)g * n + seg[g][wi];
-                // programmatic dependent launch: the next wavefront of the same sweep may start its (independent) loads
-                // early; the first launch of a sweep serialises normally, since its bricks can be ones the previous
-                // sweep's last launches still write
-                cudaLaunchConfig_t cfg = {};
-                cfg.gridDim = dim3(cnt); cfg.blockDim = dim3(64); cfg.dynamicSmemBytes = 0; cfg.stream = st;
-                cudaLaunchAttribute attr[1];
-                attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-                attr[0].val.programmaticStreamSerializationAllowed = first_of_sweep ? 0 : 1;
-                cfg.attrs = attr; cfg.numAttrs = 1;
-                bs_count_launch();
-                BS_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_sweep, P));
-                first_of_sweep = false;
-                ++n_launch;
-            }
-        }
+        int per_sm = 0;
+        BS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_all, 64, 0));
+        const unsigned grid = (unsigned)std::min<unsigned long long>(8ull * n, (unsigned long long)std::max(1, per_sm) * (unsigned long long)ctx->sm_count);
+        bs_count_launch(), k_sweep_all<<<grid, 64, 0, st>>>(P);
+        const size_t n_launch = 1;
         int flag = 0;
         BS_CUDA(ctx, cudaMemcpyAsync(&flag, d_flags, sizeof(int), cudaMemcpyDeviceToHost, st));
         BS_CUDA(ctx, cudaStreamSynchronize(st));
         bs_mark(ctx, "offset_sweep_ms");
         bs_status s = BS_OK;
         if (flag && attempt < 3) {  // pushed outside the working set (or index range hit): widen and redo
-            bs_free(ctx, d_keys); bs_free(ctx, d_values); bs_free(ctx, d_masks); bs_free(ctx, d_frozen); bs_free(ctx, d_inq); bs_free(ctx, d_nbr); bs_free(ctx, d_order);
+            bs_free(ctx, d_keys); bs_free(ctx, d_values); bs_free(ctx, d_masks); bs_free(ctx, d_frozen); bs_free(ctx, d_inq); bs_free(ctx, d_nbr); bs_free(ctx, d_order); bs_free(ctx, d_done);
             K += 2;
             continue;
         }
@@ -453,7 +450,7 @@ bs_status bs_offset_impl(bs_volume* A, float distance, bs_volume** out) {
         if (s == BS_OK && n_out) bs_count_launch(), k_compact<<<(unsigned)n, 512, 0, st>>>(d_keys, d_values, d_masks, d_rank, d_ne, R->keys, R->values, R->masks);
         if (s == BS_OK && (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess)) s = bs_fail(ctx, BS_ERR_CUDA, "offset compaction failed");
         bs_free(ctx, d_tmp); bs_free(ctx, d_ne); bs_free(ctx, d_ne32); bs_free(ctx, d_rank);
-        bs_free(ctx, d_keys); bs_free(ctx, d_values); bs_free(ctx, d_masks); bs_free(ctx, d_frozen); bs_free(ctx, d_inq); bs_free(ctx, d_nbr); bs_free(ctx, d_order);
+        bs_free(ctx, d_keys); bs_free(ctx, d_values); bs_free(ctx, d_masks); bs_free(ctx, d_frozen); bs_free(ctx, d_inq); bs_free(ctx, d_nbr); bs_free(ctx, d_order); bs_free(ctx, d_done);
         bs_free(ctx, d_seed); bs_free(ctx, d_pmasks); bs_free(ctx, d_nonempty); bs_free(ctx, d_flags);
         if (s != BS_OK) { bs_volume_free(R); return s; }
         bs_mark(ctx, "offset_finish_ms");
