@@ -26,7 +26,8 @@ constexpr int TPB = 256;
 constexpr int MAX_PROBE = 512;
 
 struct ConvertParams {
-    const float* tris; size_t n_tris;
+    const float* tris; size_t n_tris;   // n_tris = triangles this call works on (entries of tri_ids when that is set)
+    const unsigned* tri_ids;            // sharded runs: the triangles that can touch this rank's bricks (null: all, in order)
     const unsigned long long* offsets;  // exclusive prefix sum of per-triangle sub-triangle counts, n_tris + 1
     unsigned long long total;
     float vs, inv_vs; int band;
@@ -39,11 +40,13 @@ struct ConvertParams {
     int use_clip, clip_mn[3], clip_mx[3];  // sharded runs: voxel bounding box of the bricks this rank keeps
 };
 
+__device__ __forceinline__ const float* tri_ptr(const ConvertParams& P, size_t t) { return P.tris + 9 * (size_t)(P.tri_ids ? P.tri_ids[t] : t); }
 __device__ __forceinline__ unsigned long long hash64(unsigned long long k) {
     k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33; return k;
 }
 
 __device__ __forceinline__ f3 ld3(const float* p) { return {p[0], p[1], p[2]}; }
+
 
 // Triangle3::max_side / voxel_size, floored (mesh_to_volume.rs:76)
 __device__ __forceinline__ float num_subs_of(f3 p1, f3 p2, f3 p3, float vs) {
@@ -52,11 +55,11 @@ __device__ __forceinline__ float num_subs_of(f3 p1, f3 p2, f3 p3, float vs) {
     return floorf(xdiv(xsqrt(m), vs));
 }
 
-__global__ void k_tri_counts(const float* __restrict__ tris, size_t n_tris, float vs, unsigned long long* counts, double* area_vox) {
+__global__ void k_tri_counts(const float* __restrict__ tris, const unsigned* __restrict__ tri_ids, size_t n_tris, float vs, unsigned long long* counts, double* area_vox) {
     size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     double a = 0.0;
     if (t < n_tris) {
-        const float* p = tris + 9 * t;
+        const float* p = tris + 9 * (size_t)(tri_ids ? tri_ids[t] : t);
         f3 p1 = ld3(p), p2 = ld3(p + 3), p3 = ld3(p + 6);
         float n = num_subs_of(p1, p2, p3, vs);
         unsigned long long c;
@@ -174,7 +177,7 @@ __global__ void __launch_bounds__(TPB) k_mark(ConvertParams P) {
     unsigned long long vol = 0;
     int mn[3] = {0, 0, 0}, mx[3] = {-1, -1, -1};
     if (c.valid) {
-        const float* p = P.tris + 9 * c.tri;
+        const float* p = tri_ptr(P, c.tri);
         f3 A, B, C;
         make_subtri(ld3(p), ld3(p + 3), ld3(p + 6), P.vs, c.local, A, B, C);
         if (!subtri_box(A, B, C, P.inv_vs, P.band, mn, mx)) { P.flags[1] = 1; mx[0] = mn[0] - 1; }
@@ -244,7 +247,7 @@ __global__ void __launch_bounds__(TPB, BS_EVAL_MINB) k_eval(ConvertParams P) {
     int mn[3] = {0, 0, 0}, mx[3] = {-1, -1, -1};
     bool ok = false;
     if (cur.valid) {
-        const float* p = P.tris + 9 * cur.tri;
+        const float* p = tri_ptr(P, cur.tri);
         const f3 p1 = ld3(p), p2 = ld3(p + 3), p3 = ld3(p + 6);
         bool hit = true;
         if (P.use_clip) {  // the whole input triangle (plus band and rounding slack) misses this rank's bricks: skip the subdivision
@@ -379,7 +382,7 @@ struct RasterTri {  // one triangle projected along axis A: coordinates (u, v, z
     int iu0, iv0, nu, nv; bool thin, ok;
 };
 template <int A> __device__ __forceinline__ void raster_setup(const ConvertParams& P, size_t t, RasterTri& R) {
-    const float* p = P.tris + 9 * t;
+    const float* p = tri_ptr(P, t);
     constexpr int UA = (A + 1) % 3, VA = (A + 2) % 3;
     R.U0 = (double)p[UA]; R.V0 = (double)p[VA]; R.Z0 = (double)p[A];
     R.U1 = (double)p[3 + UA]; R.V1 = (double)p[3 + VA]; R.Z1 = (double)p[3 + A];
@@ -475,7 +478,7 @@ __global__ void __launch_bounds__(128, 3) k_block_edges(ConvertParams P, unsigne
     if (g >= P.n_tris * 3) return;
     const size_t t = g % P.n_tris; const int a = (int)(g / P.n_tris);
     if (P.use_clip) {  // sharded: the triangle's box (plus slack) misses every brick this rank keeps
-        const float* p = P.tris + 9 * t;
+        const float* p = tri_ptr(P, t);
         for (int d = 0; d < 3; ++d) {
             const float lo = fminf(p[d], fminf(p[3 + d], p[6 + d])), hi = fmaxf(p[d], fmaxf(p[3 + d], p[6 + d]));
             if (ceilf(hi * P.inv_vs) + 3.0f < (float)P.clip_mn[d] || floorf(lo * P.inv_vs) - 3.0f > (float)P.clip_mx[d]) return;
@@ -567,6 +570,81 @@ __global__ void k_owned(const unsigned long long* __restrict__ all_keys, size_t 
     owned[i] = (j >= (long long)lo && j < (long long)hi) ? 1 : 0;
 }
 
+// ---- sharded runs: coarse cut of the key space and the triangles a rank needs -----------------------------------------------
+// Coarse cell = brick key >> 8: one x-plane of bricks inside a 128^3 node (8 x 128 x 128 voxels); a contiguous range of
+// coarse keys is a contiguous range of brick keys, so slabs cut at coarse keys keep "concatenate the ranks' outputs in rank
+// order == the single-GPU output". Every rank derives the same cut from a histogram of the triangles' sub-triangle counts
+// per coarse cell (integer atomics: deterministic), then works only on the triangles whose box -- inflated by one brick of
+// halo, the sub-triangle box rules and the band -- can reach its range.
+__device__ __forceinline__ unsigned long long coarse_key_of_voxel(int x, int y, int z) { return bs_brick_key(x >> 3, y >> 3, z >> 3) >> 8; }
+__global__ void k_coarse_hist(const float* __restrict__ tris, size_t n_tris, float vs, float inv_vs, unsigned long long* tkeys, unsigned long long* tw, unsigned mask, int* flags) {
+    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (t >= n_tris) return;
+    const float* p = tris + 9 * t;
+    const f3 p1 = ld3(p), p2 = ld3(p + 3), p3 = ld3(p + 6);
+    const float n = num_subs_of(p1, p2, p3, vs);
+    unsigned long long w = 1;
+    if (n >= 2.0f) { const double nd = fmin((double)n, 4.0e9); w = (unsigned long long)(nd * nd); } else if (n != n) return;
+    const float cx = (p1.x + p2.x + p3.x) * (1.0f / 3.0f) * inv_vs, cy = (p1.y + p2.y + p3.y) * (1.0f / 3.0f) * inv_vs, cz = (p1.z + p2.z + p3.z) * (1.0f / 3.0f) * inv_vs;
+    if (!(fabsf(cx) < 1.0e6f && fabsf(cy) < 1.0e6f && fabsf(cz) < 1.0e6f)) return;  // k_mark reports range errors
+    const unsigned long long key = coarse_key_of_voxel((int)floorf(cx), (int)floorf(cy), (int)floorf(cz));
+    unsigned h = (unsigned)hash64(key) & mask;
+    for (int probe = 0; probe < 4096; ++probe) {
+        const unsigned long long cur = tkeys[h];
+        bool mine = cur == key;
+        if (!mine && cur == BS_KEY_INVALID) { const unsigned long long prev = atomicCAS(&tkeys[h], BS_KEY_INVALID, key); mine = prev == BS_KEY_INVALID || prev == key; }
+        if (mine) { atomicAdd(&tw[h], w); return; }
+        h = (h + 1) & mask;
+    }
+    flags[0] = 1;  // table full: the caller falls back to an unbalanced but valid cut
+}
+// bounds[r] = coarse key at which rank r starts (bounds[0] = 0, bounds[world] = KEY_INVALID): first key whose inclusive
+// weight prefix reaches r / world of the total
+__global__ void k_coarse_cut(const unsigned long long* __restrict__ keys /*sorted*/, const unsigned long long* __restrict__ C /*inclusive scan of the weights*/, size_t n, int world, unsigned long long* bounds) {
+    const int r = threadIdx.x;
+    if (r > world) return;
+    if (r == 0) { bounds[0] = 0; return; }
+    if (r == world || n == 0) { bounds[r] = BS_KEY_INVALID; return; }
+    const unsigned long long target = C[n - 1] / (unsigned long long)world * (unsigned long long)r;
+    size_t lo = 0, hi = n;  // first i with C[i] >= target
+    while (lo < hi) { const size_t mid = (lo + hi) >> 1; if (C[mid] < target) lo = mid + 1; else hi = mid; }
+    bounds[r] = lo < n ? keys[lo] : BS_KEY_INVALID;
+}
+__global__ void k_select_tris(const float* __restrict__ tris, size_t n_tris, float inv_vs, int margin /*voxels*/, unsigned long long klo, unsigned long long khi, unsigned char* keep) {
+    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (t >= n_tris) return;
+    const float* p = tris + 9 * t;
+    int lo[3], hi[3]; bool ok = true;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const float a = floorf(fminf(p[d], fminf(p[3 + d], p[6 + d])) * inv_vs), b = ceilf(fmaxf(p[d], fmaxf(p[3 + d], p[6 + d])) * inv_vs);
+        if (!(a > -1.0e6f && b < 1.0e6f)) { ok = false; lo[d] = hi[d] = 0; }  // NaN / out of range: keep it, k_mark reports
+        else { lo[d] = ((int)a - margin) >> 3; hi[d] = ((int)b + margin) >> 3; }  // brick coordinates
+        lo[d] = max(lo[d], BS_BRICK_MIN); hi[d] = min(hi[d], BS_BRICK_MAX);
+    }
+    bool hit = !ok;
+    if (ok) {
+        // coarse cells = (brick x, node y, node z): x per brick, y / z per 16 bricks
+        const long long cells = (long long)(hi[0] - lo[0] + 1) * ((hi[1] >> 4) - (lo[1] >> 4) + 1) * ((hi[2] >> 4) - (lo[2] >> 4) + 1);
+        if (cells > 256) hit = true;  // a huge triangle: every rank takes it
+        else
+            for (int bx = lo[0]; bx <= hi[0] && !hit; ++bx)
+                for (int ny = lo[1] >> 4; ny <= (hi[1] >> 4) && !hit; ++ny)
+                    for (int nz = lo[2] >> 4; nz <= (hi[2] >> 4) && !hit; ++nz) {
+                        const unsigned long long k = bs_brick_key(bx, ny * 16, nz * 16) >> 8;
+                        hit = k >= klo && k < khi;
+                    }
+    }
+    keep[t] = hit ? 1 : 0;
+}
+__global__ void k_count_below(const unsigned long long* __restrict__ keys, size_t n, unsigned long long b0, unsigned long long b1, unsigned long long* out /*[2]*/) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    unsigned c0 = 0, c1 = 0;
+    if (i < n) { const unsigned long long k = keys[i]; if (k != BS_KEY_INVALID) { c0 = k < b0; c1 = k < b1; } }
+    c0 = __popc(__ballot_sync(0xFFFFFFFFu, c0)); c1 = __popc(__ballot_sync(0xFFFFFFFFu, c1));
+    if ((threadIdx.x & 31) == 0) { if (c0) atomicAdd(out, (unsigned long long)c0); if (c1) atomicAdd(out + 1, (unsigned long long)c1); }
+}
+
 struct NotEmptyKey { __device__ bool operator()(unsigned long long k) const { return k != BS_KEY_INVALID; } };
 
 __global__ void k_counts(const float* values, const unsigned long long* masks, size_t n_bricks, unsigned long long* out /*[2]*/) {
@@ -610,20 +688,67 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
     cudaStream_t st = ctx->stream;
     bs_marks_begin(ctx);
     BS_CUDA(ctx, cudaMemsetAsync(ctx->d_err, 0, sizeof(unsigned), st));
-    // 1. per-triangle sub-triangle counts + surface area in voxel^2 (sizing only)
-    unsigned long long *d_counts = nullptr, *d_offsets = nullptr; double* d_area = nullptr; int* d_flags = nullptr;
-    BS_TRY(bs_alloc(ctx, &d_counts, n_tris + 1)); BS_TRY(bs_alloc(ctx, &d_offsets, n_tris + 1));
-    BS_TRY(bs_alloc(ctx, &d_area, 1)); BS_TRY(bs_alloc(ctx, &d_flags, 2));
-    unsigned long long* d_neval = nullptr;
-    BS_TRY(bs_alloc(ctx, &d_neval, 1));
-    BS_CUDA(ctx, cudaMemsetAsync(d_area, 0, sizeof(double), st));
+    const size_t n_mesh = n_tris;  // triangles of the whole mesh (the sign stage needs all of them)
+    int* d_flags = nullptr;
+    BS_TRY(bs_alloc(ctx, &d_flags, 2));
     BS_CUDA(ctx, cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), st));
-    BS_CUDA(ctx, cudaMemsetAsync(d_counts + n_tris, 0, sizeof(unsigned long long), st));
-    // closed mesh? (bs_signprop.cu) -- enqueued here, read at the synchronisation below
+    // closed mesh? (bs_signprop.cu) -- enqueued here, read at the next synchronisation
     bs_closed_check chk; chk.pending = false; chk.closed = false; chk.exact = false; chk.d_sums = nullptr; chk.d_bad = nullptr;
     ctx->mesh_closed = false;
     if (ctx->sign_propagation) BS_TRY(bs_mesh_closed_begin(ctx, d_tris, n_tris, &chk));
-    bs_count_launch(), k_tri_counts<<<bs_blocks(n_tris, TPB), TPB, 0, st>>>(d_tris, n_tris, voxel_size, d_counts, d_area);
+    // 0. sharded: cut the coarse key space at equal sub-triangle weight, keep the triangles that can reach this rank's range
+    unsigned* d_tri_ids = nullptr; unsigned long long klo = 0, khi = BS_KEY_INVALID;
+    if (world > 1) {
+        const unsigned tcap = 1u << 20;
+        unsigned long long *d_tk = nullptr, *d_tw = nullptr, *d_sk = nullptr, *d_sw = nullptr, *d_C = nullptr, *d_bounds = nullptr; size_t* d_nsel = nullptr; void* d_tmp0 = nullptr; size_t tmp0 = 0, tmp1 = 0, tmp2 = 0;
+        BS_TRY(bs_alloc(ctx, &d_tk, (size_t)tcap)); BS_TRY(bs_alloc(ctx, &d_tw, (size_t)tcap)); BS_TRY(bs_alloc(ctx, &d_sk, (size_t)tcap)); BS_TRY(bs_alloc(ctx, &d_sw, (size_t)tcap));
+        BS_TRY(bs_alloc(ctx, &d_C, (size_t)tcap)); BS_TRY(bs_alloc(ctx, &d_bounds, (size_t)world + 1)); BS_TRY(bs_alloc(ctx, &d_nsel, 1));
+        BS_CUDA(ctx, cudaMemsetAsync(d_tk, 0xFF, tcap * sizeof(unsigned long long), st));
+        BS_CUDA(ctx, cudaMemsetAsync(d_tw, 0, tcap * sizeof(unsigned long long), st));
+        bs_count_launch(), k_coarse_hist<<<bs_blocks(n_tris, TPB), TPB, 0, st>>>(d_tris, n_tris, voxel_size, 1.0f / voxel_size, d_tk, d_tw, tcap - 1, d_flags);
+        // sort the (key, weight) pairs: empty slots (key = all ones, weight 0) go to the end
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp0, d_tk, d_sk, d_tw, d_sw, (int)tcap, 0, 64, st);
+        cub::DeviceScan::InclusiveSum(nullptr, tmp1, d_sw, d_C, (int)tcap, st);
+        cub::DeviceSelect::If(nullptr, tmp2, d_tk, d_sk, d_nsel, (int)tcap, NotEmptyKey(), st);
+        BS_TRY(bs_alloc(ctx, (char**)&d_tmp0, std::max(tmp0, std::max(tmp1, tmp2))));
+        cub::DeviceSelect::If(d_tmp0, tmp2, d_tk, d_sk, d_nsel, (int)tcap, NotEmptyKey(), st);  // (only for the count of occupied cells)
+        size_t n_cells = 0; int hflag[2] = {0, 0};
+        BS_CUDA(ctx, cudaMemcpyAsync(&n_cells, d_nsel, sizeof(size_t), cudaMemcpyDeviceToHost, st));
+        cub::DeviceRadixSort::SortPairs(d_tmp0, tmp0, d_tk, d_sk, d_tw, d_sw, (int)tcap, 0, 64, st);
+        cub::DeviceScan::InclusiveSum(d_tmp0, tmp1, d_sw, d_C, (int)tcap, st);
+        BS_CUDA(ctx, cudaMemcpyAsync(hflag, d_flags, sizeof(hflag), cudaMemcpyDeviceToHost, st));
+        BS_CUDA(ctx, cudaStreamSynchronize(st));
+        bs_count_launch(), k_coarse_cut<<<1, 64, 0, st>>>(d_sk, d_C, hflag[0] ? 0 : n_cells, world, d_bounds);
+        unsigned long long hb[2];
+        BS_CUDA(ctx, cudaMemcpyAsync(hb, d_bounds + rank, sizeof(hb), cudaMemcpyDeviceToHost, st));
+        BS_CUDA(ctx, cudaStreamSynchronize(st));
+        if (hflag[0]) { BS_CUDA(ctx, cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), st)); }  // (table full: rank 0 takes everything; still exact)
+        klo = hb[0]; khi = hb[1];
+        bs_free(ctx, d_tmp0); bs_free(ctx, d_tk); bs_free(ctx, d_tw); bs_free(ctx, d_sk); bs_free(ctx, d_sw); bs_free(ctx, d_C); bs_free(ctx, d_bounds);
+        // triangles whose inflated box reaches [klo, khi): one brick of halo + sub-triangle box slack (2) + band + 1
+        unsigned char* d_keep = nullptr;
+        BS_TRY(bs_alloc(ctx, &d_keep, n_tris)); BS_TRY(bs_alloc(ctx, &d_tri_ids, n_tris));
+        bs_count_launch(), k_select_tris<<<bs_blocks(n_tris, TPB), TPB, 0, st>>>(d_tris, n_tris, 1.0f / voxel_size, 11 + (int)band, klo, khi, d_keep);
+        tmp0 = 0;
+        cub::DeviceSelect::Flagged(nullptr, tmp0, cub::CountingInputIterator<unsigned>(0), d_keep, d_tri_ids, d_nsel, (int)n_tris, st);
+        BS_TRY(bs_alloc(ctx, (char**)&d_tmp0, tmp0));
+        cub::DeviceSelect::Flagged(d_tmp0, tmp0, cub::CountingInputIterator<unsigned>(0), d_keep, d_tri_ids, d_nsel, (int)n_tris, st);
+        size_t n_list = 0;
+        BS_CUDA(ctx, cudaMemcpyAsync(&n_list, d_nsel, sizeof(size_t), cudaMemcpyDeviceToHost, st));
+        BS_CUDA(ctx, cudaStreamSynchronize(st));
+        bs_free(ctx, d_tmp0); bs_free(ctx, d_keep); bs_free(ctx, d_nsel);
+        n_tris = n_list;  // from here on: this rank's triangle list
+        bs_mark(ctx, "shard_select_ms");
+    }
+    // 1. per-triangle sub-triangle counts + surface area in voxel^2 (sizing only)
+    unsigned long long *d_counts = nullptr, *d_offsets = nullptr; double* d_area = nullptr;
+    BS_TRY(bs_alloc(ctx, &d_counts, n_tris + 1)); BS_TRY(bs_alloc(ctx, &d_offsets, n_tris + 1));
+    BS_TRY(bs_alloc(ctx, &d_area, 1));
+    unsigned long long* d_neval = nullptr;
+    BS_TRY(bs_alloc(ctx, &d_neval, 1));
+    BS_CUDA(ctx, cudaMemsetAsync(d_area, 0, sizeof(double), st));
+    BS_CUDA(ctx, cudaMemsetAsync(d_counts + n_tris, 0, sizeof(unsigned long long), st));
+    if (n_tris) bs_count_launch(), k_tri_counts<<<bs_blocks(n_tris, TPB), TPB, 0, st>>>(d_tris, d_tri_ids, n_tris, voxel_size, d_counts, d_area);
     void* d_tmp = nullptr; size_t tmp_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_counts, d_offsets, n_tris + 1, st);
     BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp_bytes));
@@ -635,11 +760,23 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
     ctx->mesh_closed = ctx->sign_propagation && bs_mesh_closed_finish(ctx, &chk);
     bs_free(ctx, d_tmp); bs_free(ctx, d_counts); bs_free(ctx, d_area);
     bs_mark(ctx, "subdivide_count_ms");
+    if (total == 0 && world > 1) {  // nothing of the mesh reaches this rank's range: an empty slab
+        bs_free(ctx, d_offsets); bs_free(ctx, d_flags); bs_free(ctx, d_neval); bs_free(ctx, d_tri_ids);
+        bs_volume* ev = bs_volume_new(ctx, voxel_size);
+        bs_status es = bs_volume_alloc_bricks(ev, 0);
+        if (es == BS_OK) es = bs_alloc(ctx, &ev->owned, (size_t)1);
+        if (es != BS_OK) { bs_volume_free(ev); return es; }
+        ev->n_owned = 0;
+        bs_marks_end(ctx);
+        bs_stat_add(ctx, "n_tris", (double)n_mesh); bs_stat_add(ctx, "n_bricks", 0.0); bs_stat_add(ctx, "n_bricks_owned", 0.0); bs_stat_add(ctx, "n_active", 0.0);
+        *out = ev;
+        return BS_OK;
+    }
     if (total == 0) { bs_free(ctx, d_offsets); bs_free(ctx, d_flags); bs_free(ctx, d_neval); bs_marks_end(ctx); return BS_ERR_EMPTY_MESH; }  // convert -> None (:58-60)
     if (total > (1ull << 40)) { bs_free(ctx, d_offsets); bs_free(ctx, d_flags); bs_free(ctx, d_neval); return bs_fail(ctx, BS_ERR_RANGE, "%llu sub-triangles: voxel size too small for this mesh", total); }
 
     ConvertParams P;
-    P.tris = d_tris; P.n_tris = n_tris; P.offsets = d_offsets; P.total = total;
+    P.tris = d_tris; P.n_tris = n_tris; P.tri_ids = d_tri_ids; P.offsets = d_offsets; P.total = total;
     P.vs = voxel_size; P.inv_vs = 1.0f / voxel_size; P.band = (int)band; P.flags = d_flags; P.values = nullptr; P.n_eval = d_neval; P.table_counts = nullptr; P.use_clip = 0; P.derr = ctx->d_err;
 
     // 2. mark touched bricks in a hash set; sized from the surface area, doubled on overflow
@@ -692,29 +829,20 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
     bs_status s = BS_OK;
     const size_t n_total = n_all;
     if (world > 1) {
-        // brick-slab sharding: this rank owns the contiguous slab [lo, hi) of the sorted brick list and keeps, as
-        // read-only halo, the 26 neighbours of its bricks (extraction needs +1 for MC, -1..+1 for DC)
-        // slab boundaries at equal cumulative weight (k_brick_weights): bricks under dense triangles (e.g. the poles of a
-        // UV sphere) cost hundreds of times more in the sign stage
+        // brick-slab sharding: this rank owns the bricks whose coarse key lies in [klo, khi) -- a contiguous slab [lo, hi) of
+        // the sorted brick list -- and keeps, as read-only halo, the 26 neighbours of its bricks (extraction needs +1 for MC,
+        // -1..+1 for DC). The local list also holds bricks further out (the triangle selection is conservative): dropped here.
         size_t lo, hi;
         {
-            unsigned long long *d_touch = nullptr, *d_C = nullptr, *d_bounds = nullptr; unsigned long long h_bounds[2];
-            BS_TRY(bs_alloc(ctx, &d_touch, n_all)); BS_TRY(bs_alloc(ctx, &d_C, n_all)); BS_TRY(bs_alloc(ctx, &d_bounds, (size_t)world + 1));
-            bs_count_launch(), k_brick_touches<<<bs_blocks(n_all, TPB), TPB, 0, st>>>(d_keys, n_all, d_table_keys, d_table_counts, (unsigned)(cap - 1), d_touch, ctx->d_err);
-            tmp_bytes = 0;
-            cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, d_touch, d_C, n_all, st);
-            BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp_bytes));
-            cub::DeviceScan::InclusiveSum(d_tmp, tmp_bytes, d_touch, d_C, n_all, st);
-            unsigned long long* d_w = nullptr;
-            BS_TRY(bs_alloc(ctx, &d_w, n_all));
-            bs_count_launch(), k_brick_weights<<<bs_blocks(n_all, TPB), TPB, 0, st>>>(d_touch, d_C, n_all, d_w);
-            cub::DeviceScan::InclusiveSum(d_tmp, tmp_bytes, d_w, d_C, n_all, st);
-            bs_free(ctx, d_w);
-            bs_count_launch(), k_slab_bounds<<<1, 64, 0, st>>>(d_C, n_all, world, d_bounds);
-            BS_CUDA(ctx, cudaMemcpyAsync(h_bounds, d_bounds + rank, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            unsigned long long* d_lh = nullptr; unsigned long long h_lh[2] = {0, 0};
+            BS_TRY(bs_alloc(ctx, &d_lh, 2));
+            BS_CUDA(ctx, cudaMemsetAsync(d_lh, 0, 2 * sizeof(unsigned long long), st));
+            const unsigned long long b0 = klo << 8, b1 = khi == BS_KEY_INVALID ? BS_KEY_INVALID : (khi << 8);
+            if (n_all) bs_count_launch(), k_count_below<<<bs_blocks(n_all, TPB), TPB, 0, st>>>(d_keys, n_all, b0, b1, d_lh);
+            BS_CUDA(ctx, cudaMemcpyAsync(h_lh, d_lh, sizeof(h_lh), cudaMemcpyDeviceToHost, st));
             BS_CUDA(ctx, cudaStreamSynchronize(st));
-            bs_free(ctx, d_tmp); bs_free(ctx, d_touch); bs_free(ctx, d_C); bs_free(ctx, d_bounds);
-            lo = (size_t)h_bounds[0]; hi = (size_t)h_bounds[1];
+            bs_free(ctx, d_lh);
+            lo = (size_t)h_lh[0]; hi = (size_t)h_lh[1];
             if (hi < lo) hi = lo;
         }
         unsigned char* d_keep = nullptr; unsigned long long* d_kept = nullptr; size_t* d_nk = nullptr; size_t n_kept = 0;
@@ -750,17 +878,7 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
     // 4. distances
     P.table_slots = d_table_slots; P.values = vol->values;
     P.use_clip = 0;
-    if (world > 1 && n_all) {
-        int* d_kb = nullptr; int h_kb[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
-        BS_TRY(bs_alloc(ctx, &d_kb, 6));
-        BS_CUDA(ctx, cudaMemcpyAsync(d_kb, h_kb, sizeof(h_kb), cudaMemcpyHostToDevice, st));
-        bs_count_launch(), k_key_bounds<<<bs_blocks(n_all, TPB), TPB, 0, st>>>(vol->keys, n_all, d_kb);
-        BS_CUDA(ctx, cudaMemcpyAsync(h_kb, d_kb, sizeof(h_kb), cudaMemcpyDeviceToHost, st));
-        BS_CUDA(ctx, cudaStreamSynchronize(st));
-        bs_free(ctx, d_kb);
-        P.use_clip = 1;
-        for (int d = 0; d < 3; ++d) { P.clip_mn[d] = h_kb[d]; P.clip_mx[d] = h_kb[3 + d]; }
-    }
+    // (sharded runs work on this rank's triangle list: no further clipping)
     bs_count_launch(), k_eval<<<grid, TPB, 0, st>>>(P);
     bs_mark(ctx, "udf_ms");
     // closed mesh: lattice edges met by a triangle (sign propagation, bs_signprop.cu); needs the brick hash, so it runs here
@@ -782,8 +900,8 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
     if (n_all) bs_count_launch(), k_brick_touches<<<bs_blocks(n_all, TPB), TPB, 0, st>>>(vol->keys, n_all, d_table_keys, d_table_counts, (unsigned)(cap - 1), d_touch_kept, ctx->d_err);
     bs_free(ctx, d_table_keys); bs_free(ctx, d_table_slots); bs_free(ctx, d_table_counts); bs_free(ctx, d_offsets); bs_free(ctx, d_flags); bs_free(ctx, d_neval);
     // 5. signs + masks
-    s = bs_sign_impl(ctx, d_tris, n_tris, vol, d_touch_kept, d_blk);
-    bs_free(ctx, d_touch_kept); bs_free(ctx, d_blk);
+    s = bs_sign_impl(ctx, d_tris, n_mesh, vol, d_touch_kept, d_blk);  // winding numbers see the whole mesh
+    bs_free(ctx, d_touch_kept); bs_free(ctx, d_blk); bs_free(ctx, d_tri_ids);
     if (s != BS_OK) { bs_volume_free(vol); return s; }
     BS_CUDA(ctx, cudaGetLastError());
     unsigned derr = 0;
@@ -793,7 +911,8 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
         bs_volume_free(vol);
         return bs_fail(ctx, BS_ERR_RANGE, "device limit exceeded:%s%s", (derr & BS_DERR_STACK) ? " winding-number traversal stack" : "", (derr & BS_DERR_PROBE) ? " brick hash probe length" : "");
     }
-    bs_stat_add(ctx, "n_tris", (double)n_tris);
+    bs_stat_add(ctx, "n_tris", (double)n_mesh);
+    bs_stat_add(ctx, "n_tris_local", (double)n_tris);
     bs_stat_add(ctx, "n_sub", (double)total);
     bs_stat_add(ctx, "n_bricks", (double)n_all);
     bs_stat_add(ctx, "n_bricks_total", (double)n_total);

@@ -202,3 +202,37 @@ def test_heavy_split_on_bunny_matches_unsplit_signs(bs, bunny, monkeypatch):
     m = active_mask_bits(a["masks"])
     diff = np.signbit(a["values"][m]) != np.signbit(b["values"][m])
     assert diff.mean() < 2e-3  # the split walk refines some far nodes: only voxels at the 0.2 threshold may move
+
+
+@pytest.mark.parametrize("world", [2, 4, 7])
+def test_sharded_ranks_partition_the_volume_exactly(bs, world):
+    # every rank derives the same coarse cut and works on its own triangle list; owned bricks must partition the unsharded
+    # brick list in order, with identical values, and every rank's halo must carry exact values too
+    import ctypes as C
+    import torch
+    from baby_shark_b200 import synth
+    from util import active_mask_bits
+    tris, vs, _ = synth.config_mesh(5, 0.125)
+    L, ctx = bs.load_library(), bs.Context.default()
+    d_tris = torch.from_numpy(tris).cuda()
+    full = bs.MeshToVolume().with_voxel_size(vs).convert(tris).download()
+    index = {tuple(o): i for i, o in enumerate(full["origins"].tolist())}
+    fa = active_mask_bits(full["masks"])
+    owned_total, nonempty = 0, 0
+    for r in range(world):
+        h = C.c_void_p()
+        ctx.check(L.bs_mesh_to_volume_sharded(ctx._h, C.c_void_p(d_tris.data_ptr()), tris.shape[0], vs, 0, r, world, C.byref(h)))
+        st = ctx.last_stats()
+        owned_total += int(st["n_bricks_owned"])
+        nonempty += st["n_bricks_owned"] > 0
+        assert st["n_tris_local"] < tris.shape[0] or world == 1
+        d = bs.Volume(h, ctx).download()
+        if d["origins"].shape[0] == 0:
+            continue
+        idx = np.array([index[tuple(o)] for o in d["origins"].tolist()])  # every kept brick exists in the unsharded volume
+        assert np.all(np.diff(idx) > 0)
+        a = active_mask_bits(d["masks"])
+        assert np.array_equal(a, fa[idx])
+        assert np.array_equal(d["values"][a].view(np.uint32), full["values"][idx][a].view(np.uint32))
+    assert owned_total == full["origins"].shape[0]
+    assert nonempty >= min(world, 2)
