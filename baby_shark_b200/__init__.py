@@ -32,6 +32,7 @@ EXPORTS = [
     "bs_volume_download", "bs_volume_counts", "bs_context_last_stats", "bs_context_copy_out_verts", "bs_context_copy_out_verts_device", "bs_context_set_flag", "bs_kernel_launch_count",
     "bs_stl_decode", "bs_stl_decode_device", "bs_stl_encode", "bs_stl_encode_device", "bs_mesh_active_voxels", "bs_mesh_active_voxels_device",
     "bs_merge_points", "bs_merge_points_device", "bs_device_free", "bs_mesh_mc_indexed", "bs_mesh_mc_indexed_device", "bs_copy_to_host",
+    "bs_ipc_alloc", "bs_ipc_open", "bs_ipc_close", "bs_ipc_free", "bs_context_push_out_verts",
 ]
 
 
@@ -108,6 +109,11 @@ def load_library(path=None):
         "bs_mesh_mc_indexed": (C.c_int, [vp, C.c_float, pvp, psz, pvp, psz]),
         "bs_mesh_mc_indexed_device": (C.c_int, [vp, C.c_float, pvp, psz, pvp, psz]),
         "bs_copy_to_host": (C.c_int, [vp, vp, vp, sz]),
+        "bs_ipc_alloc": (C.c_int, [vp, sz, pvp, C.c_char_p]),
+        "bs_ipc_open": (C.c_int, [vp, C.c_char_p, pvp]),
+        "bs_ipc_close": (C.c_int, [vp, vp]),
+        "bs_ipc_free": (C.c_int, [vp, vp]),
+        "bs_context_push_out_verts": (C.c_int, [vp, pvp, C.c_int, sz, sz]),
     }
     for name, (res, args) in sigs.items():
         f = getattr(L, name)

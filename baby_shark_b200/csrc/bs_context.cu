@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 
 bs_status bs_fail(bs_context* ctx, bs_status st, const char* fmt, ...) {
     char buf[1024];
@@ -64,6 +65,17 @@ template <class T> static bs_status to_host(bs_context* c, T** dst, const T* src
 }
 
 unsigned long long g_bs_launches = 0;
+
+// one source, up to 16 destinations (peers' buffers mapped over NVLink, own buffer included): each value is read once and
+// stored `world` times; 4-byte accesses because a slice starts at a multiple of 9 floats, not of 16 bytes
+struct PushDst { float* p[16]; };
+__global__ void __launch_bounds__(256) k_push_out_verts(const float* __restrict__ src, PushDst D, int world, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = src[i];
+#pragma unroll 4
+        for (int d = 0; d < world; ++d) D.p[d][i] = v;
+    }
+}
 
 // ---- block cache ------------------------------------------------------------------------------------------------------
 // cudaMallocAsync on the default pool showed sporadic 100-500 ms stalls in steady state (pool growth / remapping when
@@ -184,6 +196,51 @@ bs_status bs_context_copy_out_verts_device(bs_context* ctx, float* d_dst, size_t
     if (n_floats > ctx->out_verts_cap) return bs_fail(ctx, BS_ERR_INVALID, "no extraction result of that size on the device");
     if (n_floats) BS_CUDA(ctx, cudaMemcpyAsync(d_dst, ctx->d_out_verts, n_floats * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
     BS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return BS_OK;
+}
+bs_status bs_ipc_alloc(bs_context* ctx, size_t bytes, void** d_ptr, unsigned char handle[64]) {
+    if (!ctx || !d_ptr || !handle) return BS_ERR_INVALID;
+    BS_ENTER(ctx);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    *d_ptr = nullptr;
+    BS_CUDA(ctx, cudaMalloc(d_ptr, bytes ? bytes : 256));
+    cudaIpcMemHandle_t h;
+    const cudaError_t e = cudaIpcGetMemHandle(&h, *d_ptr);
+    if (e != cudaSuccess) { cudaFree(*d_ptr); *d_ptr = nullptr; return bs_fail(ctx, BS_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); }
+    memcpy(handle, &h, 64);
+    return BS_OK;
+}
+bs_status bs_ipc_open(bs_context* ctx, const unsigned char handle[64], void** d_ptr) {
+    if (!ctx || !d_ptr || !handle) return BS_ERR_INVALID;
+    BS_ENTER(ctx);
+    cudaIpcMemHandle_t h; memcpy(&h, handle, 64);
+    BS_CUDA(ctx, cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return BS_OK;
+}
+bs_status bs_ipc_close(bs_context* ctx, void* d_ptr) {
+    if (!ctx) return BS_ERR_INVALID;
+    BS_ENTER(ctx);
+    if (d_ptr) { BS_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); BS_CUDA(ctx, cudaIpcCloseMemHandle(d_ptr)); }
+    return BS_OK;
+}
+bs_status bs_ipc_free(bs_context* ctx, void* d_ptr) {
+    if (!ctx) return BS_ERR_INVALID;
+    BS_ENTER(ctx);
+    if (d_ptr) { BS_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); BS_CUDA(ctx, cudaFree(d_ptr)); }
+    return BS_OK;
+}
+bs_status bs_context_push_out_verts(bs_context* ctx, float* const* dst, int world, size_t offset_floats, size_t n_floats) {
+    if (!ctx || !dst || world < 1 || world > 16) return BS_ERR_INVALID;
+    BS_ENTER(ctx);
+    if (n_floats > ctx->out_verts_cap) return bs_fail(ctx, BS_ERR_INVALID, "no extraction result of that size on the device");
+    PushDst D;
+    for (int d = 0; d < 16; ++d) D.p[d] = d < world ? (dst[d] ? dst[d] + offset_floats : nullptr) : nullptr;
+    for (int d = 0; d < world; ++d) if (!D.p[d]) return bs_fail(ctx, BS_ERR_INVALID, "null destination %d", d);
+    if (n_floats) {
+        const unsigned grid = (unsigned)std::min<size_t>(bs_blocks(n_floats, 256), (size_t)ctx->sm_count * 16);
+        bs_count_launch(), k_push_out_verts<<<grid, 256, 0, ctx->stream>>>(ctx->d_out_verts, D, world, n_floats);
+    }
+    BS_CUDA(ctx, cudaGetLastError());
     return BS_OK;
 }
 bs_status bs_context_copy_out_verts(bs_context* ctx, float* dst, size_t n_floats) {

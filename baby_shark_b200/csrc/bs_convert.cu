@@ -699,7 +699,7 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
     // 0. sharded: cut the coarse key space at equal sub-triangle weight, keep the triangles that can reach this rank's range
     unsigned* d_tri_ids = nullptr; unsigned long long klo = 0, khi = BS_KEY_INVALID;
     if (world > 1) {
-        const unsigned tcap = 1u << 20;
+        const unsigned tcap = 1u << 17;  // coarse cells that can be occupied: the table is sorted whole, keep it small
         unsigned long long *d_tk = nullptr, *d_tw = nullptr, *d_sk = nullptr, *d_sw = nullptr, *d_C = nullptr, *d_bounds = nullptr; size_t* d_nsel = nullptr; void* d_tmp0 = nullptr; size_t tmp0 = 0, tmp1 = 0, tmp2 = 0;
         BS_TRY(bs_alloc(ctx, &d_tk, (size_t)tcap)); BS_TRY(bs_alloc(ctx, &d_tw, (size_t)tcap)); BS_TRY(bs_alloc(ctx, &d_sk, (size_t)tcap)); BS_TRY(bs_alloc(ctx, &d_sw, (size_t)tcap));
         BS_TRY(bs_alloc(ctx, &d_C, (size_t)tcap)); BS_TRY(bs_alloc(ctx, &d_bounds, (size_t)world + 1)); BS_TRY(bs_alloc(ctx, &d_nsel, 1));

@@ -45,6 +45,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sign-propagation", action="store_true",
                     help="A/B switch: per-voxel winding numbers even on closed meshes (BS_FLAG_SIGN_PROPAGATION = 0); recorded in config")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1 output exchange: p2p = every rank stores its slice into all peers' buffers over NVLink (bs_context_push_out_verts, "
+                         "CUDA IPC mapped peer memory); nccl = torch.distributed all-gather (the baseline)")
     ap.add_argument("--io", action="store_true", help="time the rows either side of the path on the --config mesh: STL decode / encode, merge_points, ActiveVoxelsMesher")
     ap.add_argument("--ops", action="store_true", help="time the CSG (config 2) / offset (3) / dual contouring (4) rows instead of the remesh")
     return ap.parse_args()
@@ -380,14 +383,60 @@ def main():
         def __init__(self, ptr, n):
             self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
 
+    peer = {"cap": 0, "own": None, "ptrs": None, "fence": None}
+
+    def exchange_counts(n_floats):
+        cnt = torch.tensor([n_floats], dtype=torch.int64, device="cuda")
+        got = [torch.zeros_like(cnt) for _ in range(world)]
+        dist.all_gather(got, cnt)
+        return [int(c.item()) for c in got]
+
+    def peer_buffers(total_floats):
+        """(re)allocate this rank's result buffer as an IPC-shareable allocation and map every peer's (bs_ipc_*)"""
+        if peer["ptrs"] is not None:
+            for r, p in enumerate(peer["ptrs"]):
+                if r != rank:
+                    ctx.check(L.bs_ipc_close(ctx._h, C.c_void_p(p)))
+            dist.barrier()
+            ctx.check(L.bs_ipc_free(ctx._h, C.c_void_p(peer["own"])))
+        cap = int(total_floats * 1.1) + 1024
+        own, handle = C.c_void_p(), C.create_string_buffer(64)
+        ctx.check(L.bs_ipc_alloc(ctx._h, cap * 4, C.byref(own), handle))
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle.raw))
+        ptrs = []
+        for r in range(world):
+            if r == rank:
+                ptrs.append(own.value)
+            else:
+                q = C.c_void_p()
+                ctx.check(L.bs_ipc_open(ctx._h, handles[r], C.byref(q)))
+                ptrs.append(q.value)
+        peer.update({"cap": cap, "own": own.value, "ptrs": ptrs, "arr": (C.c_void_p * world)(*ptrs), "fence": torch.zeros(1, device="cuda")})
+        dist.barrier()
+
     def gather(dv_ptr, n_floats):
-        """the path's one exchange: all-gather(v) of the compacted triangle buffers over NVLink (NCCL), straight out of the
-        library's result buffer into the final one, on the library's stream (so the stream's events time it). The per-rank
-        sizes of a steady workload are those of the previous step: no count exchange, no host synchronisation."""
-        local = torch.as_tensor(_DeviceF32(dv_ptr, n_floats), device="cuda")
+        """the path's one exchange: every rank ends up with the whole triangle soup, in rank order. The per-rank sizes of a
+        steady workload are those of the previous step: no count exchange, no host synchronisation inside the step.
+        p2p (default): each rank stores its slice into every rank's result buffer with one kernel (peer memory over NVLink,
+        bs_context_push_out_verts) and a one-element all-reduce on the same stream is the "everyone has delivered" fence;
+        nccl: torch.distributed all-gather straight out of the library's buffer (the baseline)."""
         counts = gather_buf["counts"]
         if counts is not None and counts[rank] != n_floats:
             counts = None
+        if args.gather == "p2p":
+            if counts is None:
+                counts = exchange_counts(n_floats)
+                gather_buf["counts"] = counts
+            total = sum(counts)
+            if peer["cap"] < total:
+                peer_buffers(total)
+            ctx.check(L.bs_context_push_out_verts(ctx._h, peer["arr"], world, sum(counts[:rank]), n_floats))
+            with torch.cuda.stream(stream):
+                dist.all_reduce(peer["fence"])
+            gather_buf["out"] = torch.as_tensor(_DeviceF32(peer["own"], total), device="cuda")
+            return gather_buf["out"]
+        local = torch.as_tensor(_DeviceF32(dv_ptr, n_floats), device="cuda")
         with torch.cuda.stream(stream):
             full, counts = all_gather_varlen(local, out=gather_buf["out"], counts=counts)
         if gather_buf["out"] is None or gather_buf["out"].data_ptr() != full.data_ptr():
@@ -395,16 +444,26 @@ def main():
         gather_buf["counts"] = counts
         return full
 
-    def step_device():
+    phase_ev = []  # (convert done, MC done, gather done) events of every timed step, on the library's stream
+
+    def step_device(record=False):
         """convert + MC (+ all-gather when sharded), input and output resident in HBM; returns local vertex count."""
         h = C.c_void_p()
         ctx.check(L.bs_mesh_to_volume_sharded(ctx._h, C.c_void_p(d_tris.data_ptr()), n_tris, vs, 0, rank, world, C.byref(h)))
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if record else None
+        if record:
+            ev[0].record(stream)
         dv, nv = C.c_void_p(), C.c_size_t()
         st = L.bs_mesh_mc_device(h, vs, C.byref(dv), C.byref(nv))
         L.bs_volume_free(h)
         ctx.check(st)
+        if record:
+            ev[1].record(stream)
         if world > 1:
             gather(dv.value, nv.value * 3)
+        if record:
+            ev[2].record(stream)
+            phase_ev.append(ev)
         return dv.value, nv.value, None
 
     h_out = None
@@ -499,7 +558,7 @@ def main():
     launches0 = L.bs_kernel_launch_count()
     marks = []
     for _ in range(args.steps):
-        _, nv, _ = step_device()
+        _, nv, _ = step_device(record=True)
         n_verts_local = nv
         marks.append(torch.cuda.Event(enable_timing=True))
         marks[-1].record(stream)
@@ -512,6 +571,10 @@ def main():
     clocks = sampler.finish()
     ms_total = e0.elapsed_time(e1)
     step_ms = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
+    starts = [e0] + marks[:-1]
+    phase_ms = {"convert_call": sum(a.elapsed_time(ev[0]) for a, ev in zip(starts, phase_ev)) / args.steps,
+                "mc_call": sum(ev[0].elapsed_time(ev[1]) for ev in phase_ev) / args.steps,
+                "all_gather": sum(ev[1].elapsed_time(ev[2]) for ev in phase_ev) / args.steps}
 
     # per-stage device times of convert (CUDA events on the library's stream), averaged over a few extra passes
     conv_ms = {}
@@ -538,6 +601,13 @@ def main():
     # ---- self-check: the vertices the e2e leg just delivered to the host (and, on one GPU, the volume itself) must be the
     # CPU oracle's, bit for bit and in order (fingerprints written by tests/golden/make_config_hashes.py at this size) ------
     verify_out = None
+    gathered_host = None
+    if world > 1:  # one more exchange, run by EVERY rank (it ends in a collective fence); rank 0 checks what it received
+        step_device()
+        torch.cuda.synchronize()
+        if rank == 0:
+            gathered_host = gather_buf["out"].cpu()
+        barrier()
     if rank == 0:
         from baby_shark_b200 import verify
         try:
@@ -547,6 +617,10 @@ def main():
         if golden is not None:
             host = shm["t"][: shm["offs"][world]] if world > 1 else h_out[: int(nv_e2e) * 3]
             got = verify.fingerprint_soup(host.numpy())
+            if world > 1 and gathered_host is not None:  # the device-resident result of the value leg's exchange as well
+                g2 = verify.fingerprint_soup(gathered_host.numpy())
+                got["gathered_ok"] = bool(g2 == {k: got[k] for k in g2})
+                golden = dict(golden, gathered_ok=True)
             if world == 1:
                 hv = C.c_void_p()
                 ctx.check(L.bs_mesh_to_volume_device(ctx._h, C.c_void_p(d_tris.data_ptr()), n_tris, vs, 0, C.byref(hv)))
@@ -669,9 +743,9 @@ def main():
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "config %d: %s" % (args.config, workload_desc(args)), "mesh": desc, "n_triangles": int(n_tris), "voxel_size": vs,
                        "band_width": 0, "l2": "inputs larger than L2 (triangles %.0f MB, bricks %.0f MB)" % (tris.nbytes / 1e6, work.get("n_bricks", 0) * 2112 / 1e6),
-                       "parallelism": "brick slabs x%d, mesh replicated" % world, "sign_propagation": bool(work.get("sign_propagation", 0.0))},
+                       "parallelism": "brick slabs x%d, mesh replicated" % world, "output_exchange": (args.gather if world > 1 else None), "sign_propagation": bool(work.get("sign_propagation", 0.0))},
             "remesh_ms": ms_per_step, "tris_per_s": (n_verts / 3.0) / (ms_per_step * 1e-3), "n_active_voxels": n_active, "n_out_triangles": n_verts / 3.0,
-            "step_ms": step_ms, "stage_ms": stage_all, "stage_ms_per_rank": per_rank, "work": work,
+            "step_ms": step_ms, "step_phase_ms": phase_ms, "stage_ms": stage_all, "stage_ms_per_rank": per_rank, "work": work,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": int(tris.nbytes), "d2h_bytes_per_step": int(n_verts * 12),
                     "what": "pinned host triangles in (N > 1: uploaded by rank 0, broadcast over NVLink), all output vertices back in host memory (N > 1: every rank copies its slice into one shared page-locked buffer)"},
             "e2e_indexed": None, "gpu_launches": None, "clocks": clocks,
@@ -695,6 +769,13 @@ def main():
                                    "sample": "config %d at scale %g: %s (%d triangles, %d active voxels), one convert + MC pass in %.1f s" % (args.config, cpu_scale, cdesc, ctris.shape[0], nv_c, dt_c)}
         print(json.dumps(out))
     if world > 1:
+        if peer["ptrs"] is not None:  # unmap the peers' buffers before anyone frees its own
+            torch.cuda.synchronize()
+            for r, q in enumerate(peer["ptrs"]):
+                if r != rank:
+                    L.bs_ipc_close(ctx._h, C.c_void_p(q))
+            dist.barrier()
+            L.bs_ipc_free(ctx._h, C.c_void_p(peer["own"]))
         dist.destroy_process_group()
 
 

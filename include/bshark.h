@@ -172,6 +172,22 @@ bs_status bs_context_copy_out_verts(bs_context* ctx, float* dst, size_t n_floats
 /* Same into device memory of the context's device (e.g. the send buffer of the multi-GPU all-gather). */
 bs_status bs_context_copy_out_verts_device(bs_context* ctx, float* d_dst, size_t n_floats);
 
+/* ---- multi-GPU output exchange over NVLink peer memory (one process per GPU) ---------------------------------------
+ * The brick-sharded remesh ends with every rank holding the whole triangle soup (north_star: "all-gather the compacted
+ * output triangle buffers"). Instead of a collective library the ranks write their slices straight into each other's
+ * result buffers: bs_ipc_alloc gives a device buffer plus a 64-byte CUDA IPC handle that the host exchanges by any means
+ * (bench.py: torch.distributed all_gather_object), bs_ipc_open maps a peer's buffer into this process (peer access over
+ * NVLink / NVSwitch is enabled by the mapping), and bs_context_push_out_verts copies the first n_floats of the last *_device
+ * extraction result into `world` destinations (own buffer included) at element offset `offset_floats` with ONE kernel --
+ * every byte crosses NVLink once, as P2P stores issued by the producing GPU. The call returns when the copies have been
+ * issued on the context's stream; the caller orders consumers behind it (a one-element all-reduce on that stream is the
+ * "everyone has delivered" fence bench.py uses). BS_ERR_INVALID when there is no extraction result of that size. */
+bs_status bs_ipc_alloc(bs_context* ctx, size_t bytes, void** d_ptr, unsigned char handle[64]);
+bs_status bs_ipc_open(bs_context* ctx, const unsigned char handle[64], void** d_ptr);
+bs_status bs_ipc_close(bs_context* ctx, void* d_ptr);   /* a pointer from bs_ipc_open */
+bs_status bs_ipc_free(bs_context* ctx, void* d_ptr);    /* a pointer from bs_ipc_alloc */
+bs_status bs_context_push_out_verts(bs_context* ctx, float* const* dst, int world, size_t offset_floats, size_t n_floats);
+
 /* BS_FLAG_COUNT_WORK = 1: the next bs_mesh_to_volume* calls run the instrumented winding-number traversal and
  * report fwn_visits / fwn_far / fwn_exact_tris / fwn_voxels through bs_context_last_stats (roofline work counts;
  * slower, never used in a timed region).
