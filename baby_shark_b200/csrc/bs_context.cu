@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cstdint>
 #include <algorithm>
 
 bs_status bs_fail(bs_context* ctx, bs_status st, const char* fmt, ...) {
@@ -67,14 +68,21 @@ template <class T> static bs_status to_host(bs_context* c, T** dst, const T* src
 unsigned long long g_bs_launches = 0;
 
 // one source, up to 16 destinations (peers' buffers mapped over NVLink, own buffer included): each value is read once and
-// stored `world` times; 4-byte accesses because a slice starts at a multiple of 9 floats, not of 16 bytes
+// stored `world` times. A slice starts at a multiple of 9 floats, not of 16 bytes, and source and destination are out of
+// phase: the body is cut into DESTINATION-aligned float4 stores (NVLink likes wide writes) fed by four scalar loads, the
+// ragged head and tail go out as single floats.
 struct PushDst { float* p[16]; };
-__global__ void __launch_bounds__(256) k_push_out_verts(const float* __restrict__ src, PushDst D, int world, size_t n) {
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const float v = src[i];
+__global__ void __launch_bounds__(256) k_push_out_verts(const float* __restrict__ src, PushDst D, int world, size_t n, unsigned head /*floats before the first 16 B boundary of the destinations*/) {
+    const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    const size_t h = head < n ? head : n, body4 = (n - h) / 4, tail0 = h + body4 * 4;
+    for (size_t q = tid; q < body4; q += stride) {
+        const float* s = src + h + q * 4;
+        const float4 v = make_float4(s[0], s[1], s[2], s[3]);
 #pragma unroll 4
-        for (int d = 0; d < world; ++d) D.p[d][i] = v;
+        for (int d = 0; d < world; ++d) reinterpret_cast<float4*>(D.p[d] + h)[q] = v;
     }
+    if (tid < h) { const float v = src[tid]; for (int d = 0; d < world; ++d) D.p[d][tid] = v; }
+    if (tid < n - tail0) { const float v = src[tail0 + tid]; for (int d = 0; d < world; ++d) D.p[d][tail0 + tid] = v; }
 }
 
 // ---- block cache ------------------------------------------------------------------------------------------------------
@@ -237,8 +245,11 @@ bs_status bs_context_push_out_verts(bs_context* ctx, float* const* dst, int worl
     for (int d = 0; d < 16; ++d) D.p[d] = d < world ? (dst[d] ? dst[d] + offset_floats : nullptr) : nullptr;
     for (int d = 0; d < world; ++d) if (!D.p[d]) return bs_fail(ctx, BS_ERR_INVALID, "null destination %d", d);
     if (n_floats) {
-        const unsigned grid = (unsigned)std::min<size_t>(bs_blocks(n_floats, 256), (size_t)ctx->sm_count * 16);
-        bs_count_launch(), k_push_out_verts<<<grid, 256, 0, ctx->stream>>>(ctx->d_out_verts, D, world, n_floats);
+        // all destinations share the offset, and allocations are 256 B aligned: one phase for every destination
+        const unsigned mis = (unsigned)(((uintptr_t)D.p[0] >> 2) & 3u), head = mis ? 4u - mis : 0u;
+        for (int d = 1; d < world; ++d) if ((((uintptr_t)D.p[d] >> 2) & 3u) != mis) return bs_fail(ctx, BS_ERR_INVALID, "destination buffers must be 16-byte aligned at their base");
+        const unsigned grid = (unsigned)std::min<size_t>(bs_blocks(n_floats / 4 + 8, 256), (size_t)ctx->sm_count * 16);
+        bs_count_launch(), k_push_out_verts<<<grid, 256, 0, ctx->stream>>>(ctx->d_out_verts, D, world, n_floats, head);
     }
     BS_CUDA(ctx, cudaGetLastError());
     return BS_OK;

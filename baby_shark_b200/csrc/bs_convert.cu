@@ -588,12 +588,17 @@ __global__ void k_coarse_hist(const float* __restrict__ tris, size_t n_tris, flo
     const float cx = (p1.x + p2.x + p3.x) * (1.0f / 3.0f) * inv_vs, cy = (p1.y + p2.y + p3.y) * (1.0f / 3.0f) * inv_vs, cz = (p1.z + p2.z + p3.z) * (1.0f / 3.0f) * inv_vs;
     if (!(fabsf(cx) < 1.0e6f && fabsf(cy) < 1.0e6f && fabsf(cz) < 1.0e6f)) return;  // k_mark reports range errors
     const unsigned long long key = coarse_key_of_voxel((int)floorf(cx), (int)floorf(cy), (int)floorf(cz));
+    // neighbouring triangles mostly share a cell: one table update per distinct key of the (active part of the) warp
+    const unsigned act = __activemask(), peers = __match_any_sync(act, key), leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
+    unsigned long long sum = 0;
+    for (unsigned m = peers; m; m &= m - 1) sum += __shfl_sync(peers, w, __ffs(m) - 1);
+    if (lane != leader) return;
     unsigned h = (unsigned)hash64(key) & mask;
     for (int probe = 0; probe < 4096; ++probe) {
         const unsigned long long cur = tkeys[h];
         bool mine = cur == key;
         if (!mine && cur == BS_KEY_INVALID) { const unsigned long long prev = atomicCAS(&tkeys[h], BS_KEY_INVALID, key); mine = prev == BS_KEY_INVALID || prev == key; }
-        if (mine) { atomicAdd(&tw[h], w); return; }
+        if (mine) { atomicAdd(&tw[h], sum); return; }
         h = (h + 1) & mask;
     }
     flags[0] = 1;  // table full: the caller falls back to an unbalanced but valid cut
