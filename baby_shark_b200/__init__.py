@@ -28,7 +28,7 @@ EXPORTS = [
     "bs_volume_from_voxels", "bs_volume_empty", "bs_volume_sphere", "bs_volume_cuboid", "bs_volume_iwp",
     "bs_volume_clone", "bs_volume_free", "bs_volume_voxel_size",
     "bs_volume_union", "bs_volume_subtract", "bs_volume_intersect", "bs_volume_offset",
-    "bs_mesh_mc", "bs_mesh_dc", "bs_mesh_mc_device", "bs_mesh_dc_device", "bs_buffer_free",
+    "bs_mesh_mc", "bs_mesh_dc", "bs_mesh_mc_device", "bs_mesh_dc_device", "bs_buffer_free", "bs_voxel_remesh_into",
     "bs_volume_download", "bs_volume_counts", "bs_context_last_stats", "bs_context_copy_out_verts", "bs_context_copy_out_verts_device", "bs_context_set_flag", "bs_kernel_launch_count",
     "bs_stl_decode", "bs_stl_decode_device", "bs_stl_encode", "bs_stl_encode_device", "bs_mesh_active_voxels", "bs_mesh_active_voxels_device",
     "bs_merge_points", "bs_merge_points_device", "bs_device_free", "bs_mesh_mc_indexed", "bs_mesh_mc_indexed_device", "bs_copy_to_host",
@@ -89,6 +89,7 @@ def load_library(path=None):
         "bs_mesh_mc_device": (C.c_int, [vp, C.c_float, pvp, psz]),
         "bs_mesh_dc_device": (C.c_int, [vp, C.c_float, pvp, psz]),
         "bs_buffer_free": (None, [vp]),
+        "bs_voxel_remesh_into": (C.c_int, [vp, vp, sz, C.c_float, C.c_int, C.c_int, vp, sz, psz]),
         "bs_volume_download": (C.c_int, [vp, C.POINTER(C.POINTER(C.c_int32)), C.POINTER(fp), C.POINTER(C.POINTER(C.c_uint64)), psz,
                                          C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.POINTER(C.c_int32)), C.POINTER(fp), psz]),
         "bs_volume_counts": (C.c_int, [vp, psz, psz, psz, psz]),
@@ -442,13 +443,40 @@ class VoxelRemesher:
         self.meshing_method = method
         return self
 
-    def remesh(self, mesh):
-        vol = self._m2v.convert(mesh)
-        if vol is None:
+    def remesh(self, mesh, slabs=0):
+        """Host triangles in, host vertex soup out, through the one-call pipelined entry point (bs_voxel_remesh_into)."""
+        if isinstance(mesh, DeviceTriangles):  # already on the device: convert + extract, no upload to hide
+            vol = self._m2v.convert(mesh)
+            if vol is None:
+                return None
+            if self.meshing_method == MeshingMethod.FeaturePreserving:
+                return DualContouringMesher().with_voxel_size(self.voxel_size).mesh(vol)
+            return MarchingCubesMesher().with_voxel_size(self.voxel_size).mesh(vol)
+        tris = np.ascontiguousarray(mesh, np.float32).reshape(-1, 9)
+        out = np.empty(max(1024, 4 * tris.size), np.float32)
+        n = self.remesh_into(tris, out, slabs)
+        if n is None:
             return None
-        if self.meshing_method == MeshingMethod.FeaturePreserving:
-            return DualContouringMesher().with_voxel_size(self.voxel_size).mesh(vol)
-        return MarchingCubesMesher().with_voxel_size(self.voxel_size).mesh(vol)
+        if n > out.size:  # the estimate was too small: the call reported the size, run again
+            out = np.empty(n, np.float32)
+            n = self.remesh_into(tris, out, slabs)
+        return out[:n].reshape(-1, 3).copy() if n < out.size // 2 else out[:n].reshape(-1, 3)
+
+    def remesh_into(self, tris, out, slabs=0):
+        """tris: contiguous f32 array of 9 floats per triangle (host); out: contiguous f32 host array (page-locked memory
+        lets the read-back overlap the kernels). Returns the number of floats of the result (larger than out.size: nothing
+        usable was written, retry with that size) or None where the reference returns None."""
+        ctx = self._m2v._ctx or Context.default()
+        n = C.c_size_t()
+        method = 1 if self.meshing_method == MeshingMethod.FeaturePreserving else 0
+        st = load_library().bs_voxel_remesh_into(ctx._h, C.c_void_p(tris.ctypes.data), tris.size // 9, self.voxel_size, method, int(slabs),
+                                                 C.c_void_p(out.ctypes.data), out.size, C.byref(n))
+        if st == 1:
+            return None
+        if st == 3 and n.value > out.size:
+            return n.value
+        ctx.check(st)
+        return n.value
 
 
 class DeviceTriangles:

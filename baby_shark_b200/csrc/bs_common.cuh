@@ -108,6 +108,17 @@ struct bs_context {
     unsigned* d_err = nullptr;
     float* d_out_verts = nullptr;   // last extraction result left on the device
     size_t out_verts_cap = 0;
+    // pipelined remesh (bs_voxel_remesh_into): second result buffer + copy stream so that slab k's read-back overlaps slab
+    // k + 1's kernels; the MC33 c-vertex travels from slab to slab through d_mc_carry while mc_chain is set
+    float* d_out_alt = nullptr; size_t out_alt_cap = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    float* d_mc_carry = nullptr; bool mc_chain = false;
+    // small read-backs (bs_fetch / bs_sync): page-locked scratch the device writes directly, so that the counters a call needs
+    // on the host never queue behind a bulk copy on a copy engine
+    unsigned* h_ctrl = nullptr; unsigned* d_ctrl = nullptr; size_t ctrl_used = 0;
+    struct Pending { void* dst; size_t off, bytes; };
+    std::vector<Pending> pending;
     // stage timing
     std::vector<std::pair<const char*, cudaEvent_t>> marks;
     // BS_FLAG_COUNT_WORK: instrumented winding-number traversal (node visits, far evals, exact triangles, voxels)
@@ -161,6 +172,12 @@ template <class T> bs_status bs_alloc(bs_context* ctx, T** p, size_t count) {
 }
 template <class T> void bs_free(bs_context* ctx, T* p) { if (p) bs_raw_free(ctx, (void*)p); }
 
+// Read a few words (<= 16 KB, 4-byte granular) of device memory into a host variable WITHOUT a copy engine: a tiny kernel stores them
+// into mapped page-locked scratch and bs_sync -- cudaStreamSynchronize on the context's stream -- delivers them to `host_dst`
+// (which must stay alive until then). With cudaMemcpyAsync these reads wait behind whatever bulk device-to-host copy another stream has
+// queued (measured: the slab read-back of bs_voxel_remesh_into delayed every control read of the next slab by milliseconds).
+bs_status bs_fetch(bs_context* ctx, void* host_dst, const void* d_src, size_t bytes);
+bs_status bs_sync(bs_context* ctx);
 void bs_mark(bs_context* ctx, const char* name);          // record an event named `name` on the stream
 void bs_marks_begin(bs_context* ctx);                     // clear marks + stats, record "begin"
 void bs_marks_end(bs_context* ctx);                       // sync, turn consecutive marks into "<name>_ms" stats
@@ -172,8 +189,11 @@ bs_status bs_volume_alloc_bricks(bs_volume* v, size_t n);  // keys / values / ma
 inline unsigned bs_blocks(size_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
 
 // stage entry points (one .cu each)
+// what the slabs of one mesh share (bs_voxel_remesh_into converts a mesh slab by slab): the closedness verdict and the
+// coarse cut of the key space are computed by the first slab and reused by the others
+struct bs_convert_plan { bool valid = false; bool closed = false; int world = 0; std::vector<unsigned long long> bounds; };
 bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, float voxel_size, int64_t band,
-                          int rank, int world, bs_volume** out);
+                          int rank, int world, bs_volume** out, bs_convert_plan* plan = nullptr);
 bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_volume* vol, const unsigned long long* d_touches /*per brick, may be null*/,
                        const unsigned long long* d_blk /*blocked lattice edges, 24 words per brick; null = per-voxel signs*/);
 bs_status bs_mc_impl(const bs_volume* v, float voxel_size, const float** d_verts, size_t* n_verts);

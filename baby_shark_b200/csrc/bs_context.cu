@@ -11,8 +11,36 @@
 bs_status bs_fail(bs_context* ctx, bs_status st, const char* fmt, ...) {
     char buf[1024];
     va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
-    if (ctx) { ctx->err = buf; ctx->failed_epoch = ctx->epoch; ctx->fail_pending = true; }
+    if (ctx) { ctx->err = buf; ctx->failed_epoch = ctx->epoch; ctx->fail_pending = true; ctx->pending.clear(); ctx->ctrl_used = 0; }  // (the failing call unwinds: its pending read-backs point into dead frames)
     return st;
+}
+
+namespace {
+constexpr size_t CTRL_WORDS = 1 << 14;
+__global__ void k_fetch(const unsigned* __restrict__ src, unsigned* dst, unsigned n) {
+    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+}  // namespace
+bs_status bs_fetch(bs_context* ctx, void* host_dst, const void* d_src, size_t bytes) {
+    if (bytes == 0) return BS_OK;
+    if ((bytes & 3) || ((uintptr_t)d_src & 3) || bytes > CTRL_WORDS * 2) return bs_fail(ctx, BS_ERR_INVALID, "bs_fetch: %zu bytes", bytes);
+    if (!ctx->h_ctrl) {
+        BS_CUDA(ctx, cudaHostAlloc((void**)&ctx->h_ctrl, CTRL_WORDS * sizeof(unsigned), cudaHostAllocMapped));
+        BS_CUDA(ctx, cudaHostGetDevicePointer((void**)&ctx->d_ctrl, ctx->h_ctrl, 0));
+    }
+    const size_t words = bytes / 4;
+    if (ctx->ctrl_used + words > CTRL_WORDS) BS_TRY(bs_sync(ctx));  // scratch full: deliver what is pending first
+    k_fetch<<<1, 64, 0, ctx->stream>>>((const unsigned*)d_src, ctx->d_ctrl + ctx->ctrl_used, (unsigned)words);
+    ctx->pending.push_back({host_dst, ctx->ctrl_used, bytes});
+    ctx->ctrl_used += words;
+    return BS_OK;
+}
+bs_status bs_sync(bs_context* ctx) {
+    const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return bs_fail(ctx, BS_ERR_CUDA, "stream synchronize: %s", cudaGetErrorString(e));
+    for (const auto& p : ctx->pending) memcpy(p.dst, ctx->h_ctrl + p.off, p.bytes);
+    ctx->pending.clear(); ctx->ctrl_used = 0;
+    return BS_OK;
 }
 
 void bs_marks_begin(bs_context* ctx) {
@@ -25,7 +53,7 @@ void bs_mark(bs_context* ctx, const char* name) {
     ctx->marks.push_back({name, e});
 }
 void bs_marks_end(bs_context* ctx) {
-    cudaStreamSynchronize(ctx->stream);
+    bs_sync(ctx);
     for (size_t i = 1; i < ctx->marks.size(); ++i) {
         float ms = 0.f; cudaEventElapsedTime(&ms, ctx->marks[i - 1].second, ctx->marks[i].second);
         ctx->stats.push_back({ctx->marks[i].first, (double)ms});
@@ -181,9 +209,13 @@ void bs_context_destroy(bs_context* ctx) {
     ctx->live_volumes.clear();
     for (auto& m : ctx->marks) cudaEventDestroy(m.second);
     if (ctx->d_out_verts) cudaFree(ctx->d_out_verts);
+    if (ctx->d_out_alt) cudaFree(ctx->d_out_alt);
+    if (ctx->d_mc_carry) cudaFree(ctx->d_mc_carry);
+    if (ctx->copy_stream) { cudaStreamDestroy(ctx->copy_stream); for (int i = 0; i < 2; ++i) { cudaEventDestroy(ctx->ev_done[i]); cudaEventDestroy(ctx->ev_copied[i]); } }
     bs_cache_release(ctx);
     for (auto& kv : ctx->cache_live) cudaFree(kv.first);  // volumes the caller never freed
     cudaFree(ctx->d_mc33); cudaFree(ctx->d_err);
+    if (ctx->h_ctrl) cudaFreeHost(ctx->h_ctrl);
     cudaStreamDestroy(ctx->stream);
     }
     delete ctx;
@@ -507,6 +539,87 @@ bs_status bs_mesh_dc(const bs_volume* v, float voxel_size, float** verts, size_t
     const float* d = nullptr; size_t n = 0;
     BS_TRY(bs_mesh_dc_device(v, voxel_size, &d, &n));
     return verts_to_host(v->ctx, d, n, verts, n_verts);
+}
+
+// ---- VoxelRemesher::remesh, host triangles in, host vertices out -----------------------------------------------
+// The mesh is uploaded once and converted + extracted slab by slab (the brick slabs of the multi-GPU path, run one after
+// the other on this GPU): the device-to-host copy of slab k's vertices runs on a second stream while slab k + 1 is being
+// converted, so the 1.1 GB read-back of a 10 M-triangle remesh hides behind the kernels instead of following them. Slabs are
+// contiguous ranges of the reference's leaf visit order, so the concatenation is the single-pass result bit for bit; the
+// one piece of state the reference carries from cell to cell (the MC33 c-vertex) is handed from slab
+// to slab on the device (d_mc_carry).
+static void remesh_accumulate(std::vector<bs_stat>& acc, const std::vector<bs_stat>& st) {
+    for (const bs_stat& a : st) {
+        const size_t len = strlen(a.name);
+        const bool additive = (len > 3 && !strcmp(a.name + len - 3, "_ms")) || !strcmp(a.name, "n_active") || !strcmp(a.name, "n_out_tris") || !strcmp(a.name, "n_eval") || !strcmp(a.name, "n_bricks_owned") || !strcmp(a.name, "n_sub") || !strcmp(a.name, "n_sign_seeds");
+        bool found = false;
+        for (bs_stat& b : acc) if (!strcmp(a.name, b.name)) { if (additive) b.value += a.value; else b.value = a.value; found = true; break; }
+        if (!found) acc.push_back(a);
+    }
+}
+bs_status bs_voxel_remesh_into(bs_context* ctx, const float* tris, size_t n_tris, float voxel_size, int method, int slabs,
+                               float* dst, size_t cap_floats, size_t* n_floats) {
+    if (!ctx || !n_floats || (!dst && cap_floats)) return BS_ERR_INVALID;
+    *n_floats = 0;
+    if (n_tris == 0) return BS_ERR_EMPTY_MESH;
+    if (!tris || (method != 0 && method != 1)) return BS_ERR_INVALID;
+    BS_ENTER(ctx);
+    if (!(voxel_size > 0.0f)) return bs_fail(ctx, BS_ERR_INVALID, "voxel_size must be > 0");
+    int K = slabs;
+    if (K <= 0) { if (const char* e = getenv("BSHARK_REMESH_SLABS")) K = atoi(e); }
+    if (K <= 0) K = n_tris >= (1u << 20) ? 4 : 1;  // below ~1 M triangles the per-slab overhead outweighs the hidden copy
+    if (K > 64) K = 64;
+    cudaStream_t st = ctx->stream;
+    if (!ctx->copy_stream) {
+        BS_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) { BS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming)); BS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming)); }
+        BS_CUDA(ctx, cudaMalloc((void**)&ctx->d_mc_carry, 4 * sizeof(float)));
+    }
+    float* d = nullptr;
+    BS_TRY(bs_alloc(ctx, &d, n_tris * 9));
+    BS_CUDA(ctx, cudaMemcpyAsync(d, tris, n_tris * 9 * sizeof(float), cudaMemcpyHostToDevice, st));
+    BS_CUDA(ctx, cudaMemsetAsync(ctx->d_mc_carry, 0, 4 * sizeof(float), st));
+    ctx->mc_chain = K > 1 && method == 0;
+    bs_convert_plan plan;
+    std::vector<bs_stat> acc;
+    size_t off = 0; int n_copies = 0; bs_status s = BS_OK;
+    const size_t CHUNK = (size_t)8 << 20;  // floats per copy: small control read-backs of the running slab slip in between
+    for (int k = 0; k < K && s == BS_OK; ++k) {
+        bs_volume* v = nullptr;
+        s = bs_convert_impl(ctx, d, n_tris, voxel_size, 0, k, K, &v, &plan);
+        if (s != BS_OK) break;
+        remesh_accumulate(acc, ctx->stats);
+        // the buffer this extraction writes was the source of copy k - 2
+        if (n_copies >= 2) cudaStreamWaitEvent(st, ctx->ev_copied[k & 1], 0);
+        const float* dv = nullptr; size_t nv = 0;
+        s = method == 0 ? bs_mc_impl(v, voxel_size, &dv, &nv) : bs_dc_impl(v, voxel_size, &dv, &nv);
+        bs_volume_free(v);
+        if (s != BS_OK) break;
+        remesh_accumulate(acc, ctx->stats);
+        const size_t nf = nv * 3;
+        if (nf && off + nf <= cap_floats) {
+            cudaEventRecord(ctx->ev_done[k & 1], st);
+            cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[k & 1], 0);
+            for (size_t c = 0; c < nf; c += CHUNK) {
+                const cudaError_t e = cudaMemcpyAsync(dst + off + c, dv + c, std::min(CHUNK, nf - c) * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_stream);
+                if (e != cudaSuccess) { s = bs_fail(ctx, BS_ERR_CUDA, "D2H vertices: %s", cudaGetErrorString(e)); break; }
+            }
+        }
+        cudaEventRecord(ctx->ev_copied[k & 1], ctx->copy_stream);
+        ++n_copies;
+        off += nf;
+        std::swap(ctx->d_out_verts, ctx->d_out_alt); std::swap(ctx->out_verts_cap, ctx->out_alt_cap);  // the next slab extracts into the other buffer
+    }
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamSynchronize(st);
+    ctx->mc_chain = false;
+    bs_free(ctx, d);
+    if (s != BS_OK) return s;
+    ctx->stats = acc;
+    bs_stat_add(ctx, "remesh_slabs", (double)K);
+    *n_floats = off;
+    if (off > cap_floats) return bs_fail(ctx, BS_ERR_INVALID, "result buffer too small: %zu floats needed, %zu given (n_floats holds the size to retry with)", off, cap_floats);
+    return BS_OK;
 }
 
 // ---- CSG / offset -------------------------------------------------------------------------------------------

@@ -14,6 +14,7 @@
 //   eval : point-triangle distances for every lattice point of every box, atomicMin into the brick
 // with a radix sort of the brick keys in between (sorted key order == the reference's leaf visit order).
 #include "bs_common.cuh"
+#include "bs_ptdist.cuh"
 #include <cub/cub.cuh>
 #include <cfloat>
 #include <climits>
@@ -29,6 +30,8 @@ struct ConvertParams {
     const float* tris; size_t n_tris;   // n_tris = triangles this call works on (entries of tri_ids when that is set)
     const unsigned* tri_ids;            // sharded runs: the triangles that can touch this rank's bricks (null: all, in order)
     const unsigned long long* offsets;  // exclusive prefix sum of per-triangle sub-triangle counts, n_tris + 1
+    const unsigned* cta_start;          // triangle holding sub-triangle b * TPB, per CTA b (k_cta_starts): saves every CTA of k_mark / k_eval a 23-step dependent search
+    unsigned* dummy_brick;              // 512 scratch words: where lattice points of bricks this rank does not keep are sent (sharded runs)
     unsigned long long total;
     float vs, inv_vs; int band;
     unsigned long long* table_keys; unsigned* table_slots; unsigned table_mask;
@@ -131,7 +134,7 @@ __device__ TriCursor locate(const ConvertParams& P, unsigned long long* s_off /*
     const unsigned long long g0 = (unsigned long long)blockIdx.x * TPB;
     // uniform search for the triangle containing g0 (every thread walks the same path: broadcast loads), then
     // a window of TPB+1 offsets in shared memory serves the per-thread searches
-    const size_t base = find_tri(P, g0);
+    const size_t base = P.cta_start ? (size_t)P.cta_start[blockIdx.x] : find_tri(P, g0);
     for (int i = threadIdx.x; i <= TPB; i += TPB) { size_t idx = base + i; s_off[i] = idx <= P.n_tris ? P.offsets[idx] : ~0ull; }
     __syncthreads();
     TriCursor c; c.valid = false; c.tri = 0; c.local = 0;
@@ -143,6 +146,11 @@ __device__ TriCursor locate(const ConvertParams& P, unsigned long long* s_off /*
         c.tri = t; c.local = g - P.offsets[t]; c.valid = true;
     }
     return c;
+}
+
+__global__ void k_cta_starts(ConvertParams P, unsigned n_ctas, unsigned* start) {
+    const unsigned b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < n_ctas) start[b] = (unsigned)find_tri(P, (unsigned long long)b * TPB);
 }
 
 __device__ __forceinline__ void hash_insert(const ConvertParams& P, unsigned long long key) {
@@ -191,123 +199,83 @@ __global__ void __launch_bounds__(TPB) k_mark(ConvertParams P) {
             for (int bz = mn[2] >> 3; bz <= (mx[2] >> 3); ++bz) hash_insert(P, bs_brick_key(bx, by, bz));
 }
 
-// Triangle3::closest_point (triangle3.rs:317-382) then |closest - p| (mesh_to_volume.rs:155)
-__device__ __forceinline__ float point_triangle_distance(f3 a, f3 b, f3 c, f3 ab, f3 ac, f3 p) {
-    f3 cp;
-    f3 ap = xsub(p, a);
-    float d1 = xdot(ab, ap), d2 = xdot(ac, ap);
-    if (d1 <= 0.f && d2 <= 0.f) cp = a;
-    else {
-        f3 bp = xsub(p, b);
-        float d3 = xdot(ab, bp), d4 = xdot(ac, bp);
-        if (d3 >= 0.f && d4 <= d3) cp = b;
-        else {
-            float vc = xsub(xmul(d1, d4), xmul(d3, d2));
-            if (vc <= 0.f && d1 >= 0.f && d3 <= 0.f) cp = xadd(a, xscale(ab, xdiv(d1, xsub(d1, d3))));
-            else {
-                f3 cq = xsub(p, c);
-                float d5 = xdot(ab, cq), d6 = xdot(ac, cq);
-                if (d6 >= 0.f && d5 <= d6) cp = c;
-                else {
-                    float vb = xsub(xmul(d5, d2), xmul(d1, d6));
-                    if (vb <= 0.f && d2 >= 0.f && d6 <= 0.f) cp = xadd(a, xscale(ac, xdiv(d2, xsub(d2, d6))));
-                    else {
-                        float va = xsub(xmul(d3, d6), xmul(d5, d4));
-                        float e43 = xsub(d4, d3), e56 = xsub(d5, d6);
-                        if (va <= 0.f && e43 >= 0.f && e56 >= 0.f) cp = xadd(b, xscale(xsub(c, b), xdiv(e43, xadd(e43, e56))));
-                        else {
-                            float denom = xdiv(1.0f, xadd(xadd(va, vb), vc));
-                            float v = xmul(vb, denom), w = xmul(vc, denom);
-                            cp = xadd(xadd(a, xscale(ab, v)), xscale(ac, w));
-                        }
-                    }
-                }
-            }
-        }
-    }
-    return xsqrt(xnorm2(xsub(cp, p)));
-}
-
-// Distances. Each lane derives one sub-triangle (vertices, box, the <= 2x2x2 brick slots its box touches) and parks
-// it in shared memory; then the warp flattens the (sub-triangle, z-column) pairs of its 32 sub-triangles and deals
-// them out round robin, so lanes stay busy although box sizes differ (a plain thread-per-sub-triangle loop ran at
-// 10 of 32 lanes: r1 ncu). Boxes wider than 9 voxels (large narrow bands) take the per-thread path.
-constexpr int EV_REC = 27;  // words per parked sub-triangle (odd: conflict-free when lanes read different records)
-#ifndef BS_EVAL_MINB
-#define BS_EVAL_MINB 4
-#endif
-__global__ void __launch_bounds__(TPB, BS_EVAL_MINB) k_eval(ConvertParams P) {
+// Distances. Each lane derives one sub-triangle (vertices, box, the <= 2x2x2 brick slots its box touches) and parks it in
+// shared memory; then the warp flattens the (sub-triangle, z-column) pairs of its 32 sub-triangles and deals them out
+// round robin, so lanes stay busy although box sizes differ (a plain thread-per-sub-triangle loop ran at 10 of 32 lanes:
+// r1 ncu). The point-triangle distance is bs_ptdist.cuh: the x / y halves of the six dot products are computed once per
+// column, the seven regions are predicates around one shared division instead of a chain of divergent branches (the
+// branchy form ran at 20 of 32 lanes), records are read with 128-bit shared loads, the column's (x, y) comes from a
+// multiply-shift instead of a division, its two possible brick slots (a box spans at most two bricks along z) are fetched
+// once, and the scatter-min works on SQUARED distances: sqrt is monotone, so k_masks (bs_fwn.cu), which reads every value
+// anyway, takes the root of the minimum. Boxes wider than 9 voxels (large narrow bands) take the per-thread path.
+// Measured and rejected (config 5, 6.6 ms): reading the current value first and skipping the RED when it is not lower
+// (7.3 ms through L2 or L1: the kernel is issue-bound, 603 M REDs cost nothing extra -- without any RED: 6.5 ms);
+// 3 CTAs / SM at 78 registers (7.4 ms).
+constexpr int EV2_REC = 28;  // words per parked sub-triangle: 7 x 128 bit; 28 mod 32 keeps 8 different records conflict-free
+__global__ void __launch_bounds__(TPB, 4) k_eval(ConvertParams P) {
     __shared__ unsigned long long s_off[TPB + 1];
-    __shared__ unsigned s_rec[TPB / 32][32 * EV_REC];
+    __shared__ __align__(16) unsigned s_rec[TPB / 32][32 * EV2_REC];
     __shared__ unsigned s_pre[TPB / 32][33];
     TriCursor cur = locate(P, s_off);
     const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    unsigned* rec = s_rec[w] + lane * EV_REC;
+    unsigned* rec = s_rec[w] + lane * EV2_REC;
     f3 A{0.f, 0.f, 0.f}, B = A, C = A;
     int mn[3] = {0, 0, 0}, mx[3] = {-1, -1, -1};
     bool ok = false;
     if (cur.valid) {
         const float* p = tri_ptr(P, cur.tri);
-        const f3 p1 = ld3(p), p2 = ld3(p + 3), p3 = ld3(p + 6);
-        bool hit = true;
-        if (P.use_clip) {  // the whole input triangle (plus band and rounding slack) misses this rank's bricks: skip the subdivision
-            const float lo[3] = {fminf(p1.x, fminf(p2.x, p3.x)), fminf(p1.y, fminf(p2.y, p3.y)), fminf(p1.z, fminf(p2.z, p3.z))};
-            const float hi[3] = {fmaxf(p1.x, fmaxf(p2.x, p3.x)), fmaxf(p1.y, fmaxf(p2.y, p3.y)), fmaxf(p1.z, fmaxf(p2.z, p3.z))};
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                const float a = floorf(lo[d] * P.inv_vs) - (float)(P.band + 3), b = ceilf(hi[d] * P.inv_vs) + (float)(P.band + 3);
-                if (b < (float)P.clip_mn[d] || a > (float)P.clip_mx[d]) hit = false;
-            }
-        }
-        if (hit) {
-            make_subtri(p1, p2, p3, P.vs, cur.local, A, B, C);
-            ok = subtri_box(A, B, C, P.inv_vs, P.band, mn, mx);
-        }
+        make_subtri(ld3(p), ld3(p + 3), ld3(p + 6), P.vs, cur.local, A, B, C);
+        ok = subtri_box(A, B, C, P.inv_vs, P.band, mn, mx);
     }
     const int dx = ok ? mx[0] - mn[0] + 1 : 0, dy = ok ? mx[1] - mn[1] + 1 : 0, dz = ok ? mx[2] - mn[2] + 1 : 0;
     const bool wide = dx > 9 || dy > 9 || dz > 9;
     unsigned* vals = reinterpret_cast<unsigned*>(P.values);
-    if (__any_sync(0xFFFFFFFFu, wide)) {  // rare: per-thread loops over the whole box
+    if (__any_sync(0xFFFFFFFFu, wide)) {  // rare (large narrow bands): per-thread loops over the whole box
         if (!ok) return;
-        const f3 ab = xsub(B, A), ac = xsub(C, A);
+        PtdTri T{A.x, A.y, A.z, B.x, B.y, B.z, C.x, C.y, C.z, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        ptd_tri_setup(T);
         for (int bx = mn[0] >> 3; bx <= (mx[0] >> 3); ++bx)
             for (int by = mn[1] >> 3; by <= (mx[1] >> 3); ++by)
                 for (int bz = mn[2] >> 3; bz <= (mx[2] >> 3); ++bz) {
-                    unsigned slot = hash_lookup(P, bs_brick_key(bx, by, bz));
+                    const unsigned slot = hash_lookup(P, bs_brick_key(bx, by, bz));
                     if (slot == 0xFFFFFFFFu) continue;  // brick not kept on this rank
                     unsigned* brick = vals + (size_t)slot * 512;
                     const int x0 = max(mn[0], bx << 3), x1 = min(mx[0], (bx << 3) + 7);
                     const int y0 = max(mn[1], by << 3), y1 = min(mx[1], (by << 3) + 7);
                     const int z0 = max(mn[2], bz << 3), z1 = min(mx[2], (bz << 3) + 7);
-                    for (int x = x0; x <= x1; ++x) {
-                        const float xw = xmul((float)x, P.vs);
+                    for (int x = x0; x <= x1; ++x)
                         for (int y = y0; y <= y1; ++y) {
-                            const float yw = xmul((float)y, P.vs);
+                            PtdCol K;
+                            ptd_col_setup(T, xmul((float)x, P.vs), xmul((float)y, P.vs), K);
                             unsigned* line = brick + ((x & 7) << 6) + ((y & 7) << 3);
-                            for (int z = z0; z <= z1; ++z) {
-                                const float zw = xmul((float)z, P.vs);
-                                float d = point_triangle_distance(A, B, C, ab, ac, f3{xw, yw, zw});
-                                atomicMin(line + (z & 7), __float_as_uint(d));  // d >= 0 or NaN (NaN bits sort above the sentinel)
-                            }
+                            for (int z = z0; z <= z1; ++z)
+                                atomicMin(line + (z & 7), __float_as_uint(ptd_eval2(T, K, xmul((float)z, P.vs))));  // squared distance: >= 0 or NaN (NaN bits sort above the sentinel)
                         }
-                    }
                 }
         return;
     }
-    // park: vertices, box origin, dims, brick slots
-    rec[0] = __float_as_uint(A.x); rec[1] = __float_as_uint(A.y); rec[2] = __float_as_uint(A.z);
-    rec[3] = __float_as_uint(B.x); rec[4] = __float_as_uint(B.y); rec[5] = __float_as_uint(B.z);
-    rec[6] = __float_as_uint(C.x); rec[7] = __float_as_uint(C.y); rec[8] = __float_as_uint(C.z);
-    rec[9] = (unsigned)mn[0]; rec[10] = (unsigned)mn[1]; rec[11] = (unsigned)mn[2];
-    rec[12] = (unsigned)dy | ((unsigned)dz << 8);
-    if (ok) {
-        const int bx0 = mn[0] >> 3, by0 = mn[1] >> 3, bz0 = mn[2] >> 3;
+    // park: vertices, box origin, dims + the multiply-shift constant for "/ dy", brick slots
+    {
+        uint4* r4 = reinterpret_cast<uint4*>(rec);
+        r4[0] = make_uint4(__float_as_uint(A.x), __float_as_uint(A.y), __float_as_uint(A.z), __float_as_uint(B.x));
+        r4[1] = make_uint4(__float_as_uint(B.y), __float_as_uint(B.z), __float_as_uint(C.x), __float_as_uint(C.y));
+        r4[2] = make_uint4(__float_as_uint(C.z), (unsigned)mn[0], (unsigned)mn[1], (unsigned)mn[2]);
+        const unsigned magic = dy > 0 ? 65536u / (unsigned)dy + 1u : 0u;  // (q * magic) >> 16 == q / dy for q < 81, dy <= 9
+        r4[3] = make_uint4((unsigned)dy | ((unsigned)dz << 8), magic, 0u, 0u);
+        unsigned sl[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int bx = bx0 + (k & 1), by = by0 + ((k >> 1) & 1), bz = bz0 + (k >> 2);
-            const bool touched = bx <= (mx[0] >> 3) && by <= (mx[1] >> 3) && bz <= (mx[2] >> 3);
-            rec[13 + k] = touched ? hash_lookup(P, bs_brick_key(bx, by, bz)) : 0xFFFFFFFFu;
+        for (int k = 0; k < 8; ++k) sl[k] = 0xFFFFFFFFu;
+        if (ok) {
+            const int bx0 = mn[0] >> 3, by0 = mn[1] >> 3, bz0 = mn[2] >> 3;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int bx = bx0 + (k & 1), by = by0 + ((k >> 1) & 1), bz = bz0 + (k >> 2);
+                const bool touched = bx <= (mx[0] >> 3) && by <= (mx[1] >> 3) && bz <= (mx[2] >> 3);
+                if (touched) sl[k] = hash_lookup(P, bs_brick_key(bx, by, bz));
+            }
         }
+        r4[4] = make_uint4(sl[0], sl[1], sl[2], sl[3]);
+        r4[5] = make_uint4(sl[4], sl[5], sl[6], sl[7]);
     }
     // exclusive prefix of column counts
     const unsigned ncol = (unsigned)(dx * dy);
@@ -319,30 +287,33 @@ __global__ void __launch_bounds__(TPB, BS_EVAL_MINB) k_eval(ConvertParams P) {
     __syncwarp();
     const unsigned total = s_pre[w][32];
     for (unsigned c = lane; c < total; c += 32) {
-        // owner: last s with pre[s] <= c
-        unsigned lo = 0, hi = 32;
-        while (hi - lo > 1) { const unsigned mid = (lo + hi) >> 1; if (s_pre[w][mid] <= c) lo = mid; else hi = mid; }
-        const unsigned* r = s_rec[w] + lo * EV_REC;
+        unsigned lo = 0, hi = 32;  // owner: last s with pre[s] <= c
+#pragma unroll
+        for (int it = 0; it < 5; ++it) { const unsigned mid = (lo + hi) >> 1; if (s_pre[w][mid] <= c) lo = mid; else hi = mid; }
+        const unsigned* r = s_rec[w] + lo * EV2_REC;
+        const uint4* r4 = reinterpret_cast<const uint4*>(r);
+        const uint4 q0 = r4[0], q1 = r4[1], q2 = r4[2], q3 = r4[3];
+        PtdTri T{__uint_as_float(q0.x), __uint_as_float(q0.y), __uint_as_float(q0.z), __uint_as_float(q0.w), __uint_as_float(q1.x), __uint_as_float(q1.y),
+                 __uint_as_float(q1.z), __uint_as_float(q1.w), __uint_as_float(q2.x), 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        ptd_tri_setup(T);
         const unsigned q = c - s_pre[w][lo];
-        const unsigned ddy = r[12] & 255u, ddz = r[12] >> 8;
-        const unsigned xi = q / ddy;
+        const unsigned ddy = q3.x & 255u, ddz = q3.x >> 8;
+        const unsigned xi = (q * q3.y) >> 16;
         const unsigned yi = q - xi * ddy;
-        const f3 a{__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2])};
-        const f3 bb{__uint_as_float(r[3]), __uint_as_float(r[4]), __uint_as_float(r[5])};
-        const f3 cc{__uint_as_float(r[6]), __uint_as_float(r[7]), __uint_as_float(r[8])};
-        const f3 ab = xsub(bb, a), ac = xsub(cc, a);
-        const int x = (int)r[9] + (int)xi, y = (int)r[10] + (int)yi, z0 = (int)r[11];
-        const int kx = (x >> 3) - ((int)r[9] >> 3), ky = (y >> 3) - ((int)r[10] >> 3);
-        const float xw = xmul((float)x, P.vs), yw = xmul((float)y, P.vs);
+        const int x = (int)q2.y + (int)xi, y = (int)q2.z + (int)yi, z0 = (int)q2.w;
+        const int kx = (x >> 3) - ((int)q2.y >> 3), ky = (y >> 3) - ((int)q2.z >> 3);
+        const unsigned slot_lo = r[16 + kx + 2 * ky], slot_hi = r[20 + kx + 2 * ky];
+        PtdCol K;
+        ptd_col_setup(T, xmul((float)x, P.vs), xmul((float)y, P.vs), K);
         const unsigned line_off = ((x & 7) << 6) + ((y & 7) << 3);
+        // a brick this rank does not keep (sharded runs) is replaced by a scratch brick: no test inside the loop
+        unsigned* const line_lo = (slot_lo != 0xFFFFFFFFu ? vals + (size_t)slot_lo * 512 : P.dummy_brick) + line_off;
+        unsigned* const line_hi = (slot_hi != 0xFFFFFFFFu ? vals + (size_t)slot_hi * 512 : P.dummy_brick) + line_off;
+        const int zsplit = ((z0 >> 3) + 1) << 3;  // first z of the upper brick
         for (unsigned zi = 0; zi < ddz; ++zi) {
             const int z = z0 + (int)zi;
-            const int kz = (z >> 3) - (z0 >> 3);
-            const unsigned slot = r[13 + kx + 2 * ky + 4 * kz];
-            if (slot == 0xFFFFFFFFu) continue;  // brick not kept on this rank
-            const float zw = xmul((float)z, P.vs);
-            const float d = point_triangle_distance(a, bb, cc, ab, ac, f3{xw, yw, zw});
-            atomicMin(vals + (size_t)slot * 512 + line_off + (z & 7), __float_as_uint(d));
+            const float d2 = ptd_eval2(T, K, xmul((float)z, P.vs));
+            atomicMin((z >= zsplit ? line_hi : line_lo) + (z & 7), __float_as_uint(d2));  // d2 >= 0 or NaN (NaN bits sort above the sentinel)
         }
     }
 }
@@ -472,6 +443,8 @@ template <int A> __device__ __forceinline__ void raster_big(const ConvertParams&
         raster_column<A>(P, blk, R, iu, iv, lat(iu, P.vs), last_key, last_slot);
     }
 }
+// (Measured and rejected, r2: parking the set-up projections in shared memory and dealing their lattice columns out to the
+// lanes of the warp, as k_eval does -- 2.33 ms against 2.05 ms for this per-thread walk.)
 __global__ void __launch_bounds__(128, 3) k_block_edges(ConvertParams P, unsigned long long* blk, unsigned long long* big_list, unsigned* n_big, unsigned big_cap) {
     // one thread per (axis, triangle); the axis is the SLOW index, so a warp runs one instantiation of the rasteriser
     const size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -679,8 +652,8 @@ extern "C" bs_status bs_volume_counts(const bs_volume* v, size_t* n_bricks, size
     BS_TRY(bs_alloc(ctx, &d, 2));
     BS_CUDA(ctx, cudaMemsetAsync(d, 0, 16, ctx->stream));
     if (v->n_bricks) bs_count_launch(), k_counts<<<bs_blocks(v->n_bricks * 8, TPB), TPB, 0, ctx->stream>>>(v->values, v->masks, v->n_bricks, d);
-    BS_CUDA(ctx, cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, ctx->stream));
-    BS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    BS_TRY(bs_fetch(ctx, h, d, 16));
+    BS_TRY(bs_sync(ctx));
     bs_free(ctx, d);
     if (n_bricks) *n_bricks = v->n_bricks;
     if (n_active) *n_active = h[0];
@@ -689,7 +662,8 @@ extern "C" bs_status bs_volume_counts(const bs_volume* v, size_t* n_bricks, size
     return BS_OK;
 }
 
-bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, float voxel_size, int64_t band, int rank, int world, bs_volume** out) {
+bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, float voxel_size, int64_t band, int rank, int world, bs_volume** out, bs_convert_plan* plan) {
+    const bool planned = plan && plan->valid && plan->world == world && (int)plan->bounds.size() == world + 1;  // a later slab of the same mesh
     cudaStream_t st = ctx->stream;
     bs_marks_begin(ctx);
     BS_CUDA(ctx, cudaMemsetAsync(ctx->d_err, 0, sizeof(unsigned), st));
@@ -700,10 +674,11 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
     // closed mesh? (bs_signprop.cu) -- enqueued here, read at the next synchronisation
     bs_closed_check chk; chk.pending = false; chk.closed = false; chk.exact = false; chk.d_sums = nullptr; chk.d_bad = nullptr;
     ctx->mesh_closed = false;
-    if (ctx->sign_propagation) BS_TRY(bs_mesh_closed_begin(ctx, d_tris, n_tris, &chk));
+    if (ctx->sign_propagation && !planned) BS_TRY(bs_mesh_closed_begin(ctx, d_tris, n_tris, &chk));
     // 0. sharded: cut the coarse key space at equal sub-triangle weight, keep the triangles that can reach this rank's range
     unsigned* d_tri_ids = nullptr; unsigned long long klo = 0, khi = BS_KEY_INVALID;
-    if (world > 1) {
+    if (world > 1 && planned) { klo = plan->bounds[rank]; khi = plan->bounds[rank + 1]; }
+    else if (world > 1) {
         const unsigned tcap = 1u << 17;  // coarse cells that can be occupied: the table is sorted whole, keep it small
         unsigned long long *d_tk = nullptr, *d_tw = nullptr, *d_sk = nullptr, *d_sw = nullptr, *d_C = nullptr, *d_bounds = nullptr; size_t* d_nsel = nullptr; void* d_tmp0 = nullptr; size_t tmp0 = 0, tmp1 = 0, tmp2 = 0;
         BS_TRY(bs_alloc(ctx, &d_tk, (size_t)tcap)); BS_TRY(bs_alloc(ctx, &d_tw, (size_t)tcap)); BS_TRY(bs_alloc(ctx, &d_sk, (size_t)tcap)); BS_TRY(bs_alloc(ctx, &d_sw, (size_t)tcap));
@@ -718,18 +693,23 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
         BS_TRY(bs_alloc(ctx, (char**)&d_tmp0, std::max(tmp0, std::max(tmp1, tmp2))));
         cub::DeviceSelect::If(d_tmp0, tmp2, d_tk, d_sk, d_nsel, (int)tcap, NotEmptyKey(), st);  // (only for the count of occupied cells)
         size_t n_cells = 0; int hflag[2] = {0, 0};
-        BS_CUDA(ctx, cudaMemcpyAsync(&n_cells, d_nsel, sizeof(size_t), cudaMemcpyDeviceToHost, st));
+        BS_TRY(bs_fetch(ctx, &n_cells, d_nsel, sizeof(size_t)));
         cub::DeviceRadixSort::SortPairs(d_tmp0, tmp0, d_tk, d_sk, d_tw, d_sw, (int)tcap, 0, 64, st);
         cub::DeviceScan::InclusiveSum(d_tmp0, tmp1, d_sw, d_C, (int)tcap, st);
-        BS_CUDA(ctx, cudaMemcpyAsync(hflag, d_flags, sizeof(hflag), cudaMemcpyDeviceToHost, st));
-        BS_CUDA(ctx, cudaStreamSynchronize(st));
+        BS_TRY(bs_fetch(ctx, hflag, d_flags, sizeof(hflag)));
+        BS_TRY(bs_sync(ctx));
         bs_count_launch(), k_coarse_cut<<<1, 64, 0, st>>>(d_sk, d_C, hflag[0] ? 0 : n_cells, world, d_bounds);
-        unsigned long long hb[2];
-        BS_CUDA(ctx, cudaMemcpyAsync(hb, d_bounds + rank, sizeof(hb), cudaMemcpyDeviceToHost, st));
-        BS_CUDA(ctx, cudaStreamSynchronize(st));
+        std::vector<unsigned long long> hb((size_t)world + 1);
+        BS_TRY(bs_fetch(ctx, hb.data(), d_bounds, hb.size() * sizeof(unsigned long long)));
+        BS_TRY(bs_sync(ctx));
         if (hflag[0]) { BS_CUDA(ctx, cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), st)); }  // (table full: rank 0 takes everything; still exact)
-        klo = hb[0]; khi = hb[1];
-        bs_free(ctx, d_tmp0); bs_free(ctx, d_tk); bs_free(ctx, d_tw); bs_free(ctx, d_sk); bs_free(ctx, d_sw); bs_free(ctx, d_C); bs_free(ctx, d_bounds);
+        klo = hb[rank]; khi = hb[rank + 1];
+        if (plan) { plan->bounds = hb; plan->world = world; }
+        bs_free(ctx, d_tmp0); bs_free(ctx, d_tk); bs_free(ctx, d_tw); bs_free(ctx, d_sk); bs_free(ctx, d_sw); bs_free(ctx, d_C); bs_free(ctx, d_bounds); bs_free(ctx, d_nsel);
+    }
+    if (world > 1) {
+        size_t* d_nsel = nullptr; void* d_tmp0 = nullptr; size_t tmp0 = 0;
+        BS_TRY(bs_alloc(ctx, &d_nsel, 1));
         // triangles whose inflated box reaches [klo, khi): one brick of halo + sub-triangle box slack (2) + band + 1
         unsigned char* d_keep = nullptr;
         BS_TRY(bs_alloc(ctx, &d_keep, n_tris)); BS_TRY(bs_alloc(ctx, &d_tri_ids, n_tris));
@@ -739,8 +719,8 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
         BS_TRY(bs_alloc(ctx, (char**)&d_tmp0, tmp0));
         cub::DeviceSelect::Flagged(d_tmp0, tmp0, cub::CountingInputIterator<unsigned>(0), d_keep, d_tri_ids, d_nsel, (int)n_tris, st);
         size_t n_list = 0;
-        BS_CUDA(ctx, cudaMemcpyAsync(&n_list, d_nsel, sizeof(size_t), cudaMemcpyDeviceToHost, st));
-        BS_CUDA(ctx, cudaStreamSynchronize(st));
+        BS_TRY(bs_fetch(ctx, &n_list, d_nsel, sizeof(size_t)));
+        BS_TRY(bs_sync(ctx));
         bs_free(ctx, d_tmp0); bs_free(ctx, d_keep); bs_free(ctx, d_nsel);
         n_tris = n_list;  // from here on: this rank's triangle list
         bs_mark(ctx, "shard_select_ms");
@@ -759,10 +739,11 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
     BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp_bytes));
     cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_counts, d_offsets, n_tris + 1, st);
     unsigned long long total = 0; double area_vox = 0.0;
-    BS_CUDA(ctx, cudaMemcpyAsync(&total, d_offsets + n_tris, sizeof(total), cudaMemcpyDeviceToHost, st));
-    BS_CUDA(ctx, cudaMemcpyAsync(&area_vox, d_area, sizeof(double), cudaMemcpyDeviceToHost, st));
-    BS_CUDA(ctx, cudaStreamSynchronize(st));
-    ctx->mesh_closed = ctx->sign_propagation && bs_mesh_closed_finish(ctx, &chk);
+    BS_TRY(bs_fetch(ctx, &total, d_offsets + n_tris, sizeof(total)));
+    BS_TRY(bs_fetch(ctx, &area_vox, d_area, sizeof(double)));
+    BS_TRY(bs_sync(ctx));
+    ctx->mesh_closed = planned ? (ctx->sign_propagation && plan->closed) : (ctx->sign_propagation && bs_mesh_closed_finish(ctx, &chk));
+    if (plan && !planned) { plan->closed = ctx->mesh_closed; plan->world = world; plan->valid = world == 1 || (int)plan->bounds.size() == world + 1; }
     bs_free(ctx, d_tmp); bs_free(ctx, d_counts); bs_free(ctx, d_area);
     bs_mark(ctx, "subdivide_count_ms");
     if (total == 0 && world > 1) {  // nothing of the mesh reaches this rank's range: an empty slab
@@ -783,6 +764,12 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
     ConvertParams P;
     P.tris = d_tris; P.n_tris = n_tris; P.tri_ids = d_tri_ids; P.offsets = d_offsets; P.total = total;
     P.vs = voxel_size; P.inv_vs = 1.0f / voxel_size; P.band = (int)band; P.flags = d_flags; P.values = nullptr; P.n_eval = d_neval; P.table_counts = nullptr; P.use_clip = 0; P.derr = ctx->d_err;
+    P.cta_start = nullptr; P.dummy_brick = nullptr;
+    const unsigned grid = (unsigned)((total + TPB - 1) / TPB);
+    unsigned* d_cta_start = nullptr; unsigned* d_dummy = nullptr;
+    BS_TRY(bs_alloc(ctx, &d_cta_start, (size_t)grid)); BS_TRY(bs_alloc(ctx, &d_dummy, (size_t)512));
+    bs_count_launch(), k_cta_starts<<<bs_blocks(grid, TPB), TPB, 0, st>>>(P, grid, d_cta_start);
+    P.cta_start = d_cta_start; P.dummy_brick = d_dummy;
 
     // 2. mark touched bricks in a hash set; sized from the surface area, doubled on overflow
     const double bw = (double)(2 * band + 1);
@@ -791,7 +778,6 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
     size_t cap = 1; while ((double)cap < 2.0 * est) cap <<= 1;
     unsigned long long* d_table_keys = nullptr; unsigned* d_table_slots = nullptr; unsigned* d_table_counts = nullptr;
     unsigned long long* d_keys = nullptr; size_t n_all = 0; unsigned long long n_eval = 0;
-    const unsigned grid = (unsigned)((total + TPB - 1) / TPB);
     for (;;) {
         BS_TRY(bs_alloc(ctx, &d_table_keys, cap));
         BS_CUDA(ctx, cudaMemsetAsync(d_table_keys, 0xFF, cap * sizeof(unsigned long long), st));
@@ -801,9 +787,9 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
         P.table_keys = d_table_keys; P.table_slots = nullptr; P.table_mask = (unsigned)(cap - 1);
         bs_count_launch(), k_mark<<<grid, TPB, 0, st>>>(P);
         int flags[2];
-        BS_CUDA(ctx, cudaMemcpyAsync(flags, d_flags, sizeof(flags), cudaMemcpyDeviceToHost, st));
-        BS_CUDA(ctx, cudaMemcpyAsync(&n_eval, d_neval, sizeof(n_eval), cudaMemcpyDeviceToHost, st));
-        BS_CUDA(ctx, cudaStreamSynchronize(st));
+        BS_TRY(bs_fetch(ctx, flags, d_flags, sizeof(flags)));
+        BS_TRY(bs_fetch(ctx, &n_eval, d_neval, sizeof(n_eval)));
+        BS_TRY(bs_sync(ctx));
         if (flags[1]) { bs_free(ctx, d_table_keys); bs_free(ctx, d_offsets); bs_free(ctx, d_flags); return bs_fail(ctx, BS_ERR_RANGE, "voxel index outside [-2^20, 2^20)"); }
         if (!flags[0]) break;
         bs_free(ctx, d_table_keys); bs_free(ctx, d_table_counts); d_table_counts = nullptr;
@@ -820,8 +806,8 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
         cub::DeviceSelect::If(nullptr, tmp_bytes, d_table_keys, d_sel, d_nsel, cap, NotEmptyKey(), st);
         BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp_bytes));
         cub::DeviceSelect::If(d_tmp, tmp_bytes, d_table_keys, d_sel, d_nsel, cap, NotEmptyKey(), st);
-        BS_CUDA(ctx, cudaMemcpyAsync(&n_all, d_nsel, sizeof(size_t), cudaMemcpyDeviceToHost, st));
-        BS_CUDA(ctx, cudaStreamSynchronize(st));
+        BS_TRY(bs_fetch(ctx, &n_all, d_nsel, sizeof(size_t)));
+        BS_TRY(bs_sync(ctx));
         bs_free(ctx, d_tmp); bs_free(ctx, d_nsel);
         BS_TRY(bs_alloc(ctx, &d_keys, n_all));
         tmp_bytes = 0;
@@ -844,8 +830,8 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
             BS_CUDA(ctx, cudaMemsetAsync(d_lh, 0, 2 * sizeof(unsigned long long), st));
             const unsigned long long b0 = klo << 8, b1 = khi == BS_KEY_INVALID ? BS_KEY_INVALID : (khi << 8);
             if (n_all) bs_count_launch(), k_count_below<<<bs_blocks(n_all, TPB), TPB, 0, st>>>(d_keys, n_all, b0, b1, d_lh);
-            BS_CUDA(ctx, cudaMemcpyAsync(h_lh, d_lh, sizeof(h_lh), cudaMemcpyDeviceToHost, st));
-            BS_CUDA(ctx, cudaStreamSynchronize(st));
+            BS_TRY(bs_fetch(ctx, h_lh, d_lh, sizeof(h_lh)));
+            BS_TRY(bs_sync(ctx));
             bs_free(ctx, d_lh);
             lo = (size_t)h_lh[0]; hi = (size_t)h_lh[1];
             if (hi < lo) hi = lo;
@@ -858,8 +844,8 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
         cub::DeviceSelect::Flagged(nullptr, tmp_bytes, d_keys, d_keep, d_kept, d_nk, n_all, st);
         BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp_bytes));
         cub::DeviceSelect::Flagged(d_tmp, tmp_bytes, d_keys, d_keep, d_kept, d_nk, n_all, st);
-        BS_CUDA(ctx, cudaMemcpyAsync(&n_kept, d_nk, sizeof(size_t), cudaMemcpyDeviceToHost, st));
-        BS_CUDA(ctx, cudaStreamSynchronize(st));
+        BS_TRY(bs_fetch(ctx, &n_kept, d_nk, sizeof(size_t)));
+        BS_TRY(bs_sync(ctx));
         bs_free(ctx, d_tmp); bs_free(ctx, d_nk); bs_free(ctx, d_keep);
         s = bs_volume_alloc_bricks(vol, n_kept);
         if (s == BS_OK) s = bs_alloc(ctx, &vol->owned, n_kept);
@@ -904,13 +890,14 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
     BS_TRY(bs_alloc(ctx, &d_touch_kept, n_all));
     if (n_all) bs_count_launch(), k_brick_touches<<<bs_blocks(n_all, TPB), TPB, 0, st>>>(vol->keys, n_all, d_table_keys, d_table_counts, (unsigned)(cap - 1), d_touch_kept, ctx->d_err);
     bs_free(ctx, d_table_keys); bs_free(ctx, d_table_slots); bs_free(ctx, d_table_counts); bs_free(ctx, d_offsets); bs_free(ctx, d_flags); bs_free(ctx, d_neval);
+    bs_free(ctx, d_cta_start); bs_free(ctx, d_dummy);
     // 5. signs + masks
     s = bs_sign_impl(ctx, d_tris, n_mesh, vol, d_touch_kept, d_blk);  // winding numbers see the whole mesh
     bs_free(ctx, d_touch_kept); bs_free(ctx, d_blk); bs_free(ctx, d_tri_ids);
     if (s != BS_OK) { bs_volume_free(vol); return s; }
     BS_CUDA(ctx, cudaGetLastError());
     unsigned derr = 0;
-    BS_CUDA(ctx, cudaMemcpyAsync(&derr, ctx->d_err, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    BS_TRY(bs_fetch(ctx, &derr, ctx->d_err, sizeof(unsigned)));
     bs_marks_end(ctx);  // synchronises
     if (derr) {  // a kernel ran out of a fixed-size resource: an error, never a silently wrong volume
         bs_volume_free(vol);

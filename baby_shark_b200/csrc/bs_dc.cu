@@ -295,9 +295,9 @@ bs_status bs_dc_impl(const bs_volume* v, float voxel_size, const float** d_verts
     BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp_bytes));
     cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_wide, d_off, n + 1, st);
     u64 n_tris = 0; int flag = 0;
-    BS_CUDA(ctx, cudaMemcpyAsync(&n_tris, d_off + n, sizeof(n_tris), cudaMemcpyDeviceToHost, st));
-    BS_CUDA(ctx, cudaMemcpyAsync(&flag, d_flags, sizeof(int), cudaMemcpyDeviceToHost, st));
-    BS_CUDA(ctx, cudaStreamSynchronize(st));
+    BS_TRY(bs_fetch(ctx, &n_tris, d_off + n, sizeof(n_tris)));
+    BS_TRY(bs_fetch(ctx, &flag, d_flags, sizeof(int)));
+    BS_TRY(bs_sync(ctx));
     bs_mark(ctx, "dc_count_ms");
     bs_status s = BS_OK;
     if (flag) s = bs_fail(ctx, BS_ERR_REFERENCE_PANICS, "dual contouring: a sign-change edge end point has no neighbour along some axis; the reference hits unreachable!() (dual_contouring.rs:340)");
@@ -306,7 +306,7 @@ bs_status bs_dc_impl(const bs_volume* v, float voxel_size, const float** d_verts
     bs_mark(ctx, "dc_emit_ms");
     bs_free(ctx, d_tmp); bs_free(ctx, d_cells); bs_free(ctx, d_valid); bs_free(ctx, d_counts); bs_free(ctx, d_wide); bs_free(ctx, d_off); bs_free(ctx, d_flags); bs_free(ctx, d_nbr);
     if (s != BS_OK) return s;
-    BS_CUDA(ctx, cudaStreamSynchronize(st));
+    BS_TRY(bs_sync(ctx));
     BS_CUDA(ctx, cudaGetLastError());
     bs_marks_end(ctx);
     bs_stat_add(ctx, "n_bricks", (double)n);

@@ -639,14 +639,20 @@ __device__ __forceinline__ unsigned demorton9(unsigned p) {
 }
 
 // Active masks + the list of work items for the sign kernel: one item = 32*VPL Morton-adjacent active voxels of one brick.
-__global__ void k_masks(const float* __restrict__ values, size_t n_bricks, unsigned long long* masks, unsigned* n_chunks, int per_chunk, unsigned long long* n_active) {
+// The distance pass (k_eval, bs_convert.cu) leaves the minimum SQUARED distance in every touched voxel: the root is taken
+// here, once per voxel instead of once per point-triangle pair (sqrt is monotone: root of the minimum == minimum of the roots,
+// bit for bit).
+__global__ void k_masks(float* __restrict__ values, size_t n_bricks, unsigned long long* masks, unsigned* n_chunks, int per_chunk, unsigned long long* n_active) {
     const unsigned lane = threadIdx.x & 31;
     const size_t b = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
     if (b >= n_bricks) return;
-    const float* bv = values + b * 512;
+    float* bv = values + b * 512;
     unsigned lo = 0, hi = 0, cnt = 0;
     for (int r = 0; r < 16; ++r) {
-        const unsigned bal = __ballot_sync(0xFFFFFFFFu, __float_as_uint(bv[r * 32 + lane]) != BS_UDF_SENTINEL_BITS);
+        const float v2 = bv[r * 32 + lane];
+        const bool act = __float_as_uint(v2) != BS_UDF_SENTINEL_BITS;
+        if (act) bv[r * 32 + lane] = __fsqrt_rn(v2);
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, act);
         if ((int)lane == (r >> 1)) { if (r & 1) hi = bal; else lo = bal; }
         cnt += __popc(bal);
     }
@@ -968,8 +974,8 @@ bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_v
         BS_TRY(bs_sign_components_impl(ctx, vol, d_blk, &C, d_nchunks, 32 * BS_VPL, d_sc + 1));
         prop = C.ok;
         if (prop) {
-            BS_CUDA(ctx, cudaMemcpyAsync(h_sc, d_sc, sizeof(h_sc), cudaMemcpyDeviceToHost, st));
-            BS_CUDA(ctx, cudaStreamSynchronize(st));
+            BS_TRY(bs_fetch(ctx, h_sc, d_sc, sizeof(h_sc)));
+            BS_TRY(bs_sync(ctx));
             brute = h_sc[1] <= (unsigned long long)bs_sign_brute_max() && !ctx->count_work && !getenv("BSHARK_NO_BRUTE");
         }
         bs_mark(ctx, "sign_components_ms");
@@ -1008,25 +1014,25 @@ bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_v
             BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp_bytes));
             cub::DeviceRadixSort::SortPairsDescending(d_tmp, tmp_bytes, d_k, d_k2, d_i, d_order, nb, 0, 32, st);
             if (split) bs_count_launch(), k_heavy_list<<<bs_blocks(nb, 256), 256, 0, st>>>(d_order, d_k2, nb, d_heavy, d_slot, d_nheavy);
-            BS_CUDA(ctx, cudaMemcpyAsync(&n_heavy, d_nheavy, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+            BS_TRY(bs_fetch(ctx, &n_heavy, d_nheavy, sizeof(unsigned)));
             bs_free(ctx, d_tmp); bs_free(ctx, d_k); bs_free(ctx, d_k2); bs_free(ctx, d_i); bs_free(ctx, d_nheavy);
         }
         unsigned *d_blist = nullptr, *d_nblist = nullptr; unsigned n_blist = 0;
         BS_TRY(bs_alloc(ctx, &d_blist, nb)); BS_TRY(bs_alloc(ctx, &d_nblist, 1));
         BS_CUDA(ctx, cudaMemsetAsync(d_nblist, 0, sizeof(unsigned), st));
         bs_count_launch(), k_item_bricks<<<bs_blocks(nb, 256), 256, 0, st>>>(d_nchunks, nb, d_blist, d_nblist);
-        BS_CUDA(ctx, cudaMemcpyAsync(&n_blist, d_nblist, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        BS_TRY(bs_fetch(ctx, &n_blist, d_nblist, sizeof(unsigned)));
         bs_count_launch(), k_order_chunks<<<bs_blocks(nb + 1, 256), 256, 0, st>>>(d_order, d_nchunks, nb, d_ordered);
         tmp_bytes = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_ordered, d_off, nb + 1, st);
         BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp_bytes));
         cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_ordered, d_off, nb + 1, st);
-        BS_CUDA(ctx, cudaMemcpyAsync(&n_items, d_off + nb, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-        BS_CUDA(ctx, cudaMemcpyAsync(h_sc, d_sc, sizeof(h_sc), cudaMemcpyDeviceToHost, st));
-        BS_CUDA(ctx, cudaStreamSynchronize(st));  // n_heavy has arrived too
+        BS_TRY(bs_fetch(ctx, &n_items, d_off + nb, sizeof(unsigned)));
+        BS_TRY(bs_fetch(ctx, h_sc, d_sc, sizeof(h_sc)));
+        BS_TRY(bs_sync(ctx));  // n_heavy has arrived too
         if (n_heavy) {  // the heavy bricks head `order`: their items are items [0, n_hitems)
-            BS_CUDA(ctx, cudaMemcpyAsync(&n_hitems, d_off + n_heavy, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-            BS_CUDA(ctx, cudaStreamSynchronize(st));
+            BS_TRY(bs_fetch(ctx, &n_hitems, d_off + n_heavy, sizeof(unsigned)));
+            BS_TRY(bs_sync(ctx));
         }
         bs_free(ctx, d_tmp);
         BS_TRY(bs_alloc(ctx, &d_item_brick, n_items));
@@ -1057,8 +1063,8 @@ bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_v
         if (n_hitems) bs_count_launch(), k_sign_finish<BS_VPL><<<bs_blocks((size_t)n_hitems * 32 * BS_VPL, 256), 256, 0, st>>>(vol->values, d_item_brick, 0u, n_hitems, (unsigned)HEAVY_REPL, d_partial, d_offs);
         if (ctx->count_work) {
             unsigned long long h_cnt[9];
-            BS_CUDA(ctx, cudaMemcpyAsync(h_cnt, d_cnt, 72, cudaMemcpyDeviceToHost, st));
-            BS_CUDA(ctx, cudaStreamSynchronize(st));
+            BS_TRY(bs_fetch(ctx, h_cnt, d_cnt, 72));
+            BS_TRY(bs_sync(ctx));
             bs_free(ctx, d_cnt);
             for (int i = 0; i < 9; ++i) ctx->fwn_counts[i] = (double)h_cnt[i];
         }

@@ -421,6 +421,7 @@ struct McDesc {
     unsigned long long* count;  // [n] state << 62 | triangles: state 1 = this brick only, 2 = all bricks up to and including this one
     float* carry;               // [n][4] x, y, z, state: 1 = brick computes no c-vertex (look further back), 2 = xyz is the c-vertex leaving the brick
     unsigned* ticket;
+    const float* init;          // c-vertex entering the volume (x, y, z, valid) when the volume continues an earlier slab (bs_voxel_remesh_into); else null
 };
 struct McWarp {
     float val[732];
@@ -445,7 +446,19 @@ __device__ f3 mcf_incoming_carry(const McDesc& D, long long tile, unsigned lane)
             return f3{__shfl_sync(FULL, v.x, src), __shfl_sync(FULL, v.y, src), __shfl_sync(FULL, v.z, src)};
         }
     }
+    if (D.init && D.init[3] != 0.f) return f3{D.init[0], D.init[1], D.init[2]};  // left behind by the previous slab
     return f3{0.f, 0.f, 0.f};
+}
+// c-vertex leaving the volume (all descriptors final): the next slab of a pipelined remesh starts from it. Most bricks compute
+// none, so the last one that does is found by all bricks in parallel (slot = D.ticket + 1, zeroed with the ticket, holds index + 1).
+__global__ void k_mc_last_carry(McDesc D, long long n) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n && D.carry[4 * i + 3] == 2.f) atomicMax(D.ticket + 1, (unsigned)(i + 1));
+}
+__global__ void k_mc_final_carry(McDesc D, float* out /*x, y, z, valid*/) {
+    const unsigned last = D.ticket[1];
+    if (last) { const long long i = (long long)last - 1; out[0] = D.carry[4 * i]; out[1] = D.carry[4 * i + 1]; out[2] = D.carry[4 * i + 2]; out[3] = 1.f; }
+    else if (!(D.init && D.init[3] != 0.f)) { out[0] = out[1] = out[2] = out[3] = 0.f; }  // (otherwise the incoming one passes through: out == init)
 }
 
 struct McfCarry { f3 run; bool have_run; f3 incoming; bool incoming_known; };
@@ -655,6 +668,214 @@ __global__ void __launch_bounds__(32 * MCF_WARPS, 8) k_mc_fused(VolView V, const
     }
 }
 
+// ---- two-kernel extraction: count (ticketed, carries the c-vertex chain) -> exclusive scan -> emit -------------------------------
+// The one-pass kernel above spends about half its time in the look-back (bricks retire in order) and runs the vertex
+// arithmetic twice per brick inside that wait structure. Split: k_mc_count does stage + classify + tiling + exact triangle
+// count per brick (no ordering between bricks except the rare c-vertex look-back), a device scan turns the counts into
+// offsets, and k_mc_emit -- embarrassingly parallel, bricks without output return before staging anything -- recomputes
+// the candidates, stages each round's triangles in shared memory and copies them out with coalesced stores (the one-pass
+// kernel stored 9 scattered floats per lane and triangle: 277 M four-byte transactions at config 5).
+struct McStageS {
+    float val[732];
+    unsigned short rowA[82], rowS[82];  // per (x, y), x, y in 0..8: bit z = active / negative
+    unsigned short cells[512];          // candidate cells in cell order
+};
+constexpr int MC_STG = 128;  // triangles a round can stage (32 candidates x ~2.4 triangles on average; more: the round goes in two halves, then unstaged)
+struct McEmitS { McStageS g; float tri[MC_STG * 9]; };
+
+// stage brick b (+ halo) into s, classify its 512 cells; returns the number of candidate cells (listed in s.cells)
+__device__ __forceinline__ int mcs_stage_classify(const VolView& V, size_t b, McStageS& s, unsigned lane, int& ox, int& oy, int& oz) {
+    int mynb = -1;
+    if (lane < 8) mynb = V.nbr[b * 8 + lane];
+    { int bx, by, bz; bs_key_brick(V.keys[b], bx, by, bz); ox = bx << 3; oy = by << 3; oz = bz << 3; }
+    {
+        const float4* g4 = reinterpret_cast<const float4*>(V.values + b * 512);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const unsigned q4 = lane + 32 * k, off = q4 * 4;
+            const float4 v = g4[q4];
+            float* d = s.val + (off >> 6) * 81 + ((off >> 3) & 7) * 9 + (off & 7);
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < 7; ++it) {  // the 217 halo entries: x = 8 plane (81), y = 8 plane without x = 8 (72), z = 8 plane without x, y = 8 (64)
+        const unsigned i = lane + 32 * it;
+        unsigned x = 8, y = 0, z = 0;
+        if (i < 81) { y = i / 9; z = i % 9; }
+        else if (i < 153) { x = (i - 81) / 9; y = 8; z = (i - 81) % 9; }
+        else { x = (i - 153) >> 3; y = (i - 153) & 7; z = 8; }
+        const int src = __shfl_sync(FULL, mynb, (x >> 3) | ((y >> 3) << 1) | ((z >> 3) << 2));
+        if (i < 217) s.val[x * 81 + y * 9 + z] = src >= 0 ? V.values[(size_t)src * 512 + (((x & 7) << 6) | ((y & 7) << 3) | (z & 7))] : 0.f;
+    }
+    const unsigned char* mbytes = reinterpret_cast<const unsigned char*>(V.masks);  // byte y of word x = the z-row (x, y)
+#pragma unroll
+    for (int it = 0; it < 3; ++it) {
+        const unsigned r = lane + 32 * it;
+        const unsigned x = r < 81 ? r / 9 : 0, y = r < 81 ? r % 9 : 0;
+        const unsigned nbi = (x >> 3) | ((y >> 3) << 1);
+        const int s0 = __shfl_sync(FULL, mynb, nbi), s1 = __shfl_sync(FULL, mynb, nbi | 4);
+        if (r < 81) {
+            const unsigned bo = (x & 7) * 8 + (y & 7);
+            unsigned a = s0 >= 0 ? mbytes[(size_t)s0 * 64 + bo] : 0u;
+            if (s1 >= 0) a |= (unsigned)(mbytes[(size_t)s1 * 64 + bo] & 1u) << 8;
+            s.rowA[r] = (unsigned short)a;
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 3; ++it) {
+        const unsigned r = lane + 32 * it;
+        if (r < 81) {
+            const float* p = s.val + (r / 9) * 81 + (r % 9) * 9;
+            unsigned m = 0;
+#pragma unroll
+            for (int z = 0; z < 9; ++z) m |= (__float_as_uint(p[z]) >> 31) << z;
+            s.rowS[r] = (unsigned short)m;
+        }
+    }
+    __syncwarp();
+    // a cell is a candidate if its 8 corners are active and their signs differ
+    unsigned cross[2], cnt[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const unsigned c = lane + 32 * h, x = c >> 3, y = c & 7, r = x * 9 + y;
+        const unsigned a = s.rowA[r] & s.rowA[r + 1] & s.rowA[r + 9] & s.rowA[r + 10];
+        const unsigned sa = s.rowS[r] & s.rowS[r + 1] & s.rowS[r + 9] & s.rowS[r + 10];
+        const unsigned so = s.rowS[r] | s.rowS[r + 1] | s.rowS[r + 9] | s.rowS[r + 10];
+        cross[h] = (a & (a >> 1)) & (so | (so >> 1)) & ~(sa & (sa >> 1)) & 0xFFu;
+        cnt[h] = __popc(cross[h]);
+    }
+    unsigned inc0 = cnt[0], inc1 = cnt[1];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t0 = __shfl_up_sync(FULL, inc0, o), t1 = __shfl_up_sync(FULL, inc1, o);
+        if ((int)lane >= o) { inc0 += t0; inc1 += t1; }
+    }
+    const unsigned tot0 = __shfl_sync(FULL, inc0, 31), tot1 = __shfl_sync(FULL, inc1, 31);
+    {
+        unsigned o0 = inc0 - cnt[0], o1 = tot0 + inc1 - cnt[1];
+        for (unsigned m = cross[0]; m; m &= m - 1) s.cells[o0++] = (unsigned short)((lane << 3) | (__ffs(m) - 1));
+        for (unsigned m = cross[1]; m; m &= m - 1) s.cells[o1++] = (unsigned short)(((lane + 32) << 3) | (__ffs(m) - 1));
+    }
+    __syncwarp();
+    return (int)(tot0 + tot1);
+}
+
+__global__ void __launch_bounds__(32 * MCF_WARPS, 8) k_mc_count(VolView V, const signed char* __restrict__ tables, float vs, McDesc D, unsigned* counts) {
+    __shared__ McStageS S[MCF_WARPS];
+    const unsigned lane = threadIdx.x & 31;
+    McStageS& s = S[threadIdx.x >> 5];
+    for (;;) {
+        unsigned tk = 0;
+        if (lane == 0) tk = atomicAdd(D.ticket, 1u);  // ticket order: a brick's predecessors are running or done, so the c-vertex look-back cannot deadlock
+        tk = __shfl_sync(FULL, tk, 0);
+        if (tk >= V.n) break;
+        const long long tile = tk;
+        const size_t b = tk;
+        if (V.owned && !V.owned[b]) {  // halo brick of a sharded volume: emits nothing, passes the c-vertex through
+            if (lane == 0) { *(volatile float*)(D.carry + 4 * tile + 3) = 1.f; counts[b] = 0u; }
+            continue;
+        }
+        int ox, oy, oz;
+        const int n_act = mcs_stage_classify(V, b, s, lane, ox, oy, oz);
+        McfCarry C{f3{0.f, 0.f, 0.f}, false, f3{0.f, 0.f, 0.f}, false};
+        unsigned total = 0;
+        for (int base = 0; base < n_act; base += 32) {
+            const int j = base + (int)lane;
+            Cell q; q.T = tables; q.v12 = f3{0.f, 0.f, 0.f};
+            int row = 0, len = 0; bool need_c = false, stale = false;
+            if (j < n_act) {
+                int id;
+                mcf_load_cell(q, s.val, ox, oy, oz, s.cells[j], id);
+                q.cs = tables[MC33_OFF_CASES + 2 * id]; q.cf = tables[MC33_OFF_CASES + 2 * id + 1];
+                row = select_tiling(q, len, need_c, stale);
+                if (need_c) compute_c_vertex(q);
+            }
+            mcf_resolve(q, need_c, stale, C, D, tile, lane);
+            int n = 0;
+            if (len) n = emit_rows<false>(q, vs, nullptr, row, len);  // exact: degenerate triangles are dropped like the reference does
+#pragma unroll
+            for (int o = 16; o; o >>= 1) n += __shfl_xor_sync(FULL, n, o);
+            total += (unsigned)n;
+        }
+        if (lane == 0) {
+            float* cd = D.carry + 4 * tile;
+            const bool val = C.have_run || C.incoming_known;
+            if (val) { const f3 v = C.have_run ? C.run : C.incoming; *(volatile float*)(cd) = v.x; *(volatile float*)(cd + 1) = v.y; *(volatile float*)(cd + 2) = v.z; __threadfence(); }
+            *(volatile float*)(cd + 3) = val ? 2.f : 1.f;
+            counts[b] = total;
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(32 * MCF_WARPS, 6) k_mc_emit(VolView V, const signed char* __restrict__ tables, float vs, McDesc D, const unsigned* __restrict__ counts,
+                                                                const unsigned long long* __restrict__ offsets, float* out, unsigned long long cap_tris) {
+    __shared__ McEmitS S[MCF_WARPS];
+    const unsigned lane = threadIdx.x & 31;
+    const size_t b = (size_t)blockIdx.x * MCF_WARPS + (threadIdx.x >> 5);
+    if (b >= V.n) return;
+    const unsigned total = counts[b];
+    if (total == 0) return;  // (halo bricks, bricks without a sign change: nothing is staged)
+    unsigned long long running = offsets[b];
+    if (running + total > cap_tris) return;  // the host grows the buffer and runs the emit pass again
+    McEmitS& se = S[threadIdx.x >> 5];
+    McStageS& s = se.g;
+    int ox, oy, oz;
+    const int n_act = mcs_stage_classify(V, b, s, lane, ox, oy, oz);
+    const long long tile = (long long)b;
+    McfCarry C{f3{0.f, 0.f, 0.f}, false, f3{0.f, 0.f, 0.f}, false};  // (the carry chain is final: look-backs do not wait)
+    for (int base = 0; base < n_act; base += 32) {
+        const int j = base + (int)lane;
+        Cell q; q.T = tables; q.v12 = f3{0.f, 0.f, 0.f};
+        int row = 0, len = 0; bool need_c = false, stale = false;
+        if (j < n_act) {
+            int id;
+            mcf_load_cell(q, s.val, ox, oy, oz, s.cells[j], id);
+            q.cs = tables[MC33_OFF_CASES + 2 * id]; q.cf = tables[MC33_OFF_CASES + 2 * id + 1];
+            row = select_tiling(q, len, need_c, stale);
+            if (need_c) compute_c_vertex(q);
+        }
+        mcf_resolve(q, need_c, stale, C, D, tile, lane);
+        const int nmax_all = len / 3;  // triangles of the tiling row; fewer are emitted only when one is degenerate
+        int inc_all = nmax_all;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, inc_all, o); if ((int)lane >= o) inc_all += t; }
+        const int halves = __shfl_sync(FULL, inc_all, 31) <= MC_STG ? 1 : 2;
+        for (int h = 0; h < halves; ++h) {
+            const bool in = halves == 1 || (int)(lane >> 4) == h;
+            const int nmax = in ? nmax_all : 0;
+            int incm = nmax;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, incm, o); if ((int)lane >= o) incm += t; }
+            const int totm = __shfl_sync(FULL, incm, 31);
+            bool fast = totm <= MC_STG;
+            int n = 0;
+            if (fast) {
+                if (nmax) n = emit_rows<true>(q, vs, se.tri + (incm - nmax) * 9, row, len);
+                fast = !__any_sync(FULL, n != nmax);
+            }
+            if (fast) {  // the staged triangles are dense: coalesced copy to their final place
+                __syncwarp();
+                float* dst = out + running * 9;
+                for (int i = (int)lane; i < totm * 9; i += 32) dst[i] = se.tri[i];
+                running += (unsigned long long)totm;
+                __syncwarp();
+            } else {  // a degenerate triangle was dropped (or the half does not fit): exact counts, then direct stores
+                n = nmax ? emit_rows<false>(q, vs, nullptr, row, len) : 0;
+                int inc = n;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, inc, o); if ((int)lane >= o) inc += t; }
+                if (n) emit_rows<true>(q, vs, out + (running + (unsigned long long)(inc - n)) * 9, row, len);
+                running += (unsigned long long)__shfl_sync(FULL, inc, 31);
+                __syncwarp();
+            }
+        }
+    }
+}
+struct WidenU32 { __device__ unsigned long long operator()(unsigned v) const { return v; } };
+
 __global__ void k_shift_carry(const CarryV12* __restrict__ incl, CarryV12* excl, size_t n) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i < n) excl[i] = i ? incl[i - 1] : CarryV12{0.f, 0.f, 0.f, 0};
@@ -790,12 +1011,57 @@ bs_status bs_mc_impl(const bs_volume* v, float voxel_size, const float** d_verts
     if (n) bs_count_launch(), k_mc_neighbours<<<bs_blocks(n * 8, 256), 256, 0, st>>>(v->keys, n, d_nbr);
     VolView V{v->keys, v->values, v->masks, n, v->owned, d_nbr, v->tile8_keys, v->tile8_values, nt8, v->tile128_keys, v->tile128_values, nt128};
     const signed char* tables = (const signed char*)ctx->d_mc33;
+    static const bool use_fused = getenv("BSHARK_MC_FUSED") != nullptr;  // A/B switch: the one-pass look-back kernel
+    if (!(nt8 || nt128) && !use_fused) {
+        // count (ticketed) -> scan -> emit; the output buffer is sized from the previous extraction (or a guess) and only the
+        // emit pass is repeated, with the exact size, if that turns out too small
+        unsigned long long* d_desc = nullptr;  // [2n] carry records (4 floats each), 1 ticket word
+        unsigned* d_counts = nullptr; unsigned long long* d_offsets = nullptr;
+        BS_TRY(bs_alloc(ctx, &d_desc, 2 * n + 1)); BS_TRY(bs_alloc(ctx, &d_counts, n + 1)); BS_TRY(bs_alloc(ctx, &d_offsets, n + 1));
+        McDesc D{nullptr, reinterpret_cast<float*>(d_desc), reinterpret_cast<unsigned*>(d_desc + 2 * n), ctx->mc_chain ? ctx->d_mc_carry : nullptr};
+        static bool carve = false;
+        if (!carve) {
+            cudaFuncSetAttribute(k_mc_count, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(k_mc_emit, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            carve = true;
+        }
+        BS_CUDA(ctx, cudaMemsetAsync(d_desc, 0, (2 * n + 1) * sizeof(unsigned long long), st));
+        BS_CUDA(ctx, cudaMemsetAsync(d_counts + n, 0, sizeof(unsigned), st));
+        const unsigned grid0 = (unsigned)std::min<size_t>((n + MCF_WARPS - 1) / MCF_WARPS, (size_t)ctx->sm_count * 8);
+        bs_count_launch(), k_mc_count<<<grid0, 32 * MCF_WARPS, 0, st>>>(V, tables, voxel_size, D, d_counts);
+        bs_mark(ctx, "mc_count_ms");
+        void* d_tmp = nullptr; size_t tmp_bytes = 0;
+        cub::TransformInputIterator<unsigned long long, WidenU32, const unsigned*> wide(d_counts, WidenU32());
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, wide, d_offsets, (int)(n + 1), st);
+        BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp_bytes));
+        cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, wide, d_offsets, (int)(n + 1), st);
+        unsigned long long n_tris = 0;
+        BS_TRY(bs_fetch(ctx, &n_tris, d_offsets + n, sizeof(n_tris)));
+        bs_status s = BS_OK;
+        if (ctx->out_verts_cap == 0) s = bs_ensure_out_verts(ctx, n * 160 * 9);
+        for (int attempt = 0; s == BS_OK && attempt < 2; ++attempt) {
+            bs_count_launch(), k_mc_emit<<<(unsigned)((n + MCF_WARPS - 1) / MCF_WARPS), 32 * MCF_WARPS, 0, st>>>(V, tables, voxel_size, D, d_counts, d_offsets, ctx->d_out_verts, (unsigned long long)(ctx->out_verts_cap / 9));
+            if (attempt == 0) BS_TRY(bs_sync(ctx));
+            if ((size_t)n_tris * 9 <= ctx->out_verts_cap) break;
+            s = bs_ensure_out_verts(ctx, (size_t)n_tris * 9);  // too small: grow to the exact size and emit again
+        }
+        if (s == BS_OK && ctx->mc_chain) { bs_count_launch(), k_mc_last_carry<<<bs_blocks(n, 256), 256, 0, st>>>(D, (long long)n); bs_count_launch(), k_mc_final_carry<<<1, 1, 0, st>>>(D, ctx->d_mc_carry); }
+        bs_mark(ctx, "mc_emit_ms");
+        bs_free(ctx, d_tmp); bs_free(ctx, d_desc); bs_free(ctx, d_counts); bs_free(ctx, d_offsets); bs_free(ctx, d_nbr);
+        if (s != BS_OK) return s;
+        BS_CUDA(ctx, cudaGetLastError());
+        bs_marks_end(ctx);
+        bs_stat_add(ctx, "n_bricks", (double)n);
+        bs_stat_add(ctx, "n_out_tris", (double)n_tris);
+        *d_verts = ctx->d_out_verts; *n_verts = (size_t)n_tris * 3;
+        return BS_OK;
+    }
     if (!(nt8 || nt128)) {
         // single pass: per-brick descriptors + ticket; the output buffer is sized from the previous extraction (or a
         // guess) and the pass is repeated once with the exact size if it turns out too small
         unsigned long long* d_desc = nullptr;  // [n] count descriptors, [2n] carry records (4 floats each), 1 ticket word
         BS_TRY(bs_alloc(ctx, &d_desc, 3 * n + 1));
-        McDesc D{d_desc, reinterpret_cast<float*>(d_desc + n), reinterpret_cast<unsigned*>(d_desc + 3 * n)};
+        McDesc D{d_desc, reinterpret_cast<float*>(d_desc + n), reinterpret_cast<unsigned*>(d_desc + 3 * n), ctx->mc_chain ? ctx->d_mc_carry : nullptr};
         static bool carve = false;
         if (!carve) { cudaFuncSetAttribute(k_mc_fused, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); carve = true; }
         const unsigned grid = (unsigned)std::min<size_t>((n + MCF_WARPS - 1) / MCF_WARPS, (size_t)ctx->sm_count * 8);
@@ -805,12 +1071,13 @@ bs_status bs_mc_impl(const bs_volume* v, float voxel_size, const float** d_verts
         for (int attempt = 0; s == BS_OK && attempt < 2; ++attempt) {
             BS_CUDA(ctx, cudaMemsetAsync(d_desc, 0, (3 * n + 1) * sizeof(unsigned long long), st));
             bs_count_launch(), k_mc_fused<<<grid, 32 * MCF_WARPS, 0, st>>>(V, tables, voxel_size, D, ctx->d_out_verts, (unsigned long long)(ctx->out_verts_cap / 9));
-            BS_CUDA(ctx, cudaMemcpyAsync(&n_tris, d_desc + (n - 1), sizeof(n_tris), cudaMemcpyDeviceToHost, st));
-            BS_CUDA(ctx, cudaStreamSynchronize(st));
+            BS_TRY(bs_fetch(ctx, &n_tris, d_desc + (n - 1), sizeof(n_tris)));
+            BS_TRY(bs_sync(ctx));
             n_tris &= (1ull << 62) - 1;
             if ((size_t)n_tris * 9 <= ctx->out_verts_cap) break;
             s = bs_ensure_out_verts(ctx, (size_t)n_tris * 9);  // too small: grow to the exact size and run again
         }
+        if (s == BS_OK && ctx->mc_chain) { bs_count_launch(), k_mc_last_carry<<<bs_blocks(n, 256), 256, 0, st>>>(D, (long long)n); bs_count_launch(), k_mc_final_carry<<<1, 1, 0, st>>>(D, ctx->d_mc_carry); }
         bs_mark(ctx, "mc_emit_ms");
         bs_free(ctx, d_desc); bs_free(ctx, d_nbr);
         if (s != BS_OK) return s;
@@ -833,8 +1100,8 @@ bs_status bs_mc_impl(const bs_volume* v, float voxel_size, const float** d_verts
     BS_TRY(bs_alloc(ctx, &d_writer, n)); BS_TRY(bs_alloc(ctx, &d_unres, n)); BS_TRY(bs_alloc(ctx, &d_any, 1));
     BS_CUDA(ctx, cudaMemsetAsync(d_any, 0, sizeof(int), st));
     if (n) bs_count_launch(), k_mc<false><<<(unsigned)n, MC_TPB, 0, st>>>(V, tables, voxel_size, d_pos, d_counts, nullptr, nullptr, d_writer, nullptr, d_unres, 0, d_any);
-    BS_CUDA(ctx, cudaMemcpyAsync(&any_unres, d_any, sizeof(int), cudaMemcpyDeviceToHost, st));
-    BS_CUDA(ctx, cudaStreamSynchronize(st));
+    BS_TRY(bs_fetch(ctx, &any_unres, d_any, sizeof(int)));
+    BS_TRY(bs_sync(ctx));
     if (any_unres) {  // rare: some 6.1.2 cell needs the c-vertex left behind by an earlier brick -> carry scan, recount those bricks
         BS_TRY(bs_alloc(ctx, &d_carry_incl, n)); BS_TRY(bs_alloc(ctx, &d_incoming, n));
         void* d_t2 = nullptr; size_t t2 = 0;
@@ -853,8 +1120,8 @@ bs_status bs_mc_impl(const bs_volume* v, float voxel_size, const float** d_verts
     BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp_bytes));
     cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_wide, d_off, n_items + 1, st);
     unsigned long long n_tris = 0;
-    BS_CUDA(ctx, cudaMemcpyAsync(&n_tris, d_off + n_items, sizeof(n_tris), cudaMemcpyDeviceToHost, st));
-    BS_CUDA(ctx, cudaStreamSynchronize(st));
+    BS_TRY(bs_fetch(ctx, &n_tris, d_off + n_items, sizeof(n_tris)));
+    BS_TRY(bs_sync(ctx));
     bs_mark(ctx, "mc_count_ms");
     bs_status s = bs_ensure_out_verts(ctx, (size_t)n_tris * 9);
     if (s == BS_OK && n_tris) {

@@ -411,8 +411,8 @@ static bs_status mesh_closed_exact(bs_context* ctx, const float* d_tris, size_t 
     cub::DeviceRadixSort::SortKeys(d_tmp, tmp, k1, k2, (int)nv, 0, 64, st);
     bs_count_launch(), k_sp_edges_check<<<bs_blocks(nv, 256), 256, 0, st>>>(k2, nv, d_bad);
     int bad = 1;
-    BS_CUDA(ctx, cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
-    BS_CUDA(ctx, cudaStreamSynchronize(st));
+    BS_TRY(bs_fetch(ctx, &bad, d_bad, sizeof(int)));
+    BS_TRY(bs_sync(ctx));
     bs_free(ctx, d_tmp); bs_free(ctx, table); bs_free(ctx, vid); bs_free(ctx, k1); bs_free(ctx, k2); bs_free(ctx, d_bad);
     *closed = bad == 0;
     return BS_OK;
@@ -430,8 +430,8 @@ bs_status bs_mesh_closed_begin(bs_context* ctx, const float* d_tris, size_t n_tr
     BS_CUDA(ctx, cudaMemsetAsync(chk->d_bad, 0, sizeof(int), st));
     const unsigned grid = (unsigned)std::min<size_t>(bs_blocks(n_tris, 256), (size_t)ctx->sm_count * 16);
     bs_count_launch(), k_sp_fingerprint<<<grid, 256, 0, st>>>(d_tris, n_tris, chk->d_sums, chk->d_bad);
-    BS_CUDA(ctx, cudaMemcpyAsync(chk->h_sums, chk->d_sums, 4 * sizeof(u64), cudaMemcpyDeviceToHost, st));
-    BS_CUDA(ctx, cudaMemcpyAsync(&chk->h_bad, chk->d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    BS_TRY(bs_fetch(ctx, chk->h_sums, chk->d_sums, 4 * sizeof(u64)));
+    BS_TRY(bs_fetch(ctx, &chk->h_bad, chk->d_bad, sizeof(int)));
     chk->pending = true;
     return BS_OK;
 }

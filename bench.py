@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1 output exchange: p2p = every rank stores its slice into all peers' buffers over NVLink (bs_context_push_out_verts, "
                          "CUDA IPC mapped peer memory); nccl = torch.distributed all-gather (the baseline)")
+    ap.add_argument("--remesh-slabs", type=int, default=0, help="N = 1 e2e leg: slabs of the pipelined remesh call (0 = the library's choice)")
+    ap.add_argument("--e2e-two-calls", action="store_true", help="N = 1 e2e leg through bs_mesh_to_volume + bs_mesh_mc_device + bs_context_copy_out_verts (no overlap) instead of bs_voxel_remesh_into")
     ap.add_argument("--io", action="store_true", help="time the rows either side of the path on the --config mesh: STL decode / encode, merge_points, ActiveVoxelsMesher")
     ap.add_argument("--ops", action="store_true", help="time the CSG (config 2) / offset (3) / dual contouring (4) rows instead of the remesh")
     return ap.parse_args()
@@ -523,6 +525,22 @@ def main():
         ctx.check(L.bs_context_copy_out_verts(ctx._h, C.c_void_p(h_out.data_ptr()), n_floats))
         return nv.value
 
+    def step_e2e_remesh():
+        """N = 1: VoxelRemesher::remesh as ONE library call, pinned host triangles in, pinned host vertices out; the library
+        converts + extracts slab by slab and overlaps the read-back of one slab with the kernels of the next"""
+        nonlocal h_out
+        if h_out is None:
+            h_out = torch.empty(int(n_verts_local * 3 * 1.1) + 1024, dtype=torch.float32).pin_memory()
+        nf = C.c_size_t()
+        for _ in range(2):
+            st = L.bs_voxel_remesh_into(ctx._h, C.c_void_p(h_tris.data_ptr()), n_tris, vs, 0, args.remesh_slabs, C.c_void_p(h_out.data_ptr()), h_out.numel(), C.byref(nf))
+            if st == 3 and nf.value > h_out.numel():
+                h_out = torch.empty(int(nf.value * 1.1) + 1024, dtype=torch.float32).pin_memory()
+                continue
+            break
+        ctx.check(st)
+        return nf.value // 3
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -589,14 +607,16 @@ def main():
     mc_ms = {k: v / args.steps for k, v in stage_ms.items()}
 
     # ---- e2e leg ---------------------------------------------------------------------------------------------------
+    e2e_step = step_e2e_remesh if (world == 1 and not args.e2e_two_calls) else step_e2e
     for _ in range(min(args.warmup, 2)):
-        step_e2e()
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        nv_e2e = step_e2e()
+        nv_e2e = e2e_step()
     barrier()
     e2e_s = time.perf_counter() - t0
+    e2e_stats = ctx.last_stats() if e2e_step is step_e2e_remesh else None
 
     # ---- self-check: the vertices the e2e leg just delivered to the host (and, on one GPU, the volume itself) must be the
     # CPU oracle's, bit for bit and in order (fingerprints written by tests/golden/make_config_hashes.py at this size) ------
@@ -747,7 +767,9 @@ def main():
             "remesh_ms": ms_per_step, "tris_per_s": (n_verts / 3.0) / (ms_per_step * 1e-3), "n_active_voxels": n_active, "n_out_triangles": n_verts / 3.0,
             "step_ms": step_ms, "step_phase_ms": phase_ms, "stage_ms": stage_all, "stage_ms_per_rank": per_rank, "work": work,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": int(tris.nbytes), "d2h_bytes_per_step": int(n_verts * 12),
-                    "what": "pinned host triangles in (N > 1: uploaded by rank 0, broadcast over NVLink), all output vertices back in host memory (N > 1: every rank copies its slice into one shared page-locked buffer)"},
+                    "what": ("one bs_voxel_remesh_into call (VoxelRemesher::remesh): pinned host triangles in, all output vertices in pinned host memory; %d slabs, the read-back of one slab overlaps the kernels of the next" % int((e2e_stats or {}).get("remesh_slabs", 0))) if e2e_stats is not None else
+                            "pinned host triangles in (N > 1: uploaded by rank 0, broadcast over NVLink), all output vertices back in host memory (N > 1: every rank copies its slice into one shared page-locked buffer)",
+                    "stage_ms_sum_over_slabs": {k: v for k, v in (e2e_stats or {}).items() if k.endswith("_ms") and k != "total_ms"} or None},
             "e2e_indexed": None, "gpu_launches": None, "clocks": clocks,
             "roofline": dominant, "rooflines": rl,
             "verified": verify_out["verified"] if verify_out else None, "verify": verify_out,

@@ -5,6 +5,7 @@
 //   move semantics  -> rvalue-qualified union_/subtract/intersect/offset consume *this and the argument
 // (the reference is compiled Rust; no Rust toolchain exists in this image, so the runnable host mirror is C++.)
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cstddef>
 #include <cstdint>
@@ -248,11 +249,21 @@ class VoxelRemesher {
 public:
     VoxelRemesher& with_voxel_size(float size) { m2v_.set_voxel_size(size); voxel_size_ = size; return *this; }
     VoxelRemesher& with_meshing_method(MeshingMethod m) { method_ = m; return *this; }
-    std::optional<std::vector<Vec3f>> remesh(const float* tris, std::size_t n_tris) {
-        auto sdf = m2v_.convert(tris, n_tris);
-        if (!sdf) return std::nullopt;
-        if (method_ == MeshingMethod::FeaturePreserving) return voxel::DualContouringMesher().with_voxel_size(voxel_size_).mesh(*sdf);
-        return voxel::MarchingCubesMesher().with_voxel_size(voxel_size_).mesh(*sdf);
+    // one call, host triangles in, host vertices out: upload, slab-wise convert + extraction, read-back overlapped with
+    // the kernels (bs_voxel_remesh_into); the same vertices, bit for bit, as convert() followed by mesh()
+    std::optional<std::vector<Vec3f>> remesh(const float* tris, std::size_t n_tris, Context& c = Context::global()) {
+        std::vector<Vec3f> out(std::max<std::size_t>(1024, 12 * n_tris));
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            std::size_t n = 0;
+            const bs_status st = bs_voxel_remesh_into(c.get(), tris, n_tris, voxel_size_, method_ == MeshingMethod::FeaturePreserving ? 1 : 0, 0, out[0].data(), out.size() * 3, &n);
+            if (st == BS_ERR_EMPTY_MESH) return std::nullopt;
+            if (st == BS_ERR_INVALID && n > out.size() * 3) { out.resize(n / 3); continue; }  // the estimate was too small: retry with the reported size
+            c.check(st);
+            out.resize(n / 3);
+            return out;
+        }
+        c.check(BS_ERR_INVALID);
+        return std::nullopt;
     }
 private:
     voxel::MeshToVolume m2v_{}; MeshingMethod method_ = MeshingMethod::Manifold; float voxel_size_ = 1.0f;

@@ -108,6 +108,17 @@ bs_status bs_mesh_mc(const bs_volume* v, float voxel_size, float** verts, size_t
  * nondeterministic (rayon + Mutex); this returns leaves in visit order. BS_ERR_REFERENCE_PANICS where the
  * reference hits todo!() (active tiles) or unreachable!() (:340). */
 bs_status bs_mesh_dc(const bs_volume* v, float voxel_size, float** verts, size_t* n_verts);
+/* VoxelRemesher::remesh (src/remeshing/voxel.rs:64-84): MeshToVolume::convert with band width 0, then
+ * MarchingCubesMesher (method 0 = MeshingMethod::Manifold, the default) or DualContouringMesher (method 1 =
+ * FeaturePreserving), in ONE call from host triangles (9 floats each) to the vertex soup in caller-owned host memory
+ * (`dst`, room for cap_floats floats; page-locked memory lets the read-back overlap the kernels). The mesh is converted
+ * and extracted in `slabs` contiguous pieces of the reference's leaf visit order (0 = pick: 4 from ~1 M triangles, else
+ * 1; env BSHARK_REMESH_SLABS), the copy of one piece running while the next is computed; the result is the same vertex
+ * array, bit for bit, as bs_mesh_to_volume + bs_mesh_mc / bs_mesh_dc. *n_floats receives the size of the result; when it
+ * exceeds cap_floats the call returns BS_ERR_INVALID and the caller retries with a buffer of that size.
+ * BS_ERR_EMPTY_MESH where the reference returns None. */
+bs_status bs_voxel_remesh_into(bs_context* ctx, const float* tris, size_t n_tris, float voxel_size, int method, int slabs,
+                               float* dst, size_t cap_floats, size_t* n_floats);
 /* Same, leaving the vertices on the device: *d_verts is a device pointer (n_verts x 3 floats) owned by the
  * context and valid until the next extraction call on the same context or bs_context_destroy. */
 bs_status bs_mesh_mc_device(const bs_volume* v, float voxel_size, const float** d_verts, size_t* n_verts);

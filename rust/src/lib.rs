@@ -188,6 +188,33 @@ impl MeshToVolume {
     }
 }
 
+/// remeshing::voxel::{MeshingMethod, VoxelRemesher} (src/remeshing/voxel.rs:10-95): one FFI call from the triangle soup to
+/// the vertex soup; the library converts and extracts slab by slab and overlaps the read-back with the kernels.
+#[derive(Clone, Copy, PartialEq, Eq)]
+pub enum MeshingMethod { FeaturePreserving, Manifold }
+pub struct VoxelRemesher { voxel_size: f32, method: MeshingMethod }
+impl Default for VoxelRemesher { fn default() -> Self { Self { voxel_size: 1.0, method: MeshingMethod::Manifold } } }
+impl VoxelRemesher {
+    pub fn with_voxel_size(mut self, size: f32) -> Self { self.voxel_size = size; self }
+    pub fn with_meshing_method(mut self, method: MeshingMethod) -> Self { self.method = method; self }
+    /// `remesh` of the reference takes any `TriangleMesh`; the shim's caller hands over its triangle soup (9 floats each).
+    pub fn remesh(&mut self, soup: &[Vec3f]) -> Option<Vec<Vec3f>> {
+        let n_tris = soup.len() / 3;
+        let mut out: Vec<Vec3f> = Vec::with_capacity(std::cmp::max(1024, 12 * n_tris));
+        for _ in 0..2 {
+            let mut n = 0usize;
+            let st = unsafe { ffi::bs_voxel_remesh_into(ctx(), soup.as_ptr() as *const f32, n_tris, self.voxel_size,
+                if self.method == MeshingMethod::FeaturePreserving { 1 } else { 0 }, 0, out.as_mut_ptr() as *mut f32, out.capacity() * 3, &mut n) };
+            if st == ffi::BS_ERR_EMPTY_MESH { return None; }
+            if st == ffi::BS_ERR_INVALID && n > out.capacity() * 3 { out = Vec::with_capacity(n / 3); continue; }  // estimate too small: retry with the reported size
+            check(st);
+            unsafe { out.set_len(n / 3) };
+            return Some(out);
+        }
+        unreachable!()
+    }
+}
+
 pub mod prelude {
     pub use super::{DualContouringMesher, MarchingCubesMesher, MeshToVolume, Volume, VolumeBuilder};
 }

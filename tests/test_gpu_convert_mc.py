@@ -2,6 +2,7 @@
 import numpy as np
 import pytest
 
+from baby_shark_b200 import synth
 from util import compare_soups, compare_volumes
 
 pytestmark = pytest.mark.gpu
@@ -236,3 +237,29 @@ def test_sharded_ranks_partition_the_volume_exactly(bs, world):
         assert np.array_equal(d["values"][a].view(np.uint32), full["values"][idx][a].view(np.uint32))
     assert owned_total == full["origins"].shape[0]
     assert nonempty >= min(world, 2)
+
+
+@pytest.mark.parametrize("slabs", [1, 2, 3, 8])
+def test_pipelined_remesh_equals_convert_then_mesh(bs, slabs):
+    # VoxelRemesher::remesh as one call (bs_voxel_remesh_into): slab-wise convert + extraction with the read-back of one
+    # slab overlapping the next -- the same vertices, bit for bit and in order, as convert followed by mesh
+    tris, vs, _ = synth.config_mesh(5, 0.06)
+    vol = bs.MeshToVolume().with_voxel_size(vs).convert(tris)
+    for method, mesher in ((bs.MeshingMethod.Manifold, bs.MarchingCubesMesher()), (bs.MeshingMethod.FeaturePreserving, bs.DualContouringMesher())):
+        ref = mesher.with_voxel_size(vs).mesh(vol)
+        r = bs.VoxelRemesher().with_voxel_size(vs).with_meshing_method(method)
+        out = np.full(ref.size + 64, np.nan, np.float32)
+        n = r.remesh_into(np.ascontiguousarray(tris, np.float32), out, slabs)
+        assert n == ref.size
+        assert np.array_equal(out[:n].view(np.uint32), ref.reshape(-1).view(np.uint32))
+        assert np.isnan(out[n:]).all()
+        if slabs > 1:
+            assert bs.Context.default().last_stats()["remesh_slabs"] == slabs
+    # a buffer that is too small reports the size to retry with; the public wrapper retries by itself
+    small = np.empty(1000, np.float32)
+    need = bs.VoxelRemesher().with_voxel_size(vs).remesh_into(np.ascontiguousarray(tris, np.float32), small, slabs)
+    assert need > small.size
+    got = bs.VoxelRemesher().with_voxel_size(vs).remesh(tris, slabs)
+    mc = bs.MarchingCubesMesher().with_voxel_size(vs).mesh(vol)
+    assert np.array_equal(got.view(np.uint32), mc.view(np.uint32))
+    assert bs.VoxelRemesher().with_voxel_size(vs).remesh(np.zeros((0, 9), np.float32)) is None
