@@ -28,7 +28,7 @@ EXPORTS = [
     "bs_volume_from_voxels", "bs_volume_empty", "bs_volume_sphere", "bs_volume_cuboid", "bs_volume_iwp",
     "bs_volume_clone", "bs_volume_free", "bs_volume_voxel_size",
     "bs_volume_union", "bs_volume_subtract", "bs_volume_intersect", "bs_volume_offset",
-    "bs_mesh_mc", "bs_mesh_dc", "bs_mesh_mc_device", "bs_mesh_dc_device", "bs_buffer_free", "bs_voxel_remesh_into",
+    "bs_mesh_mc", "bs_mesh_dc", "bs_mesh_mc_device", "bs_mesh_dc_device", "bs_buffer_free", "bs_voxel_remesh_into", "bs_mesh_mc_count", "bs_mesh_mc_emit_push",
     "bs_volume_download", "bs_volume_counts", "bs_context_last_stats", "bs_context_copy_out_verts", "bs_context_copy_out_verts_device", "bs_context_set_flag", "bs_kernel_launch_count",
     "bs_stl_decode", "bs_stl_decode_device", "bs_stl_encode", "bs_stl_encode_device", "bs_mesh_active_voxels", "bs_mesh_active_voxels_device",
     "bs_merge_points", "bs_merge_points_device", "bs_device_free", "bs_mesh_mc_indexed", "bs_mesh_mc_indexed_device", "bs_copy_to_host",
@@ -90,6 +90,8 @@ def load_library(path=None):
         "bs_mesh_dc_device": (C.c_int, [vp, C.c_float, pvp, psz]),
         "bs_buffer_free": (None, [vp]),
         "bs_voxel_remesh_into": (C.c_int, [vp, vp, sz, C.c_float, C.c_int, C.c_int, vp, sz, psz]),
+        "bs_mesh_mc_count": (C.c_int, [vp, C.c_float, psz]),
+        "bs_mesh_mc_emit_push": (C.c_int, [vp, pvp, C.c_int, sz, sz]),
         "bs_volume_download": (C.c_int, [vp, C.POINTER(C.POINTER(C.c_int32)), C.POINTER(fp), C.POINTER(C.POINTER(C.c_uint64)), psz,
                                          C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.POINTER(C.c_int32)), C.POINTER(fp), psz]),
         "bs_volume_counts": (C.c_int, [vp, psz, psz, psz, psz]),

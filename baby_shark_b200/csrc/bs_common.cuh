@@ -80,6 +80,11 @@ extern unsigned long long g_bs_launches;
 static inline void bs_count_launch() { ++g_bs_launches; }
 
 struct bs_volume;
+// products of a marching-cubes count that the matching emit consumes (bs_mc.cu)
+struct bs_mc_pending {
+    const bs_volume* vol = nullptr; float voxel_size = 0.f; size_t n = 0; unsigned long long n_tris = 0;
+    unsigned long long* d_desc = nullptr; unsigned* d_counts = nullptr; unsigned long long* d_offsets = nullptr; int* d_nbr = nullptr;
+};
 struct bs_context {
     // One in-flight call per context: every entry point of the ABI holds this lock for its whole duration (BS_ENTER),
     // so handles may be used from several host threads. The result of a *_device extraction stays valid until the next
@@ -114,6 +119,7 @@ struct bs_context {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     float* d_mc_carry = nullptr; bool mc_chain = false;
+    bs_mc_pending mc_pending;
     // small read-backs (bs_fetch / bs_sync): page-locked scratch the device writes directly, so that the counters a call needs
     // on the host never queue behind a bulk copy on a copy engine
     unsigned* h_ctrl = nullptr; unsigned* d_ctrl = nullptr; size_t ctrl_used = 0;
@@ -197,6 +203,9 @@ bs_status bs_convert_impl(bs_context* ctx, const float* d_tris, size_t n_tris, f
 bs_status bs_sign_impl(bs_context* ctx, const float* d_tris, size_t n_tris, bs_volume* vol, const unsigned long long* d_touches /*per brick, may be null*/,
                        const unsigned long long* d_blk /*blocked lattice edges, 24 words per brick; null = per-voxel signs*/);
 bs_status bs_mc_impl(const bs_volume* v, float voxel_size, const float** d_verts, size_t* n_verts);
+bs_status bs_mc_count_phase(const bs_volume* v, float voxel_size, size_t* n_verts);  // volumes without active tiles
+bs_status bs_mc_emit_phase(const bs_volume* v, float* const* dst, int world, size_t offset_floats, size_t cap_floats);
+void bs_mc_pending_release(bs_context* ctx);
 bs_status bs_dc_impl(const bs_volume* v, float voxel_size, const float** d_verts, size_t* n_verts);
 bs_status bs_csg_impl(bs_volume* a, bs_volume* b, int op, bs_volume** out);
 bs_status bs_offset_impl(bs_volume* a, float distance, bs_volume** out);

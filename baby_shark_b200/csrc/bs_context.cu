@@ -307,6 +307,7 @@ void bs_volume_free(bs_volume* v) {
     if (!c) { delete v; return; }  // orphaned by bs_context_destroy
     BS_ENTER(c);
     c->live_volumes.erase(v);
+    if (c->mc_pending.vol == v) bs_mc_pending_release(c);
     bs_free(c, v->keys); bs_free(c, v->values); bs_free(c, v->masks); bs_free(c, v->owned);
     bs_free(c, v->tile8_keys); bs_free(c, v->tile8_values); bs_free(c, v->tile128_keys); bs_free(c, v->tile128_values);
     delete v;
@@ -520,6 +521,33 @@ bs_status bs_mesh_mc_device(const bs_volume* v, float voxel_size, const float** 
     if (!v || !v->ctx || !d_verts || !n_verts) return BS_ERR_INVALID;
     BS_ENTER(v->ctx);
     return bs_mc_impl(v, voxel_size, d_verts, n_verts);
+}
+bs_status bs_mesh_mc_count(const bs_volume* v, float voxel_size, size_t* n_verts) {
+    if (!v || !v->ctx || !n_verts) return BS_ERR_INVALID;
+    bs_context* ctx = v->ctx;
+    BS_ENTER(ctx);
+    if (v->n_tiles8 || v->n_tiles128) return bs_fail(ctx, BS_ERR_UNSUPPORTED, "two-step marching cubes on a volume with active tiles (use bs_mesh_mc_device)");
+    bs_mc_pending_release(ctx);
+    bs_marks_begin(ctx);
+    const bs_status s = bs_mc_count_phase(v, voxel_size, n_verts);
+    if (s != BS_OK) return s;
+    bs_marks_end(ctx);
+    bs_stat_add(ctx, "n_bricks", (double)v->n_bricks);
+    bs_stat_add(ctx, "n_out_tris", (double)(*n_verts / 3));
+    return BS_OK;
+}
+bs_status bs_mesh_mc_emit_push(const bs_volume* v, float* const* dst, int world, size_t offset_floats, size_t cap_floats) {
+    if (!v || !v->ctx || !dst || world < 1 || world > 16) return BS_ERR_INVALID;
+    bs_context* ctx = v->ctx;
+    BS_ENTER(ctx);
+    for (int d = 0; d < world; ++d) if (!dst[d]) return bs_fail(ctx, BS_ERR_INVALID, "null destination %d", d);
+    bs_marks_begin(ctx);
+    const bs_status s = bs_mc_emit_phase(v, dst, world, offset_floats, cap_floats);
+    bs_mc_pending_release(ctx);
+    if (s != BS_OK) return s;
+    BS_CUDA(ctx, cudaGetLastError());
+    bs_marks_end(ctx);
+    return BS_OK;
 }
 bs_status bs_mesh_mc(const bs_volume* v, float voxel_size, float** verts, size_t* n_verts) {
     if (!v || !v->ctx || !verts || !n_verts) return BS_ERR_INVALID;

@@ -445,7 +445,9 @@ template <int A> __device__ __forceinline__ void raster_big(const ConvertParams&
 }
 // (Measured and rejected, r2: parking the set-up projections in shared memory and dealing their lattice columns out to the
 // lanes of the warp, as k_eval does -- 2.33 ms against 2.05 ms for this per-thread walk.)
-__global__ void __launch_bounds__(128, 3) k_block_edges(ConvertParams P, unsigned long long* blk, unsigned long long* big_list, unsigned* n_big, unsigned big_cap) {
+// 8 CTAs / SM (64 registers, 216 B of spills): the kernel waits on its loads -- the triangle, the brick hash -- and ran at 12 warps
+// per SM with the 106 registers the fp64 set-up would like (2.05 ms; 5 / 6 / 8 CTAs: 1.74 / 1.55 / 1.35 ms).
+__global__ void __launch_bounds__(128, 8) k_block_edges(ConvertParams P, unsigned long long* blk, unsigned long long* big_list, unsigned* n_big, unsigned big_cap) {
     // one thread per (axis, triangle); the axis is the SLOW index, so a warp runs one instantiation of the rasteriser
     const size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (g >= P.n_tris * 3) return;

@@ -13,6 +13,7 @@
 #include "bs_common.cuh"
 #include "mc33_tables.h"
 #include <cub/cub.cuh>
+#include <thrust/iterator/transform_iterator.h>
 #include <cfloat>
 #include <algorithm>
 
@@ -408,13 +409,11 @@ __global__ void __launch_bounds__(MC_TPB) k_mc(VolView V, const signed char* __r
     }
 }
 
-// ---- single-pass extraction (volumes without active tiles) ---------------------------------------------------------------
-// One WARP per brick, persistent warps drawing bricks from a ticket counter (so a brick's predecessors are always
-// running or done). The warp stages the 9^3 values, builds 9-bit active / sign rows per (x, y) from the mask bytes and
-// the staged values, classifies all 512 cells with a handful of bitwise operations per column, runs the MC33 logic on
-// the compacted candidates 32 at a time, and obtains its place in the output from a decoupled look-back over per-brick
-// descriptors (aggregate -> inclusive prefix) instead of a separate count pass + scan. The reference's stale c-vertex
-// (tiling 6.1.2) travels through a second, independent descriptor chain. No block-wide barriers anywhere.
+// ---- extraction of volumes without active tiles: one WARP per brick ----------------------------------------------------------
+// The warp stages the 9^3 values, builds 9-bit active / sign rows per (x, y) from the mask bytes and the staged values,
+// classifies all 512 cells with a handful of bitwise operations per column and runs the MC33 logic on the compacted candidates
+// 32 at a time. The reference's stale c-vertex (tiling 6.1.2) travels from brick to brick through a chain of per-brick
+// descriptors (decoupled look-back). No block-wide barriers anywhere.
 constexpr int MCF_WARPS = 4;
 constexpr unsigned FULL = 0xFFFFFFFFu;
 struct McDesc {
@@ -423,13 +422,6 @@ struct McDesc {
     unsigned* ticket;
     const float* init;          // c-vertex entering the volume (x, y, z, valid) when the volume continues an earlier slab (bs_voxel_remesh_into); else null
 };
-struct McWarp {
-    float val[732];
-    unsigned short rowA[82], rowS[82];  // per (x, y), x, y in 0..8: bit z = active / negative
-    unsigned short cells[512];          // candidate cells in cell order
-    unsigned info[512];                 // row | len << 14 | need_c << 21 | stale << 22 | triangles << 23
-};
-__device__ __forceinline__ unsigned long long ld_vol(const unsigned long long* p) { return *(const volatile unsigned long long*)p; }
 __device__ __forceinline__ float ld_volf(const float* p) { return *(const volatile float*)p; }
 
 // c-vertex entering brick `tile`: nearest earlier brick that computed one, else the reference's initial (0, 0, 0)
@@ -494,187 +486,14 @@ __device__ __forceinline__ void mcf_load_cell(Cell& q, const float* val, int ox,
     q.ox = ox + (int)x; q.oy = oy + (int)y; q.oz = oz + (int)z;
 }
 
-__global__ void __launch_bounds__(32 * MCF_WARPS, 8) k_mc_fused(VolView V, const signed char* __restrict__ tables, float vs, McDesc D, float* out, unsigned long long cap_tris) {
-    __shared__ McWarp S[MCF_WARPS];
-    const unsigned lane = threadIdx.x & 31;
-    McWarp& s = S[threadIdx.x >> 5];
-    for (;;) {
-        unsigned tk = 0;
-        if (lane == 0) tk = atomicAdd(D.ticket, 1u);
-        tk = __shfl_sync(FULL, tk, 0);
-        if (tk >= V.n) break;
-        const long long tile = tk;
-        const size_t b = tk;
-        const bool halo = V.owned && !V.owned[b];  // halo brick of a sharded volume: emits nothing, passes the c-vertex through
-        if (halo && tk + 1 < V.n) {               // (the last brick always completes its prefix: the host reads the total there)
-            if (lane == 0) {
-                *(volatile float*)(D.carry + 4 * tile + 3) = 1.f;
-                *(volatile unsigned long long*)(D.count + tile) = 1ull << 62;
-            }
-            continue;
-        }
-        int n_act = 0;
-        int ox = 0, oy = 0, oz = 0;
-        if (!halo) {
-        // ---- stage values and flag rows ----------------------------------------------------------------------------
-        int mynb = -1;
-        if (lane < 8) mynb = V.nbr[b * 8 + lane];
-        { int bx, by, bz; bs_key_brick(V.keys[b], bx, by, bz); ox = bx << 3; oy = by << 3; oz = bz << 3; }
-        {
-            const float4* g4 = reinterpret_cast<const float4*>(V.values + b * 512);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const unsigned q4 = lane + 32 * k, off = q4 * 4;
-                const float4 v = g4[q4];
-                float* d = s.val + (off >> 6) * 81 + ((off >> 3) & 7) * 9 + (off & 7);
-                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-            }
-        }
-#pragma unroll
-        for (int it = 0; it < 7; ++it) {  // the 217 halo entries: x = 8 plane (81), y = 8 plane without x = 8 (72), z = 8 plane without x, y = 8 (64)
-            const unsigned i = lane + 32 * it;
-            unsigned x = 8, y = 0, z = 0;
-            if (i < 81) { y = i / 9; z = i % 9; }
-            else if (i < 153) { x = (i - 81) / 9; y = 8; z = (i - 81) % 9; }
-            else { x = (i - 153) >> 3; y = (i - 153) & 7; z = 8; }
-            const int src = __shfl_sync(FULL, mynb, (x >> 3) | ((y >> 3) << 1) | ((z >> 3) << 2));
-            if (i < 217) s.val[x * 81 + y * 9 + z] = src >= 0 ? V.values[(size_t)src * 512 + (((x & 7) << 6) | ((y & 7) << 3) | (z & 7))] : 0.f;
-        }
-        const unsigned char* mbytes = reinterpret_cast<const unsigned char*>(V.masks);  // byte y of word x = the z-row (x, y)
-#pragma unroll
-        for (int it = 0; it < 3; ++it) {
-            const unsigned r = lane + 32 * it;
-            const unsigned x = r < 81 ? r / 9 : 0, y = r < 81 ? r % 9 : 0;
-            const unsigned nbi = (x >> 3) | ((y >> 3) << 1);
-            const int s0 = __shfl_sync(FULL, mynb, nbi), s1 = __shfl_sync(FULL, mynb, nbi | 4);
-            if (r < 81) {
-                const unsigned bo = (x & 7) * 8 + (y & 7);
-                unsigned a = s0 >= 0 ? mbytes[(size_t)s0 * 64 + bo] : 0u;
-                if (s1 >= 0) a |= (unsigned)(mbytes[(size_t)s1 * 64 + bo] & 1u) << 8;
-                s.rowA[r] = (unsigned short)a;
-            }
-        }
-        __syncwarp();
-#pragma unroll
-        for (int it = 0; it < 3; ++it) {
-            const unsigned r = lane + 32 * it;
-            if (r < 81) {
-                const float* p = s.val + (r / 9) * 81 + (r % 9) * 9;
-                unsigned m = 0;
-#pragma unroll
-                for (int z = 0; z < 9; ++z) m |= (__float_as_uint(p[z]) >> 31) << z;
-                s.rowS[r] = (unsigned short)m;
-            }
-        }
-        __syncwarp();
-        // ---- classify: a cell is a candidate if its 8 corners are active and their signs differ ----------------------
-        unsigned cross[2], cnt[2];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const unsigned c = lane + 32 * h, x = c >> 3, y = c & 7, r = x * 9 + y;
-            const unsigned a = s.rowA[r] & s.rowA[r + 1] & s.rowA[r + 9] & s.rowA[r + 10];
-            const unsigned sa = s.rowS[r] & s.rowS[r + 1] & s.rowS[r + 9] & s.rowS[r + 10];
-            const unsigned so = s.rowS[r] | s.rowS[r + 1] | s.rowS[r + 9] | s.rowS[r + 10];
-            cross[h] = (a & (a >> 1)) & (so | (so >> 1)) & ~(sa & (sa >> 1)) & 0xFFu;
-            cnt[h] = __popc(cross[h]);
-        }
-        unsigned inc0 = cnt[0], inc1 = cnt[1];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned t0 = __shfl_up_sync(FULL, inc0, o), t1 = __shfl_up_sync(FULL, inc1, o);
-            if ((int)lane >= o) { inc0 += t0; inc1 += t1; }
-        }
-        const unsigned tot0 = __shfl_sync(FULL, inc0, 31), tot1 = __shfl_sync(FULL, inc1, 31);
-        n_act = (int)(tot0 + tot1);
-        {
-            unsigned o0 = inc0 - cnt[0], o1 = tot0 + inc1 - cnt[1];
-            for (unsigned m = cross[0]; m; m &= m - 1) s.cells[o0++] = (unsigned short)((lane << 3) | (__ffs(m) - 1));
-            for (unsigned m = cross[1]; m; m &= m - 1) s.cells[o1++] = (unsigned short)(((lane + 32) << 3) | (__ffs(m) - 1));
-        }
-        __syncwarp();
-        }
-        // ---- count: tiling per candidate, triangles per candidate ----------------------------------------------------
-        McfCarry C{f3{0.f, 0.f, 0.f}, false, f3{0.f, 0.f, 0.f}, false};
-        unsigned long long total = 0;
-        for (int base = 0; base < n_act; base += 32) {
-            const int j = base + (int)lane;
-            Cell q; q.T = tables; q.v12 = f3{0.f, 0.f, 0.f};
-            int row = 0, len = 0; bool need_c = false, stale = false;
-            if (j < n_act) {
-                int id;
-                mcf_load_cell(q, s.val, ox, oy, oz, s.cells[j], id);
-                q.cs = tables[MC33_OFF_CASES + 2 * id]; q.cf = tables[MC33_OFF_CASES + 2 * id + 1];
-                row = select_tiling(q, len, need_c, stale);
-                if (need_c) compute_c_vertex(q);
-            }
-            mcf_resolve(q, need_c, stale, C, D, tile, lane);
-            int n = 0;
-            if (len) n = emit_rows<false>(q, vs, nullptr, row, len);
-            if (j < n_act) s.info[j] = (unsigned)row | ((unsigned)len << 14) | ((unsigned)need_c << 21) | ((unsigned)stale << 22) | ((unsigned)n << 23);
-            int sum = n;
-#pragma unroll
-            for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
-            total += (unsigned long long)sum;
-        }
-        // ---- publish, look back --------------------------------------------------------------------------------------
-        if (lane == 0) {
-            float* cd = D.carry + 4 * tile;
-            const bool val = C.have_run || C.incoming_known;
-            if (val) { const f3 v = C.have_run ? C.run : C.incoming; *(volatile float*)(cd) = v.x; *(volatile float*)(cd + 1) = v.y; *(volatile float*)(cd + 2) = v.z; __threadfence(); }
-            *(volatile float*)(cd + 3) = val ? 2.f : 1.f;
-            *(volatile unsigned long long*)(D.count + tile) = ((tile == 0 ? 2ull : 1ull) << 62) | total;
-        }
-        // Measured (ncu, config 5): warps spend about half their time in this look-back -- bricks retire in order, so every
-        // warp behind a brick with many candidate cells waits for it (a 256-wide window was slower: 4.5 vs 3.3 ms).
-        unsigned long long excl = 0;
-        if (tile > 0) {
-            for (long long basei = tile - 1;; basei -= 32) {
-                const long long idx = basei - lane;
-                unsigned long long d = 2ull << 62;  // before the first brick: inclusive prefix 0
-                if (idx >= 0) { while (((d = ld_vol(D.count + idx)) >> 62) == 0) __nanosleep(100); }  // back off: do not eat the issue slots of the warps being waited for
-                const unsigned pm = __ballot_sync(FULL, (d >> 62) == 2);
-                const int first = pm ? __ffs(pm) - 1 : 31;
-                unsigned long long v = ((int)lane <= first) ? (d & ((1ull << 62) - 1)) : 0ull;
-#pragma unroll
-                for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-                excl += v;
-                if (pm) break;
-            }
-            if (lane == 0) *(volatile unsigned long long*)(D.count + tile) = (2ull << 62) | (excl + total);
-        }
-        // ---- emit ----------------------------------------------------------------------------------------------------
-        if (total == 0 || excl + total > cap_tris) { __syncwarp(); continue; }
-        McfCarry C2{f3{0.f, 0.f, 0.f}, false, C.incoming, C.incoming_known};
-        unsigned long long running = excl;
-        for (int base = 0; base < n_act; base += 32) {
-            const int j = base + (int)lane;
-            Cell q; q.T = tables; q.v12 = f3{0.f, 0.f, 0.f};
-            int row = 0, len = 0, n = 0; bool need_c = false, stale = false;
-            if (j < n_act) {
-                const unsigned inf = s.info[j];
-                row = (int)(inf & 0x3FFFu); len = (int)((inf >> 14) & 0x7Fu); need_c = (inf >> 21) & 1u; stale = (inf >> 22) & 1u; n = (int)(inf >> 23);
-                int id;
-                mcf_load_cell(q, s.val, ox, oy, oz, s.cells[j], id);
-                if (need_c) compute_c_vertex(q);
-            }
-            mcf_resolve(q, need_c, stale, C2, D, tile, lane);
-            int inc = n;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, inc, o); if ((int)lane >= o) inc += t; }
-            if (n) emit_rows<true>(q, vs, out + (running + (unsigned long long)(inc - n)) * 9, row, len);
-            running += (unsigned long long)__shfl_sync(FULL, inc, 31);
-        }
-        __syncwarp();
-    }
-}
-
-// ---- two-kernel extraction: count (ticketed, carries the c-vertex chain) -> exclusive scan -> emit -------------------------------
-// The one-pass kernel above spends about half its time in the look-back (bricks retire in order) and runs the vertex
-// arithmetic twice per brick inside that wait structure. Split: k_mc_count does stage + classify + tiling + exact triangle
-// count per brick (no ordering between bricks except the rare c-vertex look-back), a device scan turns the counts into
-// offsets, and k_mc_emit -- embarrassingly parallel, bricks without output return before staging anything -- recomputes
-// the candidates, stages each round's triangles in shared memory and copies them out with coalesced stores (the one-pass
-// kernel stored 9 scattered floats per lane and triangle: 277 M four-byte transactions at config 5).
+// count (ticketed, carries the c-vertex chain) -> exclusive scan -> emit. k_mc_count does stage + classify + tiling + exact
+// triangle count per brick (no ordering between bricks except the rare c-vertex look-back), a device scan turns the counts
+// into offsets, and k_mc_emit -- embarrassingly parallel, bricks without output skipped before anything is staged --
+// recomputes the candidates, stages each round's triangles in shared memory and copies them out with coalesced stores, to
+// one destination or, on a sharded volume, straight into every rank's result buffer over NVLink (the output exchange of the
+// multi-GPU path rides on the emission instead of following it). Round 1's one-pass kernel (per-brick output offsets from a
+// decoupled look-back, 9 scattered floats stored per lane and triangle) took 3.3 ms at config 5: its warps waited in the
+// look-back about half the time (bricks retire in order); count 1.15 ms + emit 1.45 ms now.
 struct McStageS {
     float val[732];
     unsigned short rowA[82], rowS[82];  // per (x, y), x, y in 0..8: bit z = active / negative
@@ -810,18 +629,25 @@ __global__ void __launch_bounds__(32 * MCF_WARPS, 8) k_mc_count(VolView V, const
     }
 }
 
+struct McDst { float* p[16]; int world; };  // where the triangles go: one buffer, or the same place in every rank's buffer (peer memory)
 __global__ void __launch_bounds__(32 * MCF_WARPS, 6) k_mc_emit(VolView V, const signed char* __restrict__ tables, float vs, McDesc D, const unsigned* __restrict__ counts,
-                                                                const unsigned long long* __restrict__ offsets, float* out, unsigned long long cap_tris) {
+                                                                const unsigned long long* __restrict__ offsets, McDst O, unsigned long long cap_tris) {
     __shared__ McEmitS S[MCF_WARPS];
     const unsigned lane = threadIdx.x & 31;
-    const size_t b = (size_t)blockIdx.x * MCF_WARPS + (threadIdx.x >> 5);
-    if (b >= V.n) return;
-    const unsigned total = counts[b];
-    if (total == 0) return;  // (halo bricks, bricks without a sign change: nothing is staged)
-    unsigned long long running = offsets[b];
-    if (running + total > cap_tris) return;  // the host grows the buffer and runs the emit pass again
     McEmitS& se = S[threadIdx.x >> 5];
     McStageS& s = se.g;
+    // persistent warps draw bricks from a ticket counter (order does not matter here: every brick knows its offset), so a
+    // warp whose brick has no output -- a third of them at config 5 -- is not idle until its CTA retires
+    for (;;) {
+    unsigned tk = 0;
+    if (lane == 0) tk = atomicAdd(D.ticket + 2, 1u);
+    tk = __shfl_sync(FULL, tk, 0);
+    if (tk >= V.n) break;
+    const size_t b = tk;
+    const unsigned total = counts[b];
+    if (total == 0) continue;  // (halo bricks, bricks without a sign change: nothing is staged)
+    unsigned long long running = offsets[b];
+    if (running + total > cap_tris) continue;  // the host grows the buffer and runs the emit pass again
     int ox, oy, oz;
     const int n_act = mcs_stage_classify(V, b, s, lane, ox, oy, oz);
     const long long tile = (long long)b;
@@ -858,8 +684,11 @@ __global__ void __launch_bounds__(32 * MCF_WARPS, 6) k_mc_emit(VolView V, const 
             }
             if (fast) {  // the staged triangles are dense: coalesced copy to their final place
                 __syncwarp();
-                float* dst = out + running * 9;
-                for (int i = (int)lane; i < totm * 9; i += 32) dst[i] = se.tri[i];
+                const size_t at = (size_t)running * 9;
+                for (int i = (int)lane; i < totm * 9; i += 32) {
+                    const float v = se.tri[i];
+                    for (int d = 0; d < O.world; ++d) O.p[d][at + i] = v;
+                }
                 running += (unsigned long long)totm;
                 __syncwarp();
             } else {  // a degenerate triangle was dropped (or the half does not fit): exact counts, then direct stores
@@ -867,14 +696,16 @@ __global__ void __launch_bounds__(32 * MCF_WARPS, 6) k_mc_emit(VolView V, const 
                 int inc = n;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, inc, o); if ((int)lane >= o) inc += t; }
-                if (n) emit_rows<true>(q, vs, out + (running + (unsigned long long)(inc - n)) * 9, row, len);
+                if (n) for (int d = 0; d < O.world; ++d) emit_rows<true>(q, vs, O.p[d] + (running + (unsigned long long)(inc - n)) * 9, row, len);
                 running += (unsigned long long)__shfl_sync(FULL, inc, 31);
                 __syncwarp();
             }
         }
     }
+    __syncwarp();
+    }
 }
-struct WidenU32 { __device__ unsigned long long operator()(unsigned v) const { return v; } };
+struct WidenU32 { __host__ __device__ unsigned long long operator()(unsigned v) const { return v; } };
 
 __global__ void k_shift_carry(const CarryV12* __restrict__ incl, CarryV12* excl, size_t n) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -999,6 +830,68 @@ bs_status bs_ensure_out_verts(bs_context* ctx, size_t n_floats) {
     return BS_OK;
 }
 
+// ---- marching cubes in two steps (volumes without active tiles): the count leaves its per-brick products in the context, the emit
+// consumes them. bs_mc_impl runs both; the multi-GPU path runs them as two ABI calls with the ranks' count exchange in between.
+void bs_mc_pending_release(bs_context* ctx) {
+    bs_mc_pending& M = ctx->mc_pending;
+    bs_free(ctx, M.d_desc); bs_free(ctx, M.d_counts); bs_free(ctx, M.d_offsets); bs_free(ctx, M.d_nbr);
+    M = bs_mc_pending();
+}
+bs_status bs_mc_count_phase(const bs_volume* v, float voxel_size, size_t* n_verts) {
+    bs_context* ctx = v->ctx;
+    cudaStream_t st = ctx->stream;
+    bs_mc_pending& M = ctx->mc_pending;
+    const size_t n = v->n_bricks;
+    *n_verts = 0;
+    M.vol = v; M.voxel_size = voxel_size; M.n = n; M.n_tris = 0;
+    if (n == 0) return BS_OK;
+    BS_TRY(bs_alloc(ctx, &M.d_nbr, n * 8));
+    bs_count_launch(), k_mc_neighbours<<<bs_blocks(n * 8, 256), 256, 0, st>>>(v->keys, n, M.d_nbr);
+    VolView V{v->keys, v->values, v->masks, n, v->owned, M.d_nbr, nullptr, nullptr, 0, nullptr, nullptr, 0};
+    BS_TRY(bs_alloc(ctx, &M.d_desc, 2 * n + 2)); BS_TRY(bs_alloc(ctx, &M.d_counts, n + 1)); BS_TRY(bs_alloc(ctx, &M.d_offsets, n + 1));
+    McDesc D{nullptr, reinterpret_cast<float*>(M.d_desc), reinterpret_cast<unsigned*>(M.d_desc + 2 * n), ctx->mc_chain ? ctx->d_mc_carry : nullptr};
+    static bool carve = false;
+    if (!carve) {
+        cudaFuncSetAttribute(k_mc_count, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_mc_emit, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        carve = true;
+    }
+    BS_CUDA(ctx, cudaMemsetAsync(M.d_desc, 0, (2 * n + 2) * sizeof(unsigned long long), st));  // carry records, count ticket, last-carry slot, emit ticket
+    BS_CUDA(ctx, cudaMemsetAsync(M.d_counts + n, 0, sizeof(unsigned), st));
+    const unsigned grid0 = (unsigned)std::min<size_t>((n + MCF_WARPS - 1) / MCF_WARPS, (size_t)ctx->sm_count * 8);
+    bs_count_launch(), k_mc_count<<<grid0, 32 * MCF_WARPS, 0, st>>>(V, (const signed char*)ctx->d_mc33, voxel_size, D, M.d_counts);
+    void* d_tmp = nullptr; size_t tmp_bytes = 0;
+    auto wide = thrust::make_transform_iterator((const unsigned*)M.d_counts, WidenU32());
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, wide, M.d_offsets, (int)(n + 1), st);
+    BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp_bytes));
+    cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, wide, M.d_offsets, (int)(n + 1), st);
+    bs_free(ctx, d_tmp);
+    if (ctx->mc_chain) { bs_count_launch(), k_mc_last_carry<<<bs_blocks(n, 256), 256, 0, st>>>(D, (long long)n); bs_count_launch(), k_mc_final_carry<<<1, 1, 0, st>>>(D, ctx->d_mc_carry); }
+    bs_mark(ctx, "mc_count_ms");
+    BS_TRY(bs_fetch(ctx, &M.n_tris, M.d_offsets + n, sizeof(M.n_tris)));
+    BS_TRY(bs_sync(ctx));
+    *n_verts = (size_t)M.n_tris * 3;
+    return BS_OK;
+}
+bs_status bs_mc_emit_phase(const bs_volume* v, float* const* dst, int world, size_t offset_floats, size_t cap_floats) {
+    bs_context* ctx = v->ctx;
+    cudaStream_t st = ctx->stream;
+    bs_mc_pending& M = ctx->mc_pending;
+    if (M.vol != v) return bs_fail(ctx, BS_ERR_INVALID, "marching cubes emit without a count on this volume");
+    const size_t n = M.n;
+    if (n && M.n_tris) {
+        if (offset_floats + (size_t)M.n_tris * 9 > cap_floats) return bs_fail(ctx, BS_ERR_INVALID, "marching cubes: destination too small");
+        VolView V{v->keys, v->values, v->masks, n, v->owned, M.d_nbr, nullptr, nullptr, 0, nullptr, nullptr, 0};
+        McDesc D{nullptr, reinterpret_cast<float*>(M.d_desc), reinterpret_cast<unsigned*>(M.d_desc + 2 * n), ctx->mc_chain ? ctx->d_mc_carry : nullptr};
+        McDst O; O.world = world;
+        for (int d = 0; d < 16; ++d) O.p[d] = d < world ? dst[d] + offset_floats : nullptr;
+        const unsigned grid = (unsigned)std::min<size_t>((n + MCF_WARPS - 1) / MCF_WARPS, (size_t)ctx->sm_count * 6);
+        bs_count_launch(), k_mc_emit<<<grid, 32 * MCF_WARPS, 0, st>>>(V, (const signed char*)ctx->d_mc33, M.voxel_size, D, M.d_counts, M.d_offsets, O, ~0ull);
+    }
+    bs_mark(ctx, "mc_emit_ms");
+    return BS_OK;
+}
+
 bs_status bs_mc_impl(const bs_volume* v, float voxel_size, const float** d_verts, size_t* n_verts) {
     bs_context* ctx = v->ctx;
     cudaStream_t st = ctx->stream;
@@ -1006,88 +899,30 @@ bs_status bs_mc_impl(const bs_volume* v, float voxel_size, const float** d_verts
     bs_marks_begin(ctx);
     const size_t n = v->n_bricks, nt8 = v->n_tiles8, nt128 = v->n_tiles128, n_items = n + nt8 + nt128;
     if (n_items == 0) { bs_marks_end(ctx); return BS_OK; }
+    if (!(nt8 || nt128)) {
+        // count (ticketed) -> scan -> emit into the context's result buffer (grown to the exact size when it is too small)
+        bs_mc_pending_release(ctx);
+        size_t nv = 0;
+        BS_TRY(bs_mc_count_phase(v, voxel_size, &nv));
+        const unsigned long long n_tris = nv / 3;
+        bs_status s = BS_OK;
+        if (ctx->out_verts_cap == 0) s = bs_ensure_out_verts(ctx, n * 160 * 9);
+        if (s == BS_OK && (size_t)n_tris * 9 > ctx->out_verts_cap) s = bs_ensure_out_verts(ctx, (size_t)n_tris * 9);
+        if (s == BS_OK) { float* one[1] = {ctx->d_out_verts}; s = bs_mc_emit_phase(v, one, 1, 0, ctx->out_verts_cap); }
+        bs_mc_pending_release(ctx);
+        if (s != BS_OK) return s;
+        BS_CUDA(ctx, cudaGetLastError());
+        bs_marks_end(ctx);
+        bs_stat_add(ctx, "n_bricks", (double)n);
+        bs_stat_add(ctx, "n_out_tris", (double)n_tris);
+        *d_verts = ctx->d_out_verts; *n_verts = (size_t)n_tris * 3;
+        return BS_OK;
+    }
     int* d_nbr = nullptr;
     BS_TRY(bs_alloc(ctx, &d_nbr, n * 8));
     if (n) bs_count_launch(), k_mc_neighbours<<<bs_blocks(n * 8, 256), 256, 0, st>>>(v->keys, n, d_nbr);
     VolView V{v->keys, v->values, v->masks, n, v->owned, d_nbr, v->tile8_keys, v->tile8_values, nt8, v->tile128_keys, v->tile128_values, nt128};
     const signed char* tables = (const signed char*)ctx->d_mc33;
-    static const bool use_fused = getenv("BSHARK_MC_FUSED") != nullptr;  // A/B switch: the one-pass look-back kernel
-    if (!(nt8 || nt128) && !use_fused) {
-        // count (ticketed) -> scan -> emit; the output buffer is sized from the previous extraction (or a guess) and only the
-        // emit pass is repeated, with the exact size, if that turns out too small
-        unsigned long long* d_desc = nullptr;  // [2n] carry records (4 floats each), 1 ticket word
-        unsigned* d_counts = nullptr; unsigned long long* d_offsets = nullptr;
-        BS_TRY(bs_alloc(ctx, &d_desc, 2 * n + 1)); BS_TRY(bs_alloc(ctx, &d_counts, n + 1)); BS_TRY(bs_alloc(ctx, &d_offsets, n + 1));
-        McDesc D{nullptr, reinterpret_cast<float*>(d_desc), reinterpret_cast<unsigned*>(d_desc + 2 * n), ctx->mc_chain ? ctx->d_mc_carry : nullptr};
-        static bool carve = false;
-        if (!carve) {
-            cudaFuncSetAttribute(k_mc_count, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            cudaFuncSetAttribute(k_mc_emit, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            carve = true;
-        }
-        BS_CUDA(ctx, cudaMemsetAsync(d_desc, 0, (2 * n + 1) * sizeof(unsigned long long), st));
-        BS_CUDA(ctx, cudaMemsetAsync(d_counts + n, 0, sizeof(unsigned), st));
-        const unsigned grid0 = (unsigned)std::min<size_t>((n + MCF_WARPS - 1) / MCF_WARPS, (size_t)ctx->sm_count * 8);
-        bs_count_launch(), k_mc_count<<<grid0, 32 * MCF_WARPS, 0, st>>>(V, tables, voxel_size, D, d_counts);
-        bs_mark(ctx, "mc_count_ms");
-        void* d_tmp = nullptr; size_t tmp_bytes = 0;
-        cub::TransformInputIterator<unsigned long long, WidenU32, const unsigned*> wide(d_counts, WidenU32());
-        cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, wide, d_offsets, (int)(n + 1), st);
-        BS_TRY(bs_alloc(ctx, (char**)&d_tmp, tmp_bytes));
-        cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, wide, d_offsets, (int)(n + 1), st);
-        unsigned long long n_tris = 0;
-        BS_TRY(bs_fetch(ctx, &n_tris, d_offsets + n, sizeof(n_tris)));
-        bs_status s = BS_OK;
-        if (ctx->out_verts_cap == 0) s = bs_ensure_out_verts(ctx, n * 160 * 9);
-        for (int attempt = 0; s == BS_OK && attempt < 2; ++attempt) {
-            bs_count_launch(), k_mc_emit<<<(unsigned)((n + MCF_WARPS - 1) / MCF_WARPS), 32 * MCF_WARPS, 0, st>>>(V, tables, voxel_size, D, d_counts, d_offsets, ctx->d_out_verts, (unsigned long long)(ctx->out_verts_cap / 9));
-            if (attempt == 0) BS_TRY(bs_sync(ctx));
-            if ((size_t)n_tris * 9 <= ctx->out_verts_cap) break;
-            s = bs_ensure_out_verts(ctx, (size_t)n_tris * 9);  // too small: grow to the exact size and emit again
-        }
-        if (s == BS_OK && ctx->mc_chain) { bs_count_launch(), k_mc_last_carry<<<bs_blocks(n, 256), 256, 0, st>>>(D, (long long)n); bs_count_launch(), k_mc_final_carry<<<1, 1, 0, st>>>(D, ctx->d_mc_carry); }
-        bs_mark(ctx, "mc_emit_ms");
-        bs_free(ctx, d_tmp); bs_free(ctx, d_desc); bs_free(ctx, d_counts); bs_free(ctx, d_offsets); bs_free(ctx, d_nbr);
-        if (s != BS_OK) return s;
-        BS_CUDA(ctx, cudaGetLastError());
-        bs_marks_end(ctx);
-        bs_stat_add(ctx, "n_bricks", (double)n);
-        bs_stat_add(ctx, "n_out_tris", (double)n_tris);
-        *d_verts = ctx->d_out_verts; *n_verts = (size_t)n_tris * 3;
-        return BS_OK;
-    }
-    if (!(nt8 || nt128)) {
-        // single pass: per-brick descriptors + ticket; the output buffer is sized from the previous extraction (or a
-        // guess) and the pass is repeated once with the exact size if it turns out too small
-        unsigned long long* d_desc = nullptr;  // [n] count descriptors, [2n] carry records (4 floats each), 1 ticket word
-        BS_TRY(bs_alloc(ctx, &d_desc, 3 * n + 1));
-        McDesc D{d_desc, reinterpret_cast<float*>(d_desc + n), reinterpret_cast<unsigned*>(d_desc + 3 * n), ctx->mc_chain ? ctx->d_mc_carry : nullptr};
-        static bool carve = false;
-        if (!carve) { cudaFuncSetAttribute(k_mc_fused, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); carve = true; }
-        const unsigned grid = (unsigned)std::min<size_t>((n + MCF_WARPS - 1) / MCF_WARPS, (size_t)ctx->sm_count * 8);
-        unsigned long long n_tris = 0;
-        bs_status s = BS_OK;
-        if (ctx->out_verts_cap == 0) s = bs_ensure_out_verts(ctx, n * 160 * 9);
-        for (int attempt = 0; s == BS_OK && attempt < 2; ++attempt) {
-            BS_CUDA(ctx, cudaMemsetAsync(d_desc, 0, (3 * n + 1) * sizeof(unsigned long long), st));
-            bs_count_launch(), k_mc_fused<<<grid, 32 * MCF_WARPS, 0, st>>>(V, tables, voxel_size, D, ctx->d_out_verts, (unsigned long long)(ctx->out_verts_cap / 9));
-            BS_TRY(bs_fetch(ctx, &n_tris, d_desc + (n - 1), sizeof(n_tris)));
-            BS_TRY(bs_sync(ctx));
-            n_tris &= (1ull << 62) - 1;
-            if ((size_t)n_tris * 9 <= ctx->out_verts_cap) break;
-            s = bs_ensure_out_verts(ctx, (size_t)n_tris * 9);  // too small: grow to the exact size and run again
-        }
-        if (s == BS_OK && ctx->mc_chain) { bs_count_launch(), k_mc_last_carry<<<bs_blocks(n, 256), 256, 0, st>>>(D, (long long)n); bs_count_launch(), k_mc_final_carry<<<1, 1, 0, st>>>(D, ctx->d_mc_carry); }
-        bs_mark(ctx, "mc_emit_ms");
-        bs_free(ctx, d_desc); bs_free(ctx, d_nbr);
-        if (s != BS_OK) return s;
-        BS_CUDA(ctx, cudaGetLastError());
-        bs_marks_end(ctx);
-        bs_stat_add(ctx, "n_bricks", (double)n);
-        bs_stat_add(ctx, "n_out_tris", (double)n_tris);
-        *d_verts = ctx->d_out_verts; *n_verts = (size_t)n_tris * 3;
-        return BS_OK;
-    }
     // volumes with active tiles (CSG unions): count pass, scan over bricks and tiles in merged order, emit pass
     unsigned *d_counts = nullptr, *d_pos = nullptr; unsigned long long *d_wide = nullptr, *d_off = nullptr;
     BS_TRY(bs_alloc(ctx, &d_counts, n_items)); BS_TRY(bs_alloc(ctx, &d_wide, n_items + 1)); BS_TRY(bs_alloc(ctx, &d_off, n_items + 1));

@@ -45,9 +45,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sign-propagation", action="store_true",
                     help="A/B switch: per-voxel winding numbers even on closed meshes (BS_FLAG_SIGN_PROPAGATION = 0); recorded in config")
-    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
-                    help="N > 1 output exchange: p2p = every rank stores its slice into all peers' buffers over NVLink (bs_context_push_out_verts, "
-                         "CUDA IPC mapped peer memory); nccl = torch.distributed all-gather (the baseline)")
+    ap.add_argument("--gather", default="fused", choices=["fused", "p2p", "nccl"],
+                    help="N > 1 output exchange: fused = the marching-cubes emit kernel stores every triangle into all ranks' buffers over NVLink "
+                         "(bs_mesh_mc_count + bs_mesh_mc_emit_push, CUDA IPC mapped peer memory: the exchange rides on the emission); p2p = extraction, "
+                         "then one kernel copies the rank's slice into all peers' buffers (bs_context_push_out_verts); nccl = torch.distributed all-gather (the baseline)")
     ap.add_argument("--remesh-slabs", type=int, default=0, help="N = 1 e2e leg: slabs of the pipelined remesh call (0 = the library's choice)")
     ap.add_argument("--e2e-two-calls", action="store_true", help="N = 1 e2e leg through bs_mesh_to_volume + bs_mesh_mc_device + bs_context_copy_out_verts (no overlap) instead of bs_voxel_remesh_into")
     ap.add_argument("--io", action="store_true", help="time the rows either side of the path on the --config mesh: STL decode / encode, merge_points, ActiveVoxelsMesher")
@@ -449,13 +450,37 @@ def main():
     phase_ev = []  # (convert done, MC done, gather done) events of every timed step, on the library's stream
 
     def step_device(record=False):
-        """convert + MC (+ all-gather when sharded), input and output resident in HBM; returns local vertex count."""
+        """convert + MC (+ output exchange when sharded), input and output resident in HBM; returns local vertex count."""
         h = C.c_void_p()
         ctx.check(L.bs_mesh_to_volume_sharded(ctx._h, C.c_void_p(d_tris.data_ptr()), n_tris, vs, 0, rank, world, C.byref(h)))
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if record else None
         if record:
             ev[0].record(stream)
         dv, nv = C.c_void_p(), C.c_size_t()
+        if world > 1 and args.gather == "fused":
+            # count -> (counts of a steady workload: those of the previous step) -> emit straight into every rank's buffer
+            st = L.bs_mesh_mc_count(h, vs, C.byref(nv))
+            if st == 0:
+                n_floats = nv.value * 3
+                counts = gather_buf["counts"]
+                if counts is None or counts[rank] != n_floats:
+                    counts = exchange_counts(n_floats)
+                    gather_buf["counts"] = counts
+                total = sum(counts)
+                if peer["cap"] < total:
+                    peer_buffers(total)
+                if record:
+                    ev[1].record(stream)
+                st = L.bs_mesh_mc_emit_push(h, peer["arr"], world, sum(counts[:rank]), peer["cap"])
+                with torch.cuda.stream(stream):
+                    dist.all_reduce(peer["fence"])
+                gather_buf["out"] = torch.as_tensor(_DeviceF32(peer["own"], total), device="cuda")
+            L.bs_volume_free(h)
+            ctx.check(st)
+            if record:
+                ev[2].record(stream)
+                phase_ev.append(ev)
+            return None, nv.value, None
         st = L.bs_mesh_mc_device(h, vs, C.byref(dv), C.byref(nv))
         L.bs_volume_free(h)
         ctx.check(st)
@@ -591,8 +616,8 @@ def main():
     step_ms = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
     starts = [e0] + marks[:-1]
     phase_ms = {"convert_call": sum(a.elapsed_time(ev[0]) for a, ev in zip(starts, phase_ev)) / args.steps,
-                "mc_call": sum(ev[0].elapsed_time(ev[1]) for ev in phase_ev) / args.steps,
-                "all_gather": sum(ev[1].elapsed_time(ev[2]) for ev in phase_ev) / args.steps}
+                ("mc_count_call" if (world > 1 and args.gather == "fused") else "mc_call"): sum(ev[0].elapsed_time(ev[1]) for ev in phase_ev) / args.steps,
+                ("mc_emit_into_all_ranks" if (world > 1 and args.gather == "fused") else "all_gather"): sum(ev[1].elapsed_time(ev[2]) for ev in phase_ev) / args.steps}
 
     # per-stage device times of convert (CUDA events on the library's stream), averaged over a few extra passes
     conv_ms = {}

@@ -108,6 +108,14 @@ bs_status bs_mesh_mc(const bs_volume* v, float voxel_size, float** verts, size_t
  * nondeterministic (rayon + Mutex); this returns leaves in visit order. BS_ERR_REFERENCE_PANICS where the
  * reference hits todo!() (active tiles) or unreachable!() (:340). */
 bs_status bs_mesh_dc(const bs_volume* v, float voxel_size, float** verts, size_t* n_verts);
+/* MarchingCubesMesher::mesh (marching_cubes.rs:43-63) in two steps, for the multi-GPU output exchange: the count returns the
+ * number of vertices this volume (this rank's slab of a sharded volume) will emit; once the ranks have exchanged their counts,
+ * the emit writes the triangles at float offset `offset_floats` of EVERY buffer in dst[0..world) -- the ranks' result buffers,
+ * mapped with bs_ipc_open -- so the exchange over NVLink rides on the emission, tile by tile, instead of following it (every
+ * buffer must hold cap_floats floats). The emit is asynchronous on the context's stream with respect to the peers: the caller
+ * fences (bench.py: a one-element all-reduce on the same stream). Volumes with active tiles: BS_ERR_UNSUPPORTED. */
+bs_status bs_mesh_mc_count(const bs_volume* v, float voxel_size, size_t* n_verts);
+bs_status bs_mesh_mc_emit_push(const bs_volume* v, float* const* dst, int world, size_t offset_floats, size_t cap_floats);
 /* VoxelRemesher::remesh (src/remeshing/voxel.rs:64-84): MeshToVolume::convert with band width 0, then
  * MarchingCubesMesher (method 0 = MeshingMethod::Manifold, the default) or DualContouringMesher (method 1 =
  * FeaturePreserving), in ONE call from host triangles (9 floats each) to the vertex soup in caller-owned host memory
