@@ -487,6 +487,8 @@ bs_status bs_mesh_to_volume_sharded(bs_context* ctx, const float* d_tris, size_t
     BS_ENTER(ctx);  // before any bs_fail: a failure belongs to THIS call's epoch
     if (!(voxel_size > 0.0f) || band < 0 || band > 64) return bs_fail(ctx, BS_ERR_INVALID, "voxel_size must be > 0 and 0 <= band_width <= 64");
     if (n_tris == 0) return BS_ERR_EMPTY_MESH;
+    if (!d_tris) return bs_fail(ctx, BS_ERR_INVALID, "null triangle pointer");
+    if (!(voxel_size < 1.0e30f)) return bs_fail(ctx, BS_ERR_RANGE, "voxel_size must be below 1e30");  // (edge vectors of in-range triangles stay finite)
     return bs_convert_impl(ctx, d_tris, n_tris, voxel_size, band, rank, world, out);
 }
 bs_status bs_mesh_to_volume_device(bs_context* ctx, const float* d_tris, size_t n_tris, float voxel_size, int64_t band, bs_volume** out) {
@@ -592,7 +594,7 @@ bs_status bs_voxel_remesh_into(bs_context* ctx, const float* tris, size_t n_tris
     if (n_tris == 0) return BS_ERR_EMPTY_MESH;
     if (!tris || (method != 0 && method != 1)) return BS_ERR_INVALID;
     BS_ENTER(ctx);
-    if (!(voxel_size > 0.0f)) return bs_fail(ctx, BS_ERR_INVALID, "voxel_size must be > 0");
+    if (!(voxel_size > 0.0f) || !(voxel_size < 1.0e30f)) return bs_fail(ctx, BS_ERR_INVALID, "voxel_size must be in (0, 1e30)");
     int K = slabs;
     if (K <= 0) { if (const char* e = getenv("BSHARK_REMESH_SLABS")) K = atoi(e); }
     if (K <= 0) K = n_tris >= (1u << 20) ? 4 : 1;  // below ~1 M triangles the per-slab overhead outweighs the hidden copy

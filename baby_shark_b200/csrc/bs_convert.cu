@@ -153,7 +153,7 @@ __global__ void k_cta_starts(ConvertParams P, unsigned n_ctas, unsigned* start) 
     if (b < n_ctas) start[b] = (unsigned)find_tri(P, (unsigned long long)b * TPB);
 }
 
-__device__ __forceinline__ void hash_insert(const ConvertParams& P, unsigned long long key) {
+__device__ __forceinline__ void hash_insert(const ConvertParams& P, unsigned long long key, unsigned count) {
     unsigned h = (unsigned)hash64(key) & P.table_mask;
     for (int probe = 0; probe < MAX_PROBE; ++probe) {
         unsigned long long cur = P.table_keys[h];
@@ -162,7 +162,7 @@ __device__ __forceinline__ void hash_insert(const ConvertParams& P, unsigned lon
             unsigned long long prev = atomicCAS(&P.table_keys[h], BS_KEY_INVALID, key);
             mine = prev == BS_KEY_INVALID || prev == key;
         }
-        if (mine) { if (P.table_counts) atomicAdd(&P.table_counts[h], 1u); return; }
+        if (mine) { if (P.table_counts) atomicAdd(&P.table_counts[h], count); return; }
         h = (h + 1) & P.table_mask;
     }
     P.flags[0] = 1;
@@ -193,10 +193,27 @@ __global__ void __launch_bounds__(TPB) k_mark(ConvertParams P) {
     }
     for (int o = 16; o; o >>= 1) vol += __shfl_xor_sync(0xFFFFFFFFu, vol, o);
     if ((threadIdx.x & 31) == 0 && vol) atomicAdd(P.n_eval, vol);
-    if (!c.valid || mx[0] < mn[0]) return;
-    for (int bx = mn[0] >> 3; bx <= (mx[0] >> 3); ++bx)
-        for (int by = mn[1] >> 3; by <= (mx[1] >> 3); ++by)
-            for (int bz = mn[2] >> 3; bz <= (mx[2] >> 3); ++bz) hash_insert(P, bs_brick_key(bx, by, bz));
+    const bool has = c.valid && mx[0] >= mn[0];
+    const bool wide = has && ((mx[0] >> 3) - (mn[0] >> 3) > 1 || (mx[1] >> 3) - (mn[1] >> 3) > 1 || (mx[2] >> 3) - (mn[2] >> 3) > 1);
+    if (__any_sync(0xFFFFFFFFu, wide)) {  // large narrow bands: a box spans more than 2 bricks along an axis
+        if (!has) return;
+        for (int bx = mn[0] >> 3; bx <= (mx[0] >> 3); ++bx)
+            for (int by = mn[1] >> 3; by <= (mx[1] >> 3); ++by)
+                for (int bz = mn[2] >> 3; bz <= (mx[2] >> 3); ++bz) hash_insert(P, bs_brick_key(bx, by, bz), 1u);
+        return;
+    }
+    // <= 2 x 2 x 2 bricks per box. The 32 sub-triangles of a warp are neighbours on the surface and mostly touch the same few bricks:
+    // lanes holding the same key elect one of them, which inserts the key once and adds the whole group to the brick's touch count
+    const int bx0 = mn[0] >> 3, by0 = mn[1] >> 3, bz0 = mn[2] >> 3;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int bx = bx0 + (k & 1), by = by0 + ((k >> 1) & 1), bz = bz0 + (k >> 2);
+        const bool touched = has && bx <= (mx[0] >> 3) && by <= (mx[1] >> 3) && bz <= (mx[2] >> 3);
+        if (!__any_sync(0xFFFFFFFFu, touched)) continue;
+        const unsigned long long key = touched ? bs_brick_key(bx, by, bz) : BS_KEY_INVALID;
+        const unsigned peers = __match_any_sync(0xFFFFFFFFu, key);
+        if (touched && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) hash_insert(P, key, (unsigned)__popc(peers));
+    }
 }
 
 // Distances. Each lane derives one sub-triangle (vertices, box, the <= 2x2x2 brick slots its box touches) and parks it in

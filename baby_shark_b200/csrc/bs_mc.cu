@@ -685,9 +685,10 @@ __global__ void __launch_bounds__(32 * MCF_WARPS, 6) k_mc_emit(VolView V, const 
             if (fast) {  // the staged triangles are dense: coalesced copy to their final place
                 __syncwarp();
                 const size_t at = (size_t)running * 9;
-                for (int i = (int)lane; i < totm * 9; i += 32) {
-                    const float v = se.tri[i];
-                    for (int d = 0; d < O.world; ++d) O.p[d][at + i] = v;
+#pragma unroll 1
+                for (int d = 0; d < O.world; ++d) {  // (not unrolled: 16 copies of this loop and of emit_rows below thrashed the instruction cache)
+                    float* dst = O.p[d] + at;
+                    for (int i = (int)lane; i < totm * 9; i += 32) dst[i] = se.tri[i];
                 }
                 running += (unsigned long long)totm;
                 __syncwarp();
@@ -696,7 +697,8 @@ __global__ void __launch_bounds__(32 * MCF_WARPS, 6) k_mc_emit(VolView V, const 
                 int inc = n;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, inc, o); if ((int)lane >= o) inc += t; }
-                if (n) for (int d = 0; d < O.world; ++d) emit_rows<true>(q, vs, O.p[d] + (running + (unsigned long long)(inc - n)) * 9, row, len);
+#pragma unroll 1
+                for (int d = 0; d < O.world; ++d) if (n) emit_rows<true>(q, vs, O.p[d] + (running + (unsigned long long)(inc - n)) * 9, row, len);
                 running += (unsigned long long)__shfl_sync(FULL, inc, 31);
                 __syncwarp();
             }

@@ -34,7 +34,7 @@ UNIT = "voxels/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--config", type=int, default=5)
     ap.add_argument("--scale", type=float, default=1.0, help="resolution scale of the config (1.0 = BASELINE.json size)")
@@ -248,7 +248,7 @@ class ClockSampler(threading.Thread):
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 if self.stop_flag:
@@ -448,6 +448,7 @@ def main():
         return full
 
     phase_ev = []  # (convert done, MC done, gather done) events of every timed step, on the library's stream
+    mc_extra = {}  # fused exchange: stage times of the count call (the emit call's stats replace them)
 
     def step_device(record=False):
         """convert + MC (+ output exchange when sharded), input and output resident in HBM; returns local vertex count."""
@@ -461,6 +462,8 @@ def main():
             # count -> (counts of a steady workload: those of the previous step) -> emit straight into every rank's buffer
             st = L.bs_mesh_mc_count(h, vs, C.byref(nv))
             if st == 0:
+                if record:
+                    mc_extra["mc_count_ms"] = mc_extra.get("mc_count_ms", 0.0) + ctx.last_stats().get("mc_count_ms", 0.0)
                 n_floats = nv.value * 3
                 counts = gather_buf["counts"]
                 if counts is None or counts[rank] != n_floats:
@@ -630,6 +633,7 @@ def main():
                 conv_ms[k] = conv_ms.get(k, 0.0) + v / reps
         L.bs_volume_free(h)
     mc_ms = {k: v / args.steps for k, v in stage_ms.items()}
+    mc_ms.update({k: v / args.steps for k, v in mc_extra.items()})
 
     # ---- e2e leg ---------------------------------------------------------------------------------------------------
     e2e_step = step_e2e_remesh if (world == 1 and not args.e2e_two_calls) else step_e2e
@@ -761,9 +765,12 @@ def main():
                        "algorithmic": "72 B x n_tris (two passes over the triangles) + 1248 B x n_bricks (edge masks, component tables) + 8 B x n_active (sign write-back); %d representatives evaluated" % int(work.get("n_sign_seeds", 0))})
         if "mc_emit_ms" in mc_ms:
             nb = work.get("n_bricks", 0.0)
-            by = nb * (2112 + 868) + 36.0 * (n_verts_local / 3.0)
-            rl.append({"kernel": "k_mc_fused (stage + classify + MC33 + look-back + emit, one pass)", "bound": "hbm", "achieved": by / (mc_ms["mc_emit_ms"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                       "ms": mc_ms["mc_emit_ms"], "algorithmic": "n_bricks x 2980 B + 36 B x n_out_tris", "traffic": None, "peak_source": hbm_src})
+            if "mc_count_ms" in mc_ms:
+                rl.append({"kernel": "k_mc_count (stage + classify + MC33 tiling + exact triangle count per brick)", "bound": "hbm", "achieved": nb * (2112 + 868) / (mc_ms["mc_count_ms"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                           "ms": mc_ms["mc_count_ms"], "algorithmic": "n_bricks x 2980 B (values + masks + halo gathers)", "traffic": None, "peak_source": hbm_src})
+            by = nb * (2112 + 868) + 36.0 * (n_verts_local / 3.0) * (world if (world > 1 and args.gather == "fused") else 1)
+            rl.append({"kernel": "k_mc_emit (stage + classify + MC33 + vertices, staged coalesced stores%s)" % (" into every rank's buffer" if (world > 1 and args.gather == "fused") else ""), "bound": "hbm", "achieved": by / (mc_ms["mc_emit_ms"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                       "ms": mc_ms["mc_emit_ms"], "algorithmic": "n_bricks x 2980 B + 36 B x n_out_tris" + (" x world" if (world > 1 and args.gather == "fused") else ""), "traffic": None, "peak_source": hbm_src})
         # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum): read from the committed ncu capture of this exact
         # workload (profiles/r2_ncu_traffic_cfg5.json, written by tools/ncu_traffic.py from an `ncu --set full` report)
         if args.config == 5 and args.scale == 1.0 and world == 1:

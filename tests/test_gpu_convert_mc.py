@@ -263,3 +263,44 @@ def test_pipelined_remesh_equals_convert_then_mesh(bs, slabs):
     mc = bs.MarchingCubesMesher().with_voxel_size(vs).mesh(vol)
     assert np.array_equal(got.view(np.uint32), mc.view(np.uint32))
     assert bs.VoxelRemesher().with_voxel_size(vs).remesh(np.zeros((0, 9), np.float32)) is None
+
+
+def test_two_step_marching_cubes_emits_into_every_destination(bs):
+    # bs_mesh_mc_count + bs_mesh_mc_emit_push (the multi-GPU output exchange: the emit kernel stores every triangle into all
+    # ranks' buffers): here both destinations live on this GPU; each must hold the one-call result at the given offset
+    import ctypes as C
+    L, ctx = bs.load_library(), bs.Context.default()
+    tris, vs, _ = synth.config_mesh(5, 0.06)
+    vol = bs.MeshToVolume().with_voxel_size(vs).convert(tris)
+    ref = bs.MarchingCubesMesher().with_voxel_size(vs).mesh(vol).reshape(-1)
+    nv = C.c_size_t()
+    ctx.check(L.bs_mesh_mc_count(vol._h, vs, C.byref(nv)))
+    assert nv.value * 3 == ref.size
+    off, cap = 100, ref.size + 164
+    ptrs = []
+    for _ in range(2):
+        p, handle = C.c_void_p(), C.create_string_buffer(64)
+        ctx.check(L.bs_ipc_alloc(ctx._h, cap * 4, C.byref(p), handle))
+        ptrs.append(p.value)
+    arr = (C.c_void_p * 2)(*ptrs)
+    try:
+        ctx.check(L.bs_mesh_mc_emit_push(vol._h, arr, 2, off, cap))
+        for p in ptrs:
+            out = np.empty(ref.size, np.float32)
+            ctx.check(L.bs_copy_to_host(ctx._h, C.c_void_p(p + 4 * off), C.c_void_p(out.ctypes.data), out.nbytes))
+            assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))
+        assert L.bs_mesh_mc_emit_push(vol._h, arr, 2, off, cap) == 3  # the count was consumed: BS_ERR_INVALID
+        ctx.check(L.bs_mesh_mc_count(vol._h, vs, C.byref(nv)))
+        assert L.bs_mesh_mc_emit_push(vol._h, arr, 2, off, ref.size) == 3  # destination too small
+    finally:
+        for p in ptrs:
+            L.bs_ipc_free(ctx._h, C.c_void_p(p))
+
+
+def test_pipelined_remesh_with_empty_slabs(bs):
+    # 12 triangles cut into 8 slabs: most slabs own nothing
+    tris = synth.cube((0.1, -0.2, 0.3), 1.0, 0.8, 0.6)
+    vs = 0.05
+    ref = bs.MarchingCubesMesher().with_voxel_size(vs).mesh(bs.MeshToVolume().with_voxel_size(vs).convert(tris))
+    got = bs.VoxelRemesher().with_voxel_size(vs).remesh(tris, 8)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
