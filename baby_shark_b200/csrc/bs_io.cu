@@ -307,7 +307,6 @@ bs_status bs_active_voxels_impl(const bs_volume* v, int** d_verts, size_t* n_ver
     *d_verts = nullptr; *n_verts = 0;
     const size_t n = v->n_bricks, nt8 = v->n_tiles8, nt128 = v->n_tiles128, n_items = n + nt8 + nt128;
     if (n_items == 0) return BS_OK;
-    if (nt128 > 64) return bs_fail(ctx, BS_ERR_UNSUPPORTED, "ActiveVoxelsMesher: %zu active 128^3 tiles (98 304 boundary probes each)", nt128);
     bs_marks_begin(ctx);
     const AvTiles Tl{v->tile8_keys, nt8, v->tile128_keys, nt128};
     unsigned *d_cnt = nullptr, *d_pos = nullptr; u64 *d_wide = nullptr, *d_off = nullptr; void* d_tmp = nullptr; size_t tmp = 0;

@@ -771,6 +771,12 @@ def main():
             by = nb * (2112 + 868) + 36.0 * (n_verts_local / 3.0) * (world if (world > 1 and args.gather == "fused") else 1)
             rl.append({"kernel": "k_mc_emit (stage + classify + MC33 + vertices, staged coalesced stores%s)" % (" into every rank's buffer" if (world > 1 and args.gather == "fused") else ""), "bound": "hbm", "achieved": by / (mc_ms["mc_emit_ms"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                        "ms": mc_ms["mc_emit_ms"], "algorithmic": "n_bricks x 2980 B + 36 B x n_out_tris" + (" x world" if (world > 1 and args.gather == "fused") else ""), "traffic": None, "peak_source": hbm_src})
+        if world > 1 and args.gather == "fused" and "mc_emit_ms" in mc_ms:
+            # the fused compute + exchange kernel: bytes that must cross NVLink / the measured peer-copy rate of this pool (B200_PROFILING.md)
+            by = 36.0 * (n_verts_local / 3.0) * (world - 1)
+            rl.append({"kernel": "k_mc_emit as the output exchange (every triangle stored into the %d other ranks' buffers while it is computed)" % (world - 1), "bound": "nvlink",
+                       "achieved": by / (mc_ms["mc_emit_ms"] * 1e-3) / 1e9, "peak": 770.0, "unit": "GB/s", "ms": mc_ms["mc_emit_ms"], "traffic": None, "peak_source": "measured peer copy, per direction per GPU (B200_PROFILING.md)",
+                       "algorithmic": "36 B x n_out_tris of this rank x (world - 1) outbound"})
         # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum): read from the committed ncu capture of this exact
         # workload (profiles/r2_ncu_traffic_cfg5.json, written by tools/ncu_traffic.py from an `ncu --set full` report)
         if args.config == 5 and args.scale == 1.0 and world == 1:

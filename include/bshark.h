@@ -148,8 +148,8 @@ bs_status bs_stl_encode_device(bs_context* ctx, const float* d_verts, size_t n_v
                                size_t* n_bytes);
 /* ActiveVoxelsMesher::mesh (src/voxel/meshing/active_voxels.rs:12-22): two triangles per exposed voxel face, integer
  * vertices (the reference returns Vector3<isize>), 3 consecutive xyz per triangle, in the reference's order.
- * Active tiles contribute their boundary voxels (duplicates included, :128-151); more than 64 active 128^3 tiles is
- * BS_ERR_UNSUPPORTED. Host result: bs_buffer_free; device result: bs_device_free. */
+ * Active tiles contribute their boundary voxels (duplicates included, :128-151). Host result: bs_buffer_free; device
+ * result: bs_device_free. */
 bs_status bs_mesh_active_voxels(const bs_volume* v, int32_t** verts, size_t* n_verts);
 bs_status bs_mesh_active_voxels_device(const bs_volume* v, int32_t** d_verts, size_t* n_verts);
 /* merge_points (src/algo/merge_points.rs:12-41): exactly coincident points share an index; unique points keep
