@@ -612,12 +612,13 @@ bs_status bs_voxel_remesh_into(bs_context* ctx, const float* tris, size_t n_tris
     ctx->mc_chain = K > 1 && method == 0;
     bs_convert_plan plan;
     std::vector<bs_stat> acc;
-    size_t off = 0; int n_copies = 0; bs_status s = BS_OK;
+    size_t off = 0; int n_copies = 0; bs_status s = BS_OK; bool any_bricks = false;
     const size_t CHUNK = (size_t)8 << 20;  // floats per copy: small control read-backs of the running slab slip in between
     for (int k = 0; k < K && s == BS_OK; ++k) {
         bs_volume* v = nullptr;
         s = bs_convert_impl(ctx, d, n_tris, voxel_size, 0, k, K, &v, &plan);
         if (s != BS_OK) break;
+        any_bricks = any_bricks || v->n_bricks != 0;
         remesh_accumulate(acc, ctx->stats);
         // the buffer this extraction writes was the source of copy k - 2
         if (n_copies >= 2) cudaStreamWaitEvent(st, ctx->ev_copied[k & 1], 0);
@@ -645,6 +646,7 @@ bs_status bs_voxel_remesh_into(bs_context* ctx, const float* tris, size_t n_tris
     ctx->mc_chain = false;
     bs_free(ctx, d);
     if (s != BS_OK) return s;
+    if (!any_bricks) return BS_ERR_EMPTY_MESH;  // nothing of the mesh produced a voxel in any slab: convert -> None (mesh_to_volume.rs:58-60)
     ctx->stats = acc;
     bs_stat_add(ctx, "remesh_slabs", (double)K);
     *n_floats = off;

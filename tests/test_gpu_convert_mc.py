@@ -304,3 +304,7 @@ def test_pipelined_remesh_with_empty_slabs(bs):
     ref = bs.MarchingCubesMesher().with_voxel_size(vs).mesh(bs.MeshToVolume().with_voxel_size(vs).convert(tris))
     got = bs.VoxelRemesher().with_voxel_size(vs).remesh(tris, 8)
     assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    # a mesh that produces no voxel at all is None, however many slabs it is cut into (mesh_to_volume.rs:58-60)
+    nan = np.full((5, 9), np.nan, np.float32)
+    assert bs.VoxelRemesher().with_voxel_size(vs).remesh(nan, 1) is None
+    assert bs.VoxelRemesher().with_voxel_size(vs).remesh(nan, 4) is None
