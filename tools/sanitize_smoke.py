@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Every device entry point once on tiny inputs, meant to run under `compute-sanitizer --tool memcheck` (no oracle, no
 timing): convert (plain, sharded, heavy-split forced), MC, DC, indexed MC, STL codec, ActiveVoxelsMesher, merge_points,
-builders, CSG incl. active tiles, offset."""
+builders, CSG incl. active tiles, offset, the pipelined remesh, the two-step extraction, an open mesh."""
 import ctypes as C
 import os
 import sys
@@ -41,4 +41,18 @@ s = b.cuboid((0, 0, 0), (1, 1, 1)).subtract(b.sphere(0.4, (0.9, 0.9, 0.9)))
 i = b.iwp((0, 0, 0), (1, 1, 1), 0.5).intersect(b.sphere(0.5, (0.5, 0.5, 0.5)))
 o1 = bs.MeshToVolume().with_voxel_size(0.1).convert(synth.cube()).offset(0.25)
 o2 = bs.MeshToVolume().with_voxel_size(0.1).convert(synth.cube()).offset(-0.15)
+# round 2: the one-call pipelined remesh (slabs, second stream, c-vertex carry), the two-step extraction into two destinations,
+# the per-voxel sign path of an open mesh
+rm = bs.VoxelRemesher().with_voxel_size(vs)
+assert np.array_equal(rm.remesh(tris, 3), mc)
+assert np.array_equal(rm.with_meshing_method(bs.MeshingMethod.FeaturePreserving).remesh(tris, 2), dc)
+nv = C.c_size_t()
+ctx.check(L.bs_mesh_mc_count(vol._h, vs, C.byref(nv)))
+bufs = [torch.empty(nv.value * 3 + 64, dtype=torch.float32, device="cuda") for _ in range(2)]
+ctx.check(L.bs_mesh_mc_emit_push(vol._h, (C.c_void_p * 2)(*[t.data_ptr() for t in bufs]), 2, 32, nv.value * 3 + 64))
+torch.cuda.synchronize()
+assert all(np.array_equal(t[32:32 + nv.value * 3].cpu().numpy().reshape(-1, 3), mc) for t in bufs)
+cz = tris.reshape(-1, 3, 3)[:, :, 2].mean(1)
+open_vol = bs.MeshToVolume().with_voxel_size(vs).convert(np.ascontiguousarray(tris[cz < np.median(cz)]))
+assert ctx.last_stats()["sign_propagation"] == 0.0
 print("sanitize smoke ok", mc.shape, dc.shape, idx.points.shape, boxes.shape, mu.shape, s.counts(), i.counts(), o1.counts(), o2.counts())
