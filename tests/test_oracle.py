@@ -207,3 +207,89 @@ def test_mc33_random_field_is_almost_a_closed_cycle(oracle):
     assert f.shape[0] == 17268 and key.size == 24866
     assert int((balance != 0).sum()) == 48  # 0.19 %
     assert (uses == 2).mean() > 0.99 and (uses <= 4).all()
+
+
+# ---- analytic pins: stages the reference has no tests for are checked against closed-form answers, so the restatement is not
+# ---- only compared with itself ----------------------------------------------------------------------------------------------
+def test_closest_point_distance_against_dense_sampling(oracle):
+    # triangle3.rs:317-382 (Ericson's regions): the distance must equal the minimum over a dense barycentric sampling of the
+    # triangle, up to the sampling resolution, for points in every Voronoi region (vertices, edges, face)
+    rng = np.random.default_rng(3)
+    g = np.linspace(0.0, 1.0, 161)
+    u, v = np.meshgrid(g, g, indexing="ij")
+    keep = u + v <= 1.0
+    u, v = u[keep], v[keep]
+    for _ in range(40):
+        t = rng.uniform(-1, 1, 9).astype(np.float32)
+        a, b, c = t[0:3].astype(np.float64), t[3:6].astype(np.float64), t[6:9].astype(np.float64)
+        pts = rng.uniform(-2, 2, (64, 3)).astype(np.float32)
+        d = oracle.point_triangle_distance(t, pts)
+        samples = a[None, :] + u[:, None] * (b - a)[None, :] + v[:, None] * (c - a)[None, :]
+        brute = np.sqrt(((pts[:, None, :].astype(np.float64) - samples[None, :, :]) ** 2).sum(-1)).min(1)
+        h = max(np.linalg.norm(b - a), np.linalg.norm(c - a), np.linalg.norm(c - b)) / 160.0
+        assert (d <= brute + 1e-5).all() and (d >= brute - h).all(), float(np.abs(d - brute).max())
+
+
+def test_winding_numbers_of_a_closed_sphere(oracle):
+    # aabb_tree.rs:582-691: exact solid angles sum to 1 inside and 0 outside a closed, outward-oriented mesh; the beta = 2
+    # dipole approximation stays within 0.08 (0.064 measured here) -- far from the 0.2 threshold
+    from baby_shark_b200 import synth
+    tris = synth.uv_sphere(48, 24, 1.0, (0.1, -0.2, 0.3))
+    rng = np.random.default_rng(5)
+    dirs = rng.normal(size=(400, 3)); dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    centre = np.array([0.1, -0.2, 0.3])
+    inside = (centre + dirs * rng.uniform(0.0, 0.93, (400, 1))).astype(np.float32)
+    outside = (centre + dirs * rng.uniform(1.07, 3.0, (400, 1))).astype(np.float32)
+    for beta, tol in ((-1.0, 2e-4), (2.0, 0.08)):
+        wi, _ = oracle.winding_numbers(tris, inside, beta=beta)
+        wo, _ = oracle.winding_numbers(tris, outside, beta=beta)
+        assert np.abs(wi - 1.0).max() < tol and np.abs(wo).max() < tol, (beta, float(np.abs(wi - 1).max()), float(np.abs(wo).max()))
+
+
+def test_sphere_sdf_values_and_extractions_lie_on_the_sphere(oracle):
+    # mesh -> SDF -> MC / DC of a finely tessellated sphere: |SDF| is the distance to the (inscribed) polyhedron, so it must
+    # agree with | |p - c| - R | up to the sagitta of the tessellation; signs are inside / outside; MC and DC vertices lie on
+    # the sphere up to the sagitta plus the interpolation error of a voxel
+    from baby_shark_b200 import synth
+    from util import active_mask_bits
+    R, c, vs = 0.4, np.array([0.53, 0.54, 0.55]), 1.0 / 48
+    tris = synth.uv_sphere(96, 48, R, c)
+    vol, _ = oracle.mesh_to_volume(tris, vs)
+    d = vol.download()
+    m = active_mask_bits(d["masks"])
+    idx = np.argwhere(m)
+    p = (d["origins"][idx[:, 0]] + np.stack([idx[:, 1] >> 6, (idx[:, 1] >> 3) & 7, idx[:, 1] & 7], 1)).astype(np.float64) * vs
+    r = np.linalg.norm(p - c, axis=1)
+    val = d["values"][m].astype(np.float64)
+    sag = R * (1.0 - np.cos(np.pi / 48))  # the polyhedron lies at most this far inside the sphere
+    # the stored value is the distance to the nearest sub-triangle whose box contains the voxel: never below the true distance
+    assert (np.abs(val) >= np.abs(r - R) - sag - 1e-6).all() and (np.abs(val) <= np.abs(r - R) + sag + 1.8 * vs).all()
+    far = np.abs(r - R) > sag + 1e-4
+    assert ((val < 0) == (r < R))[far].all()
+    for verts in (oracle.marching_cubes(vol), oracle.dual_contouring(vol)):
+        assert verts is not None and verts.shape[0] > 1000
+        rv = np.linalg.norm(verts.astype(np.float64) - c, axis=1)
+        assert np.abs(rv - R).max() < sag + 0.35 * vs, float(np.abs(rv - R).max() / vs)
+
+
+def test_csg_of_two_spheres_is_min_max_of_the_analytic_fields(oracle):
+    # leaf_node/csg.rs:17-45 on top of the flood fill: wherever the result holds a finite value it is min(a, b) (union),
+    # max(a, -b) (subtract), max(a, b) (intersect) of the two builder fields |p - c| - R (volume/builder.rs:21-34), bit for bit
+    from util import active_mask_bits
+    vs = 1.0 / 32
+    ca, ra, cb, rb = np.array([0.40, 0.50, 0.50], np.float32), np.float32(0.30), np.array([0.62, 0.55, 0.47], np.float32), np.float32(0.25)
+    for name, f in (("union", lambda a, b: np.minimum(a, b)), ("subtract", lambda a, b: np.maximum(a, -b)), ("intersect", lambda a, b: np.maximum(a, b))):
+        A, B = oracle.sphere(vs, float(ra), ca), oracle.sphere(vs, float(rb), cb)
+        d = getattr(A, name)(B).download()
+        m = active_mask_bits(d["masks"])
+        idx = np.argwhere(m)
+        p = (d["origins"][idx[:, 0]] + np.stack([idx[:, 1] >> 6, (idx[:, 1] >> 3) & 7, idx[:, 1] & 7], 1)).astype(np.float32) * np.float32(vs)
+        sa = np.sqrt(((p - ca) ** 2).sum(1, dtype=np.float32)) - ra
+        sb = np.sqrt(((p - cb) ** 2).sum(1, dtype=np.float32)) - rb
+        val = d["values"][m]
+        finite = np.abs(val) < 1e30
+        assert finite.sum() > 2000
+        # both operands active there, or the other one far on the side that leaves the value alone: the analytic combination
+        both = finite & (np.abs(sa) <= 2 * vs) & (np.abs(sb) <= 2 * vs)
+        assert both.sum() > 100 and np.abs(val[both] - f(sa, sb)[both]).max() < 2e-6, (name, float(np.abs(val[both] - f(sa, sb)[both]).max()))
+        assert np.abs(val[finite] - f(sa, sb)[finite]).max() < 2e-6, name
