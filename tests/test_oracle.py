@@ -293,3 +293,23 @@ def test_csg_of_two_spheres_is_min_max_of_the_analytic_fields(oracle):
         both = finite & (np.abs(sa) <= 2 * vs) & (np.abs(sb) <= 2 * vs)
         assert both.sum() > 100 and np.abs(val[both] - f(sa, sb)[both]).max() < 2e-6, (name, float(np.abs(val[both] - f(sa, sb)[both]).max()))
         assert np.abs(val[finite] - f(sa, sb)[finite]).max() < 2e-6, name
+
+
+def test_offset_of_a_sphere_is_the_larger_sphere(oracle):
+    # Volume::offset (volume/mod.rs:95-108) = prune, fast-sweep extension (fast_sweep.rs), shift: the zero level set of the
+    # result is the sphere of radius R + d, and near it the values follow |p - c| - (R + d) up to the first-order error of the
+    # Godunov scheme
+    from util import active_mask_bits
+    vs, R, c = 1.0 / 32, 0.30, np.array([0.5, 0.5, 0.5], np.float32)
+    for dist in (3 * vs, -2.5 * vs):
+        d = oracle.sphere(vs, R, c).offset(float(dist)).download()
+        m = active_mask_bits(d["masks"])
+        idx = np.argwhere(m)
+        p = (d["origins"][idx[:, 0]] + np.stack([idx[:, 1] >> 6, (idx[:, 1] >> 3) & 7, idx[:, 1] & 7], 1)).astype(np.float64) * vs
+        exact = np.linalg.norm(p - c, axis=1) - (R + dist)
+        val = d["values"][m].astype(np.float64)
+        near = np.abs(exact) < 1.5 * vs
+        assert near.sum() > 1000 and np.abs(val - exact)[near].max() < 0.3 * vs, float(np.abs(val - exact)[near].max() / vs)
+        assert ((val < 0) == (exact < 0))[np.abs(exact) > 0.3 * vs].all()
+        rv = np.linalg.norm(oracle.marching_cubes(oracle.sphere(vs, R, c).offset(float(dist))).astype(np.float64) - c, axis=1)
+        assert np.abs(rv - (R + dist)).max() < 0.3 * vs
